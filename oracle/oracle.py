@@ -1,0 +1,131 @@
+"""oracle.py — CPU ORACLE driver (test infrastructure, NOT product code).
+
+Python front end for the scalar C++ oracle: builds a group with oso2cpp,
+loads the shared object with ctypes and runs it over SoA globals.  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs import this module.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import oso2cpp
+
+SG_FIELDS = ["P", "dPdx", "dPdy", "dPdz", "I", "dIdx", "dIdy", "N", "Ng", "u", "dudx",
+             "dudy", "v", "dvdx", "dvdy", "dPdu", "dPdv", "time", "dtime", "dPdtime",
+             "Ps", "dPsdx", "dPsdy", "surfacearea", "raytype", "flipHandedness",
+             "backfacing"]
+SG_VEC = {"P", "dPdx", "dPdy", "dPdz", "I", "dIdx", "dIdy", "N", "Ng", "dPdu", "dPdv",
+          "dPdtime", "Ps", "dPsdx", "dPsdy"}
+SG_INT = {"raytype", "flipHandedness", "backfacing"}
+NF = len(SG_FIELDS)
+
+
+class Launch(ctypes.Structure):
+    _fields_ = [("varying", ctypes.c_void_p * NF),
+                ("uniform", (ctypes.c_float * 4) * NF),
+                ("plane_stride", ctypes.c_longlong),
+                ("shadeindex", ctypes.c_void_p),
+                ("output_base", ctypes.c_void_p),
+                ("userdata_base", ctypes.c_void_p)]
+
+
+def testshade_globals(xres, yres, center=False, vary_udxdy=False, vary_vdxdy=False,
+                      vary_pdxdy=False, uscale=1.0, vscale=1.0, uoffset=0.0, voffset=0.0,
+                      raytype=1):
+    """Restates testshade's setup_shaderglobals (src/testshade/testshade.cpp:957-1046)
+    for the whole grid at once; returns (varying dict of float32 arrays,
+    uniform dict).  shadeindex = y*xres + x."""
+    f32 = np.float32
+    x = np.tile(np.arange(xres, dtype=f32), yres)
+    y = np.repeat(np.arange(yres, dtype=f32), xres)
+    us, vs, uo, vo = f32(uscale), f32(vscale), f32(uoffset), f32(voffset)
+    var, uni = {}, {}
+    if center:
+        u = us * ((x + f32(0.5)) / f32(xres)) + uo
+        v = vs * ((y + f32(0.5)) / f32(yres)) + vo
+        dudx, dvdy = us / f32(xres), vs / f32(yres)
+    else:
+        u = us * (np.full_like(x, 0.5) if xres == 1 else x / f32(xres - 1)) + uo
+        v = vs * (np.full_like(y, 0.5) if yres == 1 else y / f32(yres - 1)) + vo
+        dudx, dvdy = us / f32(max(1, xres - 1)), vs / f32(max(1, yres - 1))
+    u = u.astype(f32)
+    v = v.astype(f32)
+    var["u"], var["v"] = u, v
+    if vary_udxdy:
+        var["dudx"], var["dudy"] = (f32(1) - u).astype(f32), u.copy()
+    else:
+        uni["dudx"] = [float(dudx)]
+    if vary_vdxdy:
+        var["dvdx"], var["dvdy"] = (f32(1) - v).astype(f32), v.copy()
+    else:
+        uni["dvdy"] = [float(dvdy)]
+    var["P"] = np.stack([u, v, np.ones_like(u)]).astype(f32)
+    if vary_pdxdy:
+        var["dPdx"] = np.stack([f32(1) - u, f32(1) - v, (u.astype(np.float64) * 0.5).astype(f32)]).astype(f32)
+        var["dPdy"] = np.stack([f32(1) - v, f32(1) - u, (v.astype(np.float64) * 0.5).astype(f32)]).astype(f32)
+    else:
+        uni["dPdx"] = [float(us / f32(max(1, xres - 1))), 0.0, 0.0]
+        uni["dPdy"] = [0.0, float(vs / f32(max(1, yres - 1))), 0.0]
+    uni["dPdu"] = [1.0, 0.0, 0.0]
+    uni["dPdv"] = [0.0, 1.0, 0.0]
+    uni["N"] = [0.0, 0.0, 1.0]
+    uni["Ng"] = [0.0, 0.0, 1.0]
+    uni["surfacearea"] = [1.0]
+    uni["raytype"] = [raytype]
+    return var, uni
+
+
+def make_launch(n, varying, uniform, output, shadeindex=None, keep=None):
+    """Fill a Launch from numpy arrays; `keep` collects references."""
+    L = Launch()
+    keep = keep if keep is not None else []
+    for i, f in enumerate(SG_FIELDS):
+        L.varying[i] = None
+        if f in varying:
+            a = np.ascontiguousarray(varying[f], dtype=np.int32 if f in SG_INT else np.float32)
+            assert a.size == n * (3 if f in SG_VEC else 1), (f, a.shape, n)
+            keep.append(a)
+            L.varying[i] = a.ctypes.data
+        vals = list(uniform.get(f, []))
+        for c in range(4):
+            if f in SG_INT:
+                iv = int(vals[0]) if vals else 0
+                L.uniform[i][c] = np.array([iv], dtype=np.int32).view(np.float32)[0] if c == 0 else 0.0
+            else:
+                L.uniform[i][c] = float(vals[c]) if c < len(vals) else 0.0
+    L.plane_stride = n
+    if shadeindex is not None:
+        si = np.ascontiguousarray(shadeindex, dtype=np.int32)
+        keep.append(si)
+        L.shadeindex = si.ctypes.data
+    else:
+        L.shadeindex = None
+    L.output_base = output.ctypes.data if output is not None else None
+    L.userdata_base = None
+    keep.append(output)
+    return L, keep
+
+
+class OracleGroup:
+    """layers: list of dict(oso=<text>, name=<layername>, params={...})"""
+
+    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=()):
+        ls = [oso2cpp.Layer(l["oso"], l["name"], l.get("params")) for l in layers]
+        self.group = oso2cpp.Group(ls, connections, outputs)
+        self.so = oso2cpp.build_group(self.group, opt=opt, extra_flags=flags)
+        self.lib = ctypes.CDLL(self.so)
+        self.lib.oracle_run_mt.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong, ctypes.c_int]
+        self.lib.oracle_run_capture.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong,
+                                                ctypes.c_longlong]
+        self.lib.oracle_run_capture.restype = ctypes.c_char_p
+
+    def run(self, n, varying, uniform, output, shadeindex=None, nthreads=1):
+        L, keep = make_launch(n, varying, uniform, output, shadeindex)
+        self.lib.oracle_run_mt(ctypes.byref(L), n, nthreads)
+        return output
+
+    def run_capture(self, n, varying, uniform, output=None, shadeindex=None):
+        L, keep = make_launch(n, varying, uniform, output, shadeindex)
+        return self.lib.oracle_run_capture(ctypes.byref(L), 0, n).decode()

@@ -1,0 +1,169 @@
+// osl_oracle_runtime.h — CPU ORACLE (test infrastructure, NOT product code).
+//
+// Per-point execution scaffolding for the C++ that oracle/oso2cpp.py emits:
+// the scalar ShaderGlobals record (reference: include/OSL/shaderglobals.h:55-146),
+// the SoA launch description (same field order as include/osl_b200.h so tests
+// feed both sides identical buffers), printf capture (reference journal /
+// rs_printfmt path), and the range runner that mirrors testshade's
+// one-execute-per-point loop (src/testshade/testshade.cpp:1585-1672).
+#pragma once
+#include "osl_oracle_ops.h"
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace oslo {
+
+// Field order is the contract shared with include/osl_b200.h (b200_sg_field).
+enum SGField {
+    SG_P = 0, SG_dPdx, SG_dPdy, SG_dPdz, SG_I, SG_dIdx, SG_dIdy, SG_N, SG_Ng,
+    SG_u, SG_dudx, SG_dudy, SG_v, SG_dvdx, SG_dvdy, SG_dPdu, SG_dPdv,
+    SG_time, SG_dtime, SG_dPdtime, SG_Ps, SG_dPsdx, SG_dPsdy,
+    SG_surfacearea, SG_raytype, SG_flipHandedness, SG_backfacing,
+    SG_NFIELDS
+};
+
+struct Launch {
+    const float* varying[SG_NFIELDS];  // SoA planes (x[n],y[n],z[n]) or NULL
+    float uniform[SG_NFIELDS][4];      // used when varying[f] == NULL
+    long long plane_stride;            // elements between x/y/z planes
+    const int* shadeindex;             // NULL => iota
+    void* output_base;                 // renderer output arena
+    const void* userdata_base;
+};
+
+struct Ctx {
+    std::string* out;  // printf capture (NULL: discard)
+};
+
+struct SG {
+    Dv P;
+    V3 dPdz;
+    Dv I;
+    V3 N, Ng;
+    Df u, v;
+    V3 dPdu, dPdv;
+    float time, dtime;
+    V3 dPdtime;
+    Dv Ps;
+    float surfacearea;
+    int raytype, flipHandedness, backfacing;
+    int shadeindex;
+    Ctx* ctx;
+};
+
+inline float ldf(const Launch* L, int f, int c, long long i)
+{
+    return L->varying[f] ? L->varying[f][c * L->plane_stride + i] : L->uniform[f][c];
+}
+inline V3 ldv(const Launch* L, int f, long long i)
+{
+    return V3(ldf(L, f, 0, i), ldf(L, f, 1, i), ldf(L, f, 2, i));
+}
+inline int ldi(const Launch* L, int f, long long i)
+{
+    return L->varying[f] ? ((const int*)L->varying[f])[i] : (int)f2u(L->uniform[f][0]);
+}
+
+// Build the per-point globals record (what testshade's setup_shaderglobals +
+// the renderer would have put in ShaderGlobals).
+inline void load_sg(SG& sg, const Launch* L, long long i, Ctx* ctx)
+{
+    sg.P       = Dv(ldv(L, SG_P, i), ldv(L, SG_dPdx, i), ldv(L, SG_dPdy, i));
+    sg.dPdz    = ldv(L, SG_dPdz, i);
+    sg.I       = Dv(ldv(L, SG_I, i), ldv(L, SG_dIdx, i), ldv(L, SG_dIdy, i));
+    sg.N       = ldv(L, SG_N, i);
+    sg.Ng      = ldv(L, SG_Ng, i);
+    sg.u       = Df(ldf(L, SG_u, 0, i), ldf(L, SG_dudx, 0, i), ldf(L, SG_dudy, 0, i));
+    sg.v       = Df(ldf(L, SG_v, 0, i), ldf(L, SG_dvdx, 0, i), ldf(L, SG_dvdy, 0, i));
+    sg.dPdu    = ldv(L, SG_dPdu, i);
+    sg.dPdv    = ldv(L, SG_dPdv, i);
+    sg.time    = ldf(L, SG_time, 0, i);
+    sg.dtime   = ldf(L, SG_dtime, 0, i);
+    sg.dPdtime = ldv(L, SG_dPdtime, i);
+    sg.Ps      = Dv(ldv(L, SG_Ps, i), ldv(L, SG_dPsdx, i), ldv(L, SG_dPsdy, i));
+    sg.surfacearea    = ldf(L, SG_surfacearea, 0, i);
+    sg.raytype        = ldi(L, SG_raytype, i);
+    sg.flipHandedness = ldi(L, SG_flipHandedness, i);
+    sg.backfacing     = ldi(L, SG_backfacing, i);
+    sg.shadeindex     = L->shadeindex ? L->shadeindex[i] : (int)i;
+    sg.ctx            = ctx;
+}
+
+// ---------------------------------------------------------------------------
+// printf capture.  The generator splits the format at gen time and calls one
+// helper per conversion, so no varargs cross the boundary.
+// ---------------------------------------------------------------------------
+inline void pf_lit(SG& sg, const char* s)
+{
+    if (sg.ctx && sg.ctx->out)
+        sg.ctx->out->append(s);
+}
+inline void pf_fmt(SG& sg, const char* spec, double v)
+{
+    if (!(sg.ctx && sg.ctx->out))
+        return;
+    char buf[128];
+    snprintf(buf, sizeof buf, spec, v);
+    sg.ctx->out->append(buf);
+}
+inline void pf_fmt(SG& sg, const char* spec, int v)
+{
+    if (!(sg.ctx && sg.ctx->out))
+        return;
+    char buf[128];
+    snprintf(buf, sizeof buf, spec, v);
+    sg.ctx->out->append(buf);
+}
+inline void pf_fmt(SG& sg, const char* spec, const char* v)
+{
+    if (!(sg.ctx && sg.ctx->out))
+        return;
+    char buf[1024];
+    snprintf(buf, sizeof buf, spec, v ? v : "");
+    sg.ctx->out->append(buf);
+}
+inline void pf_f(SG& sg, const char* spec, float v) { pf_fmt(sg, spec, (double)v); }
+inline void pf_f(SG& sg, const char* spec, const Df& v) { pf_fmt(sg, spec, (double)v.val); }
+inline void pf_f(SG& sg, const char* spec, int v) { pf_fmt(sg, spec, (double)v); }
+inline void pf_i(SG& sg, const char* spec, int v) { pf_fmt(sg, spec, v); }
+inline void pf_i(SG& sg, const char* spec, float v) { pf_fmt(sg, spec, (int)v); }
+inline void pf_v(SG& sg, const char* spec, const V3& v)
+{
+    pf_fmt(sg, spec, (double)v.x);
+    pf_lit(sg, " ");
+    pf_fmt(sg, spec, (double)v.y);
+    pf_lit(sg, " ");
+    pf_fmt(sg, spec, (double)v.z);
+}
+inline void pf_v(SG& sg, const char* spec, const Dv& v) { pf_v(sg, spec, v.val); }
+inline void pf_s(SG& sg, const char* spec, const char* v) { pf_fmt(sg, spec, v); }
+
+inline bool str_eq(const char* a, const char* b)
+{
+    if (a == b)
+        return true;
+    if (!a || !b)
+        return false;
+    return std::strcmp(a, b) == 0;
+}
+
+// output placement: output_base + offset + stride*shadeindex
+// (llvm_instance.cpp:1807-1848)
+inline float* outp(const Launch* L, const SG& sg, long long offset, long long stride)
+{
+    return (float*)((char*)L->output_base + offset + stride * (long long)sg.shadeindex);
+}
+inline void wr(float* p, float v) { p[0] = v; }
+inline void wr(float* p, int v) { ((int*)p)[0] = v; }
+inline void wr(float* p, const V3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+inline void wr(float* p, const Df& v) { p[0] = v.val; }
+inline void wr(float* p, const Dv& v) { wr(p, v.val); }
+inline void wrd(float* p, float v) { p[0] = v; p[1] = 0; p[2] = 0; }
+inline void wrd(float* p, const Df& v) { p[0] = v.val; p[1] = v.dx; p[2] = v.dy; }
+inline void wrd(float* p, const V3& v) { wr(p, v); for (int i = 3; i < 9; ++i) p[i] = 0; }
+inline void wrd(float* p, const Dv& v) { wr(p, v.val); wr(p + 3, v.dx); wr(p + 6, v.dy); }
+
+}  // namespace oslo

@@ -1,0 +1,1051 @@
+"""oso2cpp — CPU ORACLE (test infrastructure, NOT product code).
+
+Turns a shader group (parsed .oso layers + instance params + connections +
+renderer outputs) into plain scalar C++ that is compiled with
+`g++ -O2 -ffp-contract=off` and run one shading point at a time, the way the
+reference's scalar LLVM back end does.  The product's generator (C++ ->
+CUDA text, openshadinglanguage_b200/csrc/host) is a separate implementation;
+nothing under openshadinglanguage_b200/ imports this module.
+
+What it restates (paths relative to /root/reference):
+  * .oso grammar                      src/liboslexec/osogram.y:88-318, osolex.l
+  * group assembly / connections      src/liboslexec/shadingsys.cpp:3039-3300
+  * derivative propagation            src/liboslexec/runtimeoptimize.cpp:2542-2720, 3223-3231
+  * lazy layers / run_lazily rules    src/liboslexec/oslexec_pvt.h:1344-1372,
+                                      src/liboslexec/llvm_gen.cpp:133-283
+  * layer function structure          src/liboslexec/llvm_instance.cpp:1548-1870
+  * per-op semantics                  src/liboslexec/llvm_gen.cpp (cited per emitter)
+"""
+import hashlib
+import os
+import re
+import struct
+import subprocess
+
+TRIPLES = ("color", "point", "vector", "normal")
+
+
+class OType:
+    __slots__ = ("base", "arr")
+
+    def __init__(self, base, arr=0):
+        self.base, self.arr = base, arr
+
+    @property
+    def triple(self):
+        return self.base in TRIPLES
+
+    @property
+    def floatbased(self):
+        return self.base in ("float", "matrix") + TRIPLES
+
+    @property
+    def ncomp(self):
+        return 3 if self.triple else (16 if self.base == "matrix" else 1)
+
+    def __repr__(self):
+        return self.base + ("[%d]" % self.arr if self.arr else "")
+
+
+class OSym:
+    def __init__(self, name, symtype, t, vals):
+        self.name, self.symtype, self.t, self.vals = name, symtype, t, vals
+        self.has_derivs = False
+        self.initexpr = False
+        self.connected_from = None   # (layer index, sym) feeding this param
+        self.connected_down = False
+        self.renderer_output = None  # dict(offset, stride, derivs) when placed
+        self.override = None
+        self.written = False
+
+    @property
+    def isconst(self):
+        return self.symtype == "const"
+
+
+class OOp:
+    __slots__ = ("name", "args", "jumps", "rw", "derivs", "method")
+
+    def __init__(self, name, args, jumps, rw, derivs, method):
+        self.name, self.args, self.jumps, self.rw = name, args, jumps, rw
+        self.derivs, self.method = derivs, method
+
+
+TOK = re.compile(r'"(?:\\.|[^"\\])*"|%\w+\{[^}]*\}|%\w+|\S+')
+
+
+def _unescape(s):
+    return (s.replace("\\n", "\n").replace("\\t", "\t").replace('\\"', '"')
+            .replace("\\\\", "\\"))
+
+
+class Master:
+    def __init__(self):
+        self.shadertype = self.name = None
+        self.syms = []
+        self.byname = {}
+        self.ops = []
+        self.methods = {}   # name -> (begin, end)
+
+
+def parse_oso(text):
+    m = Master()
+    lines = text.split("\n")
+    if not lines[0].startswith("OpenShadingLanguage"):
+        raise ValueError("not an OSO file")
+    method = None
+    begin = 0
+    for ln in lines[1:]:
+        if not ln.strip() or ln.lstrip().startswith("#"):
+            continue
+        if ln.startswith("%preprocessed_source"):
+            break
+        toks = TOK.findall(ln)
+        if m.name is None:
+            m.shadertype, m.name = toks[0], toks[1]
+            continue
+        if toks[0] == "code":
+            if method is not None:
+                m.methods[method] = (begin, len(m.ops))
+            method, begin = toks[1], len(m.ops)
+            continue
+        if method is None:
+            # symbol declaration
+            symtype = toks[0]
+            i = 1
+            if toks[i] == "closure":
+                base = "closure color"
+                i += 2
+            else:
+                base = toks[i]
+                i += 1
+            arr = 0
+            mm = re.match(r"(\w+)\[(\d*)\]$", base)
+            if mm:
+                base, arr = mm.group(1), int(mm.group(2) or -1)
+            name = toks[i]
+            mm = re.match(r"(.*)\[(\d*)\]$", name)
+            if mm:   # closure color x[3] style
+                name, arr = mm.group(1), int(mm.group(2) or -1)
+            i += 1
+            vals = []
+            hints = []
+            for t in toks[i:]:
+                if t.startswith("%"):
+                    hints.append(t)
+                elif t.startswith('"'):
+                    vals.append(_unescape(t[1:-1]))
+                elif base == "int":
+                    vals.append(int(t))
+                elif base == "string":
+                    vals.append(t)
+                else:
+                    vals.append(struct.unpack("f", struct.pack("f", float(t)))[0])
+            s = OSym(name, symtype, OType(base, arr), vals)
+            s.initexpr = "%initexpr" in hints
+            m.byname[name] = s
+            m.syms.append(s)
+            continue
+        # op line
+        name = toks[0]
+        if name == "end":
+            continue
+        args, jumps, rw, derivs = [], [], None, ()
+        for t in toks[1:]:
+            if t.startswith("%argrw"):
+                rw = t[t.index('"') + 1:t.rindex('"')]
+            elif t.startswith("%argderivs"):
+                derivs = tuple(int(x) for x in t[t.index("{") + 1:-1].split(",") if x)
+            elif t.startswith("%"):
+                pass
+            elif re.match(r"-?\d+$", t):
+                jumps.append(int(t))
+            else:
+                args.append(m.byname[t])
+        if rw is None:
+            rw = "w" + "r" * (len(args) - 1) if args else ""
+        m.ops.append(OOp(name, args, jumps, rw, derivs, method))
+    if method is not None:
+        m.methods[method] = (begin, len(m.ops))
+    return m
+
+
+# ----------------------------------------------------------------------------
+# group
+# ----------------------------------------------------------------------------
+class Layer:
+    def __init__(self, master_text, layername, params=None):
+        self.m = parse_oso(master_text)   # private copy per instance
+        self.name = layername
+        self.idx = -1
+        for k, v in (params or {}).items():
+            s = self.m.byname[k]
+            if not isinstance(v, (list, tuple)):
+                v = [v]
+            if s.t.base not in ("int", "string"):
+                v = [struct.unpack("f", struct.pack("f", float(x)))[0] for x in v]
+            s.vals = list(v)
+            s.initexpr = False
+            s.override = True
+        self.lazy = False
+        self.unused = False
+
+
+class Group:
+    """layers: list[Layer]; connections: (srclayer, srcparam, dstlayer, dstparam);
+    outputs: list of dict(name='layer.param' or 'param', offset, stride, derivs)."""
+
+    def __init__(self, layers, connections=(), outputs=(), name="group"):
+        self.layers = list(layers)
+        self.name = name
+        for i, l in enumerate(self.layers):
+            l.idx = i
+        byname = {l.name: l for l in self.layers}
+        self.connections = []
+        for (sl, sp, dl, dp) in connections:
+            s, d = byname[sl], byname[dl]
+            ssym, dsym = s.m.byname[sp], d.m.byname[dp]
+            dsym.connected_from = (s.idx, ssym)
+            ssym.connected_down = True
+            self.connections.append((s.idx, ssym, d.idx, dsym))
+        self.outputs = []
+        for o in outputs:
+            nm = o["name"]
+            if "." in nm:
+                ln, pn = nm.split(".", 1)
+                lay = byname[ln]
+            else:
+                pn = nm
+                lay = None
+                for l in reversed(self.layers):   # last layer that has it wins
+                    if pn in l.m.byname and l.m.byname[pn].symtype in ("param", "oparam"):
+                        lay = l
+                        break
+                if lay is None:
+                    raise KeyError("renderer output %s not found" % nm)
+            sym = lay.m.byname[pn]
+            sym.renderer_output = dict(offset=o["offset"], stride=o["stride"],
+                                       derivs=bool(o.get("derivs", False)))
+            self.outputs.append((lay.idx, sym))
+        self.analyze()
+
+    # -- analysis -----------------------------------------------------------
+    def analyze(self):
+        n = len(self.layers)
+        for l in self.layers:
+            for op in l.m.ops:
+                for a, c in zip(op.args, op.rw):
+                    if c in "wW":
+                        a.written = True
+        # unused(): not last, no downstream connection, no renderer output
+        # (llvm_instance.cpp:2306-2318)
+        for l in self.layers:
+            has_out = any(s.renderer_output for s in l.m.syms)
+            has_down = any(s.connected_down for s in l.m.syms)
+            l.unused = (l.idx != n - 1) and not has_out and not has_down
+            # run_lazily (oslexec_pvt.h:1344-1372, defaults lazylayers=1,
+            # lazyglobals=1, lazyunconnected=1, lazyerror=1)
+            l.lazy = (l.idx != n - 1) and not has_out
+        # derivative needs, last layer first so requirements flow upstream
+        for l in reversed(self.layers):
+            self.track_derivs(l)
+            for s in l.m.syms:
+                if s.connected_from and s.has_derivs:
+                    s.connected_from[1].has_derivs = True
+
+    DERIV_GLOBALS = ("P", "I", "u", "v", "Ps")
+
+    def track_derivs(self, l):
+        deps = {}
+        need = set()
+        for op in l.m.ops:
+            reads = [a for a, c in zip(op.args, op.rw) if c in "rW"]
+            writes = [a for a, c in zip(op.args, op.rw) if c in "wW"]
+            for w in writes:
+                for r in reads:
+                    if not r.isconst:
+                        deps.setdefault(w, set()).add(r)
+            for ai in op.derivs:
+                s = op.args[ai]
+                if s.isconst or not s.t.floatbased or s.t.base == "matrix":
+                    continue
+                if s.symtype == "global" and s.name not in self.DERIV_GLOBALS:
+                    continue
+                need.add(s)
+        for s in l.m.syms:
+            if s.symtype == "global" and s.written and s.t.floatbased and s.name != "N":
+                s.has_derivs = True
+            ro = s.renderer_output
+            if ro and ro["derivs"] and s.written and s.t.floatbased:
+                s.has_derivs = True
+            if s.has_derivs:
+                need.add(s)
+        seen = set()
+        stack = list(need)
+        while stack:
+            s = stack.pop()
+            if s in seen:
+                continue
+            seen.add(s)
+            if s.t.floatbased and s.t.base != "matrix" and not s.isconst:
+                s.has_derivs = True
+            for r in deps.get(s, ()):
+                stack.append(r)
+        for s in l.m.syms:
+            if s.symtype == "global" and s.name not in self.DERIV_GLOBALS:
+                s.has_derivs = False
+            if not s.t.floatbased or s.t.base == "matrix":
+                s.has_derivs = False
+
+
+# ----------------------------------------------------------------------------
+# code generation
+# ----------------------------------------------------------------------------
+def cfloat(f):
+    if f != f:
+        return "NAN"
+    if f in (float("inf"), float("-inf")):
+        return "INFINITY" if f > 0 else "(-INFINITY)"
+    s = "%.9g" % f
+    if "." not in s and "e" not in s and "n" not in s:
+        s += ".0"
+    return s + "f"
+
+
+def cstr(s):
+    return '"' + s.replace("\\", "\\\\").replace('"', '\\"').replace("\n", "\\n") \
+        .replace("\t", "\\t") + '"'
+
+
+UNARY = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "log2",
+         "log10", "exp", "exp2", "expm1", "erf", "erfc", "cbrt", "sqrt", "inversesqrt",
+         "abs", "fabs", "floor", "ceil", "round", "trunc", "sign", "logb", "neg"}
+BINARY = {"add", "sub", "mul", "atan2", "pow", "fmod", "step", "min", "max"}
+TERNARY = {"mix", "clamp", "smoothstep", "select"}
+CMP = {"eq": "==", "neq": "!=", "lt": "<", "gt": ">", "le": "<=", "ge": ">="}
+INTBIN = {"bitand": "&", "bitor": "|", "xor": "^", "shl": "<<", "shr": ">>"}
+NOISE_KIND = {"noise": "N_NOISE", "uperlin": "N_NOISE", "snoise": "N_SNOISE",
+              "perlin": "N_SNOISE", "cellnoise": "N_CELL", "cell": "N_CELL",
+              "hashnoise": "N_HASH", "hash": "N_HASH"}
+PNOISE_KIND = {"pnoise": "N_NOISE", "psnoise": "N_SNOISE", "pcellnoise": "N_CELL",
+               "phashnoise": "N_HASH", "noise": "N_NOISE", "uperlin": "N_NOISE",
+               "snoise": "N_SNOISE", "perlin": "N_SNOISE", "cell": "N_CELL",
+               "cellnoise": "N_CELL", "hash": "N_HASH", "hashnoise": "N_HASH"}
+SG_GLOBALS = {"P": "sg.P", "I": "sg.I", "N": "sg.N", "Ng": "sg.Ng", "u": "sg.u",
+              "v": "sg.v", "dPdu": "sg.dPdu", "dPdv": "sg.dPdv", "Ps": "sg.Ps",
+              "time": "sg.time", "dtime": "sg.dtime", "dPdtime": "sg.dPdtime"}
+
+
+class Gen:
+    def __init__(self, group):
+        self.g = group
+        self.out = []
+        self.ind = 1
+        self.label = 0
+
+    def w(self, s):
+        self.out.append("    " * self.ind + s)
+
+    def ident(self, name):
+        return re.sub(r"[^A-Za-z0-9_]", "_", name.replace("$", "S_"))
+
+    def ctype(self, s):
+        b = s.t.base
+        if b == "int":
+            return "int"
+        if b == "float":
+            return "Df" if s.has_derivs else "float"
+        if s.t.triple:
+            return "Dv" if s.has_derivs else "V3"
+        if b == "string":
+            return "const char*"
+        if b == "matrix":
+            return "M44"
+        if b == "closure color":
+            return "Clos*"
+        raise NotImplementedError("type %s" % s.t)
+
+    def ref(self, l, s):
+        """C++ lvalue/rvalue expression for symbol s inside layer l."""
+        if s.symtype == "const":
+            return self.constexpr(s)
+        if s.symtype in ("param", "oparam"):
+            return "gd.L%d_%s" % (l.idx, self.ident(s.name))
+        if s.symtype == "global":
+            if s.name not in SG_GLOBALS:
+                raise NotImplementedError("global %s" % s.name)
+            e = SG_GLOBALS[s.name]
+            # globals that carry derivs in SG but are used without them
+            if s.name in Group.DERIV_GLOBALS and not s.has_derivs:
+                return "%s.val" % e
+            return e
+        return self.ident(s.name)
+
+    def constexpr(self, s):
+        b = s.t.base
+        if s.t.arr:
+            return "K_" + self.ident(s.name)
+        if b == "int":
+            return str(s.vals[0])
+        if b == "float":
+            return cfloat(s.vals[0])
+        if s.t.triple:
+            return "V3(%s, %s, %s)" % tuple(cfloat(v) for v in s.vals[:3])
+        if b == "string":
+            return cstr(s.vals[0])
+        if b == "matrix":
+            return "M44{{%s}}" % ", ".join(cfloat(v) for v in s.vals)
+        raise NotImplementedError(b)
+
+    def initval(self, s):
+        """C++ initializer for a param/local from its default values."""
+        b = s.t.base
+        n = max(1, s.t.arr)
+        per = s.t.ncomp
+        vals = list(s.vals) + [0] * (n * per - len(s.vals)) if b != "string" else \
+            list(s.vals) + [""] * (n - len(s.vals))
+
+        def one(v):
+            if b == "int":
+                return str(int(v[0]))
+            if b == "float":
+                return ("Df(%s)" if s.has_derivs else "%s") % cfloat(v[0])
+            if s.t.triple:
+                e = "V3(%s, %s, %s)" % tuple(cfloat(x) for x in v)
+                return "Dv(%s)" % e if s.has_derivs else e
+            if b == "string":
+                return cstr(v[0])
+            if b == "matrix":
+                return "M44{{%s}}" % ", ".join(cfloat(x) for x in v)
+            if b == "closure color":
+                return "nullptr"
+            raise NotImplementedError(b)
+        return [one(vals[i * per:(i + 1) * per]) for i in range(n)]
+
+    # -- group --------------------------------------------------------------
+    def generate(self):
+        g = self.g
+        o = self.out
+        o.append("// generated by oracle/oso2cpp.py — CPU oracle, test infrastructure only")
+        o.append('#include "osl_oracle_runtime.h"')
+        o.append("using namespace oslo;")
+        o.append("namespace {")
+        o.append("struct GD {")
+        o.append("    bool ran[%d];" % max(1, len(g.layers)))
+        for l in g.layers:
+            if l.unused:
+                continue
+            for s in l.m.syms:
+                if s.symtype in ("param", "oparam"):
+                    arr = "[%d]" % s.t.arr if s.t.arr else ""
+                    o.append("    %s L%d_%s%s;" % (self.ctype(s), l.idx, self.ident(s.name), arr))
+        o.append("};")
+        used = [l for l in g.layers if not l.unused]
+        for l in used:
+            o.append("static void layer_%d(SG& sg, GD& gd, const Launch* L);" % l.idx)
+        for l in used:
+            self.gen_layer(l)
+        o.append("}  // namespace")
+        o.append('extern "C" void oracle_run(const Launch* L, long long begin, long long end, '
+                 'std::string* pf)')
+        o.append("{")
+        o.append("    Ctx ctx{pf};")
+        o.append("    for (long long i = begin; i < end; ++i) {")
+        o.append("        SG sg; GD gd;")
+        o.append("        load_sg(sg, L, i, &ctx);")
+        o.append("        for (int k = 0; k < %d; ++k) gd.ran[k] = false;" % max(1, len(g.layers)))
+        o.append("        layer_%d(sg, gd, L);" % (len(g.layers) - 1))
+        o.append("    }")
+        o.append("}")
+        o.append(RUNNER_TAIL)
+        return "\n".join(o) + "\n"
+
+    def gen_layer(self, l):
+        g = self.g
+        m = l.m
+        self.l = l
+        self.ind = 0
+        self.w("static void layer_%d(SG& sg, GD& gd, const Launch* L)" % l.idx)
+        self.w("{")
+        self.ind = 1
+        self.w("gd.ran[%d] = true;" % l.idx)
+        self.w("(void)L;")
+        # declare locals / temps
+        for s in m.syms:
+            if s.symtype in ("local", "temp"):
+                arr = "[%d]" % s.t.arr if s.t.arr else ""
+                init = " = {}" if s.t.arr else (" = nullptr" if s.t.base in ("string", "closure color")
+                                                else " = {}")
+                self.w("%s %s%s%s;" % (self.ctype(s), self.ident(s.name), arr, init))
+            elif s.symtype == "const" and s.t.arr:
+                vals = self.initval(s)
+                self.w("static const %s K_%s[%d] = {%s};" % (
+                    self.ctype(s), self.ident(s.name), s.t.arr, ", ".join(vals)))
+        # entry layer: run earlier non-lazy layers unconditionally
+        # (llvm_instance.cpp:1693-1720)
+        if l.idx == len(g.layers) - 1:
+            for e in g.layers[:-1]:
+                if not e.unused and not e.lazy:
+                    self.w("if (!gd.ran[%d]) layer_%d(sg, gd, L);" % (e.idx, e.idx))
+        # param initialisation (llvm_instance.cpp:1666-1690, 703-1000)
+        for s in m.syms:
+            if s.symtype not in ("param", "oparam"):
+                continue
+            if s.connected_from is not None:
+                continue   # value arrives from upstream (possibly lazily)
+            vals = self.initval(s)
+            r = self.ref(l, s)
+            if s.t.arr:
+                for i, v in enumerate(vals):
+                    self.w("%s[%d] = %s;" % (r, i, v))
+            else:
+                self.w("%s = %s;" % (r, vals[0]))
+            if s.initexpr and s.name in m.methods:
+                b, e = m.methods[s.name]
+                self.ensured = set()
+                self.emit_block(b, e, None)
+        self.ensured = set()
+        b, e = m.methods.get("___main___", (0, 0))
+        self.emit_block(b, e, None)
+        self.w("layer_end:;")
+        # copy outputs to downstream params (llvm_instance.cpp:1738-1802)
+        for (si, ssym, di, dsym) in g.connections:
+            if si != l.idx or g.layers[di].unused:
+                continue
+            self.emit_copy(g.layers[di], dsym, l, ssym)
+        # renderer outputs (llvm_instance.cpp:1807-1848)
+        for (li, s) in g.outputs:
+            if li != l.idx:
+                continue
+            ro = s.renderer_output
+            fn = "wrd" if ro["derivs"] else "wr"
+            self.w("%s(outp(L, sg, %d, %d), %s);" % (fn, ro["offset"], ro["stride"], self.ref(l, s)))
+        self.ind = 0
+        self.w("}")
+
+    def emit_copy(self, dl, dsym, sl, ssym):
+        d, s = self.ref(dl, dsym), self.ref(sl, ssym)
+        if dsym.t.arr:
+            for i in range(dsym.t.arr):
+                self.w("assign(%s[%d], %s[%d]);" % (d, i, s, i))
+        elif dsym.t.base in ("matrix", "closure color"):
+            self.w("%s = %s;" % (d, s))
+        else:
+            self.w("assign(%s, %s);" % (d, s))
+
+    # -- control flow -------------------------------------------------------
+    def emit_block(self, b, e, ctx):
+        """ctx = dict(ret=label or None, brk=label, cont=label)"""
+        ops = self.l.m.ops
+        i = b
+        while i < e:
+            op = ops[i]
+            n = op.name
+            if n == "if":
+                self.useparams(op)
+                self.w("if (%s) {" % self.ref(self.l, op.args[0]))
+                self.ind += 1
+                saved = set(self.ensured)
+                self.emit_block(i + 1, op.jumps[0], ctx)
+                self.ind -= 1
+                self.ensured = set(saved)
+                if op.jumps[1] > op.jumps[0]:
+                    self.w("} else {")
+                    self.ind += 1
+                    self.emit_block(op.jumps[0], op.jumps[1], ctx)
+                    self.ind -= 1
+                    self.ensured = set(saved)
+                self.w("}")
+                i = op.jumps[1]
+            elif n in ("for", "while", "dowhile"):
+                cl, bl, il, dl = op.jumps
+                self.label += 1
+                lab = self.label
+                c2 = dict(ctx or {})
+                c2.update(brk="brk_%d" % lab, cont="cont_%d" % lab)
+                self.emit_block(i + 1, cl, ctx)
+                saved = set(self.ensured)
+                cond = self.ref(self.l, op.args[0])
+                self.w("for (;;) {")
+                self.ind += 1
+                if n == "dowhile":
+                    self.emit_block(bl, il, c2)
+                    self.w("cont_%d:;" % lab)
+                    self.emit_block(cl, bl, c2)
+                    self.w("if (!(%s)) break;" % cond)
+                    self.emit_block(il, dl, c2)
+                else:
+                    self.emit_block(cl, bl, c2)
+                    self.w("if (!(%s)) break;" % cond)
+                    self.emit_block(bl, il, c2)
+                    self.w("cont_%d:;" % lab)
+                    self.emit_block(il, dl, c2)
+                self.ind -= 1
+                self.w("}")
+                self.w("brk_%d:;" % lab)
+                self.ensured = set(saved)
+                i = dl
+            elif n == "functioncall":
+                self.label += 1
+                lab = self.label
+                c2 = dict(ctx or {})
+                c2["ret"] = "ret_%d" % lab
+                self.w("{")
+                self.ind += 1
+                saved = set(self.ensured)
+                self.emit_block(i + 1, op.jumps[0], c2)
+                self.ensured = set(saved)
+                self.ind -= 1
+                self.w("}")
+                self.w("ret_%d:;" % lab)
+                i = op.jumps[0]
+            elif n == "break":
+                self.w("goto %s;" % ctx["brk"])
+                i += 1
+            elif n == "continue":
+                self.w("goto %s;" % ctx["cont"])
+                i += 1
+            elif n == "return":
+                self.w("goto %s;" % ((ctx or {}).get("ret") or "layer_end"))
+                i += 1
+            elif n == "exit":
+                self.w("goto layer_end;")
+                i += 1
+            elif n in ("nop", "end", "useparam"):
+                i += 1
+            else:
+                self.useparams(op)
+                self.w("{")
+                self.ind += 1
+                self.emit_op(op)
+                self.ind -= 1
+                self.w("}")
+                i += 1
+
+    def useparams(self, op):
+        """Lazy upstream evaluation before reading a connected param
+        (llvm_gen.cpp:133-283)."""
+        for a, c in zip(op.args, op.rw):
+            if c in "rW" and a.connected_from is not None:
+                up = a.connected_from[0]
+                if up in self.ensured:
+                    continue
+                self.ensured.add(up)
+                self.w("if (!gd.ran[%d]) layer_%d(sg, gd, L);" % (up, up))
+
+    # -- ops ----------------------------------------------------------------
+    def R(self, s):
+        return self.ref(self.l, s)
+
+    def comp(self, s, c, derivs):
+        """expression for component c of s as float (derivs=False) or as the
+        natural scalar (float/Df)."""
+        t = s.t
+        if s.isconst:
+            if t.base == "int":
+                return "%s" % cfloat(float(s.vals[0]))
+            if t.base == "float":
+                return cfloat(s.vals[0])
+            if t.triple:
+                return cfloat(s.vals[c])
+        e = "getc(%s, %d)" % (self.R(s), c)
+        if not derivs and s.has_derivs:
+            e = "nd(%s)" % e
+        return e
+
+    def emit_op(self, op):
+        n = op.name
+        A = op.args
+        h = getattr(self, "op_" + n, None)
+        if h is not None:
+            return h(op)
+        if n in UNARY or n in BINARY or n in TERNARY or n in ("div", "log"):
+            return self.op_percomp(op)
+        if n in CMP:
+            return self.op_cmp(op)
+        if n in INTBIN:
+            return self.w("%s = %s %s %s;" % (self.R(A[0]), self.R(A[1]), INTBIN[n], self.R(A[2])))
+        if n in TRIPLES:
+            return self.op_triple(op)
+        if n in NOISE_KIND and n != "hash":
+            return self.noise_impl(op, False)
+        if n in ("pnoise", "psnoise", "pcellnoise", "phashnoise"):
+            return self.noise_impl(op, True)
+        raise NotImplementedError("oracle: op '%s' not supported" % n)
+
+    def op_percomp(self, op):
+        n = op.name
+        A = op.args
+        d = A[0]
+        if d.t.base == "closure color":
+            return self.op_closure_arith(op)
+        if d.t.base == "matrix":
+            raise NotImplementedError("matrix %s" % n)
+        isint = d.t.base == "int"
+        dv = d.has_derivs and any(a.has_derivs for a in A[1:])
+        fn = "o_" + n
+        if n == "log" and len(A) == 3:
+            raise NotImplementedError("log(x,b) is an OSL-source function")
+        if n == "div" and A[2].isconst and not any(v == 0 for v in A[2].vals):
+            fn = "o_divc"
+        for c in range(d.t.ncomp):
+            if isint:
+                args = [self.R(a) for a in A[1:]]
+            else:
+                args = [self.comp(a, c, dv) for a in A[1:]]
+            self.w("setc(%s, %d, %s(%s));" % (self.R(d), c, fn, ", ".join(args)))
+
+    def op_mod(self, op):
+        A = op.args
+        self.w("%s = o_mod(%s, %s);" % (self.R(A[0]), self.R(A[1]), self.R(A[2])))
+
+    def op_compl(self, op):
+        self.w("%s = ~%s;" % (self.R(op.args[0]), self.R(op.args[1])))
+
+    def op_cmp(self, op):
+        A = op.args
+        a, b = A[1], A[2]
+        cop = CMP[op.name]
+        if a.t.base == "string":
+            e = "str_eq(%s, %s)" % (self.R(a), self.R(b))
+            if op.name == "neq":
+                e = "!" + e
+        elif a.t.base == "closure color":
+            e = "(%s %s nullptr)" % (self.R(a), cop)
+        elif a.t.base == "int" and b.t.base == "int":
+            e = "(%s %s %s)" % (self.R(a), cop, self.R(b))
+        else:
+            nc = max(a.t.ncomp, b.t.ncomp)
+            parts = ["(%s %s %s)" % (self.comp(a, c if a.t.ncomp > 1 else 0, False), cop,
+                                     self.comp(b, c if b.t.ncomp > 1 else 0, False))
+                     for c in range(nc)]
+            e = (" || " if op.name == "neq" else " && ").join(parts)
+        self.w("%s = (%s) ? 1 : 0;" % (self.R(A[0]), e))
+
+    def op_assign(self, op):
+        d, s = op.args
+        if d.t.arr:
+            for i in range(d.t.arr):
+                self.w("assign(%s[%d], %s[%d]);" % (self.R(d), i, self.R(s), i))
+        elif d.t.base == "matrix":
+            if s.t.base == "matrix":
+                self.w("%s = %s;" % (self.R(d), self.R(s)))
+            else:
+                self.w("%s = m44_diag(%s);" % (self.R(d), self.comp(s, 0, False)))
+        elif d.t.base == "closure color":
+            self.w("%s = %s;" % (self.R(d), "nullptr" if s.t.base == "int" else self.R(s)))
+        else:
+            self.w("assign(%s, %s);" % (self.R(d), self.R(s)))
+
+    def op_triple(self, op):
+        A = op.args
+        d = A[0]
+        if len(A) == 5:
+            raise NotImplementedError("triple constructor with a space name")
+        dv = d.has_derivs and any(a.has_derivs for a in A[1:])
+        for c in range(3):
+            self.w("setc(%s, %d, %s);" % (self.R(d), c, self.comp(A[1 + c], 0, dv)))
+
+    def op_compref(self, op):
+        d, s, i = op.args
+        if i.isconst:
+            self.w("setc(%s, 0, %s);" % (self.R(d), self.comp(s, int(i.vals[0]), d.has_derivs)))
+        else:
+            self.w("switch (%s) {" % self.R(i))
+            for c in range(3):
+                self.w("%s %d: setc(%s, 0, %s); break;" % (
+                    "default: case" if c == 0 else "case", c, self.R(d),
+                    self.comp(s, c, d.has_derivs)))
+            self.w("}")
+
+    def op_compassign(self, op):
+        d, i, s = op.args
+        v = self.comp(s, 0, d.has_derivs)
+        if i.isconst:
+            self.w("setc(%s, %d, %s);" % (self.R(d), int(i.vals[0]), v))
+        else:
+            self.w("switch (%s) {" % self.R(i))
+            for c in range(3):
+                self.w("%s %d: setc(%s, %d, %s); break;" % (
+                    "default: case" if c == 0 else "case", c, self.R(d), c, v))
+            self.w("}")
+
+    def op_aref(self, op):
+        d, s, i = op.args
+        self.w("{ int ix_ = %s; if (ix_ < 0 || ix_ >= %d) ix_ = 0; assign(%s, %s[ix_]); }" % (
+            self.R(i), s.t.arr, self.R(d), self.R(s)))
+
+    def op_aassign(self, op):
+        d, i, s = op.args
+        self.w("{ int ix_ = %s; if (ix_ < 0 || ix_ >= %d) ix_ = 0; assign(%s[ix_], %s); }" % (
+            self.R(i), d.t.arr, self.R(d), self.R(s)))
+
+    def op_arraylength(self, op):
+        self.w("%s = %d;" % (self.R(op.args[0]), op.args[1].t.arr))
+
+    def op_sincos(self, op):
+        x, s, c = op.args
+        for k in range(x.t.ncomp):
+            self.w("{ auto x_ = %s; setc(%s, %d, o_sin(x_)); setc(%s, %d, o_cos(x_)); }" % (
+                self.comp(x, k, (s.has_derivs or c.has_derivs) and x.has_derivs),
+                self.R(s), k, self.R(c), k))
+
+    def op_vec(self, op):
+        # dot cross length distance normalize: pass whole values; the C++
+        # overloads pick the Dv form only when an operand carries derivs
+        A = op.args
+        d = A[0]
+        dv = d.has_derivs and any(a.has_derivs for a in A[1:])
+        args = []
+        for a in A[1:]:
+            e = self.R(a)
+            if a.has_derivs and not dv:
+                e = "nd(%s)" % e
+            args.append(e)
+        self.w("assign(%s, o_%s(%s));" % (self.R(d), op.name, ", ".join(args)))
+
+    op_dot = op_cross = op_length = op_distance = op_normalize = op_luminance = op_vec
+
+    def op_deriv(self, op):
+        d, s = op.args
+        self.w("assign(%s, o_%s(%s));" % (self.R(d), op.name, self.R(s)))
+
+    op_Dx = op_Dy = op_filterwidth = op_deriv
+
+    def op_Dz(self, op):
+        d, s = op.args
+        if s.symtype == "global" and s.name == "P":
+            self.w("assign(%s, sg.dPdz);" % self.R(d))
+        else:
+            self.w("assign(%s, 0.0f);" % self.R(d))
+
+    def op_area(self, op):
+        self.w("assign(%s, o_area(%s));" % (self.R(op.args[0]), self.R(op.args[1])))
+
+    def op_calculatenormal(self, op):
+        self.w("assign(%s, o_calculatenormal(%s, sg.flipHandedness != 0));" % (
+            self.R(op.args[0]), self.R(op.args[1])))
+
+    def op_isnan(self, op):
+        self.w("%s = std::isnan(%s) ? 1 : 0;" % (self.R(op.args[0]), self.comp(op.args[1], 0, False)))
+
+    def op_isinf(self, op):
+        self.w("%s = std::isinf(%s) ? 1 : 0;" % (self.R(op.args[0]), self.comp(op.args[1], 0, False)))
+
+    def op_isfinite(self, op):
+        self.w("%s = std::isfinite(%s) ? 1 : 0;" % (self.R(op.args[0]), self.comp(op.args[1], 0, False)))
+
+    def op_surfacearea(self, op):
+        self.w("assign(%s, sg.surfacearea);" % self.R(op.args[0]))
+
+    def op_backfacing(self, op):
+        self.w("%s = sg.backfacing;" % self.R(op.args[0]))
+
+    def op_raytype(self, op):
+        d, nm = op.args
+        if not nm.isconst:
+            raise NotImplementedError("raytype(non-constant)")
+        self.w("%s = (sg.raytype & %d) != 0;" % (self.R(d), raytype_bit(nm.vals[0])))
+
+    def op_isconnected(self, op):
+        d, s = op.args
+        v = 1 if s.connected_from is not None else (2 if s.connected_down else 0)
+        self.w("%s = %d;" % (self.R(d), v))
+
+    def op_isconstant(self, op):
+        self.w("%s = %d;" % (self.R(op.args[0]), 1 if op.args[1].isconst else 0))
+
+    def op_hash(self, op):
+        A = op.args
+        d = A[0]
+        ins = A[1:]
+        if len(ins) == 1 and ins[0].t.base == "int":
+            e = "hash_i(%s)" % self.R(ins[0])
+        elif len(ins) == 1 and ins[0].t.base == "float":
+            e = "hash_f(%s)" % self.comp(ins[0], 0, False)
+        elif len(ins) == 2 and ins[0].t.base == "float":
+            e = "hash_ff(%s, %s)" % (self.comp(ins[0], 0, False), self.comp(ins[1], 0, False))
+        elif len(ins) == 1:
+            e = "hash_v(nd(%s))" % self.R(ins[0])
+        else:
+            e = "hash_vf(nd(%s), %s)" % (self.R(ins[0]), self.comp(ins[1], 0, False))
+        self.w("%s = %s;" % (self.R(d), e))
+
+    def noise_impl(self, op, periodic):
+        """llvm_gen_noise (llvm_gen.cpp:3117-3299): resolve the name at gen
+        time, pick float/Dual form from has_derivs of result and inputs."""
+        A = list(op.args)
+        d = A[0]
+        rest = A[1:]
+        name = op.name
+        if rest and rest[0].t.base == "string":
+            if not rest[0].isconst:
+                raise NotImplementedError("noise with a non-constant name")
+            name = rest[0].vals[0]
+            rest = rest[1:]
+            if periodic and not name.startswith("p"):
+                pass
+        # strip optional token/value pairs
+        coords = []
+        for a in rest:
+            if a.t.base == "string":
+                break
+            coords.append(a)
+        table = PNOISE_KIND if periodic else NOISE_KIND
+        if name not in table:
+            raise NotImplementedError("noise type '%s'" % name)
+        kind = table[name]
+        if periodic:
+            half = len(coords) // 2
+            pers = coords[half:]
+            coords = coords[:half]
+        # flatten coordinates
+        ins = []
+        for a in coords:
+            for c in range(a.t.ncomp):
+                ins.append((a, c))
+        dim = len(ins)
+        nc = d.t.ncomp
+        hashy = kind in ("N_CELL", "N_HASH")
+        dv = (not hashy) and d.has_derivs and any(a.has_derivs for a in coords)
+        S = "Df" if dv else "float"
+        self.w("%s in_[4] = {%s};" % (S, ", ".join(self.comp(a, c, dv) for a, c in ins)))
+        self.w("%s out_[3];" % S)
+        if periodic:
+            pin = []
+            for a in pers:
+                for c in range(a.t.ncomp):
+                    pin.append(self.comp(a, c, False))
+            if hashy:
+                self.w("float per_[4] = {%s};" % ", ".join(pin))
+                self.w("for (int k_ = 0; k_ < %d; ++k_) in_[k_] = pwrap(in_[k_], per_[k_]);" % dim)
+                self.w("ihnoise_core<%s, %d>(out_, %d, in_);" % (kind, nc, dim))
+            else:
+                self.w("int per_[4] = {%s};" % ", ".join("iperiod(%s)" % p for p in pin))
+                self.w("perlin_nd<%s, %d, %s>(out_, %d, in_, per_);" % (
+                    S, nc, "true" if kind == "N_SNOISE" else "false", dim))
+        elif hashy:
+            self.w("ihnoise_core<%s, %d>(out_, %d, in_);" % (kind, nc, dim))
+        else:
+            self.w("noise_core<%s, %s, %d>(out_, %d, in_);" % (kind, S, nc, dim))
+        for c in range(nc):
+            self.w("setc(%s, %d, out_[%d]);" % (self.R(d), c, c))
+
+
+    def op_printf(self, op):
+        A = op.args
+        fmt = A[0]
+        if not fmt.isconst:
+            raise NotImplementedError("printf with non-constant format")
+        self.emit_format(fmt.vals[0], A[1:])
+
+    def emit_format(self, f, args):
+        """Split an OSL format string at gen time (reference: llvm_gen_printf,
+        llvm_gen.cpp:350-700: one C conversion per component, space separated)."""
+        ai = 0
+        i = 0
+        lit = ""
+        while i < len(f):
+            ch = f[i]
+            if ch != "%":
+                lit += ch
+                i += 1
+                continue
+            if f[i + 1:i + 2] == "%":
+                lit += "%"
+                i += 2
+                continue
+            j = i + 1
+            while j < len(f) and f[j] not in "cdefgimnopsuvxXEG":
+                j += 1
+            spec, conv = f[i:j + 1], f[j]
+            i = j + 1
+            if lit:
+                self.w("pf_lit(sg, %s);" % cstr(lit))
+                lit = ""
+            a = args[ai]
+            ai += 1
+            n = max(1, a.t.arr)
+            for e in range(n):
+                r = self.R(a) + ("[%d]" % e if a.t.arr else "")
+                if e:
+                    self.w('pf_lit(sg, " ");')
+                if a.t.base == "string":
+                    self.w("pf_s(sg, %s, %s);" % (cstr(spec[:-1] + "s"), r))
+                elif a.t.base == "int":
+                    if conv in "di":
+                        self.w("pf_i(sg, %s, %s);" % (cstr(spec), r))
+                    else:
+                        self.w("pf_f(sg, %s, %s);" % (cstr(spec), r))
+                elif a.t.base == "float":
+                    if conv in "dixX":
+                        self.w("pf_i(sg, %s, nd(%s));" % (cstr(spec), r))
+                    else:
+                        self.w("pf_f(sg, %s, %s);" % (cstr(spec), r))
+                elif a.t.triple:
+                    self.w("pf_v(sg, %s, %s);" % (cstr(spec), r))
+                else:
+                    raise NotImplementedError("printf of %s" % a.t)
+        if lit:
+            self.w("pf_lit(sg, %s);" % cstr(lit))
+
+    def op_closure_arith(self, op):
+        raise NotImplementedError("closures not yet supported by the oracle generator")
+
+
+RAYTYPES = ["camera", "shadow", "reflection", "refraction", "diffuse", "glossy",
+            "subsurface", "displacement"]
+
+
+def raytype_bit(name):
+    """testshade/simplerend.cpp raytype names -> bit (1<<index)."""
+    return (1 << RAYTYPES.index(name)) if name in RAYTYPES else 0
+
+
+RUNNER_TAIL = r"""
+extern "C" void oracle_run_mt(const Launch* L, long long n, int nthreads)
+{
+    if (nthreads <= 1) { oracle_run(L, 0, n, nullptr); return; }
+    std::vector<std::thread> th;
+    long long chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        long long b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { oracle_run(L, b, e, nullptr); });
+    }
+    for (auto& t : th) t.join();
+}
+extern "C" const char* oracle_run_capture(const Launch* L, long long begin, long long end)
+{
+    static std::string buf;
+    buf.clear();
+    oracle_run(L, begin, end, &buf);
+    return buf.c_str();
+}
+"""
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_group(group, workdir=None, opt="-O2", extra_flags=()):
+    """Generate + compile; returns path of the shared object."""
+    src = Gen(group).generate()
+    workdir = workdir or os.path.join(HERE, "_build")
+    os.makedirs(workdir, exist_ok=True)
+    hdrs = b""
+    for h in ("osl_oracle.h", "osl_oracle_ops.h", "osl_oracle_runtime.h"):
+        with open(os.path.join(HERE, h), "rb") as f:
+            hdrs += f.read()
+    key = hashlib.sha1(src.encode() + hdrs + opt.encode() + " ".join(extra_flags).encode()).hexdigest()[:16]
+    so = os.path.join(workdir, "oracle_%s.so" % key)
+    if not os.path.exists(so):
+        cpp = os.path.join(workdir, "oracle_%s.cpp" % key)
+        with open(cpp, "w") as f:
+            f.write(src)
+        cmd = ["g++", "-std=c++17", opt, "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+               "-I", HERE, cpp, "-o", so + ".tmp"] + list(extra_flags)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle compile failed:\n" + r.stderr[:6000])
+        os.replace(so + ".tmp", so)
+    return so
