@@ -1,0 +1,167 @@
+/* osl_b200.h — C ABI of libosl_b200.so, the B200-native execution back end
+ * for Open Shading Language's data-parallel hot path.
+ *
+ * Plain C: pointers and sizes only, status codes, no exceptions cross this
+ * boundary.  Every entry point names the reference interface it stands in for
+ * (paths relative to the OSL source tree).  The C++ mirror of the reference
+ * API (OSL::ShadingSystem / BatchedExecutor) in include/OSL/oslexec_b200.h is
+ * a thin layer over these calls; INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ */
+#ifndef OSL_B200_H
+#define OSL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSL_B200_ABI_VERSION 1
+#define B200_MAX_OUTPUTS 16  /* renderer outputs per group */
+
+/* status codes */
+#define B200_OK 0
+#define B200_ERR_INVALID 1   /* bad argument / malformed group description   */
+#define B200_ERR_COMPILE 2   /* .oso parse, code generation or NVRTC failure */
+#define B200_ERR_CUDA 3      /* CUDA driver/runtime error                     */
+#define B200_ERR_UNSUPPORTED 4
+
+/* Per-point shader globals, SoA.  Field order mirrors ShaderGlobals
+ * (src/include/OSL/shaderglobals.h:55-146); layout mirrors the batched
+ * reference's Block<Vec3> = x[W],y[W],z[W] (src/include/OSL/wide.h:439-444)
+ * with W = the whole batch. */
+typedef enum b200_sg_field {
+    B200_SG_P = 0, B200_SG_dPdx, B200_SG_dPdy, B200_SG_dPdz,
+    B200_SG_I, B200_SG_dIdx, B200_SG_dIdy,
+    B200_SG_N, B200_SG_Ng,
+    B200_SG_u, B200_SG_dudx, B200_SG_dudy,
+    B200_SG_v, B200_SG_dvdx, B200_SG_dvdy,
+    B200_SG_dPdu, B200_SG_dPdv,
+    B200_SG_time, B200_SG_dtime, B200_SG_dPdtime,
+    B200_SG_Ps, B200_SG_dPsdx, B200_SG_dPsdy,
+    B200_SG_surfacearea,
+    B200_SG_raytype,        /* int32 */
+    B200_SG_flipHandedness, /* int32 */
+    B200_SG_backfacing,     /* int32 */
+    B200_SG_NFIELDS
+} b200_sg_field;
+
+/* varying[f] != NULL : per-point data.  Triples are three planes
+ * (x at +0, y at +plane_stride, z at +2*plane_stride elements); scalars one
+ * plane; int fields are int32 planes.  varying[f] == NULL : the field is
+ * uniform over the batch and uniform[f][0..2] is used (ints bit-cast in [0]),
+ * like BatchedShaderGlobals' UniformShaderGlobals
+ * (src/include/OSL/batched_shaderglobals.h:21-195). */
+typedef struct b200_globals {
+    const float* varying[B200_SG_NFIELDS];
+    float uniform[B200_SG_NFIELDS][4];
+    long long plane_stride;
+} b200_globals;
+
+/* ShadingSystem::Parameter (src/include/OSL/oslexec.h:656) */
+typedef struct b200_param {
+    const char* name;
+    int type;              /* 0 = int, 1 = float-based, 2 = string */
+    int nvalues;
+    const void* values;    /* int* / float* / const char** */
+} b200_param;
+
+/* ShadingSystem::Shader (oslexec.h:723): one layer = .oso text + instance values */
+typedef struct b200_layer {
+    const char* oso_text;
+    const char* layername;
+    int nparams;
+    const b200_param* params;
+} b200_layer;
+
+/* ShadingSystem::ConnectShaders (oslexec.h:740) */
+typedef struct b200_connection {
+    const char* srclayer;
+    const char* srcparam;
+    const char* dstlayer;
+    const char* dstparam;
+} b200_connection;
+
+/* SymLocationDesc with arena = Outputs (oslexec.h:69-105): where a renderer
+ * output lands: output_base + offset + stride*shadeindex; derivs => val,dx,dy */
+typedef struct b200_symloc {
+    const char* name;  /* "layer.param" or "param" */
+    long long offset;
+    long long stride;
+    int derivs;
+} b200_symloc;
+
+/* ShaderGroupBegin ... ShaderGroupEnd (oslexec.h:634-650) */
+typedef struct b200_group_desc {
+    const char* name;
+    int nlayers;
+    const b200_layer* layers;
+    int nconnections;
+    const b200_connection* connections;
+    int noutputs;
+    const b200_symloc* outputs;
+    /* comma separated k=v, the analogue of ShadingSystem::attribute("options"):
+     *   fma=0|1   allow FMA contraction (reference: llvm_jit_fma, default 0 scalar / 1 batched)
+     *   block=N   CTA size (default 256) */
+    const char* options;
+} b200_group_desc;
+
+typedef struct b200_group b200_group;
+
+/* Group build + JIT: replaces BackendLLVM::run / BatchedExecutor::jit_group
+ * (src/liboslexec/llvm_instance.cpp:2083, oslexec.h:982-1003).  Does not need a
+ * GPU: generation + NVRTC compile to an sm_100a cubin happen here; the cubin
+ * is loaded lazily on first execute. */
+int b200_group_compile(const b200_group_desc* desc, b200_group** out);
+void b200_group_destroy(b200_group* g);
+
+/* Introspection (ShadingSystem::getattribute(group, ...), oslexec.h:324-596) */
+const char* b200_group_cuda_source(const b200_group* g);   /* generated CUDA C++ */
+const void* b200_group_cubin(const b200_group* g, long long* size);
+int b200_group_num_warnings(const b200_group* g);
+const char* b200_group_warning(const b200_group* g, int i);
+/* 1 if the kernel reads globals field f (the reference's "globals_read" bits) */
+int b200_group_reads_global(const b200_group* g, int field);
+
+/* Execute over npoints shading points with DEVICE pointers: replaces
+ * BatchedExecutor<W>::execute(ctx, group, batch_size, wide_shadeindex, bsg,
+ * userdata_base, output_base) (oslexec.h:1005-1033) with batch = the whole
+ * range.  shadeindex == NULL means iota.  stream is a cudaStream_t (may be 0).
+ * Asynchronous with respect to the host. */
+int b200_group_execute(b200_group* g, int device, void* stream, long long npoints,
+                       const b200_globals* sg, const int* shadeindex,
+                       const void* userdata_base, void* output_base);
+
+/* Same call with HOST pointers: uploads only the planes the group reads, runs,
+ * and downloads the renderer outputs into the host arena at
+ * output_base + offset + stride*shadeindex (shadeindex = 0..npoints-1);
+ * chunked and pipelined over streams so H2D, kernel and D2H overlap.  Outputs
+ * that interleave in one record (same stride, offsets within a stride) move
+ * as whole records.  This is the renderer-facing path (ShadingSystem::execute
+ * with host ShaderGlobals, oslexec.h:833).  Synchronous.  Pinned host memory
+ * makes the copies asynchronous; pageable memory works but serialises. */
+int b200_group_execute_host(b200_group* g, int device, long long npoints,
+                            const b200_globals* sg, void* output_base);
+
+/* Number of kernel launches issued by this library so far (bench accounting) */
+long long b200_launch_count(void);
+
+/* ---- device shadeop library, batch entry points (device pointers) --------
+ * Stand-alone equivalents of the osl_<op>_<codes> runtime
+ * (src/liboslexec/builtindecl.h:19-83, opnoise.cpp:263-273, 468-473) over
+ * SoA arrays.  kind: 0 noise 1 snoise 2 cellnoise 3 hashnoise.
+ * in:  indim planes of n floats (+ 2*indim derivative planes when derivs)
+ * out: outdim planes of n floats (x3 when derivs: val planes, dx planes, dy planes)
+ * period (pnoise family): indim floats, or NULL. */
+int b200_shadeop_noise(int kind, int outdim, int indim, int derivs, int fma,
+                       long long n, const float* in, const float* period,
+                       float* out, void* stream);
+/* osl_hash_* (builtindecl.h:169-173): indim floats per point -> int32 */
+int b200_shadeop_hash(int indim, long long n, const float* in, int* out, void* stream);
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSL_B200_H */

@@ -1,0 +1,250 @@
+"""ctypes binding of include/osl_b200.h (host-side plumbing, not the product).
+
+Mirrors the reference call sequence a renderer makes
+(ShaderGroupBegin / Parameter / Shader / ConnectShaders / ShaderGroupEnd, then
+execute with ShaderGlobals + output arena; src/include/OSL/oslexec.h:634-1033)
+one-to-one on the C ABI.  Device memory and streams come from PyTorch.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libosl_b200.so")
+
+SG_FIELDS = ["P", "dPdx", "dPdy", "dPdz", "I", "dIdx", "dIdy", "N", "Ng", "u", "dudx",
+             "dudy", "v", "dvdx", "dvdy", "dPdu", "dPdv", "time", "dtime", "dPdtime",
+             "Ps", "dPsdx", "dPsdy", "surfacearea", "raytype", "flipHandedness",
+             "backfacing"]
+SG_VEC = {"P", "dPdx", "dPdy", "dPdz", "I", "dIdx", "dIdy", "N", "Ng", "dPdu", "dPdv",
+          "dPdtime", "Ps", "dPsdx", "dPsdy"}
+SG_INT = {"raytype", "flipHandedness", "backfacing"}
+NF = len(SG_FIELDS)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class _Globals(ctypes.Structure):
+    _fields_ = [("varying", ctypes.c_void_p * NF),
+                ("uniform", (ctypes.c_float * 4) * NF),
+                ("plane_stride", ctypes.c_longlong)]
+
+
+class _Param(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("type", ctypes.c_int), ("nvalues", ctypes.c_int),
+                ("values", ctypes.c_void_p)]
+
+
+class _Layer(ctypes.Structure):
+    _fields_ = [("oso_text", ctypes.c_char_p), ("layername", ctypes.c_char_p),
+                ("nparams", ctypes.c_int), ("params", ctypes.POINTER(_Param))]
+
+
+class _Connection(ctypes.Structure):
+    _fields_ = [("srclayer", ctypes.c_char_p), ("srcparam", ctypes.c_char_p),
+                ("dstlayer", ctypes.c_char_p), ("dstparam", ctypes.c_char_p)]
+
+
+class _SymLoc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("offset", ctypes.c_longlong),
+                ("stride", ctypes.c_longlong), ("derivs", ctypes.c_int)]
+
+
+class _GroupDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("nlayers", ctypes.c_int),
+                ("layers", ctypes.POINTER(_Layer)), ("nconnections", ctypes.c_int),
+                ("connections", ctypes.POINTER(_Connection)), ("noutputs", ctypes.c_int),
+                ("outputs", ctypes.POINTER(_SymLoc)), ("options", ctypes.c_char_p)]
+
+
+_lib = None
+
+
+def library_path():
+    return _LIBPATH
+
+
+def lib():
+    """Load libosl_b200.so; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise B200Error("libosl_b200.so is not built: run `python -m openshadinglanguage_b200.build` "
+                        "(or __graft_entry__.build()); the product has no CPU fallback")
+    L = ctypes.CDLL(_LIBPATH)
+    L.b200_last_error.restype = ctypes.c_char_p
+    L.b200_group_compile.argtypes = [ctypes.POINTER(_GroupDesc), ctypes.POINTER(ctypes.c_void_p)]
+    L.b200_group_destroy.argtypes = [ctypes.c_void_p]
+    L.b200_group_cuda_source.argtypes = [ctypes.c_void_p]
+    L.b200_group_cuda_source.restype = ctypes.c_char_p
+    L.b200_group_cubin.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    L.b200_group_cubin.restype = ctypes.c_void_p
+    L.b200_group_num_warnings.argtypes = [ctypes.c_void_p]
+    L.b200_group_warning.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.b200_group_warning.restype = ctypes.c_char_p
+    L.b200_group_reads_global.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.b200_group_execute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                                     ctypes.POINTER(_Globals), ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p]
+    L.b200_group_execute_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                          ctypes.POINTER(_Globals), ctypes.c_void_p]
+    L.b200_launch_count.restype = ctypes.c_longlong
+    L.b200_shadeop_noise.argtypes = [ctypes.c_int] * 5 + [ctypes.c_longlong, ctypes.c_void_p,
+                                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.b200_shadeop_hash.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200Error("libosl_b200 error %d: %s" % (rc, lib().b200_last_error().decode(errors="replace")))
+
+
+def launch_count():
+    return int(lib().b200_launch_count())
+
+
+def _ptr(x):
+    """raw address of a torch tensor / numpy array / int / None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def _fill_globals(n, varying, uniform, plane_stride=None):
+    g = _Globals()
+    for i, f in enumerate(SG_FIELDS):
+        g.varying[i] = _ptr(varying.get(f)) if varying else None
+        vals = list((uniform or {}).get(f, []))
+        for c in range(4):
+            if f in SG_INT:
+                iv = int(vals[0]) if vals else 0
+                g.uniform[i][c] = float(np.array([iv], np.int32).view(np.float32)[0]) if c == 0 else 0.0
+            else:
+                g.uniform[i][c] = float(vals[c]) if c < len(vals) else 0.0
+    g.plane_stride = n if plane_stride is None else plane_stride
+    return g
+
+
+class ShaderGroup:
+    """One compiled shader group.
+
+    layers:       [dict(oso=<.oso text>, name=<layer name>, params={name: value(s)})]
+    connections:  [(srclayer, srcparam, dstlayer, dstparam)]
+    outputs:      [dict(name='layer.param'|'param', offset=, stride=, derivs=False)]
+    options:      'fma=0' selects strict IEEE evaluation (bit-parity mode)
+    """
+
+    def __init__(self, layers, connections=(), outputs=(), options="", name="group"):
+        L = lib()
+        keep = []
+
+        def cs(s):
+            b = s.encode() if isinstance(s, str) else s
+            keep.append(b)
+            return b
+        clayers = (_Layer * len(layers))()
+        for i, l in enumerate(layers):
+            params = l.get("params") or {}
+            cp = (_Param * max(1, len(params)))()
+            for j, (k, v) in enumerate(params.items()):
+                if not isinstance(v, (list, tuple, np.ndarray)):
+                    v = [v]
+                if isinstance(v[0], str):
+                    arr = (ctypes.c_char_p * len(v))(*[cs(x) for x in v])
+                    t = 2
+                elif isinstance(v[0], (int, np.integer)) and not isinstance(v[0], bool):
+                    arr = (ctypes.c_int * len(v))(*[int(x) for x in v])
+                    t = 0
+                else:
+                    arr = (ctypes.c_float * len(v))(*[float(x) for x in v])
+                    t = 1
+                keep.append(arr)
+                cp[j].name, cp[j].type, cp[j].nvalues = cs(k), t, len(v)
+                cp[j].values = ctypes.cast(arr, ctypes.c_void_p)
+            keep.append(cp)
+            clayers[i].oso_text, clayers[i].layername = cs(l["oso"]), cs(l["name"])
+            clayers[i].nparams, clayers[i].params = len(params), cp
+        cconn = (_Connection * max(1, len(connections)))()
+        for i, (a, b, c, d) in enumerate(connections):
+            cconn[i].srclayer, cconn[i].srcparam, cconn[i].dstlayer, cconn[i].dstparam = cs(a), cs(b), cs(c), cs(d)
+        cout = (_SymLoc * max(1, len(outputs)))()
+        for i, o in enumerate(outputs):
+            cout[i].name, cout[i].offset, cout[i].stride = cs(o["name"]), int(o["offset"]), int(o["stride"])
+            cout[i].derivs = 1 if o.get("derivs") else 0
+        desc = _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, len(outputs), cout,
+                          cs(options))
+        h = ctypes.c_void_p()
+        _check(L.b200_group_compile(ctypes.byref(desc), ctypes.byref(h)))
+        self._h = h
+        self.outputs = list(outputs)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().b200_group_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def cuda_source(self):
+        return lib().b200_group_cuda_source(self._h).decode()
+
+    @property
+    def cubin(self):
+        n = ctypes.c_longlong()
+        p = lib().b200_group_cubin(self._h, ctypes.byref(n))
+        return ctypes.string_at(p, n.value)
+
+    @property
+    def warnings(self):
+        L = lib()
+        return [L.b200_group_warning(self._h, i).decode() for i in range(L.b200_group_num_warnings(self._h))]
+
+    def reads_global(self, name):
+        return bool(lib().b200_group_reads_global(self._h, SG_FIELDS.index(name)))
+
+    def execute(self, n, varying, uniform, output, shadeindex=None, device=0, stream=None,
+                plane_stride=None):
+        """Device-pointer path (b200_group_execute).  varying values and output
+        are CUDA tensors (or raw device addresses).  Asynchronous."""
+        g = _fill_globals(n, varying, uniform, plane_stride)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(device).cuda_stream
+        _check(lib().b200_group_execute(self._h, device, ctypes.c_void_p(stream), n, ctypes.byref(g),
+                                        _ptr(shadeindex), None, _ptr(output)))
+
+    def execute_host(self, n, varying, uniform, output, device=0, plane_stride=None):
+        """Host-pointer path (b200_group_execute_host): numpy arrays or pinned
+        CPU tensors in, host output arena out.  Synchronous."""
+        g = _fill_globals(n, varying, uniform, plane_stride)
+        _check(lib().b200_group_execute_host(self._h, device, n, ctypes.byref(g), _ptr(output)))
+
+
+def shadeop_noise(kind, outdim, indim, n, inp, out, period=None, derivs=False, stream=None):
+    """Batch noise over device SoA planes (b200_shadeop_noise)."""
+    kinds = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3}
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _check(lib().b200_shadeop_noise(kinds[kind], outdim, indim, 1 if derivs else 0, 0, n, _ptr(inp),
+                                    _ptr(period), _ptr(out), ctypes.c_void_p(stream)))
+
+
+def shadeop_hash(indim, n, inp, out, stream=None):
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _check(lib().b200_shadeop_hash(indim, n, _ptr(inp), _ptr(out), ctypes.c_void_p(stream)))

@@ -1,0 +1,946 @@
+// osl_b200_codegen.cpp — shader group -> CUDA C++ text for sm_100a (product code).
+//
+// This is the B200 target of the reference's code generators: it fills the
+// role of BackendLLVM::run + llvm_gen_* for the GPU
+// (src/liboslexec/llvm_instance.cpp:1288-1870, 2083-2572; llvm_gen.cpp), with
+// the structure of BackendCpp (src/liboslexec/backendcpp.cpp) — a group-data
+// struct, one device function per used layer, lazy upstream calls guarded by
+// run bits, and an entry kernel — but emitting code against the device
+// library in csrc/device/osl_b200_device.cuh.  One thread shades one point;
+// only the ShaderGlobals fields the group reads are loaded (coalesced SoA
+// planes); group data lives in registers.
+#include "../../../include/osl_b200.h"
+#include "osl_b200_group.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <sstream>
+#include <stdexcept>
+
+namespace oslb200 {
+
+namespace {
+
+std::string
+cfloat(float f)
+{
+    if (std::isnan(f))
+        return "__int_as_float(0x7fc00000)";
+    if (std::isinf(f))
+        return f > 0 ? "__int_as_float(0x7f800000)" : "__int_as_float(0xff800000)";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.9g", f);
+    std::string s = buf;
+    if (s.find('.') == std::string::npos && s.find('e') == std::string::npos)
+        s += ".0";
+    return s + "f";
+}
+
+std::string
+ident(const std::string& n)
+{
+    std::string r;
+    for (char c : n) {
+        if (c == '$')
+            r += "S_";
+        else if (isalnum((unsigned char)c) || c == '_')
+            r += c;
+        else
+            r += '_';
+    }
+    return r;
+}
+
+struct GlobalInfo {
+    const char* expr;
+    int field;          // value field
+    int dx, dy;         // derivative fields or -1
+    bool triple;
+};
+const std::map<std::string, GlobalInfo>&
+global_table()
+{
+    static const std::map<std::string, GlobalInfo> t = {
+        { "P", { "sg.P", B200_SG_P, B200_SG_dPdx, B200_SG_dPdy, true } },
+        { "I", { "sg.I", B200_SG_I, B200_SG_dIdx, B200_SG_dIdy, true } },
+        { "N", { "sg.N", B200_SG_N, -1, -1, true } },
+        { "Ng", { "sg.Ng", B200_SG_Ng, -1, -1, true } },
+        { "u", { "sg.u", B200_SG_u, B200_SG_dudx, B200_SG_dudy, false } },
+        { "v", { "sg.v", B200_SG_v, B200_SG_dvdx, B200_SG_dvdy, false } },
+        { "dPdu", { "sg.dPdu", B200_SG_dPdu, -1, -1, true } },
+        { "dPdv", { "sg.dPdv", B200_SG_dPdv, -1, -1, true } },
+        { "Ps", { "sg.Ps", B200_SG_Ps, B200_SG_dPsdx, B200_SG_dPsdy, true } },
+        { "time", { "sg.time", B200_SG_time, -1, -1, false } },
+        { "dtime", { "sg.dtime", B200_SG_dtime, -1, -1, false } },
+        { "dPdtime", { "sg.dPdtime", B200_SG_dPdtime, -1, -1, true } },
+    };
+    return t;
+}
+
+const char* RAYTYPES[] = { "camera", "shadow", "reflection", "refraction",
+                           "diffuse", "glossy", "subsurface", "displacement" };
+int
+raytype_bit(const std::string& n)
+{
+    for (int i = 0; i < 8; ++i)
+        if (n == RAYTYPES[i])
+            return 1 << i;
+    return 0;
+}
+
+const std::set<std::string> UNARY
+    = { "sin",  "cos",   "tan",   "asin",  "acos", "atan",  "sinh",  "cosh",        "tanh", "log",
+        "log2", "log10", "exp",   "exp2",  "expm1", "erf",  "erfc",  "cbrt",        "sqrt",
+        "inversesqrt", "abs", "fabs", "floor", "ceil", "round", "trunc", "sign", "logb", "neg" };
+const std::set<std::string> BINARY = { "add", "sub", "mul", "div", "atan2", "pow", "fmod", "step", "min", "max" };
+const std::set<std::string> TERNARY = { "mix", "clamp", "smoothstep", "select" };
+const std::map<std::string, const char*> CMP
+    = { { "eq", "==" }, { "neq", "!=" }, { "lt", "<" }, { "gt", ">" }, { "le", "<=" }, { "ge", ">=" } };
+const std::map<std::string, const char*> INTBIN
+    = { { "bitand", "&" }, { "bitor", "|" }, { "xor", "^" }, { "shl", "<<" }, { "shr", ">>" } };
+
+// noise name -> (kind 0 perlin-unsigned, 1 perlin-signed, 2 cell, 3 hash)
+int
+noise_kind(const std::string& n, bool periodic)
+{
+    static const std::map<std::string, int> base
+        = { { "noise", 0 },  { "uperlin", 0 },   { "snoise", 1 }, { "perlin", 1 },
+            { "cell", 2 },   { "cellnoise", 2 }, { "hash", 3 },   { "hashnoise", 3 } };
+    static const std::map<std::string, int> per
+        = { { "pnoise", 0 }, { "psnoise", 1 }, { "pcellnoise", 2 }, { "phashnoise", 3 } };
+    if (periodic) {
+        auto it = per.find(n);
+        if (it != per.end())
+            return it->second;
+    }
+    auto it = base.find(n);
+    return it == base.end() ? -1 : it->second;
+}
+
+class Gen {
+public:
+    explicit Gen(Group& g) : g(g) {}
+    std::string run();
+
+private:
+    Group& g;
+    std::ostringstream o;
+    int ind = 0, label = 0;
+    Layer* L = nullptr;
+    int li   = 0;
+    std::set<int> ensured;
+    struct Ctx {
+        std::string ret, brk, cont;
+    };
+
+    void w(const std::string& s)
+    {
+        for (int i = 0; i < ind; ++i)
+            o << "    ";
+        o << s << "\n";
+    }
+    [[noreturn]] void unsupported(const std::string& what)
+    {
+        throw std::runtime_error("B200 back end: " + what + " (layer '" + L->layername + "', shader '"
+                                 + L->m.shadername + "')");
+    }
+    Symbol& S(int i) { return L->m.syms[i]; }
+
+    std::string ctype(const Symbol& s)
+    {
+        switch (s.type.base) {
+        case Base::Int: return "int";
+        case Base::String: return "int";  // interned string id
+        case Base::Float: return s.has_derivs ? "Df" : "float";
+        case Base::Color:
+        case Base::Point:
+        case Base::Vector:
+        case Base::Normal: return s.has_derivs ? "Dv" : "V3";
+        default: break;
+        }
+        unsupported("symbol '" + s.name + "' has a type the device path does not support yet");
+    }
+    std::string constexpr_(const Symbol& s)
+    {
+        if (s.type.arraylen)
+            return "K_" + ident(s.name);
+        switch (s.type.base) {
+        case Base::Int: return std::to_string(s.ivals.empty() ? 0 : s.ivals[0]);
+        case Base::Float: return cfloat(s.fvals.empty() ? 0.0f : s.fvals[0]);
+        case Base::String: return std::to_string(g.intern(s.svals.empty() ? "" : s.svals[0]));
+        default:
+            if (s.type.is_triple()) {
+                float v[3] = { 0, 0, 0 };
+                for (size_t i = 0; i < 3 && i < s.fvals.size(); ++i)
+                    v[i] = s.fvals[i];
+                return "mkv(" + cfloat(v[0]) + ", " + cfloat(v[1]) + ", " + cfloat(v[2]) + ")";
+            }
+        }
+        unsupported("constant '" + s.name + "' type");
+    }
+    std::string ref(int layer, const Symbol& s)
+    {
+        if (s.is_const())
+            return constexpr_(s);
+        if (s.is_param())
+            return "gd.L" + std::to_string(layer) + "_" + ident(s.name);
+        if (s.symtype == SymType::Global) {
+            auto it = global_table().find(s.name);
+            if (it == global_table().end())
+                unsupported("global '" + s.name + "'");
+            const GlobalInfo& gi = it->second;
+            g.globals_read.insert(gi.field);
+            if (gi.dx >= 0) {
+                if (s.has_derivs) {
+                    g.globals_read.insert(gi.dx);
+                    g.globals_read.insert(gi.dy);
+                    return std::string(gi.expr) + "_d()";
+                }
+                return std::string(gi.expr);
+            }
+            return gi.expr;
+        }
+        return ident(s.name);
+    }
+    std::string R(int si) { return ref(li, S(si)); }
+
+    // default-value initialiser expressions, one per array element
+    std::vector<std::string> initvals(const Symbol& s)
+    {
+        int n   = s.type.arraylen ? s.type.arraylen : 1;
+        int per = s.type.ncomp();
+        std::vector<std::string> out;
+        for (int e = 0; e < n; ++e) {
+            auto fv = [&](int c) {
+                size_t k = (size_t)e * per + c;
+                return k < s.fvals.size() ? s.fvals[k] : 0.0f;
+            };
+            switch (s.type.base) {
+            case Base::Int: out.push_back(std::to_string((size_t)e < s.ivals.size() ? s.ivals[e] : 0)); break;
+            case Base::String: out.push_back(std::to_string(g.intern((size_t)e < s.svals.size() ? s.svals[e] : ""))); break;
+            case Base::Float: out.push_back(s.has_derivs ? "mkd(" + cfloat(fv(0)) + ")" : cfloat(fv(0))); break;
+            default:
+                if (s.type.is_triple()) {
+                    std::string v = "mkv(" + cfloat(fv(0)) + ", " + cfloat(fv(1)) + ", " + cfloat(fv(2)) + ")";
+                    out.push_back(s.has_derivs ? "mkdv(" + v + ")" : v);
+                } else
+                    unsupported("default value of '" + s.name + "'");
+            }
+        }
+        return out;
+    }
+
+    // component c of symbol as float (derivs=false) or natural scalar
+    std::string comp(int si, int c, bool derivs)
+    {
+        const Symbol& s = S(si);
+        if (s.is_const()) {
+            if (s.type.base == Base::Int)
+                return cfloat((float)(s.ivals.empty() ? 0 : s.ivals[0]));
+            if (s.type.base == Base::Float)
+                return cfloat(s.fvals.empty() ? 0.0f : s.fvals[0]);
+            if (s.type.is_triple())
+                return cfloat((size_t)c < s.fvals.size() ? s.fvals[c] : 0.0f);
+        }
+        std::string e = "getc(" + R(si) + ", " + std::to_string(c) + ")";
+        if (!derivs && s.has_derivs)
+            e = "nd(" + e + ")";
+        return e;
+    }
+
+    void gen_layer(int layer);
+    void emit_block(int b, int e, const Ctx* ctx);
+    void useparams(const Opcode& op);
+    void emit_op(const Opcode& op);
+    void op_percomp(const Opcode& op);
+    void op_cmp(const Opcode& op);
+    void op_noise(const Opcode& op, bool periodic);
+    void emit_copy(int dl, const Symbol& d, int sl, const Symbol& s);
+};
+
+void
+Gen::emit_copy(int dl, const Symbol& d, int sl, const Symbol& s)
+{
+    std::string de = ref(dl, d), se = ref(sl, s);
+    if (d.type.arraylen) {
+        for (int i = 0; i < d.type.arraylen; ++i)
+            w("assign(" + de + "[" + std::to_string(i) + "], " + se + "[" + std::to_string(i) + "]);");
+    } else if (d.type.base == Base::String || d.type.base == Base::Int) {
+        w(de + " = " + se + ";");
+    } else
+        w("assign(" + de + ", " + se + ");");
+}
+
+void
+Gen::useparams(const Opcode& op)
+{
+    // lazy upstream evaluation (llvm_gen.cpp:133-283): run the producing layer
+    // once, the first time a connected parameter is read
+    for (size_t a = 0; a < op.args.size(); ++a) {
+        const Symbol& s = S(op.args[a]);
+        if (op.reads((int)a) && s.conn_layer >= 0 && !ensured.count(s.conn_layer)) {
+            ensured.insert(s.conn_layer);
+            std::string k = std::to_string(s.conn_layer);
+            w("if (!(gd.ran & " + std::to_string(1u << s.conn_layer) + "u)) layer_" + k + "(sg, gd, L);");
+        }
+    }
+}
+
+void
+Gen::emit_block(int b, int e, const Ctx* ctx)
+{
+    const std::vector<Opcode>& ops = L->m.ops;
+    int i                          = b;
+    while (i < e) {
+        const Opcode& op     = ops[i];
+        const std::string& n = op.name;
+        if (n == "if") {
+            if (op.jumps.size() < 2)
+                unsupported("malformed 'if'");
+            useparams(op);
+            w("if (" + R(op.args[0]) + ") {");
+            ++ind;
+            std::set<int> saved = ensured;
+            emit_block(i + 1, op.jumps[0], ctx);
+            --ind;
+            ensured = saved;
+            if (op.jumps[1] > op.jumps[0]) {
+                w("} else {");
+                ++ind;
+                emit_block(op.jumps[0], op.jumps[1], ctx);
+                --ind;
+                ensured = saved;
+            }
+            w("}");
+            i = op.jumps[1];
+        } else if (n == "for" || n == "while" || n == "dowhile") {
+            if (op.jumps.size() < 4)
+                unsupported("malformed loop");
+            int cl = op.jumps[0], bl = op.jumps[1], il = op.jumps[2], dl = op.jumps[3];
+            int lab = ++label;
+            Ctx c2  = ctx ? *ctx : Ctx();
+            c2.brk  = "brk_" + std::to_string(lab);
+            c2.cont = "cont_" + std::to_string(lab);
+            emit_block(i + 1, cl, ctx);
+            std::set<int> saved = ensured;
+            std::string cond    = R(op.args[0]);
+            w("for (;;) {");
+            ++ind;
+            if (n == "dowhile") {
+                emit_block(bl, il, &c2);
+                w(c2.cont + ":;");
+                emit_block(cl, bl, &c2);
+                w("if (!(" + cond + ")) break;");
+                emit_block(il, dl, &c2);
+            } else {
+                emit_block(cl, bl, &c2);
+                w("if (!(" + cond + ")) break;");
+                emit_block(bl, il, &c2);
+                w(c2.cont + ":;");
+                emit_block(il, dl, &c2);
+            }
+            --ind;
+            w("}");
+            w(c2.brk + ":;");
+            ensured = saved;
+            i       = dl;
+        } else if (n == "functioncall") {
+            int lab = ++label;
+            Ctx c2  = ctx ? *ctx : Ctx();
+            c2.ret  = "ret_" + std::to_string(lab);
+            w("{");
+            ++ind;
+            std::set<int> saved = ensured;
+            emit_block(i + 1, op.jumps[0], &c2);
+            ensured = saved;
+            --ind;
+            w("}");
+            w(c2.ret + ":;");
+            i = op.jumps[0];
+        } else if (n == "break") {
+            w("goto " + ctx->brk + ";");
+            ++i;
+        } else if (n == "continue") {
+            w("goto " + ctx->cont + ";");
+            ++i;
+        } else if (n == "return") {
+            w("goto " + ((ctx && !ctx->ret.empty()) ? ctx->ret : std::string("layer_end")) + ";");
+            ++i;
+        } else if (n == "exit") {
+            w("goto layer_end;");
+            ++i;
+        } else if (n == "nop" || n == "end" || n == "useparam") {
+            ++i;
+        } else {
+            useparams(op);
+            w("{");
+            ++ind;
+            emit_op(op);
+            --ind;
+            w("}");
+            ++i;
+        }
+    }
+}
+
+void
+Gen::op_percomp(const Opcode& op)
+{
+    const Symbol& d = S(op.args[0]);
+    if (d.type.base == Base::Closure || d.type.base == Base::Matrix)
+        unsupported("op '" + op.name + "' on closures/matrices");
+    bool isint = d.type.base == Base::Int;
+    bool dv    = false;
+    if (d.has_derivs)
+        for (size_t a = 1; a < op.args.size(); ++a)
+            dv |= S(op.args[a]).has_derivs;
+    std::string fn = "o_" + op.name;
+    if (op.name == "div") {
+        const Symbol& b = S(op.args[2]);
+        bool nz         = b.is_const();
+        for (float f : b.fvals)
+            nz &= (f != 0.0f);
+        for (int v : b.ivals)
+            nz &= (v != 0);
+        if (nz)
+            fn = "o_divc";
+    }
+    for (int c = 0; c < d.type.ncomp(); ++c) {
+        std::string args;
+        for (size_t a = 1; a < op.args.size(); ++a) {
+            if (a > 1)
+                args += ", ";
+            args += isint ? R(op.args[a]) : comp(op.args[a], c, dv);
+        }
+        w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", " + fn + "(" + args + "));");
+    }
+}
+
+void
+Gen::op_cmp(const Opcode& op)
+{
+    const Symbol &a = S(op.args[1]), &b = S(op.args[2]);
+    const char* cop = CMP.at(op.name);
+    std::string e;
+    if (a.type.base == Base::String || (a.type.base == Base::Int && b.type.base == Base::Int)) {
+        e = "(" + R(op.args[1]) + " " + cop + " " + R(op.args[2]) + ")";
+    } else if (a.type.base == Base::Closure) {
+        unsupported("closure comparison");
+    } else {
+        int nc = std::max(a.type.ncomp(), b.type.ncomp());
+        for (int c = 0; c < nc; ++c) {
+            if (c)
+                e += op.name == "neq" ? " || " : " && ";
+            e += "(" + comp(op.args[1], a.type.ncomp() > 1 ? c : 0, false) + " " + cop + " "
+                 + comp(op.args[2], b.type.ncomp() > 1 ? c : 0, false) + ")";
+        }
+    }
+    w(R(op.args[0]) + " = (" + e + ") ? 1 : 0;");
+}
+
+void
+Gen::op_noise(const Opcode& op, bool periodic)
+{
+    // llvm_gen_noise (llvm_gen.cpp:3117-3299): the noise name is resolved at
+    // code-generation time; the float vs Dual2 entry is chosen from has_derivs
+    std::vector<int> rest(op.args.begin() + 1, op.args.end());
+    const Symbol& d  = S(op.args[0]);
+    std::string name = op.name;
+    if (!rest.empty() && S(rest[0]).type.base == Base::String) {
+        const Symbol& ns = S(rest[0]);
+        if (!ns.const_value())
+            unsupported("noise() with a name that is not known at compile time");
+        name = ns.svals.empty() ? "" : ns.svals[0];
+        rest.erase(rest.begin());
+    }
+    std::vector<int> coords;
+    for (int a : rest) {
+        if (S(a).type.base == Base::String)
+            break;  // optional token/value pairs (only gabor consumes them)
+        coords.push_back(a);
+    }
+    int kind = noise_kind(name, periodic);
+    if (kind < 0)
+        unsupported("noise type \"" + name + "\"");
+    std::vector<int> pers;
+    if (periodic) {
+        size_t half = coords.size() / 2;
+        pers.assign(coords.begin() + half, coords.end());
+        coords.resize(half);
+    }
+    std::vector<std::pair<int, int>> ins;
+    for (int a : coords)
+        for (int c = 0; c < S(a).type.ncomp(); ++c)
+            ins.push_back({ a, c });
+    int dim = (int)ins.size(), nc = d.type.ncomp();
+    if (dim < 1 || dim > 4)
+        unsupported("noise with " + std::to_string(dim) + " input dimensions");
+    bool hashy = kind >= 2;
+    bool dv    = false;
+    if (!hashy && d.has_derivs)
+        for (int a : coords)
+            dv |= S(a).has_derivs;
+    std::string T = dv ? "Df" : "float";
+    std::string in = T + " in_[4] = {";
+    for (int k = 0; k < dim; ++k)
+        in += (k ? ", " : "") + comp(ins[k].first, ins[k].second, dv);
+    w(in + "};");
+    w(T + " out_[3];");
+    std::string sd = std::to_string(dim), sn = std::to_string(nc);
+    if (periodic) {
+        std::string pin;
+        int np = 0;
+        for (int a : pers)
+            for (int c = 0; c < S(a).type.ncomp(); ++c, ++np)
+                pin += (np ? ", " : "") + comp(a, c, false);
+        if (hashy) {
+            w("float per_[4] = {" + pin + "};");
+            w("for (int k_ = 0; k_ < " + sd + "; ++k_) in_[k_] = pwrap(in_[k_], per_[k_]);");
+            w(std::string("ihnoise<") + (kind == 2 ? "true" : "false") + ", " + sd + ", " + sn + ">(out_, in_);");
+        } else {
+            w("float perf_[4] = {" + pin + "};");
+            w("int per_[4];");
+            w("for (int k_ = 0; k_ < " + sd + "; ++k_) per_[k_] = iperiod(perf_[k_]);");
+            w("perlin<" + T + ", " + sd + ", " + sn + ", " + (kind == 1 ? "true" : "false") + ", true>(out_, in_, per_);");
+        }
+    } else if (hashy) {
+        w(std::string("ihnoise<") + (kind == 2 ? "true" : "false") + ", " + sd + ", " + sn + ">(out_, in_);");
+    } else {
+        w("perlin<" + T + ", " + sd + ", " + sn + ", " + (kind == 1 ? "true" : "false") + ", false>(out_, in_, nullptr);");
+    }
+    for (int c = 0; c < nc; ++c)
+        w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", out_[" + std::to_string(c) + "]);");
+}
+
+void
+Gen::emit_op(const Opcode& op)
+{
+    const std::string& n = op.name;
+    auto A               = [&](int i) -> Symbol& { return S(op.args[i]); };
+    auto need            = [&](size_t k) {
+        if (op.args.size() < k)
+            unsupported("op '" + n + "' has too few arguments");
+    };
+    if (n == "mod") {
+        need(3);
+        w(R(op.args[0]) + " = o_mod(" + R(op.args[1]) + ", " + R(op.args[2]) + ");");
+    } else if (n == "compl") {
+        need(2);
+        w(R(op.args[0]) + " = ~" + R(op.args[1]) + ";");
+    } else if (UNARY.count(n) || BINARY.count(n) || TERNARY.count(n)) {
+        op_percomp(op);
+    } else if (CMP.count(n)) {
+        need(3);
+        op_cmp(op);
+    } else if (INTBIN.count(n)) {
+        need(3);
+        w(R(op.args[0]) + " = " + R(op.args[1]) + " " + INTBIN.at(n) + " " + R(op.args[2]) + ";");
+    } else if (n == "assign") {
+        need(2);
+        const Symbol &d = A(0), &s = A(1);
+        if (d.type.arraylen) {
+            for (int i = 0; i < d.type.arraylen; ++i)
+                w("assign(" + R(op.args[0]) + "[" + std::to_string(i) + "], " + R(op.args[1]) + "["
+                  + std::to_string(i) + "]);");
+        } else if (d.type.base == Base::String) {
+            w(R(op.args[0]) + " = " + R(op.args[1]) + ";");
+        } else if (d.type.base == Base::Matrix || d.type.base == Base::Closure) {
+            unsupported("assignment of matrix/closure values");
+        } else {
+            (void)s;
+            w("assign(" + R(op.args[0]) + ", " + R(op.args[1]) + ");");
+        }
+    } else if (n == "color" || n == "point" || n == "vector" || n == "normal") {
+        if (op.args.size() != 4)
+            unsupported("triple constructor with a coordinate-system name");
+        bool dv = false;
+        if (A(0).has_derivs)
+            for (int a = 1; a < 4; ++a)
+                dv |= A(a).has_derivs;
+        for (int c = 0; c < 3; ++c)
+            w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", " + comp(op.args[1 + c], 0, dv) + ");");
+    } else if (n == "compref") {
+        need(3);
+        const Symbol& ix = A(2);
+        if (ix.is_const()) {
+            w("setc(" + R(op.args[0]) + ", 0, " + comp(op.args[1], ix.ivals.empty() ? 0 : ix.ivals[0], A(0).has_derivs) + ");");
+        } else {
+            w("switch (" + R(op.args[2]) + ") {");
+            for (int c = 0; c < 3; ++c)
+                w(std::string(c == 0 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
+                  + ", 0, " + comp(op.args[1], c, A(0).has_derivs) + "); break;");
+            w("}");
+        }
+    } else if (n == "compassign") {
+        need(3);
+        const Symbol& ix = A(1);
+        std::string v    = comp(op.args[2], 0, A(0).has_derivs);
+        if (ix.is_const()) {
+            w("setc(" + R(op.args[0]) + ", " + std::to_string(ix.ivals.empty() ? 0 : ix.ivals[0]) + ", " + v + ");");
+        } else {
+            w("switch (" + R(op.args[1]) + ") {");
+            for (int c = 0; c < 3; ++c)
+                w(std::string(c == 0 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
+                  + ", " + std::to_string(c) + ", " + v + "); break;");
+            w("}");
+        }
+    } else if (n == "aref") {
+        need(3);
+        std::string len = std::to_string(A(1).type.arraylen);
+        w("{ int ix_ = " + R(op.args[2]) + "; if (ix_ < 0 || ix_ >= " + len + ") ix_ = 0; ");
+        if (A(0).type.base == Base::String || A(0).type.base == Base::Int)
+            w("  " + R(op.args[0]) + " = " + R(op.args[1]) + "[ix_]; }");
+        else
+            w("  assign(" + R(op.args[0]) + ", " + R(op.args[1]) + "[ix_]); }");
+    } else if (n == "aassign") {
+        need(3);
+        std::string len = std::to_string(A(0).type.arraylen);
+        w("{ int ix_ = " + R(op.args[1]) + "; if (ix_ < 0 || ix_ >= " + len + ") ix_ = 0; ");
+        if (A(0).type.base == Base::String || A(0).type.base == Base::Int)
+            w("  " + R(op.args[0]) + "[ix_] = " + R(op.args[2]) + "; }");
+        else
+            w("  assign(" + R(op.args[0]) + "[ix_], " + R(op.args[2]) + "); }");
+    } else if (n == "arraylength") {
+        need(2);
+        w(R(op.args[0]) + " = " + std::to_string(A(1).type.arraylen) + ";");
+    } else if (n == "sincos") {
+        need(3);
+        bool dv = (A(1).has_derivs || A(2).has_derivs) && A(0).has_derivs;
+        for (int k = 0; k < A(0).type.ncomp(); ++k) {
+            std::string ks = std::to_string(k);
+            w("{ auto x_ = " + comp(op.args[0], k, dv) + "; setc(" + R(op.args[1]) + ", " + ks + ", o_sin(x_)); setc("
+              + R(op.args[2]) + ", " + ks + ", o_cos(x_)); }");
+        }
+    } else if (n == "dot" || n == "cross" || n == "length" || n == "distance" || n == "normalize") {
+        bool dv = false;
+        if (A(0).has_derivs)
+            for (size_t a = 1; a < op.args.size(); ++a)
+                dv |= A((int)a).has_derivs;
+        std::string args;
+        for (size_t a = 1; a < op.args.size(); ++a) {
+            std::string e = R(op.args[a]);
+            if (A((int)a).has_derivs && !dv)
+                e = "nd(" + e + ")";
+            args += (a > 1 ? ", " : "") + e;
+        }
+        w("assign(" + R(op.args[0]) + ", o_" + n + "(" + args + "));");
+    } else if (n == "Dx" || n == "Dy" || n == "filterwidth") {
+        need(2);
+        w("assign(" + R(op.args[0]) + ", o_" + n + "(" + R(op.args[1]) + "));");
+    } else if (n == "Dz") {
+        need(2);
+        if (A(1).symtype == SymType::Global && A(1).name == "P") {
+            g.globals_read.insert(B200_SG_dPdz);
+            w("assign(" + R(op.args[0]) + ", sg.dPdz);");
+        } else
+            w("assign(" + R(op.args[0]) + ", 0.0f);");
+    } else if (n == "area") {
+        need(2);
+        w("assign(" + R(op.args[0]) + ", o_area(" + R(op.args[1]) + "));");
+    } else if (n == "calculatenormal") {
+        need(2);
+        g.globals_read.insert(B200_SG_flipHandedness);
+        w("assign(" + R(op.args[0]) + ", o_calculatenormal(" + R(op.args[1]) + ", sg.flipHandedness != 0));");
+    } else if (n == "isnan") {
+        w(R(op.args[0]) + " = isnan(" + comp(op.args[1], 0, false) + ") ? 1 : 0;");
+    } else if (n == "isinf") {
+        w(R(op.args[0]) + " = isinf(" + comp(op.args[1], 0, false) + ") ? 1 : 0;");
+    } else if (n == "isfinite") {
+        w(R(op.args[0]) + " = finitef(" + comp(op.args[1], 0, false) + ") ? 1 : 0;");
+    } else if (n == "surfacearea") {
+        g.globals_read.insert(B200_SG_surfacearea);
+        w("assign(" + R(op.args[0]) + ", sg.surfacearea);");
+    } else if (n == "backfacing") {
+        g.globals_read.insert(B200_SG_backfacing);
+        w(R(op.args[0]) + " = sg.backfacing;");
+    } else if (n == "raytype") {
+        need(2);
+        if (!A(1).const_value())
+            unsupported("raytype() of a non-constant name");
+        g.globals_read.insert(B200_SG_raytype);
+        w(R(op.args[0]) + " = (sg.raytype & " + std::to_string(raytype_bit(A(1).svals.empty() ? "" : A(1).svals[0]))
+          + ") != 0;");
+    } else if (n == "isconnected") {
+        need(2);
+        w(R(op.args[0]) + " = " + std::to_string(A(1).conn_layer >= 0 ? 1 : (A(1).connected_down ? 2 : 0)) + ";");
+    } else if (n == "isconstant") {
+        need(2);
+        w(R(op.args[0]) + " = " + std::to_string(A(1).is_const() ? 1 : 0) + ";");
+    } else if (n == "hash") {
+        size_t nin = op.args.size() - 1;
+        std::string e;
+        if (nin == 1 && A(1).type.base == Base::Int)
+            e = "hash_i(" + R(op.args[1]) + ")";
+        else if (nin == 1 && A(1).type.base == Base::Float)
+            e = "hash_f(" + comp(op.args[1], 0, false) + ")";
+        else if (nin == 2 && A(1).type.base == Base::Float)
+            e = "hash_ff(" + comp(op.args[1], 0, false) + ", " + comp(op.args[2], 0, false) + ")";
+        else if (nin == 1)
+            e = "hash_v(nd(" + R(op.args[1]) + "))";
+        else
+            e = "hash_vf(nd(" + R(op.args[1]) + "), " + comp(op.args[2], 0, false) + ")";
+        w(R(op.args[0]) + " = " + e + ";");
+    } else if (n == "noise" || n == "snoise" || n == "cellnoise" || n == "hashnoise") {
+        op_noise(op, false);
+    } else if (n == "pnoise" || n == "psnoise" || n == "pcellnoise" || n == "phashnoise") {
+        op_noise(op, true);
+    } else if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
+        // Device-side journal is a "next" row: the op has no
+        // effect on shading results, so it is dropped with a recorded warning.
+        std::string msg = "op '" + n + "' ignored on device (no journal yet) in layer '" + L->layername + "'";
+        bool dup = false;
+        for (auto& s : g.warnings)
+            dup |= (s == msg);
+        if (!dup)
+            g.warnings.push_back(msg);
+    } else {
+        unsupported("op '" + n + "' is not implemented");
+    }
+}
+
+void
+Gen::gen_layer(int layer)
+{
+    L                    = &g.layers[layer];
+    li                   = layer;
+    Master& m            = L->m;
+    std::string k        = std::to_string(layer);
+    int nlayers          = (int)g.layers.size();
+    ind                  = 0;
+    w("static __device__ __forceinline__ void layer_" + k + "(SG& sg, GD& gd, const B200Launch& L)");
+    w("{");
+    ind = 1;
+    w("gd.ran |= " + std::to_string(1u << layer) + "u;");
+    for (Symbol& s : m.syms) {
+        if (s.symtype == SymType::Local || s.symtype == SymType::Temp) {
+            std::string arr = s.type.arraylen ? "[" + std::to_string(s.type.arraylen) + "]" : "";
+            w(ctype(s) + " " + ident(s.name) + arr + (s.type.arraylen ? " = {};" : " = {};"));
+        } else if (s.is_const() && s.type.arraylen) {
+            std::string init;
+            for (auto& v : initvals(s))
+                init += (init.empty() ? "" : ", ") + v;
+            w("const " + ctype(s) + " K_" + ident(s.name) + "[" + std::to_string(s.type.arraylen) + "] = {" + init + "};");
+        }
+    }
+    // the group entry runs earlier non-lazy layers unconditionally
+    // (llvm_instance.cpp:1693-1720)
+    if (layer == nlayers - 1)
+        for (int e = 0; e < nlayers - 1; ++e)
+            if (!g.layers[e].unused && !g.layers[e].lazy)
+                w("if (!(gd.ran & " + std::to_string(1u << e) + "u)) layer_" + std::to_string(e) + "(sg, gd, L);");
+    // parameter initialisation (llvm_instance.cpp:703-1000, 1666-1690)
+    for (size_t si = 0; si < m.syms.size(); ++si) {
+        Symbol& s = m.syms[si];
+        if (!s.is_param() || s.conn_layer >= 0)
+            continue;
+        std::vector<std::string> vals = initvals(s);
+        std::string r                 = ref(layer, s);
+        if (s.type.arraylen)
+            for (size_t i = 0; i < vals.size(); ++i)
+                w(r + "[" + std::to_string(i) + "] = " + vals[i] + ";");
+        else
+            w(r + " = " + vals[0] + ";");
+        auto mi = m.methods.find(s.name);
+        if (s.initexpr && mi != m.methods.end()) {
+            ensured.clear();
+            emit_block(mi->second.first, mi->second.second, nullptr);
+        }
+    }
+    ensured.clear();
+    auto mi = m.methods.find("___main___");
+    if (mi != m.methods.end())
+        emit_block(mi->second.first, mi->second.second, nullptr);
+    w("layer_end:;");
+    // hand results to downstream layers (llvm_instance.cpp:1738-1802)
+    for (const Connection& c : g.connections)
+        if (c.srclayer == layer && !g.layers[c.dstlayer].unused)
+            emit_copy(c.dstlayer, g.layers[c.dstlayer].m.syms[c.dstsym], layer, m.syms[c.srcsym]);
+    // renderer outputs: output_base + offset + stride*shadeindex
+    // (llvm_instance.cpp:1807-1848)
+    for (size_t k = 0; k < g.outputs.size(); ++k) {
+        auto& o2 = g.outputs[k];
+        if (o2.first != layer)
+            continue;
+        Symbol& s = m.syms[o2.second];
+        w(std::string(s.out.derivs ? "wrd" : "wr") + "(outp(L, sg, " + std::to_string(k) + ", "
+          + std::to_string(s.out.offset) + "LL, " + std::to_string(s.out.stride) + "LL), " + ref(layer, s) + ");");
+    }
+    ind = 0;
+    w("}");
+}
+
+// Kernel prologue/epilogue shared by every group.  Loads touch only the
+// ShaderGlobals planes the group reads; uniform fields come from the launch
+// block (constant bank).
+const char* PRELUDE = R"CUDA(
+using namespace osld;
+
+struct B200Launch {
+    const float* varying[%NFIELDS%];
+    float uniform[%NFIELDS%][4];
+    long long plane_stride;
+    const int* shadeindex;
+    void* output_base;
+    const void* userdata_base;
+    long long npoints;
+    long long shadeindex_base;   // added to the point index when shadeindex == NULL
+    long long out_adjust[%MAXOUT%];   // per-output byte rebase (host staging path)
+};
+
+__device__ __forceinline__ float ldf(const B200Launch& L, int f, int c, long long i)
+{
+    const float* p = L.varying[f];
+    return p ? __ldg(p + c * L.plane_stride + i) : L.uniform[f][c];
+}
+__device__ __forceinline__ V3 ldv(const B200Launch& L, int f, long long i)
+{
+    return mkv(ldf(L, f, 0, i), ldf(L, f, 1, i), ldf(L, f, 2, i));
+}
+__device__ __forceinline__ int ldi(const B200Launch& L, int f, long long i)
+{
+    const int* p = (const int*)L.varying[f];
+    return p ? __ldg(p + i) : __float_as_int(L.uniform[f][0]);
+}
+)CUDA";
+
+const char* OUTPUT_HELPERS = R"CUDA(
+__device__ __forceinline__ float* outp(const B200Launch& L, const SG& sg, int k, long long offset, long long stride)
+{
+    return (float*)((char*)L.output_base + offset + L.out_adjust[k] + stride * (long long)sg.shadeindex);
+}
+__device__ __forceinline__ void wr(float* p, float v) { p[0] = v; }
+__device__ __forceinline__ void wr(float* p, int v) { ((int*)p)[0] = v; }
+__device__ __forceinline__ void wr(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+__device__ __forceinline__ void wr(float* p, Df v) { p[0] = v.val; }
+__device__ __forceinline__ void wr(float* p, const Dv& v) { wr(p, v.val); }
+__device__ __forceinline__ void wrd(float* p, float v) { p[0] = v; p[1] = 0.0f; p[2] = 0.0f; }
+__device__ __forceinline__ void wrd(float* p, Df v) { p[0] = v.val; p[1] = v.dx; p[2] = v.dy; }
+__device__ __forceinline__ void wrd(float* p, V3 v) { wr(p, v); for (int i = 3; i < 9; ++i) p[i] = 0.0f; }
+__device__ __forceinline__ void wrd(float* p, const Dv& v) { wr(p, v.val); wr(p + 3, v.dx); wr(p + 6, v.dy); }
+)CUDA";
+
+std::string
+Gen::run()
+{
+    int nlayers = (int)g.layers.size();
+    if (nlayers > 32)
+        throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
+    // layer bodies first (they record which globals are read)
+    std::ostringstream bodies;
+    std::string gd = "struct GD {\n    unsigned ran;\n";
+    for (int l = 0; l < nlayers; ++l) {
+        if (g.layers[l].unused)
+            continue;
+        L  = &g.layers[l];
+        li = l;
+        for (Symbol& s : g.layers[l].m.syms)
+            if (s.is_param()) {
+                std::string arr = s.type.arraylen ? "[" + std::to_string(s.type.arraylen) + "]" : "";
+                gd += "    " + ctype(s) + " L" + std::to_string(l) + "_" + ident(s.name) + arr + ";\n";
+            }
+    }
+    gd += "};\n";
+    for (int l = 0; l < nlayers; ++l)
+        if (!g.layers[l].unused)
+            o << "static __device__ __forceinline__ void layer_" << l << "(SG& sg, GD& gd, const B200Launch& L);\n";
+    for (int l = 0; l < nlayers; ++l)
+        if (!g.layers[l].unused)
+            gen_layer(l);
+    std::string layers_src = o.str();
+
+    // SG holds only what is read
+    auto rd = [&](int f) { return g.globals_read.count(f) != 0; };
+    std::ostringstream sg, ld;
+    sg << "struct SG {\n    int shadeindex;\n";
+    struct TD {
+        const char* name;
+        int f, dx, dy;
+    };
+    const TD triples_d[] = { { "P", B200_SG_P, B200_SG_dPdx, B200_SG_dPdy },
+                             { "I", B200_SG_I, B200_SG_dIdx, B200_SG_dIdy },
+                             { "Ps", B200_SG_Ps, B200_SG_dPsdx, B200_SG_dPsdy } };
+    for (const TD& t : triples_d) {
+        if (!rd(t.f))
+            continue;
+        sg << "    V3 " << t.name << ";\n";
+        ld << "        sg." << t.name << " = ldv(L, " << t.f << ", i);\n";
+        if (rd(t.dx)) {
+            sg << "    V3 " << t.name << "_dx, " << t.name << "_dy;\n";
+            sg << "    __device__ __forceinline__ Dv " << t.name << "_d() const { return mkdv(" << t.name << ", "
+               << t.name << "_dx, " << t.name << "_dy); }\n";
+            ld << "        sg." << t.name << "_dx = ldv(L, " << t.dx << ", i);\n";
+            ld << "        sg." << t.name << "_dy = ldv(L, " << t.dy << ", i);\n";
+        }
+    }
+    const TD scal_d[] = { { "u", B200_SG_u, B200_SG_dudx, B200_SG_dudy }, { "v", B200_SG_v, B200_SG_dvdx, B200_SG_dvdy } };
+    for (const TD& t : scal_d) {
+        if (!rd(t.f))
+            continue;
+        sg << "    float " << t.name << ";\n";
+        ld << "        sg." << t.name << " = ldf(L, " << t.f << ", 0, i);\n";
+        if (rd(t.dx)) {
+            sg << "    float " << t.name << "_dx, " << t.name << "_dy;\n";
+            sg << "    __device__ __forceinline__ Df " << t.name << "_d() const { return mkd(" << t.name << ", "
+               << t.name << "_dx, " << t.name << "_dy); }\n";
+            ld << "        sg." << t.name << "_dx = ldf(L, " << t.dx << ", 0, i);\n";
+            ld << "        sg." << t.name << "_dy = ldf(L, " << t.dy << ", 0, i);\n";
+        }
+    }
+    const TD plain3[] = { { "N", B200_SG_N, -1, -1 },       { "Ng", B200_SG_Ng, -1, -1 },
+                          { "dPdu", B200_SG_dPdu, -1, -1 }, { "dPdv", B200_SG_dPdv, -1, -1 },
+                          { "dPdtime", B200_SG_dPdtime, -1, -1 }, { "dPdz", B200_SG_dPdz, -1, -1 } };
+    for (const TD& t : plain3)
+        if (rd(t.f)) {
+            sg << "    V3 " << t.name << ";\n";
+            ld << "        sg." << t.name << " = ldv(L, " << t.f << ", i);\n";
+        }
+    const TD plain1[] = { { "time", B200_SG_time, -1, -1 }, { "dtime", B200_SG_dtime, -1, -1 },
+                          { "surfacearea", B200_SG_surfacearea, -1, -1 } };
+    for (const TD& t : plain1)
+        if (rd(t.f)) {
+            sg << "    float " << t.name << ";\n";
+            ld << "        sg." << t.name << " = ldf(L, " << t.f << ", 0, i);\n";
+        }
+    const TD ints[] = { { "raytype", B200_SG_raytype, -1, -1 }, { "flipHandedness", B200_SG_flipHandedness, -1, -1 },
+                        { "backfacing", B200_SG_backfacing, -1, -1 } };
+    for (const TD& t : ints)
+        if (rd(t.f)) {
+            sg << "    int " << t.name << ";\n";
+            ld << "        sg." << t.name << " = ldi(L, " << t.f << ", i);\n";
+        }
+    sg << "};\n";
+
+    std::string prelude = PRELUDE;
+    for (size_t p; (p = prelude.find("%NFIELDS%")) != std::string::npos;)
+        prelude.replace(p, 9, std::to_string((int)B200_SG_NFIELDS));
+    for (size_t p; (p = prelude.find("%MAXOUT%")) != std::string::npos;)
+        prelude.replace(p, 8, std::to_string(B200_MAX_OUTPUTS));
+    if ((int)g.outputs.size() > B200_MAX_OUTPUTS)
+        throw std::runtime_error("B200 back end: too many renderer outputs in one group");
+
+    std::ostringstream out;
+    out << "// generated by libosl_b200 for shader group '" << g.name << "'\n";
+    out << "#include \"osl_b200_device.cuh\"\n";
+    out << prelude << sg.str() << OUTPUT_HELPERS << gd << layers_src;
+    out << "extern \"C\" __global__ void __launch_bounds__(%BLOCK%) osl_b200_group_kernel(const __grid_constant__ B200Launch L)\n{\n";
+    out << "    const long long stride_ = (long long)gridDim.x * blockDim.x;\n";
+    out << "    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L.npoints; i += stride_) {\n";
+    out << "        SG sg;\n        GD gd;\n        gd.ran = 0u;\n";
+    out << "        sg.shadeindex = L.shadeindex ? __ldg(L.shadeindex + i) : (int)(i + L.shadeindex_base);\n";
+    out << ld.str();
+    out << "        layer_" << (nlayers - 1) << "(sg, gd, L);\n";
+    out << "    }\n}\n";
+    return out.str();
+}
+
+}  // namespace
+
+std::string
+generate_cuda(Group& g)
+{
+    return Gen(g).run();
+}
+
+}  // namespace oslb200

@@ -1,0 +1,131 @@
+// osl_b200_group.h — host-side group IR for the B200 back end (product code).
+//
+// Plays the role of the reference's ShaderMaster / ShaderInstance / ShaderGroup
+// (src/liboslexec/oslexec_pvt.h:409,1231,1777) for exactly what the back end
+// consumes: parsed .oso symbols and ops, instance parameter values,
+// connections, renderer outputs (SymLocationDesc, include/OSL/oslexec.h:69-105)
+// and the three optimizer facts the code generator needs — unused(),
+// run_lazily(), has_derivs().
+#pragma once
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace oslb200 {
+
+enum class Base { Int, Float, String, Color, Point, Vector, Normal, Matrix, Closure, Void };
+
+struct TypeSpec {
+    Base base   = Base::Float;
+    int arraylen = 0;  // 0: not an array
+    bool is_triple() const
+    {
+        return base == Base::Color || base == Base::Point || base == Base::Vector
+               || base == Base::Normal;
+    }
+    bool is_float_based() const { return base == Base::Float || base == Base::Matrix || is_triple(); }
+    int ncomp() const { return is_triple() ? 3 : (base == Base::Matrix ? 16 : 1); }
+};
+
+enum class SymType { Param, OutputParam, Local, Temp, Global, Const };
+
+struct OutputLoc {
+    bool placed      = false;
+    long long offset = 0, stride = 0;
+    bool derivs      = false;
+};
+
+struct Symbol {
+    std::string name;
+    SymType symtype = SymType::Local;
+    TypeSpec type;
+    std::vector<float> fvals;
+    std::vector<int> ivals;
+    std::vector<std::string> svals;
+    bool initexpr       = false;
+    bool has_derivs     = false;
+    bool written        = false;
+    bool connected_down = false;
+    int conn_layer      = -1;  // upstream layer feeding this param, or -1
+    int conn_sym        = -1;  // symbol index in that layer
+    OutputLoc out;
+    bool is_const() const { return symtype == SymType::Const; }
+    bool is_param() const { return symtype == SymType::Param || symtype == SymType::OutputParam; }
+    // would the runtime optimizer have folded this to a constant?
+    bool const_value() const
+    {
+        return is_const() || (symtype == SymType::Param && conn_layer < 0 && !initexpr && !written);
+    }
+};
+
+struct Opcode {
+    std::string name;
+    std::vector<int> args;  // symbol indices
+    std::vector<int> jumps;
+    std::string rw;
+    std::vector<int> derivs;  // arg indices whose derivatives the op takes
+    bool reads(int i) const { return rw[i] == 'r' || rw[i] == 'W'; }
+    bool writes(int i) const { return rw[i] == 'w' || rw[i] == 'W'; }
+};
+
+struct Master {
+    std::string shadertype, shadername;
+    std::vector<Symbol> syms;
+    std::map<std::string, int> byname;
+    std::vector<Opcode> ops;
+    std::map<std::string, std::pair<int, int>> methods;  // code sections
+    int find(const std::string& n) const
+    {
+        auto it = byname.find(n);
+        return it == byname.end() ? -1 : it->second;
+    }
+};
+
+// Parse OSO 1.00 text (grammar: src/liboslexec/osogram.y:88-318).  Throws
+// std::runtime_error with a line-numbered message on malformed input.
+Master parse_oso(const std::string& text);
+
+struct ParamValue {
+    std::string name;
+    std::vector<float> fvals;
+    std::vector<int> ivals;
+    std::vector<std::string> svals;
+};
+
+struct Layer {
+    Master m;
+    std::string layername;
+    bool lazy   = false;
+    bool unused = false;
+};
+
+struct Connection {
+    int srclayer, srcsym, dstlayer, dstsym;
+};
+
+struct Group {
+    std::string name;
+    std::vector<Layer> layers;
+    std::vector<Connection> connections;
+    std::vector<std::pair<int, int>> outputs;  // (layer, sym) with out.placed
+    std::vector<std::string> strings;          // interned string table (id = index)
+    std::vector<std::string> warnings;
+    std::set<int> globals_read;                // b200_sg_field ids the kernel loads
+    bool fma = true;                           // allow FMA contraction in generated code
+
+    int layer_index(const std::string& n) const;
+    void add_layer(const std::string& oso_text, const std::string& layername,
+                   const std::vector<ParamValue>& params);
+    void connect(const std::string& sl, const std::string& sp, const std::string& dl,
+                 const std::string& dp);
+    void add_output(const std::string& name, long long offset, long long stride, bool derivs);
+    void finalize();  // unused/lazy/derivs analysis
+    int intern(const std::string& s);
+};
+
+// Emit CUDA C++ for the whole group (kernel name: osl_b200_group_kernel).
+std::string generate_cuda(Group& g);
+
+}  // namespace oslb200

@@ -1,0 +1,688 @@
+// osl_b200_cabi.cu — C ABI, NVRTC JIT, kernel launch and host<->device staging
+// for libosl_b200.so (product code).
+//
+// Stands in for the reference's JIT + execute plumbing:
+//   BackendLLVM::run / JIT            src/liboslexec/llvm_instance.cpp:2083-2572
+//   ShadingContext::execute*          src/liboslexec/context.cpp:92-263, 268-440
+//   BatchedExecutor<W>::execute       src/include/OSL/oslexec.h:982-1033
+// The generated CUDA text is compiled with NVRTC straight to an sm_100a cubin
+// (no PTX JIT at load time), loaded through the driver API (resolved with
+// dlopen so the library itself loads on machines without a GPU) and launched
+// with one thread per shading point.
+#include "../../include/osl_b200.h"
+#include "host/osl_b200_group.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "device/osl_b200_device.cuh"
+
+extern const char* osl_b200_device_source;  // device header text (generated at build)
+
+using namespace oslb200;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches { 0 };
+
+int
+fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+// ---- driver API via dlopen ---------------------------------------------------
+typedef int CUresult_;
+typedef void* CUmodule_;
+typedef void* CUfunction_;
+struct Driver {
+    void* lib = nullptr;
+    CUresult_ (*cuInit)(unsigned)                                                          = nullptr;
+    CUresult_ (*cuModuleLoadData)(CUmodule_*, const void*)                                 = nullptr;
+    CUresult_ (*cuModuleUnload)(CUmodule_)                                                 = nullptr;
+    CUresult_ (*cuModuleGetFunction)(CUfunction_*, CUmodule_, const char*)                 = nullptr;
+    CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                unsigned, void*, void**, void**)                           = nullptr;
+    CUresult_ (*cuGetErrorString)(CUresult_, const char**)                                 = nullptr;
+    bool ok = false;
+    std::string why;
+};
+Driver&
+driver()
+{
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        d.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!d.lib)
+            d.lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!d.lib) {
+            d.why = "libcuda.so.1 not found: no NVIDIA driver on this machine";
+            return;
+        }
+#define LOADSYM(n)                                                   \
+    *(void**)(&d.n) = dlsym(d.lib, #n);                              \
+    if (!d.n) {                                                      \
+        d.why = std::string("libcuda is missing symbol ") + #n;     \
+        return;                                                      \
+    }
+        LOADSYM(cuInit)
+        LOADSYM(cuModuleLoadData)
+        LOADSYM(cuModuleUnload)
+        LOADSYM(cuModuleGetFunction)
+        LOADSYM(cuLaunchKernel)
+        LOADSYM(cuGetErrorString)
+#undef LOADSYM
+        if (d.cuInit(0) != 0) {
+            d.why = "cuInit failed";
+            return;
+        }
+        d.ok = true;
+    });
+    return d;
+}
+std::string
+cu_err(CUresult_ r)
+{
+    const char* s = nullptr;
+    if (driver().cuGetErrorString)
+        driver().cuGetErrorString(r, &s);
+    return s ? s : ("CUDA driver error " + std::to_string(r));
+}
+
+struct LaunchBlock {  // must match B200Launch in the generated code
+    const float* varying[B200_SG_NFIELDS];
+    float uniform[B200_SG_NFIELDS][4];
+    long long plane_stride;
+    const int* shadeindex;
+    void* output_base;
+    const void* userdata_base;
+    long long npoints;
+    long long shadeindex_base;
+    long long out_adjust[B200_MAX_OUTPUTS];
+};
+
+}  // namespace
+
+struct b200_group {
+    Group g;
+    std::string source;
+    std::vector<char> cubin;
+    int block = 256;
+    std::mutex mu;
+    std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
+    int sm_count[64] = { 0 };
+    // staging buffers for execute_host (per group, grown on demand)
+    struct Stage {
+        int device       = -1;
+        char* d_in       = nullptr;
+        char* d_out      = nullptr;
+        size_t in_bytes  = 0, out_bytes = 0;
+        cudaStream_t streams[3] = { nullptr, nullptr, nullptr };
+    } stage;
+};
+
+static std::map<std::string, std::string>
+parse_options(const char* s)
+{
+    std::map<std::string, std::string> m;
+    if (!s)
+        return m;
+    std::istringstream in(s);
+    std::string kv;
+    while (std::getline(in, kv, ',')) {
+        size_t e = kv.find('=');
+        if (e == std::string::npos)
+            m[kv] = "1";
+        else
+            m[kv.substr(0, e)] = kv.substr(e + 1);
+    }
+    return m;
+}
+
+static int
+nvrtc_compile(b200_group* G, std::string& log)
+{
+    std::string src = G->source;
+    for (size_t p; (p = src.find("%BLOCK%")) != std::string::npos;)
+        src.replace(p, 7, std::to_string(G->block));
+    G->source = src;
+    nvrtcProgram prog;
+    const char* hdr_names[] = { "osl_b200_device.cuh" };
+    const char* hdr_srcs[]  = { osl_b200_device_source };
+    if (nvrtcCreateProgram(&prog, src.c_str(), "osl_b200_group.cu", 1, hdr_srcs, hdr_names) != NVRTC_SUCCESS)
+        return fail(B200_ERR_COMPILE, "nvrtcCreateProgram failed");
+    std::vector<const char*> opts = { "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
+                                      "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+                                      "-default-device" };
+    opts.push_back(G->g.fma ? "--fmad=true" : "--fmad=false");
+    nvrtcResult r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    size_t logsz  = 0;
+    nvrtcGetProgramLogSize(prog, &logsz);
+    if (logsz > 1) {
+        log.resize(logsz);
+        nvrtcGetProgramLog(prog, &log[0]);
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(B200_ERR_COMPILE, "NVRTC: " + std::string(nvrtcGetErrorString(r)) + "\n" + log);
+    }
+    size_t sz = 0;
+    if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(B200_ERR_COMPILE, "NVRTC produced no cubin");
+    }
+    G->cubin.resize(sz);
+    nvrtcGetCUBIN(prog, G->cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return B200_OK;
+}
+
+extern "C" {
+
+int
+b200_abi_version(void)
+{
+    return OSL_B200_ABI_VERSION;
+}
+const char*
+b200_last_error(void)
+{
+    return g_err.c_str();
+}
+long long
+b200_launch_count(void)
+{
+    return g_launches.load();
+}
+
+int
+b200_group_compile(const b200_group_desc* desc, b200_group** out)
+{
+    if (!desc || !out || desc->nlayers <= 0 || !desc->layers)
+        return fail(B200_ERR_INVALID, "b200_group_compile: null or empty group description");
+    *out = nullptr;
+    std::unique_ptr<b200_group> G(new b200_group);
+    try {
+        G->g.name = desc->name ? desc->name : "group";
+        auto opt  = parse_options(desc->options);
+        if (opt.count("fma"))
+            G->g.fma = atoi(opt["fma"].c_str()) != 0;
+        if (opt.count("block"))
+            G->block = atoi(opt["block"].c_str());
+        if (G->block < 32 || G->block > 1024 || (G->block % 32))
+            return fail(B200_ERR_INVALID, "option block must be a multiple of 32 in [32,1024]");
+        for (int i = 0; i < desc->nlayers; ++i) {
+            const b200_layer& l = desc->layers[i];
+            if (!l.oso_text || !l.layername)
+                return fail(B200_ERR_INVALID, "layer without oso text or name");
+            std::vector<ParamValue> pvs;
+            for (int p = 0; p < l.nparams; ++p) {
+                const b200_param& bp = l.params[p];
+                ParamValue pv;
+                pv.name = bp.name ? bp.name : "";
+                for (int k = 0; k < bp.nvalues; ++k) {
+                    if (bp.type == 0)
+                        pv.ivals.push_back(((const int*)bp.values)[k]);
+                    else if (bp.type == 1)
+                        pv.fvals.push_back(((const float*)bp.values)[k]);
+                    else if (bp.type == 2)
+                        pv.svals.push_back(((const char* const*)bp.values)[k]);
+                    else
+                        return fail(B200_ERR_INVALID, "bad parameter type code");
+                }
+                pvs.push_back(std::move(pv));
+            }
+            G->g.add_layer(l.oso_text, l.layername, pvs);
+        }
+        for (int i = 0; i < desc->nconnections; ++i) {
+            const b200_connection& c = desc->connections[i];
+            G->g.connect(c.srclayer, c.srcparam, c.dstlayer, c.dstparam);
+        }
+        for (int i = 0; i < desc->noutputs; ++i) {
+            const b200_symloc& s = desc->outputs[i];
+            G->g.add_output(s.name, s.offset, s.stride, s.derivs != 0);
+        }
+        G->g.finalize();
+        G->source = generate_cuda(G->g);
+    } catch (const std::exception& e) {
+        return fail(B200_ERR_COMPILE, e.what());
+    }
+    std::string log;
+    int rc = nvrtc_compile(G.get(), log);
+    if (rc != B200_OK)
+        return rc;
+    *out = G.release();
+    return B200_OK;
+}
+
+void
+b200_group_destroy(b200_group* g)
+{
+    if (!g)
+        return;
+    for (auto& kv : g->loaded)
+        if (driver().ok)
+            driver().cuModuleUnload(kv.second.first);
+    if (g->stage.d_in)
+        cudaFree(g->stage.d_in);
+    if (g->stage.d_out)
+        cudaFree(g->stage.d_out);
+    for (auto s : g->stage.streams)
+        if (s)
+            cudaStreamDestroy(s);
+    delete g;
+}
+
+const char*
+b200_group_cuda_source(const b200_group* g)
+{
+    return g ? g->source.c_str() : "";
+}
+const void*
+b200_group_cubin(const b200_group* g, long long* size)
+{
+    if (size)
+        *size = g ? (long long)g->cubin.size() : 0;
+    return g ? g->cubin.data() : nullptr;
+}
+int
+b200_group_num_warnings(const b200_group* g)
+{
+    return g ? (int)g->g.warnings.size() : 0;
+}
+const char*
+b200_group_warning(const b200_group* g, int i)
+{
+    return (g && i >= 0 && i < (int)g->g.warnings.size()) ? g->g.warnings[i].c_str() : "";
+}
+int
+b200_group_reads_global(const b200_group* g, int field)
+{
+    return (g && g->g.globals_read.count(field)) ? 1 : 0;
+}
+
+static int
+ensure_loaded(b200_group* g, int device, CUfunction_* fn)
+{
+    std::lock_guard<std::mutex> lock(g->mu);
+    auto it = g->loaded.find(device);
+    if (it != g->loaded.end()) {
+        *fn = it->second.second;
+        return B200_OK;
+    }
+    Driver& d = driver();
+    if (!d.ok)
+        return fail(B200_ERR_CUDA, "CUDA driver unavailable: " + d.why);
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess)
+        ce = cudaFree(0);  // make the primary context current
+    if (ce != cudaSuccess)
+        return fail(B200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    CUmodule_ mod;
+    CUresult_ r = d.cuModuleLoadData(&mod, g->cubin.data());
+    if (r != 0)
+        return fail(B200_ERR_CUDA, "cuModuleLoadData: " + cu_err(r));
+    CUfunction_ f;
+    r = d.cuModuleGetFunction(&f, mod, "osl_b200_group_kernel");
+    if (r != 0)
+        return fail(B200_ERR_CUDA, "cuModuleGetFunction: " + cu_err(r));
+    g->loaded[device] = { mod, f };
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (device < 64)
+        g->sm_count[device] = sms;
+    *fn = f;
+    return B200_OK;
+}
+
+static int
+launch_group(b200_group* g, int device, void* stream, long long npoints, const b200_globals* sg,
+             const int* shadeindex, const void* userdata_base, void* output_base, long long sidx_base,
+             const long long* out_adjust)
+{
+    CUfunction_ fn;
+    int rc = ensure_loaded(g, device, &fn);
+    if (rc != B200_OK)
+        return rc;
+    LaunchBlock L;
+    memcpy(L.varying, sg->varying, sizeof L.varying);
+    memcpy(L.uniform, sg->uniform, sizeof L.uniform);
+    L.plane_stride    = sg->plane_stride;
+    L.shadeindex      = shadeindex;
+    L.output_base     = output_base;
+    L.userdata_base   = userdata_base;
+    L.npoints         = npoints;
+    L.shadeindex_base = sidx_base;
+    for (int k = 0; k < B200_MAX_OUTPUTS; ++k)
+        L.out_adjust[k] = out_adjust ? out_adjust[k] : 0;
+    int sms = (device >= 0 && device < 64 && g->sm_count[device]) ? g->sm_count[device] : 148;
+    // grid: cover the range, capped at a whole number of resident waves
+    long long want = (npoints + g->block - 1) / g->block;
+    long long cap  = (long long)sms * 32;
+    unsigned grid  = (unsigned)(want < cap ? want : cap);
+    void* args[]   = { &L };
+    CUresult_ r    = driver().cuLaunchKernel(fn, grid, 1, 1, (unsigned)g->block, 1, 1, 0, stream, args, nullptr);
+    if (r != 0)
+        return fail(B200_ERR_CUDA, "cuLaunchKernel: " + cu_err(r));
+    g_launches.fetch_add(1);
+    return B200_OK;
+}
+
+int
+b200_group_execute(b200_group* g, int device, void* stream, long long npoints, const b200_globals* sg,
+                   const int* shadeindex, const void* userdata_base, void* output_base)
+{
+    if (!g || !sg || npoints < 0)
+        return fail(B200_ERR_INVALID, "b200_group_execute: bad arguments");
+    if (npoints == 0)
+        return B200_OK;
+    return launch_group(g, device, stream, npoints, sg, shadeindex, userdata_base, output_base, 0, nullptr);
+}
+
+// Host-pointer path: stage only the planes the kernel reads, pipelined in
+// chunks over three streams so H2D, kernel and D2H overlap.
+int
+b200_group_execute_host(b200_group* g, int device, long long npoints, const b200_globals* sg, void* output_base)
+{
+    if (!g || !sg || npoints < 0)
+        return fail(B200_ERR_INVALID, "b200_group_execute_host: bad arguments");
+    if (npoints == 0)
+        return B200_OK;
+    CUfunction_ fn;
+    int rc = ensure_loaded(g, device, &fn);
+    if (rc != B200_OK)
+        return rc;
+    cudaSetDevice(device);
+    struct Plane {
+        int field, comps;
+    };
+    std::vector<Plane> planes;
+    static const bool is_triple[B200_SG_NFIELDS]
+        = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0 };
+    size_t in_bpp = 0;
+    for (int f = 0; f < B200_SG_NFIELDS; ++f)
+        if (sg->varying[f] && g->g.globals_read.count(f)) {
+            planes.push_back({ f, is_triple[f] ? 3 : 1 });
+            in_bpp += 4 * (is_triple[f] ? 3 : 1);
+        }
+    // cluster outputs whose records interleave (same stride, offsets within one stride)
+    struct Cluster {
+        long long stride, lo, hi;  // byte extent of one record: [lo, hi)
+        std::vector<int> outs;
+    };
+    std::vector<Cluster> clusters;
+    for (size_t k = 0; k < g->g.outputs.size(); ++k) {
+        const Symbol& s = g->g.layers[g->g.outputs[k].first].m.syms[g->g.outputs[k].second];
+        long long size  = 4LL * s.type.ncomp() * (s.out.derivs ? 3 : 1);
+        if (s.out.stride < size)
+            return fail(B200_ERR_INVALID, "execute_host: output stride smaller than the value size");
+        bool placed = false;
+        for (Cluster& c : clusters) {
+            long long lo = c.lo < s.out.offset ? c.lo : s.out.offset;
+            long long hi = c.hi > s.out.offset + size ? c.hi : s.out.offset + size;
+            if (c.stride == s.out.stride && hi - lo <= c.stride) {
+                c.lo = lo;
+                c.hi = hi;
+                c.outs.push_back((int)k);
+                placed = true;
+                break;
+            }
+        }
+        if (!placed)
+            clusters.push_back({ s.out.stride, s.out.offset, s.out.offset + size, { (int)k } });
+    }
+    size_t out_bpp = 0;
+    for (const Cluster& c : clusters)
+        out_bpp += (size_t)c.stride;
+    if (!output_base && out_bpp)
+        return fail(B200_ERR_INVALID, "execute_host: group has outputs but output_base is null");
+    const long long CH    = 1 << 20;  // points per chunk
+    const int NS          = 3;
+    long long chunk       = npoints < CH ? npoints : CH;
+    b200_group::Stage& st = g->stage;
+    size_t need_in = (size_t)chunk * in_bpp * NS, need_out = (size_t)chunk * out_bpp * NS;
+    if (st.device != device || st.in_bytes < need_in || st.out_bytes < need_out) {
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+        st.d_in = st.d_out = nullptr;
+        if (need_in && cudaMalloc(&st.d_in, need_in) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "cudaMalloc(staging in) failed");
+        if (need_out && cudaMalloc(&st.d_out, need_out) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "cudaMalloc(staging out) failed");
+        st.in_bytes  = need_in;
+        st.out_bytes = need_out;
+        st.device    = device;
+        for (int s = 0; s < NS; ++s)
+            if (!st.streams[s])
+                cudaStreamCreateWithFlags(&st.streams[s], cudaStreamNonBlocking);
+    }
+    int slot = 0;
+    for (long long b = 0; b < npoints; b += chunk, slot = (slot + 1) % NS) {
+        long long n     = (npoints - b) < chunk ? (npoints - b) : chunk;
+        cudaStream_t s  = st.streams[slot];
+        char* din       = st.d_in + (size_t)slot * chunk * in_bpp;
+        char* dout      = st.d_out + (size_t)slot * chunk * out_bpp;
+        b200_globals dg = *sg;
+        dg.plane_stride = n;
+        size_t off      = 0;
+        for (const Plane& p : planes) {
+            dg.varying[p.field] = (const float*)(din + off);
+            for (int c = 0; c < p.comps; ++c) {
+                const float* src = sg->varying[p.field] + (size_t)c * sg->plane_stride + b;
+                cudaMemcpyAsync(din + off, src, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+                off += (size_t)n * 4;
+            }
+        }
+        for (int f = 0; f < B200_SG_NFIELDS; ++f)
+            if (sg->varying[f] && !g->g.globals_read.count(f))
+                dg.varying[f] = nullptr;
+        // kernel sees shadeindex = b + i; each cluster's records are rebased
+        // into a dense staging region:  addr = dout + S_c + (offset_k - lo_c) + stride*(sidx - b)
+        long long adjust[B200_MAX_OUTPUTS] = { 0 };
+        size_t region                      = 0;
+        for (const Cluster& c : clusters) {
+            for (int k : c.outs)
+                adjust[k] = (long long)region - c.lo - c.stride * b;
+            region += (size_t)n * c.stride;
+        }
+        rc = launch_group(g, device, s, n, &dg, nullptr, nullptr, dout, b, adjust);
+        if (rc != B200_OK)
+            return rc;
+        region = 0;
+        for (const Cluster& c : clusters) {
+            size_t bytes = (size_t)(n - 1) * c.stride + (size_t)(c.hi - c.lo);
+            cudaMemcpyAsync((char*)output_base + c.lo + c.stride * b, dout + region, bytes, cudaMemcpyDeviceToHost, s);
+            region += (size_t)n * c.stride;
+        }
+    }
+    for (int s = 0; s < NS; ++s)
+        cudaStreamSynchronize(st.streams[s]);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess)
+        return fail(B200_ERR_CUDA, std::string("execute_host: ") + cudaGetErrorString(ce));
+    return B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// AOT batch kernels of the device shadeop library (b200_shadeop_*)
+// ---------------------------------------------------------------------------
+namespace {
+using namespace osld;
+
+template<int KIND, int DIM, int NC, bool DERIV, bool PER>
+__global__ void __launch_bounds__(256)
+noise_kernel(long long n, const float* __restrict__ in, const float* __restrict__ period, float* __restrict__ out)
+{
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x[4];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+            x[d] = in[d * n + i];
+        if (KIND >= 2) {
+            if (PER) {
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    x[d] = pwrap(x[d], period[d]);
+            }
+            float r[3];
+            ihnoise<KIND == 2, DIM, NC>(r, x);
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                out[c * n + i] = r[c];
+            if (DERIV) {
+#pragma unroll
+                for (int c = 0; c < 2 * NC; ++c)
+                    out[(NC + c) * n + i] = 0.0f;
+            }
+        } else {
+            int per[4] = { 1, 1, 1, 1 };
+            if (PER) {
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    per[d] = iperiod(period[d]);
+            }
+            if (DERIV) {
+                Df xd[4], r[3];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    xd[d] = mkd(x[d], in[(DIM + d) * n + i], in[(2 * DIM + d) * n + i]);
+                perlin<Df, DIM, NC, KIND == 1, PER>(r, xd, per);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    out[c * n + i]            = r[c].val;
+                    out[(NC + c) * n + i]     = r[c].dx;
+                    out[(2 * NC + c) * n + i] = r[c].dy;
+                }
+            } else {
+                float r[3];
+                perlin<float, DIM, NC, KIND == 1, PER>(r, x, per);
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    out[c * n + i] = r[c];
+            }
+        }
+    }
+}
+
+template<int DIM>
+__global__ void __launch_bounds__(256) hash_kernel(long long n, const float* __restrict__ in, int* __restrict__ out)
+{
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x[4];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+            x[d] = in[d * n + i];
+        int h = DIM == 1 ? hash_f(x[0])
+                : DIM == 2 ? hash_ff(x[0], x[1])
+                : DIM == 3 ? hash_v(mkv(x[0], x[1], x[2]))
+                           : hash_vf(mkv(x[0], x[1], x[2]), x[3]);
+        out[i] = h;
+    }
+}
+
+template<int KIND, int DIM, int NC, bool DERIV>
+void
+launch_noise2(bool per, unsigned grid, cudaStream_t s, long long n, const float* in, const float* period, float* out)
+{
+    if (per)
+        noise_kernel<KIND, DIM, NC, DERIV, true><<<grid, 256, 0, s>>>(n, in, period, out);
+    else
+        noise_kernel<KIND, DIM, NC, DERIV, false><<<grid, 256, 0, s>>>(n, in, period, out);
+}
+template<int KIND, int DIM>
+void
+launch_noise1(int nc, bool deriv, bool per, unsigned grid, cudaStream_t s, long long n, const float* in,
+              const float* period, float* out)
+{
+    if (nc == 1 && !deriv) launch_noise2<KIND, DIM, 1, false>(per, grid, s, n, in, period, out);
+    else if (nc == 1) launch_noise2<KIND, DIM, 1, true>(per, grid, s, n, in, period, out);
+    else if (!deriv) launch_noise2<KIND, DIM, 3, false>(per, grid, s, n, in, period, out);
+    else launch_noise2<KIND, DIM, 3, true>(per, grid, s, n, in, period, out);
+}
+template<int KIND>
+void
+launch_noise0(int dim, int nc, bool deriv, bool per, unsigned grid, cudaStream_t s, long long n, const float* in,
+              const float* period, float* out)
+{
+    switch (dim) {
+    case 1: launch_noise1<KIND, 1>(nc, deriv, per, grid, s, n, in, period, out); break;
+    case 2: launch_noise1<KIND, 2>(nc, deriv, per, grid, s, n, in, period, out); break;
+    case 3: launch_noise1<KIND, 3>(nc, deriv, per, grid, s, n, in, period, out); break;
+    default: launch_noise1<KIND, 4>(nc, deriv, per, grid, s, n, in, period, out); break;
+    }
+}
+unsigned
+grid_for(long long n)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long want = (n + 255) / 256, cap = (long long)sms * 32;
+    return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+}  // namespace
+
+extern "C" int
+b200_shadeop_noise(int kind, int outdim, int indim, int derivs, int fma, long long n, const float* in,
+                   const float* period, float* out, void* stream)
+{
+    (void)fma;  // the AOT library is built strict (-fmad=false); generated groups choose per group
+    if (kind < 0 || kind > 3 || (outdim != 1 && outdim != 3) || indim < 1 || indim > 4 || n < 0 || !in || !out)
+        return fail(B200_ERR_INVALID, "b200_shadeop_noise: bad arguments");
+    if (n == 0)
+        return B200_OK;
+    unsigned grid  = grid_for(n);
+    cudaStream_t s = (cudaStream_t)stream;
+    bool per       = period != nullptr;
+    switch (kind) {
+    case 0: launch_noise0<0>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    case 1: launch_noise0<1>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    case 2: launch_noise0<2>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    default: launch_noise0<3>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(B200_ERR_CUDA, std::string("b200_shadeop_noise launch: ") + cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return B200_OK;
+}
+
+extern "C" int
+b200_shadeop_hash(int indim, long long n, const float* in, int* out, void* stream)
+{
+    if (indim < 1 || indim > 4 || n < 0 || !in || !out)
+        return fail(B200_ERR_INVALID, "b200_shadeop_hash: bad arguments");
+    if (n == 0)
+        return B200_OK;
+    unsigned grid  = grid_for(n);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (indim) {
+    case 1: hash_kernel<1><<<grid, 256, 0, s>>>(n, in, out); break;
+    case 2: hash_kernel<2><<<grid, 256, 0, s>>>(n, in, out); break;
+    case 3: hash_kernel<3><<<grid, 256, 0, s>>>(n, in, out); break;
+    default: hash_kernel<4><<<grid, 256, 0, s>>>(n, in, out); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(B200_ERR_CUDA, std::string("b200_shadeop_hash launch: ") + cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return B200_OK;
+}

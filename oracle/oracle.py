@@ -108,6 +108,61 @@ def make_launch(n, varying, uniform, output, shadeindex=None, keep=None):
     return L, keep
 
 
+_shadeops = None
+
+
+def build_shadeops():
+    """Compile oracle_shadeops.cpp -> oracle/_build/liboracle_shadeops.so"""
+    import subprocess
+    here = oso2cpp.HERE
+    bdir = os.path.join(here, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    so = os.path.join(bdir, "liboracle_shadeops.so")
+    srcs = [os.path.join(here, f) for f in ("oracle_shadeops.cpp", "osl_oracle.h", "osl_oracle_ops.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                            "-I", here, srcs[0], "-o", so + ".tmp"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle shadeops compile failed:\n" + r.stderr[:4000])
+        os.replace(so + ".tmp", so)
+    return so
+
+
+def shadeops():
+    global _shadeops
+    if _shadeops is None:
+        L = ctypes.CDLL(build_shadeops())
+        L.oracle_noise.argtypes = [ctypes.c_int] * 4 + [ctypes.c_longlong, ctypes.c_void_p,
+                                                       ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_hash.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
+        _shadeops = L
+    return _shadeops
+
+
+KINDS = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3}
+
+
+def noise(kind, outdim, inp, period=None, derivs=False):
+    """inp: float32 [indim*(3 if derivs else 1), n] planes -> [outdim*(3 if derivs else 1), n]"""
+    inp = np.ascontiguousarray(inp, np.float32)
+    rows, n = inp.shape
+    indim = rows // 3 if derivs else rows
+    out = np.zeros((outdim * (3 if derivs else 1), n), np.float32)
+    per = None if period is None else np.ascontiguousarray(period, np.float32)
+    rc = shadeops().oracle_noise(KINDS[kind], outdim, indim, 1 if derivs else 0, n, inp.ctypes.data,
+                                 None if per is None else per.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def hash_(inp):
+    inp = np.ascontiguousarray(inp, np.float32)
+    indim, n = inp.shape
+    out = np.zeros(n, np.int32)
+    shadeops().oracle_hash(indim, n, inp.ctypes.data, out.ctypes.data)
+    return out
+
+
 class OracleGroup:
     """layers: list of dict(oso=<text>, name=<layername>, params={...})"""
 

@@ -62,6 +62,17 @@ class OSym:
     def isconst(self):
         return self.symtype == "const"
 
+    @property
+    def constval(self):
+        """True when the runtime optimizer would have turned this symbol into
+        a constant: a real const, or a lockgeom param that is neither
+        connected, computed by init ops, nor written
+        (runtimeoptimize.cpp find_params_holding_globals / param->const)."""
+        if self.symtype == "const":
+            return True
+        return (self.symtype == "param" and self.connected_from is None
+                and not self.initexpr and not self.written)
+
 
 class OOp:
     __slots__ = ("name", "args", "jumps", "rw", "derivs", "method")
@@ -843,7 +854,7 @@ class Gen:
 
     def op_raytype(self, op):
         d, nm = op.args
-        if not nm.isconst:
+        if not nm.constval:
             raise NotImplementedError("raytype(non-constant)")
         self.w("%s = (sg.raytype & %d) != 0;" % (self.R(d), raytype_bit(nm.vals[0])))
 
@@ -879,7 +890,7 @@ class Gen:
         rest = A[1:]
         name = op.name
         if rest and rest[0].t.base == "string":
-            if not rest[0].isconst:
+            if not rest[0].constval:
                 raise NotImplementedError("noise with a non-constant name")
             name = rest[0].vals[0]
             rest = rest[1:]
@@ -935,7 +946,7 @@ class Gen:
     def op_printf(self, op):
         A = op.args
         fmt = A[0]
-        if not fmt.isconst:
+        if not fmt.constval:
             raise NotImplementedError("printf with non-constant format")
         self.emit_format(fmt.vals[0], A[1:])
 

@@ -1,0 +1,82 @@
+"""Shared test helpers: fixture loading, the standard testshade-style cases and
+image quantisation.  The CPU oracle is imported here (tests may use it)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def oso(name):
+    with open(os.path.join(GOLDEN, "oso", name + ".oso")) as f:
+        return f.read()
+
+
+def golden_image(name):
+    d = np.load(os.path.join(GOLDEN, "images", name + ".npz"))
+    return d["pixels"], int(d["step"]), tuple(int(x) for x in d["shape"])
+
+
+def golden_text(name):
+    with open(os.path.join(GOLDEN, "text", name + ".txt")) as f:
+        return f.read()
+
+
+def noise_vectors():
+    with open(os.path.join(GOLDEN, "noise_vectors.json")) as f:
+        return json.load(f)
+
+
+def quantize_u8(img):
+    """testshade -od uint8: OIIO float->uint8 is clamp(v,0,1)*255 + 0.5, truncated."""
+    return (np.clip(img, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+
+
+# testshade-style single-output image cases that have a reference golden image.
+# (testsuite/<name>/run.py: "-g R R -od uint8 -o Cout out.tif [-param ...] shader")
+IMAGE_CASES = {
+    "noise": dict(shader="noise_test", res=512, params={}),
+    "cellnoise": dict(shader="cellnoise_test", res=512, params={}),
+    "hashnoise": dict(shader="hashnoise_test", res=128, params={}),
+    "noise-cell": dict(shader="testnoise", res=512,
+                       params=dict(noisename="cell", offset=0.0, scale=1.0)),
+    "noise-perlin": dict(shader="testnoise", res=512, params=dict(noisename="perlin")),
+    "pnoise": dict(shader="pnoise_test", res=512, params={}),
+    "pnoise-cell": dict(shader="testpnoise", res=512,
+                        params=dict(noisename="cell", offset=0.0, scale=1.0)),
+    "pnoise-perlin": dict(shader="testpnoise", res=512, params=dict(noisename="perlin")),
+}
+
+
+def image_case_group(case):
+    c = IMAGE_CASES[case]
+    layers = [dict(oso=oso(c["shader"]), name="layer0", params=dict(c["params"]))]
+    outputs = [dict(name="Cout", offset=0, stride=12)]
+    return layers, outputs, c["res"]
+
+
+LAYERS_LAZY = dict(
+    layers=[("layers_lazy_a", "alayer"), ("layers_lazy_b", "blayer"), ("layers_lazy_c", "clayer")],
+    connections=[("alayer", "f_out", "clayer", "f_in"), ("alayer", "c_out", "clayer", "c_in"),
+                 ("blayer", "out", "clayer", "unused")])
+
+
+def layers_group(with_outputs=True, derivs=True):
+    """BASELINE config 2: the layers-lazy 3-layer group with alayer.f_out and
+    alayer.c_out as renderer outputs placed in one interleaved record
+    (val,dx,dy => 12 + 36 = 48 B/pt)."""
+    layers = [dict(oso=oso(s), name=n, params={}) for s, n in LAYERS_LAZY["layers"]]
+    outputs = []
+    if with_outputs:
+        if derivs:
+            outputs = [dict(name="alayer.f_out", offset=0, stride=48, derivs=True),
+                       dict(name="alayer.c_out", offset=12, stride=48, derivs=True)]
+        else:
+            outputs = [dict(name="alayer.f_out", offset=0, stride=16, derivs=False),
+                       dict(name="alayer.c_out", offset=4, stride=16, derivs=False)]
+    return layers, list(LAYERS_LAZY["connections"]), outputs

@@ -1,0 +1,113 @@
+#!/usr/bin/env python3
+"""Generate the committed test fixtures from the reference tree.
+
+Run in the build container (needs /root/reference; the GPU box does not have
+it).  Produces, under tests/golden/:
+
+  oso/<name>.oso        testsuite shaders compiled by tools/mini_oslc.py
+  images/<test>.npz     the reference's golden images (uint8, subsampled by
+                        STEP in x and y to keep the repository small; the
+                        sampling grid is stored in the file)
+  text/<test>.txt       the reference's golden text outputs
+  noise_vectors.json    known-answer vectors parsed out of
+                        src/liboslnoise/oslnoise_test.cpp:86-334
+
+Nothing here copies reference *sources*: the .oso files are compiler output,
+the rest is the reference's published golden test data.
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools import mini_oslc  # noqa: E402
+
+REF = os.environ.get("OSL_REFERENCE", "/root/reference")
+TS = os.path.join(REF, "testsuite")
+OUT = os.path.join(ROOT, "tests", "golden")
+STEP = 2
+
+SHADERS = {
+    # fixture name: path under testsuite/
+    "noise_test": "noise/test.osl",
+    "cellnoise_test": "cellnoise/test.osl",
+    "hashnoise_test": "hashnoise/test.osl",
+    "pnoise_test": "pnoise/test.osl",
+    "testnoise": "common/shaders/testnoise.osl",
+    "testpnoise": "common/shaders/testpnoise.osl",
+    "hash_test": "hash/test.osl",
+    "layers_lazy_a": "layers-lazy/a.osl",
+    "layers_lazy_b": "layers-lazy/b.osl",
+    "layers_lazy_c": "layers-lazy/c.osl",
+    "layers_a": "layers/a.osl",
+    "layers_b": "layers/b.osl",
+}
+IMAGES = {
+    # golden name: testsuite-relative image
+    "noise": "noise/ref/out.tif",
+    "cellnoise": "cellnoise/ref/out.tif",
+    "hashnoise": "hashnoise/ref/out.tif",
+    "noise-cell": "noise-cell/ref/out.tif",
+    "noise-perlin": "noise-perlin/ref/out.tif",
+    "pnoise": "pnoise/ref/out.tif",
+    "pnoise-cell": "pnoise-cell/ref/out.tif",
+    "pnoise-perlin": "pnoise-perlin/ref/out.tif",
+}
+TEXTS = {
+    "hash": "hash/ref/out.txt",
+    "layers-lazy": "layers-lazy/ref/out.txt",
+    "layers": "layers/ref/out.txt",
+}
+
+
+def parse_noise_vectors():
+    """Pull the results_Nd / vresults_Nd tables of test_perlin/test_cell/test_hash."""
+    src = open(os.path.join(REF, "src/liboslnoise/oslnoise_test.cpp")).read()
+    out = {}
+    for fn in ("test_perlin", "test_cell", "test_hash"):
+        a = src.index("\n" + fn + "()")
+        b = src.index("for (int i", a)
+        body = src[a:b]
+        tables = {}
+        for m in re.finditer(r"static\s+(float|Vec3)\s+(\w+)\[[^\]]*\]\s*=\s*\{(.*?)\};", body, re.S):
+            kind, name, vals = m.group(1), m.group(2), m.group(3)
+            if kind == "float":
+                tables[name] = [float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", vals)]
+            else:
+                tables[name] = [[float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", v)]
+                                for v in re.findall(r"Vec3\(([^)]*)\)", vals)]
+        out[fn] = tables
+    return out
+
+
+def main():
+    from PIL import Image
+    os.makedirs(os.path.join(OUT, "oso"), exist_ok=True)
+    os.makedirs(os.path.join(OUT, "images"), exist_ok=True)
+    os.makedirs(os.path.join(OUT, "text"), exist_ok=True)
+    inc = [os.path.join(REF, "src/shaders")]
+    for name, rel in SHADERS.items():
+        oso = mini_oslc.compile_osl(os.path.join(TS, rel), inc)
+        with open(os.path.join(OUT, "oso", name + ".oso"), "w") as f:
+            f.write(oso)
+    for name, rel in IMAGES.items():
+        img = np.array(Image.open(os.path.join(TS, rel)))
+        if img.ndim == 2:
+            img = img[..., None]
+        np.savez_compressed(os.path.join(OUT, "images", name + ".npz"),
+                            pixels=img[::STEP, ::STEP, :3].copy(), step=STEP,
+                            shape=np.array(img.shape[:2]))
+    for name, rel in TEXTS.items():
+        with open(os.path.join(TS, rel)) as f, open(os.path.join(OUT, "text", name + ".txt"), "w") as o:
+            o.write(f.read())
+    with open(os.path.join(OUT, "noise_vectors.json"), "w") as f:
+        json.dump(parse_noise_vectors(), f, indent=1)
+    print("fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
