@@ -757,16 +757,8 @@ Gen::gen_layer(int layer)
     for (const Connection& c : g.connections)
         if (c.srclayer == layer && !g.layers[c.dstlayer].unused)
             emit_copy(c.dstlayer, g.layers[c.dstlayer].m.syms[c.dstsym], layer, m.syms[c.srcsym]);
-    // renderer outputs: output_base + offset + stride*shadeindex
-    // (llvm_instance.cpp:1807-1848)
-    for (size_t k = 0; k < g.outputs.size(); ++k) {
-        auto& o2 = g.outputs[k];
-        if (o2.first != layer)
-            continue;
-        Symbol& s = m.syms[o2.second];
-        w(std::string(s.out.derivs ? "wrd" : "wr") + "(outp(L, sg, " + std::to_string(k) + ", "
-          + std::to_string(s.out.offset) + "LL, " + std::to_string(s.out.stride) + "LL), " + ref(layer, s) + ");");
-    }
+    // renderer outputs are written by the kernel epilogue from the group data
+    // (reference: llvm_instance.cpp:1807-1848 does it at the end of the layer)
     ind = 0;
     w("}");
 }
@@ -787,6 +779,8 @@ struct B200Launch {
     long long npoints;
     long long shadeindex_base;   // added to the point index when shadeindex == NULL
     long long out_adjust[%MAXOUT%];   // per-output byte rebase (host staging path)
+    int stage_outputs;                // 1: stage dense output records in shared memory
+    int pad_;
 };
 
 __device__ __forceinline__ float ldf(const B200Launch& L, int f, int c, long long i)
@@ -810,6 +804,38 @@ __device__ __forceinline__ float* outp(const B200Launch& L, const SG& sg, int k,
 {
     return (float*)((char*)L.output_base + offset + L.out_adjust[k] + stride * (long long)sg.shadeindex);
 }
+// ---- shared-memory staging of dense output records + TMA bulk store ----------
+// Each thread drops its record (W words) at stage[t*W ..]; 16-byte stores when W%4==0
+// are bank-conflict free for the 48 B record of the layered group, scalar stores
+// are conflict free for odd W (12 B colour records).
+template<int W> __device__ __forceinline__ void stage_record(float* s, int t, const float (&rec)[W])
+{
+    if (W % 4 == 0) {
+        float4* p = reinterpret_cast<float4*>(s + t * W);
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j)
+            p[j] = make_float4(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3]);
+    } else if (W % 2 == 0) {
+        float2* p = reinterpret_cast<float2*>(s + t * W);
+#pragma unroll
+        for (int j = 0; j < W / 2; ++j)
+            p[j] = make_float2(rec[2 * j], rec[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            s[t * W + j] = rec[j];
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void wr(float* p, float v) { p[0] = v; }
 __device__ __forceinline__ void wr(float* p, int v) { ((int*)p)[0] = v; }
 __device__ __forceinline__ void wr(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -924,14 +950,82 @@ Gen::run()
     out << "// generated by libosl_b200 for shader group '" << g.name << "'\n";
     out << "#include \"osl_b200_device.cuh\"\n";
     out << prelude << sg.str() << OUTPUT_HELPERS << gd << layers_src;
-    out << "extern \"C\" __global__ void __launch_bounds__(%BLOCK%) osl_b200_group_kernel(const __grid_constant__ B200Launch L)\n{\n";
-    out << "    const long long stride_ = (long long)gridDim.x * blockDim.x;\n";
-    out << "    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L.npoints; i += stride_) {\n";
+    // ---- kernel: one CTA walks tiles of BLOCK consecutive points --------------
+    auto out_sym  = [&](int k) -> Symbol& { return g.layers[g.outputs[k].first].m.syms[g.outputs[k].second]; };
+    auto out_expr = [&](int k) {
+        L  = &g.layers[g.outputs[k].first];
+        li = g.outputs[k].first;
+        return ref(li, out_sym(k));
+    };
+    std::string B = "%BLOCK%";
+    long long stage_words = 0;
+    for (const OutCluster& c : g.clusters)
+        stage_words += c.stride / 4;
+    out << "extern \"C\" __global__ void __launch_bounds__(" << B
+        << ") osl_b200_group_kernel(const __grid_constant__ B200Launch L)\n{\n";
+    if (g.stage_ok)
+        out << "    __shared__ __align__(128) float stage_[" << stage_words << " * " << B << "];\n";
+    out << "    const long long ntiles_ = (L.npoints + " << B << " - 1) / " << B << ";\n";
+    out << "    const bool staged_ = " << (g.stage_ok ? "(L.shadeindex == nullptr) && (L.stage_outputs != 0)" : "false") << ";\n";
+    out << "    for (long long tile_ = blockIdx.x; tile_ < ntiles_; tile_ += gridDim.x) {\n";
+    out << "        const long long i = tile_ * " << B << " + threadIdx.x;\n";
+    out << "        const bool active_ = i < L.npoints;\n";
     out << "        SG sg;\n        GD gd;\n        gd.ran = 0u;\n";
-    out << "        sg.shadeindex = L.shadeindex ? __ldg(L.shadeindex + i) : (int)(i + L.shadeindex_base);\n";
+    out << "        if (active_) {\n";
+    out << "            sg.shadeindex = L.shadeindex ? __ldg(L.shadeindex + i) : (int)(i + L.shadeindex_base);\n";
     out << ld.str();
-    out << "        layer_" << (nlayers - 1) << "(sg, gd, L);\n";
-    out << "    }\n}\n";
+    out << "            layer_" << (nlayers - 1) << "(sg, gd, L);\n";
+    out << "        }\n";
+    if (g.stage_ok) {
+        out << "        if (staged_) {\n";
+        out << "            if (threadIdx.x == 0) bulk_wait_read();   // previous tile's bulk store has drained stage_\n";
+        out << "            __syncthreads();\n";
+        out << "            if (active_) {\n";
+        long long woff = 0;
+        for (const OutCluster& c : g.clusters) {
+            long long W = c.stride / 4;
+            out << "                {\n                    float rec_[" << W << "];\n";
+            for (int k : c.outs) {
+                Symbol& s = out_sym(k);
+                out << "                    " << (s.out.derivs ? "wrd" : "wr") << "(rec_ + " << (s.out.offset - c.lo) / 4
+                    << ", " << out_expr(k) << ");\n";
+            }
+            out << "                    stage_record<" << W << ">(stage_ + " << woff << " * " << B << ", threadIdx.x, rec_);\n";
+            out << "                }\n";
+            woff += W;
+        }
+        out << "            }\n";
+        out << "            fence_async_smem();\n            __syncthreads();\n";
+        out << "            const long long i0_ = tile_ * " << B << ";\n";
+        out << "            const long long cnt_ = (L.npoints - i0_) < " << B << " ? (L.npoints - i0_) : " << B << ";\n";
+        woff = 0;
+        for (const OutCluster& c : g.clusters) {
+            long long W = c.stride / 4;
+            out << "            {\n";
+            out << "                char* gp_ = (char*)L.output_base + " << c.lo << "LL + L.out_adjust[" << c.outs[0] << "] + "
+                << c.stride << "LL * (i0_ + L.shadeindex_base);\n";
+            out << "                const unsigned bytes_ = (unsigned)(cnt_ * " << c.stride << "LL);\n";
+            out << "                const float* sp_ = stage_ + " << woff << " * " << B << ";\n";
+            out << "                if ((((unsigned long long)gp_ | bytes_) & 15ull) == 0) {\n";
+            out << "                    if (threadIdx.x == 0) bulk_store(gp_, sp_, bytes_);\n";
+            out << "                } else {\n";
+            out << "                    for (unsigned w_ = threadIdx.x; w_ < bytes_ / 4; w_ += " << B << ") ((float*)gp_)[w_] = sp_[w_];\n";
+            out << "                }\n            }\n";
+            woff += W;
+        }
+        out << "        } else\n";
+    }
+    out << "        if (active_) {\n";
+    for (size_t k = 0; k < g.outputs.size(); ++k) {
+        Symbol& s = out_sym((int)k);
+        out << "            " << (s.out.derivs ? "wrd" : "wr") << "(outp(L, sg, " << k << ", " << s.out.offset << "LL, "
+            << s.out.stride << "LL), " << out_expr((int)k) << ");\n";
+    }
+    out << "        }\n";
+    out << "    }\n";
+    if (g.stage_ok)
+        out << "    if (staged_ && threadIdx.x == 0) bulk_wait_all();\n";
+    out << "}\n";
     return out.str();
 }
 

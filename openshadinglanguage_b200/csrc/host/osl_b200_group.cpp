@@ -9,6 +9,7 @@
 //   derivative propagation        src/liboslexec/runtimeoptimize.cpp:2542-2720, 3223-3231
 #include "osl_b200_group.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -432,6 +433,57 @@ Group::finalize()
         l.unused = (i != n - 1) && !has_out && !has_down;
         l.lazy   = (i != n - 1) && !has_out;
     }
+    // output clusters (records that interleave) and whether they can be staged
+    clusters.clear();
+    for (size_t k = 0; k < outputs.size(); ++k) {
+        const Symbol& s = layers[outputs[k].first].m.syms[outputs[k].second];
+        long long size  = 4LL * s.type.ncomp() * (s.out.derivs ? 3 : 1);
+        if (s.type.arraylen || s.out.stride < size || (s.out.offset & 3) || (s.out.stride & 3))
+            throw std::runtime_error("renderer output '" + s.name
+                                     + "': arrays, strides smaller than the value, or unaligned "
+                                       "offsets/strides are not supported");
+        bool placed = false;
+        for (OutCluster& c : clusters) {
+            long long lo = std::min(c.lo, s.out.offset), hi = std::max(c.hi, s.out.offset + size);
+            if (c.stride == s.out.stride && hi - lo <= c.stride) {
+                c.lo = lo;
+                c.hi = hi;
+                c.outs.push_back((int)k);
+                placed = true;
+                break;
+            }
+        }
+        if (!placed) {
+            OutCluster c;
+            c.stride = s.out.stride;
+            c.lo     = s.out.offset;
+            c.hi     = s.out.offset + size;
+            c.outs.push_back((int)k);
+            clusters.push_back(c);
+        }
+    }
+    long long stage_bytes = 0;
+    stage_ok              = !clusters.empty();
+    for (OutCluster& c : clusters) {
+        // dense: the fields cover [lo, lo+stride) with no gap and no overlap
+        std::vector<std::pair<long long, long long>> spans;
+        for (int k : c.outs) {
+            const Symbol& s = layers[outputs[k].first].m.syms[outputs[k].second];
+            spans.push_back({ s.out.offset, s.out.offset + 4LL * s.type.ncomp() * (s.out.derivs ? 3 : 1) });
+        }
+        std::sort(spans.begin(), spans.end());
+        long long at = c.lo;
+        bool ok      = true;
+        for (auto& sp : spans) {
+            ok &= (sp.first == at);
+            at = sp.second;
+        }
+        c.dense = ok && at == c.lo + c.stride;
+        stage_ok &= c.dense;
+        stage_bytes += c.stride * block;
+    }
+    if (stage_bytes > 48 * 1024)
+        stage_ok = false;
     for (int i = n - 1; i >= 0; --i) {
         track_derivs(layers[i]);
         for (const Symbol& s : layers[i].m.syms)

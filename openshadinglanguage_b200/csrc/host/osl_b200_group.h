@@ -105,8 +105,21 @@ struct Connection {
     int srclayer, srcsym, dstlayer, dstsym;
 };
 
+// Renderer outputs whose records interleave (same stride, offsets inside one
+// stride) form one cluster: for consecutive shade indices the cluster is one
+// contiguous byte range, which is what the kernel stages in shared memory and
+// the host path moves with one copy.
+struct OutCluster {
+    long long stride = 0, lo = 0, hi = 0;  // one record covers bytes [lo, hi)
+    std::vector<int> outs;                 // indices into Group::outputs
+    bool dense = false;                    // fields tile [lo, lo+stride) exactly
+};
+
 struct Group {
     std::string name;
+    std::vector<OutCluster> clusters;
+    bool stage_ok = false;  // every cluster dense and small enough to stage
+    int block     = 256;    // CTA size the kernel is generated for
     std::vector<Layer> layers;
     std::vector<Connection> connections;
     std::vector<std::pair<int, int>> outputs;  // (layer, sym) with out.placed

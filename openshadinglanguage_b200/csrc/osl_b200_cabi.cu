@@ -113,6 +113,8 @@ struct LaunchBlock {  // must match B200Launch in the generated code
     long long npoints;
     long long shadeindex_base;
     long long out_adjust[B200_MAX_OUTPUTS];
+    int stage_outputs;
+    int pad_;
 };
 
 }  // namespace
@@ -122,6 +124,7 @@ struct b200_group {
     std::string source;
     std::vector<char> cubin;
     int block = 256;
+    int stage_outputs = 1;  // option stage=0 forces direct stores
     std::mutex mu;
     std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
     int sm_count[64] = { 0 };
@@ -223,6 +226,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             G->g.fma = atoi(opt["fma"].c_str()) != 0;
         if (opt.count("block"))
             G->block = atoi(opt["block"].c_str());
+        if (opt.count("stage"))
+            G->stage_outputs = atoi(opt["stage"].c_str()) != 0;
         if (G->block < 32 || G->block > 1024 || (G->block % 32))
             return fail(B200_ERR_INVALID, "option block must be a multiple of 32 in [32,1024]");
         for (int i = 0; i < desc->nlayers; ++i) {
@@ -256,6 +261,7 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             const b200_symloc& s = desc->outputs[i];
             G->g.add_output(s.name, s.offset, s.stride, s.derivs != 0);
         }
+        G->g.block = G->block;
         G->g.finalize();
         G->source = generate_cuda(G->g);
     } catch (const std::exception& e) {
@@ -369,10 +375,13 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
     L.shadeindex_base = sidx_base;
     for (int k = 0; k < B200_MAX_OUTPUTS; ++k)
         L.out_adjust[k] = out_adjust ? out_adjust[k] : 0;
+    L.stage_outputs = g->stage_outputs;
+    L.pad_          = 0;
     int sms = (device >= 0 && device < 64 && g->sm_count[device]) ? g->sm_count[device] : 148;
-    // grid: cover the range, capped at a whole number of resident waves
+    // grid: one CTA per tile of `block` points, capped at 8 CTAs per SM (a
+    // multiple of the SM count); CTAs loop over the remaining tiles
     long long want = (npoints + g->block - 1) / g->block;
-    long long cap  = (long long)sms * 32;
+    long long cap  = (long long)sms * 8;
     unsigned grid  = (unsigned)(want < cap ? want : cap);
     void* args[]   = { &L };
     CUresult_ r    = driver().cuLaunchKernel(fn, grid, 1, 1, (unsigned)g->block, 1, 1, 0, stream, args, nullptr);
@@ -419,32 +428,8 @@ b200_group_execute_host(b200_group* g, int device, long long npoints, const b200
             planes.push_back({ f, is_triple[f] ? 3 : 1 });
             in_bpp += 4 * (is_triple[f] ? 3 : 1);
         }
-    // cluster outputs whose records interleave (same stride, offsets within one stride)
-    struct Cluster {
-        long long stride, lo, hi;  // byte extent of one record: [lo, hi)
-        std::vector<int> outs;
-    };
-    std::vector<Cluster> clusters;
-    for (size_t k = 0; k < g->g.outputs.size(); ++k) {
-        const Symbol& s = g->g.layers[g->g.outputs[k].first].m.syms[g->g.outputs[k].second];
-        long long size  = 4LL * s.type.ncomp() * (s.out.derivs ? 3 : 1);
-        if (s.out.stride < size)
-            return fail(B200_ERR_INVALID, "execute_host: output stride smaller than the value size");
-        bool placed = false;
-        for (Cluster& c : clusters) {
-            long long lo = c.lo < s.out.offset ? c.lo : s.out.offset;
-            long long hi = c.hi > s.out.offset + size ? c.hi : s.out.offset + size;
-            if (c.stride == s.out.stride && hi - lo <= c.stride) {
-                c.lo = lo;
-                c.hi = hi;
-                c.outs.push_back((int)k);
-                placed = true;
-                break;
-            }
-        }
-        if (!placed)
-            clusters.push_back({ s.out.stride, s.out.offset, s.out.offset + size, { (int)k } });
-    }
+    typedef OutCluster Cluster;
+    const std::vector<OutCluster>& clusters = g->g.clusters;
     size_t out_bpp = 0;
     for (const Cluster& c : clusters)
         out_bpp += (size_t)c.stride;
