@@ -148,7 +148,7 @@ long long b200_launch_count(void);
 /* ---- device shadeop library, batch entry points (device pointers) --------
  * Stand-alone equivalents of the osl_<op>_<codes> runtime
  * (src/liboslexec/builtindecl.h:19-83, opnoise.cpp:263-273, 468-473) over
- * SoA arrays.  kind: 0 noise 1 snoise 2 cellnoise 3 hashnoise.
+ * SoA arrays.  kind: 0 noise 1 snoise 2 cellnoise 3 hashnoise 4 simplex 5 usimplex.
  * in:  indim planes of n floats (+ 2*indim derivative planes when derivs)
  * out: outdim planes of n floats (x3 when derivs: val planes, dx planes, dy planes)
  * period (pnoise family): indim floats, or NULL. */

@@ -235,7 +235,7 @@ class ShaderGroup:
 
 def shadeop_noise(kind, outdim, indim, n, inp, out, period=None, derivs=False, stream=None):
     """Batch noise over device SoA planes (b200_shadeop_noise)."""
-    kinds = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3}
+    kinds = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3, "simplex": 4, "usimplex": 5}
     if stream is None:
         import torch
         stream = torch.cuda.current_stream().cuda_stream

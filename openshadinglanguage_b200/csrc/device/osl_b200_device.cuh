@@ -982,3 +982,5 @@ OSLD V3 o_Dx(V3) { return mkv(0.0f); }
 OSLD V3 o_Dy(V3) { return mkv(0.0f); }
 
 }  // namespace osld
+
+#include "osl_b200_simplex.cuh"

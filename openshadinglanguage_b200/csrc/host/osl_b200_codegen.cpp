@@ -107,7 +107,8 @@ noise_kind(const std::string& n, bool periodic)
 {
     static const std::map<std::string, int> base
         = { { "noise", 0 },  { "uperlin", 0 },   { "snoise", 1 }, { "perlin", 1 },
-            { "cell", 2 },   { "cellnoise", 2 }, { "hash", 3 },   { "hashnoise", 3 } };
+            { "cell", 2 },   { "cellnoise", 2 }, { "hash", 3 },   { "hashnoise", 3 },
+            { "simplex", 4 }, { "simplexnoise", 4 }, { "usimplex", 5 }, { "usimplexnoise", 5 } };
     static const std::map<std::string, int> per
         = { { "pnoise", 0 }, { "psnoise", 1 }, { "pcellnoise", 2 }, { "phashnoise", 3 } };
     if (periodic) {
@@ -477,8 +478,11 @@ Gen::op_noise(const Opcode& op, bool periodic)
     int dim = (int)ins.size(), nc = d.type.ncomp();
     if (dim < 1 || dim > 4)
         unsupported("noise with " + std::to_string(dim) + " input dimensions");
-    bool hashy = kind >= 2;
-    bool dv    = false;
+    bool hashy   = kind == 2 || kind == 3;
+    bool simplex = kind == 4 || kind == 5;
+    if (simplex && periodic)
+        unsupported("periodic simplex noise does not exist in OSL");
+    bool dv = false;
     if (!hashy && d.has_derivs)
         for (int a : coords)
             dv |= S(a).has_derivs;
@@ -507,6 +511,8 @@ Gen::op_noise(const Opcode& op, bool periodic)
         }
     } else if (hashy) {
         w(std::string("ihnoise<") + (kind == 2 ? "true" : "false") + ", " + sd + ", " + sn + ">(out_, in_);");
+    } else if (simplex) {
+        w("simplex<" + sd + ", " + sn + ", " + (kind == 5 ? "true" : "false") + ">(out_, in_);");
     } else {
         w("perlin<" + T + ", " + sd + ", " + sn + ", " + (kind == 1 ? "true" : "false") + ", false>(out_, in_, nullptr);");
     }

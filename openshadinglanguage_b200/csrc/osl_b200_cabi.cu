@@ -28,7 +28,10 @@
 
 #include "device/osl_b200_device.cuh"
 
-extern const char* osl_b200_device_source;  // device header text (generated at build)
+// device header texts (generated at build from csrc/device/*.cuh)
+extern const int osl_b200_num_device_headers;
+extern const char* const osl_b200_device_header_names[];
+extern const char* const osl_b200_device_header_sources[];
 
 using namespace oslb200;
 
@@ -164,9 +167,9 @@ nvrtc_compile(b200_group* G, std::string& log)
         src.replace(p, 7, std::to_string(G->block));
     G->source = src;
     nvrtcProgram prog;
-    const char* hdr_names[] = { "osl_b200_device.cuh" };
-    const char* hdr_srcs[]  = { osl_b200_device_source };
-    if (nvrtcCreateProgram(&prog, src.c_str(), "osl_b200_group.cu", 1, hdr_srcs, hdr_names) != NVRTC_SUCCESS)
+    if (nvrtcCreateProgram(&prog, src.c_str(), "osl_b200_group.cu", osl_b200_num_device_headers,
+                           osl_b200_device_header_sources, osl_b200_device_header_names)
+        != NVRTC_SUCCESS)
         return fail(B200_ERR_COMPILE, "nvrtcCreateProgram failed");
     std::vector<const char*> opts = { "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
                                       "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
@@ -520,7 +523,7 @@ noise_kernel(long long n, const float* __restrict__ in, const float* __restrict_
 #pragma unroll
         for (int d = 0; d < DIM; ++d)
             x[d] = in[d * n + i];
-        if (KIND >= 2) {
+        if (KIND == 2 || KIND == 3) {
             if (PER) {
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
@@ -548,7 +551,10 @@ noise_kernel(long long n, const float* __restrict__ in, const float* __restrict_
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
                     xd[d] = mkd(x[d], in[(DIM + d) * n + i], in[(2 * DIM + d) * n + i]);
-                perlin<Df, DIM, NC, KIND == 1, PER>(r, xd, per);
+                if (KIND >= 4)
+                    simplex<DIM, NC, KIND == 5>(r, xd);
+                else
+                    perlin<Df, DIM, NC, KIND == 1, PER>(r, xd, per);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
                     out[c * n + i]            = r[c].val;
@@ -557,7 +563,10 @@ noise_kernel(long long n, const float* __restrict__ in, const float* __restrict_
                 }
             } else {
                 float r[3];
-                perlin<float, DIM, NC, KIND == 1, PER>(r, x, per);
+                if (KIND >= 4)
+                    simplex<DIM, NC, KIND == 5>(r, x);
+                else
+                    perlin<float, DIM, NC, KIND == 1, PER>(r, x, per);
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
                     out[c * n + i] = r[c];
@@ -630,7 +639,7 @@ b200_shadeop_noise(int kind, int outdim, int indim, int derivs, int fma, long lo
                    const float* period, float* out, void* stream)
 {
     (void)fma;  // the AOT library is built strict (-fmad=false); generated groups choose per group
-    if (kind < 0 || kind > 3 || (outdim != 1 && outdim != 3) || indim < 1 || indim > 4 || n < 0 || !in || !out)
+    if (kind < 0 || kind > 5 || (kind >= 4 && period) || (outdim != 1 && outdim != 3) || indim < 1 || indim > 4 || n < 0 || !in || !out)
         return fail(B200_ERR_INVALID, "b200_shadeop_noise: bad arguments");
     if (n == 0)
         return B200_OK;
@@ -641,7 +650,9 @@ b200_shadeop_noise(int kind, int outdim, int indim, int derivs, int fma, long lo
     case 0: launch_noise0<0>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
     case 1: launch_noise0<1>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
     case 2: launch_noise0<2>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
-    default: launch_noise0<3>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    case 3: launch_noise0<3>(indim, outdim, derivs != 0, per, grid, s, n, in, period, out); break;
+    case 4: launch_noise0<4>(indim, outdim, derivs != 0, false, grid, s, n, in, period, out); break;
+    default: launch_noise0<5>(indim, outdim, derivs != 0, false, grid, s, n, in, period, out); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)

@@ -118,7 +118,7 @@ def build_shadeops():
     bdir = os.path.join(here, "_build")
     os.makedirs(bdir, exist_ok=True)
     so = os.path.join(bdir, "liboracle_shadeops.so")
-    srcs = [os.path.join(here, f) for f in ("oracle_shadeops.cpp", "osl_oracle.h", "osl_oracle_ops.h")]
+    srcs = [os.path.join(here, f) for f in ("oracle_shadeops.cpp", "osl_oracle.h", "osl_oracle_ops.h", "osl_oracle_simplex.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
                             "-I", here, srcs[0], "-o", so + ".tmp"], capture_output=True, text=True)
@@ -139,7 +139,7 @@ def shadeops():
     return _shadeops
 
 
-KINDS = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3}
+KINDS = {"noise": 0, "snoise": 1, "cellnoise": 2, "hashnoise": 3, "simplex": 4, "usimplex": 5}
 
 
 def noise(kind, outdim, inp, period=None, derivs=False):
@@ -184,3 +184,81 @@ class OracleGroup:
     def run_capture(self, n, varying, uniform, output=None, shadeindex=None):
         L, keep = make_launch(n, varying, uniform, output, shadeindex)
         return self.lib.oracle_run_capture(ctypes.byref(L), 0, n).decode()
+
+
+# ---------------------------------------------------------------------------
+# testrender oracle
+# ---------------------------------------------------------------------------
+class RenderScene(ctypes.Structure):
+    _fields_ = [("nverts", ctypes.c_int), ("ntris", ctypes.c_int), ("nnodes", ctypes.c_int),
+                ("nlightprims", ctypes.c_int), ("nshaders", ctypes.c_int), ("nmeshes", ctypes.c_int),
+                ("verts", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("uvs", ctypes.c_void_p),
+                ("triangles", ctypes.c_void_p), ("n_triangles", ctypes.c_void_p),
+                ("uv_triangles", ctypes.c_void_p), ("shaderids", ctypes.c_void_p),
+                ("meshids", ctypes.c_void_p), ("mesh_surfacearea", ctypes.c_void_p),
+                ("bvh_nodes", ctypes.c_void_p), ("bvh_indices", ctypes.c_void_p),
+                ("lightprims", ctypes.c_void_p), ("shader_is_light", ctypes.c_void_p),
+                ("eye", ctypes.c_float * 3), ("dir", ctypes.c_float * 3), ("up", ctypes.c_float * 3),
+                ("fov", ctypes.c_float), ("cx", ctypes.c_float * 3), ("cy", ctypes.c_float * 3),
+                ("invw", ctypes.c_float), ("invh", ctypes.c_float),
+                ("xres", ctypes.c_int), ("yres", ctypes.c_int),
+                ("aa", ctypes.c_int), ("max_bounces", ctypes.c_int), ("rr_depth", ctypes.c_int),
+                ("no_jitter", ctypes.c_int), ("show_globals", ctypes.c_int),
+                ("background_shader", ctypes.c_int), ("background_resolution", ctypes.c_int)]
+
+
+def fill_render_scene(RS, scene, arrays, xres, yres, aa, max_bounces=1000000, rr_depth=5,
+                      no_jitter=False, show_globals=0):
+    """Fill a RenderScene-shaped ctypes struct (oracle and product share the layout)."""
+    keep = []
+    rs = RS()
+
+    def ptr(name, dtype):
+        a = np.ascontiguousarray(arrays[name], dtype)
+        keep.append(a)
+        return a.ctypes.data
+    rs.nverts, rs.ntris = len(arrays["verts"]), len(arrays["triangles"])
+    rs.nnodes, rs.nlightprims = len(arrays["bvh_nodes"]), len(arrays["lightprims"])
+    rs.nshaders, rs.nmeshes = len(scene.materials), len(arrays["mesh_surfacearea"])
+    rs.verts, rs.normals, rs.uvs = ptr("verts", np.float32), ptr("normals", np.float32), ptr("uvs", np.float32)
+    rs.triangles, rs.n_triangles = ptr("triangles", np.int32), ptr("n_triangles", np.int32)
+    rs.uv_triangles, rs.shaderids = ptr("uv_triangles", np.int32), ptr("shaderids", np.int32)
+    rs.meshids, rs.mesh_surfacearea = ptr("meshids", np.int32), ptr("mesh_surfacearea", np.float32)
+    rs.bvh_nodes, rs.bvh_indices = ptr("bvh_nodes", np.float32), ptr("bvh_indices", np.uint32)
+    rs.lightprims = ptr("lightprims", np.uint32) if len(arrays["lightprims"]) else None
+    rs.shader_is_light = ptr("shader_is_light", np.int32)
+    for i in range(3):
+        rs.eye[i], rs.dir[i], rs.up[i] = float(scene.eye[i]), float(scene.dir[i]), float(scene.up[i])
+    rs.fov = float(scene.fov)
+    rs.xres, rs.yres, rs.aa = xres, yres, aa
+    rs.max_bounces, rs.rr_depth = max_bounces, rr_depth
+    rs.no_jitter, rs.show_globals = int(no_jitter), show_globals
+    rs.background_shader, rs.background_resolution = scene.background_shader, scene.background_resolution
+    return rs, keep
+
+
+def material_groups(scene, oso_lookup):
+    """[(layers, connections)] with .oso text resolved, ready for a generator."""
+    mats = []
+    for layers, conns in scene.materials:
+        mats.append(([dict(oso=oso_lookup(l["shader"]), name=l["name"], params=l["params"]) for l in layers],
+                     conns))
+    return mats
+
+
+class OracleRender:
+    def __init__(self, scene, arrays, oso_lookup, opt="-O2"):
+        self.scene, self.arrays = scene, arrays
+        groups = []
+        for layers, conns in material_groups(scene, oso_lookup):
+            ls = [oso2cpp.Layer(l["oso"], l["name"], l["params"]) for l in layers]
+            groups.append(oso2cpp.Group(ls, conns, ()))
+        self.so = oso2cpp.build_render(groups, opt=opt)
+        self.lib = ctypes.CDLL(self.so)
+        self.lib.oracle_render.argtypes = [ctypes.POINTER(RenderScene), ctypes.c_void_p, ctypes.c_int]
+
+    def render(self, xres, yres, aa, nthreads=None, **kw):
+        rs, keep = fill_render_scene(RenderScene, self.scene, self.arrays, xres, yres, aa, **kw)
+        out = np.zeros((yres, xres, 3), np.float32)
+        self.lib.oracle_render(ctypes.byref(rs), out.ctypes.data, nthreads or (os.cpu_count() or 1))
+        return out

@@ -20,7 +20,7 @@ run_noise(int indim, bool derivs, long long n, const float* in, const float* per
         float x[4] = { 0, 0, 0, 0 };
         for (int d = 0; d < indim; ++d)
             x[d] = in[d * n + i];
-        if (KIND >= N_CELL) {
+        if (KIND == N_CELL || KIND == N_HASH) {
             if (period)
                 for (int d = 0; d < indim; ++d)
                     x[d] = pwrap(x[d], period[d]);
@@ -42,7 +42,9 @@ run_noise(int indim, bool derivs, long long n, const float* in, const float* per
             Df xd[4], r[3];
             for (int d = 0; d < indim; ++d)
                 xd[d] = Df(x[d], in[(indim + d) * n + i], in[(2 * indim + d) * n + i]);
-            if (KIND == N_NOISE)
+            if (KIND == N_SIMPLEX || KIND == N_USIMPLEX)
+                noise_core<KIND, Df, NC>(r, indim, xd);
+            else if (KIND == N_NOISE)
                 perlin_nd<Df, NC, false>(r, indim, xd, pp);
             else
                 perlin_nd<Df, NC, true>(r, indim, xd, pp);
@@ -53,7 +55,9 @@ run_noise(int indim, bool derivs, long long n, const float* in, const float* per
             }
         } else {
             float r[3];
-            if (KIND == N_NOISE)
+            if (KIND == N_SIMPLEX || KIND == N_USIMPLEX)
+                noise_core<KIND, float, NC>(r, indim, x);
+            else if (KIND == N_NOISE)
                 perlin_nd<float, NC, false>(r, indim, x, pp);
             else
                 perlin_nd<float, NC, true>(r, indim, x, pp);
@@ -69,7 +73,7 @@ extern "C" int
 oracle_noise(int kind, int outdim, int indim, int derivs, long long n, const float* in,
              const float* period, float* out)
 {
-    if (kind < 0 || kind > 3 || (outdim != 1 && outdim != 3) || indim < 1 || indim > 4)
+    if (kind < 0 || kind > 5 || (outdim != 1 && outdim != 3) || indim < 1 || indim > 4)
         return 1;
 #define GO(K)                                                            \
     if (outdim == 1)                                                     \
@@ -80,7 +84,9 @@ oracle_noise(int kind, int outdim, int indim, int derivs, long long n, const flo
     case 0: GO(N_NOISE) break;
     case 1: GO(N_SNOISE) break;
     case 2: GO(N_CELL) break;
-    default: GO(N_HASH) break;
+    case 3: GO(N_HASH) break;
+    case 4: GO(N_SIMPLEX) break;
+    default: GO(N_USIMPLEX) break;
     }
 #undef GO
     return 0;

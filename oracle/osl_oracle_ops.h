@@ -12,6 +12,7 @@
 // (OIIO >= 3.0; not in /root/reference): value-level PARITY UNPINNED.
 #pragma once
 #include "osl_oracle.h"
+#include "osl_oracle_simplex.h"
 
 namespace oslo {
 
@@ -680,11 +681,15 @@ inline V3 o_Dy(const V3&) { return V3(0.0f); }
 // noise front ends (opnoise.cpp:71-272, 276-470; llvm_gen.cpp:3117-3299).
 // KIND: 0 noise(uperlin) 1 snoise(perlin) 2 cellnoise 3 hashnoise
 // ---------------------------------------------------------------------------
-enum { N_NOISE = 0, N_SNOISE = 1, N_CELL = 2, N_HASH = 3 };
+enum { N_NOISE = 0, N_SNOISE = 1, N_CELL = 2, N_HASH = 3, N_SIMPLEX = 4, N_USIMPLEX = 5 };
 
 template<int KIND, class S, int NC> inline void noise_core(S* out, int dim, const S* in)
 {
-    if (KIND == N_NOISE)
+    if (KIND == N_SIMPLEX)
+        simplex_nd<NC, false>(out, dim, in);
+    else if (KIND == N_USIMPLEX)
+        simplex_nd<NC, true>(out, dim, in);
+    else if (KIND == N_NOISE)
         perlin_nd<S, NC, false>(out, dim, in, nullptr);
     else
         perlin_nd<S, NC, true>(out, dim, in, nullptr);

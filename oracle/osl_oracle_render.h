@@ -1,0 +1,832 @@
+// osl_oracle_render.h — CPU ORACLE (test infrastructure, NOT product code).
+//
+// Scalar restatement of the reference path tracer `testrender`:
+//   Ray / Camera / Scene queries      src/testrender/raytracer.h:40-344
+//   BVH traversal + triangle test     src/testrender/bvh.cpp:221-356
+//   Sampler (Owen-scrambled Sobol)    src/testrender/sampling.h:212-295
+//   TangentFrame, Sampling, MIS       src/testrender/sampling.h:17-207
+//   fresnel_*                         src/testrender/optics.h:13-111
+//   Diffuse / Reflection / Refraction / Transparent lobes
+//                                     src/testrender/shading.cpp:301-322, 1081-1150
+//   CompositeBSDF                     src/testrender/shading.h:319-437
+//   process_closure                   src/testrender/shading.cpp:1448-1706
+//   globals_from_hit, subpixel_radiance, antialias_pixel
+//                                     src/testrender/simpleraytracer.cpp:889-1216
+// One pixel at a time, recursive-loop integrator, exactly the reference's
+// control flow.  Scene arrays (tessellated meshes, BVH, light list) are
+// prepared by the shared host harness and passed in.  Not restated yet:
+// participating media (MediumStack), background importance sampling,
+// displacement — none of which the cornell / bunny configs use.
+#pragma once
+#include "osl_oracle_closure.h"
+#include "osl_oracle_runtime.h"
+
+namespace oslo {
+
+// ---- Imath-style helpers ------------------------------------------------------
+inline float length2(const V3& v) { return v.x * v.x + v.y * v.y + v.z * v.z; }
+inline float vlength(const V3& v) { return imath_length(v); }
+inline V3 normalized(V3 v)
+{
+    float l = imath_length(v);
+    if (l != 0.0f) {
+        v.x /= l;
+        v.y /= l;
+        v.z /= l;
+    }
+    return v;
+}
+
+struct RenderScene {
+    int nverts, ntris, nnodes, nlightprims, nshaders, nmeshes;
+    const float* verts;         // 3 per vertex
+    const float* normals;       // 3 per normal
+    const float* uvs;           // 2 per uv
+    const int* triangles;       // 3 per triangle
+    const int* n_triangles;     // 3 per triangle, -1 = none
+    const int* uv_triangles;    // 3 per triangle, -1 = none
+    const int* shaderids;       // per triangle
+    const int* meshids;         // per triangle
+    const float* mesh_surfacearea;
+    const float* bvh_nodes;     // 8 words per node: bounds[6], child, nprims
+    const unsigned* bvh_indices;
+    const unsigned* lightprims;
+    const int* shader_is_light;
+    float eye[3], dir[3], up[3], fov;   // as given in the scene file
+    float cx[3], cy[3], invw, invh;     // derived by camera_finalize()
+    int xres, yres;
+    int aa, max_bounces, rr_depth, no_jitter, show_globals;
+    int background_shader, background_resolution;
+};
+
+inline V3 vert(const RenderScene& S, int i) { return V3(S.verts[3 * i], S.verts[3 * i + 1], S.verts[3 * i + 2]); }
+inline V3 nrm(const RenderScene& S, int i) { return V3(S.normals[3 * i], S.normals[3 * i + 1], S.normals[3 * i + 2]); }
+
+// ---- Ray / Camera -------------------------------------------------------------
+enum RayType { RAY_CAMERA = 1, RAY_SHADOW = 2, RAY_REFLECTION = 4, RAY_REFRACTION = 8, RAY_DIFFUSE = 16 };
+
+inline void ortho(const V3& n, V3& x, V3& y)
+{
+    x = normalized(std::fabs(n.x) > .01f ? V3(n.z, 0, -n.x) : V3(0, -n.z, n.y));
+    y = cross(n, x);
+}
+struct Ray {
+    V3 origin, direction;
+    float radius, spread, roughness;
+    int raytype;
+    V3 point(float t) const { return origin + direction * t; }
+    Dv dual_direction() const
+    {
+        Dv v;
+        v.val = direction;
+        ortho(direction, v.dx, v.dy);
+        v.dx = v.dx * spread;
+        v.dy = v.dy * spread;
+        return v;
+    }
+    Dv point_dual(float t) const
+    {
+        const float r = radius + spread * t;
+        Dv p;
+        p.val = point(t);
+        ortho(direction, p.dx, p.dy);
+        p.dx = p.dx * r;
+        p.dy = p.dy * r;
+        return p;
+    }
+};
+// Camera::lookat + resolution + finalize (raytracer.h:95-126)
+inline void camera_finalize(RenderScene& S)
+{
+    V3 dir = normalized(V3(S.dir[0], S.dir[1], S.dir[2]));
+    V3 up(S.up[0], S.up[1], S.up[2]);
+    S.invw   = 1.0f / S.xres;
+    S.invh   = 1.0f / S.yres;
+    float k  = fast_tan(S.fov * float(M_PI / 360));
+    V3 right = normalized(cross(dir, up));
+    V3 cx    = right * (S.xres * k / S.yres);
+    V3 cy    = normalized(cross(cx, dir)) * k;
+    for (int i = 0; i < 3; ++i) {
+        S.dir[i] = dir[i];
+        S.cx[i]  = cx[i];
+        S.cy[i]  = cy[i];
+    }
+}
+inline Ray camera_ray(const RenderScene& S, float x, float y)
+{
+    V3 cx(S.cx[0], S.cx[1], S.cx[2]), cy(S.cy[0], S.cy[1], S.cy[2]), dir(S.dir[0], S.dir[1], S.dir[2]);
+    const V3 v        = normalized(cx * (x * S.invw - 0.5f) + cy * (0.5f - y * S.invh) + dir);
+    const float cos_a = dot(dir, v);
+    const float spread = std::sqrt(S.invw * S.invh * vlength(cx) * vlength(cy) * cos_a) * cos_a;
+    Ray r;
+    r.origin    = V3(S.eye[0], S.eye[1], S.eye[2]);
+    r.direction = v;
+    r.radius    = 0;
+    r.spread    = spread;
+    r.roughness = 0.0f;
+    r.raytype   = RAY_CAMERA;
+    return r;
+}
+
+// ---- Sampler --------------------------------------------------------------------
+struct Sampler {
+    uint32_t seed, index;
+    Sampler(int px, int py, int si) : seed(((px & 2047) << 22) | ((py & 2047) << 11)), index(reversebits(si)) {}
+    static uint32_t hash(uint32_t s)
+    {
+        s ^= s >> 16; s *= 0x21f0aaadu; s ^= s >> 15; s *= 0xd35a2d97u; s ^= s >> 15;
+        return s;
+    }
+    static uint32_t reversebits(uint32_t x)
+    {
+        x = (x << 16) | (x >> 16);
+        x = ((x & 0x00ff00ff) << 8) | ((x & 0xff00ff00) >> 8);
+        x = ((x & 0x0f0f0f0f) << 4) | ((x & 0xf0f0f0f0) >> 4);
+        x = ((x & 0x33333333) << 2) | ((x & 0xcccccccc) >> 2);
+        x = ((x & 0x55555555) << 1) | ((x & 0xaaaaaaaa) >> 1);
+        return x;
+    }
+    static uint32_t owen_scramble(uint32_t p, uint32_t s)
+    {
+        p ^= p * 0x3d20adea; p += s; p *= (s >> 16) | 1; p ^= p * 0x05526c56; p ^= p * 0x53a22864;
+        return reversebits(p);
+    }
+    V3 get()
+    {
+        static const uint32_t zmatrix[24]
+            = { 0x000001u, 0x000003u, 0x000006u, 0x000009u, 0x000017u, 0x00003au, 0x000071u, 0x0000a3u,
+                0x000116u, 0x000339u, 0x000677u, 0x0009aau, 0x001601u, 0x003903u, 0x007706u, 0x00aa09u,
+                0x010117u, 0x03033au, 0x060671u, 0x0909a3u, 0x171616u, 0x3a3939u, 0x717777u, 0xa3aaaau };
+        seed += 4;
+        uint32_t si = owen_scramble(index, hash(seed - 4)) & 0xFFFFFF;
+        uint32_t rx = si, ry = 0, rz = 0, ymatrix = 1;
+        for (int c = 0; c < 24; c++) {
+            uint32_t bit = (si >> c) & 1;
+            ry ^= bit * ymatrix;
+            rz ^= bit * zmatrix[c];
+            ymatrix ^= ymatrix << 1;
+        }
+        return V3((owen_scramble(rx, hash(seed - 3)) >> 8) * 5.96046448e-8f,
+                  (owen_scramble(ry, hash(seed - 2)) >> 8) * 5.96046448e-8f,
+                  (owen_scramble(rz, hash(seed - 1)) >> 8) * 5.96046448e-8f);
+    }
+};
+
+// ---- sampling helpers -------------------------------------------------------------
+struct TangentFrame {
+    V3 u, v, w;
+    static TangentFrame from_normal(const V3& n)
+    {
+        const float sign = std::copysign(1.0f, n.z);
+        const float a    = -1 / (sign + n.z);
+        const float b    = n.x * n.y * a;
+        TangentFrame f;
+        f.u = V3(1 + sign * n.x * n.x * a, sign * b, -sign * n.x);
+        f.v = V3(b, sign + n.y * n.y * a, -n.y);
+        f.w = n;
+        return f;
+    }
+    V3 get(float x, float y, float z) const { return x * u + y * v + z * w; }
+};
+inline void to_unit_disk(float& x, float& y)
+{
+    const float PI_OVER_4 = float(M_PI_4), PI_OVER_2 = float(M_PI_2);
+    float phi, r;
+    float a = 2 * x - 1, b = 2 * y - 1;
+    if (a * a > b * b) {
+        r   = a;
+        phi = PI_OVER_4 * (b / a);
+    } else if (b != 0) {
+        r   = b;
+        phi = PI_OVER_2 - PI_OVER_4 * (a / b);
+    } else {
+        r   = 0;
+        phi = 0;
+    }
+    fast_sincos(phi, &x, &y);
+    x *= r;
+    y *= r;
+}
+inline void sample_cosine_hemisphere(const V3& N, float rndx, float rndy, V3& out, float& pdf)
+{
+    to_unit_disk(rndx, rndy);
+    float cos_theta = std::sqrt(std::max(1 - rndx * rndx - rndy * rndy, 0.0f));
+    out             = TangentFrame::from_normal(N).get(rndx, rndy, cos_theta);
+    pdf             = cos_theta * float(M_1_PI);
+}
+enum MISMode { WEIGHT_WEIGHT, WEIGHT_EVAL, EVAL_WEIGHT };
+template<MISMode mode> inline float power_heuristic(float sampled_pdf, float other_pdf)
+{
+    float r, mis;
+    if (sampled_pdf > other_pdf) {
+        r   = other_pdf / sampled_pdf;
+        mis = 1 / (1 + r * r);
+    } else if (sampled_pdf < other_pdf) {
+        r   = sampled_pdf / other_pdf;
+        mis = 1 - 1 / (1 + r * r);
+    } else {
+        r   = 1.0f;
+        mis = 0.5f;
+    }
+    const float MAX = std::numeric_limits<float>::max();
+    switch (mode) {
+    case WEIGHT_WEIGHT: return std::min(other_pdf, MAX) * mis;
+    case WEIGHT_EVAL: return mis;
+    case EVAL_WEIGHT: return mis * ((other_pdf > sampled_pdf) ? std::min(1 / r, MAX) : r);
+    }
+    return 0;
+}
+inline void update_eval(V3* w, float* pdf, V3 ow, float opdf, float b)
+{
+    if (b > std::numeric_limits<float>::min()) {
+        opdf *= b;
+        ow = ow * (1 / b);
+        float mis;
+        if (*pdf < opdf)
+            mis = 1 / (1 + *pdf / opdf);
+        else if (opdf < *pdf)
+            mis = 1 - 1 / (1 + opdf / *pdf);
+        else
+            mis = 0.5f;
+        *w = *w * (1 - mis) + ow * mis;
+        *pdf += opdf;
+    }
+}
+
+// ---- fresnel (optics.h) -----------------------------------------------------------
+inline float fresnel_dielectric(float cosi, float eta)
+{
+    if (eta == 0)
+        return 1;
+    if (cosi < 0.0f)
+        eta = 1.0f / eta;
+    float c = std::fabs(cosi);
+    float g = eta * eta - 1 + c * c;
+    if (g > 0) {
+        g       = std::sqrt(g);
+        float A = (g - c) / (g + c);
+        float B = (c * (g + c) - 1) / (c * (g - c) + 1);
+        return 0.5f * A * A * (1 + B * B);
+    }
+    return 1.0f;
+}
+inline float fresnel_refraction(const V3& I, const V3& N, float eta, V3& T)
+{
+    float cosi = -dot(I, N);
+    V3 Nn;
+    float neta;
+    if (cosi > 0) {
+        neta = 1 / eta;
+        Nn   = N;
+    } else {
+        cosi = -cosi;
+        neta = eta;
+        Nn   = -N;
+    }
+    float arg = 1.0f - (neta * neta * (1.0f - cosi * cosi));
+    if (arg >= 0) {
+        float dnp = std::sqrt(arg);
+        float nK  = (neta * cosi) - dnp;
+        T         = I * neta + Nn * nK;
+        return 1 - fresnel_dielectric(cosi, eta);
+    }
+    T = V3(0.0f);
+    return 0;
+}
+
+// ---- BSDF lobes -----------------------------------------------------------------
+struct BSample {
+    V3 wi, weight;
+    float pdf = 0, roughness = 0;
+    BSample() : wi(0.0f), weight(0.0f) {}
+    BSample(V3 wi, V3 w, float pdf, float r) : wi(wi), weight(w), pdf(pdf), roughness(r) {}
+};
+enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT };
+struct Lobe {
+    int type;
+    V3 N;
+    float eta;
+    V3 get_albedo(const V3& wo) const
+    {
+        switch (type) {
+        case LOBE_REFLECTION: {
+            float cosNO = dot(N, wo);
+            if (cosNO > 0)
+                return V3(fresnel_dielectric(cosNO, eta));
+            return V3(1.0f);
+        }
+        case LOBE_REFRACTION: return V3(1 - fresnel_dielectric(dot(N, wo), eta));
+        default: return V3(1.0f);
+        }
+    }
+    BSample eval(const V3& wo, const V3& wi) const
+    {
+        if (type == LOBE_DIFFUSE || type == LOBE_TRANSLUCENT) {
+            const float pdf = std::max(dot(N, wi), 0.0f) * float(M_1_PI);
+            return BSample(wi, V3(1.0f), pdf, 1.0f);
+        }
+        return BSample();
+    }
+    BSample sample(const V3& wo, float rx, float ry, float rz) const
+    {
+        switch (type) {
+        case LOBE_DIFFUSE:
+        case LOBE_TRANSLUCENT: {
+            V3 out;
+            float pdf;
+            sample_cosine_hemisphere(N, rx, ry, out, pdf);
+            return BSample(out, V3(1.0f), pdf, 1.0f);
+        }
+        case LOBE_REFLECTION: {
+            float cosNO = dot(N, wo);
+            if (cosNO > 0) {
+                V3 wi = (2 * cosNO) * N - wo;
+                return BSample(wi, V3(fresnel_dielectric(cosNO, eta)), std::numeric_limits<float>::infinity(), 0);
+            }
+            return BSample();
+        }
+        case LOBE_REFRACTION: {
+            V3 wi;
+            float Ft = fresnel_refraction(-wo, N, eta, wi);
+            return BSample(wi, V3(Ft), std::numeric_limits<float>::infinity(), 0);
+        }
+        case LOBE_TRANSPARENT: return BSample(-wo, V3(1.0f), std::numeric_limits<float>::infinity(), 0);
+        }
+        return BSample();
+    }
+};
+
+struct CompositeBSDF {
+    enum { MaxEntries = 8 };
+    V3 weights[MaxEntries];
+    float pdfs[MaxEntries];
+    Lobe lobes[MaxEntries];
+    int num = 0;
+    bool add(const V3& w, const Lobe& l)
+    {
+        if (num >= MaxEntries)
+            return false;
+        weights[num] = w;
+        lobes[num]   = l;
+        ++num;
+        return true;
+    }
+    void prepare(const V3& wo, const V3& path_weight, bool absorb)
+    {
+        float total = 0;
+        for (int i = 0; i < num; i++) {
+            pdfs[i] = dot(weights[i], path_weight * lobes[i].get_albedo(wo))
+                      / (path_weight.x + path_weight.y + path_weight.z);
+            total += pdfs[i];
+        }
+        if ((!absorb && total > 0) || total > 1)
+            for (int i = 0; i < num; i++)
+                pdfs[i] /= total;
+    }
+    BSample eval(const V3& wo, const V3& wi) const
+    {
+        BSample s;
+        for (int i = 0; i < num; i++) {
+            BSample b = lobes[i].eval(wo, wi);
+            b.weight  = b.weight * weights[i];
+            update_eval(&s.weight, &s.pdf, b.weight, b.pdf, pdfs[i]);
+            s.roughness += b.roughness * pdfs[i];
+        }
+        return s;
+    }
+    BSample sample(const V3& wo, float rx, float ry, float rz) const
+    {
+        float accum = 0;
+        for (int i = 0; i < num; i++) {
+            if (rx < (pdfs[i] + accum)) {
+                rx        = (rx - accum) / pdfs[i];
+                rx        = std::min(rx, 0.99999994f);
+                BSample s = lobes[i].sample(wo, rx, ry, rz);
+                s.weight  = s.weight * (weights[i] * (1 / pdfs[i]));
+                s.pdf *= pdfs[i];
+                if (s.pdf == 0.0f)
+                    return BSample();
+                for (int j = 0; j < num; j++) {
+                    if (i != j) {
+                        BSample b = lobes[j].eval(wo, s.wi);
+                        b.weight  = b.weight * weights[j];
+                        update_eval(&s.weight, &s.pdf, b.weight, b.pdf, pdfs[j]);
+                    }
+                }
+                return s;
+            }
+            accum += pdfs[i];
+        }
+        return BSample();
+    }
+};
+struct ShadingResult {
+    V3 Le = V3(0.0f);
+    CompositeBSDF bsdf;
+};
+
+// process_bsdf_closure: explicit 16-deep stack, weights multiplied root->leaf
+inline void process_closure(const SG& sg, ShadingResult& result, const Clos* closure, bool light_only)
+{
+    if (!closure)
+        return;
+    const int STACK_SIZE = 16;
+    int stack_idx        = 0;
+    const Clos* ptr_stack[STACK_SIZE];
+    V3 weight_stack[STACK_SIZE];
+    V3 weight(1.0f);
+    while (closure) {
+        switch (closure->id) {
+        case CL_MUL:
+            weight  = weight * ((const ClosMul*)closure)->weight;
+            closure = ((const ClosMul*)closure)->closure;
+            break;
+        case CL_ADD:
+            ptr_stack[stack_idx]      = ((const ClosAdd*)closure)->b;
+            weight_stack[stack_idx++] = weight;
+            closure                   = ((const ClosAdd*)closure)->a;
+            break;
+        default: {
+            const ClosComp* comp = (const ClosComp*)closure;
+            V3 cw                = weight * comp->w;
+            closure              = nullptr;
+            if (comp->id == EMISSION_ID)
+                result.Le = result.Le + cw;
+            else if (!light_only) {
+                Lobe l;
+                l.N   = V3(comp->params[0], comp->params[1], comp->params[2]);
+                l.eta = 0.0f;
+                bool known = true;
+                switch (comp->id) {
+                case DIFFUSE_ID: l.type = LOBE_DIFFUSE; break;
+                case TRANSLUCENT_ID: l.type = LOBE_TRANSLUCENT; l.N = -l.N; break;
+                case REFLECTION_ID: l.type = LOBE_REFLECTION; break;
+                case FRESNEL_REFLECTION_ID: l.type = LOBE_REFLECTION; l.eta = comp->params[3]; break;
+                case REFRACTION_ID: l.type = LOBE_REFRACTION; l.eta = comp->params[3]; break;
+                case TRANSPARENT_ID:
+                case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
+                default: known = false; break;
+                }
+                if (known)
+                    result.bsdf.add(cw, l);
+            }
+            break;
+        }
+        }
+        if (closure == nullptr && stack_idx > 0) {
+            closure = ptr_stack[--stack_idx];
+            weight  = weight_stack[stack_idx];
+        }
+    }
+}
+
+// ---- scene queries ----------------------------------------------------------------
+struct Intersection {
+    float t, u, v;
+    unsigned id;
+};
+inline float compf(const V3& v, int i) { return (&v.x)[i]; }
+inline float minf_(float a, float b) { return b < a ? b : a; }
+inline float maxf_(float a, float b) { return b > a ? b : a; }
+inline bool box_intersect(const V3& org, const V3& rdir, float tmax, const float* bounds, float* dist)
+{
+    const float tx1 = (bounds[0] - org.x) * rdir.x, tx2 = (bounds[1] - org.x) * rdir.x;
+    const float ty1 = (bounds[2] - org.y) * rdir.y, ty2 = (bounds[3] - org.y) * rdir.y;
+    const float tz1 = (bounds[4] - org.z) * rdir.z, tz2 = (bounds[5] - org.z) * rdir.z;
+    float tmin      = minf_(tx1, tx2);
+    tmax            = minf_(tmax, maxf_(tx1, tx2));
+    tmin            = maxf_(tmin, minf_(ty1, ty2));
+    tmax            = minf_(tmax, maxf_(ty1, ty2));
+    tmin            = maxf_(tmin, minf_(tz1, tz2));
+    tmax            = minf_(tmax, maxf_(tz1, tz2));
+    *dist           = tmin;
+    tmin            = maxf_(0.0f, tmin);
+    return tmin <= tmax;
+}
+inline float xorf(float a, unsigned b) { return u2f(f2u(a) ^ b); }
+
+inline Intersection scene_intersect(const RenderScene& S, const Ray& ray, const float tmax, unsigned skipID1,
+                                    unsigned skipID2 = ~0u)
+{
+    struct StackItem {
+        int node;
+        float dist;
+    } stack[64];
+    Intersection result;
+    result.t  = tmax;
+    result.u  = result.v = 0;
+    result.id = 0;
+    stack[0]  = { 0, result.t };
+    const V3 org = ray.origin, dir = ray.direction;
+    const V3 rdir(1 / dir.x, 1 / dir.y, 1 / dir.z);
+    int kz = 0;
+    if (std::fabs(dir.y) > std::fabs(compf(dir, kz)))
+        kz = 1;
+    if (std::fabs(dir.z) > std::fabs(compf(dir, kz)))
+        kz = 2;
+    int kx = kz == 2 ? 0 : kz + 1;
+    int ky = kx == 2 ? 0 : kx + 1;
+    const V3 shearDir(compf(dir, kx) / compf(dir, kz), compf(dir, ky) / compf(dir, kz), compf(rdir, kz));
+    for (int stackPtr = 1; stackPtr != 0;) {
+        if (result.t < stack[--stackPtr].dist)
+            continue;
+        const float* node = S.bvh_nodes + 8 * stack[stackPtr].node;
+        unsigned child = f2u(node[6]), nprims = f2u(node[7]);
+        if (nprims) {
+            for (unsigned i = 0; i < nprims; i++) {
+                unsigned id = S.bvh_indices[child + i];
+                const V3 A = vert(S, S.triangles[3 * id]) - org, B = vert(S, S.triangles[3 * id + 1]) - org,
+                         C = vert(S, S.triangles[3 * id + 2]) - org;
+                const float Ax = compf(A, kx) - shearDir.x * compf(A, kz);
+                const float Ay = compf(A, ky) - shearDir.y * compf(A, kz);
+                const float Bx = compf(B, kx) - shearDir.x * compf(B, kz);
+                const float By = compf(B, ky) - shearDir.y * compf(B, kz);
+                const float Cx = compf(C, kx) - shearDir.x * compf(C, kz);
+                const float Cy = compf(C, ky) - shearDir.y * compf(C, kz);
+                const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+                if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
+                    continue;
+                const float det = U + V + W;
+                if (det == 0)
+                    continue;
+                const float Az = compf(A, kz), Bz = compf(B, kz), Cz = compf(C, kz);
+                const float T       = shearDir.z * (U * Az + V * Bz + W * Cz);
+                const unsigned mask = f2u(det) & 0x80000000u;
+                if (xorf(T, mask) < 0)
+                    continue;
+                if (xorf(T, mask) > result.t * xorf(det, mask))
+                    continue;
+                if (id == skipID1 || id == skipID2)
+                    continue;
+                const float rcpDet = 1 / det;
+                result.t  = T * rcpDet;
+                result.u  = V * rcpDet;
+                result.v  = W * rcpDet;
+                result.id = id;
+            }
+        } else {
+            int child1 = (int)child, child2 = child1 + 1;
+            float dist1 = 0, dist2 = 0;
+            bool hit1 = box_intersect(org, rdir, result.t, S.bvh_nodes + 8 * child1, &dist1);
+            bool hit2 = box_intersect(org, rdir, result.t, S.bvh_nodes + 8 * child2, &dist2);
+            if (dist1 > dist2) {
+                std::swap(hit1, hit2);
+                std::swap(dist1, dist2);
+                std::swap(child1, child2);
+            }
+            stack[stackPtr] = { child2, dist2 };
+            stackPtr += hit2;
+            stack[stackPtr] = { child1, dist1 };
+            stackPtr += hit1;
+        }
+    }
+    return result;
+}
+
+struct LightSample {
+    V3 dir;
+    float dist, pdf, u, v;
+};
+inline LightSample scene_sample(const RenderScene& S, int primID, const V3& x, float xi, float yi)
+{
+    if (yi > xi) {
+        xi *= 0.5f;
+        yi -= xi;
+    } else {
+        yi *= 0.5f;
+        xi -= yi;
+    }
+    const V3 va = vert(S, S.triangles[3 * primID]), vb = vert(S, S.triangles[3 * primID + 1]),
+             vc = vert(S, S.triangles[3 * primID + 2]);
+    const V3 n  = cross(va - vb, va - vc);
+    V3 l        = ((1 - xi - yi) * va + xi * vb + yi * vc) - x;
+    float d2    = length2(l);
+    V3 dir      = normalized(l);
+    float pdf   = d2 / (0.5f * std::fabs(dot(dir, n)));
+    return { dir, std::sqrt(d2), pdf, xi, yi };
+}
+inline float scene_shapepdf(const RenderScene& S, int primID, const V3& x, const V3& p)
+{
+    const V3 va = vert(S, S.triangles[3 * primID]), vb = vert(S, S.triangles[3 * primID + 1]),
+             vc = vert(S, S.triangles[3 * primID + 2]);
+    const V3 n  = cross(va - vb, va - vc);
+    V3 l        = p - x;
+    float d2    = length2(l);
+    V3 dir      = normalized(l);
+    return d2 / (0.5f * std::fabs(dot(dir, n)));
+}
+inline V3 scene_normal(const RenderScene& S, V3& Ng, int primID, float u, float v)
+{
+    const V3 va = vert(S, S.triangles[3 * primID]), vb = vert(S, S.triangles[3 * primID + 1]),
+             vc = vert(S, S.triangles[3 * primID + 2]);
+    Ng = normalized(cross(va - vb, va - vc));
+    if (S.n_triangles[3 * primID] < 0)
+        return Ng;
+    const V3 na = nrm(S, S.n_triangles[3 * primID]), nb = nrm(S, S.n_triangles[3 * primID + 1]),
+             nc = nrm(S, S.n_triangles[3 * primID + 2]);
+    return normalized((1 - u - v) * na + u * nb + v * nc);
+}
+inline void scene_project(Dv& p, const V3& N, const V3& I)
+{
+    V3 nI      = normalized(I);
+    float cosI = dot(-nI, N);
+    if (std::fabs(cosI) > 1e-3f) {
+        float deltaX = dot(p.dx, N) / cosI;
+        float deltaY = dot(p.dy, N) / cosI;
+        p.dx = p.dx + nI * deltaX;
+        p.dy = p.dy + nI * deltaY;
+    }
+}
+struct V2 {
+    float x, y;
+};
+// Scene::uv (raytracer.h:263-300): returns uv value + screen derivatives
+inline void scene_uv(const RenderScene& S, const Dv& p, const V3& n, V3& dPdu, V3& dPdv, int primID, float u,
+                     float v, V2& uvv, V2& uvdx, V2& uvdy)
+{
+    uvv = uvdx = uvdy = { 0, 0 };
+    if (S.uv_triangles[3 * primID] < 0)
+        return;
+    auto UV = [&](int i) { return V2 { S.uvs[2 * i], S.uvs[2 * i + 1] }; };
+    const V2 ta = UV(S.uv_triangles[3 * primID]), tb = UV(S.uv_triangles[3 * primID + 1]),
+             tc = UV(S.uv_triangles[3 * primID + 2]);
+    const V3 va = vert(S, S.triangles[3 * primID]), vb = vert(S, S.triangles[3 * primID + 1]),
+             vc = vert(S, S.triangles[3 * primID + 2]);
+    const V2 dt02 = { ta.x - tc.x, ta.y - tc.y }, dt12 = { tb.x - tc.x, tb.y - tc.y };
+    const V3 dp02 = va - vc, dp12 = vb - vc;
+    const float det = dt02.x * dt12.y - dt02.y * dt12.x;
+    if (det != 0) {
+        float invdet = 1 / det;
+        dPdu         = (dt12.y * dp02 - dt02.y * dp12) * invdet;
+        dPdv         = (-dt12.x * dp02 + dt02.x * dp12) * invdet;
+    }
+    V3 La = cross(n, vc - vb);
+    La    = La / dot(va - vb, La);
+    V3 Lb = cross(n, va - vc);
+    Lb    = Lb / dot(vb - vc, Lb);
+    V3 Lc = cross(n, vb - va);
+    Lc    = Lc / dot(vc - va, Lc);
+    auto comb = [&](float a, float b, float c) {
+        return V2 { a * ta.x + b * tb.x + c * tc.x, a * ta.y + b * tb.y + c * tc.y };
+    };
+    uvdx = comb(dot(La, p.dx), dot(Lb, p.dx), dot(Lc, p.dx));
+    uvdy = comb(dot(La, p.dy), dot(Lb, p.dy), dot(Lc, p.dy));
+    uvv  = comb(1 - u - v, u, v);
+}
+
+inline void globals_from_hit(const RenderScene& S, SG& sg, const Ray& r, float t, int id, float u, float v)
+{
+    Dv direction = r.dual_direction();
+    sg.I         = direction;
+    Dv P         = r.point_dual(t);
+    V3 Ng;
+    sg.N = scene_normal(S, Ng, id, u, v);
+    scene_project(P, sg.N, sg.I.val);
+    sg.P = P;
+    V3 dPdu(0.0f), dPdv(0.0f);
+    V2 uv, uvdx, uvdy;
+    scene_uv(S, P, sg.N, dPdu, dPdv, id, u, v, uv, uvdx, uvdy);
+    sg.dPdu = dPdu;
+    sg.dPdv = dPdv;
+    sg.u    = Df(uv.x, uvdx.x, uvdy.x);
+    sg.v    = Df(uv.y, uvdx.y, uvdy.y);
+    sg.surfacearea = S.mesh_surfacearea[S.meshids[id]];
+    sg.backfacing  = dot(Ng, sg.I.val) > 0;
+    if (sg.backfacing) {
+        sg.N = -sg.N;
+        Ng   = -Ng;
+    }
+    sg.Ng             = Ng;
+    sg.raytype        = r.raytype;
+    sg.flipHandedness = dot(cross(sg.P.dx, sg.P.dy), sg.N) < 0;
+    sg.dPdz = V3(0.0f);
+    sg.time = sg.dtime = 0.0f;
+    sg.dPdtime = V3(0.0f);
+    sg.Ps      = Dv(V3(0.0f));
+}
+
+typedef void (*ShaderFn)(SG& sg);
+
+struct Renderer {
+    const RenderScene& S;
+    const ShaderFn* shaders;
+    Ctx* ctx;
+
+    void execute(int shaderID, SG& sg, ClosurePool& pool) const
+    {
+        pool.reset();
+        sg.pool = &pool;
+        sg.Ci   = nullptr;
+        sg.ctx  = ctx;
+        sg.shadeindex = 0;
+        shaders[shaderID](sg);
+    }
+
+    V3 subpixel_radiance(float x, float y, Sampler& sampler) const
+    {
+        const float inf = std::numeric_limits<float>::infinity();
+        Ray r           = camera_ray(S, x, y);
+        V3 path_weight(1.0f), path_radiance(0.0f);
+        int prev_id    = -1;
+        float bsdf_pdf = inf;
+        ClosurePool pool, light_pool;
+        for (int b = 0; b <= S.max_bounces; b++) {
+            SG sg;
+            Intersection hit = scene_intersect(S, r, inf, (unsigned)prev_id);
+            if (hit.t == inf)
+                break;  // no background in the restated configs
+            globals_from_hit(S, sg, r, hit.t, hit.id, hit.u, hit.v);
+            if (S.show_globals) {
+                V3 v = sg.Ng;
+                if (S.show_globals == 2) v = sg.N;
+                if (S.show_globals == 3) v = normalized(sg.dPdu);
+                if (S.show_globals == 4) v = normalized(sg.dPdv);
+                if (S.show_globals == 5) v = V3(sg.u.val, sg.v.val, 0);
+                V3 c = v;
+                if (S.show_globals != 5)
+                    c = c * 0.5f + V3(0.5f);
+                path_radiance = path_radiance + path_weight * c;
+                break;
+            }
+            const float radius = r.radius + r.spread * hit.t;
+            int shaderID       = S.shaderids[hit.id];
+            if (shaderID < 0)
+                break;
+            execute(shaderID, sg, pool);
+            ShadingResult result;
+            bool last_bounce = b == S.max_bounces;
+            process_closure(sg, result, sg.Ci, last_bounce);
+            const int nlights = S.nlightprims;
+            float k           = 1;
+            if (S.shader_is_light[shaderID] && nlights > 0) {
+                const float light_pick_pdf = 1.0f / nlights;
+                float light_pdf = light_pick_pdf * scene_shapepdf(S, hit.id, r.origin, sg.P.val);
+                k               = power_heuristic<WEIGHT_EVAL>(bsdf_pdf, light_pdf);
+            }
+            path_radiance = path_radiance + path_weight * k * result.Le;
+            if (last_bounce)
+                break;
+            result.bsdf.prepare(-sg.I.val, path_weight, b >= S.rr_depth);
+            V3 s     = sampler.get();
+            float xi = s.x, yi = s.y, zi = s.z;
+            if (nlights > 0) {
+                const float light_pick_pdf = 1.0f / nlights;
+                float xl = xi * nlights;
+                int ls   = (int)std::floor(xl);
+                xl -= ls;
+                unsigned lid = S.lightprims[ls];
+                if (lid != hit.id) {
+                    int lshader       = S.shaderids[lid];
+                    LightSample sample = scene_sample(S, lid, sg.P.val, xl, yi);
+                    BSample bs         = result.bsdf.eval(-sg.I.val, sample.dir);
+                    V3 contrib = path_weight * bs.weight
+                                 * power_heuristic<EVAL_WEIGHT>(light_pick_pdf * sample.pdf, bs.pdf);
+                    if ((contrib.x + contrib.y + contrib.z) > 0) {
+                        Ray shadow_ray { sg.P.val, sample.dir, radius, 0, 0, RAY_SHADOW };
+                        Intersection sh = scene_intersect(S, shadow_ray, sample.dist, hit.id, lid);
+                        if (sh.t == sample.dist) {
+                            SG lsg;
+                            globals_from_hit(S, lsg, shadow_ray, sample.dist, lid, sample.u, sample.v);
+                            execute(lshader, lsg, light_pool);
+                            ShadingResult lres;
+                            process_closure(lsg, lres, lsg.Ci, true);
+                            path_radiance = path_radiance + contrib * lres.Le;
+                        }
+                    }
+                }
+            }
+            BSample p   = result.bsdf.sample(-sg.I.val, xi, yi, zi);
+            path_weight = path_weight * p.weight;
+            bsdf_pdf    = p.pdf;
+            r.raytype   = RAY_DIFFUSE;
+            r.direction = p.wi;
+            r.radius    = radius;
+            r.spread    = std::max(r.spread, p.roughness);
+            r.roughness = p.roughness;
+            if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
+                break;
+            prev_id  = hit.id;
+            r.origin = sg.P.val;
+        }
+        return path_radiance;
+    }
+
+    V3 antialias_pixel(int x, int y) const
+    {
+        V3 result(0.0f);
+        for (int si = 0, n = S.aa * S.aa; si < n; si++) {
+            Sampler sampler(x, y, si);
+            V3 j = S.no_jitter ? V3(0.5f, 0.5f, 0) : sampler.get();
+            j.x *= 2;
+            j.x = j.x < 1 ? std::sqrt(j.x) - 1 : 1 - std::sqrt(2 - j.x);
+            j.y *= 2;
+            j.y = j.y < 1 ? std::sqrt(j.y) - 1 : 1 - std::sqrt(2 - j.y);
+            V3 r     = subpixel_radiance(x + 0.5f + j.x, y + 0.5f + j.y, sampler);
+            float t  = 1.0f / (si + 1);
+            result   = result * (1.0f - t) + r * t;
+        }
+        return result;
+    }
+};
+
+}  // namespace oslo

@@ -38,7 +38,12 @@ struct Ctx {
     std::string* out;  // printf capture (NULL: discard)
 };
 
+struct Clos;
+struct ClosurePool;
+
 struct SG {
+    const Clos* Ci    = nullptr;  // closure output (surface shaders)
+    ClosurePool* pool = nullptr;  // per-point closure arena (renderer-owned)
     Dv P;
     V3 dPdz;
     Dv I;

@@ -337,14 +337,26 @@ CMP = {"eq": "==", "neq": "!=", "lt": "<", "gt": ">", "le": "<=", "ge": ">="}
 INTBIN = {"bitand": "&", "bitor": "|", "xor": "^", "shl": "<<", "shr": ">>"}
 NOISE_KIND = {"noise": "N_NOISE", "uperlin": "N_NOISE", "snoise": "N_SNOISE",
               "perlin": "N_SNOISE", "cellnoise": "N_CELL", "cell": "N_CELL",
-              "hashnoise": "N_HASH", "hash": "N_HASH"}
+              "hashnoise": "N_HASH", "hash": "N_HASH", "simplex": "N_SIMPLEX",
+              "simplexnoise": "N_SIMPLEX", "usimplex": "N_USIMPLEX",
+              "usimplexnoise": "N_USIMPLEX"}
 PNOISE_KIND = {"pnoise": "N_NOISE", "psnoise": "N_SNOISE", "pcellnoise": "N_CELL",
                "phashnoise": "N_HASH", "noise": "N_NOISE", "uperlin": "N_NOISE",
                "snoise": "N_SNOISE", "perlin": "N_SNOISE", "cell": "N_CELL",
                "cellnoise": "N_CELL", "hash": "N_HASH", "hashnoise": "N_HASH"}
 SG_GLOBALS = {"P": "sg.P", "I": "sg.I", "N": "sg.N", "Ng": "sg.Ng", "u": "sg.u",
               "v": "sg.v", "dPdu": "sg.dPdu", "dPdv": "sg.dPdv", "Ps": "sg.Ps",
-              "time": "sg.time", "dtime": "sg.dtime", "dPdtime": "sg.dPdtime"}
+              "time": "sg.time", "dtime": "sg.dtime", "dPdtime": "sg.dPdtime", "Ci": "sg.Ci"}
+
+# closure registry of the testrender renderer (src/testrender/shading.cpp:194-297):
+# (name, number of positional params) -> closure id constant
+CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
+            ("diffuse", 1): "DIFFUSE_ID", ("oren_nayar", 2): "OREN_NAYAR_ID",
+            ("translucent", 1): "TRANSLUCENT_ID", ("phong", 2): "PHONG_ID",
+            ("ward", 4): "WARD_ID", ("microfacet", 7): "MICROFACET_ID",
+            ("reflection", 1): "REFLECTION_ID", ("reflection", 2): "FRESNEL_REFLECTION_ID",
+            ("refraction", 2): "REFRACTION_ID", ("transparent", 0): "TRANSPARENT_ID",
+            ("transparent_bsdf", 0): "MX_TRANSPARENT_ID"}
 
 
 class Gen:
@@ -373,7 +385,7 @@ class Gen:
         if b == "matrix":
             return "M44"
         if b == "closure color":
-            return "Clos*"
+            return "const Clos*"
         raise NotImplementedError("type %s" % s.t)
 
     def ref(self, l, s):
@@ -434,10 +446,41 @@ class Gen:
         return [one(vals[i * per:(i + 1) * per]) for i in range(n)]
 
     # -- group --------------------------------------------------------------
+    def generate_material(self, ns):
+        """Group as a callable `void <ns>::entry(SG&)` (the renderer executes
+        one point at a time: simpleraytracer.cpp:1034)."""
+        g = self.g
+        o = self.out
+        o.append("namespace %s {" % ns)
+        o.append("struct GD {")
+        o.append("    bool ran[%d];" % max(1, len(g.layers)))
+        for l in g.layers:
+            if l.unused:
+                continue
+            for s in l.m.syms:
+                if s.symtype in ("param", "oparam"):
+                    arr = "[%d]" % s.t.arr if s.t.arr else ""
+                    o.append("    %s L%d_%s%s;" % (self.ctype(s), l.idx, self.ident(s.name), arr))
+        o.append("};")
+        used = [l for l in g.layers if not l.unused]
+        for l in used:
+            o.append("static void layer_%d(SG& sg, GD& gd, const Launch* L);" % l.idx)
+        for l in used:
+            self.gen_layer(l)
+        o.append("static void entry(SG& sg)")
+        o.append("{")
+        o.append("    GD gd;")
+        o.append("    for (int k = 0; k < %d; ++k) gd.ran[k] = false;" % max(1, len(g.layers)))
+        o.append("    layer_%d(sg, gd, nullptr);" % (len(g.layers) - 1))
+        o.append("}")
+        o.append("}  // namespace %s" % ns)
+        return "\n".join(o) + "\n"
+
     def generate(self):
         g = self.g
         o = self.out
         o.append("// generated by oracle/oso2cpp.py — CPU oracle, test infrastructure only")
+        o.append('#include "osl_oracle_closure.h"')
         o.append('#include "osl_oracle_runtime.h"')
         o.append("using namespace oslo;")
         o.append("namespace {")
@@ -1001,7 +1044,70 @@ class Gen:
             self.w("pf_lit(sg, %s);" % cstr(lit))
 
     def op_closure_arith(self, op):
-        raise NotImplementedError("closures not yet supported by the oracle generator")
+        """mul / add on closures (llvm_gen_mul / llvm_gen_add closure branches ->
+        osl_mul_closure_{float,color}, osl_add_closure_closure)."""
+        d, a, b = op.args
+        if op.name == "add":
+            self.w("%s = clos_add(sg.pool, %s, %s);" % (self.R(d), self.R(a), self.R(b)))
+            return
+        if op.name != "mul":
+            raise NotImplementedError("closure op %s" % op.name)
+        if a.t.base != "closure color":
+            a, b = b, a
+        w = self.R(b)
+        if b.has_derivs:
+            w = "nd(%s)" % w
+        if b.t.base == "int":
+            w = "(float)%s" % w
+        self.w("%s = clos_mul(sg.pool, %s, %s);" % (self.R(d), self.R(a), w))
+
+    def op_closure(self, op):
+        """llvm_gen_closure (llvm_gen.cpp:3786-3903): allocate a component,
+        optionally weighted, and copy the positional params into its block."""
+        A = list(op.args)
+        d = A[0]
+        rest = A[1:]
+        weight = None
+        if rest[0].t.base != "string":
+            weight = rest[0]
+            rest = rest[1:]
+        name = rest[0].vals[0]
+        params = []
+        for a in rest[1:]:
+            if a.t.base == "string" and not params and False:
+                break
+            params.append(a)
+        # keyword params ("label", value) are trailing string/value pairs: drop them
+        pos = []
+        i = 0
+        while i < len(params):
+            a = params[i]
+            if a.t.base == "string" and a.constval and i + 1 < len(params) and \
+                    (name, len(pos)) in CLOSURES:
+                break
+            pos.append(a)
+            i += 1
+        key = (name, len(pos))
+        if key not in CLOSURES:
+            raise NotImplementedError("closure %s with %d params is not registered" % key)
+        nwords = sum(a.t.ncomp for a in pos)
+        wexpr = "nullptr"
+        if weight is not None:
+            self.w("V3 w_; assign(w_, %s);" % self.R(weight))
+            wexpr = "&w_"
+        self.w("ClosComp* c_ = clos_component(sg.pool, %s, %d, %s);" % (CLOSURES[key], nwords, wexpr))
+        self.w("if (c_) {")
+        off = 0
+        for a in pos:
+            e = self.R(a)
+            if a.has_derivs:
+                e = "nd(%s)" % e
+            if a.t.base == "string":
+                raise NotImplementedError("string closure params")
+            self.w("    putp(c_->params + %d, %s);" % (off, e))
+            off += a.t.ncomp
+        self.w("}")
+        self.w("%s = c_;" % self.R(d))
 
 
 RAYTYPES = ["camera", "shadow", "reflection", "refraction", "diffuse", "glossy",
@@ -1038,13 +1144,67 @@ extern "C" const char* oracle_run_capture(const Launch* L, long long begin, long
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+RENDER_TAIL = r"""
+static void oracle_render_rows(const RenderScene* S, int y0, int y1, float* out, std::string* pf)
+{
+    Ctx ctx{pf};
+    Renderer R{*S, g_shaders, &ctx};
+    for (int y = y0; y < y1; ++y)
+        for (int x = 0; x < S->xres; ++x) {
+            V3 c = R.antialias_pixel(x, y);
+            float* p = out + 3 * ((long long)y * S->xres + x);
+            p[0] = c.x; p[1] = c.y; p[2] = c.z;
+        }
+}
+extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
+{
+    RenderScene S1 = *S0;
+    camera_finalize(S1);
+    const RenderScene* S = &S1;
+    // scanline-parallel like the reference (parallel_for_chunked, simpleraytracer.cpp:1428)
+    if (nthreads <= 1) { oracle_render_rows(S, 0, S->yres, out, nullptr); return; }
+    std::vector<std::thread> th;
+    std::atomic<int> next{0};
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&] {
+            for (;;) {
+                int y = next.fetch_add(4);
+                if (y >= S->yres) break;
+                oracle_render_rows(S, y, std::min(S->yres, y + 4), out, nullptr);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+"""
+
+
+def generate_render_module(groups):
+    """One translation unit holding every material group of a scene plus the
+    restated path tracer (osl_oracle_render.h)."""
+    out = ["// generated by oracle/oso2cpp.py — CPU oracle render module, test infrastructure only",
+           '#include "osl_oracle_render.h"', "#include <atomic>", "using namespace oslo;"]
+    for k, g in enumerate(groups):
+        out.append(Gen(g).generate_material("mat%d" % k))
+    out.append("static const ShaderFn g_shaders[] = {%s};" % ", ".join(
+        "mat%d::entry" % k for k in range(len(groups))))
+    out.append(RENDER_TAIL)
+    return "\n".join(out) + "\n"
+
+
+def build_render(groups, workdir=None, opt="-O2", extra_flags=()):
+    return _compile(generate_render_module(groups), workdir, opt, extra_flags)
+
+
 def build_group(group, workdir=None, opt="-O2", extra_flags=()):
     """Generate + compile; returns path of the shared object."""
-    src = Gen(group).generate()
+    return _compile(Gen(group).generate(), workdir, opt, extra_flags)
+
+
+def _compile(src, workdir=None, opt="-O2", extra_flags=()):
     workdir = workdir or os.path.join(HERE, "_build")
     os.makedirs(workdir, exist_ok=True)
     hdrs = b""
-    for h in ("osl_oracle.h", "osl_oracle_ops.h", "osl_oracle_runtime.h"):
+    for h in sorted(f for f in os.listdir(HERE) if f.endswith(".h")):
         with open(os.path.join(HERE, h), "rb") as f:
             hdrs += f.read()
     key = hashlib.sha1(src.encode() + hdrs + opt.encode() + " ".join(extra_flags).encode()).hexdigest()[:16]

@@ -46,6 +46,7 @@ IMAGE_CASES = {
     "noise-cell": dict(shader="testnoise", res=512,
                        params=dict(noisename="cell", offset=0.0, scale=1.0)),
     "noise-perlin": dict(shader="testnoise", res=512, params=dict(noisename="perlin")),
+    "noise-simplex": dict(shader="testnoise", res=512, params=dict(noisename="simplex")),
     "pnoise": dict(shader="pnoise_test", res=512, params={}),
     "pnoise-cell": dict(shader="testpnoise", res=512,
                         params=dict(noisename="cell", offset=0.0, scale=1.0)),

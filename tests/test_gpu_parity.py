@@ -43,6 +43,21 @@ def test_shadeop_noise_matches_oracle_bitexact(b200lib, cuda_device, kind, outdi
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("kind", ["simplex", "usimplex"])
+@pytest.mark.parametrize("outdim", [1, 3])
+@pytest.mark.parametrize("indim", [1, 2, 3, 4])
+def test_shadeop_simplex_matches_oracle_bitexact(b200lib, cuda_device, kind, outdim, indim):
+    import torch
+    rng = np.random.default_rng(5000 + indim * 10 + outdim)
+    n = 20011
+    for derivs in (False, True):
+        x = _rand_inputs(rng, indim * (3 if derivs else 1), n, scale=23.0)
+        want = oracle.noise(kind, outdim, x, derivs=derivs)
+        d_out = torch.zeros((outdim * (3 if derivs else 1), n), dtype=torch.float32, device=cuda_device)
+        b200lib.shadeop_noise(kind, outdim, indim, n, torch.from_numpy(x).to(cuda_device), d_out, derivs=derivs)
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), want.view(np.uint32)), (derivs,)
+
+
 @pytest.mark.parametrize("kind", ["noise", "snoise"])
 @pytest.mark.parametrize("outdim", [1, 3])
 @pytest.mark.parametrize("indim", [1, 2, 3, 4])

@@ -53,6 +53,7 @@ IMAGES = {
     "hashnoise": "hashnoise/ref/out.tif",
     "noise-cell": "noise-cell/ref/out.tif",
     "noise-perlin": "noise-perlin/ref/out.tif",
+    "noise-simplex": "noise-simplex/ref/out.tif",
     "pnoise": "pnoise/ref/out.tif",
     "pnoise-cell": "pnoise-cell/ref/out.tif",
     "pnoise-perlin": "pnoise-perlin/ref/out.tif",

@@ -1620,7 +1620,7 @@ class Compiler:
                             break
                         derivs.append(k)
                         k += 1
-        self.emit(name, args, "".join(rw), derivs=derivs)
+        self.emit("closure" if rt.is_closure else name, args, "".join(rw), derivs=derivs)
         # write-back for indexed output args
         for w in writes:
             a = n.args[w]
