@@ -158,6 +158,52 @@ int b200_shadeop_noise(int kind, int outdim, int indim, int derivs, int fma,
 /* osl_hash_* (builtindecl.h:169-173): indim floats per point -> int32 */
 int b200_shadeop_hash(int indim, long long n, const float* in, int* out, void* stream);
 
+/* ---- wavefront path tracer (the testrender hot path) ------------------------
+ * Replaces SimpleRaytracer::render / antialias_pixel / subpixel_radiance
+ * (src/testrender/simpleraytracer.cpp:957-1216, 1424-1456) and, for the OptiX
+ * variant, optixLaunch of __raygen__deferred (src/testrender/cuda/optix_raytracer.cu:291).
+ * The renderer keeps owning scene loading, tessellation and the BVH build
+ * (bvh.cpp:43-219); it hands over the prepared arrays (HOST pointers, copied
+ * to the device once) plus one group description per material. */
+typedef struct b200_render_scene {
+    int nverts, ntris, nnodes, nlightprims, nshaders, nmeshes;
+    const float* verts;            /* 3 per vertex (Scene::verts)              */
+    const float* normals;          /* 3 per normal                             */
+    const float* uvs;              /* 2 per uv                                 */
+    const int* triangles;          /* 3 per triangle (TriangleIndices)         */
+    const int* n_triangles;        /* 3 per triangle, -1 = none                */
+    const int* uv_triangles;       /* 3 per triangle, -1 = none                */
+    const int* shaderids;          /* per triangle                             */
+    const int* meshids;            /* per triangle                             */
+    const float* mesh_surfacearea; /* per mesh (m_mesh_surfacearea)            */
+    const float* bvh_nodes;        /* 8 words per BVHNode: bounds[6],child,nprims (bvh.h) */
+    const unsigned* bvh_indices;
+    const unsigned* lightprims;    /* m_lightprims                             */
+    const int* shader_is_light;    /* per material                             */
+    float eye[3], dir[3], up[3], fov;   /* Camera::lookat arguments            */
+    float cx[3], cy[3], invw, invh;     /* derived; filled by the library      */
+    int xres, yres;
+    int aa, max_bounces, rr_depth, no_jitter, show_globals; /* testrender options */
+    int background_shader, background_resolution;
+} b200_render_scene;
+
+typedef struct b200_render_stats {
+    long long paths;        /* camera samples traced                           */
+    long long launches;     /* kernels launched                                */
+    long long bounce_iterations;
+    double device_ms;       /* CUDA-event time of the whole call               */
+} b200_render_stats;
+
+typedef struct b200_render b200_render;
+
+/* options: fma=0|1, sort=0|1 (order live paths by material), slots=N (paths in flight) */
+int b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_group_desc* materials,
+                       const char* options, b200_render** out);
+void b200_render_destroy(b200_render* r);
+const char* b200_render_cuda_source(const b200_render* r);
+/* Render image rows [y0, y1) into host_rgb ((y1-y0)*xres*3 floats).  Synchronous. */
+int b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b200_render_stats* stats);
+
 const char* b200_last_error(void);
 int b200_abi_version(void);
 

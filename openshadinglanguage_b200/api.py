@@ -248,3 +248,134 @@ def shadeop_hash(indim, n, inp, out, stream=None):
         import torch
         stream = torch.cuda.current_stream().cuda_stream
     _check(lib().b200_shadeop_hash(indim, n, _ptr(inp), _ptr(out), ctypes.c_void_p(stream)))
+
+
+# ---------------------------------------------------------------------------
+# wavefront path tracer (b200_render_*)
+# ---------------------------------------------------------------------------
+class _RenderScene(ctypes.Structure):
+    _fields_ = [("nverts", ctypes.c_int), ("ntris", ctypes.c_int), ("nnodes", ctypes.c_int),
+                ("nlightprims", ctypes.c_int), ("nshaders", ctypes.c_int), ("nmeshes", ctypes.c_int),
+                ("verts", ctypes.c_void_p), ("normals", ctypes.c_void_p), ("uvs", ctypes.c_void_p),
+                ("triangles", ctypes.c_void_p), ("n_triangles", ctypes.c_void_p),
+                ("uv_triangles", ctypes.c_void_p), ("shaderids", ctypes.c_void_p),
+                ("meshids", ctypes.c_void_p), ("mesh_surfacearea", ctypes.c_void_p),
+                ("bvh_nodes", ctypes.c_void_p), ("bvh_indices", ctypes.c_void_p),
+                ("lightprims", ctypes.c_void_p), ("shader_is_light", ctypes.c_void_p),
+                ("eye", ctypes.c_float * 3), ("dir", ctypes.c_float * 3), ("up", ctypes.c_float * 3),
+                ("fov", ctypes.c_float), ("cx", ctypes.c_float * 3), ("cy", ctypes.c_float * 3),
+                ("invw", ctypes.c_float), ("invh", ctypes.c_float),
+                ("xres", ctypes.c_int), ("yres", ctypes.c_int),
+                ("aa", ctypes.c_int), ("max_bounces", ctypes.c_int), ("rr_depth", ctypes.c_int),
+                ("no_jitter", ctypes.c_int), ("show_globals", ctypes.c_int),
+                ("background_shader", ctypes.c_int), ("background_resolution", ctypes.c_int)]
+
+
+class _RenderStats(ctypes.Structure):
+    _fields_ = [("paths", ctypes.c_longlong), ("launches", ctypes.c_longlong),
+                ("bounce_iterations", ctypes.c_longlong), ("device_ms", ctypes.c_double)]
+
+
+def _group_desc(layers, connections, name, options, keep):
+    """Build a _GroupDesc (shared by ShaderGroup and Renderer)."""
+    def cs(s):
+        b = s.encode() if isinstance(s, str) else s
+        keep.append(b)
+        return b
+    clayers = (_Layer * len(layers))()
+    for i, l in enumerate(layers):
+        params = l.get("params") or {}
+        cp = (_Param * max(1, len(params)))()
+        for j, (k, v) in enumerate(params.items()):
+            if not isinstance(v, (list, tuple, np.ndarray)):
+                v = [v]
+            if isinstance(v[0], str):
+                arr = (ctypes.c_char_p * len(v))(*[cs(x) for x in v])
+                t = 2
+            elif isinstance(v[0], (int, np.integer)) and not isinstance(v[0], bool):
+                arr = (ctypes.c_int * len(v))(*[int(x) for x in v])
+                t = 0
+            else:
+                arr = (ctypes.c_float * len(v))(*[float(x) for x in v])
+                t = 1
+            keep.append(arr)
+            cp[j].name, cp[j].type, cp[j].nvalues = cs(k), t, len(v)
+            cp[j].values = ctypes.cast(arr, ctypes.c_void_p)
+        keep.append(cp)
+        clayers[i].oso_text, clayers[i].layername = cs(l["oso"]), cs(l["name"])
+        clayers[i].nparams, clayers[i].params = len(params), cp
+    cconn = (_Connection * max(1, len(connections)))()
+    for i, (a, b, c, d) in enumerate(connections):
+        cconn[i].srclayer, cconn[i].srcparam, cconn[i].dstlayer, cconn[i].dstparam = cs(a), cs(b), cs(c), cs(d)
+    keep += [clayers, cconn]
+    return _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, 0, None, cs(options))
+
+
+class Renderer:
+    """testrender mirror: scene (openshadinglanguage_b200.render.scene.Scene),
+    its prepared arrays, and a lookup  shader name -> .oso text."""
+
+    def __init__(self, scene, arrays, oso_lookup, xres, yres, aa, max_bounces=1000000, rr_depth=5,
+                 no_jitter=False, show_globals=0, options=""):
+        L = lib()
+        L.b200_render_create.argtypes = [ctypes.POINTER(_RenderScene), ctypes.c_int, ctypes.POINTER(_GroupDesc),
+                                         ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+        L.b200_render_destroy.argtypes = [ctypes.c_void_p]
+        L.b200_render_cuda_source.argtypes = [ctypes.c_void_p]
+        L.b200_render_cuda_source.restype = ctypes.c_char_p
+        L.b200_render_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.POINTER(_RenderStats)]
+        keep = []
+        rs = _RenderScene()
+
+        def ptr(name, dtype):
+            a = np.ascontiguousarray(arrays[name], dtype)
+            keep.append(a)
+            return a.ctypes.data if a.size else None
+        rs.nverts, rs.ntris = len(arrays["verts"]), len(arrays["triangles"])
+        rs.nnodes, rs.nlightprims = len(arrays["bvh_nodes"]), len(arrays["lightprims"])
+        rs.nshaders, rs.nmeshes = len(scene.materials), len(arrays["mesh_surfacearea"])
+        rs.verts, rs.normals, rs.uvs = ptr("verts", np.float32), ptr("normals", np.float32), ptr("uvs", np.float32)
+        rs.triangles, rs.n_triangles = ptr("triangles", np.int32), ptr("n_triangles", np.int32)
+        rs.uv_triangles, rs.shaderids = ptr("uv_triangles", np.int32), ptr("shaderids", np.int32)
+        rs.meshids, rs.mesh_surfacearea = ptr("meshids", np.int32), ptr("mesh_surfacearea", np.float32)
+        rs.bvh_nodes, rs.bvh_indices = ptr("bvh_nodes", np.float32), ptr("bvh_indices", np.uint32)
+        rs.lightprims, rs.shader_is_light = ptr("lightprims", np.uint32), ptr("shader_is_light", np.int32)
+        for i in range(3):
+            rs.eye[i], rs.dir[i], rs.up[i] = float(scene.eye[i]), float(scene.dir[i]), float(scene.up[i])
+        rs.fov = float(scene.fov)
+        rs.xres, rs.yres, rs.aa = xres, yres, aa
+        rs.max_bounces, rs.rr_depth = max_bounces, rr_depth
+        rs.no_jitter, rs.show_globals = int(no_jitter), show_globals
+        rs.background_shader, rs.background_resolution = scene.background_shader, scene.background_resolution
+        mats = (_GroupDesc * len(scene.materials))()
+        for k, (layers, conns) in enumerate(scene.materials):
+            ls = [dict(oso=oso_lookup(l["shader"]), name=l["name"], params=l["params"]) for l in layers]
+            mats[k] = _group_desc(ls, conns, "material%d" % k, "", keep)
+        h = ctypes.c_void_p()
+        _check(L.b200_render_create(ctypes.byref(rs), len(scene.materials), mats, options.encode(), ctypes.byref(h)))
+        self._h, self._keep = h, keep
+        self.xres, self.yres, self.aa = xres, yres, aa
+        self.stats = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().b200_render_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def cuda_source(self):
+        return lib().b200_render_cuda_source(self._h).decode()
+
+    def render(self, y0=0, y1=None, device=0):
+        """-> float32 [(y1-y0), xres, 3]"""
+        y1 = self.yres if y1 is None else y1
+        out = np.zeros((y1 - y0, self.xres, 3), np.float32)
+        st = _RenderStats()
+        _check(lib().b200_render_rows(self._h, device, y0, y1, out.ctypes.data, ctypes.byref(st)))
+        self.stats = dict(paths=st.paths, launches=st.launches, bounce_iterations=st.bounce_iterations,
+                          device_ms=st.device_ms)
+        return out

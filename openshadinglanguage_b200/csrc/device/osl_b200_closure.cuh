@@ -1,0 +1,104 @@
+// osl_b200_closure.cuh — closure construction on the device (product code).
+//
+// Replaces osl_allocate[_weighted]_closure_component, osl_add_closure_closure,
+// osl_mul_closure_{float,color} (src/liboslexec/opclosure.cpp:18-105) and the
+// renderer's per-point bump allocator (src/testshade/render_state.h:27-54).
+// A closure value is a 32-bit word offset into a per-thread pool (0 = NULL)
+// instead of a pointer, so the tree is position independent and the pool can
+// live in local memory or be spilled to a wavefront arena:
+//   component : [id][w.x][w.y][w.z][params ...]
+//   mul       : [CL_MUL][w.x][w.y][w.z][child]
+//   add       : [CL_ADD][a][b]
+// Closure ids follow the renderer's registry (src/testrender/shading.h:25-60).
+#pragma once
+
+namespace osld {
+
+enum ClosureIDs {
+    CL_ADD = -2, CL_MUL = -1, COMPONENT_BASE_ID = 0,
+    EMISSION_ID = 1, BACKGROUND_ID, DIFFUSE_ID, OREN_NAYAR_ID, TRANSLUCENT_ID, PHONG_ID, WARD_ID,
+    MICROFACET_ID, REFLECTION_ID, FRESNEL_REFLECTION_ID, REFRACTION_ID, TRANSPARENT_ID, DEBUG_ID,
+    HOLDOUT_ID, MX_OREN_NAYAR_DIFFUSE_ID, MX_BURLEY_DIFFUSE_ID, MX_DIELECTRIC_ID, MX_CONDUCTOR_ID,
+    MX_GENERALIZED_SCHLICK_ID, MX_TRANSLUCENT_ID, MX_TRANSPARENT_ID, MX_SUBSURFACE_ID, MX_SHEEN_ID,
+    MX_UNIFORM_EDF_ID, MX_ANISOTROPIC_VDF_ID, MX_MEDIUM_VDF_ID, MX_LAYER_ID, SPI_THINLAYER, EMPTY_ID
+};
+
+#define OSLD_POOL_WORDS 256  // 1 KB, the reference's StackClosurePool size
+
+struct ClosurePool {
+    int used;  // next free word; word 0 is reserved so that offset 0 means NULL
+    float w[OSLD_POOL_WORDS];
+    OSLD void reset() { used = 1; }
+    OSLD int alloc(int nwords)
+    {
+        if (used + nwords > OSLD_POOL_WORDS)
+            return 0;
+        int at = used;
+        used += nwords;
+        return at;
+    }
+    OSLD int id(int c) const { return __float_as_int(w[c]); }
+    OSLD V3 weight(int c) const { return mkv(w[c + 1], w[c + 2], w[c + 3]); }
+};
+
+OSLD bool v3_is_zero(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
+OSLD bool v3_is_one(V3 a) { return a.x == 1.0f && a.y == 1.0f && a.z == 1.0f; }
+
+// weighted == false: weight 1 (osl_allocate_closure_component)
+OSLD int clos_component(ClosurePool& p, int id, int nparams, bool weighted, V3 wt)
+{
+    if (weighted && v3_is_zero(wt))
+        return 0;
+    int c = p.alloc(4 + nparams);
+    if (c) {
+        p.w[c] = __int_as_float(id);
+        V3 ww  = weighted ? wt : mkv(1.0f);
+        p.w[c + 1] = ww.x;
+        p.w[c + 2] = ww.y;
+        p.w[c + 3] = ww.z;
+    }
+    return c;
+}
+OSLD int clos_mul(ClosurePool& p, int a, V3 wt)
+{
+    if (!a || v3_is_zero(wt))
+        return 0;
+    if (v3_is_one(wt))
+        return a;
+    int c = p.alloc(5);
+    if (c) {
+        p.w[c]     = __int_as_float(CL_MUL);
+        p.w[c + 1] = wt.x;
+        p.w[c + 2] = wt.y;
+        p.w[c + 3] = wt.z;
+        p.w[c + 4] = __int_as_float(a);
+    }
+    return c;
+}
+OSLD int clos_mul(ClosurePool& p, int a, float wt)
+{
+    if (!a || wt == 0.0f)
+        return 0;
+    if (wt == 1.0f)
+        return a;
+    return clos_mul(p, a, mkv(wt));
+}
+OSLD int clos_add(ClosurePool& p, int a, int b)
+{
+    if (!a)
+        return b;
+    if (!b)
+        return a;
+    int c = p.alloc(3);
+    if (c) {
+        p.w[c]     = __int_as_float(CL_ADD);
+        p.w[c + 1] = __int_as_float(a);
+        p.w[c + 2] = __int_as_float(b);
+    }
+    return c;
+}
+OSLD void putp(float* q, float v) { *q = v; }
+OSLD void putp(float* q, int v) { *q = __int_as_float(v); }
+OSLD void putp(float* q, V3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; }
+
+}  // namespace osld

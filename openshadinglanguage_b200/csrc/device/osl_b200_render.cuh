@@ -1,0 +1,976 @@
+// osl_b200_render.cuh — wavefront path tracer for sm_100a (product code).
+//
+// B200-native replacement of the reference's recursive per-pixel integrator
+//   SimpleRaytracer::subpixel_radiance / antialias_pixel / globals_from_hit
+//       src/testrender/simpleraytracer.cpp:889-1216
+//   Scene::intersect (BVH + watertight triangle test)   src/testrender/bvh.cpp:221-356
+//   Scene::sample/shapepdf/normal/project/uv, Ray, Camera  src/testrender/raytracer.h:40-344
+//   Sampler, MIS, TangentFrame, Sampling               src/testrender/sampling.h:17-295
+//   CompositeBSDF + Diffuse/Reflection/Refraction/Transparent lobes
+//       src/testrender/shading.h:319-437, shading.cpp:301-322, 1081-1150
+//   process_closure                                    src/testrender/shading.cpp:1448-1706
+//   fresnel_dielectric / fresnel_refraction            src/testrender/optics.h:13-60
+//
+// Structure: path state lives in HBM as SoA planes; every bounce is
+//   rt_intersect  (closest hit for every live path, coalesced state loads)
+//   [rt_sort_*]   (counting sort of the live queue by material = closure type,
+//                  warp-aggregated with __match_any_sync)
+//   rt_shade      (globals from hit -> material dispatch -> closure -> lobes ->
+//                  emission + light-sample NEE incl. shadow ray -> BSDF sample)
+// with survivors compacted into the next queue by warp-aggregated atomics.
+// Samples of one pixel are resolved in the reference's order (running lerp), so
+// in strict mode the image is bit-identical to the scalar CPU oracle.
+//
+// This header is included by the generated render module AFTER the material
+// namespaces and `osl_execute_shader(int shaderID, SG&)` have been emitted.
+#pragma once
+
+namespace osld {
+
+// ---- scene + state ------------------------------------------------------------
+struct RenderScene {
+    int nverts, ntris, nnodes, nlightprims, nshaders, nmeshes;
+    const float* verts;
+    const float* normals;
+    const float* uvs;
+    const int* triangles;
+    const int* n_triangles;
+    const int* uv_triangles;
+    const int* shaderids;
+    const int* meshids;
+    const float* mesh_surfacearea;
+    const float4* bvh_nodes;  // 2 x float4 per node: bounds[6], child, nprims
+    const unsigned* bvh_indices;
+    const unsigned* lightprims;
+    const int* shader_is_light;
+    float eye[3], dir[3], up[3], fov;
+    float cx[3], cy[3], invw, invh;
+    int xres, yres;
+    int aa, max_bounces, rr_depth, no_jitter, show_globals;
+    int background_shader, background_resolution;
+};
+
+enum PathF { PF_OX, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_RADIUS, PF_SPREAD, PF_ROUGH, PF_WX, PF_WY, PF_WZ,
+             PF_LX, PF_LY, PF_LZ, PF_BSDFPDF, PF_HT, PF_HU, PF_HV, PF_COUNT };
+enum PathI { PI_RAYTYPE, PI_PREVID, PI_BOUNCE, PI_SEED, PI_INDEX, PI_HITID, PI_COUNT };
+
+struct RenderLaunch {
+    RenderScene S;
+    float* pf[PF_COUNT];  // float planes, nslots each
+    int* pi[PI_COUNT];    // int planes
+    int* queue_in;        // live path slots
+    int* queue_out;
+    int* counters;        // [0] in count, [1] out count, [2..] sort scratch
+    int* sort_keys;       // material key per queue entry
+    int nslots;           // SB * npix
+    int npix;             // pixels in this band
+    int y0;               // first image row of the band
+    int s0;               // first sample index of the batch
+    int nsamples;         // samples in flight (SB)
+    float* accum;         // running per-pixel result, 3 floats per pixel of the band
+};
+
+OSLD V3 ld3(const float* p, int i) { return mkv(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
+OSLD float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+OSLD float len2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+OSLD V3 vdiv(V3 a, float l) { return mkv(a.x / l, a.y / l, a.z / l); }
+OSLD V3 vnormalized(V3 v)
+{
+    float l = imath_length(v);
+    return l != 0.0f ? vdiv(v, l) : v;
+}
+OSLD float vcomp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+// ---- Ray ---------------------------------------------------------------------------
+enum { RAY_CAMERA = 1, RAY_SHADOW = 2, RAY_DIFFUSE = 16 };
+struct Ray {
+    V3 origin, direction;
+    float radius, spread, roughness;
+    int raytype;
+};
+OSLD void ortho(V3 n, V3& x, V3& y)
+{
+    x = vnormalized(fabsf(n.x) > .01f ? mkv(n.z, 0.0f, -n.x) : mkv(0.0f, -n.z, n.y));
+    y = cross3(n, x);
+}
+OSLD V3 ray_point(const Ray& r, float t) { return r.origin + r.direction * t; }
+
+// ---- Sampler (integer only: bit-exact) -------------------------------------------------
+struct Sampler {
+    u32 seed, index;
+    OSLD static u32 hash(u32 s)
+    {
+        s ^= s >> 16; s *= 0x21f0aaadu; s ^= s >> 15; s *= 0xd35a2d97u; s ^= s >> 15;
+        return s;
+    }
+    OSLD static u32 owen(u32 p, u32 s)
+    {
+        p ^= p * 0x3d20adeau; p += s; p *= (s >> 16) | 1u; p ^= p * 0x05526c56u; p ^= p * 0x53a22864u;
+        return __brev(p);
+    }
+    OSLD void init(int px, int py, int si)
+    {
+        seed  = (u32)(((px & 2047) << 22) | ((py & 2047) << 11));
+        index = __brev((u32)si);
+    }
+    OSLD V3 get()
+    {
+        const u32 zmatrix[24] = { 0x000001u, 0x000003u, 0x000006u, 0x000009u, 0x000017u, 0x00003au, 0x000071u, 0x0000a3u,
+                                  0x000116u, 0x000339u, 0x000677u, 0x0009aau, 0x001601u, 0x003903u, 0x007706u, 0x00aa09u,
+                                  0x010117u, 0x03033au, 0x060671u, 0x0909a3u, 0x171616u, 0x3a3939u, 0x717777u, 0xa3aaaau };
+        seed += 4;
+        u32 si = owen(index, hash(seed - 4)) & 0xFFFFFFu;
+        u32 rx = si, ry = 0, rz = 0, ym = 1;
+#pragma unroll
+        for (int c = 0; c < 24; c++) {
+            u32 bit = (si >> c) & 1u;
+            ry ^= bit * ym;
+            rz ^= bit * zmatrix[c];
+            ym ^= ym << 1;
+        }
+        return mkv((float)(owen(rx, hash(seed - 3)) >> 8) * 5.96046448e-8f,
+                   (float)(owen(ry, hash(seed - 2)) >> 8) * 5.96046448e-8f,
+                   (float)(owen(rz, hash(seed - 1)) >> 8) * 5.96046448e-8f);
+    }
+};
+
+// ---- sampling helpers ---------------------------------------------------------------
+struct TangentFrame {
+    V3 u, v, w;
+};
+OSLD TangentFrame frame_from_normal(V3 n)
+{
+    const float sign = copysignf(1.0f, n.z);
+    const float a    = -1 / (sign + n.z);
+    const float b    = n.x * n.y * a;
+    TangentFrame f;
+    f.u = mkv(1 + sign * n.x * n.x * a, sign * b, -sign * n.x);
+    f.v = mkv(b, sign + n.y * n.y * a, -n.y);
+    f.w = n;
+    return f;
+}
+OSLD V3 frame_get(const TangentFrame& f, float x, float y, float z) { return x * f.u + y * f.v + z * f.w; }
+OSLD void to_unit_disk(float& x, float& y)
+{
+    const float PI_OVER_4 = (float)(OSLD_PI / 4), PI_OVER_2 = (float)(OSLD_PI / 2);
+    float phi, r;
+    float a = 2 * x - 1, b = 2 * y - 1;
+    if (a * a > b * b) {
+        r   = a;
+        phi = PI_OVER_4 * (b / a);
+    } else if (b != 0) {
+        r   = b;
+        phi = PI_OVER_2 - PI_OVER_4 * (a / b);
+    } else {
+        r   = 0;
+        phi = 0;
+    }
+    fast_sincos(phi, &x, &y);
+    x *= r;
+    y *= r;
+}
+OSLD void sample_cosine_hemisphere(V3 N, float rndx, float rndy, V3& out, float& pdf)
+{
+    to_unit_disk(rndx, rndy);
+    float cos_theta = sqrtf(fmaxf(1 - rndx * rndx - rndy * rndy, 0.0f));
+    out             = frame_get(frame_from_normal(N), rndx, rndy, cos_theta);
+    pdf             = cos_theta * (float)(1.0 / OSLD_PI);
+}
+enum { WEIGHT_WEIGHT, WEIGHT_EVAL, EVAL_WEIGHT };
+template<int mode> OSLD float power_heuristic(float sampled_pdf, float other_pdf)
+{
+    float r, mis;
+    if (sampled_pdf > other_pdf) {
+        r   = other_pdf / sampled_pdf;
+        mis = 1 / (1 + r * r);
+    } else if (sampled_pdf < other_pdf) {
+        r   = sampled_pdf / other_pdf;
+        mis = 1 - 1 / (1 + r * r);
+    } else {
+        r   = 1.0f;
+        mis = 0.5f;
+    }
+    if (mode == WEIGHT_WEIGHT)
+        return fminf(other_pdf, OSLD_FLT_MAX) * mis;
+    if (mode == WEIGHT_EVAL)
+        return mis;
+    return mis * ((other_pdf > sampled_pdf) ? fminf(1 / r, OSLD_FLT_MAX) : r);
+}
+OSLD void update_eval(V3* w, float* pdf, V3 ow, float opdf, float b)
+{
+    if (b > OSLD_FLT_MIN) {
+        opdf *= b;
+        ow = ow * (1 / b);
+        float mis;
+        if (*pdf < opdf)
+            mis = 1 / (1 + *pdf / opdf);
+        else if (opdf < *pdf)
+            mis = 1 - 1 / (1 + opdf / *pdf);
+        else
+            mis = 0.5f;
+        *w = *w * (1 - mis) + ow * mis;
+        *pdf += opdf;
+    }
+}
+
+// ---- fresnel -----------------------------------------------------------------------
+OSLD float fresnel_dielectric(float cosi, float eta)
+{
+    if (eta == 0)
+        return 1;
+    if (cosi < 0.0f)
+        eta = 1.0f / eta;
+    float c = fabsf(cosi);
+    float g = eta * eta - 1 + c * c;
+    if (g > 0) {
+        g       = sqrtf(g);
+        float A = (g - c) / (g + c);
+        float B = (c * (g + c) - 1) / (c * (g - c) + 1);
+        return 0.5f * A * A * (1 + B * B);
+    }
+    return 1.0f;
+}
+OSLD float fresnel_refraction(V3 I, V3 N, float eta, V3& T)
+{
+    float cosi = -dot3(I, N);
+    V3 Nn;
+    float neta;
+    if (cosi > 0) {
+        neta = 1 / eta;
+        Nn   = N;
+    } else {
+        cosi = -cosi;
+        neta = eta;
+        Nn   = -N;
+    }
+    float arg = 1.0f - (neta * neta * (1.0f - cosi * cosi));
+    if (arg >= 0) {
+        float dnp = sqrtf(arg);
+        float nK  = (neta * cosi) - dnp;
+        T         = I * neta + Nn * nK;
+        return 1 - fresnel_dielectric(cosi, eta);
+    }
+    T = mkv(0.0f);
+    return 0;
+}
+
+// ---- lobes ---------------------------------------------------------------------------
+struct BSample {
+    V3 wi, weight;
+    float pdf, roughness;
+};
+OSLD BSample bs_null()
+{
+    BSample s;
+    s.wi = mkv(0.0f);
+    s.weight = mkv(0.0f);
+    s.pdf = 0.0f;
+    s.roughness = 0.0f;
+    return s;
+}
+OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
+{
+    BSample s;
+    s.wi = wi;
+    s.weight = w;
+    s.pdf = pdf;
+    s.roughness = r;
+    return s;
+}
+#define OSLD_INF __int_as_float(0x7f800000)
+enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT };
+struct Lobe {
+    int type;
+    V3 N;
+    float eta;
+};
+OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
+{
+    if (l.type == LOBE_REFLECTION) {
+        float cosNO = dot3(l.N, wo);
+        return cosNO > 0 ? mkv(fresnel_dielectric(cosNO, l.eta)) : mkv(1.0f);
+    }
+    if (l.type == LOBE_REFRACTION)
+        return mkv(1 - fresnel_dielectric(dot3(l.N, wo), l.eta));
+    return mkv(1.0f);
+}
+OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    if (l.type == LOBE_DIFFUSE || l.type == LOBE_TRANSLUCENT) {
+        const float pdf = fmaxf(dot3(l.N, wi), 0.0f) * (float)(1.0 / OSLD_PI);
+        return bs_make(wi, mkv(1.0f), pdf, 1.0f);
+    }
+    return bs_null();
+}
+OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
+{
+    switch (l.type) {
+    case LOBE_DIFFUSE:
+    case LOBE_TRANSLUCENT: {
+        V3 out;
+        float pdf;
+        sample_cosine_hemisphere(l.N, rx, ry, out, pdf);
+        return bs_make(out, mkv(1.0f), pdf, 1.0f);
+    }
+    case LOBE_REFLECTION: {
+        float cosNO = dot3(l.N, wo);
+        if (cosNO > 0) {
+            V3 wi = (2 * cosNO) * l.N - wo;
+            return bs_make(wi, mkv(fresnel_dielectric(cosNO, l.eta)), OSLD_INF, 0.0f);
+        }
+        return bs_null();
+    }
+    case LOBE_REFRACTION: {
+        V3 wi;
+        float Ft = fresnel_refraction(-wo, l.N, l.eta, wi);
+        return bs_make(wi, mkv(Ft), OSLD_INF, 0.0f);
+    }
+    default: return bs_make(-wo, mkv(1.0f), OSLD_INF, 0.0f);
+    }
+}
+
+#define OSLD_MAX_LOBES 8
+struct CompositeBSDF {
+    V3 weights[OSLD_MAX_LOBES];
+    float pdfs[OSLD_MAX_LOBES];
+    Lobe lobes[OSLD_MAX_LOBES];
+    int num;
+};
+OSLD void bsdf_prepare(CompositeBSDF& B, V3 wo, V3 path_weight, bool absorb)
+{
+    float total = 0;
+    for (int i = 0; i < B.num; i++) {
+        B.pdfs[i] = dot3(B.weights[i], path_weight * lobe_albedo(B.lobes[i], wo))
+                    / (path_weight.x + path_weight.y + path_weight.z);
+        total += B.pdfs[i];
+    }
+    if ((!absorb && total > 0) || total > 1)
+        for (int i = 0; i < B.num; i++)
+            B.pdfs[i] /= total;
+}
+OSLD BSample bsdf_eval(const CompositeBSDF& B, V3 wo, V3 wi)
+{
+    BSample s = bs_null();
+    for (int i = 0; i < B.num; i++) {
+        BSample b = lobe_eval(B.lobes[i], wo, wi);
+        b.weight  = b.weight * B.weights[i];
+        update_eval(&s.weight, &s.pdf, b.weight, b.pdf, B.pdfs[i]);
+        s.roughness += b.roughness * B.pdfs[i];
+    }
+    return s;
+}
+OSLD BSample bsdf_sample(const CompositeBSDF& B, V3 wo, float rx, float ry, float rz)
+{
+    float accum = 0;
+    for (int i = 0; i < B.num; i++) {
+        if (rx < (B.pdfs[i] + accum)) {
+            rx        = (rx - accum) / B.pdfs[i];
+            rx        = fminf(rx, 0.99999994f);
+            BSample s = lobe_sample(B.lobes[i], wo, rx, ry, rz);
+            s.weight  = s.weight * (B.weights[i] * (1 / B.pdfs[i]));
+            s.pdf *= B.pdfs[i];
+            if (s.pdf == 0.0f)
+                return bs_null();
+            for (int j = 0; j < B.num; j++) {
+                if (i != j) {
+                    BSample b = lobe_eval(B.lobes[j], wo, s.wi);
+                    b.weight  = b.weight * B.weights[j];
+                    update_eval(&s.weight, &s.pdf, b.weight, b.pdf, B.pdfs[j]);
+                }
+            }
+            return s;
+        }
+        accum += B.pdfs[i];
+    }
+    return bs_null();
+}
+
+// closure tree -> emission + lobes (16-deep explicit stack, weights root->leaf)
+OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only)
+{
+    int ptr_stack[16];
+    V3 weight_stack[16];
+    int sp    = 0;
+    V3 weight = mkv(1.0f);
+    while (closure) {
+        int id = pool.id(closure);
+        if (id == CL_MUL) {
+            weight  = weight * pool.weight(closure);
+            closure = __float_as_int(pool.w[closure + 4]);
+        } else if (id == CL_ADD) {
+            ptr_stack[sp]      = __float_as_int(pool.w[closure + 2]);
+            weight_stack[sp++] = weight;
+            closure            = __float_as_int(pool.w[closure + 1]);
+        } else {
+            V3 cw          = weight * pool.weight(closure);
+            const float* q = pool.w + closure + 4;
+            closure        = 0;
+            if (id == EMISSION_ID)
+                Le = Le + cw;
+            else if (!light_only) {
+                Lobe l;
+                l.N   = mkv(q[0], q[1], q[2]);
+                l.eta = 0.0f;
+                bool known = true;
+                switch (id) {
+                case DIFFUSE_ID: l.type = LOBE_DIFFUSE; break;
+                case TRANSLUCENT_ID: l.type = LOBE_TRANSLUCENT; l.N = -l.N; break;
+                case REFLECTION_ID: l.type = LOBE_REFLECTION; break;
+                case FRESNEL_REFLECTION_ID: l.type = LOBE_REFLECTION; l.eta = q[3]; break;
+                case REFRACTION_ID: l.type = LOBE_REFRACTION; l.eta = q[3]; break;
+                case TRANSPARENT_ID:
+                case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
+                default: known = false; break;
+                }
+                if (known && B.num < OSLD_MAX_LOBES) {
+                    B.weights[B.num] = cw;
+                    B.lobes[B.num]   = l;
+                    ++B.num;
+                }
+            }
+        }
+        if (closure == 0 && sp > 0) {
+            closure = ptr_stack[--sp];
+            weight  = weight_stack[sp];
+        }
+    }
+}
+
+// ---- BVH traversal ---------------------------------------------------------------------
+struct Hit {
+    float t, u, v;
+    unsigned id;
+};
+OSLD float minf_(float a, float b) { return b < a ? b : a; }
+OSLD float maxf_(float a, float b) { return b > a ? b : a; }
+OSLD bool box_intersect(V3 org, V3 rdir, float tmax, float4 b0, float4 b1, float* dist)
+{
+    // bounds = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y } = minx,maxx,miny,maxy,minz,maxz
+    const float tx1 = (b0.x - org.x) * rdir.x, tx2 = (b0.y - org.x) * rdir.x;
+    const float ty1 = (b0.z - org.y) * rdir.y, ty2 = (b0.w - org.y) * rdir.y;
+    const float tz1 = (b1.x - org.z) * rdir.z, tz2 = (b1.y - org.z) * rdir.z;
+    float tmin      = minf_(tx1, tx2);
+    tmax            = minf_(tmax, maxf_(tx1, tx2));
+    tmin            = maxf_(tmin, minf_(ty1, ty2));
+    tmax            = minf_(tmax, maxf_(ty1, ty2));
+    tmin            = maxf_(tmin, minf_(tz1, tz2));
+    tmax            = minf_(tmax, maxf_(tz1, tz2));
+    *dist           = tmin;
+    tmin            = maxf_(0.0f, tmin);
+    return tmin <= tmax;
+}
+OSLD float xorf(float a, unsigned b) { return __int_as_float((int)(fbits(a) ^ b)); }
+
+OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsigned skip1, unsigned skip2)
+{
+    int stack_node[64];
+    float stack_dist[64];
+    Hit result;
+    result.t  = tmax;
+    result.u  = result.v = 0.0f;
+    result.id = 0;
+    stack_node[0] = 0;
+    stack_dist[0] = result.t;
+    const V3 rdir = mkv(1 / dir.x, 1 / dir.y, 1 / dir.z);
+    int kz = 0;
+    if (fabsf(dir.y) > fabsf(vcomp(dir, kz)))
+        kz = 1;
+    if (fabsf(dir.z) > fabsf(vcomp(dir, kz)))
+        kz = 2;
+    int kx = kz == 2 ? 0 : kz + 1;
+    int ky = kx == 2 ? 0 : kx + 1;
+    const float shx = vcomp(dir, kx) / vcomp(dir, kz), shy = vcomp(dir, ky) / vcomp(dir, kz), shz = vcomp(rdir, kz);
+    for (int sp = 1; sp != 0;) {
+        if (result.t < stack_dist[--sp])
+            continue;
+        int node    = stack_node[sp];
+        float4 n1   = __ldg(S.bvh_nodes + 2 * node + 1);
+        unsigned child = fbits(n1.z), nprims = fbits(n1.w);
+        if (nprims) {
+            for (unsigned i = 0; i < nprims; i++) {
+                unsigned id = __ldg(S.bvh_indices + child + i);
+                const V3 A = ld3(S.verts, __ldg(S.triangles + 3 * id)) - org;
+                const V3 B = ld3(S.verts, __ldg(S.triangles + 3 * id + 1)) - org;
+                const V3 C = ld3(S.verts, __ldg(S.triangles + 3 * id + 2)) - org;
+                const float Ax = vcomp(A, kx) - shx * vcomp(A, kz), Ay = vcomp(A, ky) - shy * vcomp(A, kz);
+                const float Bx = vcomp(B, kx) - shx * vcomp(B, kz), By = vcomp(B, ky) - shy * vcomp(B, kz);
+                const float Cx = vcomp(C, kx) - shx * vcomp(C, kz), Cy = vcomp(C, ky) - shy * vcomp(C, kz);
+                const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+                if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
+                    continue;
+                const float det = U + V + W;
+                if (det == 0)
+                    continue;
+                const float T       = shz * (U * vcomp(A, kz) + V * vcomp(B, kz) + W * vcomp(C, kz));
+                const unsigned mask = fbits(det) & 0x80000000u;
+                if (xorf(T, mask) < 0)
+                    continue;
+                if (xorf(T, mask) > result.t * xorf(det, mask))
+                    continue;
+                if (id == skip1 || id == skip2)
+                    continue;
+                const float rcpDet = 1 / det;
+                result.t  = T * rcpDet;
+                result.u  = V * rcpDet;
+                result.v  = W * rcpDet;
+                result.id = id;
+            }
+        } else {
+            int c1 = (int)child, c2 = c1 + 1;
+            float d1 = 0, d2 = 0;
+            bool h1 = box_intersect(org, rdir, result.t, __ldg(S.bvh_nodes + 2 * c1), __ldg(S.bvh_nodes + 2 * c1 + 1), &d1);
+            bool h2 = box_intersect(org, rdir, result.t, __ldg(S.bvh_nodes + 2 * c2), __ldg(S.bvh_nodes + 2 * c2 + 1), &d2);
+            if (d1 > d2) {
+                bool th = h1; h1 = h2; h2 = th;
+                float td = d1; d1 = d2; d2 = td;
+                int tc = c1; c1 = c2; c2 = tc;
+            }
+            stack_node[sp] = c2;
+            stack_dist[sp] = d2;
+            sp += h2 ? 1 : 0;
+            stack_node[sp] = c1;
+            stack_dist[sp] = d1;
+            sp += h1 ? 1 : 0;
+        }
+    }
+    return result;
+}
+
+// ---- scene queries -----------------------------------------------------------------------
+struct LightSample {
+    V3 dir;
+    float dist, pdf, u, v;
+};
+OSLD void tri_verts(const RenderScene& S, int id, V3& va, V3& vb, V3& vc)
+{
+    va = ld3(S.verts, __ldg(S.triangles + 3 * id));
+    vb = ld3(S.verts, __ldg(S.triangles + 3 * id + 1));
+    vc = ld3(S.verts, __ldg(S.triangles + 3 * id + 2));
+}
+OSLD LightSample scene_sample(const RenderScene& S, int primID, V3 x, float xi, float yi)
+{
+    if (yi > xi) {
+        xi *= 0.5f;
+        yi -= xi;
+    } else {
+        yi *= 0.5f;
+        xi -= yi;
+    }
+    V3 va, vb, vc;
+    tri_verts(S, primID, va, vb, vc);
+    const V3 n = cross3(va - vb, va - vc);
+    V3 l       = ((1 - xi - yi) * va + xi * vb + yi * vc) - x;
+    float d2   = len2(l);
+    V3 dir     = vnormalized(l);
+    LightSample s;
+    s.dir  = dir;
+    s.dist = sqrtf(d2);
+    s.pdf  = d2 / (0.5f * fabsf(dot3(dir, n)));
+    s.u    = xi;
+    s.v    = yi;
+    return s;
+}
+OSLD float scene_shapepdf(const RenderScene& S, int primID, V3 x, V3 p)
+{
+    V3 va, vb, vc;
+    tri_verts(S, primID, va, vb, vc);
+    const V3 n = cross3(va - vb, va - vc);
+    V3 l       = p - x;
+    float d2   = len2(l);
+    V3 dir     = vnormalized(l);
+    return d2 / (0.5f * fabsf(dot3(dir, n)));
+}
+
+// globals_from_hit (simpleraytracer.cpp:889-932) incl. Scene::normal/project/uv
+OSLD void globals_from_hit(const RenderScene& S, SG& sg, const Ray& r, float t, int id, float u, float v)
+{
+    // r.dual_direction()
+    sg.I = r.direction;
+    ortho(r.direction, sg.I_dx, sg.I_dy);
+    sg.I_dx = sg.I_dx * r.spread;
+    sg.I_dy = sg.I_dy * r.spread;
+    // r.point(Dual t)
+    const float rr = r.radius + r.spread * t;
+    V3 P           = ray_point(r, t), Pdx, Pdy;
+    ortho(r.direction, Pdx, Pdy);
+    Pdx = Pdx * rr;
+    Pdy = Pdy * rr;
+    V3 va, vb, vc;
+    tri_verts(S, id, va, vb, vc);
+    V3 Ng = vnormalized(cross3(va - vb, va - vc));
+    V3 N  = Ng;
+    if (__ldg(S.n_triangles + 3 * id) >= 0) {
+        const V3 na = ld3(S.normals, __ldg(S.n_triangles + 3 * id)), nb = ld3(S.normals, __ldg(S.n_triangles + 3 * id + 1)),
+                 nc = ld3(S.normals, __ldg(S.n_triangles + 3 * id + 2));
+        N = vnormalized((1 - u - v) * na + u * nb + v * nc);
+    }
+    // project
+    {
+        V3 nI      = vnormalized(sg.I);
+        float cosI = dot3(-nI, N);
+        if (fabsf(cosI) > 1e-3f) {
+            float deltaX = dot3(Pdx, N) / cosI;
+            float deltaY = dot3(Pdy, N) / cosI;
+            Pdx = Pdx + nI * deltaX;
+            Pdy = Pdy + nI * deltaY;
+        }
+    }
+    sg.P    = P;
+    sg.P_dx = Pdx;
+    sg.P_dy = Pdy;
+    // uv
+    sg.dPdu = mkv(0.0f);
+    sg.dPdv = mkv(0.0f);
+    sg.u = sg.u_dx = sg.u_dy = sg.v = sg.v_dx = sg.v_dy = 0.0f;
+    if (__ldg(S.uv_triangles + 3 * id) >= 0) {
+        const int ia = __ldg(S.uv_triangles + 3 * id), ib = __ldg(S.uv_triangles + 3 * id + 1), ic = __ldg(S.uv_triangles + 3 * id + 2);
+        const float tax = __ldg(S.uvs + 2 * ia), tay = __ldg(S.uvs + 2 * ia + 1);
+        const float tbx = __ldg(S.uvs + 2 * ib), tby = __ldg(S.uvs + 2 * ib + 1);
+        const float tcx = __ldg(S.uvs + 2 * ic), tcy = __ldg(S.uvs + 2 * ic + 1);
+        const float dt02x = tax - tcx, dt02y = tay - tcy, dt12x = tbx - tcx, dt12y = tby - tcy;
+        const V3 dp02 = va - vc, dp12 = vb - vc;
+        const float det = dt02x * dt12y - dt02y * dt12x;
+        if (det != 0) {
+            float invdet = 1 / det;
+            sg.dPdu      = (dt12y * dp02 - dt02y * dp12) * invdet;
+            sg.dPdv      = (-dt12x * dp02 + dt02x * dp12) * invdet;
+        }
+        V3 La = cross3(N, vc - vb);
+        La    = vdiv(La, dot3(va - vb, La));
+        V3 Lb = cross3(N, va - vc);
+        Lb    = vdiv(Lb, dot3(vb - vc, Lb));
+        V3 Lc = cross3(N, vb - va);
+        Lc    = vdiv(Lc, dot3(vc - va, Lc));
+        float ax = dot3(La, Pdx), bx = dot3(Lb, Pdx), cx = dot3(Lc, Pdx);
+        float ay = dot3(La, Pdy), by = dot3(Lb, Pdy), cy = dot3(Lc, Pdy);
+        float w0 = 1 - u - v;
+        sg.u    = w0 * tax + u * tbx + v * tcx;
+        sg.v    = w0 * tay + u * tby + v * tcy;
+        sg.u_dx = ax * tax + bx * tbx + cx * tcx;
+        sg.v_dx = ax * tay + bx * tby + cx * tcy;
+        sg.u_dy = ay * tax + by * tbx + cy * tcx;
+        sg.v_dy = ay * tay + by * tby + cy * tcy;
+    }
+    sg.surfacearea = __ldg(S.mesh_surfacearea + __ldg(S.meshids + id));
+    sg.backfacing  = dot3(Ng, sg.I) > 0 ? 1 : 0;
+    if (sg.backfacing) {
+        N  = -N;
+        Ng = -Ng;
+    }
+    sg.N              = N;
+    sg.Ng             = Ng;
+    sg.raytype        = r.raytype;
+    sg.flipHandedness = dot3(cross3(Pdx, Pdy), N) < 0 ? 1 : 0;
+    sg.dPdz = mkv(0.0f);
+    sg.time = sg.dtime = 0.0f;
+    sg.dPdtime = mkv(0.0f);
+    sg.Ps = sg.Ps_dx = sg.Ps_dy = mkv(0.0f);
+    sg.shadeindex = 0;
+}
+
+OSLD Ray camera_ray(const RenderScene& S, float x, float y)
+{
+    V3 cx = mkv(S.cx[0], S.cx[1], S.cx[2]), cy = mkv(S.cy[0], S.cy[1], S.cy[2]), dir = mkv(S.dir[0], S.dir[1], S.dir[2]);
+    const V3 v        = vnormalized(cx * (x * S.invw - 0.5f) + cy * (0.5f - y * S.invh) + dir);
+    const float cos_a = dot3(dir, v);
+    Ray r;
+    r.origin    = mkv(S.eye[0], S.eye[1], S.eye[2]);
+    r.direction = v;
+    r.radius    = 0.0f;
+    r.spread    = sqrtf(S.invw * S.invh * imath_length(cx) * imath_length(cy) * cos_a) * cos_a;
+    r.roughness = 0.0f;
+    r.raytype   = RAY_CAMERA;
+    return r;
+}
+
+// warp-aggregated append of a surviving path to the next queue
+OSLD void queue_push(int* queue, int* counter, int value, bool pred)
+{
+    unsigned m = __ballot_sync(__activemask(), pred);
+    if (!pred)
+        return;
+    int lane   = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base   = 0;
+    if (lane == leader)
+        base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    queue[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+}  // namespace osld
+
+using namespace osld;
+
+// ---- kernels -------------------------------------------------------------------------------
+// Camera::lookat + resolution + finalize (raytracer.h:95-126), evaluated once on the
+// device so the OIIO fast_tan restatement exists in exactly one place.
+// out[0..2] = normalized dir, out[3..5] = cx, out[6..8] = cy
+extern "C" __global__ void rt_camera(const __grid_constant__ RenderLaunch L, float* out)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0)
+        return;
+    const RenderScene& S = L.S;
+    V3 dir   = vnormalized(mkv(S.dir[0], S.dir[1], S.dir[2]));
+    V3 up    = mkv(S.up[0], S.up[1], S.up[2]);
+    float k  = fast_tan(S.fov * (float)(OSLD_PI / 360));
+    V3 right = vnormalized(cross3(dir, up));
+    V3 cx    = right * ((float)S.xres * k / (float)S.yres);
+    V3 cy    = vnormalized(cross3(cx, dir)) * k;
+    out[0] = dir.x; out[1] = dir.y; out[2] = dir.z;
+    out[3] = cx.x; out[4] = cx.y; out[5] = cx.z;
+    out[6] = cy.x; out[7] = cy.y; out[8] = cy.z;
+}
+
+// one thread per path slot: camera sample -> initial path state
+extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < L.nslots; slot += gridDim.x * blockDim.x) {
+        int sb = slot / L.npix, pix = slot - sb * L.npix;
+        int x = pix % S.xres, y = L.y0 + pix / S.xres;
+        int si = L.s0 + sb;
+        Sampler sampler;
+        sampler.init(x, y, si);
+        V3 j = S.no_jitter ? mkv(0.5f, 0.5f, 0.0f) : sampler.get();
+        j.x *= 2;
+        j.x = j.x < 1 ? sqrtf(j.x) - 1 : 1 - sqrtf(2 - j.x);
+        j.y *= 2;
+        j.y = j.y < 1 ? sqrtf(j.y) - 1 : 1 - sqrtf(2 - j.y);
+        Ray r = camera_ray(S, (float)x + 0.5f + j.x, (float)y + 0.5f + j.y);
+        L.pf[PF_OX][slot] = r.origin.x; L.pf[PF_OY][slot] = r.origin.y; L.pf[PF_OZ][slot] = r.origin.z;
+        L.pf[PF_DX][slot] = r.direction.x; L.pf[PF_DY][slot] = r.direction.y; L.pf[PF_DZ][slot] = r.direction.z;
+        L.pf[PF_RADIUS][slot] = r.radius; L.pf[PF_SPREAD][slot] = r.spread; L.pf[PF_ROUGH][slot] = r.roughness;
+        L.pf[PF_WX][slot] = 1.0f; L.pf[PF_WY][slot] = 1.0f; L.pf[PF_WZ][slot] = 1.0f;
+        L.pf[PF_LX][slot] = 0.0f; L.pf[PF_LY][slot] = 0.0f; L.pf[PF_LZ][slot] = 0.0f;
+        L.pf[PF_BSDFPDF][slot] = OSLD_INF;
+        L.pi[PI_RAYTYPE][slot] = r.raytype;
+        L.pi[PI_PREVID][slot]  = -1;
+        L.pi[PI_BOUNCE][slot]  = 0;
+        L.pi[PI_SEED][slot]    = (int)sampler.seed;
+        L.pi[PI_INDEX][slot]   = (int)sampler.index;
+        L.queue_in[slot]       = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        L.counters[0] = L.nslots;
+        L.counters[1] = 0;
+    }
+}
+
+// closest hit for every live path
+extern "C" __global__ void __launch_bounds__(256) rt_intersect(const __grid_constant__ RenderLaunch L)
+{
+    const int n = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        int slot = L.queue_in[q];
+        V3 org   = mkv(L.pf[PF_OX][slot], L.pf[PF_OY][slot], L.pf[PF_OZ][slot]);
+        V3 dir   = mkv(L.pf[PF_DX][slot], L.pf[PF_DY][slot], L.pf[PF_DZ][slot]);
+        Hit h    = scene_intersect(L.S, org, dir, OSLD_INF, (unsigned)L.pi[PI_PREVID][slot], ~0u);
+        L.pf[PF_HT][slot]    = h.t;
+        L.pf[PF_HU][slot]    = h.u;
+        L.pf[PF_HV][slot]    = h.v;
+        L.pi[PI_HITID][slot] = (int)h.id;
+        if (L.sort_keys)
+            L.sort_keys[q] = (h.t == OSLD_INF) ? 0 : 1 + __ldg(L.S.shaderids + h.id);
+    }
+}
+
+// counting sort of the live queue by material key (0 = miss); counters[2+k] = histogram,
+// counters[2+64+k] = running cursor.  Stable order is not required: paths are independent.
+extern "C" __global__ void __launch_bounds__(256) rt_sort_count(const __grid_constant__ RenderLaunch L)
+{
+    const int n = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        int key    = L.sort_keys[q];
+        unsigned m = __match_any_sync(__activemask(), key);
+        if ((threadIdx.x & 31) == __ffs(m) - 1)
+            atomicAdd(L.counters + 2 + key, __popc(m));
+    }
+}
+extern "C" __global__ void rt_sort_scan(const __grid_constant__ RenderLaunch L)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k <= L.S.nshaders; ++k) {
+            int c = L.counters[2 + k];
+            L.counters[2 + 64 + k] = run;
+            run += c;
+            L.counters[2 + k] = 0;
+        }
+    }
+}
+extern "C" __global__ void __launch_bounds__(256) rt_sort_scatter(const __grid_constant__ RenderLaunch L)
+{
+    const int n = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        int key    = L.sort_keys[q];
+        int slot   = L.queue_in[q];
+        unsigned m = __match_any_sync(__activemask(), key);
+        int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+        if (lane == leader)
+            base = atomicAdd(L.counters + 2 + 64 + key, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        L.queue_out[base + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+// shade one bounce: everything between two closest-hit queries of subpixel_radiance
+extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    const int n          = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31) & ~31); q += gridDim.x * blockDim.x) {
+        bool alive = false;
+        int slot   = 0;
+        if (q < n) {
+            slot = L.queue_in[q];
+            Ray r;
+            r.origin    = mkv(L.pf[PF_OX][slot], L.pf[PF_OY][slot], L.pf[PF_OZ][slot]);
+            r.direction = mkv(L.pf[PF_DX][slot], L.pf[PF_DY][slot], L.pf[PF_DZ][slot]);
+            r.radius    = L.pf[PF_RADIUS][slot];
+            r.spread    = L.pf[PF_SPREAD][slot];
+            r.roughness = L.pf[PF_ROUGH][slot];
+            r.raytype   = L.pi[PI_RAYTYPE][slot];
+            const float ht = L.pf[PF_HT][slot], hu = L.pf[PF_HU][slot], hv = L.pf[PF_HV][slot];
+            const int hid  = L.pi[PI_HITID][slot];
+            const int b    = L.pi[PI_BOUNCE][slot];
+            V3 path_weight   = mkv(L.pf[PF_WX][slot], L.pf[PF_WY][slot], L.pf[PF_WZ][slot]);
+            V3 path_radiance = mkv(L.pf[PF_LX][slot], L.pf[PF_LY][slot], L.pf[PF_LZ][slot]);
+            float bsdf_pdf   = L.pf[PF_BSDFPDF][slot];
+            do {
+                if (ht == OSLD_INF)
+                    break;  // miss (no background in these scenes)
+                SG sg;
+                ClosurePool pool;
+                globals_from_hit(S, sg, r, ht, hid, hu, hv);
+                if (S.show_globals) {
+                    V3 v = sg.Ng;
+                    if (S.show_globals == 2) v = sg.N;
+                    if (S.show_globals == 3) v = vnormalized(sg.dPdu);
+                    if (S.show_globals == 4) v = vnormalized(sg.dPdv);
+                    if (S.show_globals == 5) v = mkv(sg.u, sg.v, 0.0f);
+                    V3 c = v;
+                    if (S.show_globals != 5)
+                        c = c * 0.5f + mkv(0.5f);
+                    path_radiance = path_radiance + path_weight * c;
+                    break;
+                }
+                const float radius = r.radius + r.spread * ht;
+                const int shaderID = __ldg(S.shaderids + hid);
+                if (shaderID < 0)
+                    break;
+                pool.reset();
+                sg.pool = &pool;
+                sg.Ci   = 0;
+                osl_execute_shader(shaderID, sg);
+                V3 Le = mkv(0.0f);
+                CompositeBSDF bsdf;
+                bsdf.num               = 0;
+                const bool last_bounce = b == S.max_bounces;
+                process_closure(pool, sg.Ci, Le, bsdf, last_bounce);
+                const int nlights = S.nlightprims;
+                float k           = 1;
+                if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {
+                    const float light_pick_pdf = 1.0f / nlights;
+                    float light_pdf            = light_pick_pdf * scene_shapepdf(S, hid, r.origin, sg.P);
+                    k                          = power_heuristic<WEIGHT_EVAL>(bsdf_pdf, light_pdf);
+                }
+                path_radiance = path_radiance + path_weight * k * Le;
+                if (last_bounce)
+                    break;
+                const V3 wo = -sg.I;
+                bsdf_prepare(bsdf, wo, path_weight, b >= S.rr_depth);
+                Sampler sampler;
+                sampler.seed  = (u32)L.pi[PI_SEED][slot];
+                sampler.index = (u32)L.pi[PI_INDEX][slot];
+                V3 s          = sampler.get();
+                L.pi[PI_SEED][slot] = (int)sampler.seed;
+                const float xi = s.x, yi = s.y, zi = s.z;
+                if (nlights > 0) {
+                    const float light_pick_pdf = 1.0f / nlights;
+                    float xl = xi * nlights;
+                    int ls   = (int)floorf(xl);
+                    xl -= ls;
+                    unsigned lid = __ldg(S.lightprims + ls);
+                    if (lid != (unsigned)hid) {
+                        LightSample sample = scene_sample(S, (int)lid, sg.P, xl, yi);
+                        BSample bs         = bsdf_eval(bsdf, wo, sample.dir);
+                        V3 contrib = path_weight * bs.weight
+                                     * power_heuristic<EVAL_WEIGHT>(light_pick_pdf * sample.pdf, bs.pdf);
+                        if ((contrib.x + contrib.y + contrib.z) > 0) {
+                            Hit sh = scene_intersect(S, sg.P, sample.dir, sample.dist, (unsigned)hid, lid);
+                            if (sh.t == sample.dist) {
+                                Ray shadow_ray;
+                                shadow_ray.origin    = sg.P;
+                                shadow_ray.direction = sample.dir;
+                                shadow_ray.radius    = radius;
+                                shadow_ray.spread = shadow_ray.roughness = 0.0f;
+                                shadow_ray.raytype = RAY_SHADOW;
+                                SG lsg;
+                                ClosurePool lpool;
+                                globals_from_hit(S, lsg, shadow_ray, sample.dist, (int)lid, sample.u, sample.v);
+                                lpool.reset();
+                                lsg.pool = &lpool;
+                                lsg.Ci   = 0;
+                                osl_execute_shader(__ldg(S.shaderids + lid), lsg);
+                                V3 lLe = mkv(0.0f);
+                                CompositeBSDF dummy;
+                                dummy.num = 0;
+                                process_closure(lpool, lsg.Ci, lLe, dummy, true);
+                                path_radiance = path_radiance + contrib * lLe;
+                            }
+                        }
+                    }
+                }
+                BSample p   = bsdf_sample(bsdf, wo, xi, yi, zi);
+                path_weight = path_weight * p.weight;
+                bsdf_pdf    = p.pdf;
+                if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
+                    break;
+                // continue the path
+                L.pf[PF_OX][slot] = sg.P.x; L.pf[PF_OY][slot] = sg.P.y; L.pf[PF_OZ][slot] = sg.P.z;
+                L.pf[PF_DX][slot] = p.wi.x; L.pf[PF_DY][slot] = p.wi.y; L.pf[PF_DZ][slot] = p.wi.z;
+                L.pf[PF_RADIUS][slot] = radius;
+                L.pf[PF_SPREAD][slot] = fmaxf(r.spread, p.roughness);
+                L.pf[PF_ROUGH][slot]  = p.roughness;
+                L.pf[PF_WX][slot] = path_weight.x; L.pf[PF_WY][slot] = path_weight.y; L.pf[PF_WZ][slot] = path_weight.z;
+                L.pf[PF_BSDFPDF][slot] = bsdf_pdf;
+                L.pi[PI_RAYTYPE][slot] = RAY_DIFFUSE;
+                L.pi[PI_PREVID][slot]  = hid;
+                L.pi[PI_BOUNCE][slot]  = b + 1;
+                alive = true;
+            } while (false);
+            L.pf[PF_LX][slot] = path_radiance.x;
+            L.pf[PF_LY][slot] = path_radiance.y;
+            L.pf[PF_LZ][slot] = path_radiance.z;
+        }
+        queue_push(L.queue_out, L.counters + 1, slot, alive);
+    }
+}
+
+// end of a bounce: the out queue becomes the in queue (host swaps the pointers)
+extern "C" __global__ void rt_swap(const __grid_constant__ RenderLaunch L)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        L.counters[0] = L.counters[1];
+        L.counters[1] = 0;
+    }
+}
+
+// fold the finished batch into the running image in the reference's order:
+// result = lerp(result, r, 1/(si+1))  for si = s0 .. s0+nsamples-1
+extern "C" __global__ void __launch_bounds__(256) rt_resolve(const __grid_constant__ RenderLaunch L)
+{
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
+        V3 result = L.s0 == 0 ? mkv(0.0f) : mkv(L.accum[3 * pix], L.accum[3 * pix + 1], L.accum[3 * pix + 2]);
+        for (int sb = 0; sb < L.nsamples; ++sb) {
+            int slot = sb * L.npix + pix;
+            V3 r     = mkv(L.pf[PF_LX][slot], L.pf[PF_LY][slot], L.pf[PF_LZ][slot]);
+            float t  = 1.0f / (float)(L.s0 + sb + 1);
+            result   = result * (1.0f - t) + r * t;
+        }
+        L.accum[3 * pix]     = result.x;
+        L.accum[3 * pix + 1] = result.y;
+        L.accum[3 * pix + 2] = result.z;
+    }
+}

@@ -124,6 +124,8 @@ class Gen {
 public:
     explicit Gen(Group& g) : g(g) {}
     std::string run();
+    // group as `namespace <ns> { ... __device__ void entry(SG&); }` for the renderer
+    std::string run_material(const std::string& ns);
 
 private:
     Group& g;
@@ -154,6 +156,7 @@ private:
         switch (s.type.base) {
         case Base::Int: return "int";
         case Base::String: return "int";  // interned string id
+        case Base::Closure: return "int";  // word offset into the closure pool
         case Base::Float: return s.has_derivs ? "Df" : "float";
         case Base::Color:
         case Base::Point:
@@ -187,6 +190,8 @@ private:
             return constexpr_(s);
         if (s.is_param())
             return "gd.L" + std::to_string(layer) + "_" + ident(s.name);
+        if (s.symtype == SymType::Global && s.name == "Ci")
+            return "sg.Ci";
         if (s.symtype == SymType::Global) {
             auto it = global_table().find(s.name);
             if (it == global_table().end())
@@ -390,8 +395,30 @@ void
 Gen::op_percomp(const Opcode& op)
 {
     const Symbol& d = S(op.args[0]);
-    if (d.type.base == Base::Closure || d.type.base == Base::Matrix)
-        unsupported("op '" + op.name + "' on closures/matrices");
+    if (d.type.base == Base::Closure) {
+        // llvm_gen_add / llvm_gen_mul closure branches -> osl_add_closure_closure,
+        // osl_mul_closure_{float,color} (opclosure.cpp:18-76)
+        if (op.args.size() != 3)
+            unsupported("closure op '" + op.name + "'");
+        int a = op.args[1], b = op.args[2];
+        if (op.name == "add") {
+            w(R(op.args[0]) + " = clos_add(*sg.pool, " + R(a) + ", " + R(b) + ");");
+            return;
+        }
+        if (op.name != "mul")
+            unsupported("closure op '" + op.name + "'");
+        if (S(a).type.base != Base::Closure)
+            std::swap(a, b);
+        std::string wt = R(b);
+        if (S(b).has_derivs)
+            wt = "nd(" + wt + ")";
+        if (S(b).type.base == Base::Int)
+            wt = "(float)" + wt;
+        w(R(op.args[0]) + " = clos_mul(*sg.pool, " + R(a) + ", " + wt + ");");
+        return;
+    }
+    if (d.type.base == Base::Matrix)
+        unsupported("op '" + op.name + "' on matrices");
     bool isint = d.type.base == Base::Int;
     bool dv    = false;
     if (d.has_derivs)
@@ -428,7 +455,7 @@ Gen::op_cmp(const Opcode& op)
     if (a.type.base == Base::String || (a.type.base == Base::Int && b.type.base == Base::Int)) {
         e = "(" + R(op.args[1]) + " " + cop + " " + R(op.args[2]) + ")";
     } else if (a.type.base == Base::Closure) {
-        unsupported("closure comparison");
+        e = "(" + R(op.args[1]) + " " + cop + " 0)";   // only closure == 0 / != 0 exist
     } else {
         int nc = std::max(a.type.ncomp(), b.type.ncomp());
         for (int c = 0; c < nc; ++c) {
@@ -552,8 +579,10 @@ Gen::emit_op(const Opcode& op)
                   + std::to_string(i) + "]);");
         } else if (d.type.base == Base::String) {
             w(R(op.args[0]) + " = " + R(op.args[1]) + ";");
-        } else if (d.type.base == Base::Matrix || d.type.base == Base::Closure) {
-            unsupported("assignment of matrix/closure values");
+        } else if (d.type.base == Base::Closure) {
+            w(R(op.args[0]) + " = " + (s.type.base == Base::Int ? std::string("0") : R(op.args[1])) + ";");
+        } else if (d.type.base == Base::Matrix) {
+            unsupported("assignment of matrix values");
         } else {
             (void)s;
             w("assign(" + R(op.args[0]) + ", " + R(op.args[1]) + ");");
@@ -692,6 +721,62 @@ Gen::emit_op(const Opcode& op)
         op_noise(op, false);
     } else if (n == "pnoise" || n == "psnoise" || n == "pcellnoise" || n == "phashnoise") {
         op_noise(op, true);
+    } else if (n == "closure") {
+        // llvm_gen_closure (llvm_gen.cpp:3786-3903): [weight] name params...
+        size_t i      = 1;
+        int weight    = -1;
+        if (i < op.args.size() && A((int)i).type.base != Base::String)
+            weight = op.args[i++];
+        if (i >= op.args.size() || !A((int)i).const_value())
+            unsupported("closure with a non-constant name");
+        std::string cname = A((int)i).svals.empty() ? "" : A((int)i).svals[0];
+        ++i;
+        std::vector<int> pos;
+        for (; i < op.args.size(); ++i)
+            pos.push_back(op.args[i]);
+        struct Reg {
+            const char* name;
+            int nparams;
+            const char* id;
+        };
+        static const Reg regs[] = {
+            { "emission", 0, "EMISSION_ID" },       { "background", 0, "BACKGROUND_ID" },
+            { "diffuse", 1, "DIFFUSE_ID" },         { "oren_nayar", 2, "OREN_NAYAR_ID" },
+            { "translucent", 1, "TRANSLUCENT_ID" }, { "phong", 2, "PHONG_ID" },
+            { "ward", 4, "WARD_ID" },               { "reflection", 1, "REFLECTION_ID" },
+            { "reflection", 2, "FRESNEL_REFLECTION_ID" }, { "refraction", 2, "REFRACTION_ID" },
+            { "transparent", 0, "TRANSPARENT_ID" }, { "transparent_bsdf", 0, "MX_TRANSPARENT_ID" },
+        };
+        const char* idname = nullptr;
+        for (const Reg& r : regs)
+            if (cname == r.name && (int)pos.size() == r.nparams)
+                idname = r.id;
+        if (!idname)
+            unsupported("closure '" + cname + "' with " + std::to_string(pos.size()) + " parameters is not registered");
+        int nwords = 0;
+        for (int a : pos) {
+            if (S(a).type.base == Base::String)
+                unsupported("string closure parameters");
+            nwords += S(a).type.ncomp();
+        }
+        std::string wexpr = "mkv(1.0f)";
+        if (weight >= 0) {
+            w("V3 w_; assign(w_, " + R(weight) + ");");
+            wexpr = "w_";
+        }
+        w(std::string("int c_ = clos_component(*sg.pool, ") + idname + ", " + std::to_string(nwords) + ", "
+          + (weight >= 0 ? "true" : "false") + ", " + wexpr + ");");
+        w("if (c_) {");
+        int off = 0;
+        for (int a : pos) {
+            std::string e = R(a);
+            if (S(a).has_derivs)
+                e = "nd(" + e + ")";
+            w("    putp(sg.pool->w + c_ + " + std::to_string(4 + off) + ", " + e + ");");
+            off += S(a).type.ncomp();
+        }
+        w("}");
+        w(R(op.args[0]) + " = c_;");
     } else if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
         // Device-side journal is a "next" row: the op has no
         // effect on shading results, so it is dropped with a recorded warning.
@@ -1035,12 +1120,62 @@ Gen::run()
     return out.str();
 }
 
+std::string
+Gen::run_material(const std::string& ns)
+{
+    int nlayers = (int)g.layers.size();
+    if (nlayers > 32)
+        throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
+    std::string gd = "struct GD {\n    unsigned ran;\n";
+    for (int l = 0; l < nlayers; ++l) {
+        if (g.layers[l].unused)
+            continue;
+        L  = &g.layers[l];
+        li = l;
+        for (Symbol& s : g.layers[l].m.syms)
+            if (s.is_param()) {
+                std::string arr = s.type.arraylen ? "[" + std::to_string(s.type.arraylen) + "]" : "";
+                gd += "    " + ctype(s) + " L" + std::to_string(l) + "_" + ident(s.name) + arr + ";\n";
+            }
+    }
+    gd += "};\n";
+    for (int l = 0; l < nlayers; ++l)
+        if (!g.layers[l].unused)
+            o << "static __device__ __forceinline__ void layer_" << l << "(SG& sg, GD& gd, const B200Launch& L);\n";
+    for (int l = 0; l < nlayers; ++l)
+        if (!g.layers[l].unused)
+            gen_layer(l);
+    std::ostringstream out;
+    out << "namespace " << ns << " {\n" << gd << o.str();
+    out << "static __device__ __noinline__ void entry(SG& sg)\n{\n    GD gd;\n    gd.ran = 0u;\n    B200Launch L;\n";
+    out << "    layer_" << (nlayers - 1) << "(sg, gd, L);\n}\n}  // namespace " << ns << "\n";
+    return out.str();
+}
+
 }  // namespace
 
 std::string
 generate_cuda(Group& g)
 {
     return Gen(g).run();
+}
+
+// All material groups of a scene + the wavefront integrator in one module.
+std::string
+generate_cuda_render(std::vector<Group*>& groups)
+{
+    std::ostringstream out;
+    out << "// generated by libosl_b200: render module with " << groups.size() << " material group(s)\n";
+    out << "#include \"osl_b200_device.cuh\"\n#include \"osl_b200_closure.cuh\"\n#include \"osl_b200_sg.cuh\"\n";
+    out << "using namespace osld;\nstruct B200Launch { int unused_; };\n";
+    for (size_t k = 0; k < groups.size(); ++k)
+        out << Gen(*groups[k]).run_material("mat" + std::to_string(k));
+    out << "static __device__ __forceinline__ void osl_execute_shader(int shaderID, SG& sg)\n{\n    switch (shaderID) {\n";
+    for (size_t k = 0; k < groups.size(); ++k)
+        out << "    case " << k << ": mat" << k << "::entry(sg); break;\n";
+    out << "    default: break;\n    }\n}\n";
+    out << "#include \"osl_b200_render.cuh\"\n";
+    return out.str();
 }
 
 }  // namespace oslb200

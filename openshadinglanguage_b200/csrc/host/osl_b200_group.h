@@ -141,4 +141,9 @@ struct Group {
 // Emit CUDA C++ for the whole group (kernel name: osl_b200_group_kernel).
 std::string generate_cuda(Group& g);
 
+// Emit one CUDA module holding every material group of a scene (namespaces
+// mat0, mat1, ...), the shader dispatch switch and the wavefront integrator
+// kernels of csrc/device/osl_b200_render.cuh.
+std::string generate_cuda_render(std::vector<Group*>& groups);
+
 }  // namespace oslb200

@@ -122,6 +122,20 @@ struct LaunchBlock {  // must match B200Launch in the generated code
 
 }  // namespace
 
+// shared with the other host translation units of the library
+namespace oslb200 {
+int
+set_error(int code, const std::string& msg)
+{
+    return fail(code, msg);
+}
+void
+count_launches(long long n)
+{
+    g_launches.fetch_add(n);
+}
+}  // namespace oslb200
+
 struct b200_group {
     Group g;
     std::string source;

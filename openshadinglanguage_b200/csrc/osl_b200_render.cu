@@ -1,0 +1,455 @@
+// osl_b200_render.cu — host side of the wavefront path tracer (product code).
+//
+// Plays the role of SimpleRaytracer::render (src/testrender/simpleraytracer.cpp:1424-1456)
+// and OptixRaytracer::render (src/testrender/optixraytracer.cpp): upload the
+// prepared scene once, JIT one module holding every material group plus the
+// integrator kernels (csrc/device/osl_b200_render.cuh), then per batch of
+// samples run  generate -> { intersect -> [sort by material] -> shade } until
+// no path is alive -> resolve.
+#include "../../include/osl_b200.h"
+#include "host/osl_b200_group.h"
+#include "osl_b200_jit.h"
+
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+
+namespace oslb200 {
+int set_error(int code, const std::string& msg);
+void count_launches(long long n);
+}  // namespace oslb200
+using namespace oslb200;
+
+namespace {
+
+// mirror of osld::RenderScene / RenderLaunch (device/osl_b200_render.cuh)
+struct DevScene {
+    int nverts, ntris, nnodes, nlightprims, nshaders, nmeshes;
+    const float* verts;
+    const float* normals;
+    const float* uvs;
+    const int* triangles;
+    const int* n_triangles;
+    const int* uv_triangles;
+    const int* shaderids;
+    const int* meshids;
+    const float* mesh_surfacearea;
+    const void* bvh_nodes;
+    const unsigned* bvh_indices;
+    const unsigned* lightprims;
+    const int* shader_is_light;
+    float eye[3], dir[3], up[3], fov;
+    float cx[3], cy[3], invw, invh;
+    int xres, yres;
+    int aa, max_bounces, rr_depth, no_jitter, show_globals;
+    int background_shader, background_resolution;
+};
+enum { PF_COUNT = 19, PI_COUNT = 6 };
+struct DevLaunch {
+    DevScene S;
+    float* pf[PF_COUNT];
+    int* pi[PI_COUNT];
+    int* queue_in;
+    int* queue_out;
+    int* counters;
+    int* sort_keys;
+    int nslots, npix, y0, s0, nsamples;
+    float* accum;
+};
+
+const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_intersect", "rt_sort_count", "rt_sort_scan",
+                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve" };
+enum { K_CAMERA, K_GENERATE, K_INTERSECT, K_SORT_COUNT, K_SORT_SCAN, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE, K_N };
+
+}  // namespace
+
+struct b200_render {
+    std::vector<std::unique_ptr<Group>> groups;
+    std::string source;
+    std::vector<char> cubin;
+    b200_render_scene host;  // host-pointer copy of the description
+    bool fma = true, sort = true;
+    long long slots_target = 4 << 20;
+    // per-device state
+    struct Dev {
+        CUmodule_ mod = nullptr;
+        CUfunction_ fn[K_N];
+        DevScene S;
+        std::vector<void*> allocs;
+        int sms = 148;
+        // path state
+        long long nslots_cap = 0;
+        float* pf            = nullptr;
+        int* pi              = nullptr;
+        int* queues          = nullptr;  // 3 x nslots
+        int* sort_keys       = nullptr;
+        int* counters        = nullptr;
+        float* accum         = nullptr;
+        long long accum_cap  = 0;
+    };
+    std::map<int, Dev> devs;
+};
+
+static std::map<std::string, std::string>
+parse_opts(const char* s)
+{
+    std::map<std::string, std::string> m;
+    if (!s)
+        return m;
+    std::istringstream in(s);
+    std::string kv;
+    while (std::getline(in, kv, ',')) {
+        size_t e = kv.find('=');
+        if (e == std::string::npos)
+            m[kv] = "1";
+        else
+            m[kv.substr(0, e)] = kv.substr(e + 1);
+    }
+    return m;
+}
+
+extern "C" int
+b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_group_desc* materials,
+                   const char* options, b200_render** out)
+{
+    if (!scene || !materials || nmaterials <= 0 || !out)
+        return set_error(B200_ERR_INVALID, "b200_render_create: bad arguments");
+    if (nmaterials > 62)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_render_create: more than 62 materials not supported yet");
+    if (scene->background_shader >= 0)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_render_create: background shaders are not supported yet");
+    *out = nullptr;
+    std::unique_ptr<b200_render> R(new b200_render);
+    auto opt = parse_opts(options);
+    if (opt.count("fma"))
+        R->fma = atoi(opt["fma"].c_str()) != 0;
+    if (opt.count("sort"))
+        R->sort = atoi(opt["sort"].c_str()) != 0;
+    if (opt.count("slots"))
+        R->slots_target = atoll(opt["slots"].c_str());
+    R->host = *scene;
+    try {
+        std::vector<Group*> gs;
+        for (int m = 0; m < nmaterials; ++m) {
+            const b200_group_desc& d = materials[m];
+            std::unique_ptr<Group> g(new Group);
+            g->name = d.name ? d.name : "material";
+            g->fma  = R->fma;
+            for (int i = 0; i < d.nlayers; ++i) {
+                const b200_layer& l = d.layers[i];
+                std::vector<ParamValue> pvs;
+                for (int p = 0; p < l.nparams; ++p) {
+                    const b200_param& bp = l.params[p];
+                    ParamValue pv;
+                    pv.name = bp.name ? bp.name : "";
+                    for (int k = 0; k < bp.nvalues; ++k) {
+                        if (bp.type == 0)
+                            pv.ivals.push_back(((const int*)bp.values)[k]);
+                        else if (bp.type == 1)
+                            pv.fvals.push_back(((const float*)bp.values)[k]);
+                        else
+                            pv.svals.push_back(((const char* const*)bp.values)[k]);
+                    }
+                    pvs.push_back(std::move(pv));
+                }
+                g->add_layer(l.oso_text, l.layername, pvs);
+            }
+            for (int i = 0; i < d.nconnections; ++i)
+                g->connect(d.connections[i].srclayer, d.connections[i].srcparam, d.connections[i].dstlayer,
+                           d.connections[i].dstparam);
+            g->finalize();
+            gs.push_back(g.get());
+            R->groups.push_back(std::move(g));
+        }
+        R->source = generate_cuda_render(gs);
+    } catch (const std::exception& e) {
+        return set_error(B200_ERR_COMPILE, e.what());
+    }
+    std::string err = jit_compile(R->source, "osl_b200_render.cu", R->fma, R->cubin);
+    if (!err.empty())
+        return set_error(B200_ERR_COMPILE, err);
+    *out = R.release();
+    return B200_OK;
+}
+
+extern "C" const char*
+b200_render_cuda_source(const b200_render* r)
+{
+    return r ? r->source.c_str() : "";
+}
+
+static void
+free_dev(b200_render::Dev& d)
+{
+    for (void* p : d.allocs)
+        cudaFree(p);
+    d.allocs.clear();
+    if (d.mod && jit_driver().ok)
+        jit_driver().cuModuleUnload(d.mod);
+}
+
+extern "C" void
+b200_render_destroy(b200_render* r)
+{
+    if (!r)
+        return;
+    for (auto& kv : r->devs) {
+        cudaSetDevice(kv.first);
+        free_dev(kv.second);
+    }
+    delete r;
+}
+
+template<class T>
+static const T*
+upload(b200_render::Dev& d, const T* host, size_t n, bool& ok)
+{
+    if (!host || n == 0)
+        return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+        ok = false;
+        return nullptr;
+    }
+    d.allocs.push_back(p);
+    if (cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+        ok = false;
+    return (const T*)p;
+}
+
+static int
+ensure_device(b200_render* r, int device, b200_render::Dev** out)
+{
+    auto it = r->devs.find(device);
+    if (it != r->devs.end()) {
+        *out = &it->second;
+        return B200_OK;
+    }
+    Driver& drv = jit_driver();
+    if (!drv.ok)
+        return set_error(B200_ERR_CUDA, "CUDA driver unavailable: " + drv.why);
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
+        return set_error(B200_ERR_CUDA, "cudaSetDevice failed");
+    b200_render::Dev d;
+    CUresult_ cr = drv.cuModuleLoadData(&d.mod, r->cubin.data());
+    if (cr != 0)
+        return set_error(B200_ERR_CUDA, "cuModuleLoadData(render): " + drv.err(cr));
+    for (int k = 0; k < K_N; ++k) {
+        cr = drv.cuModuleGetFunction(&d.fn[k], d.mod, KERNELS[k]);
+        if (cr != 0)
+            return set_error(B200_ERR_CUDA, std::string("cuModuleGetFunction(") + KERNELS[k] + "): " + drv.err(cr));
+    }
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device);
+    const b200_render_scene& h = r->host;
+    bool ok                    = true;
+    DevScene& S                = d.S;
+    memset(&S, 0, sizeof S);
+    S.nverts = h.nverts; S.ntris = h.ntris; S.nnodes = h.nnodes; S.nlightprims = h.nlightprims;
+    S.nshaders = h.nshaders; S.nmeshes = h.nmeshes;
+    // vertex-like arrays are indexed up to the largest referenced index: the caller passes exact sizes
+    S.verts   = upload(d, h.verts, (size_t)3 * h.nverts, ok);
+    // normals / uvs: sizes are not in the description; derive from the index arrays
+    int maxn = -1, maxuv = -1;
+    for (int i = 0; i < 3 * h.ntris; ++i) {
+        if (h.n_triangles[i] > maxn) maxn = h.n_triangles[i];
+        if (h.uv_triangles[i] > maxuv) maxuv = h.uv_triangles[i];
+    }
+    S.normals          = upload(d, h.normals, (size_t)3 * (maxn + 1), ok);
+    S.uvs              = upload(d, h.uvs, (size_t)2 * (maxuv + 1), ok);
+    S.triangles        = upload(d, h.triangles, (size_t)3 * h.ntris, ok);
+    S.n_triangles      = upload(d, h.n_triangles, (size_t)3 * h.ntris, ok);
+    S.uv_triangles     = upload(d, h.uv_triangles, (size_t)3 * h.ntris, ok);
+    S.shaderids        = upload(d, h.shaderids, (size_t)h.ntris, ok);
+    S.meshids          = upload(d, h.meshids, (size_t)h.ntris, ok);
+    S.mesh_surfacearea = upload(d, h.mesh_surfacearea, (size_t)h.nmeshes, ok);
+    S.bvh_nodes        = upload(d, h.bvh_nodes, (size_t)8 * h.nnodes, ok);
+    S.bvh_indices      = upload(d, h.bvh_indices, (size_t)h.ntris, ok);
+    S.lightprims       = upload(d, h.lightprims, (size_t)h.nlightprims, ok);
+    S.shader_is_light  = upload(d, h.shader_is_light, (size_t)h.nshaders, ok);
+    if (!ok) {
+        free_dev(d);
+        return set_error(B200_ERR_CUDA, "scene upload failed");
+    }
+    memcpy(S.eye, h.eye, sizeof S.eye);
+    memcpy(S.dir, h.dir, sizeof S.dir);
+    memcpy(S.up, h.up, sizeof S.up);
+    S.fov = h.fov;
+    S.xres = h.xres; S.yres = h.yres;
+    S.invw = 1.0f / h.xres;
+    S.invh = 1.0f / h.yres;
+    S.aa = h.aa < 1 ? 1 : h.aa;
+    S.max_bounces = h.max_bounces; S.rr_depth = h.rr_depth; S.no_jitter = h.no_jitter;
+    S.show_globals = h.show_globals;
+    S.background_shader = h.background_shader; S.background_resolution = h.background_resolution;
+    // camera: evaluate Camera::finalize on the device
+    float* dcam = nullptr;
+    if (cudaMalloc(&dcam, 9 * sizeof(float)) != cudaSuccess) {
+        free_dev(d);
+        return set_error(B200_ERR_CUDA, "cudaMalloc failed");
+    }
+    DevLaunch L;
+    memset(&L, 0, sizeof L);
+    L.S          = S;
+    void* args[] = { &L, &dcam };
+    cr           = drv.cuLaunchKernel(d.fn[K_CAMERA], 1, 1, 1, 32, 1, 1, 0, nullptr, args, nullptr);
+    float cam[9];
+    cudaError_t ce = cudaMemcpy(cam, dcam, sizeof cam, cudaMemcpyDeviceToHost);
+    cudaFree(dcam);
+    if (cr != 0 || ce != cudaSuccess) {
+        free_dev(d);
+        return set_error(B200_ERR_CUDA, "camera setup kernel failed: " + (cr ? drv.err(cr) : std::string(cudaGetErrorString(ce))));
+    }
+    memcpy(S.dir, cam, 12);
+    memcpy(S.cx, cam + 3, 12);
+    memcpy(S.cy, cam + 6, 12);
+    count_launches(1);
+    r->devs[device] = d;
+    *out            = &r->devs[device];
+    return B200_OK;
+}
+
+extern "C" int
+b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b200_render_stats* stats)
+{
+    if (!r || !host_rgb || y0 < 0 || y1 > r->host.yres || y0 >= y1)
+        return set_error(B200_ERR_INVALID, "b200_render_rows: bad arguments");
+    b200_render::Dev* dp = nullptr;
+    int rc               = ensure_device(r, device, &dp);
+    if (rc != B200_OK)
+        return rc;
+    b200_render::Dev& d = *dp;
+    Driver& drv         = jit_driver();
+    cudaSetDevice(device);
+    const int xres      = r->host.xres;
+    const long long npix = (long long)(y1 - y0) * xres;
+    const int nsamp     = d.S.aa * d.S.aa;
+    long long SB        = r->slots_target / npix;
+    if (SB < 1) SB = 1;
+    if (SB > nsamp) SB = nsamp;
+    const long long nslots = SB * npix;
+    if (nslots > 0x7fffffffLL / 4)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_render_rows: band too large; render fewer rows per call");
+    // (re)allocate path state
+    if (d.nslots_cap < nslots) {
+        auto drop = [&](void* p) {
+            if (!p) return;
+            cudaFree(p);
+            for (auto& a : d.allocs)
+                if (a == p) a = nullptr;
+        };
+        drop(d.pf); drop(d.pi); drop(d.queues); drop(d.sort_keys);
+        bool ok = cudaMalloc(&d.pf, sizeof(float) * PF_COUNT * nslots) == cudaSuccess
+                  && cudaMalloc(&d.pi, sizeof(int) * PI_COUNT * nslots) == cudaSuccess
+                  && cudaMalloc(&d.queues, sizeof(int) * 3 * nslots) == cudaSuccess
+                  && cudaMalloc(&d.sort_keys, sizeof(int) * nslots) == cudaSuccess;
+        if (!ok)
+            return set_error(B200_ERR_CUDA, "cudaMalloc(path state) failed");
+        d.allocs.push_back(d.pf); d.allocs.push_back(d.pi); d.allocs.push_back(d.queues); d.allocs.push_back(d.sort_keys);
+        d.nslots_cap = nslots;
+    }
+    if (!d.counters) {
+        if (cudaMalloc(&d.counters, sizeof(int) * 256) != cudaSuccess)
+            return set_error(B200_ERR_CUDA, "cudaMalloc failed");
+        d.allocs.push_back(d.counters);
+    }
+    if (d.accum_cap < npix) {
+        if (d.accum) {
+            cudaFree(d.accum);
+            for (auto& a : d.allocs)
+                if (a == d.accum) a = nullptr;
+        }
+        if (cudaMalloc(&d.accum, sizeof(float) * 3 * npix) != cudaSuccess)
+            return set_error(B200_ERR_CUDA, "cudaMalloc failed");
+        d.allocs.push_back(d.accum);
+        d.accum_cap = npix;
+    }
+    cudaMemset(d.counters, 0, sizeof(int) * 256);
+    DevLaunch L;
+    memset(&L, 0, sizeof L);
+    L.S = d.S;
+    for (int k = 0; k < PF_COUNT; ++k)
+        L.pf[k] = d.pf + (size_t)k * nslots;
+    for (int k = 0; k < PI_COUNT; ++k)
+        L.pi[k] = d.pi + (size_t)k * nslots;
+    int* qbuf[3]  = { d.queues, d.queues + nslots, d.queues + 2 * nslots };
+    L.counters    = d.counters;
+    L.sort_keys   = r->sort ? d.sort_keys : nullptr;
+    L.npix        = (int)npix;
+    L.y0          = y0;
+    L.accum       = d.accum;
+    long long launches = 0, iters = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    auto launch = [&](int k, long long work, unsigned block) -> int {
+        long long want = (work + block - 1) / block;
+        long long cap  = (long long)d.sms * 16;
+        unsigned grid  = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        void* args[]   = { &L };
+        CUresult_ cr   = drv.cuLaunchKernel(d.fn[k], grid, 1, 1, block, 1, 1, 0, nullptr, args, nullptr);
+        ++launches;
+        if (cr != 0)
+            return set_error(B200_ERR_CUDA, std::string("cuLaunchKernel(") + KERNELS[k] + "): " + drv.err(cr));
+        return B200_OK;
+    };
+    int* hcount = nullptr;
+    cudaMallocHost(&hcount, sizeof(int));
+    for (int s0 = 0; s0 < nsamp; s0 += (int)SB) {
+        int nb     = (int)((nsamp - s0) < SB ? (nsamp - s0) : SB);
+        L.s0       = s0;
+        L.nsamples = nb;
+        L.nslots   = (int)(nb * npix);
+        int cur    = 0;  // qbuf index of the live queue
+        L.queue_in = qbuf[cur];
+        if ((rc = launch(K_GENERATE, L.nslots, 256)) != B200_OK)
+            return rc;
+        long long live = L.nslots;
+        while (live > 0) {
+            ++iters;
+            L.queue_in  = qbuf[cur];
+            L.queue_out = qbuf[(cur + 1) % 3];
+            if ((rc = launch(K_INTERSECT, live, 256)) != B200_OK)
+                return rc;
+            if (r->sort && d.S.nshaders > 1) {
+                if ((rc = launch(K_SORT_COUNT, live, 256)) != B200_OK) return rc;
+                if ((rc = launch(K_SORT_SCAN, 1, 32)) != B200_OK) return rc;
+                if ((rc = launch(K_SORT_SCATTER, live, 256)) != B200_OK) return rc;
+                cur        = (cur + 1) % 3;  // sorted queue
+                L.queue_in = qbuf[cur];
+            }
+            L.queue_out = qbuf[(cur + 1) % 3];
+            if ((rc = launch(K_SHADE, live, 128)) != B200_OK)
+                return rc;
+            if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)
+                return rc;
+            cur = (cur + 1) % 3;
+            cudaMemcpyAsync(hcount, d.counters, sizeof(int), cudaMemcpyDeviceToHost, 0);
+            if (cudaStreamSynchronize(0) != cudaSuccess) {
+                cudaError_t ce = cudaGetLastError();
+                return set_error(B200_ERR_CUDA, std::string("render bounce failed: ") + cudaGetErrorString(ce));
+            }
+            live = *hcount;
+        }
+        if ((rc = launch(K_RESOLVE, npix, 256)) != B200_OK)
+            return rc;
+    }
+    cudaEventRecord(e1, 0);
+    cudaError_t ce = cudaMemcpy(host_rgb, d.accum, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost);
+    cudaFreeHost(hcount);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    count_launches(launches);
+    if (ce != cudaSuccess)
+        return set_error(B200_ERR_CUDA, std::string("render readback: ") + cudaGetErrorString(ce));
+    if (stats) {
+        stats->paths             = npix * nsamp;
+        stats->launches          = launches;
+        stats->bounce_iterations = iters;
+        stats->device_ms         = ms;
+    }
+    return B200_OK;
+}

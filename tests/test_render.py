@@ -1,0 +1,123 @@
+"""testrender path (BASELINE configs 3 and 5 at the reference test sizes).
+
+CPU: the restated scalar path tracer (oracle) reproduces the reference's
+golden renders render-cornell (128^2, aa 4) and render-bunny (128^2, aa 8)
+inside the reference's own thresholds (failthresh 0.01, failpercent 1 %;
+testsuite/render-cornell/run.py) — in practice to half-float precision.
+GPU: the wavefront integrator equals the oracle BIT FOR BIT in strict mode
+(same arithmetic, same sampler, same BVH, samples resolved in the same order)
+and stays inside the image thresholds with FMA contraction on.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle
+from openshadinglanguage_b200.render import scene as sc
+
+SCENES = os.path.join(helpers.GOLDEN, "scenes")
+CASES = {"render-cornell": ("cornell.xml", 128, 4), "render-bunny": ("bunny.xml", 128, 8)}
+_cache = {}
+
+
+def _scene(case):
+    if case not in _cache:
+        S = sc.load_scene(os.path.join(SCENES, CASES[case][0]))
+        _cache[case] = (S, S.prepare())
+    return _cache[case]
+
+
+def _golden(case):
+    return np.load(os.path.join(helpers.GOLDEN, "images", case + ".npz"))["pixels"].astype(np.float32)
+
+
+def _check_thresholds(img, ref, failthresh=0.01, failpercent=1.0):
+    d = np.abs(img - ref).max(axis=2)
+    assert (d > failthresh).mean() * 100.0 <= failpercent, "%.3f %% of pixels differ by more than %g" % (
+        (d > failthresh).mean() * 100.0, failthresh)
+
+
+def test_scene_preparation_invariants():
+    S, A = _scene("render-cornell")
+    # 6 quads x 2 triangles + 2 spheres x (2*64*128 - 2*... ) triangles; light = 2 triangles
+    assert len(A["lightprims"]) == 2 and A["shader_is_light"].sum() == 1
+    assert len(A["triangles"]) == 12 + 2 * (2 * 128 + 2 * 128 * 63)
+    nodes = A["bvh_nodes"]
+    nprims = nodes[:, 7].view(np.uint32)
+    child = nodes[:, 6].view(np.uint32)
+    assert nprims[nprims > 0].sum() == len(A["triangles"])       # every triangle in exactly one leaf
+    assert sorted(A["bvh_indices"].tolist()) == list(range(len(A["triangles"])))
+    inner = np.where(nprims == 0)[0]
+    assert np.all(child[inner] + 1 < len(nodes))
+    # children boxes are inside their parent
+    for i in inner[:200]:
+        for c in (child[i], child[i] + 1):
+            assert np.all(nodes[c, [0, 2, 4]] >= nodes[i, [0, 2, 4]]) and np.all(nodes[c, [1, 3, 5]] <= nodes[i, [1, 3, 5]])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_oracle_matches_reference_golden_render(case):
+    S, A = _scene(case)
+    xml, res, aa = CASES[case]
+    R = oracle.OracleRender(S, A, helpers.oso)
+    img = R.render(res, res, aa, nthreads=8)
+    ref = _golden(case)
+    assert img.shape == ref.shape
+    _check_thresholds(img, ref)
+    # far stronger in practice: identical after rounding to the golden's half precision
+    h = img.astype(np.float16).astype(np.float32)
+    assert (np.abs(h - ref).max(axis=2) == 0).mean() > 0.99
+
+
+def test_render_module_compiles_without_gpu(b200lib):
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-cornell")
+    R = api.Renderer(S, A, helpers.oso, 64, 64, 2)
+    src = R.cuda_source
+    assert "mat0::entry" in src and "osl_b200_render.cuh" in src and "clos_component" in src
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("sort", [0, 1])
+def test_gpu_render_bit_exact_vs_oracle(b200lib, cuda_device, case, sort):
+    from openshadinglanguage_b200 import api
+    S, A = _scene(case)
+    xml, res, aa = CASES[case]
+    want = oracle.OracleRender(S, A, helpers.oso).render(res, res, aa, nthreads=8)
+    R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=0,sort=%d" % sort)
+    got = R.render()
+    assert R.stats["paths"] == res * res * aa * aa
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+        "max |d| = %g, differing pixels %d" % (np.abs(got - want).max(), (got != want).any(axis=2).sum())
+    _check_thresholds(got, _golden(case))
+
+
+@pytest.mark.gpu
+def test_gpu_render_fast_mode_and_bands(b200lib, cuda_device):
+    """FMA mode stays inside the reference image thresholds; rendering in row
+    bands (the multi-GPU partition) and with few paths in flight gives the
+    same pixels as one call."""
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-cornell")
+    res, aa = 128, 4
+    fast = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=1").render()
+    _check_thresholds(fast, _golden("render-cornell"))
+    R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=0,slots=20000")
+    whole = R.render()
+    bands = np.concatenate([R.render(0, 50), R.render(50, 51), R.render(51, 128)])
+    assert np.array_equal(whole.view(np.uint32), bands.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_first_hit_globals(b200lib, cuda_device):
+    """Deterministic first-hit AOVs (testrender -normals / -uvs style,
+    simpleraytracer.cpp:1007-1023) equal the oracle exactly."""
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-cornell")
+    for mode in (1, 2, 5):
+        want = oracle.OracleRender(S, A, helpers.oso).render(96, 96, 1, nthreads=4, show_globals=mode)
+        got = api.Renderer(S, A, helpers.oso, 96, 96, 1, show_globals=mode, options="fma=0").render()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), mode

@@ -45,6 +45,21 @@ SHADERS = {
     "layers_lazy_c": "layers-lazy/c.osl",
     "layers_a": "layers/a.osl",
     "layers_b": "layers/b.osl",
+    # testrender materials (same sources in render-cornell and render-bunny)
+    "matte": "render-cornell/matte.osl",
+    "metal": "render-cornell/metal.osl",
+    "emitter": "render-cornell/emitter.osl",
+}
+# scene descriptions + model data of the testrender configs (test input data)
+SCENES = {
+    "cornell.xml": "render-cornell/cornell.xml",
+    "bunny.xml": "render-bunny/bunny.xml",
+    "bunny.obj": "render-bunny/bunny.obj",
+}
+# golden renders (half-float EXR in the reference; stored as float16 npz)
+RENDERS = {
+    "render-cornell": "render-cornell/ref/out.exr",
+    "render-bunny": "render-bunny/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
@@ -105,6 +120,15 @@ def main():
     for name, rel in TEXTS.items():
         with open(os.path.join(TS, rel)) as f, open(os.path.join(OUT, "text", name + ".txt"), "w") as o:
             o.write(f.read())
+    os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
+    for name, rel in SCENES.items():
+        with open(os.path.join(TS, rel), "rb") as f, open(os.path.join(OUT, "scenes", name), "wb") as o:
+            o.write(f.read())
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    import cv2
+    for name, rel in RENDERS.items():
+        img = cv2.imread(os.path.join(TS, rel), cv2.IMREAD_UNCHANGED)[..., ::-1][..., :3]
+        np.savez_compressed(os.path.join(OUT, "images", name + ".npz"), pixels=img.astype(np.float16))
     with open(os.path.join(OUT, "noise_vectors.json"), "w") as f:
         json.dump(parse_noise_vectors(), f, indent=1)
     print("fixtures written to", OUT)
