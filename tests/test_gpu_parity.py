@@ -150,7 +150,8 @@ def test_group_matches_oracle_and_golden_image(b200lib, cuda_device, case):
         # the image threshold of the reference test is the bar
         pass
     else:
-        assert np.abs(fast - want).max() <= FAST_ATOL
+        # simplex sums are scaled by 54..68 at the end, which scales the contraction drift too
+        assert np.abs(fast - want).max() <= (1e-5 if "simplex" in case else FAST_ATOL)
     # and against the reference's own golden image, through the GPU path
     ref, step, _ = helpers.golden_image(case)
     # hashnoise amplifies any input ulp into a different hash (the reference keeps a
