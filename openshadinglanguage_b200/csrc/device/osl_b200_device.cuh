@@ -984,3 +984,4 @@ OSLD V3 o_Dy(V3) { return mkv(0.0f); }
 }  // namespace osld
 
 #include "osl_b200_simplex.cuh"
+#include "osl_b200_spline.cuh"

@@ -721,6 +721,53 @@ Gen::emit_op(const Opcode& op)
         op_noise(op, false);
     } else if (n == "pnoise" || n == "psnoise" || n == "pcellnoise" || n == "phashnoise") {
         op_noise(op, true);
+    } else if (n == "spline" || n == "splineinverse") {
+        // llvm_gen_spline (llvm_gen.cpp:3673-3740): result, basis name, x, [nknots], knots[]
+        if (op.args.size() < 4)
+            unsupported("malformed spline op");
+        bool has_count = op.args.size() == 5;
+        int kn         = has_count ? op.args[4] : op.args[3];
+        const Symbol &d = A(0), &basis = A(1), &x = A(2), &knots = S(kn);
+        if (!knots.type.arraylen)
+            unsupported("spline knots must be an array");
+        std::string count = has_count ? R(op.args[3]) : std::to_string(knots.type.arraylen);
+        bool dv           = d.has_derivs && (x.has_derivs || knots.has_derivs);
+        static const char* names[] = { "catmull-rom", "bezier", "bspline", "hermite", "linear", "constant" };
+        std::string bt;
+        if (basis.const_value()) {
+            std::string bn = basis.svals.empty() ? "" : basis.svals[0];
+            int t          = 4;
+            for (int k = 0; k < 6; ++k)
+                if (bn == names[k])
+                    t = k;
+            if (bn == "catmullrom")
+                t = 0;
+            bt = std::to_string(t);
+        } else {
+            // runtime name: compare the interned string id against the known basis names
+            std::string s = R(op.args[1]);
+            bt            = "(";
+            for (int k = 0; k < 6; ++k)
+                if (k != 4)
+                    bt += s + " == " + std::to_string(g.intern(names[k])) + " ? " + std::to_string(k) + " : ";
+            bt += "4)";
+        }
+        std::string len = std::to_string(knots.type.arraylen);
+        if (n == "splineinverse") {
+            w("float k_[" + len + "]; for (int i_ = 0; i_ < " + len + "; ++i_) k_[i_] = nd(" + R(kn) + "[i_]);");
+            w("assign(" + R(op.args[0]) + ", spline_inverse(nd(" + R(op.args[2]) + "), k_, " + count + ", " + bt + "));");
+        } else {
+            std::string xe = R(op.args[2]);
+            if (x.has_derivs && !dv)
+                xe = "nd(" + xe + ")";
+            std::string ke = R(kn);
+            if (knots.has_derivs && !dv) {
+                w(std::string(knots.type.is_triple() ? "V3" : "float") + " k_[" + len + "]; for (int i_ = 0; i_ < " + len
+                  + "; ++i_) k_[i_] = nd(" + R(kn) + "[i_]);");
+                ke = "k_";
+            }
+            w("spline_eval(" + R(op.args[0]) + ", " + xe + ", " + ke + ", " + count + ", " + bt + ");");
+        }
     } else if (n == "closure") {
         // llvm_gen_closure (llvm_gen.cpp:3786-3903): [weight] name params...
         size_t i      = 1;

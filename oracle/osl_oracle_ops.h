@@ -716,4 +716,134 @@ template<int KIND, int NC> inline void ihnoise_core(float* out, int dim, const f
     }
 }
 
+// ---------------------------------------------------------------------------
+// spline / splineinverse (src/liboslexec/splineimpl.h:15-295, opspline.cpp)
+// ---------------------------------------------------------------------------
+struct SplineBasis {
+    int step;
+    float b[4][4];
+};
+enum { SPL_CATMULLROM, SPL_BEZIER, SPL_BSPLINE, SPL_HERMITE, SPL_LINEAR, SPL_CONSTANT };
+static const SplineBasis g_spline_basis[6] = {
+    { 1, { { (-1.0f / 2.0f), (3.0f / 2.0f), (-3.0f / 2.0f), (1.0f / 2.0f) },
+           { (2.0f / 2.0f), (-5.0f / 2.0f), (4.0f / 2.0f), (-1.0f / 2.0f) },
+           { (-1.0f / 2.0f), (0.0f / 2.0f), (1.0f / 2.0f), (0.0f / 2.0f) },
+           { (0.0f / 2.0f), (2.0f / 2.0f), (0.0f / 2.0f), (0.0f / 2.0f) } } },
+    { 3, { { -1, 3, -3, 1 }, { 3, -6, 3, 0 }, { -3, 3, 0, 0 }, { 1, 0, 0, 0 } } },
+    { 1, { { (-1.0f / 6.0f), (3.0f / 6.0f), (-3.0f / 6.0f), (1.0f / 6.0f) },
+           { (3.0f / 6.0f), (-6.0f / 6.0f), (3.0f / 6.0f), (0.0f / 6.0f) },
+           { (-3.0f / 6.0f), (0.0f / 6.0f), (3.0f / 6.0f), (0.0f / 6.0f) },
+           { (1.0f / 6.0f), (4.0f / 6.0f), (1.0f / 6.0f), (0.0f / 6.0f) } } },
+    { 2, { { 2, 1, -2, 1 }, { -3, -2, 3, -1 }, { 0, 1, 0, 0 }, { 1, 0, 0, 0 } } },
+    { 1, { { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, -1, 1, 0 }, { 0, 1, 0, 0 } } },
+    { 1, { { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, 0, 0, 0 }, { 0, 0, 0, 0 } } }
+};
+inline int spline_type(const char* n)
+{
+    if (!n) return SPL_LINEAR;
+    if (!std::strcmp(n, "catmull-rom") || !std::strcmp(n, "catmullrom")) return SPL_CATMULLROM;
+    if (!std::strcmp(n, "bezier")) return SPL_BEZIER;
+    if (!std::strcmp(n, "bspline")) return SPL_BSPLINE;
+    if (!std::strcmp(n, "hermite")) return SPL_HERMITE;
+    if (!std::strcmp(n, "constant")) return SPL_CONSTANT;
+    return SPL_LINEAR;
+}
+inline Dv operator*(const V3& a, const Df& b) { return Dv(a * b.val, a * b.dx, a * b.dy); }
+inline Dv operator+(const Dv& a, const V3& b) { return Dv(a.val + b, a.dx, a.dy); }
+inline float sclamp01(float a) { return (a >= 0.0f) ? ((a <= 1.0f) ? a : 1.0f) : 0.0f; }
+inline Df sclamp01(const Df& a) { return (a.val >= 0.0f) ? ((a.val <= 1.0f) ? a : Df(1.0f)) : Df(0.0f); }
+// R result, X abscissa (float|Df), K knot element type (float|Df|V3|Dv)
+template<class R, class X, class K>
+inline void spline_eval(R& result, const X& xval, const K* knots, int knot_count, int type)
+{
+    const SplineBasis& sp = g_spline_basis[type];
+    X x        = sclamp01(xval);
+    int nsegs  = ((knot_count - 4) / sp.step) + 1;
+    x          = x * (float)nsegs;
+    float segx = nd(x);
+    int segnum = (int)segx;
+    if (segnum < 0) segnum = 0;
+    if (segnum > (nsegs - 1)) segnum = nsegs - 1;
+    if (type == SPL_CONSTANT) {
+        assign(result, nd(knots[segnum + 1]));
+        return;
+    }
+    x     = x - float(segnum);
+    int s = segnum * sp.step;
+    K P[4];
+    for (int k = 0; k < 4; k++)
+        P[k] = knots[s + k];
+    K tk[4];
+    for (int k = 0; k < 4; k++)
+        tk[k] = sp.b[k][0] * P[0] + sp.b[k][1] * P[1] + sp.b[k][2] * P[2] + sp.b[k][3] * P[3];
+    auto t = (tk[0] * x + tk[1]);
+    auto t2 = (t * x + tk[2]);
+    auto t3 = (t2 * x + tk[3]);
+    assign(result, t3);
+}
+// splineinverse: OIIO::invert (regula falsi / bisection hybrid, 32 iterations, eps 1e-6)
+template<class F> inline float oiio_invert(F& func, float y, float xmin, float xmax, int maxiters, float eps, bool* brack)
+{
+    float v0 = func(xmin), v1 = func(xmax);
+    float x = xmin, v = v0;
+    bool increasing = (v0 < v1);
+    float vmin = increasing ? v0 : v1, vmax = increasing ? v1 : v0;
+    bool bracketed = (y >= vmin && y <= vmax);
+    if (brack) *brack = bracketed;
+    if (!bracketed)
+        return ((y < vmin) == increasing) ? xmin : xmax;
+    if (std::fabs(v0 - v1) < eps)
+        return x;
+    int rfiters = (3 * maxiters) / 4;
+    for (int iters = 0; iters < maxiters; ++iters) {
+        float t;
+        if (iters < rfiters) {
+            t = (y - v0) / (v1 - v0);
+            if (t <= 0.0f || t >= 1.0f)
+                t = 0.5f;
+        } else {
+            t = 0.5f;
+        }
+        x = xmin * (1.0f - t) + xmax * t;   // OIIO::lerp
+        v = func(x);
+        if ((v < y) == increasing) {
+            xmin = x;
+            v0   = v;
+        } else {
+            xmax = x;
+            v1   = v;
+        }
+        if (std::fabs(xmax - xmin) < eps || std::fabs(v - y) < eps)
+            return x;
+    }
+    return x;
+}
+inline float spline_inverse(float y, const float* knots, int knot_count, int type)
+{
+    const SplineBasis& sp = g_spline_basis[type];
+    int lowindex  = sp.step == 1 ? 1 : 0;
+    int highindex = sp.step == 1 ? knot_count - 2 : knot_count - 1;
+    bool increasing = knots[1] < knots[knot_count - 2];
+    if (increasing) {
+        if (y <= knots[lowindex]) return 0.0f;
+        if (y >= knots[highindex]) return 1.0f;
+    } else {
+        if (y >= knots[lowindex]) return 0.0f;
+        if (y <= knots[highindex]) return 1.0f;
+    }
+    auto S = [&](float x) { float v; spline_eval(v, x, knots, knot_count, type); return v; };
+    int nsegs     = (knot_count - 4) / sp.step + 1;
+    float nseginv = 1.0f / nsegs;
+    float r0 = 0.0f, x = 0.0f;
+    for (int s = 0; s < nsegs; ++s) {
+        float r1 = nseginv * (s + 1);
+        bool brack;
+        x = oiio_invert(S, y, r0, r1, 32, 1.0e-6f, &brack);
+        if (brack)
+            return x;
+        r0 = r1;
+    }
+    return x;
+}
+
 }  // namespace oslo

@@ -348,6 +348,9 @@ SG_GLOBALS = {"P": "sg.P", "I": "sg.I", "N": "sg.N", "Ng": "sg.Ng", "u": "sg.u",
               "v": "sg.v", "dPdu": "sg.dPdu", "dPdv": "sg.dPdv", "Ps": "sg.Ps",
               "time": "sg.time", "dtime": "sg.dtime", "dPdtime": "sg.dPdtime", "Ci": "sg.Ci"}
 
+SPLINE_TYPES = {"catmull-rom": 0, "catmullrom": 0, "bezier": 1, "bspline": 2, "hermite": 3,
+                "linear": 4, "constant": 5}
+
 # closure registry of the testrender renderer (src/testrender/shading.cpp:194-297):
 # (name, number of positional params) -> closure id constant
 CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
@@ -985,6 +988,33 @@ class Gen:
         for c in range(nc):
             self.w("setc(%s, %d, out_[%d]);" % (self.R(d), c, c))
 
+
+    def op_spline(self, op):
+        """llvm_gen_spline (llvm_gen.cpp:3673-3740) -> osl_spline_* (opspline.cpp)."""
+        A = op.args
+        d, basis, x = A[0], A[1], A[2]
+        knots = A[4] if len(A) == 5 else A[3]
+        count = self.R(A[3]) if len(A) == 5 else str(knots.t.arr)
+        dv = d.has_derivs and (x.has_derivs or knots.has_derivs)
+        bt = str(SPLINE_TYPES.get(basis.vals[0], 4)) if basis.constval else "spline_type(%s)" % self.R(basis)
+        xe = self.R(x)
+        if x.has_derivs and not dv:
+            xe = "nd(%s)" % xe
+        if op.name == "splineinverse":
+            self.w("{ float k_[%d]; for (int i_ = 0; i_ < %d; ++i_) k_[i_] = nd(%s[i_]);" % (
+                knots.t.arr, knots.t.arr, self.R(knots)))
+            self.w("  assign(%s, spline_inverse(nd(%s), k_, %s, %s)); }" % (self.R(d), self.R(x), count, bt))
+            return
+        if knots.has_derivs and not dv:
+            kt = "V3" if knots.t.triple else "float"
+            self.w("%s k_[%d]; for (int i_ = 0; i_ < %d; ++i_) k_[i_] = nd(%s[i_]);" % (
+                kt, knots.t.arr, knots.t.arr, self.R(knots)))
+            ke = "k_"
+        else:
+            ke = self.R(knots)
+        self.w("spline_eval(%s, %s, %s, %s, %s);" % (self.R(d), xe, ke, count, bt))
+
+    op_splineinverse = op_spline
 
     def op_printf(self, op):
         A = op.args

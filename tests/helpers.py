@@ -61,6 +61,34 @@ def image_case_group(case):
     return layers, outputs, c["res"]
 
 
+# testsuite/spline: "-g 256 256 -od uint8 -o Cspline color.tif -o DxCspline dcolor.tif
+#   -o Fspline float.tif -o DxFspline dfloat.tif -o NumKnots numknots.tif test"
+# one dense arena per output like testshade's setup_output_images
+SPLINE_OUTPUTS = [("Cspline", 3, "spline-color"), ("DxCspline", 3, "spline-dcolor"),
+                  ("Fspline", 1, "spline-float"), ("DxFspline", 1, "spline-dfloat"),
+                  ("NumKnots", 1, "spline-numknots")]
+
+
+def spline_case(res=256):
+    layers = [dict(oso=oso("spline_test"), name="layer0", params={})]
+    outputs, off = [], 0
+    for name, ch, _ in SPLINE_OUTPUTS:
+        outputs.append(dict(name=name, offset=off, stride=4 * ch))
+        off += 4 * ch * res * res
+    return layers, outputs, off // 4
+
+
+def check_spline_images(arena, res=256):
+    o = 0
+    for name, ch, gold in SPLINE_OUTPUTS:
+        img = arena[o:o + ch * res * res].reshape(res, res, ch)
+        o += ch * res * res
+        ref, step, shape = golden_image(gold)
+        assert shape == (res, res)
+        d = np.abs(quantize_u8(img)[::step, ::step].astype(int) - ref[..., :ch].astype(int))
+        assert (d > 1).mean() <= 0.0005, (name, (d > 1).mean())
+
+
 LAYERS_LAZY = dict(
     layers=[("layers_lazy_a", "alayer"), ("layers_lazy_b", "blayer"), ("layers_lazy_c", "clayer")],
     connections=[("alayer", "f_out", "clayer", "f_in"), ("alayer", "c_out", "clayer", "c_in"),

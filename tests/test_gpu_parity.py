@@ -162,6 +162,30 @@ def test_group_matches_oracle_and_golden_image(b200lib, cuda_device, case):
         assert (d > 1).mean() <= 0.0005
 
 
+def test_spline_group_matches_oracle_and_golden(b200lib, cuda_device):
+    """spline() with run-time basis names, float/colour knots, derivatives; five
+    outputs in five separate arenas (testsuite/spline)."""
+    import torch
+    res = 256
+    layers, outputs, nfloats = helpers.spline_case(res)
+    og = oracle.OracleGroup(layers, outputs=outputs)
+    ovar, ouni = oracle.testshade_globals(res, res)
+    want = np.zeros(nfloats, np.float32)
+    og.run(res * res, ovar, ouni, want, nthreads=4)
+    g = b200lib.ShaderGroup(layers, outputs=outputs, options="fma=0")
+    var, uni = b200lib.grid_globals(res, res)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(nfloats, dtype=torch.float32, device=cuda_device)
+    g.execute(res * res, dvar, uni, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), np.abs(got - want).max()
+    helpers.check_spline_images(got, res)
+    host = np.zeros(nfloats, np.float32)
+    g.execute_host(res * res, var, uni, host)
+    assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+
+
 def test_host_path_matches_device_path(b200lib, cuda_device):
     layers, outputs, res = helpers.image_case_group("noise")
     a = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=0", 3)

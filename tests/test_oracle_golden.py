@@ -113,6 +113,17 @@ def test_golden_images(case):
     assert d.max() == 0
 
 
+def test_spline_golden_images():
+    """testsuite/spline: five outputs (values and Dx derivatives, five bases chosen by a
+    run-time string, knot arrays with derivatives) against the reference images."""
+    layers, outputs, nfloats = helpers.spline_case()
+    g = oracle.OracleGroup(layers, outputs=outputs)
+    var, uni = oracle.testshade_globals(256, 256)
+    arena = np.zeros(nfloats, np.float32)
+    g.run(256 * 256, var, uni, arena, nthreads=4)
+    helpers.check_spline_images(arena)
+
+
 def test_oracle_globals_match_product_harness():
     """The product's grid harness and the oracle's restatement of testshade's
     setup_shaderglobals agree bit-for-bit."""

@@ -43,6 +43,7 @@ SHADERS = {
     "layers_lazy_a": "layers-lazy/a.osl",
     "layers_lazy_b": "layers-lazy/b.osl",
     "layers_lazy_c": "layers-lazy/c.osl",
+    "spline_test": "spline/test.osl",
     "layers_a": "layers/a.osl",
     "layers_b": "layers/b.osl",
     # testrender materials (same sources in render-cornell and render-bunny)
@@ -69,6 +70,11 @@ IMAGES = {
     "noise-cell": "noise-cell/ref/out.tif",
     "noise-perlin": "noise-perlin/ref/out.tif",
     "noise-simplex": "noise-simplex/ref/out.tif",
+    "spline-color": "spline/ref/color.tif",
+    "spline-dcolor": "spline/ref/dcolor.tif",
+    "spline-float": "spline/ref/float.tif",
+    "spline-dfloat": "spline/ref/dfloat.tif",
+    "spline-numknots": "spline/ref/numknots.tif",
     "pnoise": "pnoise/ref/out.tif",
     "pnoise-cell": "pnoise-cell/ref/out.tif",
     "pnoise-perlin": "pnoise-perlin/ref/out.tif",
