@@ -315,8 +315,13 @@ class Renderer:
     """testrender mirror: scene (openshadinglanguage_b200.render.scene.Scene),
     its prepared arrays, and a lookup  shader name -> .oso text."""
 
-    def __init__(self, scene, arrays, oso_lookup, xres, yres, aa, max_bounces=1000000, rr_depth=5,
+    def __init__(self, scene, arrays, oso_lookup, xres, yres, aa, max_bounces=None, rr_depth=None,
                  no_jitter=False, show_globals=0, options=""):
+        # testrender defaults (simpleraytracer.cpp:1226), overridden by the scene's <Option>
+        if max_bounces is None:
+            max_bounces = scene.options.get("max_bounces", 1000000)
+        if rr_depth is None:
+            rr_depth = scene.options.get("rr_depth", 5)
         L = lib()
         L.b200_render_create.argtypes = [ctypes.POINTER(_RenderScene), ctypes.c_int, ctypes.POINTER(_GroupDesc),
                                          ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]

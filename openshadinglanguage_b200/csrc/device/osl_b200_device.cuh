@@ -655,6 +655,36 @@ OSLD float fast_erf(float x)
     return copysignf(1.0f - 1.0f / v, x);
 }
 OSLD float fast_erfc(float x) { return 1.0f - fast_erf(x); }
+// Mike Giles' single-precision erfinv polynomial, as OIIO fast_ierf (fmath.h)
+OSLD float fast_ierf(float x)
+{
+    float a = fminf(fabsf(x), 0.99999994f);
+    float w = -fast_log((1.0f - a) * (1.0f + a)), p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f;
+        p = madd(p, w, 3.43273939e-07f);
+        p = madd(p, w, -3.5233877e-06f);
+        p = madd(p, w, -4.39150654e-06f);
+        p = madd(p, w, 0.00021858087f);
+        p = madd(p, w, -0.00125372503f);
+        p = madd(p, w, -0.00417768164f);
+        p = madd(p, w, 0.246640727f);
+        p = madd(p, w, 1.50140941f);
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f;
+        p = madd(p, w, 0.000100950558f);
+        p = madd(p, w, 0.00134934322f);
+        p = madd(p, w, -0.00367342844f);
+        p = madd(p, w, 0.00573950773f);
+        p = madd(p, w, -0.0076224613f);
+        p = madd(p, w, 0.00943887047f);
+        p = madd(p, w, 1.00167406f);
+        p = madd(p, w, 2.83297682f);
+    }
+    return p * x;
+}
 OSLD float fast_cbrt(float x)
 {
     float x0 = fabsf(x);

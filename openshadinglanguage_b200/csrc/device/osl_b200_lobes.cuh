@@ -1,0 +1,317 @@
+// osl_b200_lobes.cuh — testrender's glossy lobes for the wavefront integrator.
+//
+//   Phong                         src/testrender/shading.cpp:323-364
+//   Ward                          src/testrender/shading.cpp:366-448
+//   GGXDist / BeckmannDist        src/testrender/shading.cpp:472-560
+//   Microfacet<Dist, 0|1|2>       src/testrender/shading.cpp:563-799
+//
+// Included from osl_b200_render.cuh after `struct Lobe` when the scene's
+// materials use one of these closures (the host code generator defines
+// OSLD_GLOSSY_LOBES); scenes without them keep the small 5-word lobe record.
+// The reference picks the distribution and the reflect/refract/both variant
+// through template parameters; here both are fields of the lobe record and the
+// branches are warp-uniform for a material-sorted wavefront.
+#pragma once
+
+namespace osld {
+
+OSLD float sqr_(float x) { return x * x; }
+OSLD V3 frame_tolocal(const Lobe& l, V3 a) { return mkv(dot3(a, l.fu), dot3(a, l.fv), dot3(a, l.N)); }
+OSLD V3 frame_toworld(const Lobe& l, V3 a) { return a.x * l.fu + a.y * l.fv + a.z * l.N; }
+OSLD void lobe_set_frame(Lobe& l, V3 t)
+{
+    // TangentFrame::from_normal_and_tangent (sampling.h:30-42)
+    V3 x        = t - l.N * dot3(l.N, t);
+    float xlen2 = dot3(x, x);
+    if (xlen2 > 0) {
+        x    = x * (1.0f / sqrtf(xlen2));
+        l.fu = x;
+        l.fv = cross3(l.N, x);
+    } else {
+        TangentFrame f = frame_from_normal(l.N);
+        l.fu           = f.u;
+        l.fv           = f.v;
+    }
+}
+
+// ---- distributions ---------------------------------------------------------------------
+OSLD float dist_F(bool ggx, float tan_m2)
+{
+    if (ggx)
+        return 1 / ((float)OSLD_PI * (1 + tan_m2) * (1 + tan_m2));
+    return (float)(1 / OSLD_PI) * fast_exp(-tan_m2);
+}
+OSLD float dist_Lambda(bool ggx, float a2)
+{
+    if (ggx)
+        return 0.5f * (-1.0f + sqrtf(1.0f + 1.0f / a2));
+    const float a = sqrtf(a2);
+    return a < 1.6f ? (1.0f - 1.259f * a + 0.396f * a2) / (3.535f * a + 2.181f * a2) : 0.0f;
+}
+OSLD void ggx_sample_slope(float cos_theta, float randu, float randv, float& sx, float& sy)
+{
+    float c   = cos_theta < 1e-6f ? 1e-6f : cos_theta;
+    float Q   = (1 + c) * randu - c;
+    float num = c * sqrtf((1 - c) * (1 + c)) - Q * sqrtf((1 - Q) * (1 + Q));
+    float den = (Q - c) * (Q + c);
+    float eps = 1.0f / 4294967296.0f;
+    den       = fabsf(den) < eps ? copysignf(eps, den) : den;
+    sx        = num / den;
+    float Ru  = 1 - 2 * randv;
+    float u2  = fabsf(Ru);
+    float z   = (u2 * (u2 * (u2 * 0.27385f - 0.73369f) + 0.46341f))
+              / (u2 * (u2 * (u2 * 0.093073f + 0.309420f) - 1.0f) + 0.597999f);
+    sy = copysignf(1.0f, Ru) * z * sqrtf(1.0f + sx * sx);
+}
+OSLD void beckmann_sample_slope(float cos_theta, float randu, float randv, float& sx, float& sy)
+{
+    const float SQRT_PI_INV = 1 / sqrtf((float)OSLD_PI);
+    float ct                = cos_theta < 1e-6f ? 1e-6f : cos_theta;
+    float tanThetaI         = sqrtf(1 - ct * ct) / ct;
+    float cotThetaI         = 1 / tanThetaI;
+    float c       = fast_erf(cotThetaI);
+    float K       = tanThetaI * SQRT_PI_INV;
+    float yApprox = randu * (1.0f + c + K * (1 - c * c));
+    float yExact  = randu * (1.0f + c + K * fast_exp(-cotThetaI * cotThetaI));
+    float b = K > 0 ? (0.5f - sqrtf(K * (K - yApprox + 1.0f) + 0.25f)) / K : yApprox - 1.0f;
+    float invErf = fast_ierf(b);
+    float value  = 1.0f + b + K * fast_exp(-invErf * invErf) - yExact;
+    if (fabsf(value) > 1e-6f) {
+        b -= value / (1 - invErf * tanThetaI);
+        invErf = fast_ierf(b);
+        value  = 1.0f + b + K * fast_exp(-invErf * invErf) - yExact;
+        b -= value / (1 - invErf * tanThetaI);
+        sx = fast_ierf(b);
+    } else {
+        sx = invErf;
+    }
+    sy = fast_ierf(2.0f * randv - 1.0f);
+}
+
+// ---- Microfacet ------------------------------------------------------------------------
+OSLD float mf_lambda(const Lobe& l, V3 w)
+{
+    float cosTheta2  = sqr_(w.z);
+    float cosPhi2st2 = sqr_(w.x * l.ax);
+    float sinPhi2st2 = sqr_(w.y * l.ay);
+    return dist_Lambda(l.ggx, cosTheta2 / (cosPhi2st2 + sinPhi2st2));
+}
+OSLD float mf_D(const Lobe& l, V3 Hr)
+{
+    float cosThetaM = Hr.z;
+    if (cosThetaM > 0) {
+        float cosPhi2st2 = sqr_(Hr.x / l.ax);
+        float sinPhi2st2 = sqr_(Hr.y / l.ay);
+        float cosThetaM2 = sqr_(cosThetaM);
+        float cosThetaM4 = sqr_(cosThetaM2);
+        float tanThetaM2 = (cosPhi2st2 + sinPhi2st2) / cosThetaM2;
+        return dist_F(l.ggx, tanThetaM2) / (l.ax * l.ay * cosThetaM4);
+    }
+    return 0;
+}
+OSLD V3 mf_sample_micronormal(const Lobe& l, V3 wo, float randu, float randv)
+{
+    V3 swo = wo;
+    swo.x *= l.ax;
+    swo.y *= l.ay;
+    swo             = vnormalized(swo);
+    float cos_theta = fmaxf(swo.z, 0.0f);
+    float cos_phi = 1, sin_phi = 0;
+    if (cos_theta < 0.99999f) {
+        float invnorm = 1 / sqrtf(sqr_(swo.x) + sqr_(swo.y));
+        cos_phi       = swo.x * invnorm;
+        sin_phi       = swo.y * invnorm;
+    }
+    float slx, sly;
+    if (l.ggx)
+        ggx_sample_slope(cos_theta, randu, randv, slx, sly);
+    else
+        beckmann_sample_slope(cos_theta, randu, randv, slx, sly);
+    float sx = cos_phi * slx - sin_phi * sly, sy = sin_phi * slx + cos_phi * sly;
+    sx *= l.ax;
+    sy *= l.ay;
+    float mlen = sqrtf(sx * sx + sy * sy + 1);
+    return mkv(fabsf(sx) < mlen ? -sx / mlen : 1.0f, fabsf(sy) < mlen ? -sy / mlen : 1.0f, 1.0f / mlen);
+}
+OSLD V3 mf_albedo(const Lobe& l, V3 wo)
+{
+    if (l.refract == 2)
+        return mkv(1.0f);
+    float fr = fresnel_dielectric(dot3(l.N, wo), l.eta);
+    return mkv(l.refract ? 1 - fr : fr);
+}
+OSLD BSample mf_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    const int Refract = l.refract;
+    const float rough = fmaxf(l.ax, l.ay);
+    const V3 wo_l = frame_tolocal(l, wo), wi_l = frame_tolocal(l, wi);
+    if (Refract == 0 || Refract == 2) {
+        if (wo_l.z > 0 && wi_l.z > 0) {
+            const V3 m           = vnormalized(wi_l + wo_l);
+            const float D        = mf_D(l, m);
+            const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+            const float G2 = 1 / (Lambda_o + Lambda_i + 1), G1 = 1 / (Lambda_o + 1);
+            const float Fr = fresnel_dielectric(dot3(m, wo_l), l.eta);
+            float pdf      = (G1 * D * 0.25f) / wo_l.z;
+            float out      = G2 / G1;
+            if (Refract == 2) {
+                pdf *= Fr;
+                return bs_make(wi, mkv(out), pdf, rough);
+            }
+            return bs_make(wi, mkv(out * Fr), pdf, rough);
+        }
+    }
+    if (Refract == 1 || Refract == 2) {
+        if (wi_l.z < 0 && wo_l.z > 0.0f) {
+            V3 ht = -(l.eta * wi_l + wo_l);
+            if (l.eta < 1.0f)
+                ht = -ht;
+            V3 Ht             = vnormalized(ht);
+            const float cosHO = dot3(Ht, wo_l);
+            const float Ft    = 1.0f - fresnel_dielectric(cosHO, l.eta);
+            if (Ft > 0) {
+                const float cosHI = dot3(Ht, wi_l);
+                if (Ht.z <= 0.0f)
+                    return bs_null();
+                const float Dt       = mf_D(l, Ht);
+                const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+                const float G2 = 1 / (Lambda_o + Lambda_i + 1), G1 = 1 / (Lambda_o + 1);
+                float invHt2 = 1 / dot3(ht, ht);
+                float pdf    = (fabsf(cosHI * cosHO) * (l.eta * l.eta) * (G1 * Dt) * invHt2) / wo_l.z;
+                float out    = G2 / G1;
+                if (Refract == 2) {
+                    pdf *= Ft;
+                    return bs_make(wi, mkv(out), pdf, rough);
+                }
+                return bs_make(wi, mkv(out * Ft), pdf, rough);
+            }
+        }
+    }
+    return bs_null();
+}
+OSLD BSample mf_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
+{
+    const int Refract = l.refract;
+    const float rough = fmaxf(l.ax, l.ay);
+    const V3 wo_l     = frame_tolocal(l, wo);
+    const float cosNO = wo_l.z;
+    if (!(cosNO > 0))
+        return bs_null();
+    const V3 m        = mf_sample_micronormal(l, wo_l, rx, ry);
+    const float cosMO = dot3(m, wo_l);
+    const float F     = fresnel_dielectric(cosMO, l.eta);
+    if (Refract == 0 || (Refract == 2 && rz < F)) {
+        const V3 wi_l        = (2.0f * cosMO) * m - wo_l;
+        const float D        = mf_D(l, m);
+        const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+        const float G2 = 1 / (Lambda_o + Lambda_i + 1), G1 = 1 / (Lambda_o + 1);
+        V3 wi     = frame_toworld(l, wi_l);
+        float pdf = (G1 * D * 0.25f) / cosNO;
+        float out = G2 / G1;
+        if (Refract == 2) {
+            pdf *= F;
+            return bs_make(wi, mkv(out), pdf, rough);
+        }
+        return bs_make(wi, mkv(F * out), pdf, rough);
+    }
+    const V3 M = frame_toworld(l, m);
+    V3 wi;
+    float Ft             = fresnel_refraction(-wo, M, l.eta, wi);
+    const V3 wi_l        = frame_tolocal(l, wi);
+    const float cosHO    = dot3(m, wo_l), cosHI = dot3(m, wi_l);
+    const float D        = mf_D(l, m);
+    const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+    const float G2 = 1 / (Lambda_o + Lambda_i + 1), G1 = 1 / (Lambda_o + 1);
+    const V3 ht        = -(l.eta * wi_l + wo_l);
+    const float invHt2 = 1.0f / dot3(ht, ht);
+    float pdf = (fabsf(cosHI * cosHO) * (l.eta * l.eta) * (G1 * D) * invHt2) / fabsf(wo_l.z);
+    float out = G2 / G1;
+    if (Refract == 2) {
+        pdf *= Ft;
+        return bs_make(wi, mkv(out), pdf, rough);
+    }
+    return bs_make(wi, mkv(Ft * out), pdf, rough);
+}
+
+// ---- Phong (exponent kept in l.ax) -------------------------------------------------------
+OSLD BSample phong_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    const float exponent = l.ax;
+    float cosNI = dot3(l.N, wi), cosNO = dot3(l.N, wo);
+    if (cosNI > 0 && cosNO > 0) {
+        V3 R        = (2 * cosNO) * l.N - wo;
+        float cosRI = dot3(R, wi);
+        if (cosRI > 0) {
+            const float pdf = (exponent + 1) * (float)(0.31830988618379067154 / 2) * fast_safe_pow(cosRI, exponent);
+            return bs_make(wi, mkv(cosNI * (exponent + 2) / (exponent + 1)), pdf, 1 / (1 + exponent));
+        }
+    }
+    return bs_null();
+}
+OSLD BSample phong_sample(const Lobe& l, V3 wo, float rx, float ry)
+{
+    const float exponent = l.ax;
+    float cosNO          = dot3(l.N, wo);
+    if (cosNO > 0) {
+        V3 R      = (2 * cosNO) * l.N - wo;
+        float phi = 2 * (float)OSLD_PI * rx;
+        float sp, cp;
+        fast_sincos(phi, &sp, &cp);
+        float cosTheta  = fast_safe_pow(ry, 1 / (exponent + 1));
+        float sinTheta2 = 1 - cosTheta * cosTheta;
+        float sinTheta  = sinTheta2 > 0 ? sqrtf(sinTheta2) : 0;
+        V3 wi           = frame_get(frame_from_normal(R), cp * sinTheta, sp * sinTheta, cosTheta);
+        return phong_eval(l, wo, wi);
+    }
+    return bs_null();
+}
+
+// ---- Ward ------------------------------------------------------------------------------
+OSLD BSample ward_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    float cosNO = dot3(l.N, wo), cosNI = dot3(l.N, wi);
+    if (cosNI > 0 && cosNO > 0) {
+        V3 H       = vnormalized(wi + wo);
+        float dotx = dot3(H, l.fu) / l.ax, doty = dot3(H, l.fv) / l.ay, dotn = dot3(H, l.N);
+        float oh   = dot3(H, wi);
+        float e    = fast_exp(-(dotx * dotx + doty * doty) / (dotn * dotn));
+        float c    = (float)(4 * OSLD_PI) * l.ax * l.ay;
+        float k    = oh * dotn * dotn * dotn;
+        float pdf  = e / (c * k);
+        return bs_make(wi, mkv(k * sqrtf(cosNI / cosNO)), pdf, fmaxf(l.ax, l.ay));
+    }
+    return bs_null();
+}
+OSLD BSample ward_sample(const Lobe& l, V3 wo, float rx, float ry)
+{
+    float cosNO = dot3(l.N, wo);
+    if (cosNO > 0) {
+        float phi = 2 * (float)OSLD_PI * rx;
+        float sp, cp;
+        fast_sincos(phi, &sp, &cp);
+        float cosPhi = l.ax * cp, sinPhi = l.ay * sp;
+        float k      = 1 / sqrtf(cosPhi * cosPhi + sinPhi * sinPhi);
+        cosPhi *= k;
+        sinPhi *= k;
+        float thetaDenom = (cosPhi * cosPhi) / (l.ax * l.ax) + (sinPhi * sinPhi) / (l.ay * l.ay);
+        float tanTheta2  = -fast_log(1 - ry) / thetaDenom;
+        float cosTheta   = 1 / sqrtf(1 + tanTheta2);
+        float sinTheta   = cosTheta * sqrtf(tanTheta2);
+        V3 h             = mkv(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+        float dotx = h.x / l.ax, doty = h.y / l.ay, dotn = h.z;
+        h           = frame_toworld(l, h);
+        float oh    = dot3(h, wo);
+        V3 wi       = 2 * oh * h - wo;
+        float cosNI = dot3(l.N, wi);
+        if (cosNI > 0) {
+            float e   = fast_exp(-(dotx * dotx + doty * doty) / (dotn * dotn));
+            float c   = (float)(4 * OSLD_PI) * l.ax * l.ay;
+            float kk  = oh * dotn * dotn * dotn;
+            float pdf = e / (c * kk);
+            return bs_make(wi, mkv(kk * sqrtf(cosNI / cosNO)), pdf, fmaxf(l.ax, l.ay));
+        }
+    }
+    return bs_null();
+}
+
+}  // namespace osld

@@ -50,14 +50,25 @@ struct RenderScene {
     int background_shader, background_resolution;
 };
 
-enum PathF { PF_OX, PF_OY, PF_OZ, PF_DX, PF_DY, PF_DZ, PF_RADIUS, PF_SPREAD, PF_ROUGH, PF_WX, PF_WY, PF_WZ,
-             PF_LX, PF_LY, PF_LZ, PF_BSDFPDF, PF_HT, PF_HU, PF_HV, PF_COUNT };
-enum PathI { PI_RAYTYPE, PI_PREVID, PI_BOUNCE, PI_SEED, PI_INDEX, PI_HITID, PI_COUNT };
+// Path state: one 128-byte record (8 x float4) per path slot.  After the live
+// queue has been sorted by material the slots a warp touches are scattered, so
+// the state is laid out per path (every 32-byte sector fetched is fully used
+// and moved with 16-byte LDG/STG) rather than as per-field planes.
+//   q0 = origin.xyz, radius      q1 = direction.xyz, spread
+//   q2 = path_weight.rgb, bsdf_pdf   q3 = path_radiance.rgb, roughness
+//   q4 = hit t,u,v, hit id       q5 = raytype, prev_id, bounce, sampler seed
+//   q6 = sampler index, -, -, -  q7 = unused
+#define OSLD_PATH_QUADS 8
+OSLD float4 mkf4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+OSLD V3 xyz(float4 q) { return mkv(q.x, q.y, q.z); }
+OSLD float4 mki4(int a, int b, int c, int d)
+{
+    return make_float4(__int_as_float(a), __int_as_float(b), __int_as_float(c), __int_as_float(d));
+}
 
 struct RenderLaunch {
     RenderScene S;
-    float* pf[PF_COUNT];  // float planes, nslots each
-    int* pi[PI_COUNT];    // int planes
+    float4* rec;          // nslots x OSLD_PATH_QUADS
     int* queue_in;        // live path slots
     int* queue_out;
     int* counters;        // [0] in count, [1] out count, [2..] sort scratch
@@ -278,14 +289,30 @@ OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
     return s;
 }
 #define OSLD_INF __int_as_float(0x7f800000)
-enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT };
+enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
+       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET };
 struct Lobe {
     int type;
     V3 N;
     float eta;
+#ifdef OSLD_GLOSSY_LOBES
+    // phong: ax = exponent.  ward / microfacet: tangent frame (fu, fv, N) and roughnesses.
+    V3 fu, fv;
+    float ax, ay;
+    int refract, ggx;
+#endif
 };
+}  // namespace osld
+#ifdef OSLD_GLOSSY_LOBES
+#include "osl_b200_lobes.cuh"
+#endif
+namespace osld {
 OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
 {
+#ifdef OSLD_GLOSSY_LOBES
+    if (l.type == LOBE_MICROFACET)
+        return mf_albedo(l, wo);
+#endif
     if (l.type == LOBE_REFLECTION) {
         float cosNO = dot3(l.N, wo);
         return cosNO > 0 ? mkv(fresnel_dielectric(cosNO, l.eta)) : mkv(1.0f);
@@ -300,6 +327,14 @@ OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
         const float pdf = fmaxf(dot3(l.N, wi), 0.0f) * (float)(1.0 / OSLD_PI);
         return bs_make(wi, mkv(1.0f), pdf, 1.0f);
     }
+#ifdef OSLD_GLOSSY_LOBES
+    if (l.type == LOBE_PHONG)
+        return phong_eval(l, wo, wi);
+    if (l.type == LOBE_WARD)
+        return ward_eval(l, wo, wi);
+    if (l.type == LOBE_MICROFACET)
+        return mf_eval(l, wo, wi);
+#endif
     return bs_null();
 }
 OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
@@ -325,6 +360,11 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
         float Ft = fresnel_refraction(-wo, l.N, l.eta, wi);
         return bs_make(wi, mkv(Ft), OSLD_INF, 0.0f);
     }
+#ifdef OSLD_GLOSSY_LOBES
+    case LOBE_PHONG: return phong_sample(l, wo, rx, ry);
+    case LOBE_WARD: return ward_sample(l, wo, rx, ry);
+    case LOBE_MICROFACET: return mf_sample(l, wo, rx, ry, rz);
+#endif
     default: return bs_make(-wo, mkv(1.0f), OSLD_INF, 0.0f);
     }
 }
@@ -420,6 +460,32 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                 case REFRACTION_ID: l.type = LOBE_REFRACTION; l.eta = q[3]; break;
                 case TRANSPARENT_ID:
                 case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
+#ifdef OSLD_GLOSSY_LOBES
+                case PHONG_ID:
+                    l.type = LOBE_PHONG;
+                    l.ax   = q[3];
+                    break;
+                case WARD_ID:
+                    l.type = LOBE_WARD;
+                    l.ax   = q[6];
+                    l.ay   = q[7];
+                    lobe_set_frame(l, mkv(q[3], q[4], q[5]));
+                    break;
+                case MICROFACET_ID: {
+                    // params: dist code, N, U, xalpha, yalpha, eta, refract (shading.cpp:222-231)
+                    const int dist = __float_as_int(q[0]);
+                    l.type    = LOBE_MICROFACET;
+                    l.N       = mkv(q[1], q[2], q[3]);
+                    l.ax      = q[7];
+                    l.ay      = q[8];
+                    l.eta     = q[9];
+                    l.refract = __float_as_int(q[10]);
+                    l.ggx     = dist == 1;
+                    lobe_set_frame(l, mkv(q[4], q[5], q[6]));
+                    known = (dist >= 1 && dist <= 3) && l.refract >= 0 && l.refract <= 2;
+                    break;
+                }
+#endif
                 default: known = false; break;
                 }
                 if (known && B.num < OSLD_MAX_LOBES) {
@@ -738,18 +804,14 @@ extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_const
         j.y *= 2;
         j.y = j.y < 1 ? sqrtf(j.y) - 1 : 1 - sqrtf(2 - j.y);
         Ray r = camera_ray(S, (float)x + 0.5f + j.x, (float)y + 0.5f + j.y);
-        L.pf[PF_OX][slot] = r.origin.x; L.pf[PF_OY][slot] = r.origin.y; L.pf[PF_OZ][slot] = r.origin.z;
-        L.pf[PF_DX][slot] = r.direction.x; L.pf[PF_DY][slot] = r.direction.y; L.pf[PF_DZ][slot] = r.direction.z;
-        L.pf[PF_RADIUS][slot] = r.radius; L.pf[PF_SPREAD][slot] = r.spread; L.pf[PF_ROUGH][slot] = r.roughness;
-        L.pf[PF_WX][slot] = 1.0f; L.pf[PF_WY][slot] = 1.0f; L.pf[PF_WZ][slot] = 1.0f;
-        L.pf[PF_LX][slot] = 0.0f; L.pf[PF_LY][slot] = 0.0f; L.pf[PF_LZ][slot] = 0.0f;
-        L.pf[PF_BSDFPDF][slot] = OSLD_INF;
-        L.pi[PI_RAYTYPE][slot] = r.raytype;
-        L.pi[PI_PREVID][slot]  = -1;
-        L.pi[PI_BOUNCE][slot]  = 0;
-        L.pi[PI_SEED][slot]    = (int)sampler.seed;
-        L.pi[PI_INDEX][slot]   = (int)sampler.index;
-        L.queue_in[slot]       = slot;
+        float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+        rec[0] = mkf4(r.origin, r.radius);
+        rec[1] = mkf4(r.direction, r.spread);
+        rec[2] = make_float4(1.0f, 1.0f, 1.0f, OSLD_INF);
+        rec[3] = make_float4(0.0f, 0.0f, 0.0f, r.roughness);
+        rec[5] = mki4(r.raytype, -1, 0, (int)sampler.seed);
+        rec[6] = mki4((int)sampler.index, 0, 0, 0);
+        L.queue_in[slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         L.counters[0] = L.nslots;
@@ -762,14 +824,11 @@ extern "C" __global__ void __launch_bounds__(256) rt_intersect(const __grid_cons
 {
     const int n = L.counters[0];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        int slot = L.queue_in[q];
-        V3 org   = mkv(L.pf[PF_OX][slot], L.pf[PF_OY][slot], L.pf[PF_OZ][slot]);
-        V3 dir   = mkv(L.pf[PF_DX][slot], L.pf[PF_DY][slot], L.pf[PF_DZ][slot]);
-        Hit h    = scene_intersect(L.S, org, dir, OSLD_INF, (unsigned)L.pi[PI_PREVID][slot], ~0u);
-        L.pf[PF_HT][slot]    = h.t;
-        L.pf[PF_HU][slot]    = h.u;
-        L.pf[PF_HV][slot]    = h.v;
-        L.pi[PI_HITID][slot] = (int)h.id;
+        int slot    = L.queue_in[q];
+        float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+        float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
+        Hit h     = scene_intersect(L.S, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y), ~0u);
+        rec[4]    = make_float4(h.t, h.u, h.v, __int_as_float((int)h.id));
         if (L.sort_keys)
             L.sort_keys[q] = (h.t == OSLD_INF) ? 0 : 1 + __ldg(L.S.shaderids + h.id);
     }
@@ -823,20 +882,24 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
         bool alive = false;
         int slot   = 0;
         if (q < n) {
-            slot = L.queue_in[q];
+            slot        = L.queue_in[q];
+            float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+            const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4], q5 = rec[5], q6 = rec[6];
             Ray r;
-            r.origin    = mkv(L.pf[PF_OX][slot], L.pf[PF_OY][slot], L.pf[PF_OZ][slot]);
-            r.direction = mkv(L.pf[PF_DX][slot], L.pf[PF_DY][slot], L.pf[PF_DZ][slot]);
-            r.radius    = L.pf[PF_RADIUS][slot];
-            r.spread    = L.pf[PF_SPREAD][slot];
-            r.roughness = L.pf[PF_ROUGH][slot];
-            r.raytype   = L.pi[PI_RAYTYPE][slot];
-            const float ht = L.pf[PF_HT][slot], hu = L.pf[PF_HU][slot], hv = L.pf[PF_HV][slot];
-            const int hid  = L.pi[PI_HITID][slot];
-            const int b    = L.pi[PI_BOUNCE][slot];
-            V3 path_weight   = mkv(L.pf[PF_WX][slot], L.pf[PF_WY][slot], L.pf[PF_WZ][slot]);
-            V3 path_radiance = mkv(L.pf[PF_LX][slot], L.pf[PF_LY][slot], L.pf[PF_LZ][slot]);
-            float bsdf_pdf   = L.pf[PF_BSDFPDF][slot];
+            r.origin    = xyz(q0);
+            r.direction = xyz(q1);
+            r.radius    = q0.w;
+            r.spread    = q1.w;
+            r.roughness = q3.w;
+            r.raytype   = __float_as_int(q5.x);
+            const float ht = q4.x, hu = q4.y, hv = q4.z;
+            const int hid  = __float_as_int(q4.w);
+            const int b    = __float_as_int(q5.z);
+            V3 path_weight   = xyz(q2);
+            V3 path_radiance = xyz(q3);
+            float bsdf_pdf   = q2.w;
+            float out_rough  = q3.w;
+            u32 seed_now     = (u32)__float_as_int(q5.w);
             do {
                 if (ht == OSLD_INF)
                     break;  // miss (no background in these scenes)
@@ -881,10 +944,10 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
                 const V3 wo = -sg.I;
                 bsdf_prepare(bsdf, wo, path_weight, b >= S.rr_depth);
                 Sampler sampler;
-                sampler.seed  = (u32)L.pi[PI_SEED][slot];
-                sampler.index = (u32)L.pi[PI_INDEX][slot];
+                sampler.seed  = seed_now;
+                sampler.index = (u32)__float_as_int(q6.x);
                 V3 s          = sampler.get();
-                L.pi[PI_SEED][slot] = (int)sampler.seed;
+                seed_now      = sampler.seed;
                 const float xi = s.x, yi = s.y, zi = s.z;
                 if (nlights > 0) {
                     const float light_pick_pdf = 1.0f / nlights;
@@ -928,21 +991,14 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
                 if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
                     break;
                 // continue the path
-                L.pf[PF_OX][slot] = sg.P.x; L.pf[PF_OY][slot] = sg.P.y; L.pf[PF_OZ][slot] = sg.P.z;
-                L.pf[PF_DX][slot] = p.wi.x; L.pf[PF_DY][slot] = p.wi.y; L.pf[PF_DZ][slot] = p.wi.z;
-                L.pf[PF_RADIUS][slot] = radius;
-                L.pf[PF_SPREAD][slot] = fmaxf(r.spread, p.roughness);
-                L.pf[PF_ROUGH][slot]  = p.roughness;
-                L.pf[PF_WX][slot] = path_weight.x; L.pf[PF_WY][slot] = path_weight.y; L.pf[PF_WZ][slot] = path_weight.z;
-                L.pf[PF_BSDFPDF][slot] = bsdf_pdf;
-                L.pi[PI_RAYTYPE][slot] = RAY_DIFFUSE;
-                L.pi[PI_PREVID][slot]  = hid;
-                L.pi[PI_BOUNCE][slot]  = b + 1;
-                alive = true;
+                rec[0]    = mkf4(sg.P, radius);
+                rec[1]    = mkf4(p.wi, fmaxf(r.spread, p.roughness));
+                rec[2]    = mkf4(path_weight, bsdf_pdf);
+                rec[5]    = mki4(RAY_DIFFUSE, hid, b + 1, (int)seed_now);
+                out_rough = p.roughness;
+                alive     = true;
             } while (false);
-            L.pf[PF_LX][slot] = path_radiance.x;
-            L.pf[PF_LY][slot] = path_radiance.y;
-            L.pf[PF_LZ][slot] = path_radiance.z;
+            rec[3] = mkf4(path_radiance, out_rough);
         }
         queue_push(L.queue_out, L.counters + 1, slot, alive);
     }
@@ -965,7 +1021,7 @@ extern "C" __global__ void __launch_bounds__(256) rt_resolve(const __grid_consta
         V3 result = L.s0 == 0 ? mkv(0.0f) : mkv(L.accum[3 * pix], L.accum[3 * pix + 1], L.accum[3 * pix + 2]);
         for (int sb = 0; sb < L.nsamples; ++sb) {
             int slot = sb * L.npix + pix;
-            V3 r     = mkv(L.pf[PF_LX][slot], L.pf[PF_LY][slot], L.pf[PF_LZ][slot]);
+            V3 r     = xyz(L.rec[(size_t)slot * OSLD_PATH_QUADS + 3]);
             float t  = 1.0f / (float)(L.s0 + sb + 1);
             result   = result * (1.0f - t) + r * t;
         }

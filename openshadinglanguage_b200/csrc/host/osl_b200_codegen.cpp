@@ -793,6 +793,7 @@ Gen::emit_op(const Opcode& op)
             { "ward", 4, "WARD_ID" },               { "reflection", 1, "REFLECTION_ID" },
             { "reflection", 2, "FRESNEL_REFLECTION_ID" }, { "refraction", 2, "REFRACTION_ID" },
             { "transparent", 0, "TRANSPARENT_ID" }, { "transparent_bsdf", 0, "MX_TRANSPARENT_ID" },
+            { "microfacet", 7, "MICROFACET_ID" },
         };
         const char* idname = nullptr;
         for (const Reg& r : regs)
@@ -801,11 +802,11 @@ Gen::emit_op(const Opcode& op)
         if (!idname)
             unsupported("closure '" + cname + "' with " + std::to_string(pos.size()) + " parameters is not registered");
         int nwords = 0;
-        for (int a : pos) {
-            if (S(a).type.base == Base::String)
-                unsupported("string closure parameters");
+        for (int a : pos)
             nwords += S(a).type.ncomp();
-        }
+        const std::string cn = cname;
+        if (cn == "phong" || cn == "ward" || cn == "microfacet")
+            g.uses_glossy_lobes = true;
         std::string wexpr = "mkv(1.0f)";
         if (weight >= 0) {
             w("V3 w_; assign(w_, " + R(weight) + ");");
@@ -819,6 +820,13 @@ Gen::emit_op(const Opcode& op)
             std::string e = R(a);
             if (S(a).has_derivs)
                 e = "nd(" + e + ")";
+            if (S(a).type.base == Base::String) {
+                // the only string parameter on this path is microfacet's distribution
+                // name; store the code process_closure switches on (shading.cpp:1518-1534)
+                auto id = [&](const char* s) { return std::to_string(g.intern(s)); };
+                e = "((" + e + ") == " + id("ggx") + " ? 1 : (" + e + ") == " + id("beckmann") + " ? 2 : (" + e
+                    + ") == " + id("default") + " ? 3 : 0)";
+            }
             w("    putp(sg.pool->w + c_ + " + std::to_string(4 + off) + ", " + e + ");");
             off += S(a).type.ncomp();
         }
@@ -1221,6 +1229,12 @@ generate_cuda_render(std::vector<Group*>& groups)
     for (size_t k = 0; k < groups.size(); ++k)
         out << "    case " << k << ": mat" << k << "::entry(sg); break;\n";
     out << "    default: break;\n    }\n}\n";
+    // the integrator is specialised to the lobes the scene's materials can create
+    bool glossy = false;
+    for (Group* gp : groups)
+        glossy |= gp->uses_glossy_lobes;
+    if (glossy)
+        out << "#define OSLD_GLOSSY_LOBES 1\n";
     out << "#include \"osl_b200_render.cuh\"\n";
     return out.str();
 }

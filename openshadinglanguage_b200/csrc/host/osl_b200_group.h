@@ -127,6 +127,7 @@ struct Group {
     std::vector<std::string> warnings;
     std::set<int> globals_read;                // b200_sg_field ids the kernel loads
     bool fma = true;                           // allow FMA contraction in generated code
+    bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
 
     int layer_index(const std::string& n) const;
     void add_layer(const std::string& oso_text, const std::string& layername,

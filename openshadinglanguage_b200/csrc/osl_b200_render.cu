@@ -45,11 +45,10 @@ struct DevScene {
     int aa, max_bounces, rr_depth, no_jitter, show_globals;
     int background_shader, background_resolution;
 };
-enum { PF_COUNT = 19, PI_COUNT = 6 };
+enum { PATH_QUADS = 8 };  // 8 x float4 = 128 B of state per path (OSLD_PATH_QUADS)
 struct DevLaunch {
     DevScene S;
-    float* pf[PF_COUNT];
-    int* pi[PI_COUNT];
+    void* rec;
     int* queue_in;
     int* queue_out;
     int* counters;
@@ -80,8 +79,7 @@ struct b200_render {
         int sms = 148;
         // path state
         long long nslots_cap = 0;
-        float* pf            = nullptr;
-        int* pi              = nullptr;
+        void* rec            = nullptr;  // nslots x 128 B path records
         int* queues          = nullptr;  // 3 x nslots
         int* sort_keys       = nullptr;
         int* counters        = nullptr;
@@ -338,14 +336,13 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
             for (auto& a : d.allocs)
                 if (a == p) a = nullptr;
         };
-        drop(d.pf); drop(d.pi); drop(d.queues); drop(d.sort_keys);
-        bool ok = cudaMalloc(&d.pf, sizeof(float) * PF_COUNT * nslots) == cudaSuccess
-                  && cudaMalloc(&d.pi, sizeof(int) * PI_COUNT * nslots) == cudaSuccess
+        drop(d.rec); drop(d.queues); drop(d.sort_keys);
+        bool ok = cudaMalloc(&d.rec, (size_t)16 * PATH_QUADS * nslots) == cudaSuccess
                   && cudaMalloc(&d.queues, sizeof(int) * 3 * nslots) == cudaSuccess
                   && cudaMalloc(&d.sort_keys, sizeof(int) * nslots) == cudaSuccess;
         if (!ok)
             return set_error(B200_ERR_CUDA, "cudaMalloc(path state) failed");
-        d.allocs.push_back(d.pf); d.allocs.push_back(d.pi); d.allocs.push_back(d.queues); d.allocs.push_back(d.sort_keys);
+        d.allocs.push_back(d.rec); d.allocs.push_back(d.queues); d.allocs.push_back(d.sort_keys);
         d.nslots_cap = nslots;
     }
     if (!d.counters) {
@@ -368,10 +365,7 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
     DevLaunch L;
     memset(&L, 0, sizeof L);
     L.S = d.S;
-    for (int k = 0; k < PF_COUNT; ++k)
-        L.pf[k] = d.pf + (size_t)k * nslots;
-    for (int k = 0; k < PI_COUNT; ++k)
-        L.pi[k] = d.pi + (size_t)k * nslots;
+    L.rec = d.rec;
     int* qbuf[3]  = { d.queues, d.queues + nslots, d.queues + 2 * nslots };
     L.counters    = d.counters;
     L.sort_keys   = r->sort ? d.sort_keys : nullptr;

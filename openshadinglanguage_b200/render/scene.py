@@ -67,6 +67,7 @@ class Scene:
         self.fov = 90.0
         self.background_shader = -1
         self.background_resolution = 0
+        self.options = {}         # <Option name="int N"/> (max_bounces, rr_depth, ...)
 
     # -- geometry (scene.cpp) -------------------------------------------------
     def add_sphere(self, c, r, shader, resolution=64):
@@ -323,7 +324,16 @@ def load_scene(xmlfile):
     named = {}
     for node in root:
         a = node.attrib
-        if node.tag == "Camera":
+        if node.tag == "Option":
+            # simpleraytracer.cpp:302-309: only "int N" values are honoured
+            for k, v in a.items():
+                v = v.strip()
+                if v.startswith("int "):
+                    try:
+                        sc.options[k] = int(v[4:].split()[0])
+                    except (ValueError, IndexError):
+                        pass
+        elif node.tag == "Camera":
             if "eye" in a:
                 sc.eye = _vec(a["eye"])
             if "dir" in a:

@@ -207,9 +207,13 @@ class RenderScene(ctypes.Structure):
                 ("background_shader", ctypes.c_int), ("background_resolution", ctypes.c_int)]
 
 
-def fill_render_scene(RS, scene, arrays, xres, yres, aa, max_bounces=1000000, rr_depth=5,
+def fill_render_scene(RS, scene, arrays, xres, yres, aa, max_bounces=None, rr_depth=None,
                       no_jitter=False, show_globals=0):
     """Fill a RenderScene-shaped ctypes struct (oracle and product share the layout)."""
+    if max_bounces is None:
+        max_bounces = scene.options.get("max_bounces", 1000000)
+    if rr_depth is None:
+        rr_depth = scene.options.get("rr_depth", 5)
     keep = []
     rs = RS()
 

@@ -105,5 +105,21 @@ inline const Clos* clos_add(ClosurePool* pool, const Clos* a, const Clos* b)
 inline void putp(float* p, float v) { *p = v; }
 inline void putp(float* p, int v) { std::memcpy(p, &v, 4); }
 inline void putp(float* p, const V3& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+// String closure params (only microfacet's `dist` on this path) are stored as a
+// small code: the reference compares ustringhash against uh_ggx / uh_beckmann /
+// uh_default (shading.cpp:1518-1534); anything else adds no lobe.
+inline int closure_string_code(const char* s)
+{
+    if (!s)
+        return 0;
+    if (!std::strcmp(s, "ggx"))
+        return 1;
+    if (!std::strcmp(s, "beckmann"))
+        return 2;
+    if (!std::strcmp(s, "default"))
+        return 3;
+    return 0;
+}
+inline void putp(float* p, const char* s) { putp(p, closure_string_code(s)); }
 
 }  // namespace oslo

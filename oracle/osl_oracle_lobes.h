@@ -1,0 +1,326 @@
+// osl_oracle_lobes.h — CPU ORACLE (test infrastructure, NOT product code).
+//
+// Restatement of testrender's native glossy lobes:
+//   Phong                         src/testrender/shading.cpp:323-364
+//   Ward                          src/testrender/shading.cpp:366-448
+//   GGXDist / BeckmannDist        src/testrender/shading.cpp:472-560
+//   Microfacet<Dist, 0|1|2>       src/testrender/shading.cpp:563-799
+// Included from osl_oracle_render.h right after `struct Lobe`.
+#pragma once
+
+namespace oslo {
+
+namespace lobes {
+
+inline float SQR(float x) { return x * x; }
+
+struct V2f {
+    float x, y;
+};
+
+// ---- distributions ---------------------------------------------------------------
+inline float dist_F(bool ggx, float tan_m2)
+{
+    if (ggx)
+        return 1 / (float(M_PI) * (1 + tan_m2) * (1 + tan_m2));
+    return float(1 / M_PI) * fast_exp(-tan_m2);
+}
+inline float dist_Lambda(bool ggx, float a2)
+{
+    if (ggx)
+        return 0.5f * (-1.0f + std::sqrt(1.0f + 1.0f / a2));
+    const float a = std::sqrt(a2);
+    return a < 1.6f ? (1.0f - 1.259f * a + 0.396f * a2) / (3.535f * a + 2.181f * a2) : 0.0f;
+}
+inline V2f ggx_sample_slope(float cos_theta, float randu, float randv)
+{
+    V2f slope;
+    float c   = cos_theta < 1e-6f ? 1e-6f : cos_theta;
+    float Q   = (1 + c) * randu - c;
+    float num = c * std::sqrt((1 - c) * (1 + c)) - Q * std::sqrt((1 - Q) * (1 + Q));
+    float den = (Q - c) * (Q + c);
+    float eps = 1.0f / 4294967296.0f;
+    den       = std::fabs(den) < eps ? std::copysign(eps, den) : den;
+    slope.x   = num / den;
+    float Ru  = 1 - 2 * randv;
+    float u2  = std::fabs(Ru);
+    float z   = (u2 * (u2 * (u2 * 0.27385f - 0.73369f) + 0.46341f))
+              / (u2 * (u2 * (u2 * 0.093073f + 0.309420f) - 1.0f) + 0.597999f);
+    slope.y = std::copysign(1.0f, Ru) * z * std::sqrt(1.0f + slope.x * slope.x);
+    return slope;
+}
+inline V2f beckmann_sample_slope(float cos_theta, float randu, float randv)
+{
+    const float SQRT_PI_INV = 1 / std::sqrt(float(M_PI));
+    float ct                = cos_theta < 1e-6f ? 1e-6f : cos_theta;
+    float tanThetaI         = std::sqrt(1 - ct * ct) / ct;
+    float cotThetaI         = 1 / tanThetaI;
+    float c       = fast_erf(cotThetaI);
+    float K       = tanThetaI * SQRT_PI_INV;
+    float yApprox = randu * (1.0f + c + K * (1 - c * c));
+    float yExact  = randu * (1.0f + c + K * fast_exp(-cotThetaI * cotThetaI));
+    float b = K > 0 ? (0.5f - std::sqrt(K * (K - yApprox + 1.0f) + 0.25f)) / K : yApprox - 1.0f;
+    float invErf = fast_ierf(b);
+    float value  = 1.0f + b + K * fast_exp(-invErf * invErf) - yExact;
+    V2f slope;
+    if (std::fabs(value) > 1e-6f) {
+        b -= value / (1 - invErf * tanThetaI);
+        invErf = fast_ierf(b);
+        value  = 1.0f + b + K * fast_exp(-invErf * invErf) - yExact;
+        b -= value / (1 - invErf * tanThetaI);
+        slope.x = fast_ierf(b);
+    } else {
+        slope.x = invErf;
+    }
+    slope.y = fast_ierf(2.0f * randv - 1.0f);
+    return slope;
+}
+
+// ---- Microfacet -------------------------------------------------------------------
+inline float mf_lambda(const Lobe& l, const V3& w)
+{
+    float cosTheta2  = SQR(w.z);
+    float cosPhi2st2 = SQR(w.x * l.ax);
+    float sinPhi2st2 = SQR(w.y * l.ay);
+    return dist_Lambda(l.ggx, cosTheta2 / (cosPhi2st2 + sinPhi2st2));
+}
+inline float mf_G2(float Li, float Lo) { return 1 / (Li + Lo + 1); }
+inline float mf_G1(float Lv) { return 1 / (Lv + 1); }
+inline float mf_D(const Lobe& l, const V3& Hr)
+{
+    float cosThetaM = Hr.z;
+    if (cosThetaM > 0) {
+        float cosPhi2st2 = SQR(Hr.x / l.ax);
+        float sinPhi2st2 = SQR(Hr.y / l.ay);
+        float cosThetaM2 = SQR(cosThetaM);
+        float cosThetaM4 = SQR(cosThetaM2);
+        float tanThetaM2 = (cosPhi2st2 + sinPhi2st2) / cosThetaM2;
+        return dist_F(l.ggx, tanThetaM2) / (l.ax * l.ay * cosThetaM4);
+    }
+    return 0;
+}
+inline V3 mf_sample_micronormal(const Lobe& l, const V3& wo, float randu, float randv)
+{
+    V3 swo = wo;
+    swo.x *= l.ax;
+    swo.y *= l.ay;
+    swo             = normalized(swo);
+    float cos_theta = std::max(swo.z, 0.0f);
+    float cos_phi = 1, sin_phi = 0;
+    if (cos_theta < 0.99999f) {
+        float invnorm = 1 / std::sqrt(SQR(swo.x) + SQR(swo.y));
+        cos_phi       = swo.x * invnorm;
+        sin_phi       = swo.y * invnorm;
+    }
+    V2f slope = l.ggx ? ggx_sample_slope(cos_theta, randu, randv) : beckmann_sample_slope(cos_theta, randu, randv);
+    V2f s { cos_phi * slope.x - sin_phi * slope.y, sin_phi * slope.x + cos_phi * slope.y };
+    s.x *= l.ax;
+    s.y *= l.ay;
+    float mlen = std::sqrt(s.x * s.x + s.y * s.y + 1);
+    return V3(std::fabs(s.x) < mlen ? -s.x / mlen : 1.0f, std::fabs(s.y) < mlen ? -s.y / mlen : 1.0f, 1.0f / mlen);
+}
+inline V3 mf_albedo(const Lobe& l, const V3& wo)
+{
+    if (l.refract == 2)
+        return V3(1.0f);
+    float fr = fresnel_dielectric(dot(l.N, wo), l.eta);
+    return V3(l.refract ? 1 - fr : fr);
+}
+inline BSample mf_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    const int Refract = l.refract;
+    const float rough = std::max(l.ax, l.ay);
+    const V3 wo_l = l.tf.tolocal(wo), wi_l = l.tf.tolocal(wi);
+    if (Refract == 0 || Refract == 2) {
+        if (wo_l.z > 0 && wi_l.z > 0) {
+            const V3 m           = normalized(wi_l + wo_l);
+            const float D        = mf_D(l, m);
+            const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+            const float G2 = mf_G2(Lambda_o, Lambda_i), G1 = mf_G1(Lambda_o);
+            const float Fr = fresnel_dielectric(dot(m, wo_l), l.eta);
+            float pdf      = (G1 * D * 0.25f) / wo_l.z;
+            float out      = G2 / G1;
+            if (Refract == 2) {
+                pdf *= Fr;
+                return BSample(wi, V3(out), pdf, rough);
+            }
+            return BSample(wi, V3(out * Fr), pdf, rough);
+        }
+    }
+    if (Refract == 1 || Refract == 2) {
+        if (wi_l.z < 0 && wo_l.z > 0.0f) {
+            V3 ht = -(l.eta * wi_l + wo_l);
+            if (l.eta < 1.0f)
+                ht = -ht;
+            V3 Ht             = normalized(ht);
+            const float cosHO = dot(Ht, wo_l);
+            const float Ft    = 1.0f - fresnel_dielectric(cosHO, l.eta);
+            if (Ft > 0) {
+                const float cosHI = dot(Ht, wi_l);
+                if (Ht.z <= 0.0f)
+                    return BSample();
+                const float Dt       = mf_D(l, Ht);
+                const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+                const float G2 = mf_G2(Lambda_o, Lambda_i), G1 = mf_G1(Lambda_o);
+                float invHt2 = 1 / dot(ht, ht);
+                float pdf    = (std::fabs(cosHI * cosHO) * (l.eta * l.eta) * (G1 * Dt) * invHt2) / wo_l.z;
+                float out    = G2 / G1;
+                if (Refract == 2) {
+                    pdf *= Ft;
+                    return BSample(wi, V3(out), pdf, rough);
+                }
+                return BSample(wi, V3(out * Ft), pdf, rough);
+            }
+        }
+    }
+    return BSample();
+}
+inline BSample mf_sample(const Lobe& l, const V3& wo, float rx, float ry, float rz)
+{
+    const int Refract = l.refract;
+    const float rough = std::max(l.ax, l.ay);
+    const V3 wo_l     = l.tf.tolocal(wo);
+    const float cosNO = wo_l.z;
+    if (!(cosNO > 0))
+        return BSample();
+    const V3 m        = mf_sample_micronormal(l, wo_l, rx, ry);
+    const float cosMO = dot(m, wo_l);
+    const float F     = fresnel_dielectric(cosMO, l.eta);
+    if (Refract == 0 || (Refract == 2 && rz < F)) {
+        const V3 wi_l        = (2.0f * cosMO) * m - wo_l;
+        const float D        = mf_D(l, m);
+        const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+        const float G2 = mf_G2(Lambda_o, Lambda_i), G1 = mf_G1(Lambda_o);
+        V3 wi     = l.tf.toworld(wi_l);
+        float pdf = (G1 * D * 0.25f) / cosNO;
+        float out = G2 / G1;
+        if (Refract == 2) {
+            pdf *= F;
+            return BSample(wi, V3(out), pdf, rough);
+        }
+        return BSample(wi, V3(F * out), pdf, rough);
+    }
+    const V3 M = l.tf.toworld(m);
+    V3 wi;
+    float Ft             = fresnel_refraction(-wo, M, l.eta, wi);
+    const V3 wi_l        = l.tf.tolocal(wi);
+    const float cosHO    = dot(m, wo_l), cosHI = dot(m, wi_l);
+    const float D        = mf_D(l, m);
+    const float Lambda_o = mf_lambda(l, wo_l), Lambda_i = mf_lambda(l, wi_l);
+    const float G2 = mf_G2(Lambda_o, Lambda_i), G1 = mf_G1(Lambda_o);
+    const V3 ht        = -(l.eta * wi_l + wo_l);
+    const float invHt2 = 1.0f / dot(ht, ht);
+    float pdf = (std::fabs(cosHI * cosHO) * (l.eta * l.eta) * (G1 * D) * invHt2) / std::fabs(wo_l.z);
+    float out = G2 / G1;
+    if (Refract == 2) {
+        pdf *= Ft;
+        return BSample(wi, V3(out), pdf, rough);
+    }
+    return BSample(wi, V3(Ft * out), pdf, rough);
+}
+
+// ---- Phong ------------------------------------------------------------------------
+inline BSample phong_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    float cosNI = dot(l.N, wi), cosNO = dot(l.N, wo);
+    if (cosNI > 0 && cosNO > 0) {
+        V3 R        = (2 * cosNO) * l.N - wo;
+        float cosRI = dot(R, wi);
+        if (cosRI > 0) {
+            const float pdf = (l.exponent + 1) * float(M_1_PI / 2) * fast_safe_pow(cosRI, l.exponent);
+            return BSample(wi, V3(cosNI * (l.exponent + 2) / (l.exponent + 1)), pdf, 1 / (1 + l.exponent));
+        }
+    }
+    return BSample();
+}
+inline BSample phong_sample(const Lobe& l, const V3& wo, float rx, float ry)
+{
+    float cosNO = dot(l.N, wo);
+    if (cosNO > 0) {
+        V3 R      = (2 * cosNO) * l.N - wo;
+        float phi = 2 * float(M_PI) * rx;
+        float sp, cp;
+        fast_sincos(phi, &sp, &cp);
+        float cosTheta  = fast_safe_pow(ry, 1 / (l.exponent + 1));
+        float sinTheta2 = 1 - cosTheta * cosTheta;
+        float sinTheta  = sinTheta2 > 0 ? std::sqrt(sinTheta2) : 0;
+        V3 wi = TangentFrame::from_normal(R).get(cp * sinTheta, sp * sinTheta, cosTheta);
+        return phong_eval(l, wo, wi);
+    }
+    return BSample();
+}
+
+// ---- Ward -------------------------------------------------------------------------
+inline BSample ward_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    float cosNO = dot(l.N, wo), cosNI = dot(l.N, wi);
+    if (cosNI > 0 && cosNO > 0) {
+        V3 H       = normalized(wi + wo);
+        float dotx = l.tf.getx(H) / l.ax, doty = l.tf.gety(H) / l.ay, dotn = l.tf.getz(H);
+        float oh   = dot(H, wi);
+        float e    = fast_exp(-(dotx * dotx + doty * doty) / (dotn * dotn));
+        float c    = float(4 * M_PI) * l.ax * l.ay;
+        float k    = oh * dotn * dotn * dotn;
+        float pdf  = e / (c * k);
+        return BSample(wi, V3(k * std::sqrt(cosNI / cosNO)), pdf, std::max(l.ax, l.ay));
+    }
+    return BSample();
+}
+inline BSample ward_sample(const Lobe& l, const V3& wo, float rx, float ry)
+{
+    float cosNO = dot(l.N, wo);
+    if (cosNO > 0) {
+        float phi = 2 * float(M_PI) * rx;
+        float sp, cp;
+        fast_sincos(phi, &sp, &cp);
+        float cosPhi = l.ax * cp, sinPhi = l.ay * sp;
+        float k      = 1 / std::sqrt(cosPhi * cosPhi + sinPhi * sinPhi);
+        cosPhi *= k;
+        sinPhi *= k;
+        float thetaDenom = (cosPhi * cosPhi) / (l.ax * l.ax) + (sinPhi * sinPhi) / (l.ay * l.ay);
+        float tanTheta2  = -fast_log(1 - ry) / thetaDenom;
+        float cosTheta   = 1 / std::sqrt(1 + tanTheta2);
+        float sinTheta   = cosTheta * std::sqrt(tanTheta2);
+        V3 h(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+        float dotx = h.x / l.ax, doty = h.y / l.ay, dotn = h.z;
+        h           = l.tf.get(h.x, h.y, h.z);
+        float oh    = dot(h, wo);
+        V3 wi       = 2 * oh * h - wo;
+        float cosNI = dot(l.N, wi);
+        if (cosNI > 0) {
+            float e   = fast_exp(-(dotx * dotx + doty * doty) / (dotn * dotn));
+            float c   = float(4 * M_PI) * l.ax * l.ay;
+            float kk  = oh * dotn * dotn * dotn;
+            float pdf = e / (c * kk);
+            return BSample(wi, V3(kk * std::sqrt(cosNI / cosNO)), pdf, std::max(l.ax, l.ay));
+        }
+    }
+    return BSample();
+}
+
+}  // namespace lobes
+
+inline V3 ext_albedo(const Lobe& l, const V3& wo)
+{
+    return l.type == LOBE_MICROFACET ? lobes::mf_albedo(l, wo) : V3(1.0f);
+}
+inline BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    switch (l.type) {
+    case LOBE_PHONG: return lobes::phong_eval(l, wo, wi);
+    case LOBE_WARD: return lobes::ward_eval(l, wo, wi);
+    case LOBE_MICROFACET: return lobes::mf_eval(l, wo, wi);
+    }
+    return BSample();
+}
+inline BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float rz)
+{
+    switch (l.type) {
+    case LOBE_PHONG: return lobes::phong_sample(l, wo, rx, ry);
+    case LOBE_WARD: return lobes::ward_sample(l, wo, rx, ry);
+    case LOBE_MICROFACET: return lobes::mf_sample(l, wo, rx, ry, rz);
+    }
+    return BSample();
+}
+
+}  // namespace oslo

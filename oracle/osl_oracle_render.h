@@ -186,7 +186,26 @@ struct TangentFrame {
         f.w = n;
         return f;
     }
+    static TangentFrame from_normal_and_tangent(const V3& n, const V3& t)
+    {
+        V3 x        = t - n * dot(n, t);
+        float xlen2 = dot(x, x);
+        if (xlen2 > 0) {
+            x = x * (1.0f / std::sqrt(xlen2));
+            TangentFrame f;
+            f.u = x;
+            f.v = cross(n, x);
+            f.w = n;
+            return f;
+        }
+        return from_normal(n);
+    }
     V3 get(float x, float y, float z) const { return x * u + y * v + z * w; }
+    float getx(const V3& a) const { return dot(a, u); }
+    float gety(const V3& a) const { return dot(a, v); }
+    float getz(const V3& a) const { return dot(a, w); }
+    V3 tolocal(const V3& a) const { return V3(dot(a, u), dot(a, v), dot(a, w)); }
+    V3 toworld(const V3& a) const { return get(a.x, a.y, a.z); }
 };
 inline void to_unit_disk(float& x, float& y)
 {
@@ -301,11 +320,22 @@ struct BSample {
     BSample() : wi(0.0f), weight(0.0f) {}
     BSample(V3 wi, V3 w, float pdf, float r) : wi(wi), weight(w), pdf(pdf), roughness(r) {}
 };
-enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT };
+enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
+                LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET };
+struct Lobe;
+// Phong / Ward / Microfacet live in osl_oracle_lobes.h
+V3 ext_albedo(const Lobe& l, const V3& wo);
+BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi);
+BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float rz);
 struct Lobe {
     int type;
     V3 N;
     float eta;
+    // Phong: exponent ; Ward: T, ax, ay ; Microfacet: U(=T), xalpha(=ax), yalpha(=ay), eta, refract, ggx
+    V3 T;
+    float ax = 0, ay = 0, exponent = 0;
+    int refract = 0, ggx = 0;
+    TangentFrame tf;
     V3 get_albedo(const V3& wo) const
     {
         switch (type) {
@@ -316,11 +346,16 @@ struct Lobe {
             return V3(1.0f);
         }
         case LOBE_REFRACTION: return V3(1 - fresnel_dielectric(dot(N, wo), eta));
+        case LOBE_PHONG:
+        case LOBE_WARD:
+        case LOBE_MICROFACET: return ext_albedo(*this, wo);
         default: return V3(1.0f);
         }
     }
     BSample eval(const V3& wo, const V3& wi) const
     {
+        if (type >= LOBE_PHONG)
+            return ext_eval(*this, wo, wi);
         if (type == LOBE_DIFFUSE || type == LOBE_TRANSLUCENT) {
             const float pdf = std::max(dot(N, wi), 0.0f) * float(M_1_PI);
             return BSample(wi, V3(1.0f), pdf, 1.0f);
@@ -351,10 +386,14 @@ struct Lobe {
             return BSample(wi, V3(Ft), std::numeric_limits<float>::infinity(), 0);
         }
         case LOBE_TRANSPARENT: return BSample(-wo, V3(1.0f), std::numeric_limits<float>::infinity(), 0);
+        default: return ext_sample(*this, wo, rx, ry, rz);
         }
         return BSample();
     }
 };
+}  // namespace oslo
+#include "osl_oracle_lobes.h"
+namespace oslo {
 
 struct CompositeBSDF {
     enum { MaxEntries = 8 };
@@ -465,6 +504,29 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                 case REFRACTION_ID: l.type = LOBE_REFRACTION; l.eta = comp->params[3]; break;
                 case TRANSPARENT_ID:
                 case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
+                case PHONG_ID: l.type = LOBE_PHONG; l.exponent = comp->params[3]; break;
+                case WARD_ID:
+                    l.type = LOBE_WARD;
+                    l.T    = V3(comp->params[3], comp->params[4], comp->params[5]);
+                    l.ax   = comp->params[6];
+                    l.ay   = comp->params[7];
+                    l.tf   = TangentFrame::from_normal_and_tangent(l.N, l.T);
+                    break;
+                case MICROFACET_ID: {
+                    // params: dist code, N, U, xalpha, yalpha, eta, refract (shading.h MicrofacetParams)
+                    int dist = (int)f2u(comp->params[0]);
+                    l.type   = LOBE_MICROFACET;
+                    l.N      = V3(comp->params[1], comp->params[2], comp->params[3]);
+                    l.T      = V3(comp->params[4], comp->params[5], comp->params[6]);
+                    l.ax     = comp->params[7];
+                    l.ay     = comp->params[8];
+                    l.eta    = comp->params[9];
+                    l.refract = (int)f2u(comp->params[10]);
+                    l.ggx    = dist == 1;
+                    l.tf     = TangentFrame::from_normal_and_tangent(l.N, l.T);
+                    known    = (dist == 1 || dist == 2 || dist == 3) && l.refract >= 0 && l.refract <= 2;
+                    break;
+                }
                 default: known = false; break;
                 }
                 if (known)

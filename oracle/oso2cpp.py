@@ -1132,8 +1132,6 @@ class Gen:
             e = self.R(a)
             if a.has_derivs:
                 e = "nd(%s)" % e
-            if a.t.base == "string":
-                raise NotImplementedError("string closure params")
             self.w("    putp(c_->params + %d, %s);" % (off, e))
             off += a.t.ncomp
         self.w("}")

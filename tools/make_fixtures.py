@@ -50,17 +50,27 @@ SHADERS = {
     "matte": "render-cornell/matte.osl",
     "metal": "render-cornell/metal.osl",
     "emitter": "render-cornell/emitter.osl",
+    "checkerboard": "render-veachmis/checkerboard.osl",
+    "phong": "render-veachmis/phong.osl",
+    "ward": "render-ward/ward.osl",
+    "glossy_glass": "render-microfacet/glossy_glass.osl",
+    # this repo's own test shaders (path relative to the repo root)
+    "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
 }
 # scene descriptions + model data of the testrender configs (test input data)
 SCENES = {
     "cornell.xml": "render-cornell/cornell.xml",
     "bunny.xml": "render-bunny/bunny.xml",
     "bunny.obj": "render-bunny/bunny.obj",
+    "veach.xml": "render-veachmis/veach.xml",
+    "ward.xml": "render-ward/scene.xml",
 }
 # golden renders (half-float EXR in the reference; stored as float16 npz)
 RENDERS = {
     "render-cornell": "render-cornell/ref/out.exr",
     "render-bunny": "render-bunny/ref/out.exr",
+    "render-veachmis": "render-veachmis/ref/out.exr",
+    "render-ward": "render-ward/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
@@ -113,7 +123,8 @@ def main():
     os.makedirs(os.path.join(OUT, "text"), exist_ok=True)
     inc = [os.path.join(REF, "src/shaders")]
     for name, rel in SHADERS.items():
-        oso = mini_oslc.compile_osl(os.path.join(TS, rel), inc)
+        src = os.path.join(ROOT, rel[5:]) if rel.startswith("repo:") else os.path.join(TS, rel)
+        oso = mini_oslc.compile_osl(src, inc)
         with open(os.path.join(OUT, "oso", name + ".oso"), "w") as f:
             f.write(oso)
     for name, rel in IMAGES.items():
