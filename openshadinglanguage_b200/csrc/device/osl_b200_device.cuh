@@ -34,6 +34,8 @@ OSLD V3 mkv(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return
 OSLD V3 mkv(float a) { return mkv(a, a, a); }
 OSLD Df mkd(float v) { Df r; r.val = v; r.dx = 0.0f; r.dy = 0.0f; return r; }
 OSLD Df mkd(float v, float dx, float dy) { Df r; r.val = v; r.dx = dx; r.dy = dy; return r; }
+OSLD Df as_dual(float a) { return mkd(a); }
+OSLD Df as_dual(Df a) { return a; }
 OSLD Dv mkdv(V3 v) { Dv r; r.val = v; r.dx = mkv(0.0f); r.dy = mkv(0.0f); return r; }
 OSLD Dv mkdv(V3 v, V3 dx, V3 dy) { Dv r; r.val = v; r.dx = dx; r.dy = dy; return r; }
 
@@ -1015,3 +1017,4 @@ OSLD V3 o_Dy(V3) { return mkv(0.0f); }
 
 #include "osl_b200_simplex.cuh"
 #include "osl_b200_spline.cuh"
+#include "osl_b200_gabor.cuh"

@@ -108,7 +108,8 @@ noise_kind(const std::string& n, bool periodic)
     static const std::map<std::string, int> base
         = { { "noise", 0 },  { "uperlin", 0 },   { "snoise", 1 }, { "perlin", 1 },
             { "cell", 2 },   { "cellnoise", 2 }, { "hash", 3 },   { "hashnoise", 3 },
-            { "simplex", 4 }, { "simplexnoise", 4 }, { "usimplex", 5 }, { "usimplexnoise", 5 } };
+            { "simplex", 4 }, { "simplexnoise", 4 }, { "usimplex", 5 }, { "usimplexnoise", 5 },
+            { "gabor", 6 } };
     static const std::map<std::string, int> per
         = { { "pnoise", 0 }, { "psnoise", 1 }, { "pcellnoise", 2 }, { "phashnoise", 3 } };
     if (periodic) {
@@ -492,6 +493,7 @@ Gen::op_noise(const Opcode& op, bool periodic)
     int kind = noise_kind(name, periodic);
     if (kind < 0)
         unsupported("noise type \"" + name + "\"");
+    std::vector<int> opts(rest.begin() + coords.size(), rest.end());
     std::vector<int> pers;
     if (periodic) {
         size_t half = coords.size() / 2;
@@ -505,6 +507,54 @@ Gen::op_noise(const Opcode& op, bool periodic)
     int dim = (int)ins.size(), nc = d.type.ncomp();
     if (dim < 1 || dim > 4)
         unsupported("noise with " + std::to_string(dim) + " input dimensions");
+    if (kind == 6) {
+        // Gabor branch (llvm_gen.cpp:3196-3203): derivatives are always taken
+        // (zero where the coordinate has none); options travel in NoiseParams
+        // (llvm_gen_noise_options, llvm_gen.cpp:3057-3103); 1-D / 2-D slice the
+        // 3-D noise and the 4-D forms ignore time (opnoise.cpp:484-632).
+        w("NoiseParams opt_ = noise_params_default();");
+        for (size_t i = 0; i + 1 < opts.size(); i += 2) {
+            const Symbol& nm = S(opts[i]);
+            const Symbol& v  = S(opts[i + 1]);
+            if (nm.type.base != Base::String || !nm.const_value())
+                unsupported("noise option with a name that is not known at compile time");
+            std::string key = nm.svals.empty() ? "" : nm.svals[0];
+            std::string e   = R(opts[i + 1]);
+            if (v.has_derivs)
+                e = "nd(" + e + ")";
+            bool scalar = !v.type.is_triple() && v.type.arraylen == 0;
+            if (key.empty())
+                continue;
+            if ((key == "anisotropic" || key == "do_filter") && v.type.base == Base::Int && scalar)
+                w("opt_." + key + " = " + e + ";");
+            else if (key == "direction" && v.type.is_triple())
+                w("assign(opt_.direction, " + e + ");");
+            else if ((key == "bandwidth" || key == "impulses") && scalar
+                     && (v.type.base == Base::Float || v.type.base == Base::Int))
+                w("opt_." + key + " = (float)(" + e + ");");
+            else
+                g.warnings.push_back("Unknown noise optional argument: \"" + key + "\" in layer '" + L->layername + "'");
+        }
+        std::string P[3] = { "mkd(0.0f)", "mkd(0.0f)", "mkd(0.0f)" };
+        for (int k = 0; k < dim && k < 3; ++k) {
+            P[k] = "as_dual(" + comp(ins[k].first, ins[k].second, true) + ")";
+        }
+        std::string per = "nullptr";
+        if (periodic) {
+            std::string pc[3] = { "0.0f", "0.0f", "0.0f" };
+            int np = 0;
+            for (int a : pers)
+                for (int c = 0; c < S(a).type.ncomp() && np < 3; ++c, ++np)
+                    pc[np] = comp(a, c, false);
+            w("V3 per_ = mkv(" + pc[0] + ", " + pc[1] + ", " + pc[2] + ");");
+            per = "&per_";
+        }
+        w("Df out_[3];");
+        w("gabor_noise<" + std::to_string(nc) + ">(out_, " + P[0] + ", " + P[1] + ", " + P[2] + ", " + per + ", opt_);");
+        for (int c = 0; c < nc; ++c)
+            w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", out_[" + std::to_string(c) + "]);");
+        return;
+    }
     bool hashy   = kind == 2 || kind == 3;
     bool simplex = kind == 4 || kind == 5;
     if (simplex && periodic)

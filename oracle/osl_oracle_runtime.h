@@ -8,6 +8,7 @@
 // one-execute-per-point loop (src/testshade/testshade.cpp:1585-1672).
 #pragma once
 #include "osl_oracle_ops.h"
+#include "osl_oracle_gabor.h"
 #include <cstdarg>
 #include <cstdio>
 #include <string>

@@ -339,8 +339,8 @@ NOISE_KIND = {"noise": "N_NOISE", "uperlin": "N_NOISE", "snoise": "N_SNOISE",
               "perlin": "N_SNOISE", "cellnoise": "N_CELL", "cell": "N_CELL",
               "hashnoise": "N_HASH", "hash": "N_HASH", "simplex": "N_SIMPLEX",
               "simplexnoise": "N_SIMPLEX", "usimplex": "N_USIMPLEX",
-              "usimplexnoise": "N_USIMPLEX"}
-PNOISE_KIND = {"pnoise": "N_NOISE", "psnoise": "N_SNOISE", "pcellnoise": "N_CELL",
+              "usimplexnoise": "N_USIMPLEX", "gabor": "N_GABOR"}
+PNOISE_KIND = {"pnoise": "N_NOISE", "psnoise": "N_SNOISE", "pcellnoise": "N_CELL", "gabor": "N_GABOR",
                "phashnoise": "N_HASH", "noise": "N_NOISE", "uperlin": "N_NOISE",
                "snoise": "N_SNOISE", "perlin": "N_SNOISE", "cell": "N_CELL",
                "cellnoise": "N_CELL", "hash": "N_HASH", "hashnoise": "N_HASH"}
@@ -948,6 +948,7 @@ class Gen:
             if a.t.base == "string":
                 break
             coords.append(a)
+        opts = rest[len(coords):]
         table = PNOISE_KIND if periodic else NOISE_KIND
         if name not in table:
             raise NotImplementedError("noise type '%s'" % name)
@@ -956,6 +957,8 @@ class Gen:
             half = len(coords) // 2
             pers = coords[half:]
             coords = coords[:half]
+        if kind == "N_GABOR":
+            return self.gabor_impl(d, coords, pers if periodic else None, opts)
         # flatten coordinates
         ins = []
         for a in coords:
@@ -988,6 +991,51 @@ class Gen:
         for c in range(nc):
             self.w("setc(%s, %d, out_[%d]);" % (self.R(d), c, c))
 
+
+    def gabor_impl(self, d, coords, pers, opts):
+        """Gabor branch of llvm_gen_noise (llvm_gen.cpp:3196-3203): derivs are
+        always taken (zero when the coordinate has none), options go through
+        NoiseParams (llvm_gen_noise_options, llvm_gen.cpp:3057-3103); 1-D/2-D
+        slice the 3-D noise and 4-D ignores time (opnoise.cpp:484-632)."""
+        ins = [(a, c) for a in coords for c in range(a.t.ncomp)]
+        comps = ["Df(%s)" % self.comp(a, c, True) for a, c in ins][:3]
+        while len(comps) < 3:
+            comps.append("Df(0.0f)")
+        self.w("NoiseParams opt_;")
+        i = 0
+        while i + 1 < len(opts):
+            nm, val = opts[i], opts[i + 1]
+            i += 2
+            if not nm.constval:
+                raise NotImplementedError("noise option with a non-constant name")
+            key = nm.vals[0]
+            e = self.R(val)
+            if val.has_derivs:
+                e = "nd(%s)" % e
+            if key == "":
+                continue
+            if key in ("anisotropic", "do_filter") and val.t.base == "int" and not val.t.arr:
+                self.w("opt_.%s = %s;" % (key, e))
+            elif key == "direction" and val.t.triple:
+                self.w("assign(opt_.direction, %s);" % e)
+            elif key in ("bandwidth", "impulses") and val.t.base in ("float", "int") and not val.t.triple \
+                    and not val.t.arr:
+                self.w("opt_.%s = (float)(%s);" % (key, e))
+            else:
+                # the reference reports "Unknown noise optional argument" and carries on
+                self.w("// unknown noise option '%s' ignored" % key)
+        self.w("Dv P_ = make_dv(%s);" % ", ".join(comps))
+        per = "nullptr"
+        if pers is not None:
+            pc = [self.comp(a, c, False) for a in pers for c in range(a.t.ncomp)][:3]
+            while len(pc) < 3:
+                pc.append("0.0f")
+            self.w("V3 per_(%s);" % ", ".join(pc))
+            per = "&per_"
+        nc = d.t.ncomp
+        self.w("Df out_[3]; gabor_noise<%d>(out_, P_, %s, opt_);" % (nc, per))
+        for c in range(nc):
+            self.w("setc(%s, %d, out_[%d]%s);" % (self.R(d), c, c, "" if d.has_derivs else ".val"))
 
     def op_spline(self, op):
         """llvm_gen_spline (llvm_gen.cpp:3673-3740) -> osl_spline_* (opspline.cpp)."""

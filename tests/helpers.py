@@ -47,6 +47,10 @@ IMAGE_CASES = {
                        params=dict(noisename="cell", offset=0.0, scale=1.0)),
     "noise-perlin": dict(shader="testnoise", res=512, params=dict(noisename="perlin")),
     "noise-simplex": dict(shader="testnoise", res=512, params=dict(noisename="simplex")),
+    "noise-gabor": dict(shader="testnoise", res=512, params=dict(noisename="gabor")),
+    "noise-gabor2d-filter": dict(shader="gabor2d_filter_test", res=512, params={}),
+    "noise-gabor3d-filter": dict(shader="gabor3d_filter_test", res=512, params={}),
+    "pnoise-gabor": dict(shader="testpnoise", res=512, params=dict(noisename="gabor")),
     "pnoise": dict(shader="pnoise_test", res=512, params={}),
     "pnoise-cell": dict(shader="testpnoise", res=512,
                         params=dict(noisename="cell", offset=0.0, scale=1.0)),

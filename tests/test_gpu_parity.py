@@ -142,10 +142,19 @@ def test_group_matches_oracle_and_golden_image(b200lib, cuda_device, case):
     layers, outputs, res = helpers.image_case_group(case)
     want = _run_oracle_group(layers, (), outputs, res, 3)
     strict = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=0", 3)
-    assert np.array_equal(strict.view(np.uint32), want.view(np.uint32)), \
-        "strict mode differs from oracle: max |d| = %g" % np.abs(strict - want).max()
     fast = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=1", 3)
-    if "cell" in case or "hash" in case:
+    if "gabor" in case:
+        # Gabor calls libm expf / sincosf in the reference (gabornoise.h:113-121), which
+        # CUDA's expf / sincosf match to <= 2 ulp, not bit for bit: a sum of up to ~100
+        # impulses of magnitude <= 1 agrees to GABOR_ATOL.  The integer side (cell hash,
+        # LCG stream, impulse counts) is exact - a miscounted impulse would show as ~1e-1.
+        GABOR_ATOL = 2e-5
+        assert np.abs(strict - want).max() <= GABOR_ATOL, np.abs(strict - want).max()
+        assert np.abs(fast - want).max() <= 5 * GABOR_ATOL, np.abs(fast - want).max()
+    else:
+        assert np.array_equal(strict.view(np.uint32), want.view(np.uint32)), \
+            "strict mode differs from oracle: max |d| = %g" % np.abs(strict - want).max()
+    if "cell" in case or "hash" in case or "gabor" in case:
         # integer-hash outputs: contraction only touches the coordinate setup;
         # the image threshold of the reference test is the bar
         pass

@@ -44,6 +44,8 @@ SHADERS = {
     "layers_lazy_b": "layers-lazy/b.osl",
     "layers_lazy_c": "layers-lazy/c.osl",
     "spline_test": "spline/test.osl",
+    "gabor2d_filter_test": "noise-gabor2d-filter/test.osl",
+    "gabor3d_filter_test": "noise-gabor3d-filter/test.osl",
     "layers_a": "layers/a.osl",
     "layers_b": "layers/b.osl",
     # testrender materials (same sources in render-cornell and render-bunny)
@@ -80,6 +82,10 @@ IMAGES = {
     "noise-cell": "noise-cell/ref/out.tif",
     "noise-perlin": "noise-perlin/ref/out.tif",
     "noise-simplex": "noise-simplex/ref/out.tif",
+    "noise-gabor": "noise-gabor/ref/out.tif",
+    "noise-gabor2d-filter": "noise-gabor2d-filter/ref/out.tif",
+    "noise-gabor3d-filter": "noise-gabor3d-filter/ref/out.tif",
+    "pnoise-gabor": "pnoise-gabor/ref/out.tif",
     "spline-color": "spline/ref/color.tif",
     "spline-dcolor": "spline/ref/dcolor.tif",
     "spline-float": "spline/ref/float.tif",
