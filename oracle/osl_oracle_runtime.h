@@ -11,9 +11,27 @@
 #include "osl_oracle_gabor.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <thread>
 #include <vector>
+#include "osl_oracle_color.h"
+
+#ifndef OSLO_COLORSPACE
+#    define OSLO_COLORSPACE "Rec709" /* ShadingSystem attribute "colorspace" default */
+#endif
+namespace oslo {
+// uniform colour state of the shading system (ShadingStateUniform::m_colorsystem)
+inline const ColorSystem& colorsystem()
+{
+    static const ColorSystem cs = [] {
+        ColorSystem c;
+        colorsystem_setup(c, OSLO_COLORSPACE);
+        return c;
+    }();
+    return cs;
+}
+}  // namespace oslo
 
 namespace oslo {
 

@@ -798,7 +798,14 @@ class Gen:
         A = op.args
         d = A[0]
         if len(A) == 5:
-            raise NotImplementedError("triple constructor with a space name")
+            if op.name != "color":
+                raise NotImplementedError("triple constructor with a space name")
+            # llvm_gen_construct_color (llvm_gen.cpp:1826-1865): osl_prepend_color_from on
+            # the value, derivatives of the result are zeroed
+            self.w("{ V3 c_(%s, %s, %s); assign(%s, color_to_rgb(colorsystem(), %s, c_)); }" % (
+                self.comp(A[2], 0, False), self.comp(A[3], 0, False), self.comp(A[4], 0, False),
+                self.R(d), self.R(A[1])))
+            return
         dv = d.has_derivs and any(a.has_derivs for a in A[1:])
         for c in range(3):
             self.w("setc(%s, %d, %s);" % (self.R(d), c, self.comp(A[1 + c], 0, dv)))
@@ -1036,6 +1043,33 @@ class Gen:
         self.w("Df out_[3]; gabor_noise<%d>(out_, P_, %s, opt_);" % (nc, per))
         for c in range(nc):
             self.w("setc(%s, %d, out_[%d]%s);" % (self.R(d), c, c, "" if d.has_derivs else ".val"))
+
+    # ---- colour shadeops (opcolor.cpp:434-518) -------------------------------------
+    def op_luminance(self, op):
+        d, c = op.args
+        dv = d.has_derivs and c.has_derivs
+        e = self.R(c) if (dv or not c.has_derivs) else "nd(%s)" % self.R(c)
+        if c.isconst:
+            e = "V3(%s)" % ", ".join(self.comp(c, k, False) for k in range(3))
+        self.w("assign(%s, color_luminance(colorsystem(), %s));" % (self.R(d), e))
+
+    def op_blackbody(self, op):
+        d, t = op.args
+        self.w("assign(%s, color_blackbody(colorsystem(), %s));" % (self.R(d), self.comp(t, 0, False)))
+
+    def op_wavelength_color(self, op):
+        d, t = op.args
+        self.w("assign(%s, color_wavelength(colorsystem(), %s));" % (self.R(d), self.comp(t, 0, False)))
+
+    def op_transformc(self, op):
+        """osl_transformc (opcolor.cpp:487-518): Dual form only when both sides carry derivs."""
+        d, frm, to, c = op.args
+        dv = d.has_derivs and c.has_derivs
+        e = self.R(c) if (dv or not c.has_derivs) else "nd(%s)" % self.R(c)
+        if c.isconst:
+            e = "V3(%s)" % ", ".join(self.comp(c, k, False) for k in range(3))
+        self.w("assign(%s, color_transformc(colorsystem(), %s, %s, %s));" % (
+            self.R(d), self.R(frm), self.R(to), e))
 
     def op_spline(self, op):
         """llvm_gen_spline (llvm_gen.cpp:3673-3740) -> osl_spline_* (opspline.cpp)."""

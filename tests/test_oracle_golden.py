@@ -6,6 +6,8 @@ hashes of testsuite/hash/ref/out.txt, the golden images of the noise tests
 (reference thresholds: failthresh 0.004 on [0,1] = 1 LSB of uint8, failpercent
 0.05 %; testsuite/noise/run.py) and the lazy-evaluation text goldens.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -94,6 +96,39 @@ def test_layers_text_golden():
     want = "\n".join(l for l in helpers.golden_text("layers").split("\n")
                      if not l.startswith(("Compiled", "Connect")))
     assert txt.rstrip("\n") == want.rstrip("\n")
+
+
+@pytest.mark.parametrize("case", ["color", "transformc"])
+def test_color_text_goldens(case):
+    """testsuite/color and testsuite/transformc (`testshade test`, one point):
+    colour constructors with space names, luminance, transformc between
+    rgb/hsv/hsl/YIQ/XYZ/xyY/sRGB incl. derivatives, printed at %g / %0.3f."""
+    g = oracle.OracleGroup([dict(oso=helpers.oso(case + "_test"), name="l0")])
+    var, uni = oracle.testshade_globals(1, 1)
+    txt = g.run_capture(1, var, uni)
+    want = "\n".join(l for l in helpers.golden_text(case).split("\n") if not l.startswith("Compiled"))
+    assert txt.rstrip("\n") == want.rstrip("\n")
+
+
+@pytest.mark.parametrize("case,xres,yres", [("blackbody", 1000, 64), ("wavelength_color", 1000, 64)])
+def test_color_exr_goldens(case, xres, yres):
+    """testsuite/blackbody (`-g 1000 64 -od half`) and testsuite/wavelength_color
+    (`-od float`): image thresholds of the tests (failthresh 0.004, 0.05 % of pixels)."""
+    g = oracle.OracleGroup([dict(oso=helpers.oso(case + "_test"), name="l0")],
+                           outputs=[dict(name="Cout", offset=0, stride=12)])
+    var, uni = oracle.testshade_globals(xres, yres)
+    out = np.zeros((xres * yres, 3), np.float32)
+    g.run(xres * yres, var, uni, out, nthreads=4)
+    ref = np.load(os.path.join(helpers.GOLDEN, "images", case + ".npz"))["pixels"]
+    img = out.reshape(yres, xres, 3)
+    assert ref.shape == img.shape
+    if case == "blackbody":     # the test writes half pixels: compare what the file would hold
+        img = img.astype(np.float16).astype(np.float32)
+    d = np.abs(img - ref).max(axis=2)
+    # one half ulp at the image's magnitude (values reach 8728) is the tightest meaningful bar
+    ulp = np.maximum(np.abs(ref).max(axis=2), 1e-4) * (2.0 ** -10 if case == "blackbody" else 2.0 ** -22)
+    assert (d > np.maximum(0.004, ulp)).mean() <= 0.0005, d.max()
+    assert np.all(d <= 2 * ulp + 1e-7), (d / ulp).max()
 
 
 @pytest.mark.parametrize("case", sorted(helpers.IMAGE_CASES))

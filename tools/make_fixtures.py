@@ -46,6 +46,10 @@ SHADERS = {
     "spline_test": "spline/test.osl",
     "gabor2d_filter_test": "noise-gabor2d-filter/test.osl",
     "gabor3d_filter_test": "noise-gabor3d-filter/test.osl",
+    "color_test": "color/test.osl",
+    "transformc_test": "transformc/test.osl",
+    "blackbody_test": "blackbody/test.osl",
+    "wavelength_color_test": "wavelength_color/test.osl",
     "layers_a": "layers/a.osl",
     "layers_b": "layers/b.osl",
     # testrender materials (same sources in render-cornell and render-bunny)
@@ -99,6 +103,13 @@ TEXTS = {
     "hash": "hash/ref/out.txt",
     "layers-lazy": "layers-lazy/ref/out.txt",
     "layers": "layers/ref/out.txt",
+    "color": "color/ref/out.txt",
+    "transformc": "transformc/ref/out.txt",
+}
+# float / half EXR goldens of testshade image tests (stored as float32 npz, full size)
+EXR_IMAGES = {
+    "blackbody": "blackbody/ref/out.exr",
+    "wavelength_color": "wavelength_color/ref/out.exr",
 }
 
 
@@ -152,6 +163,9 @@ def main():
     for name, rel in RENDERS.items():
         img = cv2.imread(os.path.join(TS, rel), cv2.IMREAD_UNCHANGED)[..., ::-1][..., :3]
         np.savez_compressed(os.path.join(OUT, "images", name + ".npz"), pixels=img.astype(np.float16))
+    for name, rel in EXR_IMAGES.items():
+        img = cv2.imread(os.path.join(TS, rel), cv2.IMREAD_UNCHANGED)[..., ::-1][..., :3]
+        np.savez_compressed(os.path.join(OUT, "images", name + ".npz"), pixels=img.astype(np.float32))
     with open(os.path.join(OUT, "noise_vectors.json"), "w") as f:
         json.dump(parse_noise_vectors(), f, indent=1)
     print("fixtures written to", OUT)
