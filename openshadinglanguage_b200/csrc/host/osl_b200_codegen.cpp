@@ -257,6 +257,39 @@ private:
         return e;
     }
 
+    // Colour-space name -> OSLD_CS_* code (osl_b200_color.cuh).  ctor: the name feeds
+    // ColorSystem::to_rgb (no "linear"/"sRGB" clauses) instead of transformc.
+    std::string space_code(int si, bool ctor)
+    {
+        struct E {
+            const char* name;
+            const char* code;
+            bool ctor_ok;
+        };
+        static const E table[] = { { "RGB", "OSLD_CS_RGB", true },   { "rgb", "OSLD_CS_RGB", true },
+                                   { "linear", "OSLD_CS_RGB", false }, { "hsv", "OSLD_CS_HSV", true },
+                                   { "hsl", "OSLD_CS_HSL", true },   { "YIQ", "OSLD_CS_YIQ", true },
+                                   { "XYZ", "OSLD_CS_XYZ", true },   { "xyY", "OSLD_CS_XYY", true },
+                                   { "sRGB", "OSLD_CS_SRGB", false } };
+        const Symbol& s = S(si);
+        if (s.const_value()) {
+            std::string v = s.svals.empty() ? "" : s.svals[0];
+            if (v == g.colorspace)
+                return "OSLD_CS_RGB";
+            for (const E& e : table)
+                if (v == e.name && (e.ctor_ok || !ctor))
+                    return e.code;
+            return "OSLD_CS_UNKNOWN";
+        }
+        // run-time name: compare interned ids
+        std::string e = R(si), r = "(";
+        r += "(" + e + ") == " + std::to_string(g.intern(g.colorspace)) + " ? OSLD_CS_RGB : ";
+        for (const E& t : table)
+            if (t.ctor_ok || !ctor)
+                r += "(" + e + ") == " + std::to_string(g.intern(t.name)) + " ? " + t.code + " : ";
+        return r + "OSLD_CS_UNKNOWN)";
+    }
+
     void gen_layer(int layer);
     void emit_block(int b, int e, const Ctx* ctx);
     void useparams(const Opcode& op);
@@ -637,6 +670,38 @@ Gen::emit_op(const Opcode& op)
             (void)s;
             w("assign(" + R(op.args[0]) + ", " + R(op.args[1]) + ");");
         }
+    } else if (n == "color" && op.args.size() == 5) {
+        // llvm_gen_construct_color (llvm_gen.cpp:1826-1865): osl_prepend_color_from on the
+        // value; the derivatives of the result are zeroed.  ColorSystem::to_rgb has no
+        // "linear"/"sRGB" clause, so those names pass through here (opcolor.cpp:287-305).
+        g.uses_colorsystem = true;
+        w("assign(" + R(op.args[0]) + ", color_transformc(osl_cs_, " + space_code(op.args[1], true) + ", OSLD_CS_RGB, mkv("
+          + comp(op.args[2], 0, false) + ", " + comp(op.args[3], 0, false) + ", " + comp(op.args[4], 0, false) + ")));");
+    } else if (n == "luminance" || n == "transformc") {
+        // osl_luminance_fv/_dfdv, osl_transformc (opcolor.cpp:464-518): dual form only
+        // when both sides carry derivatives
+        g.uses_colorsystem = true;
+        int ci             = (int)op.args.size() - 1;
+        const Symbol& c    = A(ci);
+        bool dv            = A(0).has_derivs && c.has_derivs;
+        std::string e      = R(op.args[ci]);
+        if (c.is_const())
+            e = "mkv(" + comp(op.args[ci], 0, false) + ", " + comp(op.args[ci], 1, false) + ", " + comp(op.args[ci], 2, false) + ")";
+        else if (c.has_derivs && !dv)
+            e = "nd(" + e + ")";
+        if (n == "luminance") {
+            need(2);
+            w("assign(" + R(op.args[0]) + ", color_luminance(osl_cs_, " + e + "));");
+        } else {
+            need(4);
+            w("assign(" + R(op.args[0]) + ", color_transformc(osl_cs_, " + space_code(op.args[1], false) + ", "
+              + space_code(op.args[2], false) + ", " + e + "));");
+        }
+    } else if (n == "blackbody" || n == "wavelength_color") {
+        need(2);
+        g.uses_colorsystem = true;
+        w("assign(" + R(op.args[0]) + ", color_" + std::string(n == "blackbody" ? "blackbody" : "wavelength") + "(osl_cs_, "
+          + comp(op.args[1], 0, false) + "));");
     } else if (n == "color" || n == "point" || n == "vector" || n == "normal") {
         if (op.args.size() != 4)
             unsupported("triple constructor with a coordinate-system name");
@@ -1145,6 +1210,8 @@ Gen::run()
     std::ostringstream out;
     out << "// generated by libosl_b200 for shader group '" << g.name << "'\n";
     out << "#include \"osl_b200_device.cuh\"\n";
+    if (g.uses_colorsystem)
+        out << "#include \"osl_b200_color.cuh\"\n" << colorsystem_cuda_definition(g.colorspace);
     out << prelude << sg.str() << OUTPUT_HELPERS << gd << layers_src;
     // ---- kernel: one CTA walks tiles of BLOCK consecutive points --------------
     auto out_sym  = [&](int k) -> Symbol& { return g.layers[g.outputs[k].first].m.syms[g.outputs[k].second]; };
@@ -1272,9 +1339,15 @@ generate_cuda_render(std::vector<Group*>& groups)
     std::ostringstream out;
     out << "// generated by libosl_b200: render module with " << groups.size() << " material group(s)\n";
     out << "#include \"osl_b200_device.cuh\"\n#include \"osl_b200_closure.cuh\"\n#include \"osl_b200_sg.cuh\"\n";
-    out << "using namespace osld;\nstruct B200Launch { int unused_; };\n";
-    for (size_t k = 0; k < groups.size(); ++k)
-        out << Gen(*groups[k]).run_material("mat" + std::to_string(k));
+    std::string mats;
+    bool color = false;
+    for (size_t k = 0; k < groups.size(); ++k) {
+        mats += Gen(*groups[k]).run_material("mat" + std::to_string(k));
+        color |= groups[k]->uses_colorsystem;
+    }
+    if (color)  // one colour system per module: the shading system's, i.e. the first group's
+        out << "#include \"osl_b200_color.cuh\"\n" << colorsystem_cuda_definition(groups[0]->colorspace);
+    out << "using namespace osld;\nstruct B200Launch { int unused_; };\n" << mats;
     out << "static __device__ __forceinline__ void osl_execute_shader(int shaderID, SG& sg)\n{\n    switch (shaderID) {\n";
     for (size_t k = 0; k < groups.size(); ++k)
         out << "    case " << k << ": mat" << k << "::entry(sg); break;\n";

@@ -128,6 +128,8 @@ struct Group {
     std::set<int> globals_read;                // b200_sg_field ids the kernel loads
     bool fma = true;                           // allow FMA contraction in generated code
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
+    bool uses_colorsystem  = false;            // set by codegen: luminance / blackbody / transformc ...
+    std::string colorspace = "Rec709";         // ShadingSystem attribute "colorspace"
 
     int layer_index(const std::string& n) const;
     void add_layer(const std::string& oso_text, const std::string& layername,
@@ -138,6 +140,11 @@ struct Group {
     void finalize();  // unused/lazy/derivs analysis
     int intern(const std::string& s);
 };
+
+// Colour system of a working space as floats (osl_b200_color.cpp; false: unknown name)
+// and as the CUDA constant array `osl_cs_` that generated modules embed.
+bool colorsystem_table(const std::string& colorspace, std::vector<float>& out);
+std::string colorsystem_cuda_definition(const std::string& colorspace);
 
 // Emit CUDA C++ for the whole group (kernel name: osl_b200_group_kernel).
 std::string generate_cuda(Group& g);

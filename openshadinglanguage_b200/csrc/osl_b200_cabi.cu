@@ -241,6 +241,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
         auto opt  = parse_options(desc->options);
         if (opt.count("fma"))
             G->g.fma = atoi(opt["fma"].c_str()) != 0;
+        if (opt.count("colorspace"))
+            G->g.colorspace = opt["colorspace"];
         if (opt.count("block"))
             G->block = atoi(opt["block"].c_str());
         if (opt.count("stage"))

@@ -82,6 +82,28 @@ def spline_case(res=256):
     return layers, outputs, off // 4
 
 
+# tests/shaders/color_ops.osl: one dense arena per output
+COLOR_OPS_OUTPUTS = [("Cto", 3), ("Cback", 3), ("Cctor", 3), ("Csrgb", 3), ("Clin", 3), ("DxCto", 3),
+                     ("DyCto", 3), ("Lum", 1), ("DxLum", 1), ("BB", 3), ("WL", 3)]
+
+
+def color_ops_case(space, res=96):
+    layers = [dict(oso=oso("color_ops"), name="layer0", params=dict(space=space))]
+    outputs, off = [], 0
+    for name, ch in COLOR_OPS_OUTPUTS:
+        outputs.append(dict(name=name, offset=off, stride=4 * ch))
+        off += 4 * ch * res * res
+    return layers, outputs, off // 4
+
+
+def color_ops_split(arena, res=96):
+    out, o = {}, 0
+    for name, ch in COLOR_OPS_OUTPUTS:
+        out[name] = arena[o:o + ch * res * res].reshape(res * res, ch)
+        o += ch * res * res
+    return out
+
+
 def check_spline_images(arena, res=256):
     o = 0
     for name, ch, gold in SPLINE_OUTPUTS:

@@ -198,6 +198,38 @@ def test_spline_group_matches_oracle_and_golden(b200lib, cuda_device):
     assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("space", ["hsv", "hsl", "YIQ", "XYZ", "xyY", "sRGB", "rgb", "Rec709", "nonsense"])
+def test_color_ops_match_oracle(b200lib, cuda_device, space):
+    """luminance / transformc (+Dx, Dy) / colour constructor with a space name /
+    blackbody (table and direct branch) / wavelength_color, one arena per output
+    (tests/shaders/color_ops.osl).  Everything that is table look-ups, matrix
+    products and compares is bit-exact; the sRGB curves call powf in the
+    reference (OIIO safe_pow -> std::pow), so they carry an ulp-level tolerance."""
+    import torch
+    res = 96
+    layers, outputs, nfloats = helpers.color_ops_case(space, res)
+    og = oracle.OracleGroup(layers, outputs=outputs)
+    ovar, ouni = oracle.testshade_globals(res, res)
+    want = np.zeros(nfloats, np.float32)
+    og.run(res * res, ovar, ouni, want, nthreads=4)
+    g = b200lib.ShaderGroup(layers, outputs=outputs, options="fma=0")
+    var, uni = b200lib.grid_globals(res, res)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(nfloats, dtype=torch.float32, device=cuda_device)
+    g.execute(res * res, dvar, uni, out)
+    torch.cuda.synchronize()
+    W, G = helpers.color_ops_split(want, res), helpers.color_ops_split(out.cpu().numpy(), res)
+    POW_RTOL = 4e-7 * 4          # <= 4 ulp of powf
+    for name in W:
+        uses_pow = name in ("Csrgb", "Clin") or (space == "sRGB" and name in ("Cto", "Cback", "DxCto", "DyCto"))
+        if uses_pow:
+            assert np.allclose(G[name], W[name], rtol=POW_RTOL, atol=1e-7), (name, np.abs(G[name] - W[name]).max())
+        else:
+            assert np.array_equal(G[name].view(np.uint32), W[name].view(np.uint32)), \
+                (name, np.abs(G[name] - W[name]).max())
+    assert np.isfinite(W["BB"]).all() and W["BB"].max() > 0 and W["WL"].max() > 0
+
+
 def test_host_path_matches_device_path(b200lib, cuda_device):
     layers, outputs, res = helpers.image_case_group("noise")
     a = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=0", 3)

@@ -62,6 +62,7 @@ SHADERS = {
     "glossy_glass": "render-microfacet/glossy_glass.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
+    "color_ops": "repo:tests/shaders/color_ops.osl",
 }
 # scene descriptions + model data of the testrender configs (test input data)
 SCENES = {
