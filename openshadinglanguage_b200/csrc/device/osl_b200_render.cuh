@@ -48,6 +48,13 @@ struct RenderScene {
     int xres, yres;
     int aa, max_bounces, rr_depth, no_jitter, show_globals;
     int background_shader, background_resolution;
+    // background importance table (background.h:38-276), built on the device by the
+    // rt_bg_* kernels; null when the scene has no importance-sampled background
+    float* bg_values;  // res*res RGB, already divided by the texel pdf
+    float* bg_rows;    // res: CDF over rows
+    float* bg_cols;    // res*res: per-row CDF over columns
+    int bg_res;
+    float bg_invres, bg_invjacobian;
 };
 
 // Path state: one 128-byte record (8 x float4) per path slot.  After the live
@@ -749,6 +756,129 @@ OSLD Ray camera_ray(const RenderScene& S, float x, float y)
     return r;
 }
 
+// ---- background (background.h, simpleraytracer.cpp:937-954, shading.cpp:1709-1746) ---------
+// Compiled in only for scenes with a <Background> (OSLD_HAS_BACKGROUND from the generator).
+#ifdef OSLD_HAS_BACKGROUND
+// The reference returns the weight held when the tree walk ends (last visited branch).
+OSLD V3 process_background_closure(const ClosurePool& pool, int closure)
+{
+    if (!closure)
+        return mkv(0.0f);
+    int ptr_stack[16];
+    V3 weight_stack[16];
+    int sp    = 0;
+    V3 weight = mkv(1.0f);
+    while (closure) {
+        int id = pool.id(closure);
+        if (id == CL_MUL) {
+            weight  = weight * pool.weight(closure);
+            closure = __float_as_int(pool.w[closure + 4]);
+        } else if (id == CL_ADD) {
+            ptr_stack[sp]      = __float_as_int(pool.w[closure + 2]);
+            weight_stack[sp++] = weight;
+            closure            = __float_as_int(pool.w[closure + 1]);
+        } else {
+            if (id == BACKGROUND_ID)
+                weight = weight * pool.weight(closure);
+            closure = 0;
+        }
+        if (closure == 0 && sp > 0) {
+            closure = ptr_stack[--sp];
+            weight  = weight_stack[sp];
+        }
+    }
+    return weight;
+}
+OSLD V3 eval_background(const RenderScene& S, V3 dir, V3 ddx, V3 ddy, int bounce)
+{
+    SG sg;
+    memset(&sg, 0, sizeof(SG));
+    sg.I    = dir;
+    sg.I_dx = ddx;
+    sg.I_dy = ddy;
+    if (bounce >= 0)
+        sg.raytype = bounce > 0 ? RAY_DIFFUSE : RAY_CAMERA;
+    ClosurePool pool;
+    pool.reset();
+    sg.pool = &pool;
+    sg.Ci   = 0;
+    osl_execute_shader(S.background_shader, sg);
+    return process_background_closure(pool, sg.Ci);
+}
+// texel (x, y) of the table -> direction with derivatives (Background::map)
+OSLD void bg_map(const RenderScene& S, float x, float y, V3& d, V3& ddx, V3& ddy)
+{
+    Df u     = mkd(x, 1.0f, 0.0f) * S.bg_invres;
+    Df v     = mkd(y, 0.0f, 1.0f) * S.bg_invres;
+    Df theta = u * (float)(2 * OSLD_PI);
+    float s, c;
+    fast_sincos(theta.val, &s, &c);
+    Df st = chain(theta, s, c), ct = chain(theta, c, -s);
+    Df cos_phi = 1.0f - 2.0f * v;
+    Df sin_phi = d_sqrt(1.0f - cos_phi * cos_phi);
+    Df X = sin_phi * ct, Y = sin_phi * st;
+    d   = mkv(X.val, Y.val, cos_phi.val);
+    ddx = mkv(X.dx, Y.dx, cos_phi.dx);
+    ddy = mkv(X.dy, Y.dy, cos_phi.dy);
+}
+OSLD V3 bg_eval(const RenderScene& S, V3 dir, float& pdf)
+{
+    const int res = S.bg_res;
+    float u = fast_atan2(dir.y, dir.x) * (float)(0.31830988618379067154 * 0.5f);
+    if (u < 0)
+        u++;
+    float v = (1 - dir.z) * 0.5f;
+    int x   = (int)(u * res);
+    x       = x < 0 ? 0 : (x >= res ? res - 1 : x);
+    int y   = (int)(v * res);
+    y       = y < 0 ? 0 : (y >= res ? res - 1 : y);
+    int i   = y * res + x;
+    float row_pdf = S.bg_rows[y] - (y > 0 ? S.bg_rows[y - 1] : 0.0f);
+    float col_pdf = S.bg_cols[i] - (x > 0 ? S.bg_cols[i - 1] : 0.0f);
+    pdf           = fmaxf(0.0f, row_pdf * col_pdf * S.bg_invjacobian);
+    return mkv(S.bg_values[3 * i], S.bg_values[3 * i + 1], S.bg_values[3 * i + 2]);
+}
+OSLD float bg_sample_cdf(const float* data, int n, float x, int* idx, float* pdf)
+{
+    const float* first = data;
+    int len            = n;
+    while (len != 0) {  // upper_bound
+        int l2         = len / 2;
+        const float* m = first + l2;
+        if (x < *m)
+            len = l2;
+        else {
+            first = m + 1;
+            len -= l2 + 1;
+        }
+    }
+    int i = (int)(first - data);
+    *idx  = i;
+    float scaled;
+    if (i == 0) {
+        *pdf   = data[0];
+        scaled = x / data[0];
+    } else {
+        *pdf   = data[i] - data[i - 1];
+        scaled = (x - data[i - 1]) / (data[i] - data[i - 1]);
+    }
+    return fminf(scaled, 0.99999994f);
+}
+OSLD V3 bg_sample(const RenderScene& S, float rx, float ry, V3& dir, float& pdf)
+{
+    const int res = S.bg_res;
+    float row_pdf, col_pdf;
+    int x, y;
+    ry = bg_sample_cdf(S.bg_rows, res, ry, &y, &row_pdf);
+    rx = bg_sample_cdf(S.bg_cols + (size_t)y * res, res, rx, &x, &col_pdf);
+    V3 ddx, ddy;
+    bg_map(S, (float)x + rx, (float)y + ry, dir, ddx, ddy);
+    pdf   = fmaxf(0.0f, row_pdf * col_pdf * S.bg_invjacobian);
+    int i = y * res + x;
+    return mkv(S.bg_values[3 * i], S.bg_values[3 * i + 1], S.bg_values[3 * i + 2]);
+}
+#endif  // OSLD_HAS_BACKGROUND
+
 // warp-aggregated append of a surviving path to the next queue
 OSLD void queue_push(int* queue, int* counter, int value, bool pred)
 {
@@ -787,6 +917,67 @@ extern "C" __global__ void rt_camera(const __grid_constant__ RenderLaunch L, flo
     out[3] = cx.x; out[4] = cx.y; out[5] = cx.z;
     out[6] = cy.x; out[7] = cy.y; out[8] = cy.z;
 }
+
+// Background::prepare (background.h:52-95) in four passes that keep the reference's
+// floating-point summation order: (1) shade every texel, (2) one thread per row runs the
+// sequential column prefix sum and normalises the row, (3) one thread runs the row prefix
+// sum, (4) every texel is divided by its pdf.
+#ifdef OSLD_HAS_BACKGROUND
+extern "C" __global__ void __launch_bounds__(128) rt_bg_eval(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    const int res = S.bg_res, n = res * res;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int y = i / res, x = i - y * res;
+        V3 d, ddx, ddy;
+        bg_map(S, (float)x + 0.5f, (float)y + 0.5f, d, ddx, ddy);
+        V3 c = eval_background(S, d, ddx, ddy, -1);
+        S.bg_values[3 * i] = c.x; S.bg_values[3 * i + 1] = c.y; S.bg_values[3 * i + 2] = c.z;
+    }
+}
+extern "C" __global__ void __launch_bounds__(128) rt_bg_rows(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    const int res = S.bg_res;
+    for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < res; y += gridDim.x * blockDim.x) {
+        float* cols = S.bg_cols + (size_t)y * res;
+        const float* vals = S.bg_values + (size_t)3 * y * res;
+        float run = 0.0f;
+        for (int x = 0; x < res; ++x) {
+            float m = fmaxf(fmaxf(vals[3 * x], vals[3 * x + 1]), vals[3 * x + 2]);
+            run     = m + ((x > 0) ? run : 0.0f);
+            cols[x] = run;
+        }
+        S.bg_rows[y] = run;  // row total; the prefix sum over rows runs in rt_bg_finish
+        if (run > 0)
+            for (int x = 0; x < res; ++x)
+                cols[x] /= run;
+    }
+}
+extern "C" __global__ void rt_bg_finish(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    if (blockIdx.x != 0 || threadIdx.x != 0)
+        return;
+    const int res = S.bg_res;
+    for (int y = 1; y < res; ++y)
+        S.bg_rows[y] = S.bg_rows[y] + S.bg_rows[y - 1];
+    for (int y = 0; y < res; ++y)
+        S.bg_rows[y] /= S.bg_rows[res - 1];
+}
+extern "C" __global__ void __launch_bounds__(256) rt_bg_scale(const __grid_constant__ RenderLaunch L)
+{
+    const RenderScene& S = L.S;
+    const int res = S.bg_res, n = res * res;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int y = i / res, x = i - y * res;
+        float row_pdf = S.bg_rows[y] - (y > 0 ? S.bg_rows[y - 1] : 0.0f);
+        float col_pdf = S.bg_cols[i] - (x > 0 ? S.bg_cols[i - 1] : 0.0f);
+        float dv      = row_pdf * col_pdf * S.bg_invjacobian;
+        S.bg_values[3 * i] /= dv; S.bg_values[3 * i + 1] /= dv; S.bg_values[3 * i + 2] /= dv;
+    }
+}
+#endif  // OSLD_HAS_BACKGROUND
 
 // one thread per path slot: camera sample -> initial path state
 extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_constant__ RenderLaunch L)
@@ -901,8 +1092,23 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
             float out_rough  = q3.w;
             u32 seed_now     = (u32)__float_as_int(q5.w);
             do {
-                if (ht == OSLD_INF)
-                    break;  // miss (no background in these scenes)
+                if (ht == OSLD_INF) {
+                    // miss: background (simpleraytracer.cpp:980-996)
+#ifdef OSLD_HAS_BACKGROUND
+                    if (S.background_shader >= 0) {
+                        if (b > 0 && S.bg_values) {
+                            float bg_pdf = 0;
+                            V3 bg        = bg_eval(S, r.direction, bg_pdf);
+                            path_radiance = path_radiance
+                                            + path_weight * bg * power_heuristic<WEIGHT_WEIGHT>(bsdf_pdf, bg_pdf);
+                        } else {
+                            path_radiance = path_radiance
+                                            + path_weight * eval_background(S, r.direction, mkv(0.0f), mkv(0.0f), b);
+                        }
+                    }
+#endif
+                    break;
+                }
                 SG sg;
                 ClosurePool pool;
                 globals_from_hit(S, sg, r, ht, hid, hu, hv);
@@ -949,6 +1155,21 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
                 V3 s          = sampler.get();
                 seed_now      = sampler.seed;
                 const float xi = s.x, yi = s.y, zi = s.z;
+#ifdef OSLD_HAS_BACKGROUND
+                if (S.bg_values) {
+                    // one shadow ray towards an importance-sampled background direction
+                    V3 bg_dir;
+                    float bg_pdf = 0;
+                    V3 bg        = bg_sample(S, xi, yi, bg_dir, bg_pdf);
+                    BSample bs   = bsdf_eval(bsdf, wo, bg_dir);
+                    V3 contrib   = path_weight * bs.weight * bg * power_heuristic<WEIGHT_WEIGHT>(bg_pdf, bs.pdf);
+                    if ((contrib.x + contrib.y + contrib.z) > 0) {
+                        Hit sh = scene_intersect(S, sg.P, bg_dir, OSLD_INF, (unsigned)hid, ~0u);
+                        if (sh.t == OSLD_INF)
+                            path_radiance = path_radiance + contrib;
+                    }
+                }
+#endif
                 if (nlights > 0) {
                     const float light_pick_pdf = 1.0f / nlights;
                     float xl = xi * nlights;

@@ -1334,7 +1334,7 @@ generate_cuda(Group& g)
 
 // All material groups of a scene + the wavefront integrator in one module.
 std::string
-generate_cuda_render(std::vector<Group*>& groups)
+generate_cuda_render(std::vector<Group*>& groups, bool has_background)
 {
     std::ostringstream out;
     out << "// generated by libosl_b200: render module with " << groups.size() << " material group(s)\n";
@@ -1358,6 +1358,8 @@ generate_cuda_render(std::vector<Group*>& groups)
         glossy |= gp->uses_glossy_lobes;
     if (glossy)
         out << "#define OSLD_GLOSSY_LOBES 1\n";
+    if (has_background)
+        out << "#define OSLD_HAS_BACKGROUND 1\n";
     out << "#include \"osl_b200_render.cuh\"\n";
     return out.str();
 }

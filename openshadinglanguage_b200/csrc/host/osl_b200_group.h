@@ -152,6 +152,6 @@ std::string generate_cuda(Group& g);
 // Emit one CUDA module holding every material group of a scene (namespaces
 // mat0, mat1, ...), the shader dispatch switch and the wavefront integrator
 // kernels of csrc/device/osl_b200_render.cuh.
-std::string generate_cuda_render(std::vector<Group*>& groups);
+std::string generate_cuda_render(std::vector<Group*>& groups, bool has_background = false);
 
 }  // namespace oslb200

@@ -44,6 +44,11 @@ struct DevScene {
     int xres, yres;
     int aa, max_bounces, rr_depth, no_jitter, show_globals;
     int background_shader, background_resolution;
+    float* bg_values;
+    float* bg_rows;
+    float* bg_cols;
+    int bg_res;
+    float bg_invres, bg_invjacobian;
 };
 enum { PATH_QUADS = 8 };  // 8 x float4 = 128 B of state per path (OSLD_PATH_QUADS)
 struct DevLaunch {
@@ -58,8 +63,12 @@ struct DevLaunch {
 };
 
 const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_intersect", "rt_sort_count", "rt_sort_scan",
-                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve" };
-enum { K_CAMERA, K_GENERATE, K_INTERSECT, K_SORT_COUNT, K_SORT_SCAN, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE, K_N };
+                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve",
+                          // only in modules generated for a scene with a background
+                          "rt_bg_eval", "rt_bg_rows", "rt_bg_finish", "rt_bg_scale" };
+enum { K_CAMERA, K_GENERATE, K_INTERSECT, K_SORT_COUNT, K_SORT_SCAN, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE,
+       K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE, K_N };
+enum { K_FIRST_BG = K_BG_EVAL };
 
 }  // namespace
 
@@ -115,8 +124,8 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
         return set_error(B200_ERR_INVALID, "b200_render_create: bad arguments");
     if (nmaterials > 62)
         return set_error(B200_ERR_UNSUPPORTED, "b200_render_create: more than 62 materials not supported yet");
-    if (scene->background_shader >= 0)
-        return set_error(B200_ERR_UNSUPPORTED, "b200_render_create: background shaders are not supported yet");
+    if (scene->background_shader >= nmaterials)
+        return set_error(B200_ERR_INVALID, "b200_render_create: background_shader is not a material index");
     *out = nullptr;
     std::unique_ptr<b200_render> R(new b200_render);
     auto opt = parse_opts(options);
@@ -160,7 +169,7 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
             gs.push_back(g.get());
             R->groups.push_back(std::move(g));
         }
-        R->source = generate_cuda_render(gs);
+        R->source = generate_cuda_render(gs, scene->background_shader >= 0);
     } catch (const std::exception& e) {
         return set_error(B200_ERR_COMPILE, e.what());
     }
@@ -233,7 +242,8 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
     CUresult_ cr = drv.cuModuleLoadData(&d.mod, r->cubin.data());
     if (cr != 0)
         return set_error(B200_ERR_CUDA, "cuModuleLoadData(render): " + drv.err(cr));
-    for (int k = 0; k < K_N; ++k) {
+    const bool has_bg = r->host.background_shader >= 0;
+    for (int k = 0; k < (has_bg ? (int)K_N : (int)K_FIRST_BG); ++k) {
         cr = drv.cuModuleGetFunction(&d.fn[k], d.mod, KERNELS[k]);
         if (cr != 0)
             return set_error(B200_ERR_CUDA, std::string("cuModuleGetFunction(") + KERNELS[k] + "): " + drv.err(cr));
@@ -302,6 +312,40 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
     memcpy(S.cx, cam + 3, 12);
     memcpy(S.cy, cam + 6, 12);
     count_launches(1);
+    // background importance table (SimpleRaytracer::prepare_render, simpleraytracer.cpp:1232-1249):
+    // the background shader runs on the device at every texel, the CDFs are built there too
+    if (has_bg && h.background_resolution > 0) {
+        int res = h.background_resolution < 32 ? 32 : h.background_resolution;
+        size_t n = (size_t)res * res;
+        bool okb = cudaMalloc(&S.bg_values, 3 * n * sizeof(float)) == cudaSuccess
+                   && cudaMalloc(&S.bg_cols, n * sizeof(float)) == cudaSuccess
+                   && cudaMalloc(&S.bg_rows, res * sizeof(float)) == cudaSuccess;
+        if (S.bg_values) d.allocs.push_back(S.bg_values);
+        if (S.bg_cols) d.allocs.push_back(S.bg_cols);
+        if (S.bg_rows) d.allocs.push_back(S.bg_rows);
+        if (!okb) {
+            free_dev(d);
+            return set_error(B200_ERR_CUDA, "cudaMalloc(background table) failed");
+        }
+        S.bg_res         = res;
+        S.bg_invres      = 1.0f / res;
+        S.bg_invjacobian = res * res / float(4 * M_PI);
+        L.S              = S;
+        void* bargs[]    = { &L };
+        const int ks[4]  = { K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE };
+        for (int i = 0; i < 4 && cr == 0; ++i) {
+            int block = (ks[i] == K_BG_SCALE) ? 256 : (ks[i] == K_BG_FINISH ? 32 : 128);
+            long long work = ks[i] == K_BG_ROWS ? res : (ks[i] == K_BG_FINISH ? 1 : (long long)n);
+            int grid = (int)std::min<long long>((work + block - 1) / block, (long long)d.sms * 16);
+            cr       = drv.cuLaunchKernel(d.fn[ks[i]], grid < 1 ? 1 : grid, 1, 1, block, 1, 1, 0, nullptr, bargs, nullptr);
+            count_launches(1);
+        }
+        if (cr != 0 || cudaDeviceSynchronize() != cudaSuccess) {
+            free_dev(d);
+            return set_error(B200_ERR_CUDA, "background table kernels failed: "
+                                                + (cr ? drv.err(cr) : std::string(cudaGetErrorString(cudaGetLastError()))));
+        }
+    }
     r->devs[device] = d;
     *out            = &r->devs[device];
     return B200_OK;

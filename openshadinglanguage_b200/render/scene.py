@@ -360,7 +360,9 @@ def load_scene(xmlfile):
             else:
                 raise FileNotFoundError("Unable to find model file %s" % fn)
         elif node.tag == "Background":
-            sc.background_resolution = int(a.get("resolution", 0))
+            # simpleraytracer.h:125: the importance table defaults to 1024^2 when a
+            # background is present; resolution="0" turns importance sampling off
+            sc.background_resolution = int(a.get("resolution", 1024))
             sc.background_shader = len(sc.materials) - 1
         elif node.tag == "ShaderGroup":
             text = a.get("commands", node.text or "")

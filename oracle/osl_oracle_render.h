@@ -769,10 +769,168 @@ inline void globals_from_hit(const RenderScene& S, SG& sg, const Ray& r, float t
 
 typedef void (*ShaderFn)(SG& sg);
 
+// process_background_closure (shading.cpp:1709-1746): walks the tree and returns the
+// weight it holds when the walk ends (the last visited branch), as the reference does.
+inline V3 process_background_closure(const Clos* closure)
+{
+    if (!closure)
+        return V3(0.0f);
+    const int STACK_SIZE = 16;
+    int stack_idx        = 0;
+    const Clos* ptr_stack[STACK_SIZE];
+    V3 weight_stack[STACK_SIZE];
+    V3 weight(1.0f);
+    while (closure) {
+        switch (closure->id) {
+        case CL_MUL:
+            weight  = weight * ((const ClosMul*)closure)->weight;
+            closure = ((const ClosMul*)closure)->closure;
+            break;
+        case CL_ADD:
+            ptr_stack[stack_idx]      = ((const ClosAdd*)closure)->b;
+            weight_stack[stack_idx++] = weight;
+            closure                   = ((const ClosAdd*)closure)->a;
+            break;
+        case BACKGROUND_ID:
+            weight  = weight * ((const ClosComp*)closure)->w;
+            closure = nullptr;
+            break;
+        default:
+            // the reference's switch has no default: an unexpected component would spin
+            // forever there; treat it as the end of this branch
+            closure = nullptr;
+            break;
+        }
+        if (closure == nullptr && stack_idx > 0) {
+            closure = ptr_stack[--stack_idx];
+            weight  = weight_stack[stack_idx];
+        }
+    }
+    return weight;
+}
+
+// Importance table over the sphere of directions (background.h:38-276)
+struct Background {
+    std::vector<V3> values;
+    std::vector<float> rows, cols;
+    int res = -1;
+    float invres = 0.0f, invjacobian = 0.0f;
+
+    Dv map(float x, float y) const
+    {
+        Df u     = Df(x, 1, 0) * invres;
+        Df v     = Df(y, 0, 1) * invres;
+        Df theta = u * float(2 * M_PI);
+        float s, c;
+        fast_sincos(theta.val, &s, &c);
+        Df st = dualfunc(theta, s, c), ct = dualfunc(theta, c, -s);
+        Df cos_phi = 1.0f - 2.0f * v;
+        Df sin_phi = d_sqrt(1.0f - cos_phi * cos_phi);
+        return make_dv(sin_phi * ct, sin_phi * st, cos_phi);
+    }
+    template<class F> void prepare(int resolution, F cb)
+    {
+        res = resolution;
+        if (res < 32)
+            res = 32;
+        invres      = 1.0f / res;
+        invjacobian = res * res / float(4 * M_PI);
+        values.assign((size_t)res * res, V3(0.0f));
+        rows.assign(res, 0.0f);
+        cols.assign((size_t)res * res, 0.0f);
+        for (int y = 0, i = 0; y < res; y++) {
+            for (int x = 0; x < res; x++, i++) {
+                values[i] = cb(map(x + 0.5f, y + 0.5f));
+                cols[i]   = std::max(std::max(values[i].x, values[i].y), values[i].z) + ((x > 0) ? cols[i - 1] : 0.0f);
+            }
+            rows[y] = cols[i - 1] + ((y > 0) ? rows[y - 1] : 0.0f);
+            if (cols[i - 1] > 0)
+                for (int x = 0; x < res; x++)
+                    cols[i - res + x] /= cols[i - 1];
+        }
+        for (int y = 0; y < res; y++)
+            rows[y] /= rows[res - 1];
+        for (int y = 0, i = 0; y < res; y++) {
+            float row_pdf = rows[y] - (y > 0 ? rows[y - 1] : 0.0f);
+            for (int x = 0; x < res; x++, i++) {
+                float col_pdf = cols[i] - (x > 0 ? cols[i - 1] : 0.0f);
+                values[i]     = values[i] / (row_pdf * col_pdf * invjacobian);
+            }
+        }
+    }
+    V3 eval(const V3& dir, float& pdf) const
+    {
+        float u = fast_atan2(dir.y, dir.x) * float(M_1_PI * 0.5f);
+        if (u < 0)
+            u++;
+        float v = (1 - dir.z) * 0.5f;
+        int x   = (int)(u * res);
+        if (x < 0) x = 0;
+        else if (x >= res) x = res - 1;
+        int y = (int)(v * res);
+        if (y < 0) y = 0;
+        else if (y >= res) y = res - 1;
+        int i         = y * res + x;
+        float row_pdf = rows[y] - (y > 0 ? rows[y - 1] : 0.0f);
+        float col_pdf = cols[i] - (x > 0 ? cols[i - 1] : 0.0f);
+        pdf           = std::max(0.0f, row_pdf * col_pdf * invjacobian);
+        return values[i];
+    }
+    static float sample_cdf(const float* data, unsigned n, float x, unsigned* idx, float* pdf)
+    {
+        // upper_bound (background.h:14-34)
+        const float* first = data;
+        int len            = (int)n;
+        while (len != 0) {
+            int l2         = len / 2;
+            const float* m = first + l2;
+            if (x < *m)
+                len = l2;
+            else {
+                first = m + 1;
+                len -= l2 + 1;
+            }
+        }
+        *idx = (unsigned)(first - data);
+        float scaled_sample;
+        if (*idx == 0) {
+            *pdf          = data[0];
+            scaled_sample = x / data[0];
+        } else {
+            *pdf          = data[*idx] - data[*idx - 1];
+            scaled_sample = (x - data[*idx - 1]) / (data[*idx] - data[*idx - 1]);
+        }
+        return std::min(scaled_sample, 0.99999994f);
+    }
+    V3 sample(float rx, float ry, Dv& dir, float& pdf) const
+    {
+        float row_pdf, col_pdf;
+        unsigned x, y;
+        ry  = sample_cdf(rows.data(), res, ry, &y, &row_pdf);
+        rx  = sample_cdf(cols.data() + (size_t)y * res, res, rx, &x, &col_pdf);
+        dir = map(x + rx, y + ry);
+        pdf = std::max(0.0f, row_pdf * col_pdf * invjacobian);
+        return values[(size_t)y * res + x];
+    }
+};
+
 struct Renderer {
     const RenderScene& S;
     const ShaderFn* shaders;
     Ctx* ctx;
+    const Background* background = nullptr;   // importance table, when S.background_resolution > 0
+
+    // SimpleRaytracer::eval_background (simpleraytracer.cpp:937-954)
+    V3 eval_background(const Dv& dir, int bounce, ClosurePool& pool) const
+    {
+        SG sg;
+        std::memset((void*)&sg, 0, sizeof(SG));
+        sg.I = dir;
+        if (bounce >= 0)
+            sg.raytype = bounce > 0 ? RAY_DIFFUSE : RAY_CAMERA;
+        execute(S.background_shader, sg, pool);
+        return process_background_closure(sg.Ci);
+    }
 
     void execute(int shaderID, SG& sg, ClosurePool& pool) const
     {
@@ -795,8 +953,19 @@ struct Renderer {
         for (int b = 0; b <= S.max_bounces; b++) {
             SG sg;
             Intersection hit = scene_intersect(S, r, inf, (unsigned)prev_id);
-            if (hit.t == inf)
-                break;  // no background in the restated configs
+            if (hit.t == inf) {
+                if (S.background_shader >= 0) {
+                    if (b > 0 && background) {
+                        float bg_pdf = 0;
+                        V3 bg        = background->eval(r.direction, bg_pdf);
+                        path_radiance = path_radiance
+                                        + path_weight * bg * power_heuristic<WEIGHT_WEIGHT>(bsdf_pdf, bg_pdf);
+                    } else {
+                        path_radiance = path_radiance + path_weight * eval_background(Dv(r.direction), b, pool);
+                    }
+                }
+                break;
+            }
             globals_from_hit(S, sg, r, hit.t, hit.id, hit.u, hit.v);
             if (S.show_globals) {
                 V3 v = sg.Ng;
@@ -831,6 +1000,20 @@ struct Renderer {
             result.bsdf.prepare(-sg.I.val, path_weight, b >= S.rr_depth);
             V3 s     = sampler.get();
             float xi = s.x, yi = s.y, zi = s.z;
+            if (background) {
+                // one shadow ray towards an importance-sampled background direction
+                Dv bg_dir;
+                float bg_pdf = 0;
+                V3 bg        = background->sample(xi, yi, bg_dir, bg_pdf);
+                BSample bs   = result.bsdf.eval(-sg.I.val, bg_dir.val);
+                V3 contrib   = path_weight * bs.weight * bg * power_heuristic<WEIGHT_WEIGHT>(bg_pdf, bs.pdf);
+                if ((contrib.x + contrib.y + contrib.z) > 0) {
+                    Ray shadow_ray { sg.P.val, bg_dir.val, radius, 0, 0, RAY_SHADOW };
+                    Intersection sh = scene_intersect(S, shadow_ray, inf, hit.id);
+                    if (sh.t == inf)
+                        path_radiance = path_radiance + contrib;
+                }
+            }
             if (nlights > 0) {
                 const float light_pick_pdf = 1.0f / nlights;
                 float xl = xi * nlights;

@@ -1255,10 +1255,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 RENDER_TAIL = r"""
+static const Background* g_background = nullptr;
 static void oracle_render_rows(const RenderScene* S, int y0, int y1, float* out, std::string* pf)
 {
     Ctx ctx{pf};
     Renderer R{*S, g_shaders, &ctx};
+    R.background = g_background;
     for (int y = y0; y < y1; ++y)
         for (int x = 0; x < S->xres; ++x) {
             V3 c = R.antialias_pixel(x, y);
@@ -1271,6 +1273,16 @@ extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
     RenderScene S1 = *S0;
     camera_finalize(S1);
     const RenderScene* S = &S1;
+    // background importance table (simpleraytracer.cpp:1232-1249)
+    Background bg;
+    g_background = nullptr;
+    if (S->background_resolution > 0 && S->background_shader >= 0) {
+        Ctx ctx{nullptr};
+        Renderer R{*S, g_shaders, &ctx};
+        ClosurePool pool;
+        bg.prepare(S->background_resolution, [&](const Dv& d) { return R.eval_background(d, -1, pool); });
+        g_background = &bg;
+    }
     // scanline-parallel like the reference (parallel_for_chunked, simpleraytracer.cpp:1428)
     if (nthreads <= 1) { oracle_render_rows(S, 0, S->yres, out, nullptr); return; }
     std::vector<std::thread> th;

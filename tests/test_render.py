@@ -21,7 +21,9 @@ SCENES = os.path.join(helpers.GOLDEN, "scenes")
 # case: (scene, xres, yres, aa) — the command lines of testsuite/<case>/run.py
 CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny.xml", 128, 128, 8),
          "render-veachmis": ("veach.xml", 160, 120, 16),     # phong lobes, max_bounces 1, 4 lights
-         "render-ward": ("ward.xml", 160, 120, 4)}            # anisotropic ward lobes
+         "render-ward": ("ward.xml", 160, 120, 4),            # anisotropic ward lobes
+         # white sphere in a uniform background: importance table (1024^2), MIS'd background NEE
+         "render-furnace-diffuse": ("furnace.xml", 160, 120, 20)}
 # scenes of this repo (no reference golden image): the oracle restates the lobes
 # from shading.cpp and the device must equal the oracle.  render-microfacet itself
 # needs an HDR environment texture, which is outside this path.

@@ -60,6 +60,7 @@ SHADERS = {
     "phong": "render-veachmis/phong.osl",
     "ward": "render-ward/ward.osl",
     "glossy_glass": "render-microfacet/glossy_glass.osl",
+    "furnace": "render-furnace-diffuse/furnace.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -71,6 +72,7 @@ SCENES = {
     "bunny.obj": "render-bunny/bunny.obj",
     "veach.xml": "render-veachmis/veach.xml",
     "ward.xml": "render-ward/scene.xml",
+    "furnace.xml": "render-furnace-diffuse/scene.xml",
 }
 # golden renders (half-float EXR in the reference; stored as float16 npz)
 RENDERS = {
@@ -78,6 +80,7 @@ RENDERS = {
     "render-bunny": "render-bunny/ref/out.exr",
     "render-veachmis": "render-veachmis/ref/out.exr",
     "render-ward": "render-ward/ref/out.exr",
+    "render-furnace-diffuse": "render-furnace-diffuse/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
