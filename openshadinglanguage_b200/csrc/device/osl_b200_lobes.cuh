@@ -233,6 +233,150 @@ OSLD BSample mf_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
     return bs_make(wi, mkv(Ft * out), pdf, rough);
 }
 
+// ---- libbsdl lobes behind testrender's BSDL_WRAP (shading.cpp:73-115) ----------------------
+// BSDL_WRAP builds BsdfGlobals(wo, N, N, backfacing, path_roughness, 1, 0); the lobe frame is
+// Frame(visible_normal(N)) (libbsdl/include/BSDL/bsdf_impl.h:48-76, tools.h:459-510) and
+// eval / sample run in that local frame.  The frame's Z is kept in l.N.
+OSLD float bsdl_max_abs_xyz(V3 v) { return fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z))); }
+OSLD float bsdl_clamp(float x, float a, float b)
+{
+    float m = fmaxf(x, a);
+    return m < b ? m : b;
+}
+OSLD V3 bsdl_visible_normal(V3 wo, V3 Ngf, V3 N)
+{
+    if (dot3(wo, N) > 0.0f)
+        return N;
+    V3 V = cross3(wo, N);
+    if (bsdl_max_abs_xyz(V) < 1e-4f) {
+        V = cross3(wo, Ngf);
+        if (bsdl_max_abs_xyz(V) < 1e-4f) {
+            const float s = copysignf(1.0f, wo.z);
+            const float a = -1.0f / (s + wo.z);
+            V             = mkv(wo.x * wo.y * a, s + wo.y * wo.y * a, -wo.y);
+        } else
+            V = vnormalized(V);
+    } else
+        V = vnormalized(V);
+    return vnormalized(cross3(V, wo) + 1e-4f * wo);
+}
+OSLD void lobe_set_bsdl_frame(Lobe& l, V3 wo)
+{
+    TangentFrame f = frame_from_normal(bsdl_visible_normal(wo, l.N, l.N));
+    l.fu           = f.u;
+    l.fv           = f.v;
+    l.N            = f.w;
+}
+// tools.h:200-278
+OSLD V3 bsdl_sample_cos_hemisphere(float randu, float randv)
+{
+    const float a = 2 * randu - 1, qa = fabsf(a);
+    const float b = 2 * randv - 1, qb = fabsf(b);
+    const float rad = qa > qb ? qa : qb;
+    const float phi = qa > qb ? qb / qa : ((qa == qb) ? 1.0f : 2 - qa / qb);
+    const float x2  = phi * phi;
+    float cp = 0.01578646f + -0.00029826362f * x2;
+    cp       = -0.30837047f + cp * x2;
+    cp       = 0.99998736f + cp * x2;
+    float sp = 0.0024843954015523195266723632812500f + -0.0000341485538228880614042282104492f * x2;
+    sp       = -0.0807407423853874206542968750000000f + sp * x2;
+    sp       = 0.7853975892066955566406250000000000f + sp * x2;
+    sp       = sp * phi;
+    return mkv(copysignf(rad * cp, a), copysignf(rad * sp, b), sqrtf(1 - rad * rad));
+}
+// mtx::OrenNayarDiffuseLobe::eval_impl without energy compensation (OREN_NAYAR_ID maps to
+// {N, albedo 1, sigma, energy_compensation false}, shading.cpp:1496-1503;
+// MTX/bsdf_oren_nayar_diffuse_impl.h:40-62).  sigma (clamped) is kept in l.ax.
+OSLD BSample oren_nayar_eval_local(const Lobe& l, V3 wo, V3 wi)
+{
+    const float ONEOVERPI = 1 / (float)OSLD_PI;
+    const float cosNI = bsdl_clamp(wi.z, 0.0f, 1.0f);
+    const float cosNO = bsdl_clamp(wo.z, 0.0f, 1.0f);
+    if (cosNI <= 0.0f || cosNO <= 0.0f)
+        return bs_null();
+    const float cosIO = bsdl_clamp(dot3(wo, wi), -1.0f, 1.0f);
+    const float s     = cosIO - cosNI * cosNO;
+    const float pdf   = cosNI * ONEOVERPI;
+    if (!l.refract) {
+        const float s2    = sqr_(l.ax);
+        const float A     = 1.0f - 0.50f * s2 / (s2 + 0.33f);
+        const float B     = 0.45f * s2 / (s2 + 0.09f);
+        const float stinv = s > 0.0f ? s / fmaxf(cosNI, cosNO) : 0.0f;
+        const float f_ss  = A + B * stinv;
+        return bs_make(wi, l.albedo * f_ss, pdf, 1.0f);
+    }
+    // energy-preserving Oren-Nayar (MTX/bsdf_oren_nayar_diffuse_impl.h:24-37, 63-93)
+    const float PI_F          = (float)OSLD_PI;
+    const float constant1_FON = 0.5f - 2.0f / (3.0f * PI_F);
+    const float constant2_FON = 2.0f / 3.0f - 28.0f / (15.0f * PI_F);
+    const float sigma         = l.ax;
+    const float AF            = 1.0f / (1.0f + constant1_FON * sigma);
+    const float BF            = sigma * AF;
+    float EF[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float mu = k == 0 ? cosNO : cosNI;
+        const float Si = sqrtf(fmaxf(0.0f, 1.0f - mu * mu));
+        const float G  = Si * (fast_acos(mu) - Si * mu)
+                        + 2.0f * ((Si / fmaxf(mu, 1e-7f)) * (1.0f - Si * Si * Si) - Si) * (1.0f / 3.0f);
+        EF[k] = AF + (BF * ONEOVERPI) * G;
+    }
+    const float stinv = s > 0.0f ? s / fmaxf(cosNI, cosNO) : s;
+    const float f_ss  = AF * (1.0f + sigma * stinv);
+    const float avgEF = AF * (1.0f + constant2_FON * sigma);
+    const float om    = fmaxf(0.0f, 1.0f - avgEF);
+    const V3 a        = l.albedo;
+    const V3 rho_ms   = mkv(sqr_(a.x) * avgEF / (1 - a.x * om), sqr_(a.y) * avgEF / (1 - a.y * om),
+                            sqr_(a.z) * avgEF / (1 - a.z * om));
+    const float f_ms = fmaxf(1e-7f, 1.0f - EF[0]) * fmaxf(1e-7f, 1.0f - EF[1]) / fmaxf(1e-7f, 1.0f - avgEF);
+    return bs_make(wi, l.albedo * f_ss + rho_ms * f_ms, pdf, 1.0f);
+}
+// mtx::BurleyDiffuseLobe (MTX/bsdf_burley_diffuse_impl.h:24-58)
+OSLD float burley_fresnel(float cos_theta, float F90)
+{
+    const float x  = bsdl_clamp(1.0f - cos_theta, 0.0f, 1.0f);
+    const float x2 = x * x;
+    float f        = bsdl_clamp(x2 * x2 * x, 0.0f, 1.0f);
+    return (1 - f) * 1.0f + f * F90;
+}
+OSLD BSample burley_eval_local(const Lobe& l, V3 wo, V3 wi)
+{
+    const float ONEOVERPI = 1 / (float)OSLD_PI;
+    if (wo.z <= 0.0f || wi.z <= 0.0f)
+        return bs_null();
+    const V3 H = wi + wo;
+    if (bsdl_max_abs_xyz(H) < 1e-4f)
+        return bs_null();
+    const V3 Hn       = vnormalized(H);
+    const float cosHI = bsdl_clamp(dot3(wi, Hn), 0.0f, 1.0f);
+    const float cosNO = bsdl_clamp(wo.z, 0.0f, 1.0f);
+    const float cosNI = bsdl_clamp(wi.z, 0.0f, 1.0f);
+    const float F90   = 0.5f + 2.0f * l.ax * sqr_(cosHI);
+    const float refL  = burley_fresnel(cosNI, F90);
+    const float refV  = burley_fresnel(cosNO, F90);
+    return bs_make(wi, l.albedo * (refL * refV), cosNI * ONEOVERPI, 1.0f);
+}
+OSLD BSample bsdl_diffuse_eval_local(const Lobe& l, V3 wo, V3 wi)
+{
+    return l.type == LOBE_BSDL_BURLEY ? burley_eval_local(l, wo, wi) : oren_nayar_eval_local(l, wo, wi);
+}
+// BSDL_WRAP::eval / ::sample (shading.cpp:88-103)
+OSLD BSample bsdl_diffuse_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    BSample s = bsdl_diffuse_eval_local(l, frame_tolocal(l, wo), frame_tolocal(l, wi));
+    s.wi      = wi;
+    return s;
+}
+OSLD BSample bsdl_diffuse_sample(const Lobe& l, V3 wo, float rx, float ry)
+{
+    const V3 wo_l = frame_tolocal(l, wo);
+    BSample s     = bs_null();
+    if (!(wo_l.z <= 0.0f))
+        s = bsdl_diffuse_eval_local(l, wo_l, bsdl_sample_cos_hemisphere(rx, ry));
+    s.wi = frame_toworld(l, s.wi);
+    return s;
+}
+
 // ---- Phong (exponent kept in l.ax) -------------------------------------------------------
 OSLD BSample phong_eval(const Lobe& l, V3 wo, V3 wi)
 {

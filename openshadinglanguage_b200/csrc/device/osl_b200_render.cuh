@@ -297,16 +297,19 @@ OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
 }
 #define OSLD_INF __int_as_float(0x7f800000)
 enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
-       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET };
+       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY };
 struct Lobe {
     int type;
     V3 N;
     float eta;
 #ifdef OSLD_GLOSSY_LOBES
     // phong: ax = exponent.  ward / microfacet: tangent frame (fu, fv, N) and roughnesses.
+    // libbsdl diffuse lobes: frame in (fu, fv, N), roughness in ax, the
+    // energy-compensation flag in refract, albedo below.
     V3 fu, fv;
     float ax, ay;
     int refract, ggx;
+    V3 albedo;
 #endif
 };
 }  // namespace osld
@@ -319,6 +322,8 @@ OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
 #ifdef OSLD_GLOSSY_LOBES
     if (l.type == LOBE_MICROFACET)
         return mf_albedo(l, wo);
+    if (l.type == LOBE_BSDL_OREN_NAYAR || l.type == LOBE_BSDL_BURLEY)
+        return l.albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
 #endif
     if (l.type == LOBE_REFLECTION) {
         float cosNO = dot3(l.N, wo);
@@ -341,6 +346,8 @@ OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
         return ward_eval(l, wo, wi);
     if (l.type == LOBE_MICROFACET)
         return mf_eval(l, wo, wi);
+    if (l.type == LOBE_BSDL_OREN_NAYAR || l.type == LOBE_BSDL_BURLEY)
+        return bsdl_diffuse_eval(l, wo, wi);
 #endif
     return bs_null();
 }
@@ -371,6 +378,8 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
     case LOBE_PHONG: return phong_sample(l, wo, rx, ry);
     case LOBE_WARD: return ward_sample(l, wo, rx, ry);
     case LOBE_MICROFACET: return mf_sample(l, wo, rx, ry, rz);
+    case LOBE_BSDL_OREN_NAYAR:
+    case LOBE_BSDL_BURLEY: return bsdl_diffuse_sample(l, wo, rx, ry);
 #endif
     default: return bs_make(-wo, mkv(1.0f), OSLD_INF, 0.0f);
     }
@@ -433,7 +442,8 @@ OSLD BSample bsdf_sample(const CompositeBSDF& B, V3 wo, float rx, float ry, floa
 }
 
 // closure tree -> emission + lobes (16-deep explicit stack, weights root->leaf)
-OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only)
+OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only,
+                          V3 wo = mkv(0.0f, 0.0f, 1.0f))
 {
     int ptr_stack[16];
     V3 weight_stack[16];
@@ -468,6 +478,23 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                 case TRANSPARENT_ID:
                 case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
 #ifdef OSLD_GLOSSY_LOBES
+                case OREN_NAYAR_ID:
+                    // -> MxOrenNayarDiffuse{N, albedo 1, sigma, no energy compensation}
+                    l.type    = LOBE_BSDL_OREN_NAYAR;
+                    l.ax      = bsdl_clamp(q[3], 0.0f, 1.0f);
+                    l.albedo  = mkv(1.0f);
+                    l.refract = 0;
+                    lobe_set_bsdl_frame(l, wo);
+                    break;
+                case MX_OREN_NAYAR_DIFFUSE_ID:
+                case MX_BURLEY_DIFFUSE_ID:
+                    // params: N, albedo, roughness [, energy_compensation] (libbsdl Data structs)
+                    l.type    = id == MX_BURLEY_DIFFUSE_ID ? LOBE_BSDL_BURLEY : LOBE_BSDL_OREN_NAYAR;
+                    l.albedo  = mkv(q[3], q[4], q[5]);
+                    l.ax      = bsdl_clamp(q[6], 0.0f, 1.0f);
+                    l.refract = (id == MX_OREN_NAYAR_DIFFUSE_ID) ? (__float_as_int(q[7]) != 0) : 0;
+                    lobe_set_bsdl_frame(l, wo);
+                    break;
                 case PHONG_ID:
                     l.type = LOBE_PHONG;
                     l.ax   = q[3];
@@ -1136,7 +1163,7 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
                 CompositeBSDF bsdf;
                 bsdf.num               = 0;
                 const bool last_bounce = b == S.max_bounces;
-                process_closure(pool, sg.Ci, Le, bsdf, last_bounce);
+                process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I);
                 const int nlights = S.nlightprims;
                 float k           = 1;
                 if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {

@@ -893,15 +893,16 @@ Gen::emit_op(const Opcode& op)
             unsupported("closure with a non-constant name");
         std::string cname = A((int)i).svals.empty() ? "" : A((int)i).svals[0];
         ++i;
-        std::vector<int> pos;
-        for (; i < op.args.size(); ++i)
-            pos.push_back(op.args[i]);
         struct Reg {
             const char* name;
             int nparams;
             const char* id;
+            const char* keys;  // keyword parameters "name:i,name:f" in slot order after the positional words
         };
         static const Reg regs[] = {
+            // MaterialX closures registered from libbsdl lobes (BSDLtoOSL, shading.cpp:156-182)
+            { "oren_nayar_diffuse_bsdf", 3, "MX_OREN_NAYAR_DIFFUSE_ID", "energy_compensation:i" },
+            { "burley_diffuse_bsdf", 3, "MX_BURLEY_DIFFUSE_ID", nullptr },
             { "emission", 0, "EMISSION_ID" },       { "background", 0, "BACKGROUND_ID" },
             { "diffuse", 1, "DIFFUSE_ID" },         { "oren_nayar", 2, "OREN_NAYAR_ID" },
             { "translucent", 1, "TRANSLUCENT_ID" }, { "phong", 2, "PHONG_ID" },
@@ -910,17 +911,49 @@ Gen::emit_op(const Opcode& op)
             { "transparent", 0, "TRANSPARENT_ID" }, { "transparent_bsdf", 0, "MX_TRANSPARENT_ID" },
             { "microfacet", 7, "MICROFACET_ID" },
         };
-        const char* idname = nullptr;
-        for (const Reg& r : regs)
-            if (cname == r.name && (int)pos.size() == r.nparams)
-                idname = r.id;
+        auto find_reg = [&](size_t npos) -> const Reg* {
+            for (const Reg& r : regs)
+                if (cname == r.name && (int)npos == r.nparams)
+                    return &r;
+            return nullptr;
+        };
+        // positional parameters end where a constant string followed by a value starts the
+        // "keyword", value pairs (llvm_gen_closure / llvm_gen_keyword_fill)
+        std::vector<int> pos, kw;
+        for (; i < op.args.size(); ++i) {
+            const Symbol& a = S(op.args[i]);
+            if (a.type.base == Base::String && a.const_value() && i + 1 < op.args.size() && find_reg(pos.size()))
+                break;
+            pos.push_back(op.args[i]);
+        }
+        for (; i < op.args.size(); ++i)
+            kw.push_back(op.args[i]);
+        const Reg* reg     = find_reg(pos.size());
+        const char* idname = reg ? reg->id : nullptr;
         if (!idname)
             unsupported("closure '" + cname + "' with " + std::to_string(pos.size()) + " parameters is not registered");
         int nwords = 0;
         for (int a : pos)
             nwords += S(a).type.ncomp();
+        // keyword slots: zero unless given (the reference memsets the parameter block)
+        std::vector<std::pair<std::string, char>> keys;
+        if (reg->keys) {
+            std::string ks = reg->keys;
+            size_t p = 0;
+            while (p < ks.size()) {
+                size_t c = ks.find(',', p);
+                std::string item = ks.substr(p, c == std::string::npos ? std::string::npos : c - p);
+                keys.push_back({ item.substr(0, item.find(':')), item.back() });
+                if (c == std::string::npos)
+                    break;
+                p = c + 1;
+            }
+        }
+        const int key_base = nwords;
+        nwords += (int)keys.size();
         const std::string cn = cname;
-        if (cn == "phong" || cn == "ward" || cn == "microfacet")
+        if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
+            || cn == "burley_diffuse_bsdf")
             g.uses_glossy_lobes = true;
         std::string wexpr = "mkv(1.0f)";
         if (weight >= 0) {
@@ -944,6 +977,21 @@ Gen::emit_op(const Opcode& op)
             }
             w("    putp(sg.pool->w + c_ + " + std::to_string(4 + off) + ", " + e + ");");
             off += S(a).type.ncomp();
+        }
+        for (size_t k = 0; k < keys.size(); ++k) {
+            std::string e = keys[k].second == 'i' ? "0" : "0.0f";
+            for (size_t j = 0; j + 1 < kw.size(); j += 2) {
+                const Symbol& ks = S(kw[j]);
+                const Symbol& kv = S(kw[j + 1]);
+                bool type_ok = keys[k].second == 'i' ? kv.type.base == Base::Int : kv.type.base == Base::Float;
+                if (ks.type.base == Base::String && ks.const_value() && !ks.svals.empty() && ks.svals[0] == keys[k].first
+                    && type_ok && kv.type.arraylen == 0) {
+                    e = R(kw[j + 1]);
+                    if (kv.has_derivs)
+                        e = "nd(" + e + ")";
+                }
+            }
+            w("    putp(sg.pool->w + c_ + " + std::to_string(4 + key_base + (int)k) + ", " + e + ");");
         }
         w("}");
         w(R(op.args[0]) + " = c_;");

@@ -298,6 +298,153 @@ inline BSample ward_sample(const Lobe& l, const V3& wo, float rx, float ry)
     return BSample();
 }
 
+// ---- libbsdl lobes behind testrender's BSDL_WRAP (shading.cpp:73-115) ----------------
+// BSDL_WRAP builds bsdl::BsdfGlobals(wo, N, N, backfacing, path_roughness, 1, 0), the
+// lobe frame is Frame(visible_normal(N)) and eval/sample run in that local frame
+// (libbsdl/include/BSDL/bsdf_impl.h:48-76, tools.h:459-510).
+inline float bsdl_max_abs_xyz(const V3& v) { return std::max(std::fabs(v.x), std::max(std::fabs(v.y), std::fabs(v.z))); }
+inline float bsdl_clamp(float x, float a, float b)
+{
+    float m = std::max(x, a);
+    return m < b ? m : b;
+}
+inline V3 bsdl_visible_normal(const V3& wo, const V3& Ngf, const V3& N)
+{
+    if (dot(wo, N) > 0.0f)
+        return N;
+    V3 V = cross(wo, N);
+    if (bsdl_max_abs_xyz(V) < 1e-4f) {
+        V = cross(wo, Ngf);
+        if (bsdl_max_abs_xyz(V) < 1e-4f) {
+            const float s = std::copysign(1.0f, wo.z);
+            const float a = -1.0f / (s + wo.z);
+            V             = V3(wo.x * wo.y * a, s + wo.y * wo.y * a, -wo.y);
+        } else
+            V = normalized(V);
+    } else
+        V = normalized(V);
+    return normalized(cross(V, wo) + 1e-4f * wo);
+}
+// tools.h:200-278
+inline float bsdl_fast_cos_quadrant(float x)
+{
+    const float c1 = 0.99998736f, c2 = -0.30837047f, c3 = 0.01578646f, c4 = -0.00029826362f;
+    float x2 = x * x;
+    float cp = c3 + c4 * x2;
+    cp       = c2 + cp * x2;
+    cp       = c1 + cp * x2;
+    return cp;
+}
+inline float bsdl_fast_sin_quadrant(float x)
+{
+    const float s1 = 0.7853975892066955566406250000000000f, s2 = -0.0807407423853874206542968750000000f,
+                s3 = 0.0024843954015523195266723632812500f, s4 = -0.0000341485538228880614042282104492f;
+    float x2 = x * x;
+    float sp = s3 + s4 * x2;
+    sp       = s2 + sp * x2;
+    sp       = s1 + sp * x2;
+    return sp * x;
+}
+inline V3 bsdl_sample_cos_hemisphere(float randu, float randv)
+{
+    const float a = 2 * randu - 1, qa = std::fabs(a);
+    const float b = 2 * randv - 1, qb = std::fabs(b);
+    const float rad = qa > qb ? qa : qb;
+    const float phi = qa > qb ? qb / qa : ((qa == qb) ? 1.0f : 2 - qa / qb);
+    const float x   = std::copysign(rad * bsdl_fast_cos_quadrant(phi), a);
+    const float y   = std::copysign(rad * bsdl_fast_sin_quadrant(phi), b);
+    return V3(x, y, std::sqrt(1 - rad * rad));
+}
+// mtx::OrenNayarDiffuseLobe::eval_impl without energy compensation (the OREN_NAYAR_ID
+// closure maps to {N, albedo 1, sigma, energy_compensation false}, shading.cpp:1496-1503);
+// MTX/bsdf_oren_nayar_diffuse_impl.h:40-62.  wo, wi in the lobe frame.
+inline BSample oren_nayar_eval_local(const Lobe& l, const V3& wo, const V3& wi)
+{
+    const float ONEOVERPI = 1 / float(M_PI);
+    const float cosNI = bsdl_clamp(wi.z, 0.0f, 1.0f);
+    const float cosNO = bsdl_clamp(wo.z, 0.0f, 1.0f);
+    if (cosNI <= 0.0f || cosNO <= 0.0f)
+        return BSample();
+    const float cosIO = bsdl_clamp(dot(wo, wi), -1.0f, 1.0f);
+    const float s     = cosIO - cosNI * cosNO;
+    const float pdf   = cosNI * ONEOVERPI;
+    if (!l.energy_compensation) {
+        const float s2    = SQR(l.ax);
+        const float A     = 1.0f - 0.50f * s2 / (s2 + 0.33f);
+        const float B     = 0.45f * s2 / (s2 + 0.09f);
+        const float stinv = s > 0.0f ? s / std::max(cosNI, cosNO) : 0.0f;
+        const float f_ss  = A + B * stinv;
+        return BSample(wi, l.albedo * f_ss, pdf, 1.0f);
+    }
+    // energy-preserving Oren-Nayar (Portsmouth), :63-93
+    const float PI_F          = float(M_PI);
+    const float constant1_FON = 0.5f - 2.0f / (3.0f * PI_F);
+    const float constant2_FON = 2.0f / 3.0f - 28.0f / (15.0f * PI_F);
+    const float sigma         = l.ax;
+    auto E_FON_analytic = [&](float mu) {
+        const float AF = 1.0f / (1.0f + constant1_FON * sigma);
+        const float BF = sigma * AF;
+        const float Si = std::sqrt(std::max(0.0f, 1.0f - mu * mu));
+        const float G  = Si * (fast_acos(mu) - Si * mu)
+                        + 2.0f * ((Si / std::max(mu, 1e-7f)) * (1.0f - Si * Si * Si) - Si) * (1.0f / 3.0f);
+        return AF + (BF * ONEOVERPI) * G;
+    };
+    const float AF    = 1.0f / (1.0f + constant1_FON * sigma);
+    const float stinv = s > 0.0f ? s / std::max(cosNI, cosNO) : s;
+    const float f_ss  = AF * (1.0f + sigma * stinv);
+    const float EFo   = E_FON_analytic(cosNO);
+    const float EFi   = E_FON_analytic(cosNI);
+    const float avgEF = AF * (1.0f + constant2_FON * sigma);
+    auto rho = [&](float a) { return SQR(a) * avgEF / (1 - a * std::max(0.0f, 1.0f - avgEF)); };
+    const V3 rho_ms(rho(l.albedo.x), rho(l.albedo.y), rho(l.albedo.z));
+    const float f_ms = std::max(1e-7f, 1.0f - EFo) * std::max(1e-7f, 1.0f - EFi) / std::max(1e-7f, 1.0f - avgEF);
+    return BSample(wi, l.albedo * f_ss + rho_ms * f_ms, pdf, 1.0f);
+}
+// mtx::BurleyDiffuseLobe (MTX/bsdf_burley_diffuse_impl.h:24-58)
+inline float burley_fresnel(float cos_theta, float F90)
+{
+    const float x  = bsdl_clamp(1.0f - cos_theta, 0.0f, 1.0f);
+    const float x2 = x * x;            // pown<5>: rec = pown<2>(x); rec * rec * x
+    float f        = bsdl_clamp(x2 * x2 * x, 0.0f, 1.0f);   // LERP clamps its parameter
+    return (1 - f) * 1.0f + f * F90;
+}
+inline BSample burley_eval_local(const Lobe& l, const V3& wo, const V3& wi)
+{
+    const float ONEOVERPI = 1 / float(M_PI);
+    if (wo.z <= 0.0f || wi.z <= 0.0f)
+        return BSample();
+    const V3 H = wi + wo;
+    if (bsdl_max_abs_xyz(H) < 1e-4f)
+        return BSample();
+    const V3 Hn       = normalized(H);
+    const float cosHI = bsdl_clamp(dot(wi, Hn), 0.0f, 1.0f);
+    const float cosNO = bsdl_clamp(wo.z, 0.0f, 1.0f);
+    const float cosNI = bsdl_clamp(wi.z, 0.0f, 1.0f);
+    const float F90   = 0.5f + 2.0f * l.ax * SQR(cosHI);
+    const float refL  = burley_fresnel(cosNI, F90);
+    const float refV  = burley_fresnel(cosNO, F90);
+    const float pdf   = cosNI * ONEOVERPI;
+    return BSample(wi, l.albedo * (refL * refV), pdf, 1.0f);
+}
+inline BSample bsdl_diffuse_eval_local(const Lobe& l, const V3& wo, const V3& wi)
+{
+    return l.type == LOBE_BSDL_BURLEY ? burley_eval_local(l, wo, wi) : oren_nayar_eval_local(l, wo, wi);
+}
+// BSDL_WRAP::eval / ::sample (shading.cpp:88-103): both diffuse lobes sample the cosine lobe
+inline BSample bsdl_diffuse_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    BSample s = bsdl_diffuse_eval_local(l, l.tf.tolocal(wo), l.tf.tolocal(wi));
+    return BSample(wi, s.weight, s.pdf, s.roughness);
+}
+inline BSample bsdl_diffuse_sample(const Lobe& l, const V3& wo, float rx, float ry)
+{
+    const V3 wo_l = l.tf.tolocal(wo);
+    BSample s;
+    if (!(wo_l.z <= 0.0f))
+        s = bsdl_diffuse_eval_local(l, wo_l, bsdl_sample_cos_hemisphere(rx, ry));
+    return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
+}
+
 }  // namespace lobes
 
 inline V3 ext_albedo(const Lobe& l, const V3& wo)
@@ -310,6 +457,8 @@ inline BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi)
     case LOBE_PHONG: return lobes::phong_eval(l, wo, wi);
     case LOBE_WARD: return lobes::ward_eval(l, wo, wi);
     case LOBE_MICROFACET: return lobes::mf_eval(l, wo, wi);
+    case LOBE_BSDL_OREN_NAYAR:
+    case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_eval(l, wo, wi);
     }
     return BSample();
 }
@@ -319,6 +468,8 @@ inline BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float
     case LOBE_PHONG: return lobes::phong_sample(l, wo, rx, ry);
     case LOBE_WARD: return lobes::ward_sample(l, wo, rx, ry);
     case LOBE_MICROFACET: return lobes::mf_sample(l, wo, rx, ry, rz);
+    case LOBE_BSDL_OREN_NAYAR:
+    case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_sample(l, wo, rx, ry);
     }
     return BSample();
 }

@@ -321,7 +321,9 @@ struct BSample {
     BSample(V3 wi, V3 w, float pdf, float r) : wi(wi), weight(w), pdf(pdf), roughness(r) {}
 };
 enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
-                LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET };
+                LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET,
+                LOBE_BSDL_OREN_NAYAR /* libbsdl mtx::OrenNayarDiffuseLobe through BSDL_WRAP */,
+                LOBE_BSDL_BURLEY /* mtx::BurleyDiffuseLobe */ };
 struct Lobe;
 // Phong / Ward / Microfacet live in osl_oracle_lobes.h
 V3 ext_albedo(const Lobe& l, const V3& wo);
@@ -335,6 +337,9 @@ struct Lobe {
     V3 T;
     float ax = 0, ay = 0, exponent = 0;
     int refract = 0, ggx = 0;
+    // libbsdl diffuse lobes: albedo, roughness (in ax), energy compensation flag
+    V3 albedo = V3(1.0f);
+    int energy_compensation = 0;
     TangentFrame tf;
     V3 get_albedo(const V3& wo) const
     {
@@ -349,6 +354,8 @@ struct Lobe {
         case LOBE_PHONG:
         case LOBE_WARD:
         case LOBE_MICROFACET: return ext_albedo(*this, wo);
+        case LOBE_BSDL_OREN_NAYAR:
+        case LOBE_BSDL_BURLEY: return albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
         default: return V3(1.0f);
         }
     }
@@ -504,6 +511,25 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                 case REFRACTION_ID: l.type = LOBE_REFRACTION; l.eta = comp->params[3]; break;
                 case TRANSPARENT_ID:
                 case MX_TRANSPARENT_ID: l.type = LOBE_TRANSPARENT; break;
+                case OREN_NAYAR_ID: {
+                    // -> MxOrenNayarDiffuse{N, albedo 1, sigma, no energy compensation}
+                    // (shading.cpp:1496-1503); frame on the visible normal, Nf = Ngf = N
+                    l.type = LOBE_BSDL_OREN_NAYAR;
+                    l.ax   = lobes::bsdl_clamp(comp->params[3], 0.0f, 1.0f);
+                    l.tf   = TangentFrame::from_normal(lobes::bsdl_visible_normal(-sg.I.val, l.N, l.N));
+                    break;
+                }
+                case MX_OREN_NAYAR_DIFFUSE_ID:
+                case MX_BURLEY_DIFFUSE_ID: {
+                    // params: N, albedo, roughness [, energy_compensation] (libbsdl Data structs)
+                    l.type   = comp->id == MX_BURLEY_DIFFUSE_ID ? LOBE_BSDL_BURLEY : LOBE_BSDL_OREN_NAYAR;
+                    l.albedo = V3(comp->params[3], comp->params[4], comp->params[5]);
+                    l.ax     = lobes::bsdl_clamp(comp->params[6], 0.0f, 1.0f);
+                    if (comp->id == MX_OREN_NAYAR_DIFFUSE_ID)
+                        l.energy_compensation = f2u(comp->params[7]) != 0;
+                    l.tf = TangentFrame::from_normal(lobes::bsdl_visible_normal(-sg.I.val, l.N, l.N));
+                    break;
+                }
                 case PHONG_ID: l.type = LOBE_PHONG; l.exponent = comp->params[3]; break;
                 case WARD_ID:
                     l.type = LOBE_WARD;

@@ -359,7 +359,15 @@ CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
             ("ward", 4): "WARD_ID", ("microfacet", 7): "MICROFACET_ID",
             ("reflection", 1): "REFLECTION_ID", ("reflection", 2): "FRESNEL_REFLECTION_ID",
             ("refraction", 2): "REFRACTION_ID", ("transparent", 0): "TRANSPARENT_ID",
-            ("transparent_bsdf", 0): "MX_TRANSPARENT_ID"}
+            ("transparent_bsdf", 0): "MX_TRANSPARENT_ID",
+            # MaterialX closures registered from libbsdl lobes (BSDLtoOSL, shading.cpp:156-182)
+            ("oren_nayar_diffuse_bsdf", 3): "MX_OREN_NAYAR_DIFFUSE_ID",
+            ("burley_diffuse_bsdf", 3): "MX_BURLEY_DIFFUSE_ID"}
+# keyword parameters per closure id, in slot order after the positional words; value
+# type "int" / "float".  Unspecified keywords are zero (llvm_gen_closure memsets the
+# parameter block when there is no prepare callback).  String keywords ("label") have
+# no effect on this path and take no slot.
+CLOSURE_KEYS = {"MX_OREN_NAYAR_DIFFUSE_ID": [("energy_compensation", "int")]}
 
 
 class Gen:
@@ -1203,6 +1211,14 @@ class Gen:
         if key not in CLOSURES:
             raise NotImplementedError("closure %s with %d params is not registered" % key)
         nwords = sum(a.t.ncomp for a in pos)
+        keys = CLOSURE_KEYS.get(CLOSURES[key], [])
+        given = {}
+        kw = params[len(pos):]
+        for j in range(0, len(kw) - 1, 2):
+            if kw[j].t.base == "string" and kw[j].constval:
+                given[kw[j].vals[0]] = kw[j + 1]
+        key_base = nwords
+        nwords += len(keys)
         wexpr = "nullptr"
         if weight is not None:
             self.w("V3 w_; assign(w_, %s);" % self.R(weight))
@@ -1216,6 +1232,15 @@ class Gen:
                 e = "nd(%s)" % e
             self.w("    putp(c_->params + %d, %s);" % (off, e))
             off += a.t.ncomp
+        for k, (kname, ktype) in enumerate(keys):
+            a = given.get(kname)
+            if a is not None and a.t.base == ktype and not a.t.arr:
+                e = self.R(a)
+                if a.has_derivs:
+                    e = "nd(%s)" % e
+                self.w("    putp(c_->params + %d, %s);" % (key_base + k, e))
+            else:
+                self.w("    putp(c_->params + %d, %s);" % (key_base + k, "0" if ktype == "int" else "0.0f"))
         self.w("}")
         self.w("%s = c_;" % self.R(d))
 

@@ -23,7 +23,14 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          "render-veachmis": ("veach.xml", 160, 120, 16),     # phong lobes, max_bounces 1, 4 lights
          "render-ward": ("ward.xml", 160, 120, 4),            # anisotropic ward lobes
          # white sphere in a uniform background: importance table (1024^2), MIS'd background NEE
-         "render-furnace-diffuse": ("furnace.xml", 160, 120, 20)}
+         "render-furnace-diffuse": ("furnace.xml", 160, 120, 20),
+         # oren_nayar() -> libbsdl mtx::OrenNayarDiffuseLobe through BSDL_WRAP (a16)
+         "render-oren-nayar": ("oren_nayar.xml", 160, 120, 4),
+         # MaterialX diffuse lobes in a grey furnace: oren_nayar_diffuse_bsdf with the
+         # "energy_compensation" keyword parameter (both branches), burley_diffuse_bsdf;
+         # <Background resolution="1"> -> 32^2 importance table
+         "render-mx-furnace-oren-nayar": ("mx_furnace_oren_nayar.xml", 384, 64, 16),
+         "render-mx-furnace-burley-diffuse": ("mx_furnace_burley.xml", 384, 64, 16)}
 # scenes of this repo (no reference golden image): the oracle restates the lobes
 # from shading.cpp and the device must equal the oracle.  render-microfacet itself
 # needs an HDR environment texture, which is outside this path.
@@ -77,7 +84,14 @@ def test_oracle_matches_reference_golden_render(case):
     _check_thresholds(img, ref)
     # far stronger in practice: identical after rounding to the golden's half precision
     h = img.astype(np.float16).astype(np.float32)
-    assert (np.abs(h - ref).max(axis=2) == 0).mean() > 0.99
+    exact = (np.abs(h - ref).max(axis=2) == 0).mean()
+    if case.startswith("render-mx-furnace"):
+        # These goldens carry per-path noise against this host (the reference's run.py
+        # loosens them "to allow a little more LSB noise between platforms"): ~4 % of
+        # pixels differ by one or two paths out of 256.  The difference must be unbiased.
+        assert exact > 0.95 and abs(float((img - ref).mean())) < 1e-4, (exact, float((img - ref).mean()))
+    else:
+        assert exact > 0.99, exact
 
 
 def test_render_module_compiles_without_gpu(b200lib):

@@ -61,6 +61,12 @@ SHADERS = {
     "ward": "render-ward/ward.osl",
     "glossy_glass": "render-microfacet/glossy_glass.osl",
     "furnace": "render-furnace-diffuse/furnace.osl",
+    "rough_matte": "render-oren-nayar/rough_matte.osl",
+    # MaterialX furnace tests: several tests reuse the file names matte.osl / envmap.osl for
+    # different shaders, so the fixtures (and the shader names in the copied scenes) are prefixed
+    "mxon_matte": "render-mx-furnace-oren-nayar/matte.osl",
+    "mxburley_matte": "render-mx-furnace-burley-diffuse/matte.osl",
+    "mx_envmap": "render-mx-furnace-oren-nayar/envmap.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -73,6 +79,12 @@ SCENES = {
     "veach.xml": "render-veachmis/veach.xml",
     "ward.xml": "render-ward/scene.xml",
     "furnace.xml": "render-furnace-diffuse/scene.xml",
+    "oren_nayar.xml": "render-oren-nayar/scene.xml",
+    # (path, {shader name in the scene: fixture name})
+    "mx_furnace_oren_nayar.xml": ("render-mx-furnace-oren-nayar/scene.xml",
+                                  {"matte": "mxon_matte", "envmap": "mx_envmap"}),
+    "mx_furnace_burley.xml": ("render-mx-furnace-burley-diffuse/scene.xml",
+                              {"matte": "mxburley_matte", "envmap": "mx_envmap"}),
 }
 # golden renders (half-float EXR in the reference; stored as float16 npz)
 RENDERS = {
@@ -81,6 +93,9 @@ RENDERS = {
     "render-veachmis": "render-veachmis/ref/out.exr",
     "render-ward": "render-ward/ref/out.exr",
     "render-furnace-diffuse": "render-furnace-diffuse/ref/out.exr",
+    "render-oren-nayar": "render-oren-nayar/ref/out.exr",
+    "render-mx-furnace-oren-nayar": "render-mx-furnace-oren-nayar/ref/out.exr",
+    "render-mx-furnace-burley-diffuse": "render-mx-furnace-burley-diffuse/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
@@ -160,8 +175,14 @@ def main():
             o.write(f.read())
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
     for name, rel in SCENES.items():
+        rename = {}
+        if isinstance(rel, tuple):
+            rel, rename = rel
         with open(os.path.join(TS, rel), "rb") as f, open(os.path.join(OUT, "scenes", name), "wb") as o:
-            o.write(f.read())
+            data = f.read()
+            for old, new in rename.items():
+                data = re.sub((r"\bshader\s+%s\b" % re.escape(old)).encode(), ("shader " + new).encode(), data)
+            o.write(data)
     os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
     import cv2
     for name, rel in RENDERS.items():

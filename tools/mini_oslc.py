@@ -1222,6 +1222,12 @@ class Compiler:
             fi += 1
         if fi < len(formals) and formals[fi] in ("*", "."):
             fi += 1
+        if fi == len(formals) and i < n and f.rtype.is_closure and getattr(f, "builtin", True):
+            # closure constructors take trailing "keyword", value pairs (oslc:
+            # ASTfunction_call::check_arglist accepts them for closure-returning builtins)
+            rest = argtypes[i:]
+            if len(rest) % 2 == 0 and all(rest[k].is_string for k in range(0, len(rest), 2)):
+                i = n
         if fi < len(formals) or i < n:
             return 0
         return max(score, 1)
