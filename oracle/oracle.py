@@ -28,7 +28,43 @@ class Launch(ctypes.Structure):
                 ("plane_stride", ctypes.c_longlong),
                 ("shadeindex", ctypes.c_void_p),
                 ("output_base", ctypes.c_void_p),
-                ("userdata_base", ctypes.c_void_p)]
+                ("userdata_base", ctypes.c_void_p),
+                ("ntransforms", ctypes.c_int),
+                ("transforms", ctypes.c_void_p)]
+
+
+class NamedTransform(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("m", ctypes.c_float * 16)]
+
+
+def testshade_transforms():
+    """setup_transformations (src/testshade/testshade.cpp:925-950): "shader" = translate(1,0,0)
+    then rotate z 45 deg, "object" = translate(0,1,0) then rotate z 90 deg, "myspace" =
+    scale(1,2,1).  Imath's Matrix44::translate / rotate / scale in float32; these are harness
+    inputs handed identically to the oracle and to the device."""
+    f32 = np.float32
+
+    def translate(M, t):
+        M = M.copy()
+        for j in range(4):
+            M[3, j] = f32(M[3, j] + f32(f32(f32(t[0] * M[0, j]) + f32(t[1] * M[1, j])) + f32(t[2] * M[2, j])))
+        return M
+
+    def rotate_z(M, rz):
+        c, s = f32(np.cos(f32(rz))), f32(np.sin(f32(rz)))
+        m = np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]], f32)   # Matrix44::rotate with rx = ry = 0
+        P = M.copy()
+        for i in range(3):
+            for j in range(4):
+                M[i, j] = f32(f32(f32(P[0, j] * m[i, 0]) + f32(P[1, j] * m[i, 1])) + f32(P[2, j] * m[i, 2]))
+        return M
+    I = np.eye(4, dtype=f32)
+    Mshad = rotate_z(translate(I, (f32(1), f32(0), f32(0))), np.pi / 4)
+    Mobj = rotate_z(translate(I, (f32(0), f32(1), f32(0))), np.pi / 2)
+    Mmy = I.copy()
+    Mmy[1, :] *= f32(2)
+    return {"shader": Mshad.reshape(-1).tolist(), "object": Mobj.reshape(-1).tolist(),
+            "myspace": Mmy.reshape(-1).tolist()}
 
 
 def testshade_globals(xres, yres, center=False, vary_udxdy=False, vary_vdxdy=False,
@@ -74,6 +110,7 @@ def testshade_globals(xres, yres, center=False, vary_udxdy=False, vary_vdxdy=Fal
     uni["Ng"] = [0.0, 0.0, 1.0]
     uni["surfacearea"] = [1.0]
     uni["raytype"] = [raytype]
+    uni["transforms"] = testshade_transforms()
     return var, uni
 
 
@@ -105,6 +142,15 @@ def make_launch(n, varying, uniform, output, shadeindex=None, keep=None):
     L.output_base = output.ctypes.data if output is not None else None
     L.userdata_base = None
     keep.append(output)
+    xf = uniform.get("transforms") or {}
+    arr = (NamedTransform * max(1, len(xf)))()
+    for k, (name, m) in enumerate(xf.items()):
+        arr[k].name = name.encode()
+        for c in range(16):
+            arr[k].m[c] = float(m[c])
+    keep.append(arr)
+    L.ntransforms = len(xf)
+    L.transforms = ctypes.cast(arr, ctypes.c_void_p)
     return L, keep
 
 

@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 #include "osl_oracle_color.h"
+#include "osl_oracle_matrix.h"
 
 #ifndef OSLO_COLORSPACE
 #    define OSLO_COLORSPACE "Rec709" /* ShadingSystem attribute "colorspace" default */
@@ -51,10 +52,27 @@ struct Launch {
     const int* shadeindex;             // NULL => iota
     void* output_base;                 // renderer output arena
     const void* userdata_base;
+    // named coordinate systems of the renderer, "shader" / "object" included
+    // (ShaderGlobals::shader2common / object2common + RendererServices::get_matrix)
+    int ntransforms;
+    const struct NamedTransform* transforms;
 };
+inline TransformSet xf_set(const Launch* L)
+{
+    TransformSet ts;
+    if (L) {
+        ts.n = L->ntransforms;
+        ts.t = L->transforms;
+    }
+    return ts;
+}
+inline M44 m44_diag(float f) { return M44(f); }
 
 struct Ctx {
     std::string* out;  // printf capture (NULL: discard)
+    // error messages already reported: the shading system prints a repeated error once
+    // (attribute "error_repeats" = 0, shadingsys.cpp)
+    std::vector<std::string> errseen = {};
 };
 
 struct Clos;
@@ -164,6 +182,58 @@ inline void pf_v(SG& sg, const char* spec, const V3& v)
 }
 inline void pf_v(SG& sg, const char* spec, const Dv& v) { pf_v(sg, spec, v.val); }
 inline void pf_s(SG& sg, const char* spec, const char* v) { pf_fmt(sg, spec, v); }
+inline void pf_v(SG& sg, const char* spec, const M44& m)
+{
+    for (int i = 0; i < 16; ++i) {
+        if (i)
+            pf_lit(sg, " ");
+        pf_fmt(sg, spec, (double)m[i]);
+    }
+}
+
+// named-space lookups that report unknown names the way the reference does with the
+// default unknown_coordsys_error=1 (opmatrix.cpp:129-134, 160-165, 188-196): the message
+// goes through the error handler, which testshade prints inline as "ERROR: ..."
+inline void xf_unknown(SG& sg, const char* name)
+{
+    if (!(sg.ctx && sg.ctx->out))
+        return;
+    std::string msg = std::string("ERROR: Unknown transformation \"") + (name ? name : "") + "\"\n";
+    for (const std::string& s : sg.ctx->errseen)
+        if (s == msg)
+            return;
+    sg.ctx->errseen.push_back(msg);
+    pf_lit(sg, msg.c_str());
+}
+inline bool xf_get_matrix_err(SG& sg, const TransformSet& ts, const char* from, M44& r)
+{
+    bool ok = xf_get_matrix(ts, from, r);
+    if (!ok) {
+        xf_unknown(sg, from);   // once in osl_get_matrix ...
+        xf_unknown(sg, from);   // ... and once more in osl_prepend_matrix_from
+    }
+    return ok;
+}
+inline bool xf_get_from_to_matrix_err(SG& sg, const TransformSet& ts, const char* from, const char* to, M44& r)
+{
+    M44 a, b;
+    if (!xf_get_matrix(ts, from, a))
+        xf_unknown(sg, from);
+    if (!xf_get_inverse_matrix(ts, to, b))
+        xf_unknown(sg, to);
+    return xf_get_from_to_matrix(ts, from, to, r);
+}
+template<class T>
+inline bool xf_transform_triple_err(SG& sg, const TransformSet& ts, const char* from, const char* to, const T& in, T& out,
+                                    int vectype)
+{
+    M44 t;
+    if (std::strcmp(from, "common") && !xf_get_matrix(ts, from, t))
+        xf_unknown(sg, from);
+    if (std::strcmp(to, "common") && !xf_get_inverse_matrix(ts, to, t))
+        xf_unknown(sg, to);
+    return xf_transform_triple(ts, from, to, in, out, vectype);
+}
 
 inline bool str_eq(const char* a, const char* b)
 {

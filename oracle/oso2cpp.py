@@ -428,7 +428,7 @@ class Gen:
         if b == "string":
             return cstr(s.vals[0])
         if b == "matrix":
-            return "M44{{%s}}" % ", ".join(cfloat(v) for v in s.vals)
+            return "M44(%s)" % ", ".join(cfloat(v) for v in (list(s.vals) + [0.0] * 16)[:16])
         raise NotImplementedError(b)
 
     def initval(self, s):
@@ -450,7 +450,7 @@ class Gen:
             if b == "string":
                 return cstr(v[0])
             if b == "matrix":
-                return "M44{{%s}}" % ", ".join(cfloat(x) for x in v)
+                return "M44(%s)" % ", ".join(cfloat(x) for x in v)
             if b == "closure color":
                 return "nullptr"
             raise NotImplementedError(b)
@@ -745,7 +745,7 @@ class Gen:
         if d.t.base == "closure color":
             return self.op_closure_arith(op)
         if d.t.base == "matrix":
-            raise NotImplementedError("matrix %s" % n)
+            return self.op_matrix_arith(op)
         isint = d.t.base == "int"
         dv = d.has_derivs and any(a.has_derivs for a in A[1:])
         fn = "o_" + n
@@ -775,6 +775,10 @@ class Gen:
             e = "str_eq(%s, %s)" % (self.R(a), self.R(b))
             if op.name == "neq":
                 e = "!" + e
+        elif a.t.base == "matrix" or b.t.base == "matrix":
+            am = self.R(a) if a.t.base == "matrix" else "m44_diag(%s)" % self.fl(a)
+            bm = self.R(b) if b.t.base == "matrix" else "m44_diag(%s)" % self.fl(b)
+            e = "%s(%s == %s)" % ("!" if op.name == "neq" else "", am, bm)
         elif a.t.base == "closure color":
             e = "(%s %s nullptr)" % (self.R(a), cop)
         elif a.t.base == "int" and b.t.base == "int":
@@ -1079,6 +1083,97 @@ class Gen:
         self.w("assign(%s, color_transformc(colorsystem(), %s, %s, %s));" % (
             self.R(d), self.R(frm), self.R(to), e))
 
+    # ---- matrix shadeops (opmatrix.cpp; llvm_gen_matrix / _getmatrix / _transform) ----
+    def fl(self, s):
+        """scalar float expression of an int/float symbol (no derivs)"""
+        return self.comp(s, 0, False)
+
+    def op_matrix_arith(self, op):
+        n, A = op.name, op.args
+        d = self.R(A[0])
+        if n == "neg":
+            return self.w("%s = -%s;" % (d, self.R(A[1])))
+        a, b = A[1], A[2]
+        am, bm = a.t.base == "matrix", b.t.base == "matrix"
+        if n == "mul":
+            if am and bm:
+                return self.w("%s = %s * %s;" % (d, self.R(a), self.R(b)))
+            m, f = (a, b) if am else (b, a)
+            return self.w("%s = %s * %s;" % (d, self.R(m), self.fl(f)))
+        if n == "div":
+            if am and bm:       # osl_div_mmm
+                return self.w("%s = %s * m44_inverse(%s);" % (d, self.R(a), self.R(b)))
+            if am:              # osl_div_mmf
+                return self.w("%s = %s * (1.0f / %s);" % (d, self.R(a), self.fl(b)))
+            if bm:              # osl_div_mfm
+                return self.w("%s = %s * m44_inverse(%s);" % (d, self.fl(a), self.R(b)))
+            # osl_div_m_ff
+            return self.w("{ float b_ = %s; %s = m44_diag(b_ == 0 ? 0.0f : (%s / b_)); }" % (self.fl(b), d, self.fl(a)))
+        raise NotImplementedError("matrix %s" % n)
+
+    def op_matrix(self, op):
+        """llvm_gen_matrix (llvm_gen.cpp:2295-2370)"""
+        A = op.args
+        d = self.R(A[0])
+        nargs = len(A)
+        using_space = nargs in (3, 18) and A[1].t.base == "string"
+        two_spaces = nargs == 3 and A[2].t.base == "string"
+        if two_spaces:
+            return self.w("xf_get_from_to_matrix_err(sg, xf_set(L), %s, %s, %s);" % (self.R(A[1]), self.R(A[2]), d))
+        vals = A[1 + using_space:]
+        if len(vals) == 1:
+            self.w("%s = m44_diag(%s);" % (d, self.fl(vals[0])))
+        elif len(vals) == 16:
+            self.w("%s = M44(%s);" % (d, ", ".join(self.fl(v) for v in vals)))
+        else:
+            raise NotImplementedError("matrix constructor with %d values" % len(vals))
+        if using_space:   # osl_prepend_matrix_from
+            self.w("{ M44 f_; if (xf_get_matrix_err(sg, xf_set(L), %s, f_)) %s = f_ * %s; }" % (self.R(A[1]), d, d))
+
+    def op_getmatrix(self, op):
+        r, frm, to, m = op.args
+        self.w("%s = xf_get_from_to_matrix_err(sg, xf_set(L), %s, %s, %s) ? 1 : 0;" % (
+            self.R(r), self.R(frm), self.R(to), self.R(m)))
+
+    def op_mxcompref(self, op):
+        d, m, i, j = op.args
+        self.w("assign(%s, %s.x[%s][%s]);" % (self.R(d), self.R(m), self.R(i), self.R(j)))
+
+    def op_mxcompassign(self, op):
+        m, i, j, v = op.args
+        self.w("%s.x[%s][%s] = %s;" % (self.R(m), self.R(i), self.R(j), self.fl(v)))
+
+    def op_transpose(self, op):
+        self.w("%s = m44_transposed(%s);" % (self.R(op.args[0]), self.R(op.args[1])))
+
+    def op_determinant(self, op):
+        self.w("assign(%s, m44_determinant(%s));" % (self.R(op.args[0]), self.R(op.args[1])))
+
+    def op_transform(self, op):
+        """llvm_gen_transform (llvm_gen.cpp:2376-2466): transform / transformv / transformn with
+        a matrix, or with (from, to) space names through osl_transform_triple."""
+        A = op.args
+        vt = {"transform": 0, "transformv": 1, "transformn": 2}[op.name]
+        d, p = A[0], A[-1]
+        dv = d.has_derivs and p.has_derivs
+        pe = self.R(p)
+        if p.isconst:
+            pe = "V3(%s)" % ", ".join(self.comp(p, k, False) for k in range(3))
+        elif p.has_derivs and not dv:
+            pe = "nd(%s)" % pe
+        if len(A) == 3 and A[1].t.base == "matrix":
+            return self.w("assign(%s, m44_transform(%s, %s, %d));" % (self.R(d), self.R(A[1]), pe, vt))
+        if len(A) == 3:      # transform("to", p): from = "common"
+            frm, to = '"common"', self.R(A[1])
+        else:
+            frm, to = self.R(A[1]), self.R(A[2])
+        T = "Dv" if dv else "V3"
+        self.w("{ %s o_; xf_transform_triple_err(sg, xf_set(L), %s, %s, %s(%s), o_, %d); assign(%s, o_); }" % (
+            T, frm, to, T, pe, vt, self.R(d)))
+
+    op_transformv = op_transform
+    op_transformn = op_transform
+
     def op_spline(self, op):
         """llvm_gen_spline (llvm_gen.cpp:3673-3740) -> osl_spline_* (opspline.cpp)."""
         A = op.args
@@ -1156,7 +1251,7 @@ class Gen:
                         self.w("pf_i(sg, %s, nd(%s));" % (cstr(spec), r))
                     else:
                         self.w("pf_f(sg, %s, %s);" % (cstr(spec), r))
-                elif a.t.triple:
+                elif a.t.triple or a.t.base == "matrix":
                     self.w("pf_v(sg, %s, %s);" % (cstr(spec), r))
                 else:
                     raise NotImplementedError("printf of %s" % a.t)

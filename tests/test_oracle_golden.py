@@ -110,6 +110,20 @@ def test_color_text_goldens(case):
     assert txt.rstrip("\n") == want.rstrip("\n")
 
 
+@pytest.mark.parametrize("case", ["matrix", "transform"])
+def test_matrix_text_goldens(case):
+    """testsuite/matrix and testsuite/transform (`testshade -g 2 2 test`): matrix
+    constructors (with space names, from-to), getmatrix incl. an unknown space,
+    element access, * / unary -, transpose, determinant, ==, and transform /
+    transformv / transformn of points, vectors, normals with derivatives between
+    "common", "shader", "object" and the renderer-named "myspace"."""
+    g = oracle.OracleGroup([dict(oso=helpers.oso(case + "_test"), name="l0")])
+    var, uni = oracle.testshade_globals(2, 2)
+    txt = g.run_capture(4, var, uni)
+    want = "\n".join(l for l in helpers.golden_text(case).split("\n") if not l.startswith("Compiled"))
+    assert txt.rstrip("\n") == want.rstrip("\n")
+
+
 @pytest.mark.parametrize("case,xres,yres", [("blackbody", 1000, 64), ("wavelength_color", 1000, 64)])
 def test_color_exr_goldens(case, xres, yres):
     """testsuite/blackbody (`-g 1000 64 -od half`) and testsuite/wavelength_color

@@ -46,6 +46,8 @@ SHADERS = {
     "spline_test": "spline/test.osl",
     "gabor2d_filter_test": "noise-gabor2d-filter/test.osl",
     "gabor3d_filter_test": "noise-gabor3d-filter/test.osl",
+    "matrix_test": "matrix/test.osl",
+    "transform_test": "transform/test.osl",
     "color_test": "color/test.osl",
     "transformc_test": "transformc/test.osl",
     "blackbody_test": "blackbody/test.osl",
@@ -123,6 +125,8 @@ TEXTS = {
     "layers-lazy": "layers-lazy/ref/out.txt",
     "layers": "layers/ref/out.txt",
     "color": "color/ref/out.txt",
+    "matrix": "matrix/ref/out.txt",
+    "transform": "transform/ref/out.txt",
     "transformc": "transformc/ref/out.txt",
 }
 # float / half EXR goldens of testshade image tests (stored as float32 npz, full size)
