@@ -51,10 +51,23 @@ typedef enum b200_sg_field {
  * uniform over the batch and uniform[f][0..2] is used (ints bit-cast in [0]),
  * like BatchedShaderGlobals' UniformShaderGlobals
  * (src/include/OSL/batched_shaderglobals.h:21-195). */
+/* A named coordinate system, <name> -> "common", row-major like Imath::M44f.
+ * Replaces RendererServices::get_matrix(sg, result, from, time)
+ * (src/include/OSL/rendererservices.h) and, under the names "shader" and
+ * "object", ShaderGlobals::shader2common / object2common
+ * (src/include/OSL/shaderglobals.h:118-123): uniform over the batch. */
+typedef struct b200_transform {
+    const char* name;
+    float m[16];
+} b200_transform;
+#define B200_MAX_SPACES 8 /* distinct named spaces one group may reference */
+
 typedef struct b200_globals {
     const float* varying[B200_SG_NFIELDS];
     float uniform[B200_SG_NFIELDS][4];
     long long plane_stride;
+    int ntransforms;                  /* may be 0 */
+    const b200_transform* transforms; /* HOST pointer, read at launch */
 } b200_globals;
 
 /* ShadingSystem::Parameter (src/include/OSL/oslexec.h:656) */

@@ -27,10 +27,16 @@ class B200Error(RuntimeError):
     pass
 
 
+class _Transform(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("m", ctypes.c_float * 16)]
+
+
 class _Globals(ctypes.Structure):
     _fields_ = [("varying", ctypes.c_void_p * NF),
                 ("uniform", (ctypes.c_float * 4) * NF),
-                ("plane_stride", ctypes.c_longlong)]
+                ("plane_stride", ctypes.c_longlong),
+                ("ntransforms", ctypes.c_int),
+                ("transforms", ctypes.POINTER(_Transform))]
 
 
 class _Param(ctypes.Structure):
@@ -133,6 +139,16 @@ def _fill_globals(n, varying, uniform, plane_stride=None):
             else:
                 g.uniform[i][c] = float(vals[c]) if c < len(vals) else 0.0
     g.plane_stride = n if plane_stride is None else plane_stride
+    # named coordinate systems ("shader", "object", renderer-named spaces): {name: 16 floats}
+    xf = (uniform or {}).get("transforms") or {}
+    arr = (_Transform * max(1, len(xf)))()
+    for k, (name, m) in enumerate(xf.items()):
+        arr[k].name = name.encode()
+        for c in range(16):
+            arr[k].m[c] = float(m[c])
+    g.ntransforms = len(xf)
+    g.transforms = arr
+    g._keep_transforms = arr   # keep the array alive as long as the struct
     return g
 
 

@@ -1018,3 +1018,4 @@ OSLD V3 o_Dy(V3) { return mkv(0.0f); }
 #include "osl_b200_simplex.cuh"
 #include "osl_b200_spline.cuh"
 #include "osl_b200_gabor.cuh"
+#include "osl_b200_matrix.cuh"

@@ -163,9 +163,46 @@ private:
         case Base::Point:
         case Base::Vector:
         case Base::Normal: return s.has_derivs ? "Dv" : "V3";
+        case Base::Matrix: return "M44";
         default: break;
         }
         unsupported("symbol '" + s.name + "' has a type the device path does not support yet");
+    }
+    static std::string m44_literal(const std::vector<float>& v, size_t at)
+    {
+        std::string r = "m44_make(";
+        for (size_t k = 0; k < 16; ++k)
+            r += (k ? ", " : "") + cfloat(at + k < v.size() ? v[at + k] : 0.0f);
+        return r + ")";
+    }
+    // slot of a named coordinate system in the launch block's xf table
+    int space_slot(const std::string& name)
+    {
+        for (size_t k = 0; k < g.spaces.size(); ++k)
+            if (g.spaces[k] == name)
+                return (int)k;
+        if ((int)g.spaces.size() >= B200_MAX_SPACES)
+            unsupported("more than " + std::to_string(B200_MAX_SPACES) + " named coordinate systems in one group");
+        g.spaces.push_back(name);
+        return (int)g.spaces.size() - 1;
+    }
+    // Expressions for osl_get_matrix(from) / osl_get_inverse_matrix(to) with a compile-time
+    // space name: {matrix expression, ok expression}.  "common" and its synonym are identity.
+    std::pair<std::string, std::string> space_matrix(int si, bool inverse)
+    {
+        const Symbol& s = S(si);
+        if (s.type.base != Base::String || !s.const_value())
+            unsupported("coordinate-system name that is not known at compile time");
+        std::string name = s.svals.empty() ? "" : s.svals[0];
+        if (name == "common" || name == g.commonspace_synonym)
+            return { "m44_diag(1.0f)", "1" };
+        std::string k = std::to_string(space_slot(name));
+        return { "m44_load(L.xf[" + k + "][" + (inverse ? "1" : "0") + "])", "L.xf_ok[" + k + "]" };
+    }
+    bool space_is(int si, const char* what)
+    {
+        const Symbol& s = S(si);
+        return s.type.base == Base::String && s.const_value() && !s.svals.empty() && s.svals[0] == what;
     }
     std::string constexpr_(const Symbol& s)
     {
@@ -182,6 +219,8 @@ private:
                     v[i] = s.fvals[i];
                 return "mkv(" + cfloat(v[0]) + ", " + cfloat(v[1]) + ", " + cfloat(v[2]) + ")";
             }
+            if (s.type.base == Base::Matrix)
+                return m44_literal(s.fvals, 0);
         }
         unsupported("constant '" + s.name + "' type");
     }
@@ -232,7 +271,9 @@ private:
                 if (s.type.is_triple()) {
                     std::string v = "mkv(" + cfloat(fv(0)) + ", " + cfloat(fv(1)) + ", " + cfloat(fv(2)) + ")";
                     out.push_back(s.has_derivs ? "mkdv(" + v + ")" : v);
-                } else
+                } else if (s.type.base == Base::Matrix)
+                    out.push_back(m44_literal(s.fvals, (size_t)e * 16));
+                else
                     unsupported("default value of '" + s.name + "'");
             }
         }
@@ -290,6 +331,7 @@ private:
         return r + "OSLD_CS_UNKNOWN)";
     }
 
+    void emit_matrix_op(const Opcode& op);
     void gen_layer(int layer);
     void emit_block(int b, int e, const Ctx* ctx);
     void useparams(const Opcode& op);
@@ -630,6 +672,134 @@ Gen::op_noise(const Opcode& op, bool periodic)
         w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", out_[" + std::to_string(c) + "]);");
 }
 
+// Matrix shadeops (opmatrix.cpp; llvm_gen_matrix, llvm_gen_getmatrix, llvm_gen_transform,
+// llvm_gen_mxcompref/assign).  Space names must be compile-time constants; their matrices
+// come from the launch block (see space_matrix).
+void
+Gen::emit_matrix_op(const Opcode& op)
+{
+    const std::string& n = op.name;
+    auto A               = [&](int i) -> Symbol& { return S(op.args[i]); };
+    auto fl              = [&](int i) { return comp(op.args[i], 0, false); };
+    auto is_m            = [&](int i) { return A(i).type.base == Base::Matrix; };
+    const std::string d  = R(op.args[0]);
+    if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
+        std::string msg = "op '" + n + "' ignored on device (no journal yet) in layer '" + L->layername + "'";
+        bool dup = false;
+        for (auto& s : g.warnings)
+            dup |= (s == msg);
+        if (!dup)
+            g.warnings.push_back(msg);
+    } else if (n == "assign") {
+        w(is_m(1) ? d + " = " + R(op.args[1]) + ";" : d + " = m44_diag(" + fl(1) + ");");
+    } else if (n == "neg") {
+        w(d + " = -" + R(op.args[1]) + ";");
+    } else if (n == "mul") {
+        if (is_m(1) && is_m(2))
+            w(d + " = " + R(op.args[1]) + " * " + R(op.args[2]) + ";");
+        else
+            w(d + " = " + R(op.args[is_m(1) ? 1 : 2]) + " * " + fl(is_m(1) ? 2 : 1) + ";");
+    } else if (n == "div") {
+        if (is_m(1) && is_m(2))
+            w(d + " = " + R(op.args[1]) + " * m44_inverse(" + R(op.args[2]) + ");");
+        else if (is_m(1))
+            w(d + " = " + R(op.args[1]) + " * (1.0f / " + fl(2) + ");");
+        else if (is_m(2))
+            w(d + " = " + fl(1) + " * m44_inverse(" + R(op.args[2]) + ");");
+        else
+            w("{ float b_ = " + fl(2) + "; " + d + " = m44_diag(b_ == 0 ? 0.0f : (" + fl(1) + " / b_)); }");
+    } else if (n == "eq" || n == "neq") {
+        std::string a = is_m(1) ? R(op.args[1]) : "m44_diag(" + fl(1) + ")";
+        std::string b = is_m(2) ? R(op.args[2]) : "m44_diag(" + fl(2) + ")";
+        w(d + " = (" + (n == "neq" ? "!" : "") + "(" + a + " == " + b + ")) ? 1 : 0;");
+    } else if (n == "transpose") {
+        w(d + " = m44_transposed(" + R(op.args[1]) + ");");
+    } else if (n == "determinant") {
+        w("assign(" + d + ", m44_determinant(" + R(op.args[1]) + "));");
+    } else if (n == "mxcompref") {
+        w("assign(" + d + ", " + R(op.args[1]) + ".x[" + R(op.args[2]) + " & 3][" + R(op.args[3]) + " & 3]);");
+    } else if (n == "mxcompassign") {
+        w(d + ".x[" + R(op.args[1]) + " & 3][" + R(op.args[2]) + " & 3] = " + fl(3) + ";");
+    } else if (n == "matrix") {
+        // llvm_gen_matrix (llvm_gen.cpp:2295-2370)
+        size_t nargs     = op.args.size();
+        bool using_space = (nargs == 3 || nargs == 18) && A(1).type.base == Base::String;
+        bool two_spaces  = nargs == 3 && A(2).type.base == Base::String;
+        if (two_spaces) {  // osl_get_from_to_matrix
+            auto mf = space_matrix(op.args[1], false), mt = space_matrix(op.args[2], true);
+            w(d + " = " + mf.first + " * " + mt.first + ";");
+            return;
+        }
+        size_t v0 = 1 + (using_space ? 1 : 0), nv = nargs - v0;
+        if (nv == 1)
+            w(d + " = m44_diag(" + fl((int)v0) + ");");
+        else if (nv == 16) {
+            std::string e = "m44_make(";
+            for (size_t k = 0; k < 16; ++k)
+                e += (k ? ", " : "") + fl((int)(v0 + k));
+            w(d + " = " + e + ");");
+        } else
+            unsupported("matrix constructor with " + std::to_string(nv) + " values");
+        if (using_space) {  // osl_prepend_matrix_from: only when the space is known
+            auto mf = space_matrix(op.args[1], false);
+            w("if (" + mf.second + ") " + d + " = " + mf.first + " * " + d + ";");
+        }
+    } else if (n == "getmatrix") {
+        auto mf = space_matrix(op.args[1], false), mt = space_matrix(op.args[2], true);
+        w(R(op.args[3]) + " = " + mf.first + " * " + mt.first + ";");
+        w(d + " = (" + mf.second + " & " + mt.second + ") ? 1 : 0;");
+    } else if (n == "transform" || n == "transformv" || n == "transformn") {
+        // llvm_gen_transform (llvm_gen.cpp:2376-2466) -> osl_transform{,v,n}_* / osl_transform_triple
+        const char* vt = n == "transform" ? "0" : (n == "transformv" ? "1" : "2");
+        int pi         = (int)op.args.size() - 1;
+        const Symbol& p = A(pi);
+        bool dv        = A(0).has_derivs && p.has_derivs;
+        std::string pe = R(op.args[pi]);
+        if (p.has_derivs && !dv)
+            pe = "nd(" + pe + ")";
+        if (op.args.size() == 3 && is_m(1)) {
+            w("assign(" + d + ", m44_transform(" + R(op.args[1]) + ", " + pe + ", " + vt + "));");
+            return;
+        }
+        int fi = op.args.size() == 3 ? -1 : 1, ti = op.args.size() == 3 ? 1 : 2;
+        {
+            // same space on both sides (after the "world" synonym): an identity, just copy
+            auto norm = [&](int i) -> std::string {
+                if (i < 0)
+                    return "common";
+                const Symbol& s = S(op.args[i]);
+                if (s.type.base != Base::String || !s.const_value())
+                    unsupported("coordinate-system name that is not known at compile time");
+                std::string v = s.svals.empty() ? "" : s.svals[0];
+                return v == g.commonspace_synonym ? "common" : v;
+            };
+            if (norm(fi) == norm(ti)) {
+                w("assign(" + d + ", " + pe + ");");
+                return;
+            }
+        }
+        bool from_common = fi < 0 || space_is(op.args[fi], "common");
+        bool to_common   = space_is(op.args[ti], "common");
+        std::string M, ok;
+        if (from_common) {
+            auto mt = space_matrix(op.args[ti], true);
+            M = mt.first; ok = mt.second;
+        } else if (to_common) {
+            auto mf = space_matrix(op.args[fi], false);
+            M = mf.first; ok = mf.second;
+        } else {
+            auto mf = space_matrix(op.args[fi], false), mt = space_matrix(op.args[ti], true);
+            M  = mf.first + " * " + mt.first;
+            ok = "(" + mf.second + " & " + mt.second + ")";
+        }
+        // unknown space: the value passes through unchanged (osl_transform_triple)
+        w("if (" + ok + ") assign(" + d + ", m44_transform(" + M + ", " + pe + ", " + vt + ")); else assign(" + d + ", "
+          + pe + ");");
+    } else {
+        unsupported("op '" + n + "' on a matrix");
+    }
+}
+
 void
 Gen::emit_op(const Opcode& op)
 {
@@ -639,7 +809,13 @@ Gen::emit_op(const Opcode& op)
         if (op.args.size() < k)
             unsupported("op '" + n + "' has too few arguments");
     };
-    if (n == "mod") {
+    bool any_matrix = false;
+    for (int a : op.args)
+        any_matrix |= S(a).type.base == Base::Matrix;
+    if (any_matrix || n == "transform" || n == "transformv" || n == "transformn" || n == "getmatrix"
+        || n == "matrix") {
+        emit_matrix_op(op);
+    } else if (n == "mod") {
         need(3);
         w(R(op.args[0]) + " = o_mod(" + R(op.args[1]) + ", " + R(op.args[2]) + ");");
     } else if (n == "compl") {
@@ -1090,6 +1266,11 @@ struct B200Launch {
     long long out_adjust[%MAXOUT%];   // per-output byte rebase (host staging path)
     int stage_outputs;                // 1: stage dense output records in shared memory
     int pad_;
+    // named coordinate systems the group references (slot order fixed at code generation):
+    // [k][0] = space -> common, [k][1] = its inverse; xf_ok[k] = 0 when the renderer does
+    // not know the name (identity is stored)
+    float xf[%MAXSPACES%][2][16];
+    int xf_ok[%MAXSPACES%];
 };
 
 __device__ __forceinline__ float ldf(const B200Launch& L, int f, int c, long long i)
@@ -1252,6 +1433,8 @@ Gen::run()
         prelude.replace(p, 9, std::to_string((int)B200_SG_NFIELDS));
     for (size_t p; (p = prelude.find("%MAXOUT%")) != std::string::npos;)
         prelude.replace(p, 8, std::to_string(B200_MAX_OUTPUTS));
+    for (size_t p; (p = prelude.find("%MAXSPACES%")) != std::string::npos;)
+        prelude.replace(p, 11, std::to_string(B200_MAX_SPACES));
     if ((int)g.outputs.size() > B200_MAX_OUTPUTS)
         throw std::runtime_error("B200 back end: too many renderer outputs in one group");
 

@@ -130,6 +130,8 @@ struct Group {
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
     bool uses_colorsystem  = false;            // set by codegen: luminance / blackbody / transformc ...
     std::string colorspace = "Rec709";         // ShadingSystem attribute "colorspace"
+    std::vector<std::string> spaces;           // named coordinate systems referenced (launch-block slots)
+    std::string commonspace_synonym = "world"; // ShadingSystem attribute "commonspace"
 
     int layer_index(const std::string& n) const;
     void add_layer(const std::string& oso_text, const std::string& layername,

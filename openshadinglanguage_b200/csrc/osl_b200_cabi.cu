@@ -118,6 +118,8 @@ struct LaunchBlock {  // must match B200Launch in the generated code
     long long out_adjust[B200_MAX_OUTPUTS];
     int stage_outputs;
     int pad_;
+    float xf[B200_MAX_SPACES][2][16];
+    int xf_ok[B200_MAX_SPACES];
 };
 
 }  // namespace
@@ -396,6 +398,23 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
         L.out_adjust[k] = out_adjust ? out_adjust[k] : 0;
     L.stage_outputs = g->stage_outputs;
     L.pad_          = 0;
+    // named coordinate systems: resolve the names the generated code references and invert
+    // once per launch (the reference inverts per call: rs_get_inverse_matrix_*)
+    for (int k = 0; k < B200_MAX_SPACES; ++k) {
+        osld::M44 m = osld::m44_diag(1.0f), mi = m;
+        L.xf_ok[k]  = 0;
+        if (k < (int)g->g.spaces.size()) {
+            for (int t = 0; t < sg->ntransforms && sg->transforms; ++t)
+                if (sg->transforms[t].name && g->g.spaces[k] == sg->transforms[t].name) {
+                    m          = osld::m44_load(sg->transforms[t].m);
+                    mi         = osld::m44_inverse(m);
+                    L.xf_ok[k] = 1;
+                    break;
+                }
+        }
+        memcpy(L.xf[k][0], m.x, sizeof m.x);
+        memcpy(L.xf[k][1], mi.x, sizeof mi.x);
+    }
     int sms = (device >= 0 && device < 64 && g->sm_count[device]) ? g->sm_count[device] : 148;
     // grid: one CTA per tile of `block` points, capped at 8 CTAs per SM (a
     // multiple of the SM count); CTAs loop over the remaining tiles

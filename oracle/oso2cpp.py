@@ -1163,6 +1163,12 @@ class Gen:
             pe = "nd(%s)" % pe
         if len(A) == 3 and A[1].t.base == "matrix":
             return self.w("assign(%s, m44_transform(%s, %s, %d));" % (self.R(d), self.R(A[1]), pe, vt))
+        fs = None if len(A) == 3 else A[1]
+        ts = A[1] if len(A) == 3 else A[2]
+        if (fs is None or fs.constval) and ts.constval:
+            norm = lambda s: "common" if s in ("common", "world") else s
+            if norm(fs.vals[0] if fs is not None else "common") == norm(ts.vals[0]):
+                return self.w("assign(%s, %s);" % (self.R(d), pe))   # identity: just copy
         if len(A) == 3:      # transform("to", p): from = "common"
             frm, to = '"common"', self.R(A[1])
         else:

@@ -87,6 +87,28 @@ COLOR_OPS_OUTPUTS = [("Cto", 3), ("Cback", 3), ("Cctor", 3), ("Csrgb", 3), ("Cli
                      ("DyCto", 3), ("Lum", 1), ("DxLum", 1), ("BB", 3), ("WL", 3)]
 
 
+# tests/shaders/matrix_ops.osl
+MATRIX_OPS_OUTPUTS = [("Pshader", 3), ("Vobj", 3), ("Nmy", 3), ("Pback", 3), ("Pm", 3), ("DxPm", 3), ("Det", 1),
+                      ("Row", 3), ("Ok", 1), ("Punk", 3), ("Eq", 1), ("Nm", 3), ("PjP", 3), ("PjN", 3), ("DyV", 3)]
+
+
+def multi_output_case(shader, outputs_spec, res, params=None):
+    layers = [dict(oso=oso(shader), name="layer0", params=dict(params or {}))]
+    outputs, off = [], 0
+    for name, ch in outputs_spec:
+        outputs.append(dict(name=name, offset=off, stride=4 * ch))
+        off += 4 * ch * res * res
+    return layers, outputs, off // 4
+
+
+def multi_output_split(arena, outputs_spec, res):
+    out, o = {}, 0
+    for name, ch in outputs_spec:
+        out[name] = arena[o:o + ch * res * res].reshape(res * res, ch)
+        o += ch * res * res
+    return out
+
+
 def color_ops_case(space, res=96):
     layers = [dict(oso=oso("color_ops"), name="layer0", params=dict(space=space))]
     outputs, off = [], 0

@@ -230,6 +230,39 @@ def test_color_ops_match_oracle(b200lib, cuda_device, space):
     assert np.isfinite(W["BB"]).all() and W["BB"].max() > 0 and W["WL"].max() > 0
 
 
+def test_matrix_ops_match_oracle(b200lib, cuda_device):
+    """Matrix constructors with space names / from-to, getmatrix (known and unknown
+    spaces), * / with scalars and matrices, transpose, determinant, element access,
+    ==, transform of points / vectors / normals (+ derivatives) by matrices (affine and
+    projective: Imath's fast inverse and the Gauss-Jordan one) and by space names
+    (tests/shaders/matrix_ops.osl).  The named transforms come from the harness
+    (`testshade`'s setup_transformations) through b200_globals.transforms.  Bit-exact."""
+    import torch
+    res = 64
+    layers, outputs, nfloats = helpers.multi_output_case("matrix_ops", helpers.MATRIX_OPS_OUTPUTS, res)
+    og = oracle.OracleGroup(layers, outputs=outputs)
+    ovar, ouni = oracle.testshade_globals(res, res)
+    want = np.zeros(nfloats, np.float32)
+    og.run(res * res, ovar, ouni, want, nthreads=4)
+    g = b200lib.ShaderGroup(layers, outputs=outputs, options="fma=0")
+    var, uni = b200lib.grid_globals(res, res)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(nfloats, dtype=torch.float32, device=cuda_device)
+    g.execute(res * res, dvar, uni, out)
+    torch.cuda.synchronize()
+    W = helpers.multi_output_split(want, helpers.MATRIX_OPS_OUTPUTS, res)
+    G = helpers.multi_output_split(out.cpu().numpy(), helpers.MATRIX_OPS_OUTPUTS, res)
+    for name in W:
+        assert np.array_equal(G[name].view(np.uint32), W[name].view(np.uint32)), \
+            (name, np.abs(G[name] - W[name]).max())
+    assert np.all(W["Ok"] == 2.0) and np.all(W["Eq"] == 3.0)          # unknown space -> 0, == / != work
+    assert np.array_equal(W["Punk"][:, 0], ovar["u"])                  # unknown space: value passes through
+    assert np.abs(W["Pback"][:, :2] - np.stack([ovar["u"], ovar["v"]], 1)).max() < 1e-5   # there and back
+    host = np.zeros(nfloats, np.float32)
+    g.execute_host(res * res, var, uni, host)
+    assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
+
+
 def test_host_path_matches_device_path(b200lib, cuda_device):
     layers, outputs, res = helpers.image_case_group("noise")
     a = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=0", 3)

@@ -184,4 +184,9 @@ def test_oracle_globals_match_product_harness():
         for k in va:
             assert np.array_equal(np.asarray(va[k]).ravel(), np.asarray(vb[k]).ravel()), k
         for k in set(ua) | set(ub):
+            if k == "transforms":
+                assert set(ua[k]) == set(ub[k])
+                for name in ua[k]:
+                    assert np.array_equal(np.float32(ua[k][name]), np.float32(ub[k][name])), name
+                continue
             assert list(map(float, ua[k])) == list(map(float, ub[k])), k

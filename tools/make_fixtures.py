@@ -72,6 +72,7 @@ SHADERS = {
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
+    "matrix_ops": "repo:tests/shaders/matrix_ops.osl",
 }
 # scene descriptions + model data of the testrender configs (test input data)
 SCENES = {
