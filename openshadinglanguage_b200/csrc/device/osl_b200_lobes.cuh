@@ -377,6 +377,101 @@ OSLD BSample bsdl_diffuse_sample(const Lobe& l, V3 wo, float rx, float ry)
     return s;
 }
 
+// ---- mtx::SheenLobe, Conty-Kulla mode (MTX/bsdf_sheen_impl.h:17-175) ------------------------
+// Lobe fields: frame (fu, fv, N) = Frame(visible normal, wo); ax = sheen alpha, ay = regularized
+// roughness, eta = Emiss (what the lobe lets through to a layer below), refract = backfacing,
+// albedo = tint.
+OSLD V3 bsdl_sample_uniform_hemisphere(float randu, float randv)
+{
+    const float a = 2 * randu - 1, qa = fabsf(a);
+    const float b = 2 * randv - 1, qb = fabsf(b);
+    const float rad = qa > qb ? qa : qb;
+    const float phi = qa > qb ? qb / qa : ((qa == qb) ? 1.0f : 2 - qa / qb);
+    const float x2  = phi * phi;
+    float cp = 0.01578646f + -0.00029826362f * x2;
+    cp       = -0.30837047f + cp * x2;
+    cp       = 0.99998736f + cp * x2;
+    float sp = 0.0024843954015523195266723632812500f + -0.0000341485538228880614042282104492f * x2;
+    sp       = -0.0807407423853874206542968750000000f + sp * x2;
+    sp       = 0.7853975892066955566406250000000000f + sp * x2;
+    sp       = sp * phi;
+    const float x = copysignf(rad * cp, a), y = copysignf(rad * sp, b);
+    const float cos_theta = 1 - rad * rad;
+    const float sin_theta = sqrtf(2 - rad * rad);
+    return mkv(sin_theta * x, sin_theta * y, cos_theta);
+}
+OSLD float sheen_conty_albedo(float cosNO, float rough)
+{
+    float rx = 13.67300f, ry = 1.0f;
+    rx = rx + -68.78018f * cosNO;               ry = ry + 61.57746f * cosNO;
+    rx = rx + 799.08825f * rough;               ry = ry + 442.78211f * rough;
+    rx = rx + -905.00061f * cosNO * rough;      ry = ry + 2597.49308f * cosNO * rough;
+    rx = rx + 60.28956f * cosNO * cosNO;        ry = ry + 121.81241f * cosNO * cosNO;
+    rx = rx + 1086.96473f * rough * rough;      ry = ry + 3045.55075f * rough * rough;
+    return bsdl_clamp(rx / ry, 0.0f, 1.0f);
+}
+// everything SheenLobe's constructor derives; l.N (shading normal) and l.albedo set by the caller
+OSLD void sheen_setup(Lobe& l, V3 wo, float roughness_param, bool backfacing, float path_roughness)
+{
+    const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
+    // Frame(Z, X = wo) (tools.h:483-495)
+    if (bsdl_max_abs_xyz(wo) < 1e-4f || fabsf(dot3(Z, vnormalized(wo))) > 0.999f) {
+        TangentFrame f = frame_from_normal(Z);
+        l.fu           = f.u;
+        l.fv           = f.v;
+    } else {
+        l.fv = vnormalized(cross3(Z, wo));
+        l.fu = cross3(l.fv, Z);
+    }
+    l.N           = Z;
+    const float r = bsdl_clamp(roughness_param, 0.0f, 1.0f);
+    l.ay          = 1.0f - (1.0f - r) * (1.0f - path_roughness);
+    l.ax          = fmaxf(0.06f, l.ay);
+    l.refract     = backfacing ? 1 : 0;
+    const float cosNO = bsdl_clamp(dot3(Z, wo), 0.0f, 1.0f);
+    const float tmax  = fmaxf(l.albedo.x, fmaxf(l.albedo.y, l.albedo.z));
+    l.eta = backfacing ? 1.0f : 1 - fminf(sheen_conty_albedo(cosNO, bsdl_clamp(l.ax, 0.06f, 1.0f)) * tmax, 1.0f);
+}
+// SheenMicrofacet<ContyKullaDist<false>>::eval, then SheenLobe's tint and roughness tag
+OSLD BSample sheen_micro_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    const float PI_F = (float)OSLD_PI, ONEOVERPI = 1 / (float)OSLD_PI;
+    const float cosNO = wo.z, cosNI = wi.z;
+    BSample s = bs_null();
+    if (!(cosNI <= 1e-5f || cosNO <= 1e-5f)) {
+        const float a   = bsdl_clamp(l.ax, 0.06f, 1.0f);
+        const V3 Hr     = vnormalized(wo + wi);
+        float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
+        float sin_theta = sqrtf(1.0f - sqr_(cos_theta));
+        const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
+        if (!((double)D < 1e-6)) {
+            float cI = fminf(1.0f, wi.z), cO = fminf(1.0f, wo.z);
+            const float G2 = (cI * cO) / (cI + cO - cI * cO);
+            s = bs_make(wi, mkv(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0.0f);
+        }
+    }
+    s.weight    = s.weight * l.albedo;
+    s.roughness = l.ay;
+    return s;
+}
+OSLD BSample sheen_eval(const Lobe& l, V3 wo, V3 wi)
+{
+    const V3 wo_l = frame_tolocal(l, wo), wi_l = frame_tolocal(l, wi);
+    BSample s     = bs_null();
+    if (wi_l.z > 0 && wo_l.z >= 0 && !l.refract)
+        s = sheen_micro_eval(l, wo_l, wi_l);
+    s.wi = wi;
+    return s;
+}
+OSLD BSample sheen_sample(const Lobe& l, V3 wo, float rx, float ry)
+{
+    BSample s = bs_null();
+    if (!l.refract)
+        s = sheen_micro_eval(l, frame_tolocal(l, wo), bsdl_sample_uniform_hemisphere(rx, ry));
+    s.wi = frame_toworld(l, s.wi);
+    return s;
+}
+
 // ---- Phong (exponent kept in l.ax) -------------------------------------------------------
 OSLD BSample phong_eval(const Lobe& l, V3 wo, V3 wi)
 {

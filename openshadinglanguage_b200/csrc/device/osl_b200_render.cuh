@@ -297,7 +297,7 @@ OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
 }
 #define OSLD_INF __int_as_float(0x7f800000)
 enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
-       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY };
+       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY, LOBE_BSDL_SHEEN };
 struct Lobe {
     int type;
     V3 N;
@@ -324,6 +324,8 @@ OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
         return mf_albedo(l, wo);
     if (l.type == LOBE_BSDL_OREN_NAYAR || l.type == LOBE_BSDL_BURLEY)
         return l.albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
+    if (l.type == LOBE_BSDL_SHEEN)
+        return l.albedo * (1 - l.eta);  // tint * (1 - Emiss)
 #endif
     if (l.type == LOBE_REFLECTION) {
         float cosNO = dot3(l.N, wo);
@@ -348,6 +350,8 @@ OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
         return mf_eval(l, wo, wi);
     if (l.type == LOBE_BSDL_OREN_NAYAR || l.type == LOBE_BSDL_BURLEY)
         return bsdl_diffuse_eval(l, wo, wi);
+    if (l.type == LOBE_BSDL_SHEEN)
+        return sheen_eval(l, wo, wi);
 #endif
     return bs_null();
 }
@@ -380,6 +384,7 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
     case LOBE_MICROFACET: return mf_sample(l, wo, rx, ry, rz);
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return bsdl_diffuse_sample(l, wo, rx, ry);
+    case LOBE_BSDL_SHEEN: return sheen_sample(l, wo, rx, ry);
 #endif
     default: return bs_make(-wo, mkv(1.0f), OSLD_INF, 0.0f);
     }
@@ -441,9 +446,60 @@ OSLD BSample bsdf_sample(const CompositeBSDF& B, V3 wo, float rx, float ry, floa
     return bs_null();
 }
 
+#ifdef OSLD_GLOSSY_LOBES
+// evaluate_layer_opacity (shading.cpp:1198-1282): what the top stack of a layer() takes;
+// returns the weight held when the walk ends, as the reference does
+OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool backfacing, float path_roughness)
+{
+    if (!closure)
+        return mkv(0.0f);
+    int ptr_stack[16];
+    V3 weight_stack[16];
+    int sp    = 0;
+    V3 weight = mkv(1.0f);
+    while (closure) {
+        int id = pool.id(closure);
+        if (id == CL_MUL) {
+            weight  = weight * pool.weight(closure);
+            closure = __float_as_int(pool.w[closure + 4]);
+        } else if (id == CL_ADD) {
+            ptr_stack[sp]      = __float_as_int(pool.w[closure + 2]);
+            weight_stack[sp++] = weight;
+            closure            = __float_as_int(pool.w[closure + 1]);
+        } else {
+            const V3 w     = pool.weight(closure);
+            const float* q = pool.w + closure + 4;
+            closure        = 0;
+            if (id == MX_LAYER_ID) {
+                closure            = __float_as_int(q[0]);
+                ptr_stack[sp]      = __float_as_int(q[1]);
+                weight_stack[sp++] = weight * w;
+            } else if (id == REFLECTION_ID || id == FRESNEL_REFLECTION_ID) {
+                Lobe l;
+                l.type = LOBE_REFLECTION;
+                l.N    = mkv(q[0], q[1], q[2]);
+                l.eta  = id == FRESNEL_REFLECTION_ID ? q[3] : 0.0f;
+                weight = weight * (w * lobe_albedo(l, wo));
+            } else if (id == MX_SHEEN_ID) {
+                Lobe l;
+                l.N      = mkv(q[0], q[1], q[2]);
+                l.albedo = mkv(q[3], q[4], q[5]);
+                sheen_setup(l, wo, q[6], backfacing, path_roughness);
+                weight = weight * (w * (mkv(1.0f) - mkv(l.eta)));
+            }  // anything else: opaque
+        }
+        if (closure == 0 && sp > 0) {
+            closure = ptr_stack[--sp];
+            weight  = weight_stack[sp];
+        }
+    }
+    return weight;
+}
+#endif
+
 // closure tree -> emission + lobes (16-deep explicit stack, weights root->leaf)
 OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only,
-                          V3 wo = mkv(0.0f, 0.0f, 1.0f))
+                          V3 wo = mkv(0.0f, 0.0f, 1.0f), bool backfacing = false, float path_roughness = 0.0f)
 {
     int ptr_stack[16];
     V3 weight_stack[16];
@@ -464,6 +520,8 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
             closure        = 0;
             if (id == EMISSION_ID)
                 Le = Le + cw;
+            else if (id == MX_UNIFORM_EDF_ID)
+                Le = Le + cw * mkv(q[0], q[1], q[2]);
             else if (!light_only) {
                 Lobe l;
                 l.N   = mkv(q[0], q[1], q[2]);
@@ -486,6 +544,29 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                     l.refract = 0;
                     lobe_set_bsdl_frame(l, wo);
                     break;
+                case MX_SHEEN_ID:
+                    // params: N, albedo, roughness, mode; mode 1 (Zeltner LTC sheen) is not built
+                    l.albedo = mkv(q[3], q[4], q[5]);
+                    l.type   = LOBE_BSDL_SHEEN;
+                    sheen_setup(l, wo, q[6], backfacing, path_roughness);
+                    known = __float_as_int(q[7]) == 0;
+                    break;
+                case MX_LAYER_ID: {
+                    // layer(top, base): the base is attenuated by what the top stack takes
+                    // (shading.cpp:1645-1661)
+                    const int top = __float_as_int(q[0]), base = __float_as_int(q[1]);
+                    V3 op     = evaluate_layer_opacity(pool, top, wo, backfacing, path_roughness);
+                    op        = mkv(fminf(fmaxf(op.x, 0.f), 1.f), fminf(fmaxf(op.y, 0.f), 1.f), fminf(fmaxf(op.z, 0.f), 1.f));
+                    V3 base_w = weight * (mkv(1.0f) - op);
+                    closure   = top;
+                    weight    = cw;
+                    if (!(base_w.x == 0 && base_w.y == 0 && base_w.z == 0)) {
+                        ptr_stack[sp]      = base;
+                        weight_stack[sp++] = base_w;
+                    }
+                    known = false;
+                    break;
+                }
                 case MX_OREN_NAYAR_DIFFUSE_ID:
                 case MX_BURLEY_DIFFUSE_ID:
                     // params: N, albedo, roughness [, energy_compensation] (libbsdl Data structs)
@@ -1163,7 +1244,7 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
                 CompositeBSDF bsdf;
                 bsdf.num               = 0;
                 const bool last_bounce = b == S.max_bounces;
-                process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I);
+                process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness);
                 const int nlights = S.nlightprims;
                 float k           = 1;
                 if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {

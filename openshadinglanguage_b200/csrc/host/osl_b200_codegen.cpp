@@ -1079,6 +1079,9 @@ Gen::emit_op(const Opcode& op)
             // MaterialX closures registered from libbsdl lobes (BSDLtoOSL, shading.cpp:156-182)
             { "oren_nayar_diffuse_bsdf", 3, "MX_OREN_NAYAR_DIFFUSE_ID", "energy_compensation:i" },
             { "burley_diffuse_bsdf", 3, "MX_BURLEY_DIFFUSE_ID", nullptr },
+            { "sheen_bsdf", 3, "MX_SHEEN_ID", "mode:i" },
+            { "layer", 2, "MX_LAYER_ID", nullptr },  // closure-typed params: pool word offsets
+            { "uniform_edf", 1, "MX_UNIFORM_EDF_ID", nullptr },
             { "emission", 0, "EMISSION_ID" },       { "background", 0, "BACKGROUND_ID" },
             { "diffuse", 1, "DIFFUSE_ID" },         { "oren_nayar", 2, "OREN_NAYAR_ID" },
             { "translucent", 1, "TRANSLUCENT_ID" }, { "phong", 2, "PHONG_ID" },
@@ -1129,7 +1132,7 @@ Gen::emit_op(const Opcode& op)
         nwords += (int)keys.size();
         const std::string cn = cname;
         if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
-            || cn == "burley_diffuse_bsdf")
+            || cn == "burley_diffuse_bsdf" || cn == "sheen_bsdf" || cn == "layer")
             g.uses_glossy_lobes = true;
         std::string wexpr = "mkv(1.0f)";
         if (weight >= 0) {

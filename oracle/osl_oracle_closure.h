@@ -121,5 +121,7 @@ inline int closure_string_code(const char* s)
     return 0;
 }
 inline void putp(float* p, const char* s) { putp(p, closure_string_code(s)); }
+// closure-typed parameter (layer's top / base): the pointer itself, two words
+inline void putp(float* p, const Clos* c) { std::memcpy(p, &c, sizeof c); }
 
 }  // namespace oslo

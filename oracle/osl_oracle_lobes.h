@@ -445,6 +445,112 @@ inline BSample bsdl_diffuse_sample(const Lobe& l, const V3& wo, float rx, float 
     return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
 }
 
+// ---- mtx::SheenLobe, Conty-Kulla mode (MTX/bsdf_sheen_impl.h:17-175) ----------------------
+// Frame(Z = visible normal, X = wo) (tools.h:483-495)
+inline TangentFrame bsdl_frame_zx(const V3& Z, const V3& Xin)
+{
+    if (bsdl_max_abs_xyz(Xin) < 1e-4f || std::fabs(dot(Z, normalized(Xin))) > 0.999f)
+        return TangentFrame::from_normal(Z);
+    TangentFrame f;
+    f.w = Z;
+    f.v = normalized(cross(Z, Xin));
+    f.u = cross(f.v, Z);
+    return f;
+}
+inline V3 bsdl_sample_uniform_hemisphere(float randu, float randv)
+{
+    const float a = 2 * randu - 1, qa = std::fabs(a);
+    const float b = 2 * randv - 1, qb = std::fabs(b);
+    const float rad = qa > qb ? qa : qb;
+    const float phi = qa > qb ? qb / qa : ((qa == qb) ? 1.0f : 2 - qa / qb);
+    const float x   = std::copysign(rad * bsdl_fast_cos_quadrant(phi), a);
+    const float y   = std::copysign(rad * bsdl_fast_sin_quadrant(phi), b);
+    const float cos_theta = 1 - rad * rad;
+    const float sin_theta = std::sqrt(2 - rad * rad);
+    return V3(sin_theta * x, sin_theta * y, cos_theta);
+}
+// ContyKullaSheenMTX::albedo: rational fit in (cosNO, roughness)
+inline float sheen_conty_albedo(float cosNO, float rough)
+{
+    float rx = 13.67300f, ry = 1.0f;
+    rx = rx + -68.78018f * cosNO;               ry = ry + 61.57746f * cosNO;
+    rx = rx + 799.08825f * rough;               ry = ry + 442.78211f * rough;
+    rx = rx + -905.00061f * cosNO * rough;      ry = ry + 2597.49308f * cosNO * rough;
+    rx = rx + 60.28956f * cosNO * cosNO;        ry = ry + 121.81241f * cosNO * cosNO;
+    rx = rx + 1086.96473f * rough * rough;      ry = ry + 3045.55075f * rough * rough;
+    return bsdl_clamp(rx / ry, 0.0f, 1.0f);
+}
+// set up everything SheenLobe's constructor derives (sheen_alpha in ax, regularized
+// roughness in ay, Emiss in emiss)
+inline void sheen_setup(Lobe& l, const V3& wo, float roughness_param, bool backfacing, float path_roughness)
+{
+    const V3 Z   = bsdl_visible_normal(wo, l.N, l.N);
+    l.tf         = bsdl_frame_zx(Z, wo);
+    const float r = bsdl_clamp(roughness_param, 0.0f, 1.0f);
+    l.ay         = 1.0f - (1.0f - r) * (1.0f - path_roughness);   // regularize_roughness
+    l.ax         = std::max(0.06f, l.ay);                          // ContyKullaDist::MIN_ROUGHNESS
+    l.backfacing = backfacing;
+    const float cosNO = bsdl_clamp(dot(Z, wo), 0.0f, 1.0f);
+    const float tmax  = std::max(l.albedo.x, std::max(l.albedo.y, l.albedo.z));
+    l.emiss = backfacing ? 1.0f : 1 - std::min(sheen_conty_albedo(cosNO, bsdl_clamp(l.ax, 0.06f, 1.0f)) * tmax, 1.0f);
+}
+inline BSample sheen_eval_local(const Lobe& l, const V3& wo, const V3& wi)
+{
+    const float PI_F = float(M_PI), ONEOVERPI = 1 / float(M_PI);
+    const float cosNO = wo.z, cosNI = wi.z;
+    const bool is_reflection = cosNI > 0 && cosNO >= 0;
+    BSample s;
+    if (is_reflection && !l.backfacing) {
+        // SheenMicrofacet<ContyKullaDist<false>>::eval
+        if (!(cosNI <= 1e-5f || cosNO <= 1e-5f)) {
+            const float a  = bsdl_clamp(l.ax, 0.06f, 1.0f);
+            const V3 Hr    = normalized(wo + wi);
+            float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
+            float sin_theta = std::sqrt(1.0f - SQR(cos_theta));
+            const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
+            if (!(D < 1e-6)) {
+                float cI = std::min(1.0f, wi.z), cO = std::min(1.0f, wo.z);
+                const float G2 = (cI * cO) / (cI + cO - cI * cO);
+                s = BSample(wi, V3(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0);
+            }
+        }
+        s.weight    = s.weight * l.albedo;
+        s.roughness = l.ay;
+    }
+    return s;
+}
+inline BSample sheen_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    BSample s = sheen_eval_local(l, l.tf.tolocal(wo), l.tf.tolocal(wi));
+    return BSample(wi, s.weight, s.pdf, s.roughness);
+}
+inline BSample sheen_sample(const Lobe& l, const V3& wo, float rx, float ry)
+{
+    BSample s;
+    if (!l.backfacing) {
+        const V3 wo_l = l.tf.tolocal(wo);
+        const V3 wi   = bsdl_sample_uniform_hemisphere(rx, ry);
+        // SheenMicrofacet::sample -> eval, then SheenLobe::sample_impl scales and tags it
+        const float PI_F = float(M_PI), ONEOVERPI = 1 / float(M_PI);
+        const float cosNO = wo_l.z, cosNI = wi.z;
+        if (!(cosNI <= 1e-5f || cosNO <= 1e-5f)) {
+            const float a  = bsdl_clamp(l.ax, 0.06f, 1.0f);
+            const V3 Hr    = normalized(wo_l + wi);
+            float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
+            float sin_theta = std::sqrt(1.0f - SQR(cos_theta));
+            const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
+            if (!(D < 1e-6)) {
+                float cI = std::min(1.0f, wi.z), cO = std::min(1.0f, wo_l.z);
+                const float G2 = (cI * cO) / (cI + cO - cI * cO);
+                s = BSample(wi, V3(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0);
+            }
+        }
+        s.weight    = s.weight * l.albedo;
+        s.roughness = l.ay;
+    }
+    return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
+}
+
 }  // namespace lobes
 
 inline V3 ext_albedo(const Lobe& l, const V3& wo)
@@ -459,6 +565,7 @@ inline BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi)
     case LOBE_MICROFACET: return lobes::mf_eval(l, wo, wi);
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_eval(l, wo, wi);
+    case LOBE_BSDL_SHEEN: return lobes::sheen_eval(l, wo, wi);
     }
     return BSample();
 }
@@ -470,6 +577,7 @@ inline BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float
     case LOBE_MICROFACET: return lobes::mf_sample(l, wo, rx, ry, rz);
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_sample(l, wo, rx, ry);
+    case LOBE_BSDL_SHEEN: return lobes::sheen_sample(l, wo, rx, ry);
     }
     return BSample();
 }

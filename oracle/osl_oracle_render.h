@@ -323,7 +323,8 @@ struct BSample {
 enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
                 LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET,
                 LOBE_BSDL_OREN_NAYAR /* libbsdl mtx::OrenNayarDiffuseLobe through BSDL_WRAP */,
-                LOBE_BSDL_BURLEY /* mtx::BurleyDiffuseLobe */ };
+                LOBE_BSDL_BURLEY /* mtx::BurleyDiffuseLobe */,
+                LOBE_BSDL_SHEEN /* mtx::SheenLobe, Conty-Kulla mode */ };
 struct Lobe;
 // Phong / Ward / Microfacet live in osl_oracle_lobes.h
 V3 ext_albedo(const Lobe& l, const V3& wo);
@@ -340,6 +341,9 @@ struct Lobe {
     // libbsdl diffuse lobes: albedo, roughness (in ax), energy compensation flag
     V3 albedo = V3(1.0f);
     int energy_compensation = 0;
+    // sheen: ax = sheen alpha, ay = regularized roughness, emiss = layering transmittance
+    float emiss = 1.0f;
+    bool backfacing = false;
     TangentFrame tf;
     V3 get_albedo(const V3& wo) const
     {
@@ -356,6 +360,7 @@ struct Lobe {
         case LOBE_MICROFACET: return ext_albedo(*this, wo);
         case LOBE_BSDL_OREN_NAYAR:
         case LOBE_BSDL_BURLEY: return albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
+        case LOBE_BSDL_SHEEN: return albedo * (1 - emiss);
         default: return V3(1.0f);
         }
     }
@@ -471,8 +476,89 @@ struct ShadingResult {
     CompositeBSDF bsdf;
 };
 
+inline const Clos* clos_ptr_param(const ClosComp* c, int word)
+{
+    const Clos* p;
+    std::memcpy(&p, c->params + word, sizeof p);
+    return p;
+}
+inline V3 clamp01(const V3& c)
+{
+    auto f = [](float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); };
+    return V3(f(c.x), f(c.y), f(c.z));
+}
+// mtx::SheenLobe construction from an MX_SHEEN_ID component; false: unsupported mode
+inline bool sheen_from_component(Lobe& l, const ClosComp* comp, const SG& sg, float path_roughness)
+{
+    l.type   = LOBE_BSDL_SHEEN;
+    l.N      = V3(comp->params[0], comp->params[1], comp->params[2]);
+    l.albedo = V3(comp->params[3], comp->params[4], comp->params[5]);
+    lobes::sheen_setup(l, -sg.I.val, comp->params[6], sg.backfacing != 0, path_roughness);
+    return f2u(comp->params[7]) == 0;   // mode 1 (Zeltner LTC sheen) is not restated
+}
+// evaluate_layer_opacity (shading.cpp:1198-1282): how much of the light the top stack of a
+// layer() takes; returns the weight held when the walk ends, as the reference does
+inline V3 evaluate_layer_opacity(const SG& sg, float path_roughness, const Clos* closure)
+{
+    if (closure == nullptr)
+        return V3(0.0f);
+    const int STACK_SIZE = 16;
+    int stack_idx        = 0;
+    const Clos* ptr_stack[STACK_SIZE];
+    V3 weight_stack[STACK_SIZE];
+    V3 weight(1.0f);
+    while (closure) {
+        switch (closure->id) {
+        case CL_MUL:
+            weight  = weight * ((const ClosMul*)closure)->weight;
+            closure = ((const ClosMul*)closure)->closure;
+            break;
+        case CL_ADD:
+            ptr_stack[stack_idx]      = ((const ClosAdd*)closure)->b;
+            weight_stack[stack_idx++] = weight;
+            closure                   = ((const ClosAdd*)closure)->a;
+            break;
+        default: {
+            const ClosComp* comp = (const ClosComp*)closure;
+            V3 w                 = comp->w;
+            switch (comp->id) {
+            case MX_LAYER_ID:
+                closure                   = clos_ptr_param(comp, 0);
+                ptr_stack[stack_idx]      = clos_ptr_param(comp, 2);
+                weight_stack[stack_idx++] = weight * w;
+                break;
+            case REFLECTION_ID:
+            case FRESNEL_REFLECTION_ID: {
+                Lobe l;
+                l.type = LOBE_REFLECTION;
+                l.N    = V3(comp->params[0], comp->params[1], comp->params[2]);
+                l.eta  = comp->id == FRESNEL_REFLECTION_ID ? comp->params[3] : 0.0f;
+                weight  = weight * (w * l.get_albedo(-sg.I.val));
+                closure = nullptr;
+                break;
+            }
+            case MX_SHEEN_ID: {
+                Lobe l;
+                sheen_from_component(l, comp, sg, path_roughness);
+                weight  = weight * (w * (V3(1.0f) - V3(l.emiss)));
+                closure = nullptr;
+                break;
+            }
+            default: closure = nullptr; break;   // unhandled BSDFs are opaque
+            }
+        }
+        }
+        if (closure == nullptr && stack_idx > 0) {
+            closure = ptr_stack[--stack_idx];
+            weight  = weight_stack[stack_idx];
+        }
+    }
+    return weight;
+}
+
 // process_bsdf_closure: explicit 16-deep stack, weights multiplied root->leaf
-inline void process_closure(const SG& sg, ShadingResult& result, const Clos* closure, bool light_only)
+inline void process_closure(const SG& sg, ShadingResult& result, const Clos* closure, bool light_only,
+                            float path_roughness = 0.0f)
 {
     if (!closure)
         return;
@@ -498,6 +584,8 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
             closure              = nullptr;
             if (comp->id == EMISSION_ID)
                 result.Le = result.Le + cw;
+            else if (comp->id == MX_UNIFORM_EDF_ID)
+                result.Le = result.Le + cw * V3(comp->params[0], comp->params[1], comp->params[2]);
             else if (!light_only) {
                 Lobe l;
                 l.N   = V3(comp->params[0], comp->params[1], comp->params[2]);
@@ -528,6 +616,22 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                     if (comp->id == MX_OREN_NAYAR_DIFFUSE_ID)
                         l.energy_compensation = f2u(comp->params[7]) != 0;
                     l.tf = TangentFrame::from_normal(lobes::bsdl_visible_normal(-sg.I.val, l.N, l.N));
+                    break;
+                }
+                case MX_SHEEN_ID: known = sheen_from_component(l, comp, sg, path_roughness); break;
+                case MX_LAYER_ID: {
+                    // layer(top, base): the base is attenuated by what the top stack takes
+                    // (shading.cpp:1645-1661)
+                    const Clos* top  = clos_ptr_param(comp, 0);
+                    const Clos* base = clos_ptr_param(comp, 2);
+                    V3 base_w = weight * (V3(1.0f) - clamp01(evaluate_layer_opacity(sg, path_roughness, top)));
+                    closure   = top;
+                    weight    = cw;
+                    if (!(base_w.x == 0 && base_w.y == 0 && base_w.z == 0)) {
+                        ptr_stack[stack_idx]      = base;
+                        weight_stack[stack_idx++] = base_w;
+                    }
+                    known = false;   // nothing to add for the layer node itself
                     break;
                 }
                 case PHONG_ID: l.type = LOBE_PHONG; l.exponent = comp->params[3]; break;
@@ -1012,7 +1116,7 @@ struct Renderer {
             execute(shaderID, sg, pool);
             ShadingResult result;
             bool last_bounce = b == S.max_bounces;
-            process_closure(sg, result, sg.Ci, last_bounce);
+            process_closure(sg, result, sg.Ci, last_bounce, r.roughness);
             const int nlights = S.nlightprims;
             float k           = 1;
             if (S.shader_is_light[shaderID] && nlights > 0) {
@@ -1060,7 +1164,7 @@ struct Renderer {
                             globals_from_hit(S, lsg, shadow_ray, sample.dist, lid, sample.u, sample.v);
                             execute(lshader, lsg, light_pool);
                             ShadingResult lres;
-                            process_closure(lsg, lres, lsg.Ci, true);
+                            process_closure(lsg, lres, lsg.Ci, true, r.roughness);
                             path_radiance = path_radiance + contrib * lres.Le;
                         }
                     }

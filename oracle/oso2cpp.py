@@ -362,12 +362,15 @@ CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
             ("transparent_bsdf", 0): "MX_TRANSPARENT_ID",
             # MaterialX closures registered from libbsdl lobes (BSDLtoOSL, shading.cpp:156-182)
             ("oren_nayar_diffuse_bsdf", 3): "MX_OREN_NAYAR_DIFFUSE_ID",
-            ("burley_diffuse_bsdf", 3): "MX_BURLEY_DIFFUSE_ID"}
+            ("burley_diffuse_bsdf", 3): "MX_BURLEY_DIFFUSE_ID",
+            ("sheen_bsdf", 3): "MX_SHEEN_ID", ("layer", 2): "MX_LAYER_ID",
+            ("uniform_edf", 1): "MX_UNIFORM_EDF_ID"}
 # keyword parameters per closure id, in slot order after the positional words; value
 # type "int" / "float".  Unspecified keywords are zero (llvm_gen_closure memsets the
 # parameter block when there is no prepare callback).  String keywords ("label") have
 # no effect on this path and take no slot.
-CLOSURE_KEYS = {"MX_OREN_NAYAR_DIFFUSE_ID": [("energy_compensation", "int")]}
+CLOSURE_KEYS = {"MX_OREN_NAYAR_DIFFUSE_ID": [("energy_compensation", "int")],
+                "MX_SHEEN_ID": [("mode", "int")]}
 
 
 class Gen:
@@ -1311,7 +1314,9 @@ class Gen:
         key = (name, len(pos))
         if key not in CLOSURES:
             raise NotImplementedError("closure %s with %d params is not registered" % key)
-        nwords = sum(a.t.ncomp for a in pos)
+        # closure-typed parameters (layer's top / base) are host pointers: two words each
+        wsize = lambda a: 2 if a.t.base == "closure color" else a.t.ncomp
+        nwords = sum(wsize(a) for a in pos)
         keys = CLOSURE_KEYS.get(CLOSURES[key], [])
         given = {}
         kw = params[len(pos):]
@@ -1332,7 +1337,7 @@ class Gen:
             if a.has_derivs:
                 e = "nd(%s)" % e
             self.w("    putp(c_->params + %d, %s);" % (off, e))
-            off += a.t.ncomp
+            off += wsize(a)
         for k, (kname, ktype) in enumerate(keys):
             a = given.get(kname)
             if a is not None and a.t.base == ktype and not a.t.arr:

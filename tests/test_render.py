@@ -30,7 +30,10 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          # "energy_compensation" keyword parameter (both branches), burley_diffuse_bsdf;
          # <Background resolution="1"> -> 32^2 importance table
          "render-mx-furnace-oren-nayar": ("mx_furnace_oren_nayar.xml", 384, 64, 16),
-         "render-mx-furnace-burley-diffuse": ("mx_furnace_burley.xml", 384, 64, 16)}
+         "render-mx-furnace-burley-diffuse": ("mx_furnace_burley.xml", 384, 64, 16),
+         # BASELINE config 4: layer() of sheen_bsdf / reflection / oren_nayar_diffuse_bsdf / diffuse,
+         # lit by a procedural sky + sun through the 1024^2 background importance table
+         "render-mx-layer": ("mx_layer.xml", 160, 120, 6)}
 # scenes of this repo (no reference golden image): the oracle restates the lobes
 # from shading.cpp and the device must equal the oracle.  render-microfacet itself
 # needs an HDR environment texture, which is outside this path.

@@ -69,6 +69,8 @@ SHADERS = {
     "mxon_matte": "render-mx-furnace-oren-nayar/matte.osl",
     "mxburley_matte": "render-mx-furnace-burley-diffuse/matte.osl",
     "mx_envmap": "render-mx-furnace-oren-nayar/envmap.osl",
+    "mxlayer_layer": "render-mx-layer/layer.osl",
+    "mxlayer_envmap": "render-mx-layer/envmap.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -88,6 +90,7 @@ SCENES = {
                                   {"matte": "mxon_matte", "envmap": "mx_envmap"}),
     "mx_furnace_burley.xml": ("render-mx-furnace-burley-diffuse/scene.xml",
                               {"matte": "mxburley_matte", "envmap": "mx_envmap"}),
+    "mx_layer.xml": ("render-mx-layer/scene.xml", {"layer": "mxlayer_layer", "envmap": "mxlayer_envmap"}),
 }
 # golden renders (half-float EXR in the reference; stored as float16 npz)
 RENDERS = {
@@ -99,6 +102,7 @@ RENDERS = {
     "render-oren-nayar": "render-oren-nayar/ref/out.exr",
     "render-mx-furnace-oren-nayar": "render-mx-furnace-oren-nayar/ref/out.exr",
     "render-mx-furnace-burley-diffuse": "render-mx-furnace-burley-diffuse/ref/out.exr",
+    "render-mx-layer": "render-mx-layer/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
