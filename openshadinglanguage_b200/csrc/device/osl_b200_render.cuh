@@ -55,6 +55,10 @@ struct RenderScene {
     float* bg_cols;    // res*res: per-row CDF over columns
     int bg_res;
     float bg_invres, bg_invjacobian;
+    // triangles in BVH leaf order, 3 x float4 each: vertex a (w = primitive id bits), b, c.
+    // The leaf loop reads them with three contiguous 16-byte loads instead of the reference's
+    // index -> triangle -> vertex gather (same values, one dependent load level instead of three).
+    const float4* leaf_tris;
 };
 
 // Path state: one 128-byte record (8 x float4) per path slot.  After the live
@@ -644,13 +648,19 @@ OSLD float xorf(float a, unsigned b) { return __int_as_float((int)(fbits(a) ^ b)
 
 OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsigned skip1, unsigned skip2)
 {
-    int stack_node[64];
+    // the stack keeps each pending node's (child, nprims) words, already fetched with its
+    // bounds when the parent was visited, so a pop costs no further node load
+    unsigned stack_child[64], stack_nprims[64];
     float stack_dist[64];
     Hit result;
     result.t  = tmax;
     result.u  = result.v = 0.0f;
     result.id = 0;
-    stack_node[0] = 0;
+    {
+        const float4 r1 = __ldg(S.bvh_nodes + 1);
+        stack_child[0]  = fbits(r1.z);
+        stack_nprims[0] = fbits(r1.w);
+    }
     stack_dist[0] = result.t;
     const V3 rdir = mkv(1 / dir.x, 1 / dir.y, 1 / dir.z);
     int kz = 0;
@@ -661,18 +671,52 @@ OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsig
     int kx = kz == 2 ? 0 : kz + 1;
     int ky = kx == 2 ? 0 : kx + 1;
     const float shx = vcomp(dir, kx) / vcomp(dir, kz), shy = vcomp(dir, ky) / vcomp(dir, kz), shz = vcomp(rdir, kz);
-    for (int sp = 1; sp != 0;) {
-        if (result.t < stack_dist[--sp])
-            continue;
-        int node    = stack_node[sp];
-        float4 n1   = __ldg(S.bvh_nodes + 2 * node + 1);
-        unsigned child = fbits(n1.z), nprims = fbits(n1.w);
-        if (nprims) {
+    // "while-while" traversal (Aila & Laine): every lane first walks inner nodes until it holds
+    // a leaf, then the warp tests triangles together.  Per ray the visiting order is exactly
+    // the reference's pop / test / push-far-then-near sequence; only the lock-step grouping of
+    // the lanes changes (leaf tests no longer serialise against other lanes' box tests).
+    int sp = 1;
+    for (;;) {
+        unsigned child = 0, nprims = 0;
+        while (sp != 0) {
+            if (result.t < stack_dist[--sp])
+                continue;
+            child  = stack_child[sp];
+            nprims = stack_nprims[sp];
+            if (nprims)
+                break;
+            // the two children are adjacent: 64 contiguous bytes
+            const float4* cn = S.bvh_nodes + 2 * (size_t)child;
+            const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
+            float d1 = 0, d2 = 0;
+            bool h1 = box_intersect(org, rdir, result.t, a0, a1, &d1);
+            bool h2 = box_intersect(org, rdir, result.t, b0, b1, &d2);
+            unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
+            if (d1 > d2) {
+                bool th = h1; h1 = h2; h2 = th;
+                float td = d1; d1 = d2; d2 = td;
+                unsigned tk = k1; k1 = k2; k2 = tk;
+                unsigned tn = n1; n1 = n2; n2 = tn;
+            }
+            stack_child[sp]  = k2;
+            stack_nprims[sp] = n2;
+            stack_dist[sp]   = d2;
+            sp += h2 ? 1 : 0;
+            stack_child[sp]  = k1;
+            stack_nprims[sp] = n1;
+            stack_dist[sp]   = d1;
+            sp += h1 ? 1 : 0;
+        }
+        if (!nprims)
+            break;
+        {
             for (unsigned i = 0; i < nprims; i++) {
-                unsigned id = __ldg(S.bvh_indices + child + i);
-                const V3 A = ld3(S.verts, __ldg(S.triangles + 3 * id)) - org;
-                const V3 B = ld3(S.verts, __ldg(S.triangles + 3 * id + 1)) - org;
-                const V3 C = ld3(S.verts, __ldg(S.triangles + 3 * id + 2)) - org;
+                const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
+                const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
+                const unsigned id = fbits(ta.w);
+                const V3 A = xyz(ta) - org;
+                const V3 B = xyz(tb) - org;
+                const V3 C = xyz(tc) - org;
                 const float Ax = vcomp(A, kx) - shx * vcomp(A, kz), Ay = vcomp(A, ky) - shy * vcomp(A, kz);
                 const float Bx = vcomp(B, kx) - shx * vcomp(B, kz), By = vcomp(B, ky) - shy * vcomp(B, kz);
                 const float Cx = vcomp(C, kx) - shx * vcomp(C, kz), Cy = vcomp(C, ky) - shy * vcomp(C, kz);
@@ -696,22 +740,6 @@ OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsig
                 result.v  = W * rcpDet;
                 result.id = id;
             }
-        } else {
-            int c1 = (int)child, c2 = c1 + 1;
-            float d1 = 0, d2 = 0;
-            bool h1 = box_intersect(org, rdir, result.t, __ldg(S.bvh_nodes + 2 * c1), __ldg(S.bvh_nodes + 2 * c1 + 1), &d1);
-            bool h2 = box_intersect(org, rdir, result.t, __ldg(S.bvh_nodes + 2 * c2), __ldg(S.bvh_nodes + 2 * c2 + 1), &d2);
-            if (d1 > d2) {
-                bool th = h1; h1 = h2; h2 = th;
-                float td = d1; d1 = d2; d2 = td;
-                int tc = c1; c1 = c2; c2 = tc;
-            }
-            stack_node[sp] = c2;
-            stack_dist[sp] = d2;
-            sp += h2 ? 1 : 0;
-            stack_node[sp] = c1;
-            stack_dist[sp] = d1;
-            sp += h1 ? 1 : 0;
         }
     }
     return result;

@@ -49,6 +49,7 @@ struct DevScene {
     float* bg_cols;
     int bg_res;
     float bg_invres, bg_invjacobian;
+    const void* leaf_tris;
 };
 enum { PATH_QUADS = 8 };  // 8 x float4 = 128 B of state per path (OSLD_PATH_QUADS)
 struct DevLaunch {
@@ -275,6 +276,19 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
     S.bvh_indices      = upload(d, h.bvh_indices, (size_t)h.ntris, ok);
     S.lightprims       = upload(d, h.lightprims, (size_t)h.nlightprims, ok);
     S.shader_is_light  = upload(d, h.shader_is_light, (size_t)h.nshaders, ok);
+    {
+        // triangles in BVH leaf order as 3 x float4 (vertex a with the primitive id in w, b, c)
+        std::vector<float> lt((size_t)12 * h.ntris, 0.0f);
+        for (int p = 0; p < h.ntris; ++p) {
+            unsigned id = h.bvh_indices[p];
+            for (int v = 0; v < 3; ++v) {
+                int vi = h.triangles[3 * id + v];
+                memcpy(&lt[(size_t)12 * p + 4 * v], h.verts + 3 * (size_t)vi, 12);
+            }
+            memcpy(&lt[(size_t)12 * p + 3], &id, 4);
+        }
+        S.leaf_tris = upload(d, lt.data(), lt.size(), ok);
+    }
     if (!ok) {
         free_dev(d);
         return set_error(B200_ERR_CUDA, "scene upload failed");
