@@ -458,6 +458,12 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
         if ((rc = launch(K_GENERATE, L.nslots, 256)) != B200_OK)
             return rc;
         long long live = L.nslots;
+        // The kernels take the live count from device memory; the host only needs it to size
+        // grids (an upper bound is enough: the count never grows) and to stop.  So several
+        // bounces are enqueued back to back and the count is read once per chunk: no host
+        // round trip per bounce, and the launches of a chunk overlap the execution of the
+        // previous kernels.  Empty trailing bounces cost a few microseconds each.
+        int since_sync = 0, chunk = 1;
         while (live > 0) {
             ++iters;
             L.queue_in  = qbuf[cur];
@@ -477,6 +483,10 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
             if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)
                 return rc;
             cur = (cur + 1) % 3;
+            if (++since_sync < chunk)
+                continue;
+            since_sync = 0;
+            chunk      = chunk < 8 ? chunk * 2 : 8;   // 1, 2, 4, 8, 8, ... bounces per read-back
             cudaMemcpyAsync(hcount, d.counters, sizeof(int), cudaMemcpyDeviceToHost, 0);
             if (cudaStreamSynchronize(0) != cudaSuccess) {
                 cudaError_t ce = cudaGetLastError();
