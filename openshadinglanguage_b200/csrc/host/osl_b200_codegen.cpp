@@ -1327,7 +1327,16 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigne
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_nocommit(void* gdst, const void* ssrc, unsigned bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent group have finished READING shared memory (double buffering)
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void wr(float* p, float v) { p[0] = v; }
 __device__ __forceinline__ void wr(float* p, int v) { ((int*)p)[0] = v; }
@@ -1460,23 +1469,47 @@ Gen::run()
         stage_words += c.stride / 4;
     out << "extern \"C\" __global__ void __launch_bounds__(" << B
         << ") osl_b200_group_kernel(const __grid_constant__ B200Launch L)\n{\n";
+    // Staging is per WARP and double buffered: a warp's 32 records are contiguous in the
+    // output arena, so lane 0 issues the warp's own TMA bulk store and only __syncwarp is
+    // needed - no CTA barrier on the path (the CTA-wide version spent 43 % of its stall
+    // cycles in barriers, profiles/ncu_layers4096_r01_details.txt).  The globals of the next
+    // tile are loaded before the current tile is shaded, so their latency hides behind it.
     if (g.stage_ok)
-        out << "    __shared__ __align__(128) float stage_[" << stage_words << " * " << B << "];\n";
+        out << "    __shared__ __align__(128) float stage_[2 * " << stage_words << " * " << B << "];\n";
     out << "    const long long ntiles_ = (L.npoints + " << B << " - 1) / " << B << ";\n";
     out << "    const bool staged_ = " << (g.stage_ok ? "(L.shadeindex == nullptr) && (L.stage_outputs != 0)" : "false") << ";\n";
-    out << "    for (long long tile_ = blockIdx.x; tile_ < ntiles_; tile_ += gridDim.x) {\n";
+    std::string ldn = ld.str();
+    for (size_t p = 0; (p = ldn.find("sg.", p)) != std::string::npos; p += 5)
+        ldn.replace(p, 3, "sgn_.");
+    for (size_t p = 0; (p = ldn.find(", i);", p)) != std::string::npos; p += 7)
+        ldn.replace(p, 5, ", in_);");
+    auto emit_fetch = [&](const char* tile_expr) {
+        out << "        {\n            const long long tn_ = " << tile_expr << ";\n";
+        out << "            const long long in_ = tn_ * " << B << " + threadIdx.x;\n";
+        out << "            actn_ = tn_ < ntiles_ && in_ < L.npoints;\n";
+        out << "            if (actn_) {\n";
+        out << "                sgn_.shadeindex = L.shadeindex ? __ldg(L.shadeindex + in_) : (int)(in_ + L.shadeindex_base);\n";
+        out << ldn;
+        out << "            }\n        }\n";
+    };
+    out << "    SG sgn_ = SG();\n    bool actn_ = false;\n";
+    emit_fetch("(long long)blockIdx.x");
+    out << "    int it_ = 0;\n";
+    out << "    for (long long tile_ = blockIdx.x; tile_ < ntiles_; tile_ += gridDim.x, ++it_) {\n";
     out << "        const long long i = tile_ * " << B << " + threadIdx.x;\n";
-    out << "        const bool active_ = i < L.npoints;\n";
-    out << "        SG sg;\n        GD gd;\n        gd.ran = 0u;\n";
+    out << "        const bool active_ = actn_;\n";
+    out << "        SG sg = sgn_;\n";
+    emit_fetch("tile_ + gridDim.x");
+    out << "        GD gd;\n        gd.ran = 0u;\n";
     out << "        if (active_) {\n";
-    out << "            sg.shadeindex = L.shadeindex ? __ldg(L.shadeindex + i) : (int)(i + L.shadeindex_base);\n";
-    out << ld.str();
     out << "            layer_" << (nlayers - 1) << "(sg, gd, L);\n";
     out << "        }\n";
     if (g.stage_ok) {
         out << "        if (staged_) {\n";
-        out << "            if (threadIdx.x == 0) bulk_wait_read();   // previous tile's bulk store has drained stage_\n";
-        out << "            __syncthreads();\n";
+        out << "            float* const stg_ = stage_ + (it_ & 1) * (" << stage_words << " * " << B << ");\n";
+        out << "            const int lane_ = threadIdx.x & 31, w0_ = threadIdx.x & ~31;\n";
+        out << "            if (lane_ == 0) bulk_wait_read1();   // this warp's store from two tiles ago has drained its buffer\n";
+        out << "            __syncwarp();\n";
         out << "            if (active_) {\n";
         long long woff = 0;
         for (const OutCluster& c : g.clusters) {
@@ -1487,29 +1520,31 @@ Gen::run()
                 out << "                    " << (s.out.derivs ? "wrd" : "wr") << "(rec_ + " << (s.out.offset - c.lo) / 4
                     << ", " << out_expr(k) << ");\n";
             }
-            out << "                    stage_record<" << W << ">(stage_ + " << woff << " * " << B << ", threadIdx.x, rec_);\n";
+            out << "                    stage_record<" << W << ">(stg_ + " << woff << " * " << B << ", threadIdx.x, rec_);\n";
             out << "                }\n";
             woff += W;
         }
         out << "            }\n";
-        out << "            fence_async_smem();\n            __syncthreads();\n";
-        out << "            const long long i0_ = tile_ * " << B << ";\n";
-        out << "            const long long cnt_ = (L.npoints - i0_) < " << B << " ? (L.npoints - i0_) : " << B << ";\n";
+        out << "            fence_async_smem();\n            __syncwarp();\n";
+        out << "            const long long i0_ = tile_ * " << B << " + w0_;   // first point of this warp\n";
+        out << "            long long cnt_ = L.npoints - i0_;\n";
+        out << "            cnt_ = cnt_ < 0 ? 0 : (cnt_ < 32 ? cnt_ : 32);\n";
         woff = 0;
         for (const OutCluster& c : g.clusters) {
             long long W = c.stride / 4;
-            out << "            {\n";
+            out << "            if (cnt_ > 0) {\n";
             out << "                char* gp_ = (char*)L.output_base + " << c.lo << "LL + L.out_adjust[" << c.outs[0] << "] + "
                 << c.stride << "LL * (i0_ + L.shadeindex_base);\n";
             out << "                const unsigned bytes_ = (unsigned)(cnt_ * " << c.stride << "LL);\n";
-            out << "                const float* sp_ = stage_ + " << woff << " * " << B << ";\n";
+            out << "                const float* sp_ = stg_ + " << woff << " * " << B << " + w0_ * " << W << ";\n";
             out << "                if ((((unsigned long long)gp_ | bytes_) & 15ull) == 0) {\n";
-            out << "                    if (threadIdx.x == 0) bulk_store(gp_, sp_, bytes_);\n";
+            out << "                    if (lane_ == 0) bulk_store_nocommit(gp_, sp_, bytes_);\n";
             out << "                } else {\n";
-            out << "                    for (unsigned w_ = threadIdx.x; w_ < bytes_ / 4; w_ += " << B << ") ((float*)gp_)[w_] = sp_[w_];\n";
+            out << "                    for (unsigned w_ = lane_; w_ < bytes_ / 4; w_ += 32) ((float*)gp_)[w_] = sp_[w_];\n";
             out << "                }\n            }\n";
             woff += W;
         }
+        out << "            if (lane_ == 0) bulk_commit();   // one bulk group per warp and tile\n";
         out << "        } else\n";
     }
     out << "        if (active_) {\n";
@@ -1521,7 +1556,7 @@ Gen::run()
     out << "        }\n";
     out << "    }\n";
     if (g.stage_ok)
-        out << "    if (staged_ && threadIdx.x == 0) bulk_wait_all();\n";
+        out << "    if (staged_ && (threadIdx.x & 31) == 0) bulk_wait_all();\n";
     out << "}\n";
     return out.str();
 }

@@ -482,7 +482,7 @@ Group::finalize()
         stage_ok &= c.dense;
         stage_bytes += c.stride * block;
     }
-    if (stage_bytes > 48 * 1024)
+    if (2 * stage_bytes > 48 * 1024)  // double-buffered staging must fit static shared memory
         stage_ok = false;
     for (int i = n - 1; i >= 0; --i) {
         track_derivs(layers[i]);
