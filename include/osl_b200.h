@@ -155,6 +155,16 @@ int b200_group_execute(b200_group* g, int device, void* stream, long long npoint
 int b200_group_execute_host(b200_group* g, int device, long long npoints,
                             const b200_globals* sg, void* output_base);
 
+/* Text written by the group's printf() ops on `device` since the previous call, ordered by
+ * shade index and, within a point, by execution order (what single-threaded testshade
+ * prints).  The device only records (format id, argument words); formatting happens here,
+ * like the reference's journal (src/include/OSL/journal.h, rs_printfmt in
+ * rs_free_function.h).  Synchronises the device.  The pointer is owned by the group and
+ * valid until the next call.  Recording is opt-in: group option journal=1 (default buffer,
+ * 4 Mi words) or journal=WORDS; without it printf ops are dropped and reported in the
+ * group's warnings, so production launches never pay for a debugging aid. */
+const char* b200_group_journal(b200_group* g, int device);
+
 /* Number of kernel launches issued by this library so far (bench accounting) */
 long long b200_launch_count(void);
 

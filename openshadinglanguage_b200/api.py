@@ -248,6 +248,14 @@ class ShaderGroup:
         g = _fill_globals(n, varying, uniform, plane_stride)
         _check(lib().b200_group_execute_host(self._h, device, n, ctypes.byref(g), _ptr(output)))
 
+    def journal(self, device=0):
+        """Text printed by the group's printf() ops since the previous call, in shade index
+        order (b200_group_journal).  Synchronises the device."""
+        L = lib()
+        L.b200_group_journal.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.b200_group_journal.restype = ctypes.c_char_p
+        return L.b200_group_journal(self._h, device).decode(errors="replace")
+
 
 def shadeop_noise(kind, outdim, indim, n, inp, out, period=None, derivs=False, stream=None):
     """Batch noise over device SoA planes (b200_shadeop_noise)."""

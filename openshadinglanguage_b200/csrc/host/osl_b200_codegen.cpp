@@ -332,6 +332,8 @@ private:
     }
 
     void emit_matrix_op(const Opcode& op);
+    void emit_printf(const Opcode& op);
+    bool journal_ok = false;  // grid kernels write printf records to the launch's journal
     void gen_layer(int layer);
     void emit_block(int b, int e, const Ctx* ctx);
     void useparams(const Opcode& op);
@@ -672,6 +674,50 @@ Gen::op_noise(const Opcode& op, bool periodic)
         w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", out_[" + std::to_string(c) + "]);");
 }
 
+// printf -> one journal record: [words][shadeindex][sequence][format id][argument words].
+// The reference's device path does the same through its journal (src/include/OSL/journal.h,
+// rs_printfmt) and formats on the host; llvm_gen_printf (llvm_gen.cpp:350-700) fixes the
+// per-type conversion rules that the host decoder (osl_b200_cabi.cu) applies.
+void
+Gen::emit_printf(const Opcode& op)
+{
+    const Symbol& f = S(op.args[0]);
+    if (f.type.base != Base::String || !f.const_value())
+        unsupported("printf with a format that is not known at compile time");
+    JournalFormat jf;
+    jf.fmt = f.svals.empty() ? "" : f.svals[0];
+    std::vector<std::string> words;
+    for (size_t a = 1; a < op.args.size(); ++a) {
+        const Symbol& s = S(op.args[a]);
+        JournalArg ja;
+        ja.base     = s.type.base;
+        ja.ncomp    = s.type.ncomp();
+        ja.arraylen = s.type.arraylen;
+        if (s.type.base == Base::Closure || s.type.base == Base::Void)
+            unsupported("printf of a closure");
+        jf.args.push_back(ja);
+        int n = s.type.arraylen ? s.type.arraylen : 1;
+        for (int e = 0; e < n; ++e) {
+            std::string el = R(op.args[a]) + (s.type.arraylen ? "[" + std::to_string(e) + "]" : "");
+            if (s.type.base == Base::Int || s.type.base == Base::String)
+                words.push_back("(unsigned)(" + el + ")");
+            else if (s.type.base == Base::Matrix)
+                for (int c = 0; c < 16; ++c)
+                    words.push_back("__float_as_uint(" + el + ".x[" + std::to_string(c / 4) + "][" + std::to_string(c % 4) + "])");
+            else
+                for (int c = 0; c < ja.ncomp; ++c)
+                    words.push_back("__float_as_uint(nd(getc(" + el + ", " + std::to_string(c) + ")))");
+        }
+    }
+    int id = (int)g.jformats.size();
+    g.jformats.push_back(jf);
+    w("{ unsigned* j_ = jr_reserve(L, sg, " + std::to_string(id) + "u, " + std::to_string(words.size()) + "u);");
+    w("  if (j_) {");
+    for (size_t k = 0; k < words.size(); ++k)
+        w("    j_[" + std::to_string(k) + "] = " + words[k] + ";");
+    w("  } }");
+}
+
 // Matrix shadeops (opmatrix.cpp; llvm_gen_matrix, llvm_gen_getmatrix, llvm_gen_transform,
 // llvm_gen_mxcompref/assign).  Space names must be compile-time constants; their matrices
 // come from the launch block (see space_matrix).
@@ -682,6 +728,10 @@ Gen::emit_matrix_op(const Opcode& op)
     auto A               = [&](int i) -> Symbol& { return S(op.args[i]); };
     auto fl              = [&](int i) { return comp(op.args[i], 0, false); };
     auto is_m            = [&](int i) { return A(i).type.base == Base::Matrix; };
+    if (n == "printf" && journal_ok) {
+        emit_printf(op);
+        return;
+    }
     const std::string d  = R(op.args[0]);
     if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
         std::string msg = "op '" + n + "' ignored on device (no journal yet) in layer '" + L->layername + "'";
@@ -1174,9 +1224,11 @@ Gen::emit_op(const Opcode& op)
         }
         w("}");
         w(R(op.args[0]) + " = c_;");
+    } else if (n == "printf" && journal_ok) {
+        emit_printf(op);
     } else if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
-        // Device-side journal is a "next" row: the op has no
-        // effect on shading results, so it is dropped with a recorded warning.
+        // error / warning / fprintf, and printf inside renderer materials, have no effect on
+        // shading results: dropped with a recorded warning.
         std::string msg = "op '" + n + "' ignored on device (no journal yet) in layer '" + L->layername + "'";
         bool dup = false;
         for (auto& s : g.warnings)
@@ -1274,6 +1326,10 @@ struct B200Launch {
     // not know the name (identity is stored)
     float xf[%MAXSPACES%][2][16];
     int xf_ok[%MAXSPACES%];
+    // printf journal: [0] = words used (bumped atomically), [1] = overflow flag, records from [2]
+    unsigned* journal;
+    unsigned journal_words;
+    unsigned pad2_;
 };
 
 __device__ __forceinline__ float ldf(const B200Launch& L, int f, int c, long long i)
@@ -1296,6 +1352,27 @@ const char* OUTPUT_HELPERS = R"CUDA(
 __device__ __forceinline__ float* outp(const B200Launch& L, const SG& sg, int k, long long offset, long long stride)
 {
     return (float*)((char*)L.output_base + offset + L.out_adjust[k] + stride * (long long)sg.shadeindex);
+}
+// ---- printf journal -------------------------------------------------------------
+// Reserve one record and fill its header; returns where the argument words go, or
+// nullptr when there is no journal or it is full (the overflow flag is raised).
+__device__ __forceinline__ unsigned* jr_reserve(const B200Launch& L, SG& sg, unsigned fmt, unsigned nargs)
+{
+    if (!L.journal)
+        return nullptr;
+    const unsigned n  = nargs + 4u;
+    const unsigned at = atomicAdd(L.journal, n);
+    const unsigned seq = sg.jseq++;
+    if (at + n + 2u > L.journal_words) {
+        L.journal[1] = 1u;
+        return nullptr;
+    }
+    unsigned* r = L.journal + 2 + at;
+    r[0] = n;
+    r[1] = (unsigned)sg.shadeindex;
+    r[2] = seq;
+    r[3] = fmt;
+    return r + 4;
 }
 // ---- shared-memory staging of dense output records + TMA bulk store ----------
 // Each thread drops its record (W words) at stage[t*W ..]; 16-byte stores when W%4==0
@@ -1356,6 +1433,7 @@ Gen::run()
     if (nlayers > 32)
         throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
     // layer bodies first (they record which globals are read)
+    journal_ok = g.journal_enabled;
     std::ostringstream bodies;
     std::string gd = "struct GD {\n    unsigned ran;\n";
     for (int l = 0; l < nlayers; ++l) {
@@ -1381,7 +1459,7 @@ Gen::run()
     // SG holds only what is read
     auto rd = [&](int f) { return g.globals_read.count(f) != 0; };
     std::ostringstream sg, ld;
-    sg << "struct SG {\n    int shadeindex;\n";
+    sg << "struct SG {\n    int shadeindex;\n    unsigned jseq;   // printf records written so far by this point\n";
     struct TD {
         const char* name;
         int f, dx, dy;
@@ -1498,7 +1576,7 @@ Gen::run()
     out << "    for (long long tile_ = blockIdx.x; tile_ < ntiles_; tile_ += gridDim.x, ++it_) {\n";
     out << "        const long long i = tile_ * " << B << " + threadIdx.x;\n";
     out << "        const bool active_ = actn_;\n";
-    out << "        SG sg = sgn_;\n";
+    out << "        SG sg = sgn_;\n        sg.jseq = 0u;\n";
     emit_fetch("tile_ + gridDim.x");
     out << "        GD gd;\n        gd.ran = 0u;\n";
     out << "        if (active_) {\n";

@@ -115,6 +115,18 @@ struct OutCluster {
     bool dense = false;                    // fields tile [lo, lo+stride) exactly
 };
 
+// One printf() site of the group: the format string and the layout of the argument words
+// its device record carries (the journal is decoded and formatted on the host).
+struct JournalArg {
+    Base base    = Base::Float;
+    int ncomp    = 1;
+    int arraylen = 0;
+};
+struct JournalFormat {
+    std::string fmt;
+    std::vector<JournalArg> args;
+};
+
 struct Group {
     std::string name;
     std::vector<OutCluster> clusters;
@@ -130,6 +142,8 @@ struct Group {
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
     bool uses_colorsystem  = false;            // set by codegen: luminance / blackbody / transformc ...
     std::string colorspace = "Rec709";         // ShadingSystem attribute "colorspace"
+    std::vector<JournalFormat> jformats;       // printf sites (id = index), grid kernels only
+    bool journal_enabled = false;              // group option journal=WORDS (> 0): record printf output
     std::vector<std::string> spaces;           // named coordinate systems referenced (launch-block slots)
     std::string commonspace_synonym = "world"; // ShadingSystem attribute "commonspace"
 

@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -120,6 +121,9 @@ struct LaunchBlock {  // must match B200Launch in the generated code
     int pad_;
     float xf[B200_MAX_SPACES][2][16];
     int xf_ok[B200_MAX_SPACES];
+    unsigned* journal;
+    unsigned journal_words;
+    unsigned pad2_;
 };
 
 }  // namespace
@@ -147,6 +151,10 @@ struct b200_group {
     std::mutex mu;
     std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
     int sm_count[64] = { 0 };
+    // printf journal (only for groups that have printf sites): one device buffer per device
+    unsigned journal_words = 4u << 20;   // option journal=WORDS
+    std::map<int, unsigned*> journal_dev;
+    std::string journal_text;
     // staging buffers for execute_host (per group, grown on demand)
     struct Stage {
         int device       = -1;
@@ -245,6 +253,13 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             G->g.fma = atoi(opt["fma"].c_str()) != 0;
         if (opt.count("colorspace"))
             G->g.colorspace = opt["colorspace"];
+        if (opt.count("journal")) {
+            // journal=1 asks for the default size, any larger value is the size in words
+            unsigned long jw     = strtoul(opt["journal"].c_str(), nullptr, 10);
+            G->g.journal_enabled = jw > 0;
+            if (jw > 1)
+                G->journal_words = (unsigned)jw;
+        }
         if (opt.count("block"))
             G->block = atoi(opt["block"].c_str());
         if (opt.count("stage"))
@@ -311,7 +326,121 @@ b200_group_destroy(b200_group* g)
     for (auto s : g->stage.streams)
         if (s)
             cudaStreamDestroy(s);
+    for (auto& kv : g->journal_dev)
+        if (kv.second)
+            cudaFree(kv.second);
     delete g;
+}
+
+// ---- printf journal: decode + format on the host -----------------------------------
+// One conversion per argument component, components and array elements separated by a
+// blank, ints through %d-family conversions print as ints and otherwise as floats, floats
+// through %d/%i/%x print truncated (llvm_gen_printf, llvm_gen.cpp:350-700).
+static void
+journal_format(const Group& g, const JournalFormat& jf, const unsigned* w, size_t nw, std::string& out)
+{
+    const std::string& f = jf.fmt;
+    size_t ai = 0, wi = 0;
+    char buf[1100];
+    for (size_t i = 0; i < f.size();) {
+        if (f[i] != '%') {
+            out += f[i++];
+            continue;
+        }
+        if (i + 1 < f.size() && f[i + 1] == '%') {
+            out += '%';
+            i += 2;
+            continue;
+        }
+        size_t j = i + 1;
+        while (j < f.size() && !strchr("cdefgimnopsuvxXEG", f[j]))
+            ++j;
+        std::string spec = f.substr(i, j + 1 - i);
+        char conv        = j < f.size() ? f[j] : 'g';
+        i                = j + 1;
+        if (ai >= jf.args.size())
+            continue;
+        const JournalArg& a = jf.args[ai++];
+        int nel             = a.arraylen ? a.arraylen : 1;
+        bool first          = true;
+        for (int e = 0; e < nel; ++e)
+            for (int c = 0; c < a.ncomp; ++c, ++wi) {
+                if (wi >= nw)
+                    return;
+                if (!first)
+                    out += ' ';
+                first = false;
+                if (a.base == Base::String) {
+                    std::string s = spec.substr(0, spec.size() - 1) + "s";
+                    unsigned id   = w[wi];
+                    snprintf(buf, sizeof buf, s.c_str(), id < g.strings.size() ? g.strings[id].c_str() : "");
+                } else if (a.base == Base::Int) {
+                    int v = (int)w[wi];
+                    if (conv == 'd' || conv == 'i')
+                        snprintf(buf, sizeof buf, spec.c_str(), v);
+                    else
+                        snprintf(buf, sizeof buf, spec.c_str(), (double)v);
+                } else {
+                    float v;
+                    memcpy(&v, &w[wi], 4);
+                    if (conv == 'd' || conv == 'i' || conv == 'x' || conv == 'X')
+                        snprintf(buf, sizeof buf, spec.c_str(), (int)v);
+                    else
+                        snprintf(buf, sizeof buf, spec.c_str(), (double)v);
+                }
+                out += buf;
+            }
+    }
+}
+
+/* Text printed by the group's printf ops since the previous call, ordered by shade index
+ * and, within a point, by execution order - what single-threaded testshade prints.
+ * Synchronises `device`.  The pointer stays valid until the next call on this group. */
+const char*
+b200_group_journal(b200_group* g, int device)
+{
+    if (!g)
+        return "";
+    g->journal_text.clear();
+    auto it = g->journal_dev.find(device);
+    if (it == g->journal_dev.end() || !it->second)
+        return g->journal_text.c_str();
+    cudaSetDevice(device);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        fail(B200_ERR_CUDA, std::string("journal: ") + cudaGetErrorString(cudaGetLastError()));
+        return g->journal_text.c_str();
+    }
+    unsigned head[2] = { 0, 0 };
+    cudaMemcpy(head, it->second, sizeof head, cudaMemcpyDeviceToHost);
+    size_t used = head[0];
+    if (used > (size_t)g->journal_words - 2)
+        used = (size_t)g->journal_words - 2;
+    std::vector<unsigned> rec(used);
+    if (used)
+        cudaMemcpy(rec.data(), it->second + 2, used * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    struct Ref {
+        unsigned si, seq;
+        size_t at;
+    };
+    std::vector<Ref> refs;
+    for (size_t p = 0; p + 4 <= used;) {
+        unsigned n = rec[p];
+        if (n < 4 || p + n > used)
+            break;  // unwritten space: a record that did not fit
+        refs.push_back({ rec[p + 1], rec[p + 2], p });
+        p += n;
+    }
+    std::stable_sort(refs.begin(), refs.end(),
+                     [](const Ref& a, const Ref& b) { return a.si != b.si ? (int)a.si < (int)b.si : a.seq < b.seq; });
+    for (const Ref& r : refs) {
+        unsigned fmt = rec[r.at + 3];
+        if (fmt < g->g.jformats.size())
+            journal_format(g->g, g->g.jformats[fmt], rec.data() + r.at + 4, rec[r.at] - 4, g->journal_text);
+    }
+    if (head[1])
+        g->journal_text += "[journal overflow: output truncated; raise the group option journal=WORDS]\n";
+    cudaMemset(it->second, 0, sizeof(unsigned) * (2 + used));
+    return g->journal_text.c_str();
 }
 
 const char*
@@ -414,6 +543,21 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
         }
         memcpy(L.xf[k][0], m.x, sizeof m.x);
         memcpy(L.xf[k][1], mi.x, sizeof mi.x);
+    }
+    L.journal       = nullptr;
+    L.journal_words = 0;
+    L.pad2_         = 0;
+    if (!g->g.jformats.empty() && g->journal_words > 16) {
+        std::lock_guard<std::mutex> lk(g->mu);
+        unsigned*& jb = g->journal_dev[device];
+        if (!jb) {
+            cudaSetDevice(device);
+            if (cudaMalloc(&jb, sizeof(unsigned) * (size_t)g->journal_words) != cudaSuccess
+                || cudaMemset(jb, 0, sizeof(unsigned) * (size_t)g->journal_words) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMalloc(journal) failed");
+        }
+        L.journal       = jb;
+        L.journal_words = g->journal_words;
     }
     int sms = (device >= 0 && device < 64 && g->sm_count[device]) ? g->sm_count[device] : 148;
     // grid: one CTA per tile of `block` points, capped at 8 CTAs per SM (a

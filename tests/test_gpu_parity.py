@@ -263,6 +263,66 @@ def test_matrix_ops_match_oracle(b200lib, cuda_device):
     assert np.array_equal(host.view(np.uint32), want.view(np.uint32))
 
 
+TEXT_CASES = {
+    # golden name: (layers, connections, grid, harness options)
+    "hash": ([("hash_test", "l0")], (), (2, 2), dict(center=True)),
+    "layers": ([("layers_a", "alayer"), ("layers_b", "blayer")],
+               [("alayer", "f_out", "blayer", "f_in"), ("alayer", "c_out", "blayer", "c_in")], (1, 1), {}),
+    "color": ([("color_test", "l0")], (), (1, 1), {}),
+    "transformc": ([("transformc_test", "l0")], (), (1, 1), {}),
+    "matrix": ([("matrix_test", "l0")], (), (2, 2), {}),
+    "transform": ([("transform_test", "l0")], (), (2, 2), {}),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TEXT_CASES) + ["layers-lazy"])
+def test_printf_journal_reproduces_reference_text_goldens(b200lib, cuda_device, case):
+    """The device records printf() arguments in a journal, the host formats them: the text
+    of the reference's own `testshade` text tests comes out of the GPU path character for
+    character (strict mode).  Only the error-handler line of testsuite/matrix
+    ("ERROR: Unknown transformation ...") is not produced: errors are not journaled."""
+    import torch
+    if case == "layers-lazy":
+        layers, conns, _ = helpers.layers_group(with_outputs=False)
+        grid, gl = (2, 2), {}
+    else:
+        spec, conns, grid, gl = TEXT_CASES[case]
+        layers = [dict(oso=helpers.oso(s), name=n) for s, n in spec]
+    g = b200lib.ShaderGroup(layers, conns, (), options="fma=0,journal=1")
+    assert not [w for w in g.warnings if "printf" in w]
+    var, uni = b200lib.grid_globals(grid[0], grid[1], **gl)
+    n = grid[0] * grid[1]
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(16, dtype=torch.float32, device=cuda_device)
+    g.execute(n, dvar, uni, out)
+    got = g.journal()
+    want = "\n".join(l for l in helpers.golden_text(case).split("\n")
+                     if not l.startswith(("Compiled", "Connect", "ERROR:")))
+    assert got.rstrip("\n") == want.rstrip("\n")
+    assert g.journal() == ""          # drained
+    # the oracle prints the same
+    og = oracle.OracleGroup(layers, conns)
+    ovar, ouni = oracle.testshade_globals(grid[0], grid[1], **gl)
+    otxt = "\n".join(l for l in og.run_capture(n, ovar, ouni).split("\n") if not l.startswith("ERROR:"))
+    assert got.rstrip("\n") == otxt.rstrip("\n")
+
+
+def test_printf_journal_orders_by_point_and_reports_overflow(b200lib, cuda_device):
+    import torch
+    layers = [dict(oso=helpers.oso("hash_test"), name="l0")]
+    var, uni = b200lib.grid_globals(64, 64, center=True)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(16, dtype=torch.float32, device=cuda_device)
+    g = b200lib.ShaderGroup(layers, (), (), options="fma=0,journal=1")
+    g.execute(64 * 64, dvar, uni, out)
+    big = g.journal()
+    want = oracle.OracleGroup(layers).run_capture(64 * 64, *oracle.testshade_globals(64, 64, center=True))
+    assert big == want                # 4096 points, printed in shade-index order
+    small = b200lib.ShaderGroup(layers, (), (), options="fma=0,journal=4096")
+    small.execute(64 * 64, dvar, uni, out)
+    assert "journal overflow" in small.journal()
+
+
 def test_host_path_matches_device_path(b200lib, cuda_device):
     layers, outputs, res = helpers.image_case_group("noise")
     a = _run_gpu_group(b200lib, cuda_device, layers, (), outputs, res, "fma=0", 3)
