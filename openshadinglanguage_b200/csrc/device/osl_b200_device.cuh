@@ -875,6 +875,10 @@ OSLD Df o_fmod(Df a, Df b) { return mkd(safe_fmod(a.val, b.val), a.dx, a.dy); }
 OSLD_PROMOTE2(fmod)
 OSLD int o_fmod(int a, int b) { return o_mod(a, b); }
 OSLD float o_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+// step has no derivative form (osl_step_fff only): the result's derivatives are zero
+OSLD float o_step(Df edge, Df x) { return o_step(edge.val, x.val); }
+OSLD float o_step(float edge, Df x) { return o_step(edge, x.val); }
+OSLD float o_step(Df edge, float x) { return o_step(edge.val, x); }
 OSLD float o_min(float a, float b) { return a <= b ? a : b; }
 OSLD float o_max(float a, float b) { return a > b ? a : b; }
 OSLD Df o_min(Df a, Df b) { return a.val <= b.val ? a : b; }

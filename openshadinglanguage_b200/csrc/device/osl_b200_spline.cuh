@@ -133,4 +133,63 @@ OSLD float spline_inverse(float y, const float* knots, int knot_count, int type)
     return x;
 }
 
+// osl_splineinverse_dfdff: the same search on Dual2<float> - comparisons look at the values,
+// the arithmetic carries the derivatives of y through the regula falsi steps
+OSLD Df spline_inverse(Df y, const float* knots, int knot_count, int type)
+{
+    const int step = spline_step(type);
+    int lowindex   = step == 1 ? 1 : 0;
+    int highindex  = step == 1 ? knot_count - 2 : knot_count - 1;
+    bool incr      = knots[1] < knots[knot_count - 2];
+    if (incr) {
+        if (y.val <= knots[lowindex]) return mkd(0.0f);
+        if (y.val >= knots[highindex]) return mkd(1.0f);
+    } else {
+        if (y.val >= knots[lowindex]) return mkd(0.0f);
+        if (y.val <= knots[highindex]) return mkd(1.0f);
+    }
+    int nsegs     = (knot_count - 4) / step + 1;
+    float nseginv = 1.0f / (float)nsegs;
+    Df r0 = mkd(0.0f), x = mkd(0.0f);
+    for (int sg = 0; sg < nsegs; ++sg) {
+        Df r1 = mkd(nseginv * (float)(sg + 1));
+        Df xmin = r0, xmax = r1, v0, v1;
+        spline_eval(v0, xmin, knots, knot_count, type);
+        spline_eval(v1, xmax, knots, knot_count, type);
+        x = xmin;
+        Df v = v0;
+        bool increasing = (v0.val < v1.val);
+        Df vmin = increasing ? v0 : v1, vmax = increasing ? v1 : v0;
+        bool bracketed = (y.val >= vmin.val && y.val <= vmax.val);
+        if (bracketed) {
+            if (fabsf((v0 - v1).val) < 1.0e-6f)
+                return x;
+            for (int it = 0; it < 32; ++it) {
+                Df t;
+                if (it < 24) {
+                    t = (y - v0) / (v1 - v0);
+                    if (t.val <= 0.0f || t.val >= 1.0f)
+                        t = mkd(0.5f);
+                } else
+                    t = mkd(0.5f);
+                x = xmin * (mkd(1.0f) - t) + xmax * t;
+                spline_eval(v, x, knots, knot_count, type);
+                if ((v.val < y.val) == increasing) {
+                    xmin = x;
+                    v0   = v;
+                } else {
+                    xmax = x;
+                    v1   = v;
+                }
+                if (fabsf((xmax - xmin).val) < 1.0e-6f || fabsf((v - y).val) < 1.0e-6f)
+                    return x;
+            }
+            return x;
+        }
+        x  = ((y.val < vmin.val) == increasing) ? xmin : xmax;
+        r0 = r1;
+    }
+    return x;
+}
+
 }  // namespace osld

@@ -928,6 +928,21 @@ Gen::emit_op(const Opcode& op)
         g.uses_colorsystem = true;
         w("assign(" + R(op.args[0]) + ", color_" + std::string(n == "blackbody" ? "blackbody" : "wavelength") + "(osl_cs_, "
           + comp(op.args[1], 0, false) + "));");
+    } else if ((n == "point" || n == "vector" || n == "normal") && op.args.size() == 5) {
+        // llvm_gen_construct_triple (llvm_gen.cpp:1871-1933): build the triple, then
+        // osl_transform_triple(space -> "common") on it, in place
+        bool dv = false;
+        if (A(0).has_derivs)
+            for (int a = 2; a < 5; ++a)
+                dv |= A(a).has_derivs;
+        for (int c = 0; c < 3; ++c)
+            w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", " + comp(op.args[2 + c], 0, dv) + ");");
+        if (!(space_is(op.args[1], "common") || space_is(op.args[1], g.commonspace_synonym.c_str()))) {
+            auto mf        = space_matrix(op.args[1], false);
+            const char* vt = n == "point" ? "0" : (n == "vector" ? "1" : "2");
+            std::string d  = R(op.args[0]);
+            w("if (" + mf.second + ") assign(" + d + ", m44_transform(" + mf.first + ", " + d + ", " + vt + "));");
+        }
     } else if (n == "color" || n == "point" || n == "vector" || n == "normal") {
         if (op.args.size() != 4)
             unsupported("triple constructor with a coordinate-system name");
@@ -1043,7 +1058,7 @@ Gen::emit_op(const Opcode& op)
         w(R(op.args[0]) + " = " + std::to_string(A(1).conn_layer >= 0 ? 1 : (A(1).connected_down ? 2 : 0)) + ";");
     } else if (n == "isconstant") {
         need(2);
-        w(R(op.args[0]) + " = " + std::to_string(A(1).is_const() ? 1 : 0) + ";");
+        w(R(op.args[0]) + " = " + std::to_string(A(1).const_value() ? 1 : 0) + ";");
     } else if (n == "hash") {
         size_t nin = op.args.size() - 1;
         std::string e;
@@ -1096,7 +1111,9 @@ Gen::emit_op(const Opcode& op)
         std::string len = std::to_string(knots.type.arraylen);
         if (n == "splineinverse") {
             w("float k_[" + len + "]; for (int i_ = 0; i_ < " + len + "; ++i_) k_[i_] = nd(" + R(kn) + "[i_]);");
-            w("assign(" + R(op.args[0]) + ", spline_inverse(nd(" + R(op.args[2]) + "), k_, " + count + ", " + bt + "));");
+            // derivatives only flow from x (osl_splineinverse_dfdff / _dfdfdf ignore knot derivs)
+            std::string xi = (d.has_derivs && x.has_derivs) ? R(op.args[2]) : "nd(" + R(op.args[2]) + ")";
+            w("assign(" + R(op.args[0]) + ", spline_inverse(" + xi + ", k_, " + count + ", " + bt + "));");
         } else {
             std::string xe = R(op.args[2]);
             if (x.has_derivs && !dv)

@@ -376,7 +376,7 @@ journal_format(const Group& g, const JournalFormat& jf, const unsigned* w, size_
                     snprintf(buf, sizeof buf, s.c_str(), id < g.strings.size() ? g.strings[id].c_str() : "");
                 } else if (a.base == Base::Int) {
                     int v = (int)w[wi];
-                    if (conv == 'd' || conv == 'i')
+                    if (strchr("dioxXuc", conv))
                         snprintf(buf, sizeof buf, spec.c_str(), v);
                     else
                         snprintf(buf, sizeof buf, spec.c_str(), (double)v);

@@ -493,6 +493,10 @@ inline float o_fmod(float a, float b) { return safe_fmod(a, b); }
 inline Df o_fmod(const Df& a, const Df& b) { return Df(safe_fmod(a.val, b.val), a.dx, a.dy); }
 inline int o_fmod(int a, int b) { return o_mod(a, b); }
 inline float o_step(float edge, float x) { return x < edge ? 0.0f : 1.0f; }
+// step has no derivative form (osl_step_fff only): the result's derivatives are zero
+inline float o_step(const Df& edge, const Df& x) { return o_step(edge.val, x.val); }
+inline float o_step(float edge, const Df& x) { return o_step(edge, x.val); }
+inline float o_step(const Df& edge, float x) { return o_step(edge.val, x); }
 // llvm_gen_minmax: min = select(x<=y, x, y), max = select(x>y, x, y)
 inline float o_min(float a, float b) { return a <= b ? a : b; }
 inline float o_max(float a, float b) { return a > b ? a : b; }
@@ -837,6 +841,71 @@ inline float spline_inverse(float y, const float* knots, int knot_count, int typ
     float r0 = 0.0f, x = 0.0f;
     for (int s = 0; s < nsegs; ++s) {
         float r1 = nseginv * (s + 1);
+        bool brack;
+        x = oiio_invert(S, y, r0, r1, 32, 1.0e-6f, &brack);
+        if (brack)
+            return x;
+        r0 = r1;
+    }
+    return x;
+}
+// osl_splineinverse_dfdff: the same search instantiated on Dual2<float> - comparisons look at
+// the values, the arithmetic carries the derivatives of y through the regula falsi steps
+template<class F> inline Df oiio_invert(F& func, const Df& y, Df xmin, Df xmax, int maxiters, float eps, bool* brack)
+{
+    Df v0 = func(xmin), v1 = func(xmax);
+    Df x = xmin, v = v0;
+    bool increasing = (v0.val < v1.val);
+    Df vmin = increasing ? v0 : v1, vmax = increasing ? v1 : v0;
+    bool bracketed = (y.val >= vmin.val && y.val <= vmax.val);
+    if (brack) *brack = bracketed;
+    if (!bracketed)
+        return ((y.val < vmin.val) == increasing) ? xmin : xmax;
+    if (std::fabs((v0 - v1).val) < eps)
+        return x;
+    int rfiters = (3 * maxiters) / 4;
+    for (int iters = 0; iters < maxiters; ++iters) {
+        Df t;
+        if (iters < rfiters) {
+            t = (y - v0) / (v1 - v0);
+            if (t.val <= 0.0f || t.val >= 1.0f)
+                t = Df(0.5f);
+        } else {
+            t = Df(0.5f);
+        }
+        x = lerp(xmin, xmax, t);
+        v = func(x);
+        if ((v.val < y.val) == increasing) {
+            xmin = x;
+            v0   = v;
+        } else {
+            xmax = x;
+            v1   = v;
+        }
+        if (std::fabs((xmax - xmin).val) < eps || std::fabs((v - y).val) < eps)
+            return x;
+    }
+    return x;
+}
+inline Df spline_inverse(const Df& y, const float* knots, int knot_count, int type)
+{
+    const SplineBasis& sp = g_spline_basis[type];
+    int lowindex  = sp.step == 1 ? 1 : 0;
+    int highindex = sp.step == 1 ? knot_count - 2 : knot_count - 1;
+    bool increasing = knots[1] < knots[knot_count - 2];
+    if (increasing) {
+        if (y.val <= knots[lowindex]) return Df(0.0f);
+        if (y.val >= knots[highindex]) return Df(1.0f);
+    } else {
+        if (y.val >= knots[lowindex]) return Df(0.0f);
+        if (y.val <= knots[highindex]) return Df(1.0f);
+    }
+    auto S = [&](const Df& x) { Df v; spline_eval(v, x, knots, knot_count, type); return v; };
+    int nsegs     = (knot_count - 4) / sp.step + 1;
+    float nseginv = 1.0f / nsegs;
+    Df r0(0.0f), x(0.0f);
+    for (int s = 0; s < nsegs; ++s) {
+        Df r1(nseginv * (s + 1));
         bool brack;
         x = oiio_invert(S, y, r0, r1, 32, 1.0e-6f, &brack);
         if (brack)

@@ -423,7 +423,9 @@ class Gen:
         if s.t.arr:
             return "K_" + self.ident(s.name)
         if b == "int":
-            return str(s.vals[0])
+            v = int(s.vals[0]) & 0xffffffff          # OSL ints are 32 bit: 0xffffffff is -1
+            v = v - (1 << 32) if v & 0x80000000 else v
+            return "(-2147483647 - 1)" if v == -(1 << 31) else str(v)
         if b == "float":
             return cfloat(s.vals[0])
         if s.t.triple:
@@ -520,6 +522,7 @@ class Gen:
         o.append("    Ctx ctx{pf};")
         o.append("    for (long long i = begin; i < end; ++i) {")
         o.append("        SG sg; GD gd;")
+        o.append("        ClosurePool pool_; pool_.reset(); sg.pool = &pool_;   // per-point closure arena")
         o.append("        load_sg(sg, L, i, &ctx);")
         o.append("        for (int k = 0; k < %d; ++k) gd.ran[k] = false;" % max(1, len(g.layers)))
         o.append("        layer_%d(sg, gd, L);" % (len(g.layers) - 1))
@@ -812,6 +815,20 @@ class Gen:
     def op_triple(self, op):
         A = op.args
         d = A[0]
+        if len(A) == 5 and op.name != "color":
+            # llvm_gen_construct_triple (llvm_gen.cpp:1871-1933): build the triple (with the
+            # derivatives of the components), then osl_transform_triple(space -> "common")
+            dv = d.has_derivs and any(a.has_derivs for a in A[2:])
+            for c in range(3):
+                self.w("setc(%s, %d, %s);" % (self.R(d), c, self.comp(A[2 + c], 0, dv)))
+            sp = A[1]
+            if sp.constval and sp.vals[0] in ("common", "world"):
+                return
+            vt = {"point": 0, "vector": 1, "normal": 2}[op.name]
+            T = "Dv" if d.has_derivs else "V3"
+            self.w("{ %s i_ = %s, o_; xf_transform_triple_err(sg, xf_set(L), %s, \"common\", i_, o_, %d); %s = o_; }" % (
+                T, self.R(d), self.R(sp), vt, self.R(d)))
+            return
         if len(A) == 5:
             if op.name != "color":
                 raise NotImplementedError("triple constructor with a space name")
@@ -932,7 +949,7 @@ class Gen:
         self.w("%s = %d;" % (self.R(d), v))
 
     def op_isconstant(self, op):
-        self.w("%s = %d;" % (self.R(op.args[0]), 1 if op.args[1].isconst else 0))
+        self.w("%s = %d;" % (self.R(op.args[0]), 1 if op.args[1].constval else 0))
 
     def op_hash(self, op):
         A = op.args
@@ -1197,7 +1214,9 @@ class Gen:
         if op.name == "splineinverse":
             self.w("{ float k_[%d]; for (int i_ = 0; i_ < %d; ++i_) k_[i_] = nd(%s[i_]);" % (
                 knots.t.arr, knots.t.arr, self.R(knots)))
-            self.w("  assign(%s, spline_inverse(nd(%s), k_, %s, %s)); }" % (self.R(d), self.R(x), count, bt))
+            # derivatives only flow from x (osl_splineinverse_dfdff / _dfdfdf ignore knot derivs)
+            xi = self.R(x) if (d.has_derivs and x.has_derivs) else "nd(%s)" % self.R(x)
+            self.w("  assign(%s, spline_inverse(%s, k_, %s, %s)); }" % (self.R(d), xi, count, bt))
             return
         if knots.has_derivs and not dv:
             kt = "V3" if knots.t.triple else "float"
@@ -1251,7 +1270,7 @@ class Gen:
                 if a.t.base == "string":
                     self.w("pf_s(sg, %s, %s);" % (cstr(spec[:-1] + "s"), r))
                 elif a.t.base == "int":
-                    if conv in "di":
+                    if conv in "dioxXuc":   # integer conversions keep the int (llvm_gen_printf)
                         self.w("pf_i(sg, %s, %s);" % (cstr(spec), r))
                     else:
                         self.w("pf_f(sg, %s, %s);" % (cstr(spec), r))

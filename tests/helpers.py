@@ -87,6 +87,31 @@ COLOR_OPS_OUTPUTS = [("Cto", 3), ("Cback", 3), ("Cctor", 3), ("Csrgb", 3), ("Cli
                      ("DyCto", 3), ("Lum", 1), ("DxLum", 1), ("BB", 3), ("WL", 3)]
 
 
+# Reference testsuite directories whose run.py is one `testshade [-g X Y] [-center] test` with a
+# text golden (tools/make_fixtures.py TESTSUITE_TEXT): dir -> (grid x, grid y, center).
+# Between them they print the value of nearly every math / logic / control-flow op, so they
+# pin the restated OIIO fast_* transcendentals at print precision (trig, exponential, hyperb,
+# miscmath, geomath, blendmath ...).
+TESTSUITE_TEXT = {
+    "arithmetic": (1, 1, 0), "array-derivs": (2, 2, 0), "blendmath": (1, 1, 0), "breakcont": (1, 1, 0),
+    "bug-locallifetime": (1, 1, 0), "bug-peep": (2, 2, 0), "comparison": (1, 1, 0),
+    "const-array-fill": (1, 1, 0), "const-array-params": (1, 1, 0), "derivs": (2, 2, 0),
+    "derivs-muldiv-clobber": (1, 1, 0), "exit": (1, 1, 0), "exponential": (1, 1, 0),
+    "function-earlyreturn": (2, 2, 0), "function-outputelem": (2, 2, 0), "function-simple": (1, 1, 0),
+    "geomath": (2, 2, 0), "hex": (1, 1, 0), "hyperb": (1, 1, 0), "ieee_fp": (1, 1, 0), "incdec": (1, 1, 0),
+    "intbits": (1, 1, 0), "logic": (1, 1, 0), "loop": (2, 2, 0), "miscmath": (2, 2, 0),
+    "named-components": (1, 1, 0), "oslc-literalfold": (1, 1, 0), "pragma-nowarn": (1, 1, 0),
+    "printf-whole-array": (1, 1, 0), "select": (2, 2, 0), "shortcircuit": (2, 2, 0),
+    "spline-boundarybug": (1, 1, 0), "splineinverse": (3, 1, 1), "ternary": (2, 2, 0),
+    "transitive-assign": (1, 1, 0), "trig": (1, 1, 0), "typecast": (2, 2, 0), "userdata-defaults": (1, 1, 0),
+    "vecctr": (1, 1, 0), "vector": (1, 1, 0),
+}
+
+
+def testsuite_text_want(d):
+    return "\n".join(l for l in golden_text("ts_" + d).split("\n") if not l.startswith("Compiled"))
+
+
 # tests/shaders/matrix_ops.osl
 MATRIX_OPS_OUTPUTS = [("Pshader", 3), ("Vobj", 3), ("Nmy", 3), ("Pback", 3), ("Pm", 3), ("DxPm", 3), ("Det", 1),
                       ("Row", 3), ("Ok", 1), ("Punk", 3), ("Eq", 1), ("Nm", 3), ("PjP", 3), ("PjN", 3), ("DyV", 3)]

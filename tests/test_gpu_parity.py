@@ -307,6 +307,24 @@ def test_printf_journal_reproduces_reference_text_goldens(b200lib, cuda_device, 
     assert got.rstrip("\n") == otxt.rstrip("\n")
 
 
+# closures inside a testshade grid group are not supported by the grid kernels (typecast)
+TESTSUITE_TEXT_DEVICE_SKIP = {"typecast"}
+
+
+@pytest.mark.parametrize("d", sorted(set(helpers.TESTSUITE_TEXT) - TESTSUITE_TEXT_DEVICE_SKIP))
+def test_testsuite_text_goldens_through_the_device(b200lib, cuda_device, d):
+    """The same reference text tests through the GPU path (strict mode + printf journal):
+    character-for-character equal to the reference's golden text."""
+    import torch
+    gx, gy, center = helpers.TESTSUITE_TEXT[d]
+    g = b200lib.ShaderGroup([dict(oso=helpers.oso("ts_" + d), name="l0")], (), (), options="fma=0,journal=1")
+    var, uni = b200lib.grid_globals(gx, gy, center=bool(center))
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(16, dtype=torch.float32, device=cuda_device)
+    g.execute(gx * gy, dvar, uni, out)
+    assert g.journal().rstrip("\n") == helpers.testsuite_text_want(d).rstrip("\n")
+
+
 def test_printf_journal_orders_by_point_and_reports_overflow(b200lib, cuda_device):
     import torch
     layers = [dict(oso=helpers.oso("hash_test"), name="l0")]

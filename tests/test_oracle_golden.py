@@ -124,6 +124,19 @@ def test_matrix_text_goldens(case):
     assert txt.rstrip("\n") == want.rstrip("\n")
 
 
+@pytest.mark.parametrize("d", sorted(helpers.TESTSUITE_TEXT))
+def test_testsuite_text_goldens(d):
+    """40 more `testshade` text tests of the reference (arithmetic, trig, exponential, hyperb,
+    miscmath, geomath, blendmath, logic, loops, functions, arrays, derivs, vector / matrix
+    constructors with spaces, splineinverse with derivatives, ...): the oracle's output equals
+    the reference's golden text character for character."""
+    gx, gy, center = helpers.TESTSUITE_TEXT[d]
+    g = oracle.OracleGroup([dict(oso=helpers.oso("ts_" + d), name="l0")])
+    var, uni = oracle.testshade_globals(gx, gy, center=bool(center))
+    txt = g.run_capture(gx * gy, var, uni)
+    assert txt.rstrip("\n") == helpers.testsuite_text_want(d).rstrip("\n")
+
+
 @pytest.mark.parametrize("case,xres,yres", [("blackbody", 1000, 64), ("wavelength_color", 1000, 64)])
 def test_color_exr_goldens(case, xres, yres):
     """testsuite/blackbody (`-g 1000 64 -od half`) and testsuite/wavelength_color

@@ -134,6 +134,23 @@ TEXTS = {
     "transform": "transform/ref/out.txt",
     "transformc": "transformc/ref/out.txt",
 }
+# testsuite directories whose run.py is a single `testshade [-g X Y] [-center] test` with a text
+# golden: (grid x, grid y, center).  Fixtures: oso/ts_<dir>.oso, text/ts_<dir>.txt.
+# tests/helpers.py TESTSUITE_TEXT mirrors this table.
+TESTSUITE_TEXT = {
+    "arithmetic": (1, 1, 0), "array-derivs": (2, 2, 0), "blendmath": (1, 1, 0), "breakcont": (1, 1, 0),
+    "bug-locallifetime": (1, 1, 0), "bug-peep": (2, 2, 0), "comparison": (1, 1, 0),
+    "const-array-fill": (1, 1, 0), "const-array-params": (1, 1, 0), "derivs": (2, 2, 0),
+    "derivs-muldiv-clobber": (1, 1, 0), "exit": (1, 1, 0), "exponential": (1, 1, 0),
+    "function-earlyreturn": (2, 2, 0), "function-outputelem": (2, 2, 0), "function-simple": (1, 1, 0),
+    "geomath": (2, 2, 0), "hex": (1, 1, 0), "hyperb": (1, 1, 0), "ieee_fp": (1, 1, 0), "incdec": (1, 1, 0),
+    "intbits": (1, 1, 0), "logic": (1, 1, 0), "loop": (2, 2, 0), "miscmath": (2, 2, 0),
+    "named-components": (1, 1, 0), "oslc-literalfold": (1, 1, 0), "pragma-nowarn": (1, 1, 0),
+    "printf-whole-array": (1, 1, 0), "select": (2, 2, 0), "shortcircuit": (2, 2, 0),
+    "spline-boundarybug": (1, 1, 0), "splineinverse": (3, 1, 1), "ternary": (2, 2, 0),
+    "transitive-assign": (1, 1, 0), "trig": (1, 1, 0), "typecast": (2, 2, 0), "userdata-defaults": (1, 1, 0),
+    "vecctr": (1, 1, 0), "vector": (1, 1, 0),
+}
 # float / half EXR goldens of testshade image tests (stored as float32 npz, full size)
 EXR_IMAGES = {
     "blackbody": "blackbody/ref/out.exr",
@@ -179,6 +196,12 @@ def main():
         np.savez_compressed(os.path.join(OUT, "images", name + ".npz"),
                             pixels=img[::STEP, ::STEP, :3].copy(), step=STEP,
                             shape=np.array(img.shape[:2]))
+    for d in TESTSUITE_TEXT:
+        oso = mini_oslc.compile_osl(os.path.join(TS, d, "test.osl"), inc)
+        with open(os.path.join(OUT, "oso", "ts_" + d + ".oso"), "w") as f:
+            f.write(oso)
+        with open(os.path.join(TS, d, "ref", "out.txt")) as f, open(os.path.join(OUT, "text", "ts_" + d + ".txt"), "w") as o:
+            o.write(f.read())
     for name, rel in TEXTS.items():
         with open(os.path.join(TS, rel)) as f, open(os.path.join(OUT, "text", name + ".txt"), "w") as o:
             o.write(f.read())

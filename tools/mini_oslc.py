@@ -390,7 +390,8 @@ def lex(text):
         if k == "float":
             toks.append(("float", float(v.rstrip("fF"))))
         elif k == "hex":
-            toks.append(("int", int(v, 16)))
+            h = int(v, 16) & 0xffffffff        # OSL ints are 32 bit: 0xffffffff is -1
+            toks.append(("int", h - (1 << 32) if h & 0x80000000 else h))
         elif k == "int":
             toks.append(("int", int(v)))
         elif k == "str":
