@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--workload", default="layers-4096", choices=["layers-4096", "noise-1024"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary noise-1024 numbers")
+    ap.add_argument("--config5", action="store_true",
+                    help="also render BASELINE config 5 (render-bunny 4096^2, 256 spp; ~25 s on one GPU)")
     args = ap.parse_args()
     wl = workload(args.workload)
     if args.impl == "reference":
@@ -168,6 +170,27 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:
+        # One process per GPU: run (and first-touch the pinned host buffers) on the NUMA node the
+        # GPU's PCIe root hangs off, so that host<->device copies do not cross the socket link.
+        try:
+            bus = torch.cuda.get_device_properties(local).pci_bus_id
+            dom = torch.cuda.get_device_properties(local).pci_domain_id
+            dev_id = torch.cuda.get_device_properties(local).pci_device_id
+            sysdir = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev_id)
+            node = int(open(sysdir + "/numa_node").read())
+            if node >= 0:
+                cpus = set()
+                for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    numa = node
+        except Exception:
+            numa = None
     if world > 1:
         # stdout carries exactly one JSON line.  With NCCL_DEBUG >= VERSION in the environment
         # NCCL printf()s its banner to stdout at communicator creation, so fd 1 points at stderr
@@ -260,6 +283,8 @@ def main():
     # with NCCL (the only collective on this path)
     render_cfgs = [("render-cornell-1024-64spp", "cornell.xml", 1024, 8, 128),
                    ("render-mx-layer-2048-36spp", "mx_layer.xml", 2048, 6, 160)]
+    if args.config5:
+        render_cfgs.append(("render-bunny-4096-256spp", "bunny.xml", 4096, 16, 96))
     for rname, rxml, res, aa, cpu_res in (render_cfgs if (not args.no_extra and args.workload == "layers-4096") else []):
         try:
             import helpers
@@ -272,6 +297,8 @@ def main():
             rows = [(res * k) // world for k in range(world + 1)]
             y0, y1 = rows[rank], rows[rank + 1]
             R.render(y0, min(y1, y0 + 16), device=local)      # warm-up: module load + scene upload
+            if world > 1:                                     # and the gather's communicator channels
+                gather_strips(torch.zeros((res * (y1 - y0), 3), device=dev), res * res, rank, world, align=res)
             barrier()
             t0 = time.perf_counter()
             img = R.render(y0, y1, device=local)
@@ -327,7 +354,8 @@ def main():
                    "partition": "one full grid tile per GPU, no data-path collective", "fma": 1},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d"],
                 "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["e2e_ms"] / steps,
-                "timer": "host wall clock around the synchronous C-ABI call, max over ranks"},
+                "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
+                "host_numa_node_rank0": numa},
         "gpu_launches": int(r["launches"]),
         "clocks": sampler.summary() if sampler else None,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

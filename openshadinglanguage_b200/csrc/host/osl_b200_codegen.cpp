@@ -334,6 +334,7 @@ private:
     void emit_matrix_op(const Opcode& op);
     void emit_printf(const Opcode& op);
     bool journal_ok = false;  // grid kernels write printf records to the launch's journal
+    bool uses_closures = false;  // a grid kernel then carries a per-point closure pool
     void gen_layer(int layer);
     void emit_block(int b, int e, const Ctx* ctx);
     void useparams(const Opcode& op);
@@ -478,6 +479,7 @@ Gen::op_percomp(const Opcode& op)
         // osl_mul_closure_{float,color} (opclosure.cpp:18-76)
         if (op.args.size() != 3)
             unsupported("closure op '" + op.name + "'");
+        uses_closures = true;
         int a = op.args[1], b = op.args[2];
         if (op.name == "add") {
             w(R(op.args[0]) + " = clos_add(*sg.pool, " + R(a) + ", " + R(b) + ");");
@@ -1128,6 +1130,7 @@ Gen::emit_op(const Opcode& op)
         }
     } else if (n == "closure") {
         // llvm_gen_closure (llvm_gen.cpp:3786-3903): [weight] name params...
+        uses_closures = true;
         size_t i      = 1;
         int weight    = -1;
         if (i < op.args.size() && A((int)i).type.base != Base::String)
@@ -1533,6 +1536,10 @@ Gen::run()
             sg << "    int " << t.name << ";\n";
             ld << "        sg." << t.name << " = ldi(L, " << t.f << ", i);\n";
         }
+    // Closures in a grid execution (testshade): built in a per-point pool like the reference's
+    // StackClosurePool (render_state.h:27-54) and dropped - only the integrator consumes them.
+    if (uses_closures)
+        sg << "    int Ci;\n    ClosurePool* pool;\n";
     sg << "};\n";
 
     std::string prelude = PRELUDE;
@@ -1548,6 +1555,8 @@ Gen::run()
     std::ostringstream out;
     out << "// generated by libosl_b200 for shader group '" << g.name << "'\n";
     out << "#include \"osl_b200_device.cuh\"\n";
+    if (uses_closures)
+        out << "#include \"osl_b200_closure.cuh\"\n";
     if (g.uses_colorsystem)
         out << "#include \"osl_b200_color.cuh\"\n" << colorsystem_cuda_definition(g.colorspace);
     out << prelude << sg.str() << OUTPUT_HELPERS << gd << layers_src;
@@ -1596,6 +1605,8 @@ Gen::run()
     out << "        SG sg = sgn_;\n        sg.jseq = 0u;\n";
     emit_fetch("tile_ + gridDim.x");
     out << "        GD gd;\n        gd.ran = 0u;\n";
+    if (uses_closures)
+        out << "        ClosurePool pool_;\n        pool_.reset();\n        sg.pool = &pool_;\n        sg.Ci = 0;\n";
     out << "        if (active_) {\n";
     out << "            layer_" << (nlayers - 1) << "(sg, gd, L);\n";
     out << "        }\n";

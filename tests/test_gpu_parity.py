@@ -307,8 +307,8 @@ def test_printf_journal_reproduces_reference_text_goldens(b200lib, cuda_device, 
     assert got.rstrip("\n") == otxt.rstrip("\n")
 
 
-# closures inside a testshade grid group are not supported by the grid kernels (typecast)
-TESTSUITE_TEXT_DEVICE_SKIP = {"typecast"}
+# (typecast builds closures inside a grid group: the kernel then carries a per-point pool)
+TESTSUITE_TEXT_DEVICE_SKIP = set()
 
 
 @pytest.mark.parametrize("d", sorted(set(helpers.TESTSUITE_TEXT) - TESTSUITE_TEXT_DEVICE_SKIP))
