@@ -321,6 +321,7 @@ def load_scene(xmlfile):
     if root.tag != "World":
         raise ValueError("Error reading scene: Root element <World> is missing")
     sc = Scene()
+    sc.basedir = basedir      # texture file names in shader parameters are relative to the scene
     named = {}
     for node in root:
         a = node.attrib

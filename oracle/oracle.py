@@ -212,7 +212,7 @@ def hash_(inp):
 class OracleGroup:
     """layers: list of dict(oso=<text>, name=<layername>, params={...})"""
 
-    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=()):
+    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=(), textures=None):
         ls = [oso2cpp.Layer(l["oso"], l["name"], l.get("params")) for l in layers]
         self.group = oso2cpp.Group(ls, connections, outputs)
         self.so = oso2cpp.build_group(self.group, opt=opt, extra_flags=flags)
@@ -221,6 +221,7 @@ class OracleGroup:
         self.lib.oracle_run_capture.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong,
                                                 ctypes.c_longlong]
         self.lib.oracle_run_capture.restype = ctypes.c_char_p
+        register_textures(self.lib, textures)
 
     def run(self, n, varying, uniform, output, shadeindex=None, nthreads=1):
         L, keep = make_launch(n, varying, uniform, output, shadeindex)
@@ -296,9 +297,77 @@ def material_groups(scene, oso_lookup):
     return mats
 
 
+def load_hdr(path):
+    """Radiance RGBE (.hdr) -> float32 [h, w, 3], top scanline first.  Texel value =
+    mantissa * 2^(e-136), zero when e == 0 (Ward's rgbe2float, which OIIO's hdr reader
+    follows); handles the new-style per-channel run-length coding and flat pixels."""
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = 0
+    while True:
+        end = data.index(b"\n", pos)
+        line = data[pos:end]
+        pos = end + 1
+        if line == b"":
+            break
+    end = data.index(b"\n", pos)
+    res = data[pos:end].split()
+    pos = end + 1
+    if res[0] != b"-Y" or res[2] != b"+X":
+        raise ValueError("unsupported .hdr orientation %r" % res)
+    h, w = int(res[1]), int(res[3])
+    buf = np.frombuffer(data, np.uint8)
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    for y in range(h):
+        if 8 <= w < 32768 and buf[pos] == 2 and buf[pos + 1] == 2 and (int(buf[pos + 2]) << 8 | int(buf[pos + 3])) == w:
+            pos += 4
+            for c in range(4):
+                x = 0
+                while x < w:
+                    n = int(buf[pos])
+                    if n > 128:
+                        n -= 128
+                        rgbe[y, x:x + n, c] = buf[pos + 1]
+                        pos += 2
+                    else:
+                        rgbe[y, x:x + n, c] = buf[pos + 1:pos + 1 + n]
+                        pos += 1 + n
+                    x += n
+        else:
+            rgbe[y] = buf[pos:pos + 4 * w].reshape(w, 4)
+            pos += 4 * w
+    e = rgbe[..., 3].astype(np.int32)
+    scale = np.where(e > 0, np.ldexp(np.float32(1.0), e - 136), np.float32(0.0)).astype(np.float32)
+    return (rgbe[..., :3].astype(np.float32) * scale[..., None]).astype(np.float32)
+
+
+def scene_textures(scene):
+    """{name as written in the shader parameter: float32 [h, w, nch]} for every string
+    parameter of the scene's groups that names an image file next to the scene."""
+    out = {}
+    for layers, _ in scene.materials:
+        for l in layers:
+            for v in (l.get("params") or {}).values():
+                if v and isinstance(v[0], str) and v[0].lower().endswith(".hdr"):
+                    p = os.path.join(getattr(scene, "basedir", "."), v[0])
+                    if os.path.exists(p):
+                        out[v[0]] = load_hdr(p)
+    return out
+
+
+def register_textures(lib, textures):
+    lib.oracle_texture_add.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    for name, img in (textures or {}).items():
+        img = np.ascontiguousarray(img, np.float32)
+        if img.ndim == 2:
+            img = img[..., None]
+        lib.oracle_texture_add(name.encode(), img.shape[1], img.shape[0], img.shape[2], img.ctypes.data)
+
+
 class OracleRender:
     def __init__(self, scene, arrays, oso_lookup, opt="-O2"):
         self.scene, self.arrays = scene, arrays
+        self.textures = scene_textures(scene)
         groups = []
         for layers, conns in material_groups(scene, oso_lookup):
             ls = [oso2cpp.Layer(l["oso"], l["name"], l["params"]) for l in layers]
@@ -306,6 +375,7 @@ class OracleRender:
         self.so = oso2cpp.build_render(groups, opt=opt)
         self.lib = ctypes.CDLL(self.so)
         self.lib.oracle_render.argtypes = [ctypes.POINTER(RenderScene), ctypes.c_void_p, ctypes.c_int]
+        register_textures(self.lib, self.textures)
 
     def render(self, xres, yres, aa, nthreads=None, **kw):
         rs, keep = fill_render_scene(RenderScene, self.scene, self.arrays, xres, yres, aa, **kw)

@@ -17,6 +17,7 @@
 #include <vector>
 #include "osl_oracle_color.h"
 #include "osl_oracle_matrix.h"
+#include "osl_oracle_texture.h"
 
 #ifndef OSLO_COLORSPACE
 #    define OSLO_COLORSPACE "Rec709" /* ShadingSystem attribute "colorspace" default */

@@ -1166,6 +1166,49 @@ class Gen:
     def op_transpose(self, op):
         self.w("%s = m44_transposed(%s);" % (self.R(op.args[0]), self.R(op.args[1])))
 
+    def op_texture(self, op):
+        """llvm_gen_texture (llvm_gen.cpp:2715-2830) -> osl_texture (optexture.cpp:235-310):
+        result, filename, s, t, [dsdx, dtdx, dsdy, dtdy,] then "name", value option pairs
+        (llvm_gen_texture_options, llvm_gen.cpp:2480-2713).  Derivatives of s and t come
+        from the Dual2 arguments unless given explicitly."""
+        A = op.args
+        d, fn, s, t = A[:4]
+        i = 4
+
+        def dpart(sym, which):
+            return "(%s).%s" % (self.R(sym), which) if sym.has_derivs else "0.0f"
+        if len(A) >= 8 and all(a.t.base in ("float", "int") for a in A[4:8]):
+            dd = [self.fl(a) for a in A[4:8]]
+            i = 8
+        else:
+            dd = [dpart(s, "dx"), dpart(t, "dx"), dpart(s, "dy"), dpart(t, "dy")]
+        self.w("{")
+        self.w("    TexOpt o_;")
+        while i < len(A):
+            key, val = A[i], A[i + 1]
+            i += 2
+            if not key.constval:
+                raise NotImplementedError("texture option with a non-constant name")
+            k = key.vals[0]
+            if k in ("wrap", "swrap", "twrap"):
+                for f in (("swrap", "twrap") if k == "wrap" else (k,)):
+                    self.w("    o_.%s = tex_wrap_code(%s);" % (f, self.R(val)))
+            elif k in ("width", "swidth", "twidth", "blur", "sblur", "tblur"):
+                for f in (("s" + k, "t" + k) if k in ("width", "blur") else (k,)):
+                    self.w("    o_.%s = %s;" % (f, self.fl(val)))
+            elif k == "fill":
+                self.w("    o_.fill = %s;" % self.fl(val))
+            elif k == "interp":
+                self.w("    o_.interp = tex_interp_code(%s);" % self.R(val))
+            else:
+                raise NotImplementedError("texture option '%s'" % k)
+        nch = 3 if d.t.triple else 1
+        self.w("    float r_[4];")
+        self.w("    texture_lookup(%s, o_, %s, %s, %s, %s, %s, %s, %d, r_);" % (
+            self.R(fn), self.fl(s), self.fl(t), dd[0], dd[1], dd[2], dd[3], nch))
+        self.w("    assign(%s, %s);" % (self.R(d), "V3(r_[0], r_[1], r_[2])" if nch == 3 else "r_[0]"))
+        self.w("}")
+
     def op_determinant(self, op):
         self.w("assign(%s, m44_determinant(%s));" % (self.R(op.args[0]), self.R(op.args[1])))
 
@@ -1380,6 +1423,10 @@ def raytype_bit(name):
 
 
 RUNNER_TAIL = r"""
+extern "C" void oracle_texture_add(const char* name, int w, int h, int nch, const float* px)
+{
+    oracle_texture_add_impl(name, w, h, nch, px);
+}
 extern "C" void oracle_run_mt(const Launch* L, long long n, int nthreads)
 {
     if (nthreads <= 1) { oracle_run(L, 0, n, nullptr); return; }
@@ -1405,6 +1452,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 RENDER_TAIL = r"""
+extern "C" void oracle_texture_add(const char* name, int w, int h, int nch, const float* px)
+{
+    oracle_texture_add_impl(name, w, h, nch, px);
+}
 static const Background* g_background = nullptr;
 static void oracle_render_rows(const RenderScene* S, int y0, int y1, float* out, std::string* pf)
 {

@@ -71,6 +71,7 @@ SHADERS = {
     "mx_envmap": "render-mx-furnace-oren-nayar/envmap.osl",
     "mxlayer_layer": "render-mx-layer/layer.osl",
     "mxlayer_envmap": "render-mx-layer/envmap.osl",
+    "mf_envmap": "render-microfacet/envmap.osl",      # texture() of the HDR probe
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -91,7 +92,12 @@ SCENES = {
     "mx_furnace_burley.xml": ("render-mx-furnace-burley-diffuse/scene.xml",
                               {"matte": "mxburley_matte", "envmap": "mx_envmap"}),
     "mx_layer.xml": ("render-mx-layer/scene.xml", {"layer": "mxlayer_layer", "envmap": "mxlayer_envmap"}),
+    # (microfacet.xml is this repo's own emitter-lit variant; this is the reference's scene, whose
+    #  environment shader reads ../common/textures/kitchen_probe.hdr -> ../textures/ here)
+    "render_microfacet.xml": ("render-microfacet/scene.xml", {"envmap": "mf_envmap"}),
 }
+# input images read by texture() (test input data, copied byte for byte)
+TEXTURES = {"kitchen_probe.hdr": "common/textures/kitchen_probe.hdr"}
 # golden renders (half-float EXR in the reference; stored as float16 npz)
 RENDERS = {
     "render-cornell": "render-cornell/ref/out.exr",
@@ -103,6 +109,7 @@ RENDERS = {
     "render-mx-furnace-oren-nayar": "render-mx-furnace-oren-nayar/ref/out.exr",
     "render-mx-furnace-burley-diffuse": "render-mx-furnace-burley-diffuse/ref/out.exr",
     "render-mx-layer": "render-mx-layer/ref/out.exr",
+    "render-microfacet": "render-microfacet/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
@@ -214,7 +221,12 @@ def main():
             data = f.read()
             for old, new in rename.items():
                 data = re.sub((r"\bshader\s+%s\b" % re.escape(old)).encode(), ("shader " + new).encode(), data)
+            data = data.replace(b"../common/textures/", b"../textures/")
             o.write(data)
+    os.makedirs(os.path.join(OUT, "textures"), exist_ok=True)
+    for name, rel in TEXTURES.items():
+        with open(os.path.join(TS, rel), "rb") as f, open(os.path.join(OUT, "textures", name), "wb") as o:
+            o.write(f.read())
     os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
     import cv2
     for name, rel in RENDERS.items():
