@@ -165,6 +165,18 @@ int b200_group_execute_host(b200_group* g, int device, long long npoints,
  * group's warnings, so production launches never pay for a debugging aid. */
 const char* b200_group_journal(b200_group* g, int device);
 
+/* Image data for texture() (src/liboslexec/optexture.cpp:235-310 osl_texture ->
+ * RendererServices::texture, rendservices.cpp:166-232, which the reference forwards to the
+ * renderer's OIIO TextureSystem, include/OSL/oslexec.h:172).  The renderer registers a
+ * decoded image under the file name its shaders use: `pixels` is [height][width][nchannels]
+ * float32 in host memory, top scanline first, nchannels 1..4; it is copied.  Names that
+ * were not registered are looked up as Radiance .hdr files (as written, then under the
+ * ':'-separated directories of the group / render option texturepath=...) when a group
+ * that reads them is first launched on a device.  File names must be constant once the
+ * group is compiled (instance parameter values are).  Filtering: level-0 B-spline bicubic
+ * with anisotropic probes, options wrap/swrap/twrap, width, blur, fill, interp. */
+int b200_texture_add(const char* name, int width, int height, int nchannels, const float* pixels);
+
 /* Number of kernel launches issued by this library so far (bench accounting) */
 long long b200_launch_count(void);
 

@@ -116,6 +116,18 @@ def launch_count():
     return int(lib().b200_launch_count())
 
 
+def add_texture(name, pixels):
+    """Register a decoded image ([h, w] or [h, w, nch] float32, top scanline first) under the
+    file name shaders pass to texture() (b200_texture_add)."""
+    import numpy as np
+    a = np.ascontiguousarray(pixels, dtype=np.float32)
+    if a.ndim == 2:
+        a = a[..., None]
+    L = lib()
+    L.b200_texture_add.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    _check(L.b200_texture_add(name.encode(), a.shape[1], a.shape[0], a.shape[2], a.ctypes.data))
+
+
 def _ptr(x):
     """raw address of a torch tensor / numpy array / int / None"""
     if x is None:
@@ -382,6 +394,9 @@ class Renderer:
             ls = [dict(oso=oso_lookup(l["shader"]), name=l["name"], params=l["params"]) for l in layers]
             mats[k] = _group_desc(ls, conns, "material%d" % k, "", keep)
         h = ctypes.c_void_p()
+        basedir = getattr(scene, "basedir", None)
+        if basedir and "texturepath=" not in options:     # texture files are relative to the scene file
+            options = (options + "," if options else "") + "texturepath=" + basedir
         _check(L.b200_render_create(ctypes.byref(rs), len(scene.materials), mats, options.encode(), ctypes.byref(h)))
         self._h, self._keep = h, keep
         self.xres, self.yres, self.aa = xres, yres, aa

@@ -905,6 +905,70 @@ Gen::emit_op(const Opcode& op)
         g.uses_colorsystem = true;
         w("assign(" + R(op.args[0]) + ", color_transformc(osl_cs_, " + space_code(op.args[1], true) + ", OSLD_CS_RGB, mkv("
           + comp(op.args[2], 0, false) + ", " + comp(op.args[3], 0, false) + ", " + comp(op.args[4], 0, false) + ")));");
+    } else if (n == "texture") {
+        // llvm_gen_texture (llvm_gen.cpp:2715-2830): result, filename, s, t, [dsdx, dtdx, dsdy,
+        // dtdy,] then ("name", value) option pairs (llvm_gen_texture_options, :2480-2713).
+        if (op.args.size() < 4)
+            unsupported("texture with fewer than 4 arguments");
+        const Symbol& fn = A(1);
+        if (!fn.const_value() || fn.svals.empty())
+            unsupported("texture() with a file name that is not constant at compile time");
+        size_t slot = 0;
+        for (; slot < g.textures.size() && g.textures[slot] != fn.svals[0]; ++slot) {}
+        if (slot == g.textures.size())
+            g.textures.push_back(fn.svals[0]);
+        auto dpart = [&](int ai, const char* which) {
+            return A(ai).has_derivs && !A(ai).is_const() ? "(" + R(op.args[ai]) + ")." + which : std::string("0.0f");
+        };
+        std::string dd[4];
+        size_t i = 4;
+        if (op.args.size() >= 8 && A(4).type.base != Base::String && A(5).type.base != Base::String
+            && A(6).type.base != Base::String && A(7).type.base != Base::String) {
+            for (int k = 0; k < 4; ++k)
+                dd[k] = comp(op.args[4 + k], 0, false);
+            i = 8;
+        } else {
+            dd[0] = dpart(2, "dx"), dd[1] = dpart(3, "dx"), dd[2] = dpart(2, "dy"), dd[3] = dpart(3, "dy");
+        }
+        w("{");
+        w("    TexOpt o_ = tex_default_options();");
+        auto code_of = [&](int ai, bool wrap) -> std::string {
+            const Symbol& v = A(ai);
+            if (!v.const_value() || v.svals.empty())
+                unsupported("texture option with a string that is not constant at compile time");
+            const std::string& s = v.svals[0];
+            if (wrap)
+                return s == "clamp" ? "TEX_CLAMP" : s == "periodic" ? "TEX_PERIODIC" : s == "mirror" ? "TEX_MIRROR" : "TEX_BLACK";
+            return s == "closest"                       ? "TEX_CLOSEST"
+                   : (s == "bilinear" || s == "linear") ? "TEX_BILINEAR"
+                   : (s == "bicubic" || s == "cubic")   ? "TEX_BICUBIC"
+                                                        : "TEX_SMARTCUBIC";
+        };
+        for (; i + 1 < op.args.size(); i += 2) {
+            const Symbol& key = A((int)i);
+            if (!key.const_value() || key.svals.empty())
+                unsupported("texture option with a non-constant name");
+            const std::string& k = key.svals[0];
+            int vi                = (int)i + 1;
+            if (k == "wrap")
+                w("    o_.swrap = o_.twrap = " + code_of(vi, true) + ";");
+            else if (k == "swrap" || k == "twrap")
+                w("    o_." + k + " = " + code_of(vi, true) + ";");
+            else if (k == "width" || k == "blur")
+                w("    o_.s" + k + " = o_.t" + k + " = " + comp(op.args[vi], 0, false) + ";");
+            else if (k == "swidth" || k == "twidth" || k == "sblur" || k == "tblur" || k == "fill")
+                w("    o_." + k + " = " + comp(op.args[vi], 0, false) + ";");
+            else if (k == "interp")
+                w("    o_.interp = " + code_of(vi, false) + ";");
+            else
+                unsupported("texture option '" + k + "'");
+        }
+        bool triple = A(0).type.is_triple();
+        w("    V3 r_ = texture_lookup(osl_tex_[" + std::to_string(g.texture_base + (int)slot) + "], o_, "
+          + comp(op.args[2], 0, false) + ", " + comp(op.args[3], 0, false) + ", " + dd[0] + ", " + dd[1] + ", " + dd[2]
+          + ", " + dd[3] + ", " + (triple ? "3" : "1") + ");");
+        w("    assign(" + R(op.args[0]) + ", " + (triple ? "r_" : "r_.x") + ");");
+        w("}");
     } else if (n == "luminance" || n == "transformc") {
         // osl_luminance_fv/_dfdv, osl_transformc (opcolor.cpp:464-518): dual form only
         // when both sides carry derivatives
@@ -1454,6 +1518,8 @@ Gen::run()
         throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
     // layer bodies first (they record which globals are read)
     journal_ok = g.journal_enabled;
+    g.textures.clear();
+    g.texture_base = 0;
     std::ostringstream bodies;
     std::string gd = "struct GD {\n    unsigned ran;\n";
     for (int l = 0; l < nlayers; ++l) {
@@ -1557,6 +1623,9 @@ Gen::run()
     out << "#include \"osl_b200_device.cuh\"\n";
     if (uses_closures)
         out << "#include \"osl_b200_closure.cuh\"\n";
+    if (!g.textures.empty())
+        out << "#include \"osl_b200_texture.cuh\"\nextern \"C\" __device__ osld::TexDesc osl_tex_[" << g.textures.size()
+            << "];\n";
     if (g.uses_colorsystem)
         out << "#include \"osl_b200_color.cuh\"\n" << colorsystem_cuda_definition(g.colorspace);
     out << prelude << sg.str() << OUTPUT_HELPERS << gd << layers_src;
@@ -1716,10 +1785,16 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background)
     out << "#include \"osl_b200_device.cuh\"\n#include \"osl_b200_closure.cuh\"\n#include \"osl_b200_sg.cuh\"\n";
     std::string mats;
     bool color = false;
+    int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
     for (size_t k = 0; k < groups.size(); ++k) {
+        groups[k]->texture_base = ntex;
+        groups[k]->textures.clear();
         mats += Gen(*groups[k]).run_material("mat" + std::to_string(k));
         color |= groups[k]->uses_colorsystem;
+        ntex += (int)groups[k]->textures.size();
     }
+    if (ntex)
+        out << "#include \"osl_b200_texture.cuh\"\nextern \"C\" __device__ osld::TexDesc osl_tex_[" << ntex << "];\n";
     if (color)  // one colour system per module: the shading system's, i.e. the first group's
         out << "#include \"osl_b200_color.cuh\"\n" << colorsystem_cuda_definition(groups[0]->colorspace);
     out << "using namespace osld;\nstruct B200Launch { int unused_; };\n" << mats;

@@ -146,6 +146,9 @@ struct Group {
     bool journal_enabled = false;              // group option journal=WORDS (> 0): record printf output
     std::vector<std::string> spaces;           // named coordinate systems referenced (launch-block slots)
     std::string commonspace_synonym = "world"; // ShadingSystem attribute "commonspace"
+    std::vector<std::string> textures;         // constant texture() file names (module table slots)
+    int texture_base = 0;                      // first slot of this group in a multi-group module
+    std::string texturepath;                   // ':'-separated directories searched for texture files
 
     int layer_index(const std::string& n) const;
     void add_layer(const std::string& oso_text, const std::string& layername,

@@ -11,6 +11,7 @@
 // with one thread per shading point.
 #include "../../include/osl_b200.h"
 #include "host/osl_b200_group.h"
+#include "host/osl_b200_texture.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -151,6 +152,7 @@ struct b200_group {
     std::mutex mu;
     std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
     int sm_count[64] = { 0 };
+    std::vector<void*> texture_allocs;  // device images of the textures the group reads (all devices)
     // printf journal (only for groups that have printf sites): one device buffer per device
     unsigned journal_words = 4u << 20;   // option journal=WORDS
     std::map<int, unsigned*> journal_dev;
@@ -264,6 +266,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             G->block = atoi(opt["block"].c_str());
         if (opt.count("stage"))
             G->stage_outputs = atoi(opt["stage"].c_str()) != 0;
+        if (opt.count("texturepath"))
+            G->g.texturepath = opt["texturepath"];
         if (G->block < 32 || G->block > 1024 || (G->block % 32))
             return fail(B200_ERR_INVALID, "option block must be a multiple of 32 in [32,1024]");
         for (int i = 0; i < desc->nlayers; ++i) {
@@ -319,6 +323,8 @@ b200_group_destroy(b200_group* g)
     for (auto& kv : g->loaded)
         if (driver().ok)
             driver().cuModuleUnload(kv.second.first);
+    for (void* p : g->texture_allocs)
+        cudaFree(p);
     if (g->stage.d_in)
         cudaFree(g->stage.d_in);
     if (g->stage.d_out)
@@ -396,6 +402,15 @@ journal_format(const Group& g, const JournalFormat& jf, const unsigned* w, size_
 /* Text printed by the group's printf ops since the previous call, ordered by shade index
  * and, within a point, by execution order - what single-threaded testshade prints.
  * Synchronises `device`.  The pointer stays valid until the next call on this group. */
+int
+b200_texture_add(const char* name, int width, int height, int nchannels, const float* pixels)
+{
+    if (!name || !pixels || width <= 0 || height <= 0 || nchannels < 1 || nchannels > 4)
+        return fail(B200_ERR_INVALID, "b200_texture_add: bad arguments");
+    texture_add(name, width, height, nchannels, pixels);
+    return B200_OK;
+}
+
 const char*
 b200_group_journal(b200_group* g, int device)
 {
@@ -496,6 +511,9 @@ ensure_loaded(b200_group* g, int device, CUfunction_* fn)
     r = d.cuModuleGetFunction(&f, mod, "osl_b200_group_kernel");
     if (r != 0)
         return fail(B200_ERR_CUDA, "cuModuleGetFunction: " + cu_err(r));
+    std::string terr = bind_module_textures(mod, g->g.textures, g->g.texturepath, g->texture_allocs);
+    if (!terr.empty())
+        return fail(B200_ERR_INVALID, terr);
     g->loaded[device] = { mod, f };
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

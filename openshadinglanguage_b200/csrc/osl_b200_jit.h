@@ -5,6 +5,8 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include "host/osl_b200_texture.h"
+
 #include <mutex>
 #include <string>
 #include <vector>
@@ -28,6 +30,7 @@ struct Driver {
     CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                 void*, void**, void**)                     = nullptr;
     CUresult_ (*cuGetErrorString)(CUresult_, const char**)                 = nullptr;
+    CUresult_ (*cuModuleGetGlobal)(unsigned long long*, size_t*, CUmodule_, const char*) = nullptr;
     bool ok = false;
     std::string why;
     std::string err(CUresult_ r) const
@@ -66,6 +69,11 @@ jit_driver()
         OSLB200_SYM(cuModuleGetFunction)
         OSLB200_SYM(cuLaunchKernel)
         OSLB200_SYM(cuGetErrorString)
+        *(void**)(&d.cuModuleGetGlobal) = dlsym(d.lib, "cuModuleGetGlobal_v2");
+        if (!d.cuModuleGetGlobal) {
+            d.why = "libcuda is missing symbol cuModuleGetGlobal_v2";
+            return;
+        }
 #undef OSLB200_SYM
         if (d.cuInit(0) != 0) {
             d.why = "cuInit failed";
@@ -108,6 +116,43 @@ jit_compile(const std::string& src, const char* name, bool fma, std::vector<char
     cubin.resize(sz);
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
+    return "";
+}
+
+// Uploads the images a module's texture() calls name to the CURRENT device and fills the
+// module's `osl_tex_` table (device/osl_b200_texture.cuh).  Returns "" or the error.
+// `allocations` receives the device buffers (owned by the caller, freed with cudaFree).
+inline std::string
+bind_module_textures_impl(CUmodule_ mod, const std::vector<std::string>& names, const std::string& searchpath,
+                     std::vector<void*>& allocations)
+{
+    if (names.empty())
+        return "";
+    Driver& d = jit_driver();
+    if (!d.ok)
+        return "CUDA driver unavailable: " + d.why;
+    unsigned long long dptr = 0;
+    size_t bytes            = 0;
+    CUresult_ r             = d.cuModuleGetGlobal(&dptr, &bytes, mod, "osl_tex_");
+    if (r != 0)
+        return "cuModuleGetGlobal(osl_tex_): " + d.err(r);
+    std::vector<TexDescHost> table(names.size());
+    if (bytes < table.size() * sizeof(TexDescHost))
+        return "texture table of the module is smaller than its texture list";
+    for (size_t i = 0; i < names.size(); ++i) {
+        std::string err;
+        const TextureImage* im = texture_get(names[i], searchpath, err);
+        if (!im)
+            return err;
+        void* p   = nullptr;
+        size_t nb = im->rgba.size() * sizeof(float);
+        if (cudaMalloc(&p, nb) != cudaSuccess || cudaMemcpy(p, im->rgba.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess)
+            return "uploading texture '" + names[i] + "': " + cudaGetErrorString(cudaGetLastError());
+        allocations.push_back(p);
+        table[i] = TexDescHost { p, im->w, im->h, im->nch, 0 };
+    }
+    if (cudaMemcpy((void*)dptr, table.data(), table.size() * sizeof(TexDescHost), cudaMemcpyHostToDevice) != cudaSuccess)
+        return std::string("filling osl_tex_: ") + cudaGetErrorString(cudaGetLastError());
     return "";
 }
 

@@ -19,6 +19,14 @@ namespace oslb200 {
 int set_error(int code, const std::string& msg);
 void count_launches(long long n);
 }  // namespace oslb200
+namespace oslb200 {
+std::string
+bind_module_textures(void* module, const std::vector<std::string>& names, const std::string& searchpath,
+                     std::vector<void*>& allocations)
+{
+    return bind_module_textures_impl(module, names, searchpath, allocations);
+}
+}  // namespace oslb200
 using namespace oslb200;
 
 namespace {
@@ -80,6 +88,8 @@ struct b200_render {
     b200_render_scene host;  // host-pointer copy of the description
     bool fma = true, sort = true;
     long long slots_target = 4 << 20;
+    std::vector<std::string> textures;  // the module's texture table, in slot order
+    std::string texturepath;            // option texturepath=dir[:dir...]
     // per-device state
     struct Dev {
         CUmodule_ mod = nullptr;
@@ -171,6 +181,9 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
             R->groups.push_back(std::move(g));
         }
         R->source = generate_cuda_render(gs, scene->background_shader >= 0);
+        for (Group* gp : gs)  // module texture table = the groups' lists in order
+            R->textures.insert(R->textures.end(), gp->textures.begin(), gp->textures.end());
+        R->texturepath = opt.count("texturepath") ? opt["texturepath"] : std::string();
     } catch (const std::exception& e) {
         return set_error(B200_ERR_COMPILE, e.what());
     }
@@ -250,6 +263,9 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
             return set_error(B200_ERR_CUDA, std::string("cuModuleGetFunction(") + KERNELS[k] + "): " + drv.err(cr));
     }
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device);
+    std::string terr = bind_module_textures(d.mod, r->textures, r->texturepath, d.allocs);
+    if (!terr.empty())
+        return set_error(B200_ERR_INVALID, terr);
     const b200_render_scene& h = r->host;
     bool ok                    = true;
     DevScene& S                = d.S;

@@ -112,6 +112,12 @@ def testsuite_text_want(d):
     return "\n".join(l for l in golden_text("ts_" + d).split("\n") if not l.startswith("Compiled"))
 
 
+# tests/shaders/texture_ops.osl
+TEXTURE_OPS_OUTPUTS = [("Cdef", 3), ("Cperiodic", 3), ("Cmirror", 3), ("Cclamp", 3), ("Cbilinear", 3), ("Cclosest", 3),
+                       ("Cblur", 3), ("Cwide", 3), ("Cexplicit", 3), ("Fone", 1), ("Cnoderiv", 3)]
+TEXTURES = os.path.join(GOLDEN, "textures")
+
+
 # tests/shaders/matrix_ops.osl
 MATRIX_OPS_OUTPUTS = [("Pshader", 3), ("Vobj", 3), ("Nmy", 3), ("Pback", 3), ("Pm", 3), ("DxPm", 3), ("Det", 1),
                       ("Row", 3), ("Ok", 1), ("Punk", 3), ("Eq", 1), ("Nm", 3), ("PjP", 3), ("PjN", 3), ("DyV", 3)]

@@ -9,6 +9,8 @@ indexing; for float outputs
     absolute on noise values in [-1,1] (a few ulp of contraction drift),
     derivatives 1e-4 relative to the input scale.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -228,6 +230,62 @@ def test_color_ops_match_oracle(b200lib, cuda_device, space):
             assert np.array_equal(G[name].view(np.uint32), W[name].view(np.uint32)), \
                 (name, np.abs(G[name] - W[name]).max())
     assert np.isfinite(W["BB"]).all() and W["BB"].max() > 0 and W["WL"].max() > 0
+
+
+@pytest.mark.parametrize("source", ["hdr-file", "registered"])
+@pytest.mark.parametrize("scale", [1.0, 6.0])
+def test_texture_ops_match_oracle(b200lib, cuda_device, source, scale):
+    """texture() (tests/shaders/texture_ops.osl): default lookup, wrap modes, interp modes,
+    blur, width, explicit derivatives, one-channel result with fill, constant coordinates -
+    over a grid whose u,v derivatives vary (isotropic to 32:1 footprints; scale 6 minifies
+    so the multi-probe path runs).  "hdr-file": the library's own C++ Radiance reader via
+    texturepath against the oracle's numpy reader; "registered": a 1-channel image through
+    b200_texture_add.  Strict mode, bit-exact."""
+    import torch
+    res = 96
+    if source == "hdr-file":
+        name = "kitchen_probe.hdr"
+        img = oracle.load_hdr(os.path.join(helpers.TEXTURES, name))
+    else:
+        name = "procedural-%g.tex" % scale
+        rng = np.random.default_rng(5)
+        img = (rng.random((37, 53), dtype=np.float32) ** 4 * 30).astype(np.float32)
+        b200lib.add_texture(name, img)
+    layers, outputs, nfloats = helpers.multi_output_case("texture_ops", helpers.TEXTURE_OPS_OUTPUTS, res,
+                                                         params=dict(filename=[name], scale=[scale]))
+    og = oracle.OracleGroup(layers, outputs=outputs, textures={name: img})
+    kw = dict(vary_udxdy=True, vary_vdxdy=True)
+    ovar, ouni = oracle.testshade_globals(res, res, **kw)
+    want = np.zeros(nfloats, np.float32)
+    og.run(res * res, ovar, ouni, want, nthreads=4)
+    g = b200lib.ShaderGroup(layers, outputs=outputs, options="fma=0,texturepath=" + helpers.TEXTURES)
+    var, uni = b200lib.grid_globals(res, res, **kw)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(nfloats, dtype=torch.float32, device=cuda_device)
+    g.execute(res * res, dvar, uni, out)
+    torch.cuda.synchronize()
+    W = helpers.multi_output_split(want, helpers.TEXTURE_OPS_OUTPUTS, res)
+    G = helpers.multi_output_split(out.cpu().numpy(), helpers.TEXTURE_OPS_OUTPUTS, res)
+    for k in W:
+        assert np.array_equal(G[k].view(np.uint32), W[k].view(np.uint32)), (k, np.abs(G[k] - W[k]).max())
+    # the outputs are not degenerate: options change the result, fill reaches missing channels
+    assert W["Cdef"].max() > 0 and not np.array_equal(W["Cdef"], W["Cbilinear"])
+    assert not np.array_equal(W["Cdef"], W["Cblur"]) and not np.array_equal(W["Cdef"], W["Cwide"])
+    assert np.ptp(W["Cnoderiv"], axis=0).max() == 0
+    if source == "registered":      # 1-channel file: channels 1,2 of a colour lookup take fill (0)
+        assert np.all(W["Cdef"][:, 1:] == 0)
+
+
+def test_texture_missing_file_is_an_error(b200lib, cuda_device):
+    import torch
+    layers, outputs, nfloats = helpers.multi_output_case("texture_ops", helpers.TEXTURE_OPS_OUTPUTS, 8,
+                                                         params=dict(filename=["no-such-file.hdr"]))
+    g = b200lib.ShaderGroup(layers, outputs=outputs)
+    var, uni = b200lib.grid_globals(8, 8)
+    dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
+    out = torch.zeros(nfloats, dtype=torch.float32, device=cuda_device)
+    with pytest.raises(Exception, match="no-such-file.hdr"):
+        g.execute(64, dvar, uni, out)
 
 
 def test_matrix_ops_match_oracle(b200lib, cuda_device):

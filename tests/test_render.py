@@ -34,16 +34,20 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          # BASELINE config 4: layer() of sheen_bsdf / reflection / oren_nayar_diffuse_bsdf / diffuse,
          # lit by a procedural sky + sun through the 1024^2 background importance table
          "render-mx-layer": ("mx_layer.xml", 160, 120, 6)}
+# BASELINE config 4's other half: glossy glass spheres under the kitchen light probe, read by
+# texture() in the background shader (1024^2 importance table + directly seen + bounce misses).
+# Texture filtering is OIIO's in the reference (not buildable here), so this golden pins the
+# restated filter at the thresholds of the reference's own test, not at pixel identity.
+TEXTURED_CASES = {"render-microfacet": ("render_microfacet.xml", 160, 120, 8)}
 # scenes of this repo (no reference golden image): the oracle restates the lobes
-# from shading.cpp and the device must equal the oracle.  render-microfacet itself
-# needs an HDR environment texture, which is outside this path.
+# from shading.cpp and the device must equal the oracle.
 OWN_CASES = {"microfacet": ("microfacet.xml", 160, 120, 4)}   # ggx/beckmann x reflect/refract/both
 _cache = {}
 
 
 def _scene(case):
     if case not in _cache:
-        S = sc.load_scene(os.path.join(SCENES, (CASES.get(case) or OWN_CASES[case])[0]))
+        S = sc.load_scene(os.path.join(SCENES, (CASES.get(case) or TEXTURED_CASES.get(case) or OWN_CASES[case])[0]))
         _cache[case] = (S, S.prepare())
     return _cache[case]
 
@@ -97,6 +101,28 @@ def test_oracle_matches_reference_golden_render(case):
         assert exact > 0.99, exact
 
 
+def test_oracle_render_microfacet_within_reference_thresholds():
+    """testsuite/render-microfacet/run.py: failthresh 0.04, failrelative 0.03, failpercent 1
+    (idiff: a pixel fails when it is off by more than failthresh AND by more than failrelative
+    of its value).  The HDR probe is decoded by the oracle's own reader."""
+    case = "render-microfacet"
+    S, A = _scene(case)
+    xml, xres, yres, aa = TEXTURED_CASES[case]
+    R = oracle.OracleRender(S, A, helpers.oso)
+    assert list(R.textures) == ["../textures/kitchen_probe.hdr"]
+    img = R.render(xres, yres, aa, nthreads=8)
+    ref = _golden(case)
+    d = np.abs(img - ref).max(axis=2)
+    rel = d / np.maximum(np.abs(ref).max(axis=2), 1e-6)
+    assert ((d > 0.04) & (rel > 0.03)).mean() * 100.0 <= 1.0
+    assert abs(float(img.mean() / ref.mean()) - 1.0) < 1e-3          # no brightness bias
+    # a third of the pixels are identical at the golden's half precision; the rest sit within a
+    # half-float ulp or two (median relative difference 4e-4): filter details, not a different image
+    h = img.astype(np.float16).astype(np.float32)
+    assert (np.abs(h - ref).max(axis=2) == 0).mean() > 0.25
+    assert float(np.median(rel)) < 1e-3
+
+
 def test_render_module_compiles_without_gpu(b200lib):
     from openshadinglanguage_b200 import api
     S, A = _scene("render-cornell")
@@ -106,12 +132,12 @@ def test_render_module_compiles_without_gpu(b200lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("case", sorted(CASES) + sorted(TEXTURED_CASES))
 @pytest.mark.parametrize("sort", [0, 1])
 def test_gpu_render_bit_exact_vs_oracle(b200lib, cuda_device, case, sort):
     from openshadinglanguage_b200 import api
     S, A = _scene(case)
-    xml, xres, yres, aa = CASES[case]
+    xml, xres, yres, aa = CASES.get(case) or TEXTURED_CASES[case]
     want = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
     R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options="fma=0,sort=%d" % sort)
     got = R.render()

@@ -76,6 +76,7 @@ SHADERS = {
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
     "matrix_ops": "repo:tests/shaders/matrix_ops.osl",
+    "texture_ops": "repo:tests/shaders/texture_ops.osl",
 }
 # scene descriptions + model data of the testrender configs (test input data)
 SCENES = {
