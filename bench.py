@@ -282,7 +282,9 @@ def main():
     # importance sampling): rows sharded over the GPUs, framebuffer strips gathered to rank 0
     # with NCCL (the only collective on this path)
     render_cfgs = [("render-cornell-1024-64spp", "cornell.xml", 1024, 8, 128),
-                   ("render-mx-layer-2048-36spp", "mx_layer.xml", 2048, 6, 160)]
+                   ("render-mx-layer-2048-36spp", "mx_layer.xml", 2048, 6, 160),
+                   # config 4's other half: microfacet glass under the HDR probe read by texture()
+                   ("render-microfacet-2048-64spp", "render_microfacet.xml", 2048, 8, 128)]
     if args.config5:
         render_cfgs.append(("render-bunny-4096-256spp", "bunny.xml", 4096, 16, 96))
     for rname, rxml, res, aa, cpu_res in (render_cfgs if (not args.no_extra and args.workload == "layers-4096") else []):

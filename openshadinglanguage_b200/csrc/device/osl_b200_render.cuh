@@ -1147,15 +1147,21 @@ extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_const
 }
 
 // closest hit for every live path
+OSLD Hit intersect_slot(const RenderLaunch& L, int slot)
+{
+    float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+    float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
+    Hit h     = scene_intersect(L.S, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y), ~0u);
+    rec[4]    = make_float4(h.t, h.u, h.v, __int_as_float((int)h.id));
+    return h;
+}
+
 extern "C" __global__ void __launch_bounds__(256) rt_intersect(const __grid_constant__ RenderLaunch L)
 {
     const int n = L.counters[0];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        int slot    = L.queue_in[q];
-        float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-        float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
-        Hit h     = scene_intersect(L.S, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y), ~0u);
-        rec[4]    = make_float4(h.t, h.u, h.v, __int_as_float((int)h.id));
+        int slot = L.queue_in[q];
+        Hit h    = intersect_slot(L, slot);
         if (L.sort_keys)
             L.sort_keys[q] = (h.t == OSLD_INF) ? 0 : 1 + __ldg(L.S.shaderids + h.id);
     }
@@ -1201,15 +1207,13 @@ extern "C" __global__ void __launch_bounds__(256) rt_sort_scatter(const __grid_c
 }
 
 // shade one bounce: everything between two closest-hit queries of subpixel_radiance
-extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant__ RenderLaunch L)
+// returns whether the path continues (its record then holds the next ray)
+OSLD bool shade_slot(const RenderLaunch& L, int slot)
 {
     const RenderScene& S = L.S;
-    const int n          = L.counters[0];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31) & ~31); q += gridDim.x * blockDim.x) {
-        bool alive = false;
-        int slot   = 0;
-        if (q < n) {
-            slot        = L.queue_in[q];
+    bool alive           = false;
+    {
+        {
             float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
             const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4], q5 = rec[5], q6 = rec[6];
             Ray r;
@@ -1357,7 +1361,39 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
             } while (false);
             rec[3] = mkf4(path_radiance, out_rough);
         }
+    }
+    return alive;
+}
+
+extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant__ RenderLaunch L)
+{
+    const int n = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31) & ~31); q += gridDim.x * blockDim.x) {
+        bool alive = false;
+        int slot   = 0;
+        if (q < n) {
+            slot  = L.queue_in[q];
+            alive = shade_slot(L, slot);
+        }
         queue_push(L.queue_out, L.counters + 1, slot, alive);
+    }
+}
+
+// The tail of a batch: once only a few paths are left (glass interiors keep a handful alive
+// for tens of thousands of bounces) a bounce costs six launches for almost no work.  Each
+// remaining path is then run to its end by one thread, one warp per CTA so that the paths
+// spread over the SMs.  Same per-path arithmetic as the staged kernels, hence same pixels.
+extern "C" __global__ void __launch_bounds__(32) rt_tail(const __grid_constant__ RenderLaunch L)
+{
+    const int n = L.counters[0];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int slot = L.queue_in[q];
+        bool alive     = true;
+        while (alive) {
+            intersect_slot(L, slot);
+            __threadfence_block();
+            alive = shade_slot(L, slot);
+        }
     }
 }
 

@@ -72,11 +72,11 @@ struct DevLaunch {
 };
 
 const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_intersect", "rt_sort_count", "rt_sort_scan",
-                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve",
+                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve", "rt_tail",
                           // only in modules generated for a scene with a background
                           "rt_bg_eval", "rt_bg_rows", "rt_bg_finish", "rt_bg_scale" };
 enum { K_CAMERA, K_GENERATE, K_INTERSECT, K_SORT_COUNT, K_SORT_SCAN, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE,
-       K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE, K_N };
+       K_TAIL, K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE, K_N };
 enum { K_FIRST_BG = K_BG_EVAL };
 
 }  // namespace
@@ -87,7 +87,8 @@ struct b200_render {
     std::vector<char> cubin;
     b200_render_scene host;  // host-pointer copy of the description
     bool fma = true, sort = true;
-    long long slots_target = 4 << 20;
+    long long slots_target = 0;         // option slots=N; 0 = sized from the free device memory
+    long long tail_paths   = 2048;      // option tail=N: at most N live paths -> rt_tail (0 = never)
     std::vector<std::string> textures;  // the module's texture table, in slot order
     std::string texturepath;            // option texturepath=dir[:dir...]
     // per-device state
@@ -146,6 +147,8 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
         R->sort = atoi(opt["sort"].c_str()) != 0;
     if (opt.count("slots"))
         R->slots_target = atoll(opt["slots"].c_str());
+    if (opt.count("tail"))
+        R->tail_paths = atoll(opt["tail"].c_str());
     R->host = *scene;
     try {
         std::vector<Group*> gs;
@@ -396,7 +399,20 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
     const int xres      = r->host.xres;
     const long long npix = (long long)(y1 - y0) * xres;
     const int nsamp     = d.S.aa * d.S.aa;
-    long long SB        = r->slots_target / npix;
+    // Path slots per batch.  Every batch ends in a tail of a few long paths during which the
+    // GPU is nearly idle, so batches are made as large as memory allows (HBM is there to be
+    // used): by default a quarter of the free device memory at ~148 B of state per slot
+    // (render-microfacet 2048^2 x 64 spp: 37 s with 32 Mi slots, 152 s with 4 Mi).
+    long long target = r->slots_target;
+    if (target <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        target = (long long)(free_b / 4 / 148);
+        if (target < (4 << 20)) target = 4 << 20;
+    }
+    const long long max_slots = 0x7fffffffLL / 4;
+    if (target > max_slots) target = max_slots;
+    long long SB = target / npix;
     if (SB < 1) SB = 1;
     if (SB > nsamp) SB = nsamp;
     const long long nslots = SB * npix;
@@ -483,6 +499,18 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
         while (live > 0) {
             ++iters;
             L.queue_in  = qbuf[cur];
+            if (live <= r->tail_paths) {
+                // the stragglers: one launch runs each of them to its end (rt_tail)
+                if ((rc = launch(K_TAIL, live, 32)) != B200_OK)
+                    return rc;
+                if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)   // counters[1] is 0: nothing is queued
+                    return rc;
+                if (cudaStreamSynchronize(0) != cudaSuccess) {
+                    cudaError_t ce = cudaGetLastError();
+                    return set_error(B200_ERR_CUDA, std::string("render tail failed: ") + cudaGetErrorString(ce));
+                }
+                break;
+            }
             L.queue_out = qbuf[(cur + 1) % 3];
             if ((rc = launch(K_INTERSECT, live, 256)) != B200_OK)
                 return rc;

@@ -139,12 +139,19 @@ def test_gpu_render_bit_exact_vs_oracle(b200lib, cuda_device, case, sort):
     S, A = _scene(case)
     xml, xres, yres, aa = CASES.get(case) or TEXTURED_CASES[case]
     want = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
-    R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options="fma=0,sort=%d" % sort)
+    # sort=0 also keeps every bounce on the staged kernels (tail=0); sort=1 finishes the last
+    # <= 2048 paths in rt_tail (the default) - both must give the oracle's pixels
+    R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options="fma=0,sort=%d%s" % (sort, "" if sort else ",tail=0"))
     got = R.render()
     assert R.stats["paths"] == xres * yres * aa * aa
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
         "max |d| = %g, differing pixels %d" % (np.abs(got - want).max(), (got != want).any(axis=2).sum())
-    _check_thresholds(got, _golden(case))
+    if case in TEXTURED_CASES:      # the reference test's own thresholds (run.py), see the oracle test
+        ref = _golden(case)
+        d = np.abs(got - ref).max(axis=2)
+        assert ((d > 0.04) & (d > 0.03 * np.abs(ref).max(axis=2))).mean() * 100.0 <= 1.0
+    else:
+        _check_thresholds(got, _golden(case))
 
 
 def test_oracle_microfacet_scene_is_sane():
