@@ -298,7 +298,9 @@ def main():
             R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=1,sort=1")
             rows = [(res * k) // world for k in range(world + 1)]
             y0, y1 = rows[rank], rows[rank + 1]
-            R.render(y0, min(y1, y0 + 16), device=local)      # warm-up: module load + scene upload
+            # warm-up: module load, scene upload and the path-state allocation (sized for the band,
+            # GBs of HBM, kept for the renderer's life) - one whole frame, as a renderer's first frame
+            R.render(y0, y1, device=local)
             if world > 1:                                     # and the gather's communicator channels
                 gather_strips(torch.zeros((res * (y1 - y0), 3), device=dev), res * res, rank, world, align=res)
             barrier()
