@@ -1385,8 +1385,12 @@ extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant
 // spread over the SMs.  Same per-path arithmetic as the staged kernels, hence same pixels.
 extern "C" __global__ void __launch_bounds__(32) rt_tail(const __grid_constant__ RenderLaunch L)
 {
+    // one path per WARP (lane 0): paths of very different lengths sharing a warp would
+    // serialise each other's bounces; <= 2048 paths fit the GPU's warp slots many times over
+    if (threadIdx.x != 0)
+        return;
     const int n = L.counters[0];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
         const int slot = L.queue_in[q];
         bool alive     = true;
         while (alive) {

@@ -501,7 +501,7 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
             L.queue_in  = qbuf[cur];
             if (live <= r->tail_paths) {
                 // the stragglers: one launch runs each of them to its end (rt_tail)
-                if ((rc = launch(K_TAIL, live, 32)) != B200_OK)
+                if ((rc = launch(K_TAIL, live * 32, 32)) != B200_OK)   // one CTA (one warp) per path
                     return rc;
                 if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)   // counters[1] is 0: nothing is queued
                     return rc;
