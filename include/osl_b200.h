@@ -15,7 +15,7 @@
 extern "C" {
 #endif
 
-#define OSL_B200_ABI_VERSION 1
+#define OSL_B200_ABI_VERSION 2
 #define B200_MAX_OUTPUTS 16  /* renderer outputs per group */
 
 /* status codes */
@@ -227,17 +227,30 @@ typedef struct b200_render_stats {
     long long launches;     /* kernels launched                                */
     long long bounce_iterations;
     double device_ms;       /* CUDA-event time of the whole call               */
+    double tail_ms;         /* of which: the final rt_tail launches            */
+    long long slots;        /* path slots in the pool                          */
+    long long rounds;       /* regeneration rounds (1 unless spp x pixels > 2^30) */
 } b200_render_stats;
 
 typedef struct b200_render b200_render;
 
-/* options: fma=0|1, sort=0|1 (order live paths by material), slots=N (paths in flight) */
+/* options: fma=0|1, sort=0|1 (order live paths by closure signature / material),
+ * slots=N (path slots in the regenerating pool), tail=N (run the last N paths in one launch) */
 int b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_group_desc* materials,
                        const char* options, b200_render** out);
 void b200_render_destroy(b200_render* r);
 const char* b200_render_cuda_source(const b200_render* r);
+const void* b200_render_cubin(const b200_render* r, long long* size);   /* the sm_100a module */
 /* Render image rows [y0, y1) into host_rgb ((y1-y0)*xres*3 floats).  Synchronous. */
 int b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b200_render_stats* stats);
+/* Render a work set of image tiles: tiles = ntiles x {x0, y0, width, height}.  This is how a
+ * frame is shared between GPUs (interleaved tiles per GPU; the reference spreads
+ * scanline chunks over host threads, simpleraytracer.cpp:1428).  Pixels are numbered tile
+ * after tile, row-major inside a tile; out_rgb receives 3 floats per pixel in that order, in
+ * host memory or, with out_on_device != 0, in device memory of `device` (for a framebuffer
+ * gather without a host round trip).  Synchronous. */
+int b200_render_tiles(b200_render* r, int device, int ntiles, const int* tiles, void* out_rgb,
+                      int out_on_device, b200_render_stats* stats);
 
 const char* b200_last_error(void);
 int b200_abi_version(void);

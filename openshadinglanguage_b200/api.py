@@ -309,7 +309,8 @@ class _RenderScene(ctypes.Structure):
 
 class _RenderStats(ctypes.Structure):
     _fields_ = [("paths", ctypes.c_longlong), ("launches", ctypes.c_longlong),
-                ("bounce_iterations", ctypes.c_longlong), ("device_ms", ctypes.c_double)]
+                ("bounce_iterations", ctypes.c_longlong), ("device_ms", ctypes.c_double),
+                ("tail_ms", ctypes.c_double), ("slots", ctypes.c_longlong), ("rounds", ctypes.c_longlong)]
 
 
 def _group_desc(layers, connections, name, options, keep):
@@ -366,6 +367,8 @@ class Renderer:
         L.b200_render_cuda_source.restype = ctypes.c_char_p
         L.b200_render_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_void_p, ctypes.POINTER(_RenderStats)]
+        L.b200_render_tiles.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(_RenderStats)]
         keep = []
         rs = _RenderScene()
 
@@ -414,12 +417,57 @@ class Renderer:
     def cuda_source(self):
         return lib().b200_render_cuda_source(self._h).decode()
 
+    @property
+    def cubin(self):
+        L = lib()
+        L.b200_render_cubin.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+        L.b200_render_cubin.restype = ctypes.c_void_p
+        n = ctypes.c_longlong()
+        p = L.b200_render_cubin(self._h, ctypes.byref(n))
+        return ctypes.string_at(p, n.value)
+
     def render(self, y0=0, y1=None, device=0):
         """-> float32 [(y1-y0), xres, 3]"""
         y1 = self.yres if y1 is None else y1
         out = np.zeros((y1 - y0, self.xres, 3), np.float32)
         st = _RenderStats()
         _check(lib().b200_render_rows(self._h, device, y0, y1, out.ctypes.data, ctypes.byref(st)))
-        self.stats = dict(paths=st.paths, launches=st.launches, bounce_iterations=st.bounce_iterations,
-                          device_ms=st.device_ms)
+        self._set_stats(st)
         return out
+
+    def _set_stats(self, st):
+        self.stats = dict(paths=st.paths, launches=st.launches, bounce_iterations=st.bounce_iterations,
+                          device_ms=st.device_ms, tail_ms=st.tail_ms, slots=st.slots, rounds=st.rounds)
+
+    def render_tiles(self, tiles, device=0, out=None):
+        """Render a work set of tiles [(x0, y0, w, h), ...] -> float32 [npix, 3], pixels tile after
+        tile (row-major inside a tile).  `out`: optional CUDA torch tensor [npix, 3] float32 on
+        `device`; the result then stays in device memory (framebuffer gather without a host copy)."""
+        t = np.ascontiguousarray(np.asarray(tiles, np.int32).reshape(-1, 4))
+        npix = int((t[:, 2].astype(np.int64) * t[:, 3]).sum())
+        st = _RenderStats()
+        if out is None:
+            res = np.zeros((npix, 3), np.float32)
+            _check(lib().b200_render_tiles(self._h, device, len(t), t.ctypes.data, res.ctypes.data, 0, ctypes.byref(st)))
+        else:
+            assert out.is_cuda and out.is_contiguous() and out.numel() == npix * 3 and out.element_size() == 4
+            res = out
+            _check(lib().b200_render_tiles(self._h, device, len(t), t.ctypes.data, out.data_ptr(), 1, ctypes.byref(st)))
+        self._set_stats(st)
+        return res
+
+
+def tile_list(xres, yres, tile=64):
+    """All tiles of an image, row-major, as an int32 [n, 4] array of (x0, y0, w, h)."""
+    ts = [(x, y, min(tile, xres - x), min(tile, yres - y)) for y in range(0, yres, tile) for x in range(0, xres, tile)]
+    return np.asarray(ts, np.int32)
+
+
+def tile_pixels(tiles):
+    """Image coordinates (ys, xs) of a tile work set's pixels, in the order render_tiles returns them."""
+    ys, xs = [], []
+    for x0, y0, w, h in np.asarray(tiles, np.int64).reshape(-1, 4):
+        yy, xx = np.mgrid[y0:y0 + h, x0:x0 + w]
+        ys.append(yy.ravel())
+        xs.append(xx.ravel())
+    return np.concatenate(ys), np.concatenate(xs)

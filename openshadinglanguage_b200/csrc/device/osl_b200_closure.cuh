@@ -5,7 +5,7 @@
 // renderer's per-point bump allocator (src/testshade/render_state.h:27-54).
 // A closure value is a 32-bit word offset into a per-thread pool (0 = NULL)
 // instead of a pointer, so the tree is position independent and the pool can
-// live in local memory or be spilled to a wavefront arena:
+// live in local memory or, interleaved by thread, in the CTA's shared memory:
 //   component : [id][w.x][w.y][w.z][params ...]
 //   mul       : [CL_MUL][w.x][w.y][w.z][child]
 //   add       : [CL_ADD][a][b]
@@ -23,11 +23,35 @@ enum ClosureIDs {
     MX_UNIFORM_EDF_ID, MX_ANISOTROPIC_VDF_ID, MX_MEDIUM_VDF_ID, MX_LAYER_ID, SPI_THINLAYER, EMPTY_ID
 };
 
+#ifndef OSLD_POOL_WORDS
 #define OSLD_POOL_WORDS 256  // 1 KB, the reference's StackClosurePool size
+#endif
+
+// Word i of a thread's arena sits at p[i * s]: s = 1 for a private (local-memory) array,
+// s = CTA size when the arenas of a CTA are staged in shared memory, interleaved by thread
+// so that a warp touching "its word i" hits 32 different banks.  The code generator sizes
+// the arena from the closure ops of the material (OSLD_POOL_WORDS) so that it fits there.
+struct PoolPtr {
+    float* p;
+    int s;
+    OSLD float& operator[](int i) const { return p[i * s]; }
+    OSLD PoolPtr operator+(int k) const
+    {
+        PoolPtr r;
+        r.p = p + k * s;
+        r.s = s;
+        return r;
+    }
+};
 
 struct ClosurePool {
-    int used;  // next free word; word 0 is reserved so that offset 0 means NULL
-    float w[OSLD_POOL_WORDS];
+    int used;   // next free word; word 0 is reserved so that offset 0 means NULL
+    PoolPtr w;  // storage: bind() before use
+    OSLD void bind(float* storage, int stride)
+    {
+        w.p = storage;
+        w.s = stride;
+    }
     OSLD void reset() { used = 1; }
     OSLD int alloc(int nwords)
     {
@@ -39,6 +63,7 @@ struct ClosurePool {
     }
     OSLD int id(int c) const { return __float_as_int(w[c]); }
     OSLD V3 weight(int c) const { return mkv(w[c + 1], w[c + 2], w[c + 3]); }
+    OSLD int child(int c, int k) const { return __float_as_int(w[c + k]); }
 };
 
 OSLD bool v3_is_zero(V3 a) { return a.x == 0.0f && a.y == 0.0f && a.z == 0.0f; }
@@ -97,8 +122,8 @@ OSLD int clos_add(ClosurePool& p, int a, int b)
     }
     return c;
 }
-OSLD void putp(float* q, float v) { *q = v; }
-OSLD void putp(float* q, int v) { *q = __int_as_float(v); }
-OSLD void putp(float* q, V3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; }
+OSLD void putp(PoolPtr q, float v) { q[0] = v; }
+OSLD void putp(PoolPtr q, int v) { q[0] = __int_as_float(v); }
+OSLD void putp(PoolPtr q, V3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; }
 
 }  // namespace osld

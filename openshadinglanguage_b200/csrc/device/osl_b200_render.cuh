@@ -11,15 +11,24 @@
 //   process_closure                                    src/testrender/shading.cpp:1448-1706
 //   fresnel_dielectric / fresnel_refraction            src/testrender/optics.h:13-60
 //
-// Structure: path state lives in HBM as SoA planes; every bounce is
-//   rt_intersect  (closest hit for every live path, coalesced state loads)
-//   [rt_sort_*]   (counting sort of the live queue by material = closure type,
-//                  warp-aggregated with __match_any_sync)
-//   rt_shade      (globals from hit -> material dispatch -> closure -> lobes ->
-//                  emission + light-sample NEE incl. shadow ray -> BSDF sample)
-// with survivors compacted into the next queue by warp-aggregated atomics.
-// Samples of one pixel are resolved in the reference's order (running lerp), so
-// in strict mode the image is bit-identical to the scalar CPU oracle.
+// Structure: a pool of path slots lives in HBM, one 128-byte record per slot.  A render is a
+// loop of "bounce steps" over the pool; every step is
+//   rt_trace         one persistent kernel walks the BVH for ALL rays of the step: the closest
+//                    hit of every live path and the NEE shadow rays (any-hit) the previous
+//                    shade emitted.  Warps refill finished lanes from the queues (dynamic
+//                    fetch), traversal stacks are staged in shared memory.
+//   rt_light         NEE of the previous bounce: unoccluded shadow rays add their contribution
+//                    (light shader executed here), finished paths are written out and their
+//                    slot is REGENERATED with the next camera sample.
+//   rt_sort_scatter  counting sort of the live queue by closure-type signature / material
+//                    (histogram accumulated by rt_trace in shared memory)
+//   rt_shade         globals from hit -> material dispatch -> closure arena (shared memory)
+//                    -> lobes -> emission -> NEE set-up -> BSDF sample; dead paths regenerate.
+// so a long path (glass interiors live for 10^5 bounces) never drains the machine: the pool
+// stays full until the samples of the work set run out.  Every finished sample stores its
+// radiance in a per-sample slot and rt_resolve folds them in the reference's order (running
+// lerp over the sample index), so in strict mode the image is bit-identical to the scalar
+// CPU oracle whatever the scheduling was.
 //
 // This header is included by the generated render module AFTER the material
 // namespaces and `osl_execute_shader(int shaderID, SG&)` have been emitted.
@@ -62,34 +71,58 @@ struct RenderScene {
 };
 
 // Path state: one 128-byte record (8 x float4) per path slot.  After the live
-// queue has been sorted by material the slots a warp touches are scattered, so
+// queue has been sorted the slots a warp touches are scattered, so
 // the state is laid out per path (every 32-byte sector fetched is fully used
 // and moved with 16-byte LDG/STG) rather than as per-field planes.
 //   q0 = origin.xyz, radius      q1 = direction.xyz, spread
 //   q2 = path_weight.rgb, bsdf_pdf   q3 = path_radiance.rgb, roughness
 //   q4 = hit t,u,v, hit id       q5 = raytype, prev_id, bounce, sampler seed
-//   q6 = sampler index, -, -, -  q7 = unused
+//   q6 = sampler index, sample id, -, -  q7 = light sample u, v, -, -
+// Pending NEE shadow rays of a slot: 4 x float4 in a second array
+//   s0 = background dir.xyz, flags   s1 = background contribution.rgb, visibility bits
+//   s2 = light dir.xyz, distance     s3 = light contribution.rgb, light primitive id
 #define OSLD_PATH_QUADS 8
+#define OSLD_SHADOW_QUADS 4
 OSLD float4 mkf4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 OSLD V3 xyz(float4 q) { return mkv(q.x, q.y, q.z); }
 OSLD float4 mki4(int a, int b, int c, int d)
 {
     return make_float4(__int_as_float(a), __int_as_float(b), __int_as_float(c), __int_as_float(d));
 }
+enum { SH_BG = 1, SH_LIGHT = 2, SH_DEAD = 4 };
+
+// counters[]: device-side loop state of a render call
+enum { C_LIVE = 0,     // paths in queue_in
+       C_OUT,          // paths appended to queue_out by this step
+       C_SHADOW,       // entries of queue_sh to trace + light in this step
+       C_SHADOW_OUT,   // entries appended to queue_sh by this step's shade
+       C_NEXT,         // next sample id of the round to start
+       C_FETCH,        // rt_trace's dynamic-fetch cursor
+       C_ITER,         // bounce steps done
+       C_FINISHED,     // samples written out
+       C_HIST   = 8,   // 64 sort buckets: histogram
+       C_CURSOR = 8 + 64,
+       C_WORDS  = 8 + 128 };
 
 struct RenderLaunch {
     RenderScene S;
     float4* rec;          // nslots x OSLD_PATH_QUADS
+    float4* shrec;        // nslots x OSLD_SHADOW_QUADS
     int* queue_in;        // live path slots
     int* queue_out;
-    int* counters;        // [0] in count, [1] out count, [2..] sort scratch
-    int* sort_keys;       // material key per queue entry
-    int nslots;           // SB * npix
-    int npix;             // pixels in this band
-    int y0;               // first image row of the band
-    int s0;               // first sample index of the batch
-    int nsamples;         // samples in flight (SB)
-    float* accum;         // running per-pixel result, 3 floats per pixel of the band
+    int* queue_sh;        // slots with pending shadow rays
+    int* counters;
+    int* sort_keys;       // bucket per queue_in entry (null: no sort)
+    const int* shader_key;  // bucket of a material: closure-type signature rank, then material
+    const int* pixmap;    // the work set: packed (y << 16) | x per pixel, tile after tile
+    volatile int* host_state;  // mapped pinned host memory: {iter, live, shadow, next} after every step
+    int nslots;           // path slots in the pool
+    int npix;             // pixels in the work set
+    int s0;               // first sample plane of the round
+    int nsamples;         // sample planes in the round
+    int total;            // samples in the round = nsamples * npix
+    float* result;        // total x 3: radiance of every sample of the round
+    float* accum;         // running per-pixel result, 3 floats per work-set pixel
 };
 
 OSLD V3 ld3(const float* p, int i) { return mkv(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
@@ -394,7 +427,16 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
     }
 }
 
+// The reference's CompositeBSDF holds at most 8 lobes (shading.h:319).  The code generator
+// knows how many BSDF components the scene's materials can create (OSLD_MAX_LOBES <= 8) and how
+// deep their add / layer trees go (OSLD_CLOSURE_STACK <= 16), so the per-thread arrays are
+// sized for the scene, not for the worst case.
+#ifndef OSLD_MAX_LOBES
 #define OSLD_MAX_LOBES 8
+#endif
+#ifndef OSLD_CLOSURE_STACK
+#define OSLD_CLOSURE_STACK 16
+#endif
 struct CompositeBSDF {
     V3 weights[OSLD_MAX_LOBES];
     float pdfs[OSLD_MAX_LOBES];
@@ -457,8 +499,8 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
 {
     if (!closure)
         return mkv(0.0f);
-    int ptr_stack[16];
-    V3 weight_stack[16];
+    int ptr_stack[OSLD_CLOSURE_STACK];
+    V3 weight_stack[OSLD_CLOSURE_STACK];
     int sp    = 0;
     V3 weight = mkv(1.0f);
     while (closure) {
@@ -472,7 +514,7 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
             closure            = __float_as_int(pool.w[closure + 1]);
         } else {
             const V3 w     = pool.weight(closure);
-            const float* q = pool.w + closure + 4;
+            const PoolPtr q = pool.w + (closure + 4);
             closure        = 0;
             if (id == MX_LAYER_ID) {
                 closure            = __float_as_int(q[0]);
@@ -505,8 +547,8 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
 OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only,
                           V3 wo = mkv(0.0f, 0.0f, 1.0f), bool backfacing = false, float path_roughness = 0.0f)
 {
-    int ptr_stack[16];
-    V3 weight_stack[16];
+    int ptr_stack[OSLD_CLOSURE_STACK];
+    V3 weight_stack[OSLD_CLOSURE_STACK];
     int sp    = 0;
     V3 weight = mkv(1.0f);
     while (closure) {
@@ -520,7 +562,7 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
             closure            = __float_as_int(pool.w[closure + 1]);
         } else {
             V3 cw          = weight * pool.weight(closure);
-            const float* q = pool.w + closure + 4;
+            const PoolPtr q = pool.w + (closure + 4);
             closure        = 0;
             if (id == EMISSION_ID)
                 Le = Le + cw;
@@ -646,23 +688,69 @@ OSLD bool box_intersect(V3 org, V3 rdir, float tmax, float4 b0, float4 b1, float
 }
 OSLD float xorf(float a, unsigned b) { return __int_as_float((int)(fbits(a) ^ b)); }
 
-OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsigned skip1, unsigned skip2)
+// Traversal stack of a thread: OSLD_BVH_STACK entries (the host sizes it from the depth of the
+// scene's BVH when the module is compiled) of OSLD_STK_WORDS words, word j of the thread at
+// stk[j * stride] - a slice of the CTA's shared memory interleaved by thread (conflict free),
+// where the reference keeps three 64-entry arrays on the CPU stack (bvh.cpp:271-273).
+// An entry carries the pending node's (child, nprims) words, already fetched with its bounds
+// when the parent was visited, so a pop costs no further node load; packed into one word when
+// the host found child < 2^26 and nprims < 64 for every node.
+#ifndef OSLD_BVH_STACK
+#define OSLD_BVH_STACK 64
+#endif
+#ifdef OSLD_BVH_UNPACKED
+#define OSLD_STK_WORDS 3
+#else
+#define OSLD_STK_WORDS 2
+#endif
+struct Trav {
+    V3 org, rdir;
+    float shx, shy, shz;
+    float tmax0;     // any-hit rays: a hit strictly closer than this ends the walk (occluded)
+    Hit hit;
+    unsigned skip1, skip2;
+    int kx, ky, kz, sp, anyhit;
+    unsigned* stk;
+    int stride;
+};
+OSLD void stk_put(const Trav& T, int i, unsigned child, unsigned nprims, float dist)
 {
-    // the stack keeps each pending node's (child, nprims) words, already fetched with its
-    // bounds when the parent was visited, so a pop costs no further node load
-    unsigned stack_child[64], stack_nprims[64];
-    float stack_dist[64];
-    Hit result;
-    result.t  = tmax;
-    result.u  = result.v = 0.0f;
-    result.id = 0;
-    {
-        const float4 r1 = __ldg(S.bvh_nodes + 1);
-        stack_child[0]  = fbits(r1.z);
-        stack_nprims[0] = fbits(r1.w);
-    }
-    stack_dist[0] = result.t;
-    const V3 rdir = mkv(1 / dir.x, 1 / dir.y, 1 / dir.z);
+    unsigned* e = T.stk + (size_t)(OSLD_STK_WORDS * i) * T.stride;
+#ifdef OSLD_BVH_UNPACKED
+    e[0]            = child;
+    e[T.stride]     = fbits(dist);
+    e[2 * T.stride] = nprims;
+#else
+    e[0]        = child | (nprims << 26);
+    e[T.stride] = fbits(dist);
+#endif
+}
+OSLD float stk_dist(const Trav& T, int i)
+{
+    return __int_as_float((int)T.stk[(size_t)(OSLD_STK_WORDS * i + 1) * T.stride]);
+}
+OSLD void stk_get(const Trav& T, int i, unsigned& child, unsigned& nprims)
+{
+    const unsigned* e = T.stk + (size_t)(OSLD_STK_WORDS * i) * T.stride;
+#ifdef OSLD_BVH_UNPACKED
+    child  = e[0];
+    nprims = e[2 * T.stride];
+#else
+    child  = e[0] & 0x3ffffffu;
+    nprims = e[0] >> 26;
+#endif
+}
+OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3 org, V3 dir, float tmax,
+                    unsigned skip1, unsigned skip2, int anyhit)
+{
+    T.stk = stk; T.stride = stride;
+    T.org = org;
+    T.hit.t = tmax; T.hit.u = T.hit.v = 0.0f; T.hit.id = 0;
+    T.tmax0 = tmax; T.skip1 = skip1; T.skip2 = skip2; T.anyhit = anyhit;
+    const float4 r1 = __ldg(S.bvh_nodes + 1);
+    stk_put(T, 0, fbits(r1.z), fbits(r1.w), tmax);
+    T.sp   = 1;
+    T.rdir = mkv(1 / dir.x, 1 / dir.y, 1 / dir.z);
     int kz = 0;
     if (fabsf(dir.y) > fabsf(vcomp(dir, kz)))
         kz = 1;
@@ -670,21 +758,35 @@ OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsig
         kz = 2;
     int kx = kz == 2 ? 0 : kz + 1;
     int ky = kx == 2 ? 0 : kx + 1;
-    const float shx = vcomp(dir, kx) / vcomp(dir, kz), shy = vcomp(dir, ky) / vcomp(dir, kz), shz = vcomp(rdir, kz);
-    // "while-while" traversal (Aila & Laine): every lane first walks inner nodes until it holds
-    // a leaf, then the warp tests triangles together.  Per ray the visiting order is exactly
-    // the reference's pop / test / push-far-then-near sequence; only the lock-step grouping of
-    // the lanes changes (leaf tests no longer serialise against other lanes' box tests).
-    int sp = 1;
-    for (;;) {
+    T.kx = kx; T.ky = ky; T.kz = kz;
+    T.shx = vcomp(dir, kx) / vcomp(dir, kz);
+    T.shy = vcomp(dir, ky) / vcomp(dir, kz);
+    T.shz = vcomp(T.rdir, kz);
+}
+// Scene::intersect (bvh.cpp:265-356), resumable: walks until the ray is finished (returns true)
+// or `budget` node / leaf visits have been spent (returns false; call again).
+// "while-while" traversal (Aila & Laine): every lane first walks inner nodes until it holds
+// a leaf, then the warp tests triangles together.  Per ray the visiting order is exactly
+// the reference's pop / test / push-far-then-near sequence; only the lock-step grouping of
+// the lanes changes, so the hit (and any tie between coplanar triangles) is the reference's.
+OSLD bool trav_run(const RenderScene& S, Trav& T, int budget)
+{
+    const V3 org = T.org, rdir = T.rdir;
+    const int kx = T.kx, ky = T.ky, kz = T.kz;
+    const float shx = T.shx, shy = T.shy, shz = T.shz;
+    int sp = T.sp;
+    Hit result = T.hit;
+    bool finished = false;
+    while (budget > 0) {
         unsigned child = 0, nprims = 0;
         while (sp != 0) {
-            if (result.t < stack_dist[--sp])
+            --sp;
+            if (result.t < stk_dist(T, sp))
                 continue;
-            child  = stack_child[sp];
-            nprims = stack_nprims[sp];
+            stk_get(T, sp, child, nprims);
             if (nprims)
                 break;
+            --budget;
             // the two children are adjacent: 64 contiguous bytes
             const float4* cn = S.bvh_nodes + 2 * (size_t)child;
             const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
@@ -698,51 +800,64 @@ OSLD Hit scene_intersect(const RenderScene& S, V3 org, V3 dir, float tmax, unsig
                 unsigned tk = k1; k1 = k2; k2 = tk;
                 unsigned tn = n1; n1 = n2; n2 = tn;
             }
-            stack_child[sp]  = k2;
-            stack_nprims[sp] = n2;
-            stack_dist[sp]   = d2;
+            stk_put(T, sp, k2, n2, d2);
             sp += h2 ? 1 : 0;
-            stack_child[sp]  = k1;
-            stack_nprims[sp] = n1;
-            stack_dist[sp]   = d1;
+            stk_put(T, sp, k1, n1, d1);
             sp += h1 ? 1 : 0;
         }
-        if (!nprims)
+        if (!nprims) {
+            finished = true;
             break;
-        {
-            for (unsigned i = 0; i < nprims; i++) {
-                const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
-                const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
-                const unsigned id = fbits(ta.w);
-                const V3 A = xyz(ta) - org;
-                const V3 B = xyz(tb) - org;
-                const V3 C = xyz(tc) - org;
-                const float Ax = vcomp(A, kx) - shx * vcomp(A, kz), Ay = vcomp(A, ky) - shy * vcomp(A, kz);
-                const float Bx = vcomp(B, kx) - shx * vcomp(B, kz), By = vcomp(B, ky) - shy * vcomp(B, kz);
-                const float Cx = vcomp(C, kx) - shx * vcomp(C, kz), Cy = vcomp(C, ky) - shy * vcomp(C, kz);
-                const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
-                if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
-                    continue;
-                const float det = U + V + W;
-                if (det == 0)
-                    continue;
-                const float T       = shz * (U * vcomp(A, kz) + V * vcomp(B, kz) + W * vcomp(C, kz));
-                const unsigned mask = fbits(det) & 0x80000000u;
-                if (xorf(T, mask) < 0)
-                    continue;
-                if (xorf(T, mask) > result.t * xorf(det, mask))
-                    continue;
-                if (id == skip1 || id == skip2)
-                    continue;
-                const float rcpDet = 1 / det;
-                result.t  = T * rcpDet;
-                result.u  = V * rcpDet;
-                result.v  = W * rcpDet;
-                result.id = id;
-            }
+        }
+        --budget;
+        for (unsigned i = 0; i < nprims; i++) {
+            const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
+            const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
+            const unsigned id = fbits(ta.w);
+            const V3 A = xyz(ta) - org;
+            const V3 B = xyz(tb) - org;
+            const V3 C = xyz(tc) - org;
+            const float Ax = vcomp(A, kx) - shx * vcomp(A, kz), Ay = vcomp(A, ky) - shy * vcomp(A, kz);
+            const float Bx = vcomp(B, kx) - shx * vcomp(B, kz), By = vcomp(B, ky) - shy * vcomp(B, kz);
+            const float Cx = vcomp(C, kx) - shx * vcomp(C, kz), Cy = vcomp(C, ky) - shy * vcomp(C, kz);
+            const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+            if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
+                continue;
+            const float det = U + V + W;
+            if (det == 0)
+                continue;
+            const float Tt      = shz * (U * vcomp(A, kz) + V * vcomp(B, kz) + W * vcomp(C, kz));
+            const unsigned mask = fbits(det) & 0x80000000u;
+            if (xorf(Tt, mask) < 0)
+                continue;
+            if (xorf(Tt, mask) > result.t * xorf(det, mask))
+                continue;
+            if (id == T.skip1 || id == T.skip2)
+                continue;
+            const float rcpDet = 1 / det;
+            result.t  = Tt * rcpDet;
+            result.u  = V * rcpDet;
+            result.v  = W * rcpDet;
+            result.id = id;
+        }
+        // a shadow ray only asks "is anything strictly closer than tmax0": the closest-hit walk
+        // can only move t further down from here, so the answer is already known
+        if (T.anyhit && result.t < T.tmax0) {
+            finished = true;
+            break;
         }
     }
-    return result;
+    T.sp  = sp;
+    T.hit = result;
+    return finished;
+}
+OSLD Hit scene_intersect(const RenderScene& S, unsigned* stk, int stride, V3 org, V3 dir, float tmax,
+                         unsigned skip1, unsigned skip2, int anyhit = 0)
+{
+    Trav T;
+    trav_init(S, T, stk, stride, org, dir, tmax, skip1, skip2, anyhit);
+    while (!trav_run(S, T, 1 << 30)) {}
+    return T.hit;
 }
 
 // ---- scene queries -----------------------------------------------------------------------
@@ -900,8 +1015,8 @@ OSLD V3 process_background_closure(const ClosurePool& pool, int closure)
 {
     if (!closure)
         return mkv(0.0f);
-    int ptr_stack[16];
-    V3 weight_stack[16];
+    int ptr_stack[OSLD_CLOSURE_STACK];
+    V3 weight_stack[OSLD_CLOSURE_STACK];
     int sp    = 0;
     V3 weight = mkv(1.0f);
     while (closure) {
@@ -925,7 +1040,7 @@ OSLD V3 process_background_closure(const ClosurePool& pool, int closure)
     }
     return weight;
 }
-OSLD V3 eval_background(const RenderScene& S, V3 dir, V3 ddx, V3 ddy, int bounce)
+OSLD V3 eval_background(const RenderScene& S, V3 dir, V3 ddx, V3 ddy, int bounce, ClosurePool& pool)
 {
     SG sg;
     memset(&sg, 0, sizeof(SG));
@@ -934,7 +1049,6 @@ OSLD V3 eval_background(const RenderScene& S, V3 dir, V3 ddx, V3 ddy, int bounce
     sg.I_dy = ddy;
     if (bounce >= 0)
         sg.raytype = bounce > 0 ? RAY_DIFFUSE : RAY_CAMERA;
-    ClosurePool pool;
     pool.reset();
     sg.pool = &pool;
     sg.Ci   = 0;
@@ -1015,7 +1129,8 @@ OSLD V3 bg_sample(const RenderScene& S, float rx, float ry, V3& dir, float& pdf)
 }
 #endif  // OSLD_HAS_BACKGROUND
 
-// warp-aggregated append of a surviving path to the next queue
+
+// warp-aggregated append to a queue
 OSLD void queue_push(int* queue, int* counter, int value, bool pred)
 {
     unsigned m = __ballot_sync(__activemask(), pred);
@@ -1029,6 +1144,19 @@ OSLD void queue_push(int* queue, int* counter, int value, bool pred)
     base = __shfl_sync(m, base, leader);
     queue[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
+
+// The closure arena of a thread: a slice of the CTA's shared memory when the generator could
+// bound it (OSLD_POOL_SMEM: <= 64 words per thread), else a private array.
+#ifdef OSLD_POOL_SMEM
+#define OSLD_POOL_DECL(pool, smem_words)                                   \
+    ClosurePool pool;                                                      \
+    pool.bind(reinterpret_cast<float*>(smem_words) + threadIdx.x, blockDim.x)
+#else
+#define OSLD_POOL_DECL(pool, smem_words)     \
+    float pool##_store_[OSLD_POOL_WORDS];    \
+    ClosurePool pool;                        \
+    pool.bind(pool##_store_, 1)
+#endif
 
 }  // namespace osld
 
@@ -1061,13 +1189,15 @@ extern "C" __global__ void rt_camera(const __grid_constant__ RenderLaunch L, flo
 #ifdef OSLD_HAS_BACKGROUND
 extern "C" __global__ void __launch_bounds__(128) rt_bg_eval(const __grid_constant__ RenderLaunch L)
 {
+    extern __shared__ unsigned smem_[];
+    OSLD_POOL_DECL(pool, smem_);
     const RenderScene& S = L.S;
     const int res = S.bg_res, n = res * res;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int y = i / res, x = i - y * res;
         V3 d, ddx, ddy;
         bg_map(S, (float)x + 0.5f, (float)y + 0.5f, d, ddx, ddy);
-        V3 c = eval_background(S, d, ddx, ddy, -1);
+        V3 c = eval_background(S, d, ddx, ddy, -1, pool);
         S.bg_values[3 * i] = c.x; S.bg_values[3 * i + 1] = c.y; S.bg_values[3 * i + 2] = c.z;
     }
 }
@@ -1115,310 +1245,536 @@ extern "C" __global__ void __launch_bounds__(256) rt_bg_scale(const __grid_const
 }
 #endif  // OSLD_HAS_BACKGROUND
 
-// one thread per path slot: camera sample -> initial path state
-extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_constant__ RenderLaunch L)
+// ---- path life cycle ---------------------------------------------------------------------------
+// Sample `sid` of the round = sample plane sid / npix of work-set pixel sid % npix
+// (antialias_pixel, simpleraytracer.cpp:1197-1213): camera sample -> initial path state.
+OSLD void path_start(const RenderLaunch& L, int slot, int sid)
 {
     const RenderScene& S = L.S;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < L.nslots; slot += gridDim.x * blockDim.x) {
-        int sb = slot / L.npix, pix = slot - sb * L.npix;
-        int x = pix % S.xres, y = L.y0 + pix / S.xres;
-        int si = L.s0 + sb;
-        Sampler sampler;
-        sampler.init(x, y, si);
-        V3 j = S.no_jitter ? mkv(0.5f, 0.5f, 0.0f) : sampler.get();
-        j.x *= 2;
-        j.x = j.x < 1 ? sqrtf(j.x) - 1 : 1 - sqrtf(2 - j.x);
-        j.y *= 2;
-        j.y = j.y < 1 ? sqrtf(j.y) - 1 : 1 - sqrtf(2 - j.y);
-        Ray r = camera_ray(S, (float)x + 0.5f + j.x, (float)y + 0.5f + j.y);
-        float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-        rec[0] = mkf4(r.origin, r.radius);
-        rec[1] = mkf4(r.direction, r.spread);
-        rec[2] = make_float4(1.0f, 1.0f, 1.0f, OSLD_INF);
-        rec[3] = make_float4(0.0f, 0.0f, 0.0f, r.roughness);
-        rec[5] = mki4(r.raytype, -1, 0, (int)sampler.seed);
-        rec[6] = mki4((int)sampler.index, 0, 0, 0);
+    const int sb = sid / L.npix, pix = sid - sb * L.npix;
+    const int xy = __ldg(L.pixmap + pix);
+    const int x = xy & 0xffff, y = (int)((unsigned)xy >> 16);
+    const int si = L.s0 + sb;
+    Sampler sampler;
+    sampler.init(x, y, si);
+    V3 j = S.no_jitter ? mkv(0.5f, 0.5f, 0.0f) : sampler.get();
+    j.x *= 2;
+    j.x = j.x < 1 ? sqrtf(j.x) - 1 : 1 - sqrtf(2 - j.x);
+    j.y *= 2;
+    j.y = j.y < 1 ? sqrtf(j.y) - 1 : 1 - sqrtf(2 - j.y);
+    Ray r = camera_ray(S, (float)x + 0.5f + j.x, (float)y + 0.5f + j.y);
+    float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+    rec[0] = mkf4(r.origin, r.radius);
+    rec[1] = mkf4(r.direction, r.spread);
+    rec[2] = make_float4(1.0f, 1.0f, 1.0f, OSLD_INF);
+    rec[3] = make_float4(0.0f, 0.0f, 0.0f, r.roughness);
+    rec[5] = mki4(r.raytype, -1, 0, (int)sampler.seed);
+    rec[6] = mki4((int)sampler.index, sid, 0, 0);
+}
+// a finished sample: its radiance goes to the sample's own slot (rt_resolve folds in order)
+OSLD void path_finish(const RenderLaunch& L, int slot)
+{
+    const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+    const float4 q3 = rec[3];
+    const int sid   = __float_as_int(rec[6].y);
+    float* r        = L.result + 3 * (size_t)sid;
+    r[0] = q3.x; r[1] = q3.y; r[2] = q3.z;
+}
+// path regeneration: a freed slot takes the next sample of the round, if any is left
+OSLD bool path_regen(const RenderLaunch& L, int slot, bool want)
+{
+    unsigned m = __ballot_sync(__activemask(), want);
+    if (!want)
+        return false;
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+    if (lane == leader)
+        base = atomicAdd(L.counters + C_NEXT, __popc(m));
+    base    = __shfl_sync(m, base, leader);
+    int sid = base + __popc(m & ((1u << lane) - 1u));
+    if (sid >= L.total)
+        return false;
+    path_start(L, slot, sid);
+    return true;
+}
+
+// one thread per path slot of the initial fill
+extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_constant__ RenderLaunch L)
+{
+    const int n0 = L.nslots < L.total ? L.nslots : L.total;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n0; slot += gridDim.x * blockDim.x) {
+        path_start(L, slot, slot);
         L.queue_in[slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        L.counters[0] = L.nslots;
-        L.counters[1] = 0;
+        L.counters[C_LIVE]   = n0;
+        L.counters[C_NEXT]   = n0;
+        L.counters[C_OUT]    = 0;
+        L.counters[C_SHADOW] = L.counters[C_SHADOW_OUT] = L.counters[C_FETCH] = 0;
     }
 }
 
-// closest hit for every live path
-OSLD Hit intersect_slot(const RenderLaunch& L, int slot)
+// ---- rt_trace: every ray of the step -----------------------------------------------------------
+// Work items [0, live) are closest-hit queries of the live paths, [live, live + shadow) are the
+// slots with pending NEE shadow rays (background ray, then light ray: two any-hit walks).
+// Persistent warps: a lane that finishes its item takes the next one from the global cursor
+// while the other lanes keep walking (rays of very different length share a warp; without
+// this the warp idles on its longest ray: ncu showed 7 of 32 lanes active in round 1).
+#ifndef OSLD_TRACE_CHUNK
+#define OSLD_TRACE_CHUNK 12   // node / leaf visits between two refills
+#endif
+#define OSLD_TRACE_BLOCK 128
+extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __grid_constant__ RenderLaunch L)
 {
-    float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-    float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
-    Hit h     = scene_intersect(L.S, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y), ~0u);
-    rec[4]    = make_float4(h.t, h.u, h.v, __int_as_float((int)h.id));
-    return h;
-}
-
-extern "C" __global__ void __launch_bounds__(256) rt_intersect(const __grid_constant__ RenderLaunch L)
-{
-    const int n = L.counters[0];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        int slot = L.queue_in[q];
-        Hit h    = intersect_slot(L, slot);
-        if (L.sort_keys)
-            L.sort_keys[q] = (h.t == OSLD_INF) ? 0 : 1 + __ldg(L.S.shaderids + h.id);
-    }
-}
-
-// counting sort of the live queue by material key (0 = miss); counters[2+k] = histogram,
-// counters[2+64+k] = running cursor.  Stable order is not required: paths are independent.
-extern "C" __global__ void __launch_bounds__(256) rt_sort_count(const __grid_constant__ RenderLaunch L)
-{
-    const int n = L.counters[0];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        int key    = L.sort_keys[q];
-        unsigned m = __match_any_sync(__activemask(), key);
-        if ((threadIdx.x & 31) == __ffs(m) - 1)
-            atomicAdd(L.counters + 2 + key, __popc(m));
-    }
-}
-extern "C" __global__ void rt_sort_scan(const __grid_constant__ RenderLaunch L)
-{
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int run = 0;
-        for (int k = 0; k <= L.S.nshaders; ++k) {
-            int c = L.counters[2 + k];
-            L.counters[2 + 64 + k] = run;
-            run += c;
-            L.counters[2 + k] = 0;
-        }
-    }
-}
-extern "C" __global__ void __launch_bounds__(256) rt_sort_scatter(const __grid_constant__ RenderLaunch L)
-{
-    const int n = L.counters[0];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        int key    = L.sort_keys[q];
-        int slot   = L.queue_in[q];
-        unsigned m = __match_any_sync(__activemask(), key);
-        int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-        if (lane == leader)
-            base = atomicAdd(L.counters + 2 + 64 + key, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        L.queue_out[base + __popc(m & ((1u << lane) - 1u))] = slot;
-    }
-}
-
-// shade one bounce: everything between two closest-hit queries of subpixel_radiance
-// returns whether the path continues (its record then holds the next ray)
-OSLD bool shade_slot(const RenderLaunch& L, int slot)
-{
+    extern __shared__ unsigned smem_[];
+    __shared__ int sh_hist[64];
     const RenderScene& S = L.S;
-    bool alive           = false;
-    {
-        {
-            float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-            const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4], q5 = rec[5], q6 = rec[6];
-            Ray r;
-            r.origin    = xyz(q0);
-            r.direction = xyz(q1);
-            r.radius    = q0.w;
-            r.spread    = q1.w;
-            r.roughness = q3.w;
-            r.raytype   = __float_as_int(q5.x);
-            const float ht = q4.x, hu = q4.y, hv = q4.z;
-            const int hid  = __float_as_int(q4.w);
-            const int b    = __float_as_int(q5.z);
-            V3 path_weight   = xyz(q2);
-            V3 path_radiance = xyz(q3);
-            float bsdf_pdf   = q2.w;
-            float out_rough  = q3.w;
-            u32 seed_now     = (u32)__float_as_int(q5.w);
-            do {
-                if (ht == OSLD_INF) {
-                    // miss: background (simpleraytracer.cpp:980-996)
-#ifdef OSLD_HAS_BACKGROUND
-                    if (S.background_shader >= 0) {
-                        if (b > 0 && S.bg_values) {
-                            float bg_pdf = 0;
-                            V3 bg        = bg_eval(S, r.direction, bg_pdf);
-                            path_radiance = path_radiance
-                                            + path_weight * bg * power_heuristic<WEIGHT_WEIGHT>(bsdf_pdf, bg_pdf);
+    unsigned* const stk  = smem_ + threadIdx.x;
+    const int stride     = blockDim.x;
+    const int nlive = L.counters[C_LIVE], n = nlive + L.counters[C_SHADOW];
+    if (threadIdx.x < 64)
+        sh_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    bool have = false, exhausted = false;
+    int q = 0, slot = 0, phase = 0, flags = 0, vis = 0;
+    Trav T;
+    for (;;) {
+        if (!exhausted) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (need) {
+                const int leader = __ffs(need) - 1;
+                int base = 0;
+                if (lane == leader)
+                    base = atomicAdd(L.counters + C_FETCH, __popc(need));
+                base      = __shfl_sync(0xffffffffu, base, leader);
+                exhausted = base + __popc(need) >= n;
+                if (!have) {
+                    q = base + __popc(need & ((1u << lane) - 1u));
+                    if (q < n) {
+                        have = true;
+                        if (q < nlive) {
+                            slot = L.queue_in[q];
+                            const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+                            const float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
+                            phase = 0;
+                            trav_init(S, T, stk, stride, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y),
+                                      ~0u, 0);
                         } else {
-                            path_radiance = path_radiance
-                                            + path_weight * eval_background(S, r.direction, mkv(0.0f), mkv(0.0f), b);
-                        }
-                    }
-#endif
-                    break;
-                }
-                SG sg;
-                ClosurePool pool;
-                globals_from_hit(S, sg, r, ht, hid, hu, hv);
-                if (S.show_globals) {
-                    V3 v = sg.Ng;
-                    if (S.show_globals == 2) v = sg.N;
-                    if (S.show_globals == 3) v = vnormalized(sg.dPdu);
-                    if (S.show_globals == 4) v = vnormalized(sg.dPdv);
-                    if (S.show_globals == 5) v = mkv(sg.u, sg.v, 0.0f);
-                    V3 c = v;
-                    if (S.show_globals != 5)
-                        c = c * 0.5f + mkv(0.5f);
-                    path_radiance = path_radiance + path_weight * c;
-                    break;
-                }
-                const float radius = r.radius + r.spread * ht;
-                const int shaderID = __ldg(S.shaderids + hid);
-                if (shaderID < 0)
-                    break;
-                pool.reset();
-                sg.pool = &pool;
-                sg.Ci   = 0;
-                osl_execute_shader(shaderID, sg);
-                V3 Le = mkv(0.0f);
-                CompositeBSDF bsdf;
-                bsdf.num               = 0;
-                const bool last_bounce = b == S.max_bounces;
-                process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness);
-                const int nlights = S.nlightprims;
-                float k           = 1;
-                if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {
-                    const float light_pick_pdf = 1.0f / nlights;
-                    float light_pdf            = light_pick_pdf * scene_shapepdf(S, hid, r.origin, sg.P);
-                    k                          = power_heuristic<WEIGHT_EVAL>(bsdf_pdf, light_pdf);
-                }
-                path_radiance = path_radiance + path_weight * k * Le;
-                if (last_bounce)
-                    break;
-                const V3 wo = -sg.I;
-                bsdf_prepare(bsdf, wo, path_weight, b >= S.rr_depth);
-                Sampler sampler;
-                sampler.seed  = seed_now;
-                sampler.index = (u32)__float_as_int(q6.x);
-                V3 s          = sampler.get();
-                seed_now      = sampler.seed;
-                const float xi = s.x, yi = s.y, zi = s.z;
-#ifdef OSLD_HAS_BACKGROUND
-                if (S.bg_values) {
-                    // one shadow ray towards an importance-sampled background direction
-                    V3 bg_dir;
-                    float bg_pdf = 0;
-                    V3 bg        = bg_sample(S, xi, yi, bg_dir, bg_pdf);
-                    BSample bs   = bsdf_eval(bsdf, wo, bg_dir);
-                    V3 contrib   = path_weight * bs.weight * bg * power_heuristic<WEIGHT_WEIGHT>(bg_pdf, bs.pdf);
-                    if ((contrib.x + contrib.y + contrib.z) > 0) {
-                        Hit sh = scene_intersect(S, sg.P, bg_dir, OSLD_INF, (unsigned)hid, ~0u);
-                        if (sh.t == OSLD_INF)
-                            path_radiance = path_radiance + contrib;
-                    }
-                }
-#endif
-                if (nlights > 0) {
-                    const float light_pick_pdf = 1.0f / nlights;
-                    float xl = xi * nlights;
-                    int ls   = (int)floorf(xl);
-                    xl -= ls;
-                    unsigned lid = __ldg(S.lightprims + ls);
-                    if (lid != (unsigned)hid) {
-                        LightSample sample = scene_sample(S, (int)lid, sg.P, xl, yi);
-                        BSample bs         = bsdf_eval(bsdf, wo, sample.dir);
-                        V3 contrib = path_weight * bs.weight
-                                     * power_heuristic<EVAL_WEIGHT>(light_pick_pdf * sample.pdf, bs.pdf);
-                        if ((contrib.x + contrib.y + contrib.z) > 0) {
-                            Hit sh = scene_intersect(S, sg.P, sample.dir, sample.dist, (unsigned)hid, lid);
-                            if (sh.t == sample.dist) {
-                                Ray shadow_ray;
-                                shadow_ray.origin    = sg.P;
-                                shadow_ray.direction = sample.dir;
-                                shadow_ray.radius    = radius;
-                                shadow_ray.spread = shadow_ray.roughness = 0.0f;
-                                shadow_ray.raytype = RAY_SHADOW;
-                                SG lsg;
-                                ClosurePool lpool;
-                                globals_from_hit(S, lsg, shadow_ray, sample.dist, (int)lid, sample.u, sample.v);
-                                lpool.reset();
-                                lsg.pool = &lpool;
-                                lsg.Ci   = 0;
-                                osl_execute_shader(__ldg(S.shaderids + lid), lsg);
-                                V3 lLe = mkv(0.0f);
-                                CompositeBSDF dummy;
-                                dummy.num = 0;
-                                process_closure(lpool, lsg.Ci, lLe, dummy, true);
-                                path_radiance = path_radiance + contrib * lLe;
+                            slot = L.queue_sh[q - nlive];
+                            const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+                            const float4* sh  = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+                            const float4 q0 = rec[0], s0 = sh[0];
+                            const unsigned hid = (unsigned)__float_as_int(rec[5].y);
+                            flags = __float_as_int(s0.w);
+                            vis   = 0;
+                            if (flags & SH_BG) {
+                                phase = 1;
+                                trav_init(S, T, stk, stride, xyz(q0), xyz(s0), OSLD_INF, hid, ~0u, 1);
+                            } else {
+                                const float4 s2 = sh[2];
+                                phase = 2;
+                                trav_init(S, T, stk, stride, xyz(q0), xyz(s2), s2.w, hid,
+                                          (unsigned)__float_as_int(sh[3].w), 1);
                             }
                         }
                     }
                 }
-                BSample p   = bsdf_sample(bsdf, wo, xi, yi, zi);
-                path_weight = path_weight * p.weight;
-                bsdf_pdf    = p.pdf;
-                if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
-                    break;
-                // continue the path
-                rec[0]    = mkf4(sg.P, radius);
-                rec[1]    = mkf4(p.wi, fmaxf(r.spread, p.roughness));
-                rec[2]    = mkf4(path_weight, bsdf_pdf);
-                rec[5]    = mki4(RAY_DIFFUSE, hid, b + 1, (int)seed_now);
-                out_rough = p.roughness;
-                alive     = true;
-            } while (false);
-            rec[3] = mkf4(path_radiance, out_rough);
+            }
+        }
+        if (!__any_sync(0xffffffffu, have))
+            break;
+        if (have && trav_run(S, T, OSLD_TRACE_CHUNK)) {
+            if (phase == 0) {
+                float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+                rec[4]      = make_float4(T.hit.t, T.hit.u, T.hit.v, __int_as_float((int)T.hit.id));
+                if (L.sort_keys) {
+                    const int key = (T.hit.t == OSLD_INF) ? 0 : __ldg(L.shader_key + __ldg(S.shaderids + T.hit.id));
+                    L.sort_keys[q] = key;
+                    atomicAdd(&sh_hist[key], 1);
+                }
+                have = false;
+            } else {
+                float4* sh = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+                if (phase == 1) {
+                    vis |= (T.hit.t == OSLD_INF) ? 1 : 0;
+                    if (flags & SH_LIGHT) {
+                        // second shadow ray of the slot: towards the sampled light point
+                        const float4 s2 = sh[2];
+                        const V3 org    = T.org;
+                        const unsigned hid = T.skip1;
+                        phase = 2;
+                        trav_init(S, T, stk, stride, org, xyz(s2), s2.w, hid, (unsigned)__float_as_int(sh[3].w), 1);
+                    } else
+                        have = false;
+                } else {
+                    vis |= (T.hit.t == T.tmax0) ? 2 : 0;
+                    have = false;
+                }
+                if (!have)
+                    reinterpret_cast<int*>(sh + 1)[3] = vis;
+            }
         }
     }
-    return alive;
+    if (L.sort_keys) {
+        __syncthreads();
+        if (threadIdx.x < 64 && sh_hist[threadIdx.x])
+            atomicAdd(L.counters + C_HIST + threadIdx.x, sh_hist[threadIdx.x]);
+    }
 }
 
-extern "C" __global__ void __launch_bounds__(128) rt_shade(const __grid_constant__ RenderLaunch L)
+// Counting sort of the live queue by bucket (0 = miss, else the material's closure-signature
+// rank); the histogram comes from rt_trace.  Stable order is not required: paths are independent.
+extern "C" __global__ void __launch_bounds__(256) rt_sort_scatter(const __grid_constant__ RenderLaunch L)
 {
-    const int n = L.counters[0];
+    __shared__ int sh_prefix[64], sh_cnt[64], sh_base[64];
+    const int n = L.counters[C_LIVE];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 64) {
+        // exclusive prefix of the 64 bucket counts (two warps, shuffle scan)
+        int c = L.counters[C_HIST + tid], v = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d)
+                v += o;
+        }
+        sh_cnt[tid] = v;  // inclusive, per warp
+        __syncwarp();
+        sh_prefix[tid] = v - c;
+    }
+    __syncthreads();
+    if (tid >= 32 && tid < 64)
+        sh_prefix[tid] += sh_cnt[31];
+    __syncthreads();
+    for (int tile = blockIdx.x; tile * 256 < n; tile += gridDim.x) {
+        if (tid < 64)
+            sh_cnt[tid] = 0;
+        __syncthreads();
+        const int q   = tile * 256 + tid;
+        const int key = q < n ? L.sort_keys[q] : 63;
+        const int slot = q < n ? L.queue_in[q] : 0;
+        const unsigned m = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(m) - 1;
+        int r = 0;
+        if (lane == leader)
+            r = atomicAdd(&sh_cnt[key], __popc(m));
+        r = __shfl_sync(0xffffffffu, r, leader) + __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (tid < 63 && sh_cnt[tid])
+            sh_base[tid] = atomicAdd(L.counters + C_CURSOR + tid, sh_cnt[tid]);
+        __syncthreads();
+        if (q < n)
+            L.queue_out[sh_prefix[key] + sh_base[key] + r] = slot;
+        __syncthreads();
+    }
+}
+
+// ---- rt_shade ------------------------------------------------------------------------------------
+// One bounce of subpixel_radiance (simpleraytracer.cpp:975-1189) between two closest-hit
+// queries, minus the two NEE shadow-ray walks: their rays are written to the slot's shadow
+// record and traced with everything else by the next rt_trace.
+// Returns bit 0: the path continues (its record holds the next ray); bit 1: shadow rays pending.
+OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
+{
+    const RenderScene& S = L.S;
+    bool alive           = false;
+    int shflags          = 0;
+    float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+    float4* sh  = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2], q3 = rec[3], q4 = rec[4], q5 = rec[5], q6 = rec[6];
+    Ray r;
+    r.origin    = xyz(q0);
+    r.direction = xyz(q1);
+    r.radius    = q0.w;
+    r.spread    = q1.w;
+    r.roughness = q3.w;
+    r.raytype   = __float_as_int(q5.x);
+    const float ht = q4.x, hu = q4.y, hv = q4.z;
+    const int hid  = __float_as_int(q4.w);
+    const int b    = __float_as_int(q5.z);
+    V3 path_weight   = xyz(q2);
+    V3 path_radiance = xyz(q3);
+    float bsdf_pdf   = q2.w;
+    float out_rough  = q3.w;
+    u32 seed_now     = (u32)__float_as_int(q5.w);
+    V3 bg_dir        = mkv(0.0f);
+    do {
+        if (ht == OSLD_INF) {
+            // miss: background (simpleraytracer.cpp:980-996)
+#ifdef OSLD_HAS_BACKGROUND
+            if (S.background_shader >= 0) {
+                if (b > 0 && S.bg_values) {
+                    float bg_pdf = 0;
+                    V3 bg        = bg_eval(S, r.direction, bg_pdf);
+                    path_radiance = path_radiance + path_weight * bg * power_heuristic<WEIGHT_WEIGHT>(bsdf_pdf, bg_pdf);
+                } else {
+                    path_radiance = path_radiance
+                                    + path_weight * eval_background(S, r.direction, mkv(0.0f), mkv(0.0f), b, pool);
+                }
+            }
+#endif
+            break;
+        }
+        SG sg;
+        globals_from_hit(S, sg, r, ht, hid, hu, hv);
+        if (S.show_globals) {
+            V3 v = sg.Ng;
+            if (S.show_globals == 2) v = sg.N;
+            if (S.show_globals == 3) v = vnormalized(sg.dPdu);
+            if (S.show_globals == 4) v = vnormalized(sg.dPdv);
+            if (S.show_globals == 5) v = mkv(sg.u, sg.v, 0.0f);
+            V3 c = v;
+            if (S.show_globals != 5)
+                c = c * 0.5f + mkv(0.5f);
+            path_radiance = path_radiance + path_weight * c;
+            break;
+        }
+        const float radius = r.radius + r.spread * ht;
+        const int shaderID = __ldg(S.shaderids + hid);
+        if (shaderID < 0)
+            break;
+        pool.reset();
+        sg.pool = &pool;
+        sg.Ci   = 0;
+        osl_execute_shader(shaderID, sg);
+        V3 Le = mkv(0.0f);
+        CompositeBSDF bsdf;
+        bsdf.num               = 0;
+        const bool last_bounce = b == S.max_bounces;
+        process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness);
+        const int nlights = S.nlightprims;
+        float k           = 1;
+        if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {
+            const float light_pick_pdf = 1.0f / nlights;
+            float light_pdf            = light_pick_pdf * scene_shapepdf(S, hid, r.origin, sg.P);
+            k                          = power_heuristic<WEIGHT_EVAL>(bsdf_pdf, light_pdf);
+        }
+        path_radiance = path_radiance + path_weight * k * Le;
+        if (last_bounce)
+            break;
+        const V3 wo = -sg.I;
+        bsdf_prepare(bsdf, wo, path_weight, b >= S.rr_depth);
+        Sampler sampler;
+        sampler.seed  = seed_now;
+        sampler.index = (u32)__float_as_int(q6.x);
+        V3 s          = sampler.get();
+        seed_now      = sampler.seed;
+        const float xi = s.x, yi = s.y, zi = s.z;
+#ifdef OSLD_HAS_BACKGROUND
+        if (S.bg_values) {
+            // one shadow ray towards an importance-sampled background direction
+            float bg_pdf = 0;
+            V3 bg        = bg_sample(S, xi, yi, bg_dir, bg_pdf);
+            BSample bs   = bsdf_eval(bsdf, wo, bg_dir);
+            V3 contrib   = path_weight * bs.weight * bg * power_heuristic<WEIGHT_WEIGHT>(bg_pdf, bs.pdf);
+            if ((contrib.x + contrib.y + contrib.z) > 0) {
+                sh[1] = mkf4(contrib, 0.0f);
+                shflags |= SH_BG;
+            }
+        }
+#endif
+        if (nlights > 0) {
+            const float light_pick_pdf = 1.0f / nlights;
+            float xl = xi * nlights;
+            int ls   = (int)floorf(xl);
+            xl -= ls;
+            unsigned lid = __ldg(S.lightprims + ls);
+            if (lid != (unsigned)hid) {
+                LightSample sample = scene_sample(S, (int)lid, sg.P, xl, yi);
+                BSample bs         = bsdf_eval(bsdf, wo, sample.dir);
+                V3 contrib = path_weight * bs.weight * power_heuristic<EVAL_WEIGHT>(light_pick_pdf * sample.pdf, bs.pdf);
+                if ((contrib.x + contrib.y + contrib.z) > 0) {
+                    sh[2]  = mkf4(sample.dir, sample.dist);
+                    sh[3]  = mkf4(contrib, __int_as_float((int)lid));
+                    rec[7] = make_float4(sample.u, sample.v, 0.0f, 0.0f);
+                    shflags |= SH_LIGHT;
+                }
+            }
+        }
+        BSample p   = bsdf_sample(bsdf, wo, xi, yi, zi);
+        path_weight = path_weight * p.weight;
+        bsdf_pdf    = p.pdf;
+        // the shadow rays start at P and skip this primitive, whether or not the path goes on
+        rec[0] = mkf4(sg.P, radius);
+        rec[5] = mki4(RAY_DIFFUSE, hid, b + 1, (int)seed_now);
+        if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
+            break;
+        // continue the path
+        rec[1]    = mkf4(p.wi, fmaxf(r.spread, p.roughness));
+        rec[2]    = mkf4(path_weight, bsdf_pdf);
+        out_rough = p.roughness;
+        alive     = true;
+    } while (false);
+    rec[3] = mkf4(path_radiance, out_rough);
+    if (shflags)
+        sh[0] = mkf4(bg_dir, __int_as_float(shflags | (alive ? 0 : SH_DEAD)));
+    return (alive ? 1 : 0) | (shflags ? 2 : 0);
+}
+
+// NEE of the previous bounce, after rt_trace has answered the visibility of its shadow rays
+// (simpleraytracer.cpp:1083-1161): unoccluded background sample adds its contribution, an
+// unoccluded light sample runs the light's shader for its emission.  Returns whether the
+// path ended at that bounce.
+OSLD bool light_path(const RenderLaunch& L, int slot, ClosurePool& pool)
+{
+    const RenderScene& S = L.S;
+    float4* rec      = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+    const float4* sh = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+    const float4 s0 = sh[0], s1 = sh[1], q3 = rec[3];
+    const int flags = __float_as_int(s0.w), vis = __float_as_int(s1.w);
+    V3 rad          = xyz(q3);
+    if ((flags & SH_BG) && (vis & 1))
+        rad = rad + xyz(s1);
+    if ((flags & SH_LIGHT) && (vis & 2)) {
+        const float4 s2 = sh[2], s3 = sh[3], q0 = rec[0], q7 = rec[7];
+        const int lid = __float_as_int(s3.w);
+        Ray shadow_ray;
+        shadow_ray.origin    = xyz(q0);
+        shadow_ray.direction = xyz(s2);
+        shadow_ray.radius    = q0.w;
+        shadow_ray.spread = shadow_ray.roughness = 0.0f;
+        shadow_ray.raytype = RAY_SHADOW;
+        SG lsg;
+        globals_from_hit(S, lsg, shadow_ray, s2.w, lid, q7.x, q7.y);
+        pool.reset();
+        lsg.pool = &pool;
+        lsg.Ci   = 0;
+        osl_execute_shader(__ldg(S.shaderids + lid), lsg);
+        V3 lLe = mkv(0.0f);
+        CompositeBSDF dummy;
+        dummy.num = 0;
+        process_closure(pool, lsg.Ci, lLe, dummy, true);
+        rad = rad + xyz(s3) * lLe;
+    }
+    rec[3] = mkf4(rad, q3.w);
+    return (flags & SH_DEAD) != 0;
+}
+
+#define OSLD_SHADE_BLOCK 128
+extern "C" __global__ void __launch_bounds__(OSLD_SHADE_BLOCK) rt_shade(const __grid_constant__ RenderLaunch L)
+{
+    extern __shared__ unsigned smem_[];
+    OSLD_POOL_DECL(pool, smem_);
+    const int n = L.counters[C_LIVE];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31) & ~31); q += gridDim.x * blockDim.x) {
-        bool alive = false;
+        int fl = 0, slot = 0;
+        if (q < n) {
+            slot = L.queue_in[q];
+            fl   = shade_path(L, slot, pool);
+        }
+        bool alive = (fl & 1) != 0;
+        const bool pending = (fl & 2) != 0, ended = q < n && fl == 0;
+        if (ended)
+            path_finish(L, slot);
+        if (path_regen(L, slot, ended))
+            alive = true;
+        queue_push(L.queue_out, L.counters + C_OUT, slot, alive);
+        queue_push(L.queue_sh, L.counters + C_SHADOW_OUT, slot, pending);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(OSLD_SHADE_BLOCK) rt_light(const __grid_constant__ RenderLaunch L)
+{
+    extern __shared__ unsigned smem_[];
+    OSLD_POOL_DECL(pool, smem_);
+    const int n = L.counters[C_SHADOW];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ((n + 31) & ~31); q += gridDim.x * blockDim.x) {
+        bool ended = false;
         int slot   = 0;
         if (q < n) {
-            slot  = L.queue_in[q];
-            alive = shade_slot(L, slot);
+            slot  = L.queue_sh[q];
+            ended = light_path(L, slot, pool);
+            if (ended)
+                path_finish(L, slot);
         }
-        queue_push(L.queue_out, L.counters + 1, slot, alive);
+        const bool alive = path_regen(L, slot, ended);
+        queue_push(L.queue_out, L.counters + C_OUT, slot, alive);
     }
 }
 
-// The tail of a batch: once only a few paths are left (glass interiors keep a handful alive
-// for tens of thousands of bounces) a bounce costs six launches for almost no work.  Each
-// remaining path is then run to its end by one thread, one warp per CTA so that the paths
-// spread over the SMs.  Same per-path arithmetic as the staged kernels, hence same pixels.
+// end of a step: the out queue becomes the in queue (the host rotates the pointers), the
+// shadow entries shade appended become the next step's, and the host's copy of the loop
+// state is refreshed (mapped pinned memory: the host polls it instead of synchronising)
+extern "C" __global__ void __launch_bounds__(128) rt_swap(const __grid_constant__ RenderLaunch L)
+{
+    if (blockIdx.x != 0)
+        return;
+    L.counters[C_HIST + threadIdx.x] = 0;  // histogram + cursors
+    if (threadIdx.x == 0) {
+        const int live = L.counters[C_OUT], shadow = L.counters[C_SHADOW_OUT];
+        L.counters[C_LIVE]       = live;
+        L.counters[C_OUT]        = 0;
+        L.counters[C_SHADOW]     = shadow;
+        L.counters[C_SHADOW_OUT] = 0;
+        L.counters[C_FETCH]      = 0;
+        const int it             = L.counters[C_ITER] + 1;
+        L.counters[C_ITER]       = it;
+        if (L.host_state) {
+            L.host_state[1] = live;
+            L.host_state[2] = shadow;
+            L.host_state[3] = L.counters[C_NEXT];
+            __threadfence_system();
+            L.host_state[0] = it;
+        }
+    }
+}
+
+// The end of a work set: once no sample is left to start and only a few paths are alive (glass
+// interiors keep a handful going for 10^4..10^5 bounces) a step costs five launches for almost
+// no work.  Each remaining path is then run to its end by one thread, one path per warp (paths
+// of very different lengths sharing a warp would serialise each other's bounces).  Same
+// per-path arithmetic as the staged kernels, hence the same pixels.  Expects the closest hit of
+// every queued path in its record and no pending shadow entries (the host runs rt_trace +
+// rt_light first).
 extern "C" __global__ void __launch_bounds__(32) rt_tail(const __grid_constant__ RenderLaunch L)
 {
-    // one path per WARP (lane 0): paths of very different lengths sharing a warp would
-    // serialise each other's bounces; <= 2048 paths fit the GPU's warp slots many times over
+    extern __shared__ unsigned smem_[];
     if (threadIdx.x != 0)
         return;
-    const int n = L.counters[0];
+    const RenderScene& S = L.S;
+    unsigned* const stk  = smem_;
+    OSLD_POOL_DECL(pool, smem_ + OSLD_STK_WORDS * OSLD_BVH_STACK * 32);
+    const int n = L.counters[C_LIVE];
     for (int q = blockIdx.x; q < n; q += gridDim.x) {
         const int slot = L.queue_in[q];
-        bool alive     = true;
-        while (alive) {
-            intersect_slot(L, slot);
-            __threadfence_block();
-            alive = shade_slot(L, slot);
+        float4* rec    = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+        float4* sh     = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+        for (;;) {
+            const int fl = shade_path(L, slot, pool);
+            if (fl & 2) {
+                const float4 q0 = rec[0], s0 = sh[0];
+                const unsigned hid = (unsigned)__float_as_int(rec[5].y);
+                const int flags    = __float_as_int(s0.w);
+                int vis            = 0;
+                if (flags & SH_BG)
+                    vis |= scene_intersect(S, stk, 32, xyz(q0), xyz(s0), OSLD_INF, hid, ~0u, 1).t == OSLD_INF ? 1 : 0;
+                if (flags & SH_LIGHT) {
+                    const float4 s2 = sh[2];
+                    vis |= scene_intersect(S, stk, 32, xyz(q0), xyz(s2), s2.w, hid, (unsigned)__float_as_int(sh[3].w), 1).t
+                                   == s2.w ? 2 : 0;
+                }
+                reinterpret_cast<int*>(sh + 1)[3] = vis;
+                light_path(L, slot, pool);
+            }
+            if (!(fl & 1)) {
+                path_finish(L, slot);
+                break;
+            }
+            const float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
+            const Hit h = scene_intersect(S, stk, 32, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y), ~0u);
+            rec[4]      = make_float4(h.t, h.u, h.v, __int_as_float((int)h.id));
         }
     }
 }
 
-// end of a bounce: the out queue becomes the in queue (host swaps the pointers)
-extern "C" __global__ void rt_swap(const __grid_constant__ RenderLaunch L)
-{
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        L.counters[0] = L.counters[1];
-        L.counters[1] = 0;
-    }
-}
-
-// fold the finished batch into the running image in the reference's order:
-// result = lerp(result, r, 1/(si+1))  for si = s0 .. s0+nsamples-1
+// fold the round's samples into the running image in the reference's order:
+// result = lerp(result, r, 1/(si+1))  for si = s0 .. s0+nsamples-1  (simpleraytracer.cpp:1211-1213)
 extern "C" __global__ void __launch_bounds__(256) rt_resolve(const __grid_constant__ RenderLaunch L)
 {
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < L.npix; pix += gridDim.x * blockDim.x) {
         V3 result = L.s0 == 0 ? mkv(0.0f) : mkv(L.accum[3 * pix], L.accum[3 * pix + 1], L.accum[3 * pix + 2]);
         for (int sb = 0; sb < L.nsamples; ++sb) {
-            int slot = sb * L.npix + pix;
-            V3 r     = xyz(L.rec[(size_t)slot * OSLD_PATH_QUADS + 3]);
+            const float* rp = L.result + 3 * ((size_t)sb * L.npix + pix);
+            V3 r     = mkv(rp[0], rp[1], rp[2]);
             float t  = 1.0f / (float)(L.s0 + sb + 1);
             result   = result * (1.0f - t) + r * t;
         }

@@ -131,7 +131,7 @@ public:
 private:
     Group& g;
     std::ostringstream o;
-    int ind = 0, label = 0;
+    int ind = 0, label = 0, loop_depth = 0;
     Layer* L = nullptr;
     int li   = 0;
     std::set<int> ensured;
@@ -413,6 +413,7 @@ Gen::emit_block(int b, int e, const Ctx* ctx)
             std::string cond    = R(op.args[0]);
             w("for (;;) {");
             ++ind;
+            ++loop_depth;
             if (n == "dowhile") {
                 emit_block(bl, il, &c2);
                 w(c2.cont + ":;");
@@ -426,6 +427,7 @@ Gen::emit_block(int b, int e, const Ctx* ctx)
                 w(c2.cont + ":;");
                 emit_block(il, dl, &c2);
             }
+            --loop_depth;
             --ind;
             w("}");
             w(c2.brk + ":;");
@@ -481,7 +483,10 @@ Gen::op_percomp(const Opcode& op)
             unsupported("closure op '" + op.name + "'");
         uses_closures = true;
         int a = op.args[1], b = op.args[2];
+        g.closure_in_loop |= loop_depth > 0;
         if (op.name == "add") {
+            g.pool_words_bound += 3;
+            g.closure_adds += 1;
             w(R(op.args[0]) + " = clos_add(*sg.pool, " + R(a) + ", " + R(b) + ");");
             return;
         }
@@ -494,6 +499,7 @@ Gen::op_percomp(const Opcode& op)
             wt = "nd(" + wt + ")";
         if (S(b).type.base == Base::Int)
             wt = "(float)" + wt;
+        g.pool_words_bound += 5;
         w(R(op.args[0]) + " = clos_mul(*sg.pool, " + R(a) + ", " + wt + ");");
         return;
     }
@@ -1265,6 +1271,13 @@ Gen::emit_op(const Opcode& op)
         const int key_base = nwords;
         nwords += (int)keys.size();
         const std::string cn = cname;
+        g.closure_in_loop |= loop_depth > 0;
+        g.pool_words_bound += 4 + nwords;
+        g.closure_names.insert(cname);
+        if (cn == "layer")
+            g.closure_adds += 1;
+        else if (cn != "emission" && cn != "background" && cn != "uniform_edf")
+            g.lobe_bound += 1;
         if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
             || cn == "burley_diffuse_bsdf" || cn == "sheen_bsdf" || cn == "layer")
             g.uses_glossy_lobes = true;
@@ -1519,7 +1532,10 @@ Gen::run()
     // layer bodies first (they record which globals are read)
     journal_ok = g.journal_enabled;
     g.textures.clear();
-    g.texture_base = 0;
+    g.texture_base     = 0;
+    g.pool_words_bound = 1;
+    g.lobe_bound = g.closure_adds = 0;
+    g.closure_in_loop             = false;
     std::ostringstream bodies;
     std::string gd = "struct GD {\n    unsigned ran;\n";
     for (int l = 0; l < nlayers; ++l) {
@@ -1622,7 +1638,8 @@ Gen::run()
     out << "// generated by libosl_b200 for shader group '" << g.name << "'\n";
     out << "#include \"osl_b200_device.cuh\"\n";
     if (uses_closures)
-        out << "#include \"osl_b200_closure.cuh\"\n";
+        out << "#define OSLD_POOL_WORDS " << (g.closure_in_loop ? 256 : std::min(256, std::max(2, g.pool_words_bound)))
+            << "\n#include \"osl_b200_closure.cuh\"\n";
     if (!g.textures.empty())
         out << "#include \"osl_b200_texture.cuh\"\nextern \"C\" __device__ osld::TexDesc osl_tex_[" << g.textures.size()
             << "];\n";
@@ -1675,7 +1692,8 @@ Gen::run()
     emit_fetch("tile_ + gridDim.x");
     out << "        GD gd;\n        gd.ran = 0u;\n";
     if (uses_closures)
-        out << "        ClosurePool pool_;\n        pool_.reset();\n        sg.pool = &pool_;\n        sg.Ci = 0;\n";
+        out << "        float pool_store_[OSLD_POOL_WORDS];\n        ClosurePool pool_;\n        pool_.bind(pool_store_, 1);\n"
+               "        pool_.reset();\n        sg.pool = &pool_;\n        sg.Ci = 0;\n";
     out << "        if (active_) {\n";
     out << "            layer_" << (nlayers - 1) << "(sg, gd, L);\n";
     out << "        }\n";
@@ -1778,21 +1796,46 @@ generate_cuda(Group& g)
 
 // All material groups of a scene + the wavefront integrator in one module.
 std::string
-generate_cuda_render(std::vector<Group*>& groups, bool has_background)
+generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderModuleInfo* info)
 {
+    std::string mats;
+    bool color = false, glossy = false, in_loop = false;
+    int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
+    int pool_words = 2, lobes = 1, adds = 0;
+    for (size_t k = 0; k < groups.size(); ++k) {
+        Group& g       = *groups[k];
+        g.texture_base = ntex;
+        g.textures.clear();
+        g.pool_words_bound = 1;
+        g.lobe_bound = g.closure_adds = 0;
+        g.closure_in_loop             = false;
+        g.closure_names.clear();
+        mats += Gen(g).run_material("mat" + std::to_string(k));
+        color |= g.uses_colorsystem;
+        glossy |= g.uses_glossy_lobes;
+        in_loop |= g.closure_in_loop;
+        pool_words = std::max(pool_words, g.pool_words_bound);
+        lobes      = std::max(lobes, g.lobe_bound);
+        adds       = std::max(adds, g.closure_adds);
+        ntex += (int)g.textures.size();
+    }
+    // the integrator's per-thread closure arena, lobe array and tree-walk stack are sized from
+    // what the scene's materials can build, capped at the reference's own limits (1 KB pool,
+    // 8 lobes, 16-deep stack: render_state.h:27, shading.h:319, shading.cpp:1456)
+    RenderModuleInfo mi;
+    mi.pool_words    = in_loop ? 256 : std::min(256, pool_words);
+    mi.max_lobes     = in_loop ? 8 : std::min(8, lobes);
+    mi.closure_stack = in_loop ? 16 : std::min(16, adds + 1);
+    mi.pool_in_smem  = mi.pool_words <= 64;
+    if (info)
+        *info = mi;
     std::ostringstream out;
     out << "// generated by libosl_b200: render module with " << groups.size() << " material group(s)\n";
+    out << "#define OSLD_POOL_WORDS " << mi.pool_words << "\n#define OSLD_MAX_LOBES " << mi.max_lobes
+        << "\n#define OSLD_CLOSURE_STACK " << mi.closure_stack << "\n";
+    if (mi.pool_in_smem)
+        out << "#define OSLD_POOL_SMEM 1\n";
     out << "#include \"osl_b200_device.cuh\"\n#include \"osl_b200_closure.cuh\"\n#include \"osl_b200_sg.cuh\"\n";
-    std::string mats;
-    bool color = false;
-    int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
-    for (size_t k = 0; k < groups.size(); ++k) {
-        groups[k]->texture_base = ntex;
-        groups[k]->textures.clear();
-        mats += Gen(*groups[k]).run_material("mat" + std::to_string(k));
-        color |= groups[k]->uses_colorsystem;
-        ntex += (int)groups[k]->textures.size();
-    }
     if (ntex)
         out << "#include \"osl_b200_texture.cuh\"\nextern \"C\" __device__ osld::TexDesc osl_tex_[" << ntex << "];\n";
     if (color)  // one colour system per module: the shading system's, i.e. the first group's
@@ -1803,9 +1846,6 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background)
         out << "    case " << k << ": mat" << k << "::entry(sg); break;\n";
     out << "    default: break;\n    }\n}\n";
     // the integrator is specialised to the lobes the scene's materials can create
-    bool glossy = false;
-    for (Group* gp : groups)
-        glossy |= gp->uses_glossy_lobes;
     if (glossy)
         out << "#define OSLD_GLOSSY_LOBES 1\n";
     if (has_background)

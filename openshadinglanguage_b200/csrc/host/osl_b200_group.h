@@ -148,6 +148,14 @@ struct Group {
     std::string commonspace_synonym = "world"; // ShadingSystem attribute "commonspace"
     std::vector<std::string> textures;         // constant texture() file names (module table slots)
     int texture_base = 0;                      // first slot of this group in a multi-group module
+    // Static bounds of one execution's closure arena, set by codegen from the group's closure ops
+    // (a layer runs at most once per execution).  closure_in_loop: a closure op sits inside a loop,
+    // the bounds do not hold and the integrator keeps the reference's 1 KB pool / 8 lobes.
+    int pool_words_bound = 1;                  // word 0 is reserved
+    int lobe_bound       = 0;                  // BSDF components that can reach the CompositeBSDF
+    int closure_adds     = 0;                  // add / layer nodes: bounds the tree-walk stack
+    bool closure_in_loop = false;
+    std::set<std::string> closure_names;       // closures the group can emit: its closure-type signature
     std::string texturepath;                   // ':'-separated directories searched for texture files
 
     int layer_index(const std::string& n) const;
@@ -171,6 +179,14 @@ std::string generate_cuda(Group& g);
 // Emit one CUDA module holding every material group of a scene (namespaces
 // mat0, mat1, ...), the shader dispatch switch and the wavefront integrator
 // kernels of csrc/device/osl_b200_render.cuh.
-std::string generate_cuda_render(std::vector<Group*>& groups, bool has_background = false);
+// what the render module was specialised to (the host sizes shared memory from it)
+struct RenderModuleInfo {
+    int pool_words    = 256;    // OSLD_POOL_WORDS: per-thread closure arena
+    int max_lobes     = 8;      // OSLD_MAX_LOBES
+    int closure_stack = 16;     // OSLD_CLOSURE_STACK
+    bool pool_in_smem = false;  // OSLD_POOL_SMEM: arena staged in shared memory
+};
+std::string generate_cuda_render(std::vector<Group*>& groups, bool has_background = false,
+                                 RenderModuleInfo* info = nullptr);
 
 }  // namespace oslb200

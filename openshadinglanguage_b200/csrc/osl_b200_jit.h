@@ -31,6 +31,9 @@ struct Driver {
                                 void*, void**, void**)                     = nullptr;
     CUresult_ (*cuGetErrorString)(CUresult_, const char**)                 = nullptr;
     CUresult_ (*cuModuleGetGlobal)(unsigned long long*, size_t*, CUmodule_, const char*) = nullptr;
+    CUresult_ (*cuFuncSetAttribute)(CUfunction_, int, int)                 = nullptr;
+    CUresult_ (*cuFuncGetAttribute)(int*, int, CUfunction_)                = nullptr;
+    CUresult_ (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction_, int, size_t) = nullptr;
     bool ok = false;
     std::string why;
     std::string err(CUresult_ r) const
@@ -69,6 +72,9 @@ jit_driver()
         OSLB200_SYM(cuModuleGetFunction)
         OSLB200_SYM(cuLaunchKernel)
         OSLB200_SYM(cuGetErrorString)
+        OSLB200_SYM(cuFuncSetAttribute)
+        OSLB200_SYM(cuFuncGetAttribute)
+        OSLB200_SYM(cuOccupancyMaxActiveBlocksPerMultiprocessor)
         *(void**)(&d.cuModuleGetGlobal) = dlsym(d.lib, "cuModuleGetGlobal_v2");
         if (!d.cuModuleGetGlobal) {
             d.why = "libcuda is missing symbol cuModuleGetGlobal_v2";

@@ -10,6 +10,7 @@
 #include "host/osl_b200_group.h"
 #include "osl_b200_jit.h"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -59,25 +60,34 @@ struct DevScene {
     float bg_invres, bg_invjacobian;
     const void* leaf_tris;
 };
-enum { PATH_QUADS = 8 };  // 8 x float4 = 128 B of state per path (OSLD_PATH_QUADS)
+enum { PATH_QUADS = 8, SHADOW_QUADS = 4 };  // 128 B of path state + 64 B of pending shadow rays per slot
+// device loop state (osld::C_*)
+enum { C_LIVE = 0, C_OUT, C_SHADOW, C_SHADOW_OUT, C_NEXT, C_FETCH, C_ITER, C_FINISHED, C_WORDS = 8 + 128 };
 struct DevLaunch {
     DevScene S;
     void* rec;
+    void* shrec;
     int* queue_in;
     int* queue_out;
+    int* queue_sh;
     int* counters;
     int* sort_keys;
-    int nslots, npix, y0, s0, nsamples;
+    const int* shader_key;
+    const int* pixmap;
+    volatile int* host_state;
+    int nslots, npix, s0, nsamples, total;
+    float* result;
     float* accum;
 };
 
-const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_intersect", "rt_sort_count", "rt_sort_scan",
-                          "rt_sort_scatter", "rt_shade", "rt_swap", "rt_resolve", "rt_tail",
+const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_trace", "rt_light", "rt_sort_scatter", "rt_shade",
+                          "rt_swap", "rt_resolve", "rt_tail",
                           // only in modules generated for a scene with a background
                           "rt_bg_eval", "rt_bg_rows", "rt_bg_finish", "rt_bg_scale" };
-enum { K_CAMERA, K_GENERATE, K_INTERSECT, K_SORT_COUNT, K_SORT_SCAN, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE,
-       K_TAIL, K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE, K_N };
+enum { K_CAMERA, K_GENERATE, K_TRACE, K_LIGHT, K_SORT_SCATTER, K_SHADE, K_SWAP, K_RESOLVE, K_TAIL,
+       K_BG_EVAL, K_BG_ROWS, K_BG_FINISH, K_BG_SCALE, K_N };
 enum { K_FIRST_BG = K_BG_EVAL };
+enum { TRACE_BLOCK = 128, SHADE_BLOCK = 128 };  // OSLD_TRACE_BLOCK / OSLD_SHADE_BLOCK
 
 }  // namespace
 
@@ -87,25 +97,36 @@ struct b200_render {
     std::vector<char> cubin;
     b200_render_scene host;  // host-pointer copy of the description
     bool fma = true, sort = true;
-    long long slots_target = 0;         // option slots=N; 0 = sized from the free device memory
+    long long slots_target = 0;         // option slots=N: path slots in the pool (0 = default)
     long long tail_paths   = 2048;      // option tail=N: at most N live paths -> rt_tail (0 = never)
     std::vector<std::string> textures;  // the module's texture table, in slot order
     std::string texturepath;            // option texturepath=dir[:dir...]
+    RenderModuleInfo info;              // what the module was specialised to
+    int bvh_stack = 64, stk_words = 3;  // OSLD_BVH_STACK, OSLD_STK_WORDS
+    std::vector<int> shader_key;        // sort bucket per material
     // per-device state
     struct Dev {
         CUmodule_ mod = nullptr;
         CUfunction_ fn[K_N];
+        int resident[K_N];  // CTAs per SM at the launch configuration used
         DevScene S;
         std::vector<void*> allocs;
         int sms = 148;
-        // path state
+        const int* shader_key = nullptr;
+        // path pool
         long long nslots_cap = 0;
         void* rec            = nullptr;  // nslots x 128 B path records
-        int* queues          = nullptr;  // 3 x nslots
+        void* shrec          = nullptr;  // nslots x 64 B shadow records
+        int* queues          = nullptr;  // 4 x nslots
         int* sort_keys       = nullptr;
         int* counters        = nullptr;
+        volatile int* host_state = nullptr;  // mapped pinned: {iter, live, shadow, next}
+        // work set
         float* accum         = nullptr;
-        long long accum_cap  = 0;
+        int* pixmap          = nullptr;
+        long long pix_cap    = 0;
+        float* result        = nullptr;
+        long long result_cap = 0;  // samples
     };
     std::map<int, Dev> devs;
 };
@@ -183,7 +204,56 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
             gs.push_back(g.get());
             R->groups.push_back(std::move(g));
         }
-        R->source = generate_cuda_render(gs, scene->background_shader >= 0);
+        std::string body = generate_cuda_render(gs, scene->background_shader >= 0, &R->info);
+        // Traversal stack: sized from the depth of THIS scene's BVH (a walk holds at most one
+        // pending sibling per level plus the node in hand) instead of the reference's fixed 64
+        // entries, so that the stacks of a CTA fit its shared memory; an entry packs
+        // (child, nprims) into one word when every node allows it.
+        int depth = 1;
+        bool packable = true;
+        if (scene->nnodes > 0 && scene->bvh_nodes) {
+            std::vector<std::pair<unsigned, int>> st;
+            st.push_back({ 0u, 1 });
+            while (!st.empty()) {
+                auto [node, d] = st.back();
+                st.pop_back();
+                if (node >= (unsigned)scene->nnodes)
+                    throw std::runtime_error("b200_render_create: BVH child index out of range");
+                depth = std::max(depth, d);
+                unsigned child, nprims;
+                memcpy(&child, scene->bvh_nodes + 8 * (size_t)node + 6, 4);
+                memcpy(&nprims, scene->bvh_nodes + 8 * (size_t)node + 7, 4);
+                packable &= child < (1u << 26) && nprims < 64u;
+                if (!nprims) {
+                    if (d > 4096)
+                        throw std::runtime_error("b200_render_create: BVH is not a tree");
+                    st.push_back({ child, d + 1 });
+                    st.push_back({ child + 1, d + 1 });
+                }
+            }
+        }
+        R->bvh_stack = depth + 2;
+        R->stk_words = packable ? 2 : 3;
+        std::ostringstream pre;
+        pre << "#define OSLD_BVH_STACK " << R->bvh_stack << "\n";
+        if (!packable)
+            pre << "#define OSLD_BVH_UNPACKED 1\n";
+        R->source = pre.str() + body;
+        // Sort buckets: materials that emit the same set of closures (their closure-type
+        // signature) are neighbours in the sorted wavefront; within a signature, by material.
+        {
+            std::vector<std::pair<std::string, int>> order;
+            for (int m = 0; m < nmaterials; ++m) {
+                std::string sig;
+                for (const std::string& c : gs[m]->closure_names)
+                    sig += c + ",";
+                order.push_back({ sig, m });
+            }
+            std::sort(order.begin(), order.end());
+            R->shader_key.assign(nmaterials, 0);
+            for (int k = 0; k < nmaterials; ++k)
+                R->shader_key[order[k].second] = 1 + k;
+        }
         for (Group* gp : gs)  // module texture table = the groups' lists in order
             R->textures.insert(R->textures.end(), gp->textures.begin(), gp->textures.end());
         R->texturepath = opt.count("texturepath") ? opt["texturepath"] : std::string();
@@ -203,12 +273,23 @@ b200_render_cuda_source(const b200_render* r)
     return r ? r->source.c_str() : "";
 }
 
+extern "C" const void*
+b200_render_cubin(const b200_render* r, long long* size)
+{
+    if (size)
+        *size = r ? (long long)r->cubin.size() : 0;
+    return r ? r->cubin.data() : nullptr;
+}
+
 static void
 free_dev(b200_render::Dev& d)
 {
     for (void* p : d.allocs)
         cudaFree(p);
     d.allocs.clear();
+    if (d.host_state)
+        cudaFreeHost((void*)d.host_state);
+    d.host_state = nullptr;
     if (d.mod && jit_driver().ok)
         jit_driver().cuModuleUnload(d.mod);
 }
@@ -242,6 +323,22 @@ upload(b200_render::Dev& d, const T* host, size_t n, bool& ok)
     return (const T*)p;
 }
 
+// dynamic shared memory (bytes) and CTA size of kernel k; *block = 0 for kernels without any
+static size_t
+kernel_smem(const b200_render* r, int k, unsigned* block)
+{
+    const size_t stack = (size_t)r->stk_words * r->bvh_stack * 4;              // per thread
+    const size_t pool  = r->info.pool_in_smem ? (size_t)r->info.pool_words * 4 : 0;  // per thread
+    switch (k) {
+    case K_TRACE: *block = TRACE_BLOCK; return stack * TRACE_BLOCK;
+    case K_SHADE:
+    case K_LIGHT: *block = SHADE_BLOCK; return pool * SHADE_BLOCK;
+    case K_BG_EVAL: *block = 128; return pool * 128;
+    case K_TAIL: *block = 32; return (stack + pool) * 32;
+    default: *block = 0; return 0;
+    }
+}
+
 static int
 ensure_device(b200_render* r, int device, b200_render::Dev** out)
 {
@@ -266,6 +363,23 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
             return set_error(B200_ERR_CUDA, std::string("cuModuleGetFunction(") + KERNELS[k] + "): " + drv.err(cr));
     }
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device);
+    // dynamic shared memory of the kernels that stage traversal stacks / closure arenas there
+    for (int k = 0; k < (has_bg ? (int)K_N : (int)K_FIRST_BG); ++k) {
+        d.resident[k] = 8;
+        unsigned block = 0;
+        size_t smem    = kernel_smem(r, k, &block);
+        if (!block)
+            continue;
+        if (smem > 48 * 1024) {
+            cr = drv.cuFuncSetAttribute(d.fn[k], 8 /* MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
+            if (cr != 0)
+                return set_error(B200_ERR_CUDA, std::string("cuFuncSetAttribute(") + KERNELS[k] + ", "
+                                                    + std::to_string(smem) + " B of shared memory): " + drv.err(cr));
+        }
+        int nb = 0;
+        if (drv.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, d.fn[k], (int)block, smem) == 0 && nb > 0)
+            d.resident[k] = nb;
+    }
     std::string terr = bind_module_textures(d.mod, r->textures, r->texturepath, d.allocs);
     if (!terr.empty())
         return set_error(B200_ERR_INVALID, terr);
@@ -295,6 +409,13 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
     S.bvh_indices      = upload(d, h.bvh_indices, (size_t)h.ntris, ok);
     S.lightprims       = upload(d, h.lightprims, (size_t)h.nlightprims, ok);
     S.shader_is_light  = upload(d, h.shader_is_light, (size_t)h.nshaders, ok);
+    d.shader_key       = upload(d, r->shader_key.data(), r->shader_key.size(), ok);
+    {
+        int* hs = nullptr;
+        if (cudaHostAlloc((void**)&hs, 4 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+            ok = false;
+        d.host_state = hs;
+    }
     {
         // triangles in BVH leaf order as 3 x float4 (vertex a with the primitive id in w, b, c)
         std::vector<float> lt((size_t)12 * h.ntris, 0.0f);
@@ -370,7 +491,10 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
             int block = (ks[i] == K_BG_SCALE) ? 256 : (ks[i] == K_BG_FINISH ? 32 : 128);
             long long work = ks[i] == K_BG_ROWS ? res : (ks[i] == K_BG_FINISH ? 1 : (long long)n);
             int grid = (int)std::min<long long>((work + block - 1) / block, (long long)d.sms * 16);
-            cr       = drv.cuLaunchKernel(d.fn[ks[i]], grid < 1 ? 1 : grid, 1, 1, block, 1, 1, 0, nullptr, bargs, nullptr);
+            unsigned kb = 0;
+            size_t smem = kernel_smem(r, ks[i], &kb);
+            cr = drv.cuLaunchKernel(d.fn[ks[i]], grid < 1 ? 1 : grid, 1, 1, block, 1, 1, (unsigned)smem, nullptr, bargs,
+                                    nullptr);
             count_launches(1);
         }
         if (cr != 0 || cudaDeviceSynchronize() != cudaSuccess) {
@@ -384,11 +508,47 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
     return B200_OK;
 }
 
-extern "C" int
-b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b200_render_stats* stats)
+template<class T>
+static bool
+grow(b200_render::Dev& d, T*& p, long long& cap, long long want, size_t elem)
 {
-    if (!r || !host_rgb || y0 < 0 || y1 > r->host.yres || y0 >= y1)
-        return set_error(B200_ERR_INVALID, "b200_render_rows: bad arguments");
+    if (cap >= want && p)
+        return true;
+    if (p) {
+        cudaFree((void*)p);
+        for (auto& a : d.allocs)
+            if (a == (void*)p) a = nullptr;
+        p = nullptr;
+    }
+    void* q = nullptr;
+    if (cudaMalloc(&q, (size_t)want * elem) != cudaSuccess) {
+        cap = 0;
+        return false;
+    }
+    d.allocs.push_back(q);
+    p   = (T*)q;
+    cap = want;
+    return true;
+}
+
+// The work set of one call: ntiles rectangles (x0, y0, w, h) of the image.  Pixels are numbered
+// tile after tile, row-major inside a tile; out_rgb receives 3 floats per pixel in that order.
+extern "C" int
+b200_render_tiles(b200_render* r, int device, int ntiles, const int* tiles, void* out_rgb, int out_on_device,
+                  b200_render_stats* stats)
+{
+    if (!r || !out_rgb || ntiles <= 0 || !tiles)
+        return set_error(B200_ERR_INVALID, "b200_render_tiles: bad arguments");
+    const int xres = r->host.xres, yres = r->host.yres;
+    if (xres > 65535 || yres > 65535)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_render_tiles: images beyond 65535 pixels a side are not supported");
+    long long npix = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int *q = tiles + 4 * t;
+        if (q[0] < 0 || q[1] < 0 || q[2] <= 0 || q[3] <= 0 || q[0] + q[2] > xres || q[1] + q[3] > yres)
+            return set_error(B200_ERR_INVALID, "b200_render_tiles: tile outside the image");
+        npix += (long long)q[2] * q[3];
+    }
     b200_render::Dev* dp = nullptr;
     int rc               = ensure_device(r, device, &dp);
     if (rc != B200_OK)
@@ -396,158 +556,193 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
     b200_render::Dev& d = *dp;
     Driver& drv         = jit_driver();
     cudaSetDevice(device);
-    const int xres      = r->host.xres;
-    const long long npix = (long long)(y1 - y0) * xres;
-    const int nsamp     = d.S.aa * d.S.aa;
-    // Path slots per batch.  Every batch ends in a tail of a few long paths during which the
-    // GPU is nearly idle, so batches are made as large as memory allows (HBM is there to be
-    // used): by default a quarter of the free device memory at ~148 B of state per slot
-    // (render-microfacet 2048^2 x 64 spp: 37 s with 32 Mi slots, 152 s with 4 Mi).
-    long long target = r->slots_target;
-    if (target <= 0) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        target = (long long)(free_b / 4 / 148);
-        if (target < (4 << 20)) target = 4 << 20;
-    }
-    const long long max_slots = 0x7fffffffLL / 4;
-    if (target > max_slots) target = max_slots;
-    long long SB = target / npix;
-    if (SB < 1) SB = 1;
-    if (SB > nsamp) SB = nsamp;
-    const long long nslots = SB * npix;
-    if (nslots > 0x7fffffffLL / 4)
-        return set_error(B200_ERR_UNSUPPORTED, "b200_render_rows: band too large; render fewer rows per call");
-    // (re)allocate path state
+    const int nsamp = d.S.aa * d.S.aa;
+    // ---- rounds: as many whole sample planes as fit the per-sample result buffer ----------------
+    // Every sample of a round owns a 12-byte result slot (rt_resolve folds them in sample order
+    // afterwards); sample ids are 32-bit.  One round covers the whole call unless the work set
+    // times spp is beyond 2^30 samples or a third of the free device memory.
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += (size_t)d.result_cap * 12;   // our own buffer is reusable
+    long long max_samples = std::min<long long>(1LL << 30, (long long)(free_b / 3 / 12));
+    long long SB          = std::min<long long>(nsamp, max_samples / npix);
+    if (SB < 1)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_render_tiles: work set too large for one call; pass fewer tiles");
+    // ---- the path pool ----------------------------------------------------------------------------
+    // With regeneration the pool only has to keep the machine busy, not hold a frame: the
+    // default is 2 Mi slots (13 waves of the 148 x 2048 resident threads; 400 MB of state).
+    long long nslots = r->slots_target > 0 ? r->slots_target : (2LL << 20);
+    nslots           = std::min<long long>(nslots, SB * npix);
+    nslots           = std::max<long long>(nslots, 1);
     if (d.nslots_cap < nslots) {
-        auto drop = [&](void* p) {
-            if (!p) return;
-            cudaFree(p);
-            for (auto& a : d.allocs)
-                if (a == p) a = nullptr;
-        };
-        drop(d.rec); drop(d.queues); drop(d.sort_keys);
-        bool ok = cudaMalloc(&d.rec, (size_t)16 * PATH_QUADS * nslots) == cudaSuccess
-                  && cudaMalloc(&d.queues, sizeof(int) * 3 * nslots) == cudaSuccess
-                  && cudaMalloc(&d.sort_keys, sizeof(int) * nslots) == cudaSuccess;
-        if (!ok)
-            return set_error(B200_ERR_CUDA, "cudaMalloc(path state) failed");
-        d.allocs.push_back(d.rec); d.allocs.push_back(d.queues); d.allocs.push_back(d.sort_keys);
+        long long c1 = d.nslots_cap, c2 = d.nslots_cap, c3 = d.nslots_cap, c4 = d.nslots_cap;
+        bool ok = grow(d, d.rec, c1, nslots, (size_t)16 * PATH_QUADS) && grow(d, d.shrec, c2, nslots, (size_t)16 * SHADOW_QUADS)
+                  && grow(d, d.queues, c3, nslots, sizeof(int) * 4) && grow(d, d.sort_keys, c4, nslots, sizeof(int));
+        if (!ok) {
+            d.nslots_cap = 0;
+            return set_error(B200_ERR_CUDA, "cudaMalloc(path pool) failed");
+        }
         d.nslots_cap = nslots;
     }
     if (!d.counters) {
-        if (cudaMalloc(&d.counters, sizeof(int) * 256) != cudaSuccess)
+        if (cudaMalloc(&d.counters, sizeof(int) * C_WORDS) != cudaSuccess)
             return set_error(B200_ERR_CUDA, "cudaMalloc failed");
         d.allocs.push_back(d.counters);
     }
-    if (d.accum_cap < npix) {
-        if (d.accum) {
-            cudaFree(d.accum);
-            for (auto& a : d.allocs)
-                if (a == d.accum) a = nullptr;
+    {
+        long long c1 = d.pix_cap, c2 = d.pix_cap;
+        if (!grow(d, d.accum, c1, npix, sizeof(float) * 3) || !grow(d, d.pixmap, c2, npix, sizeof(int))) {
+            d.pix_cap = 0;
+            return set_error(B200_ERR_CUDA, "cudaMalloc(work set) failed");
         }
-        if (cudaMalloc(&d.accum, sizeof(float) * 3 * npix) != cudaSuccess)
-            return set_error(B200_ERR_CUDA, "cudaMalloc failed");
-        d.allocs.push_back(d.accum);
-        d.accum_cap = npix;
+        d.pix_cap = std::min(c1, c2);
+        if (!grow(d, d.result, d.result_cap, SB * npix, sizeof(float) * 3))
+            return set_error(B200_ERR_CUDA, "cudaMalloc(sample results) failed");
     }
-    cudaMemset(d.counters, 0, sizeof(int) * 256);
+    {
+        std::vector<int> pm((size_t)npix);
+        size_t k = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            const int* q = tiles + 4 * t;
+            for (int y = q[1]; y < q[1] + q[3]; ++y)
+                for (int x = q[0]; x < q[0] + q[2]; ++x)
+                    pm[k++] = (int)(((unsigned)y << 16) | (unsigned)x);
+        }
+        if (cudaMemcpy(d.pixmap, pm.data(), sizeof(int) * (size_t)npix, cudaMemcpyHostToDevice) != cudaSuccess)
+            return set_error(B200_ERR_CUDA, "work set upload failed");
+    }
     DevLaunch L;
     memset(&L, 0, sizeof L);
     L.S = d.S;
     L.rec = d.rec;
+    L.shrec = d.shrec;
     int* qbuf[3]  = { d.queues, d.queues + nslots, d.queues + 2 * nslots };
+    L.queue_sh    = d.queues + 3 * nslots;
     L.counters    = d.counters;
-    L.sort_keys   = r->sort ? d.sort_keys : nullptr;
+    const bool sorting = r->sort && d.S.nshaders > 1;
+    L.sort_keys   = sorting ? d.sort_keys : nullptr;
+    L.shader_key  = d.shader_key;
+    L.pixmap      = d.pixmap;
+    L.host_state  = d.host_state;
+    L.nslots      = (int)nslots;
     L.npix        = (int)npix;
-    L.y0          = y0;
-    L.accum       = d.accum;
+    L.result      = d.result;
+    L.accum       = out_on_device ? (float*)out_rgb : d.accum;
     long long launches = 0, iters = 0;
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1, t0, t1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
     cudaEventRecord(e0, 0);
-    auto launch = [&](int k, long long work, unsigned block) -> int {
+    float tail_ms = 0;
+    auto launch = [&](int k, long long work, bool persistent) -> int {
+        unsigned block = 0;
+        size_t smem    = kernel_smem(r, k, &block);
+        if (!block)
+            block = (k == K_SWAP) ? 128 : 256;
         long long want = (work + block - 1) / block;
-        long long cap  = (long long)d.sms * 16;
+        long long cap  = (long long)d.sms * (persistent ? d.resident[k] : 16);
+        if (k == K_TAIL)
+            cap = want;
         unsigned grid  = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
         void* args[]   = { &L };
-        CUresult_ cr   = drv.cuLaunchKernel(d.fn[k], grid, 1, 1, block, 1, 1, 0, nullptr, args, nullptr);
+        CUresult_ cr   = drv.cuLaunchKernel(d.fn[k], grid, 1, 1, block, 1, 1, (unsigned)smem, nullptr, args, nullptr);
         ++launches;
         if (cr != 0)
             return set_error(B200_ERR_CUDA, std::string("cuLaunchKernel(") + KERNELS[k] + "): " + drv.err(cr));
         return B200_OK;
     };
-    int* hcount = nullptr;
-    cudaMallocHost(&hcount, sizeof(int));
+    auto fail = [&](const char* what) {
+        cudaError_t ce = cudaGetLastError();
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+        return set_error(B200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    };
+    volatile int* hs = d.host_state;
     for (int s0 = 0; s0 < nsamp; s0 += (int)SB) {
-        int nb     = (int)((nsamp - s0) < SB ? (nsamp - s0) : SB);
+        const int nb = (int)std::min<long long>(nsamp - s0, SB);
         L.s0       = s0;
         L.nsamples = nb;
-        L.nslots   = (int)(nb * npix);
+        L.total    = (int)(nb * npix);
+        const long long fill = std::min<long long>(nslots, L.total);
+        hs[0] = hs[1] = hs[2] = hs[3] = 0;
+        if (cudaMemsetAsync(d.counters, 0, sizeof(int) * C_WORDS, 0) != cudaSuccess)
+            return fail("counter reset");
         int cur    = 0;  // qbuf index of the live queue
         L.queue_in = qbuf[cur];
-        if ((rc = launch(K_GENERATE, L.nslots, 256)) != B200_OK)
+        if ((rc = launch(K_GENERATE, fill, false)) != B200_OK)
             return rc;
-        long long live = L.nslots;
-        // The kernels take the live count from device memory; the host only needs it to size
-        // grids (an upper bound is enough: the count never grows) and to stop.  So several
-        // bounces are enqueued back to back and the count is read once per chunk: no host
-        // round trip per bounce, and the launches of a chunk overlap the execution of the
-        // previous kernels.  Empty trailing bounces cost a few microseconds each.
-        int since_sync = 0, chunk = 1;
-        while (live > 0) {
-            ++iters;
-            L.queue_in  = qbuf[cur];
-            if (live <= r->tail_paths) {
-                // the stragglers: one launch runs each of them to its end (rt_tail)
-                if ((rc = launch(K_TAIL, live * 32, 32)) != B200_OK)   // one CTA (one warp) per path
-                    return rc;
-                if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)   // counters[1] is 0: nothing is queued
-                    return rc;
-                if (cudaStreamSynchronize(0) != cudaSuccess) {
-                    cudaError_t ce = cudaGetLastError();
-                    return set_error(B200_ERR_CUDA, std::string("render tail failed: ") + cudaGetErrorString(ce));
-                }
+        // One step = trace, light, [scatter], shade, swap.  The kernels take their counts from
+        // device memory; the host only needs upper bounds for the grids and the moment to stop.
+        // rt_swap publishes {step, live, shadow, next} in mapped pinned memory, so the host
+        // keeps up to RUNAHEAD steps enqueued and never synchronises inside the loop.
+        const int RUNAHEAD = 12;
+        long long enq = 0;
+        bool tail = false;
+        for (;;) {
+            const int it = hs[0];
+            const long long live = hs[1], shadow = hs[2], next = hs[3];
+            const bool exhausted = it > 0 && next >= L.total;
+            if (it > 0 && live == 0 && shadow == 0)
+                break;
+            if (exhausted && r->tail_paths > 0 && live > 0 && live <= r->tail_paths) {
+                tail = true;
                 break;
             }
-            L.queue_out = qbuf[(cur + 1) % 3];
-            if ((rc = launch(K_INTERSECT, live, 256)) != B200_OK)
-                return rc;
-            if (r->sort && d.S.nshaders > 1) {
-                if ((rc = launch(K_SORT_COUNT, live, 256)) != B200_OK) return rc;
-                if ((rc = launch(K_SORT_SCAN, 1, 32)) != B200_OK) return rc;
-                if ((rc = launch(K_SORT_SCATTER, live, 256)) != B200_OK) return rc;
-                cur        = (cur + 1) % 3;  // sorted queue
-                L.queue_in = qbuf[cur];
-            }
-            L.queue_out = qbuf[(cur + 1) % 3];
-            if ((rc = launch(K_SHADE, live, 128)) != B200_OK)
-                return rc;
-            if ((rc = launch(K_SWAP, 1, 32)) != B200_OK)
-                return rc;
-            cur = (cur + 1) % 3;
-            if (++since_sync < chunk)
+            if (enq - it >= RUNAHEAD) {
+                cudaError_t q = cudaStreamQuery(0);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail("render step failed");
                 continue;
-            since_sync = 0;
-            chunk      = chunk < 8 ? chunk * 2 : 8;   // 1, 2, 4, 8, 8, ... bounces per read-back
-            cudaMemcpyAsync(hcount, d.counters, sizeof(int), cudaMemcpyDeviceToHost, 0);
-            if (cudaStreamSynchronize(0) != cudaSuccess) {
-                cudaError_t ce = cudaGetLastError();
-                return set_error(B200_ERR_CUDA, std::string("render bounce failed: ") + cudaGetErrorString(ce));
             }
-            live = *hcount;
+            const long long bound = exhausted ? std::max(live, shadow) : fill;
+            ++iters;
+            ++enq;
+            L.queue_in  = qbuf[cur];
+            L.queue_out = qbuf[(cur + 1) % 3];   // next live queue: filled by light (regen) and shade
+            if ((rc = launch(K_TRACE, 2 * bound, true)) != B200_OK) return rc;
+            if ((rc = launch(K_LIGHT, bound, false)) != B200_OK) return rc;
+            if (sorting) {
+                L.queue_out = qbuf[(cur + 2) % 3];   // the sorted copy of the live queue
+                if ((rc = launch(K_SORT_SCATTER, bound, false)) != B200_OK) return rc;
+                L.queue_in  = qbuf[(cur + 2) % 3];
+                L.queue_out = qbuf[(cur + 1) % 3];
+            }
+            if ((rc = launch(K_SHADE, bound, false)) != B200_OK) return rc;
+            if ((rc = launch(K_SWAP, 1, false)) != B200_OK) return rc;
+            cur = (cur + 1) % 3;
         }
-        if ((rc = launch(K_RESOLVE, npix, 256)) != B200_OK)
+        if (tail) {
+            // the stragglers: finish the pending shadow rays, find the closest hits, then one
+            // launch runs every remaining path to its end (rt_tail)
+            L.queue_in  = qbuf[cur];
+            L.queue_out = qbuf[(cur + 1) % 3];
+            const long long bound = std::max<long long>(hs[1], hs[2]);
+            if ((rc = launch(K_TRACE, 2 * std::max<long long>(bound, r->tail_paths), true)) != B200_OK) return rc;
+            if ((rc = launch(K_LIGHT, std::max<long long>(bound, r->tail_paths), false)) != B200_OK) return rc;
+            cudaEventRecord(t0, 0);
+            if ((rc = launch(K_TAIL, r->tail_paths * 32, false)) != B200_OK) return rc;   // one CTA (one warp) per path
+            cudaEventRecord(t1, 0);
+        }
+        if (cudaStreamSynchronize(0) != cudaSuccess)
+            return fail("render round failed");
+        if (tail) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, t1);
+            tail_ms += ms;
+        }
+        if ((rc = launch(K_RESOLVE, npix, false)) != B200_OK)
             return rc;
     }
     cudaEventRecord(e1, 0);
-    cudaError_t ce = cudaMemcpy(host_rgb, d.accum, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost);
-    cudaFreeHost(hcount);
+    cudaError_t ce = cudaSuccess;
+    if (!out_on_device)
+        ce = cudaMemcpy(out_rgb, d.accum, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost);
+    else
+        ce = cudaStreamSynchronize(0);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
     count_launches(launches);
     if (ce != cudaSuccess)
         return set_error(B200_ERR_CUDA, std::string("render readback: ") + cudaGetErrorString(ce));
@@ -556,6 +751,18 @@ b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b2
         stats->launches          = launches;
         stats->bounce_iterations = iters;
         stats->device_ms         = ms;
+        stats->tail_ms           = tail_ms;
+        stats->slots             = nslots;
+        stats->rounds            = (nsamp + SB - 1) / SB;
     }
     return B200_OK;
+}
+
+extern "C" int
+b200_render_rows(b200_render* r, int device, int y0, int y1, float* host_rgb, b200_render_stats* stats)
+{
+    if (!r || !host_rgb || y0 < 0 || y1 > r->host.yres || y0 >= y1)
+        return set_error(B200_ERR_INVALID, "b200_render_rows: bad arguments");
+    const int tile[4] = { 0, y0, r->host.xres, y1 - y0 };
+    return b200_render_tiles(r, device, 1, tile, host_rgb, 0, stats);
 }

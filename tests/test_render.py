@@ -221,3 +221,34 @@ def test_gpu_first_hit_globals(b200lib, cuda_device):
         want = oracle.OracleRender(S, A, helpers.oso).render(96, 96, 1, nthreads=4, show_globals=mode)
         got = api.Renderer(S, A, helpers.oso, 96, 96, 1, show_globals=mode, options="fma=0").render()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), mode
+
+
+@pytest.mark.gpu
+def test_gpu_render_tiles_and_regeneration(b200lib, cuda_device):
+    """The multi-GPU partition: interleaved 64x64 tiles per GPU.  Any split of the
+    image into tile work sets, any pool size (paths regenerate into freed slots, so a tiny pool
+    means every slot is reused hundreds of times) and a device-resident output give the pixels of
+    one whole-frame call."""
+    import torch
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-cornell")
+    res, aa = 128, 4
+    dev = cuda_device.index or 0
+    R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=0")
+    whole = R.render()
+    assert R.stats["rounds"] == 1 and R.stats["slots"] == res * res * aa * aa
+    tiles = api.tile_list(res, res, 48)          # 48 does not divide 128: ragged edge tiles
+    assert int((tiles[:, 2] * tiles[:, 3]).sum()) == res * res
+    img = np.zeros_like(whole)
+    Rs = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=0,slots=3000,tail=64")
+    for rank in range(3):                        # round-robin tiles over 3 "GPUs"
+        mine = tiles[rank::3]
+        ys, xs = api.tile_pixels(mine)
+        if rank == 1:                            # device-resident output
+            out = torch.zeros((len(ys), 3), dtype=torch.float32, device=cuda_device)
+            Rs.render_tiles(mine, device=dev, out=out)
+            img[ys, xs] = out.cpu().numpy()
+        else:
+            img[ys, xs] = Rs.render_tiles(mine, device=dev)
+        assert Rs.stats["slots"] == 3000
+    assert np.array_equal(whole.view(np.uint32), img.view(np.uint32))
