@@ -254,6 +254,23 @@ class ShaderGroup:
         _check(lib().b200_group_execute(self._h, device, ctypes.c_void_p(stream), n, ctypes.byref(g),
                                         _ptr(shadeindex), None, _ptr(output)))
 
+    def bind(self, n, varying, uniform, output, shadeindex=None, device=0, stream=None, plane_stride=None):
+        """-> zero-argument callable that issues b200_group_execute with the globals block,
+        pointers and stream bound once - a renderer reusing its ShaderGlobals batch between
+        launches.  The per-call cost is one foreign call."""
+        g = _fill_globals(n, varying, uniform, plane_stride)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(device).cuda_stream
+        fn, h = lib().b200_group_execute, self._h
+        args = (h, device, ctypes.c_void_p(stream), n, ctypes.byref(g), _ptr(shadeindex), None, _ptr(output))
+
+        def launch(_keep=(g, varying, output, shadeindex)):
+            rc = fn(*args)
+            if rc:
+                _check(rc)
+        return launch
+
     def execute_host(self, n, varying, uniform, output, device=0, plane_stride=None):
         """Host-pointer path (b200_group_execute_host): numpy arrays or pinned
         CPU tensors in, host output arena out.  Synchronous."""

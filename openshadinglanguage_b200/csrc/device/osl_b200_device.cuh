@@ -15,6 +15,9 @@
 #pragma once
 
 #define OSLD __device__ __forceinline__
+#ifndef OSLD_ENTRY_INLINE
+#define OSLD_ENTRY_INLINE __forceinline__   // a material group called from the integrator
+#endif
 
 namespace osld {
 

@@ -1320,7 +1320,7 @@ extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_const
 // while the other lanes keep walking (rays of very different length share a warp; without
 // this the warp idles on its longest ray: ncu showed 7 of 32 lanes active in round 1).
 #ifndef OSLD_TRACE_CHUNK
-#define OSLD_TRACE_CHUNK 12   // node / leaf visits between two refills
+#define OSLD_TRACE_CHUNK 32   // node / leaf visits between two refills (sweep: profiles/render_tune_r02.txt)
 #endif
 #define OSLD_TRACE_BLOCK 128
 extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __grid_constant__ RenderLaunch L)
@@ -1650,7 +1650,10 @@ OSLD bool light_path(const RenderLaunch& L, int slot, ClosurePool& pool)
 }
 
 #define OSLD_SHADE_BLOCK 128
-extern "C" __global__ void __launch_bounds__(OSLD_SHADE_BLOCK) rt_shade(const __grid_constant__ RenderLaunch L)
+#ifndef OSLD_SHADE_MINBLOCKS
+#define OSLD_SHADE_MINBLOCKS 8   // 64 registers: 32 resident warps per SM (4, 6 and 8 time the same)
+#endif
+extern "C" __global__ void __launch_bounds__(OSLD_SHADE_BLOCK, OSLD_SHADE_MINBLOCKS) rt_shade(const __grid_constant__ RenderLaunch L)
 {
     extern __shared__ unsigned smem_[];
     OSLD_POOL_DECL(pool, smem_);

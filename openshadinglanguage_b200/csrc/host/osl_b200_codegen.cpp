@@ -1781,7 +1781,7 @@ Gen::run_material(const std::string& ns)
             gen_layer(l);
     std::ostringstream out;
     out << "namespace " << ns << " {\n" << gd << o.str();
-    out << "static __device__ __noinline__ void entry(SG& sg)\n{\n    GD gd;\n    gd.ran = 0u;\n    B200Launch L;\n";
+    out << "static __device__ OSLD_ENTRY_INLINE void entry(SG& sg)\n{\n    GD gd;\n    gd.ran = 0u;\n    B200Launch L;\n";
     out << "    layer_" << (nlayers - 1) << "(sg, gd, L);\n}\n}  // namespace " << ns << "\n";
     return out.str();
 }

@@ -238,6 +238,13 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
         pre << "#define OSLD_BVH_STACK " << R->bvh_stack << "\n";
         if (!packable)
             pre << "#define OSLD_BVH_UNPACKED 1\n";
+        // tuning knobs of the integrator kernels (defaults in device/osl_b200_render.cuh)
+        if (opt.count("chunk"))
+            pre << "#define OSLD_TRACE_CHUNK " << atoi(opt["chunk"].c_str()) << "\n";
+        if (opt.count("shade_blocks"))
+            pre << "#define OSLD_SHADE_MINBLOCKS " << atoi(opt["shade_blocks"].c_str()) << "\n";
+        if (opt.count("inline"))
+            pre << "#define OSLD_ENTRY_INLINE " << (atoi(opt["inline"].c_str()) ? "__forceinline__" : "__noinline__") << "\n";
         R->source = pre.str() + body;
         // Sort buckets: materials that emit the same set of closures (their closure-type
         // signature) are neighbours in the sorted wavefront; within a signature, by material.

@@ -38,3 +38,55 @@ def gather_strips(local, npoints, rank, world, align=256, floats_per_point=None)
         return out
     dist.gather(pad, None, dst=0)
     return None
+
+
+def tile_list(xres, yres, tile=64):
+    """Row-major list of the image's tiles (x0, y0, w, h); edge tiles are smaller."""
+    return [(x, y, min(tile, xres - x), min(tile, yres - y))
+            for y in range(0, yres, tile) for x in range(0, xres, tile)]
+
+
+def rank_tiles(xres, yres, rank, world, tile=64):
+    """The interleaved tile work set of `rank`: tile k of the row-major
+    list goes to rank k % world, so every GPU gets an even sample of cheap (sky) and expensive
+    (glass, interreflection) image regions - contiguous bands do not (the top band of
+    render-mx-layer is all sky)."""
+    return tile_list(xres, yres, tile)[rank::world]
+
+
+def tile_pixel_index(tiles, xres):
+    """Flat image index y*xres + x of every pixel of a tile work set, in work-set order
+    (tile after tile, row-major inside a tile) as an int64 torch tensor."""
+    import torch
+    parts = []
+    for x0, y0, w, h in tiles:
+        ys = torch.arange(y0, y0 + h, dtype=torch.int64).unsqueeze(1)
+        xs = torch.arange(x0, x0 + w, dtype=torch.int64).unsqueeze(0)
+        parts.append((ys * xres + xs).reshape(-1))
+    return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64)
+
+
+def gather_tiles(local, xres, yres, rank, world, tile=64):
+    """Framebuffer gather of a tile-sharded render: every rank contributes its work set's
+    [npix_local, 3] strip (device memory on GPUs: no host round trip); rank 0 receives the
+    padded strips with one gather and scatters them into the [yres, xres, 3] image on its
+    device.  Returns the image on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    sets = [rank_tiles(xres, yres, r, world, tile) for r in range(world)]
+    sizes = [sum(w * h for _, _, w, h in s) for s in sets]
+    longest = max(sizes)
+    if local.shape[0] == longest:
+        pad = local.contiguous()
+    else:
+        pad = torch.zeros((longest, 3), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+    if rank != 0:
+        dist.gather(pad, None, dst=0)
+        return None
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.gather(pad, bufs, dst=0)
+    img = torch.empty((yres * xres, 3), dtype=local.dtype, device=local.device)
+    for s, n, buf in zip(sets, sizes, bufs):
+        img[tile_pixel_index(s, xres).to(local.device)] = buf[:n]
+    return img.reshape(yres, xres, 3)

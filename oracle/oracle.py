@@ -364,6 +364,22 @@ def register_textures(lib, textures):
         lib.oracle_texture_add(name.encode(), img.shape[1], img.shape[0], img.shape[2], img.ctypes.data)
 
 
+class OracleGroupWide(OracleGroup):
+    """The 16-wide batched restatement (oso2cpp.WideGen): same interface, same results up to FMA
+    contraction; bench.py's batched CPU baseline."""
+
+    def __init__(self, layers, connections=(), outputs=(), textures=None):
+        ls = [oso2cpp.Layer(l["oso"], l["name"], l.get("params")) for l in layers]
+        self.group = oso2cpp.Group(ls, connections, outputs)
+        self.so = oso2cpp.build_group_wide(self.group)
+        self.lib = ctypes.CDLL(self.so)
+        self.lib.oracle_run_mt.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong, ctypes.c_int]
+        self.lib.oracle_run_capture.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong,
+                                                ctypes.c_longlong]
+        self.lib.oracle_run_capture.restype = ctypes.c_char_p
+        register_textures(self.lib, textures)
+
+
 class OracleRender:
     def __init__(self, scene, arrays, oso_lookup, opt="-O2"):
         self.scene, self.arrays = scene, arrays

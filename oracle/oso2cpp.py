@@ -1501,6 +1501,260 @@ extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
 """
 
 
+
+# ---------------------------------------------------------------------------
+# 16-wide batched restatement (the reference's BatchedExecutor<16> path:
+# testshade.cpp:1829-1922 batched_shade_region, batched_llvm_gen.cpp).  Every
+# symbol is a block of WIDTH lanes, every op is a loop over the lanes enabled in
+# the current execution mask (the reference's wide ops are OMP-simd lane loops
+# too: wide/*.cpp), `if` splits the mask, loops run while any lane is active,
+# `return` retires lanes until the end of the function, a lazily evaluated
+# upstream layer runs for (mask & ~already-run lanes) (batched_llvm_gen.cpp:116-137).
+# Used as the batched CPU baseline of bench.py and pinned against the scalar
+# oracle by tests/test_oracle_wide.py.  printf text is dropped (no journal); closures /
+# break / continue / exit are not restated in this mode (NotImplementedError).
+# ---------------------------------------------------------------------------
+WIDTH = 16
+
+WIDE_PRELUDE = r"""
+#define OSLO_W %d
+#define OSLO_LANES(m) _Pragma("omp simd") for (int l_ = 0; l_ < OSLO_W; ++l_) if (((m) >> l_) & 1u)
+""" % WIDTH
+
+
+class WideGen(Gen):
+    def ref(self, l, s):
+        e = Gen.ref(self, l, s)
+        if s.symtype in ("const", "global"):
+            return e
+        return e + "[l_]"
+
+    def eff(self, ctx):
+        r = ctx.get("ret")
+        return "(%s & ~%s)" % (ctx["mask"], r) if r else ctx["mask"]
+
+    def generate(self):
+        g = self.g
+        o = self.out
+        o.append("// generated by oracle/oso2cpp.py (wide mode) — CPU oracle, test infrastructure only")
+        o.append('#include "osl_oracle_closure.h"')
+        o.append('#include "osl_oracle_runtime.h"')
+        o.append(WIDE_PRELUDE)
+        o.append("using namespace oslo;")
+        o.append("namespace {")
+        o.append("struct GD {")
+        o.append("    unsigned ran[%d];   // lanes for which the layer has run" % max(1, len(g.layers)))
+        for l in g.layers:
+            if l.unused:
+                continue
+            for s in l.m.syms:
+                if s.symtype in ("param", "oparam"):
+                    arr = "[%d]" % s.t.arr if s.t.arr else ""
+                    o.append("    %s L%d_%s[OSLO_W]%s;" % (self.ctype(s), l.idx, self.ident(s.name), arr))
+        o.append("};")
+        used = [l for l in g.layers if not l.unused]
+        for l in used:
+            o.append("static void layer_%d(SG* sgw, GD& gd, const Launch* L, unsigned m0);" % l.idx)
+        for l in used:
+            self.gen_layer(l)
+        o.append("}  // namespace")
+        o.append('extern "C" void oracle_run(const Launch* L, long long begin, long long end, std::string* pf)')
+        o.append("{")
+        o.append("    Ctx ctx{pf};")
+        o.append("    for (long long i0 = begin; i0 < end; i0 += OSLO_W) {")
+        o.append("        SG sgw[OSLO_W]; GD gd;")
+        o.append("        const int nb = (int)std::min<long long>(OSLO_W, end - i0);")
+        o.append("        const unsigned m0 = nb >= 32 ? ~0u : ((1u << nb) - 1u);")
+        o.append("        for (int l = 0; l < nb; ++l) load_sg(sgw[l], L, i0 + l, &ctx);")
+        o.append("        for (int k = 0; k < %d; ++k) gd.ran[k] = 0u;" % max(1, len(g.layers)))
+        o.append("        layer_%d(sgw, gd, L, m0);" % (len(g.layers) - 1))
+        o.append("    }")
+        o.append("}")
+        o.append(RUNNER_TAIL)
+        return "\n".join(o) + "\n"
+
+    def lanes(self, mask):
+        self.w("OSLO_LANES(%s) {" % mask)
+        self.ind += 1
+        self.w("SG& sg = sgw[l_]; (void)sg;")
+
+    def end_lanes(self):
+        self.ind -= 1
+        self.w("}")
+
+    def gen_layer(self, l):
+        g = self.g
+        m = l.m
+        self.l = l
+        self.ind = 0
+        self.w("static void layer_%d(SG* sgw, GD& gd, const Launch* L, unsigned m0)" % l.idx)
+        self.w("{")
+        self.ind = 1
+        self.w("gd.ran[%d] |= m0;" % l.idx)
+        self.w("(void)L;")
+        for s in m.syms:
+            if s.symtype in ("local", "temp"):
+                arr = "[%d]" % s.t.arr if s.t.arr else ""
+                self.w("%s %s[OSLO_W]%s = {};" % (self.ctype(s), self.ident(s.name), arr))
+            elif s.symtype == "const" and s.t.arr:
+                vals = self.initval(s)
+                self.w("static const %s K_%s[%d] = {%s};" % (
+                    self.ctype(s), self.ident(s.name), s.t.arr, ", ".join(vals)))
+        ctx = dict(mask="m0")
+        if l.idx == len(g.layers) - 1:
+            for e in g.layers[:-1]:
+                if not e.unused and not e.lazy:
+                    self.w("if (m0 & ~gd.ran[%d]) layer_%d(sgw, gd, L, m0 & ~gd.ran[%d]);" % (e.idx, e.idx, e.idx))
+        for s in m.syms:
+            if s.symtype not in ("param", "oparam"):
+                continue
+            if s.connected_from is not None:
+                continue
+            vals = self.initval(s)
+            r = self.ref(l, s)
+            self.lanes("m0")
+            if s.t.arr:
+                for i, v in enumerate(vals):
+                    self.w("%s[%d] = %s;" % (r, i, v))
+            else:
+                self.w("%s = %s;" % (r, vals[0]))
+            self.end_lanes()
+            if s.initexpr and s.name in m.methods:
+                b, e = m.methods[s.name]
+                self.ensured = set()
+                self.emit_block(b, e, ctx)
+        self.ensured = set()
+        b, e = m.methods.get("___main___", (0, 0))
+        self.emit_block(b, e, ctx)
+        self.lanes("m0")
+        for (si, ssym, di, dsym) in g.connections:
+            if si != l.idx or g.layers[di].unused:
+                continue
+            self.emit_copy(g.layers[di], dsym, l, ssym)
+        for (li, s) in g.outputs:
+            if li != l.idx:
+                continue
+            ro = s.renderer_output
+            fn = "wrd" if ro["derivs"] else "wr"
+            self.w("%s(outp(L, sg, %d, %d), %s);" % (fn, ro["offset"], ro["stride"], self.ref(l, s)))
+        self.end_lanes()
+        self.ind = 0
+        self.w("}")
+
+    def mask_where(self, var, mask, cond, negate=False):
+        """var = lanes of `mask` whose condition symbol is true (false with negate)"""
+        self.w("for (int l_ = 0; l_ < OSLO_W; ++l_) if (((%s) >> l_) & 1u) { if (%s(%s)) %s |= 1u << l_; }"
+               % (mask, "!" if negate else "", cond, var))
+
+    def emit_block(self, b, e, ctx):
+        ops = self.l.m.ops
+        i = b
+        while i < e:
+            op = ops[i]
+            n = op.name
+            if n == "if":
+                self.useparams(op, ctx)
+                self.label += 1
+                k = self.label
+                self.w("unsigned mt_%d = 0u;" % k)
+                self.mask_where("mt_%d" % k, self.eff(ctx), self.ref(self.l, op.args[0]))
+                saved = set(self.ensured)
+                self.w("if (mt_%d) {" % k)
+                self.ind += 1
+                self.emit_block(i + 1, op.jumps[0], dict(ctx, mask="mt_%d" % k))
+                self.ind -= 1
+                self.w("}")
+                self.ensured = set(saved)
+                if op.jumps[1] > op.jumps[0]:
+                    self.w("const unsigned me_%d = %s & ~mt_%d;" % (k, self.eff(ctx), k))
+                    self.w("if (me_%d) {" % k)
+                    self.ind += 1
+                    self.emit_block(op.jumps[0], op.jumps[1], dict(ctx, mask="me_%d" % k))
+                    self.ind -= 1
+                    self.w("}")
+                    self.ensured = set(saved)
+                i = op.jumps[1]
+            elif n in ("for", "while", "dowhile"):
+                cl, bl, il, dl = op.jumps
+                self.label += 1
+                k = self.label
+                self.emit_block(i + 1, cl, ctx)
+                saved = set(self.ensured)
+                cond = self.ref(self.l, op.args[0])
+                self.w("unsigned ml_%d = %s;" % (k, self.eff(ctx)))
+                c2 = dict(ctx, mask="ml_%d" % k, loop=True)
+                self.w("for (;;) {")
+                self.ind += 1
+                if n == "dowhile":
+                    self.emit_block(bl, il, c2)
+                    self.emit_block(cl, bl, c2)
+                else:
+                    self.emit_block(cl, bl, c2)
+                self.w("{ unsigned keep_ = 0u;")
+                self.mask_where("keep_", self.eff(c2), cond)
+                self.w("  ml_%d = keep_; }" % k)
+                self.w("if (!ml_%d) break;" % k)
+                if n == "dowhile":
+                    self.emit_block(il, dl, c2)
+                else:
+                    self.emit_block(bl, il, c2)
+                    self.emit_block(il, dl, c2)
+                self.ind -= 1
+                self.w("}")
+                self.ensured = set(saved)
+                i = dl
+            elif n == "functioncall":
+                self.label += 1
+                k = self.label
+                # lanes that executed `return` inside the body stay off until its end
+                self.w("unsigned mr_%d = %s;" % (k, ("~" + self.eff(ctx)) if ctx.get("ret") else "0u"))
+                saved = set(self.ensured)
+                self.w("{")
+                self.ind += 1
+                self.emit_block(i + 1, op.jumps[0], dict(ctx, ret="mr_%d" % k))
+                self.ind -= 1
+                self.w("}")
+                self.ensured = set(saved)
+                i = op.jumps[0]
+            elif n == "return":
+                if not ctx.get("ret"):
+                    raise NotImplementedError("wide oracle: 'return' outside a function")
+                self.w("%s |= %s;" % (ctx["ret"], ctx["mask"]))
+                i += 1
+            elif n in ("break", "continue", "exit"):
+                raise NotImplementedError("wide oracle: op '%s' is not restated in batched mode" % n)
+            elif n in ("nop", "end", "useparam"):
+                i += 1
+            else:
+                if n in ("printf", "error", "warning", "fprintf"):
+                    i += 1      # no journal in batched mode: the text is dropped (results are unaffected)
+                    continue
+                if n == "closure":
+                    raise NotImplementedError("wide oracle: op '%s' is not restated in batched mode" % n)
+                self.useparams(op, ctx)
+                self.lanes(self.eff(ctx))
+                self.emit_op(op)
+                self.end_lanes()
+                i += 1
+
+    def useparams(self, op, ctx=None):
+        for a, c in zip(op.args, op.rw):
+            if c in "rW" and a.connected_from is not None:
+                up = a.connected_from[0]
+                if up in self.ensured:
+                    continue
+                self.ensured.add(up)
+                m = self.eff(ctx)
+                self.w("if (%s & ~gd.ran[%d]) layer_%d(sgw, gd, L, %s & ~gd.ran[%d]);" % (m, up, up, m, up))
+
+
+def build_group_wide(group, workdir=None):
+    """The batched restatement, built the way testshade --batched runs: native ISA (AVX-512 when
+    the host has it), FMA contraction allowed (testshade.cpp:294-298 turns llvm_jit_fma on)."""
+    return _compile(WideGen(group).generate(), workdir, "-O3",
+                    ("-march=native", "-fopenmp-simd", "-ffp-contract=fast"))
+
+
 def generate_render_module(groups):
     """One translation unit holding every material group of a scene plus the
     restated path tracer (osl_oracle_render.h)."""

@@ -75,3 +75,50 @@ def test_two_rank_shard_and_gather_matches_single_process():
     want = np.zeros((n, 3), np.float32)
     g.run(n, var, uni, want)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_rank_tiles_partition_the_image():
+    from openshadinglanguage_b200.sharding import rank_tiles, tile_pixel_index
+    for (xres, yres) in ((128, 128), (160, 120), (100, 70)):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(xres * yres, np.int32)
+            for r in range(world):
+                idx = tile_pixel_index(rank_tiles(xres, yres, r, world), xres).numpy()
+                seen[idx] += 1
+            assert (seen == 1).all()          # every pixel in exactly one work set
+
+
+def _tile_worker(rank, world, port, xres, yres, q):
+    sys.path.insert(0, helpers.ROOT)
+    import torch
+    import torch.distributed as dist
+    from openshadinglanguage_b200.sharding import gather_tiles, rank_tiles, tile_pixel_index
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(xres * yres * 3, dtype=torch.float32).reshape(xres * yres, 3)   # the "frame"
+    strip = full[tile_pixel_index(rank_tiles(xres, yres, rank, world), xres)]           # this rank's render
+    img = gather_tiles(strip, xres, yres, rank, world)
+    if rank == 0:
+        q.put(img.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_gather_reassembles_the_frame():
+    import torch.multiprocessing as mp
+    xres, yres = 160, 120          # ragged: 64 divides neither
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tile_worker, args=(r, 2, port, xres, yres, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(xres * yres * 3, dtype=np.float32).reshape(yres, xres, 3)
+    assert np.array_equal(got, want)
