@@ -360,7 +360,7 @@ def main():
             import helpers
             from openshadinglanguage_b200 import api
             from openshadinglanguage_b200.render import scene as rsc
-            from openshadinglanguage_b200.sharding import gather_tiles, rank_tiles
+            from openshadinglanguage_b200.sharding import gather_plan, gather_tiles, rank_tiles
             S = rsc.load_scene(os.path.join(helpers.GOLDEN, "scenes", rxml))
             A = S.prepare()
             R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=1,sort=1")
@@ -368,6 +368,8 @@ def main():
             npix = sum(w * h for _, _, w, h in tiles)
             strip = torch.zeros((npix, 3), dtype=torch.float32, device=dev)
             himg = torch.zeros((res, res, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+            # the tile layout is static: index tables for the reassembly are built once, like a renderer would
+            plan = gather_plan(res, res, world, dev if rank == 0 else "cpu")
 
             def frame():
                 """one frame end to end: render the work set, gather, image in host memory on rank 0"""
@@ -375,18 +377,17 @@ def main():
                 st = dict(R.stats)
                 g0 = time.perf_counter()
                 if world > 1:
-                    img = gather_tiles(strip, res, res, rank, world)
+                    img = gather_tiles(strip, res, res, rank, world, plan=plan)
                 else:
-                    img = strip.reshape(res, res, 3) if len(tiles) == 1 else gather_tiles_single(strip)
+                    img = gather_tiles_single(strip)
                 if rank == 0:
                     himg.copy_(img, non_blocking=False)
                 torch.cuda.synchronize()
                 return st, (time.perf_counter() - g0) * 1e3
 
             def gather_tiles_single(s):
-                from openshadinglanguage_b200.sharding import tile_pixel_index
                 img = torch.empty((res * res, 3), dtype=torch.float32, device=dev)
-                img[tile_pixel_index(tiles, res).to(dev)] = s
+                img[plan[1][0]] = s
                 return img.reshape(res, res, 3)
 
             # warm-up: module load, scene upload, pool allocation, NCCL channels - one whole frame

@@ -763,53 +763,50 @@ OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3
     T.shy = vcomp(dir, ky) / vcomp(dir, kz);
     T.shz = vcomp(T.rdir, kz);
 }
-// Scene::intersect (bvh.cpp:265-356), resumable: walks until the ray is finished (returns true)
-// or `budget` node / leaf visits have been spent (returns false; call again).
-// "while-while" traversal (Aila & Laine): every lane first walks inner nodes until it holds
-// a leaf, then the warp tests triangles together.  Per ray the visiting order is exactly
-// the reference's pop / test / push-far-then-near sequence; only the lock-step grouping of
-// the lanes changes, so the hit (and any tie between coplanar triangles) is the reference's.
-OSLD bool trav_run(const RenderScene& S, Trav& T, int budget)
+// Scene::intersect (bvh.cpp:265-356), resumable, one STEP per call: walk at most `max_nodes`
+// inner nodes; if that reaches a leaf, test its triangles.  Returns true when the ray is finished.
+// "while-while" traversal (Aila & Laine) with a bounded walk: every lane first walks inner
+// nodes until it holds a leaf (or has spent its node budget), then the lanes holding a leaf
+// test triangles together - a lane that finds its leaf early waits for at most max_nodes
+// visits of the others.  Per ray the visiting order is exactly the reference's pop / test /
+// push-far-then-near sequence; only the lock-step grouping of the lanes changes, so the hit
+// (and any tie between coplanar triangles) is the reference's.
+OSLD bool trav_step(const RenderScene& S, Trav& T, int max_nodes)
 {
     const V3 org = T.org, rdir = T.rdir;
-    const int kx = T.kx, ky = T.ky, kz = T.kz;
-    const float shx = T.shx, shy = T.shy, shz = T.shz;
     int sp = T.sp;
     Hit result = T.hit;
-    bool finished = false;
-    while (budget > 0) {
-        unsigned child = 0, nprims = 0;
-        while (sp != 0) {
-            --sp;
-            if (result.t < stk_dist(T, sp))
-                continue;
-            stk_get(T, sp, child, nprims);
-            if (nprims)
-                break;
-            --budget;
-            // the two children are adjacent: 64 contiguous bytes
-            const float4* cn = S.bvh_nodes + 2 * (size_t)child;
-            const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
-            float d1 = 0, d2 = 0;
-            bool h1 = box_intersect(org, rdir, result.t, a0, a1, &d1);
-            bool h2 = box_intersect(org, rdir, result.t, b0, b1, &d2);
-            unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
-            if (d1 > d2) {
-                bool th = h1; h1 = h2; h2 = th;
-                float td = d1; d1 = d2; d2 = td;
-                unsigned tk = k1; k1 = k2; k2 = tk;
-                unsigned tn = n1; n1 = n2; n2 = tn;
-            }
-            stk_put(T, sp, k2, n2, d2);
-            sp += h2 ? 1 : 0;
-            stk_put(T, sp, k1, n1, d1);
-            sp += h1 ? 1 : 0;
-        }
-        if (!nprims) {
-            finished = true;
+    unsigned child = 0, nprims = 0;
+    while (sp != 0 && max_nodes > 0) {
+        --sp;
+        if (result.t < stk_dist(T, sp))
+            continue;
+        stk_get(T, sp, child, nprims);
+        if (nprims)
             break;
+        --max_nodes;
+        // the two children are adjacent: 64 contiguous bytes
+        const float4* cn = S.bvh_nodes + 2 * (size_t)child;
+        const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
+        float d1 = 0, d2 = 0;
+        bool h1 = box_intersect(org, rdir, result.t, a0, a1, &d1);
+        bool h2 = box_intersect(org, rdir, result.t, b0, b1, &d2);
+        unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
+        if (d1 > d2) {
+            bool th = h1; h1 = h2; h2 = th;
+            float td = d1; d1 = d2; d2 = td;
+            unsigned tk = k1; k1 = k2; k2 = tk;
+            unsigned tn = n1; n1 = n2; n2 = tn;
         }
-        --budget;
+        stk_put(T, sp, k2, n2, d2);
+        sp += h2 ? 1 : 0;
+        stk_put(T, sp, k1, n1, d1);
+        sp += h1 ? 1 : 0;
+    }
+    bool finished = false;
+    if (nprims) {
+        const int kx = T.kx, ky = T.ky, kz = T.kz;
+        const float shx = T.shx, shy = T.shy, shz = T.shz;
         for (unsigned i = 0; i < nprims; i++) {
             const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
             const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
@@ -842,11 +839,9 @@ OSLD bool trav_run(const RenderScene& S, Trav& T, int budget)
         }
         // a shadow ray only asks "is anything strictly closer than tmax0": the closest-hit walk
         // can only move t further down from here, so the answer is already known
-        if (T.anyhit && result.t < T.tmax0) {
-            finished = true;
-            break;
-        }
-    }
+        finished = T.anyhit && result.t < T.tmax0;
+    } else
+        finished = sp == 0;
     T.sp  = sp;
     T.hit = result;
     return finished;
@@ -856,7 +851,7 @@ OSLD Hit scene_intersect(const RenderScene& S, unsigned* stk, int stride, V3 org
 {
     Trav T;
     trav_init(S, T, stk, stride, org, dir, tmax, skip1, skip2, anyhit);
-    while (!trav_run(S, T, 1 << 30)) {}
+    while (!trav_step(S, T, 1 << 30)) {}
     return T.hit;
 }
 
@@ -1320,7 +1315,10 @@ extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_const
 // while the other lanes keep walking (rays of very different length share a warp; without
 // this the warp idles on its longest ray: ncu showed 7 of 32 lanes active in round 1).
 #ifndef OSLD_TRACE_CHUNK
-#define OSLD_TRACE_CHUNK 32   // node / leaf visits between two refills (sweep: profiles/render_tune_r02.txt)
+#define OSLD_TRACE_CHUNK 8    // inner nodes a lane may walk per step before the leaf phase
+#endif
+#ifndef OSLD_TRACE_REFILL
+#define OSLD_TRACE_REFILL 16  // idle lanes that trigger a refill from the queues (sweep: profiles/render_tune_r02.txt)
 #endif
 #define OSLD_TRACE_BLOCK 128
 extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __grid_constant__ RenderLaunch L)
@@ -1339,51 +1337,51 @@ extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __
     int q = 0, slot = 0, phase = 0, flags = 0, vis = 0;
     Trav T;
     for (;;) {
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(0xffffffffu, !have);
-            if (need) {
-                const int leader = __ffs(need) - 1;
-                int base = 0;
-                if (lane == leader)
-                    base = atomicAdd(L.counters + C_FETCH, __popc(need));
-                base      = __shfl_sync(0xffffffffu, base, leader);
-                exhausted = base + __popc(need) >= n;
-                if (!have) {
-                    q = base + __popc(need & ((1u << lane) - 1u));
-                    if (q < n) {
-                        have = true;
-                        if (q < nlive) {
-                            slot = L.queue_in[q];
-                            const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-                            const float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
-                            phase = 0;
-                            trav_init(S, T, stk, stride, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y),
-                                      ~0u, 0);
+        unsigned hm = __ballot_sync(0xffffffffu, have);
+        if (!exhausted && __popc(hm) <= 32 - OSLD_TRACE_REFILL) {
+            const unsigned need = ~hm;
+            const int leader = __ffs(need) - 1;
+            int base = 0;
+            if (lane == leader)
+                base = atomicAdd(L.counters + C_FETCH, __popc(need));
+            base      = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + __popc(need) >= n;
+            if (!have) {
+                q = base + __popc(need & ((1u << lane) - 1u));
+                if (q < n) {
+                    have = true;
+                    if (q < nlive) {
+                        slot = L.queue_in[q];
+                        const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+                        const float4 q0 = rec[0], q1 = rec[1], q5 = rec[5];
+                        phase = 0;
+                        trav_init(S, T, stk, stride, xyz(q0), xyz(q1), OSLD_INF, (unsigned)__float_as_int(q5.y),
+                                  ~0u, 0);
+                    } else {
+                        slot = L.queue_sh[q - nlive];
+                        const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
+                        const float4* sh  = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
+                        const float4 q0 = rec[0], s0 = sh[0];
+                        const unsigned hid = (unsigned)__float_as_int(rec[5].y);
+                        flags = __float_as_int(s0.w);
+                        vis   = 0;
+                        if (flags & SH_BG) {
+                            phase = 1;
+                            trav_init(S, T, stk, stride, xyz(q0), xyz(s0), OSLD_INF, hid, ~0u, 1);
                         } else {
-                            slot = L.queue_sh[q - nlive];
-                            const float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
-                            const float4* sh  = L.shrec + (size_t)slot * OSLD_SHADOW_QUADS;
-                            const float4 q0 = rec[0], s0 = sh[0];
-                            const unsigned hid = (unsigned)__float_as_int(rec[5].y);
-                            flags = __float_as_int(s0.w);
-                            vis   = 0;
-                            if (flags & SH_BG) {
-                                phase = 1;
-                                trav_init(S, T, stk, stride, xyz(q0), xyz(s0), OSLD_INF, hid, ~0u, 1);
-                            } else {
-                                const float4 s2 = sh[2];
-                                phase = 2;
-                                trav_init(S, T, stk, stride, xyz(q0), xyz(s2), s2.w, hid,
-                                          (unsigned)__float_as_int(sh[3].w), 1);
-                            }
+                            const float4 s2 = sh[2];
+                            phase = 2;
+                            trav_init(S, T, stk, stride, xyz(q0), xyz(s2), s2.w, hid,
+                                      (unsigned)__float_as_int(sh[3].w), 1);
                         }
                     }
                 }
             }
+            hm = __ballot_sync(0xffffffffu, have);
         }
-        if (!__any_sync(0xffffffffu, have))
+        if (hm == 0u)
             break;
-        if (have && trav_run(S, T, OSLD_TRACE_CHUNK)) {
+        if (have && trav_step(S, T, OSLD_TRACE_CHUNK)) {
             if (phase == 0) {
                 float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
                 rec[4]      = make_float4(T.hit.t, T.hit.u, T.hit.v, __int_as_float((int)T.hit.id));

@@ -98,7 +98,7 @@ struct b200_render {
     b200_render_scene host;  // host-pointer copy of the description
     bool fma = true, sort = true;
     long long slots_target = 0;         // option slots=N: path slots in the pool (0 = default)
-    long long tail_paths   = 2048;      // option tail=N: at most N live paths -> rt_tail (0 = never)
+    long long tail_paths   = 8192;      // option tail=N: at most N live paths -> rt_tail (0 = never)
     std::vector<std::string> textures;  // the module's texture table, in slot order
     std::string texturepath;            // option texturepath=dir[:dir...]
     RenderModuleInfo info;              // what the module was specialised to
@@ -241,6 +241,8 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
         // tuning knobs of the integrator kernels (defaults in device/osl_b200_render.cuh)
         if (opt.count("chunk"))
             pre << "#define OSLD_TRACE_CHUNK " << atoi(opt["chunk"].c_str()) << "\n";
+        if (opt.count("refill"))
+            pre << "#define OSLD_TRACE_REFILL " << atoi(opt["refill"].c_str()) << "\n";
         if (opt.count("shade_blocks"))
             pre << "#define OSLD_SHADE_MINBLOCKS " << atoi(opt["shade_blocks"].c_str()) << "\n";
         if (opt.count("inline"))

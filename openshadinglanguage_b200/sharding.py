@@ -66,15 +66,25 @@ def tile_pixel_index(tiles, xres):
     return torch.cat(parts) if parts else torch.zeros(0, dtype=torch.int64)
 
 
-def gather_tiles(local, xres, yres, rank, world, tile=64):
+def gather_plan(xres, yres, world, device, tile=64):
+    """What rank 0 needs to reassemble a tile-sharded frame, computed once per (resolution, world):
+    per rank the work-set size and the flat image index of each of its pixels (on `device`)."""
+    sets = [rank_tiles(xres, yres, r, world, tile) for r in range(world)]
+    sizes = [sum(w * h for _, _, w, h in s) for s in sets]
+    return sizes, [tile_pixel_index(s, xres).to(device) for s in sets]
+
+
+def gather_tiles(local, xres, yres, rank, world, tile=64, plan=None):
     """Framebuffer gather of a tile-sharded render: every rank contributes its work set's
     [npix_local, 3] strip (device memory on GPUs: no host round trip); rank 0 receives the
     padded strips with one gather and scatters them into the [yres, xres, 3] image on its
-    device.  Returns the image on rank 0, None elsewhere."""
+    device.  Returns the image on rank 0, None elsewhere.  `plan`: gather_plan(...) result,
+    so that a renderer does not rebuild the (static) index tables every frame."""
     import torch
     import torch.distributed as dist
-    sets = [rank_tiles(xres, yres, r, world, tile) for r in range(world)]
-    sizes = [sum(w * h for _, _, w, h in s) for s in sets]
+    if plan is None:
+        plan = gather_plan(xres, yres, world, local.device if rank == 0 else "cpu", tile)
+    sizes, index = plan
     longest = max(sizes)
     if local.shape[0] == longest:
         pad = local.contiguous()
@@ -87,6 +97,6 @@ def gather_tiles(local, xres, yres, rank, world, tile=64):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.gather(pad, bufs, dst=0)
     img = torch.empty((yres * xres, 3), dtype=local.dtype, device=local.device)
-    for s, n, buf in zip(sets, sizes, bufs):
-        img[tile_pixel_index(s, xres).to(local.device)] = buf[:n]
+    for idx, n, buf in zip(index, sizes, bufs):
+        img[idx] = buf[:n]
     return img.reshape(yres, xres, 3)

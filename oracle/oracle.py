@@ -174,6 +174,34 @@ def build_shadeops():
     return so
 
 
+def build_bsdl_check():
+    """Compile oracle_bsdl_check.cpp -> oracle/_build/liboracle_bsdl_check.so (the restated libbsdl
+    lobes behind the signature of oracle/ref_bsdl.cpp)."""
+    import subprocess
+    here = oso2cpp.HERE
+    bdir = os.path.join(here, "_build")
+    os.makedirs(bdir, exist_ok=True)
+    so = os.path.join(bdir, "liboracle_bsdl_check.so")
+    srcs = [os.path.join(here, "oracle_bsdl_check.cpp")] + [os.path.join(here, f) for f in sorted(os.listdir(here))
+                                                            if f.endswith(".h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        r = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                            "-I", here, srcs[0], "-o", so + ".tmp"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle bsdl check compile failed:\n" + r.stderr[:4000])
+        os.replace(so + ".tmp", so)
+    return so
+
+
+BSDL_LUTS = os.path.join(os.path.dirname(oso2cpp.HERE), "openshadinglanguage_b200", "data", "bsdl_luts.bin")
+
+
+def bsdl_luts():
+    """The energy tables of the libbsdl microfacet lobes (float32, layout in osl_oracle_mxlobes.h):
+    data baked by tools/bake_bsdl_luts.cpp and shipped with the product."""
+    return np.fromfile(BSDL_LUTS, np.float32)
+
+
 def shadeops():
     global _shadeops
     if _shadeops is None:
@@ -392,6 +420,10 @@ class OracleRender:
         self.lib = ctypes.CDLL(self.so)
         self.lib.oracle_render.argtypes = [ctypes.POINTER(RenderScene), ctypes.c_void_p, ctypes.c_int]
         register_textures(self.lib, self.textures)
+        if os.path.exists(BSDL_LUTS):
+            self._luts = bsdl_luts()
+            self.lib.oracle_set_bsdl_luts.argtypes = [ctypes.c_void_p]
+            self.lib.oracle_set_bsdl_luts(self._luts.ctypes.data)
 
     def render(self, xres, yres, aa, nthreads=None, **kw):
         rs, keep = fill_render_scene(RenderScene, self.scene, self.arrays, xres, yres, aa, **kw)

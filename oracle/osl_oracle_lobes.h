@@ -566,6 +566,16 @@ inline BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi)
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_eval(l, wo, wi);
     case LOBE_BSDL_SHEEN: return lobes::sheen_eval(l, wo, wi);
+    case LOBE_MX_SPEC: {   // BSDL_WRAP::eval (shading.cpp:88-93)
+        BSample s = mx_eval_local(l.mx, l.tf.tolocal(wo), l.tf.tolocal(wi));
+        return BSample(wi, s.weight, s.pdf, s.roughness);
+    }
+    case LOBE_MX_TRANSLUCENT: {
+        const V3 wi_l = l.tf.tolocal(wi);
+        if (wi_l.z >= 0.0f)
+            return BSample(wi, V3(0.0f), 0, 0);
+        return BSample(wi, l.albedo, std::fabs(wi_l.z) * (1 / float(M_PI)), 1.0f);
+    }
     }
     return BSample();
 }
@@ -578,6 +588,17 @@ inline BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return lobes::bsdl_diffuse_sample(l, wo, rx, ry);
     case LOBE_BSDL_SHEEN: return lobes::sheen_sample(l, wo, rx, ry);
+    case LOBE_MX_SPEC: {   // BSDL_WRAP::sample (shading.cpp:94-101)
+        BSample s = mx_sample_local(l.mx, l.tf.tolocal(wo), rx, ry, rz);
+        return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
+    }
+    case LOBE_MX_TRANSLUCENT: {
+        V3 wi_l = lobes::bsdl_sample_cos_hemisphere(rx, ry);
+        wi_l.z  = -wi_l.z;
+        if (wi_l.z >= 0.0f)
+            return BSample(l.tf.toworld(V3(0.0f)), V3(0.0f), 0, 0);
+        return BSample(l.tf.toworld(wi_l), l.albedo, std::fabs(wi_l.z) * (1 / float(M_PI)), 1.0f);
+    }
     }
     return BSample();
 }

@@ -324,7 +324,12 @@ enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION
                 LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET,
                 LOBE_BSDL_OREN_NAYAR /* libbsdl mtx::OrenNayarDiffuseLobe through BSDL_WRAP */,
                 LOBE_BSDL_BURLEY /* mtx::BurleyDiffuseLobe */,
-                LOBE_BSDL_SHEEN /* mtx::SheenLobe, Conty-Kulla mode */ };
+                LOBE_BSDL_SHEEN /* mtx::SheenLobe, Conty-Kulla mode */,
+                LOBE_MX_SPEC /* mtx::ConductorLobe / DielectricLobe / SchlickLobe */,
+                LOBE_MX_TRANSLUCENT /* mtx::TranslucentLobe */ };
+}  // namespace oslo
+#include "osl_oracle_mxlobes.h"
+namespace oslo {
 struct Lobe;
 // Phong / Ward / Microfacet live in osl_oracle_lobes.h
 V3 ext_albedo(const Lobe& l, const V3& wo);
@@ -345,6 +350,7 @@ struct Lobe {
     float emiss = 1.0f;
     bool backfacing = false;
     TangentFrame tf;
+    MxSpec mx;   // conductor / dielectric / generalized schlick state (LOBE_MX_SPEC)
     V3 get_albedo(const V3& wo) const
     {
         switch (type) {
@@ -361,6 +367,8 @@ struct Lobe {
         case LOBE_BSDL_OREN_NAYAR:
         case LOBE_BSDL_BURLEY: return albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
         case LOBE_BSDL_SHEEN: return albedo * (1 - emiss);
+        case LOBE_MX_SPEC: return mx_albedo(mx);
+        case LOBE_MX_TRANSLUCENT: return albedo;
         default: return V3(1.0f);
         }
     }
@@ -496,6 +504,27 @@ inline bool sheen_from_component(Lobe& l, const ClosComp* comp, const SG& sg, fl
     lobes::sheen_setup(l, -sg.I.val, comp->params[6], sg.backfacing != 0, path_roughness);
     return f2u(comp->params[7]) == 0;   // mode 1 (Zeltner LTC sheen) is not restated
 }
+// mtx::ConductorLobe / DielectricLobe / SchlickLobe from their closure components (parameter
+// order = the Data structs' registration order; the distribution string takes one word)
+inline void mx_from_component(Lobe& l, const ClosComp* comp, const SG& sg, float path_roughness)
+{
+    const float* p = comp->params;
+    const V3 wo    = -sg.I.val;
+    l.type         = LOBE_MX_SPEC;
+    l.N            = V3(p[0], p[1], p[2]);
+    const V3 Z     = lobes::bsdl_visible_normal(wo, l.N, l.N);
+    l.tf           = lobes::bsdl_frame_zx(Z, V3(p[3], p[4], p[5]));
+    const float cosNO     = dot(Z, wo);
+    const bool backfacing = sg.backfacing != 0;
+    if (comp->id == MX_CONDUCTOR_ID)
+        l.mx = mx_conductor_setup(cosNO, p[6], p[7], V3(p[8], p[9], p[10]), V3(p[11], p[12], p[13]), path_roughness);
+    else if (comp->id == MX_DIELECTRIC_ID)
+        l.mx = mx_dielectric_setup(cosNO, V3(p[6], p[7], p[8]), V3(p[9], p[10], p[11]), p[12], p[13], p[14],
+                                   V3(p[18], p[19], p[20]), backfacing, path_roughness);
+    else
+        l.mx = mx_schlick_setup(cosNO, V3(p[6], p[7], p[8]), V3(p[9], p[10], p[11]), p[12], p[13],
+                                V3(p[14], p[15], p[16]), V3(p[17], p[18], p[19]), p[20], backfacing, path_roughness);
+}
 // evaluate_layer_opacity (shading.cpp:1198-1282): how much of the light the top stack of a
 // layer() takes; returns the weight held when the walk ends, as the reference does
 inline V3 evaluate_layer_opacity(const SG& sg, float path_roughness, const Clos* closure)
@@ -542,6 +571,23 @@ inline V3 evaluate_layer_opacity(const SG& sg, float path_roughness, const Clos*
                 sheen_from_component(l, comp, sg, path_roughness);
                 weight  = weight * (w * (V3(1.0f) - V3(l.emiss)));
                 closure = nullptr;
+                break;
+            }
+            case MX_DIELECTRIC_ID: {
+                Lobe l;
+                mx_from_component(l, comp, sg, path_roughness);
+                weight  = weight * (w * (V3(1.0f) - mx_filter_o(l.mx, false)));
+                closure = nullptr;
+                break;
+            }
+            case MX_GENERALIZED_SCHLICK_ID: {
+                closure = nullptr;
+                // transmissive dielectrics are opaque to the layer below
+                if (!(comp->params[9] == 0 && comp->params[10] == 0 && comp->params[11] == 0))
+                    break;
+                Lobe l;
+                mx_from_component(l, comp, sg, path_roughness);
+                weight = weight * (w * (V3(1.0f) - mx_filter_o(l.mx, true)));
                 break;
             }
             default: closure = nullptr; break;   // unhandled BSDFs are opaque
@@ -619,6 +665,22 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                     break;
                 }
                 case MX_SHEEN_ID: known = sheen_from_component(l, comp, sg, path_roughness); break;
+                case MX_CONDUCTOR_ID:
+                case MX_DIELECTRIC_ID:
+                case MX_GENERALIZED_SCHLICK_ID: mx_from_component(l, comp, sg, path_roughness); break;
+                case MX_TRANSLUCENT_ID: {
+                    // params: N, albedo (bsdf_translucent_impl.h): cosine lobe on the far side
+                    l.type   = LOBE_MX_TRANSLUCENT;
+                    l.albedo = V3(comp->params[3], comp->params[4], comp->params[5]);
+                    l.tf     = TangentFrame::from_normal(lobes::bsdl_visible_normal(-sg.I.val, l.N, l.N));
+                    break;
+                }
+                case MX_SUBSURFACE_ID: {
+                    // no BSSRDF in testrender: a diffuse lobe weighted by the albedo (shading.cpp:1626-1635)
+                    l.type = LOBE_DIFFUSE;
+                    cw     = cw * V3(comp->params[3], comp->params[4], comp->params[5]);
+                    break;
+                }
                 case MX_LAYER_ID: {
                     // layer(top, base): the base is attenuated by what the top stack takes
                     // (shading.cpp:1645-1661)

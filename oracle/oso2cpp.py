@@ -364,13 +364,22 @@ CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
             ("oren_nayar_diffuse_bsdf", 3): "MX_OREN_NAYAR_DIFFUSE_ID",
             ("burley_diffuse_bsdf", 3): "MX_BURLEY_DIFFUSE_ID",
             ("sheen_bsdf", 3): "MX_SHEEN_ID", ("layer", 2): "MX_LAYER_ID",
-            ("uniform_edf", 1): "MX_UNIFORM_EDF_ID"}
+            ("uniform_edf", 1): "MX_UNIFORM_EDF_ID",
+            ("conductor_bsdf", 7): "MX_CONDUCTOR_ID", ("dielectric_bsdf", 8): "MX_DIELECTRIC_ID",
+            ("generalized_schlick_bsdf", 10): "MX_GENERALIZED_SCHLICK_ID",
+            ("translucent_bsdf", 2): "MX_TRANSLUCENT_ID",
+            ("subsurface_bssrdf", 4): "MX_SUBSURFACE_ID"}
 # keyword parameters per closure id, in slot order after the positional words; value
 # type "int" / "float".  Unspecified keywords are zero (llvm_gen_closure memsets the
 # parameter block when there is no prepare callback).  String keywords ("label") have
 # no effect on this path and take no slot.
 CLOSURE_KEYS = {"MX_OREN_NAYAR_DIFFUSE_ID": [("energy_compensation", "int")],
-                "MX_SHEEN_ID": [("mode", "int")]}
+                "MX_SHEEN_ID": [("mode", "int")],
+                # libbsdl Data structs: bsdf_conductor_decl.h:43-46, bsdf_dielectric_decl.h:112-120
+                "MX_CONDUCTOR_ID": [("thinfilm_thickness", "float"), ("thinfilm_ior", "float")],
+                "MX_DIELECTRIC_ID": [("thinfilm_thickness", "float"), ("thinfilm_ior", "float"),
+                                     ("absorption", "color"), ("dispersion", "float")]}
+KEY_WORDS = {"int": 1, "float": 1, "color": 3}
 
 
 class Gen:
@@ -1386,7 +1395,7 @@ class Gen:
             if kw[j].t.base == "string" and kw[j].constval:
                 given[kw[j].vals[0]] = kw[j + 1]
         key_base = nwords
-        nwords += len(keys)
+        nwords += sum(KEY_WORDS[t] for _, t in keys)
         wexpr = "nullptr"
         if weight is not None:
             self.w("V3 w_; assign(w_, %s);" % self.R(weight))
@@ -1400,15 +1409,18 @@ class Gen:
                 e = "nd(%s)" % e
             self.w("    putp(c_->params + %d, %s);" % (off, e))
             off += wsize(a)
-        for k, (kname, ktype) in enumerate(keys):
+        koff = key_base
+        for kname, ktype in keys:
             a = given.get(kname)
             if a is not None and a.t.base == ktype and not a.t.arr:
                 e = self.R(a)
                 if a.has_derivs:
                     e = "nd(%s)" % e
-                self.w("    putp(c_->params + %d, %s);" % (key_base + k, e))
+                self.w("    putp(c_->params + %d, %s);" % (koff, e))
             else:
-                self.w("    putp(c_->params + %d, %s);" % (key_base + k, "0" if ktype == "int" else "0.0f"))
+                zero = {"int": "0", "float": "0.0f", "color": "V3(0.0f)"}[ktype]
+                self.w("    putp(c_->params + %d, %s);" % (koff, zero))
+            koff += KEY_WORDS[ktype]
         self.w("}")
         self.w("%s = c_;" % self.R(d))
 
@@ -1456,6 +1468,8 @@ extern "C" void oracle_texture_add(const char* name, int w, int h, int nch, cons
 {
     oracle_texture_add_impl(name, w, h, nch, px);
 }
+// energy tables of the libbsdl microfacet lobes (data; see osl_oracle_mxlobes.h)
+extern "C" void oracle_set_bsdl_luts(const float* p) { bsdl_luts() = p; }
 static const Background* g_background = nullptr;
 static void oracle_render_rows(const RenderScene* S, int y0, int y1, float* out, std::string* pf)
 {
