@@ -103,6 +103,26 @@ typedef struct b200_symloc {
     int derivs;
 } b200_symloc;
 
+/* Userdata the renderer supplies per point for interpolated ([[ int lockgeom = 0 ]])
+ * parameters: SymLocationDesc with arena = UserData (oslexec.h:69-105) and the "found" result of
+ * RendererServices::get_userdata (rendererservices.h; osl_bind_interpolated_param,
+ * src/liboslexec/llvm_instance.cpp:805-970).  The value of point i lies at
+ *   userdata_base + offset + stride * shadeindex      (val[,dx,dy] contiguous when derivs)
+ * so one dense array per name (stride = element size) gives coalesced loads.  A parameter binds
+ * to the entry of the same name and type; points whose int32 at
+ *   userdata_base + valid_offset + valid_stride * shadeindex
+ * is zero (valid_offset >= 0) do not have the value and run the parameter's default / init ops,
+ * like a get_userdata() that returns false for them. */
+typedef struct b200_userdata {
+    const char* name;
+    int ncomp;               /* 1 (float, int) or 3 (color, point, vector, normal) */
+    int is_int;
+    long long offset, stride;
+    int derivs;
+    long long valid_offset;  /* < 0: every point has the value */
+    long long valid_stride;
+} b200_userdata;
+
 /* ShaderGroupBegin ... ShaderGroupEnd (oslexec.h:634-650) */
 typedef struct b200_group_desc {
     const char* name;
@@ -116,6 +136,8 @@ typedef struct b200_group_desc {
      *   fma=0|1   allow FMA contraction (reference: llvm_jit_fma, default 0 scalar / 1 batched)
      *   block=N   CTA size (default 256) */
     const char* options;
+    int nuserdata;                 /* may be 0 */
+    const b200_userdata* userdata;
 } b200_group_desc;
 
 typedef struct b200_group b200_group;
@@ -154,6 +176,11 @@ int b200_group_execute(b200_group* g, int device, void* stream, long long npoint
  * makes the copies asynchronous; pageable memory works but serialises. */
 int b200_group_execute_host(b200_group* g, int device, long long npoints,
                             const b200_globals* sg, void* output_base);
+
+/* execute_host for a group with userdata: the userdata arena (HOST memory, userdata_bytes
+ * long) is uploaded once per call, then as above. */
+int b200_group_execute_host_userdata(b200_group* g, int device, long long npoints, const b200_globals* sg,
+                                     const void* userdata_base, long long userdata_bytes, void* output_base);
 
 /* Text written by the group's printf() ops on `device` since the previous call, ordered by
  * shade index and, within a point, by execution order (what single-threaded testshade

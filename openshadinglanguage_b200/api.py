@@ -59,11 +59,46 @@ class _SymLoc(ctypes.Structure):
                 ("stride", ctypes.c_longlong), ("derivs", ctypes.c_int)]
 
 
+class _UserData(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("ncomp", ctypes.c_int), ("is_int", ctypes.c_int),
+                ("offset", ctypes.c_longlong), ("stride", ctypes.c_longlong), ("derivs", ctypes.c_int),
+                ("valid_offset", ctypes.c_longlong), ("valid_stride", ctypes.c_longlong)]
+
+
 class _GroupDesc(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char_p), ("nlayers", ctypes.c_int),
                 ("layers", ctypes.POINTER(_Layer)), ("nconnections", ctypes.c_int),
                 ("connections", ctypes.POINTER(_Connection)), ("noutputs", ctypes.c_int),
-                ("outputs", ctypes.POINTER(_SymLoc)), ("options", ctypes.c_char_p)]
+                ("outputs", ctypes.POINTER(_SymLoc)), ("options", ctypes.c_char_p),
+                ("nuserdata", ctypes.c_int), ("userdata", ctypes.POINTER(_UserData))]
+
+
+def pack_userdata(entries):
+    """Lay named per-point userdata out as one arena (b200_userdata, include/osl_b200.h).
+    entries: list of dict(name, data [n, ncomp] float32 (or [n, 3*ncomp] = val,dx,dy with
+    derivs=True) or int32 [n]; valid=int32[n] marks the points that have the value).
+    -> (arena uint8 numpy array, list of descriptor dicts for ShaderGroup(userdata=...)).
+    One dense array per entry (stride = its row size), so a warp's loads coalesce."""
+    blobs, descs, off = [], [], 0
+    for e in entries:
+        a = np.ascontiguousarray(e["data"])
+        is_int = a.dtype.kind in "iu"
+        a = a.astype(np.int32 if is_int else np.float32).reshape(len(a), -1)
+        derivs = bool(e.get("derivs"))
+        d = dict(name=e["name"], ncomp=a.shape[1] // (3 if derivs else 1), is_int=int(is_int), offset=off,
+                 stride=a.shape[1] * 4, derivs=int(derivs), valid_offset=-1, valid_stride=0)
+        b = a.tobytes()
+        b = b.ljust((len(b) + 15) // 16 * 16, b"\0")
+        blobs.append(b)
+        off += len(b)
+        if e.get("valid") is not None:
+            v = np.ascontiguousarray(e["valid"], np.int32).tobytes()
+            v = v.ljust((len(v) + 15) // 16 * 16, b"\0")
+            d["valid_offset"], d["valid_stride"] = off, 4
+            blobs.append(v)
+            off += len(v)
+        descs.append(d)
+    return np.frombuffer(b"".join(blobs) or b"\0" * 16, np.uint8).copy(), descs
 
 
 _lib = None
@@ -173,7 +208,9 @@ class ShaderGroup:
     options:      'fma=0' selects strict IEEE evaluation (bit-parity mode)
     """
 
-    def __init__(self, layers, connections=(), outputs=(), options="", name="group"):
+    def __init__(self, layers, connections=(), outputs=(), options="", name="group", userdata=()):
+        """userdata: descriptor dicts (pack_userdata) of the per-point values the renderer supplies
+        for interpolated ([[ int lockgeom = 0 ]]) parameters."""
         L = lib()
         keep = []
 
@@ -210,8 +247,13 @@ class ShaderGroup:
         for i, o in enumerate(outputs):
             cout[i].name, cout[i].offset, cout[i].stride = cs(o["name"]), int(o["offset"]), int(o["stride"])
             cout[i].derivs = 1 if o.get("derivs") else 0
+        cud = (_UserData * max(1, len(userdata)))()
+        for i, u in enumerate(userdata):
+            cud[i].name, cud[i].ncomp, cud[i].is_int = cs(u["name"]), int(u["ncomp"]), int(u["is_int"])
+            cud[i].offset, cud[i].stride, cud[i].derivs = int(u["offset"]), int(u["stride"]), int(u["derivs"])
+            cud[i].valid_offset, cud[i].valid_stride = int(u["valid_offset"]), int(u["valid_stride"])
         desc = _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, len(outputs), cout,
-                          cs(options))
+                          cs(options), len(userdata), cud)
         h = ctypes.c_void_p()
         _check(L.b200_group_compile(ctypes.byref(desc), ctypes.byref(h)))
         self._h = h
@@ -244,15 +286,15 @@ class ShaderGroup:
         return bool(lib().b200_group_reads_global(self._h, SG_FIELDS.index(name)))
 
     def execute(self, n, varying, uniform, output, shadeindex=None, device=0, stream=None,
-                plane_stride=None):
-        """Device-pointer path (b200_group_execute).  varying values and output
-        are CUDA tensors (or raw device addresses).  Asynchronous."""
+                plane_stride=None, userdata=None):
+        """Device-pointer path (b200_group_execute).  varying values, output and the userdata
+        arena are CUDA tensors (or raw device addresses).  Asynchronous."""
         g = _fill_globals(n, varying, uniform, plane_stride)
         if stream is None:
             import torch
             stream = torch.cuda.current_stream(device).cuda_stream
         _check(lib().b200_group_execute(self._h, device, ctypes.c_void_p(stream), n, ctypes.byref(g),
-                                        _ptr(shadeindex), None, _ptr(output)))
+                                        _ptr(shadeindex), _ptr(userdata), _ptr(output)))
 
     def bind(self, n, varying, uniform, output, shadeindex=None, device=0, stream=None, plane_stride=None):
         """-> zero-argument callable that issues b200_group_execute with the globals block,
@@ -271,11 +313,19 @@ class ShaderGroup:
                 _check(rc)
         return launch
 
-    def execute_host(self, n, varying, uniform, output, device=0, plane_stride=None):
-        """Host-pointer path (b200_group_execute_host): numpy arrays or pinned
+    def execute_host(self, n, varying, uniform, output, device=0, plane_stride=None, userdata=None):
+        """Host-pointer path (b200_group_execute_host[_userdata]): numpy arrays or pinned
         CPU tensors in, host output arena out.  Synchronous."""
         g = _fill_globals(n, varying, uniform, plane_stride)
-        _check(lib().b200_group_execute_host(self._h, device, n, ctypes.byref(g), _ptr(output)))
+        if userdata is None:
+            _check(lib().b200_group_execute_host(self._h, device, n, ctypes.byref(g), _ptr(output)))
+        else:
+            L = lib()
+            L.b200_group_execute_host_userdata.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                                           ctypes.c_void_p]
+            _check(L.b200_group_execute_host_userdata(self._h, device, n, ctypes.byref(g), _ptr(userdata),
+                                                      int(userdata.nbytes), _ptr(output)))
 
     def journal(self, device=0):
         """Text printed by the group's printf() ops since the previous call, in shade index
@@ -362,7 +412,7 @@ def _group_desc(layers, connections, name, options, keep):
     for i, (a, b, c, d) in enumerate(connections):
         cconn[i].srclayer, cconn[i].srcparam, cconn[i].dstlayer, cconn[i].dstparam = cs(a), cs(b), cs(c), cs(d)
     keep += [clayers, cconn]
-    return _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, 0, None, cs(options))
+    return _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, 0, None, cs(options), 0, None)
 
 
 class Renderer:

@@ -26,6 +26,10 @@ enum ClosureIDs {
 #ifndef OSLD_POOL_WORDS
 #define OSLD_POOL_WORDS 256  // 1 KB, the reference's StackClosurePool size
 #endif
+// Storage behind a pool: the allocatable words plus a few words of slack, because the closure
+// tree walkers read "the normal" (3 words after the header) of a component before they look at
+// its id, and the last component of a tightly sized arena may be shorter than that.
+#define OSLD_POOL_STORE (OSLD_POOL_WORDS + 4)
 
 // Word i of a thread's arena sits at p[i * s]: s = 1 for a private (local-memory) array,
 // s = CTA size when the arenas of a CTA are staged in shared memory, interleaved by thread

@@ -267,6 +267,37 @@ OSLD void lobe_set_bsdl_frame(Lobe& l, V3 wo)
     l.fv           = f.v;
     l.N            = f.w;
 }
+#ifdef OSLD_MX_LOBES
+// mtx::ConductorLobe / DielectricLobe / SchlickLobe from their closure components (parameter
+// order = the libbsdl Data structs' registration order; the distribution string takes one word).
+// Frame(Z = visible normal, X = U) (tools.h:483-495).
+OSLD void mx_from_component(const float* luts, Lobe& l, int id, PoolPtr p, V3 wo, bool backfacing, float path_roughness)
+{
+    l.type = LOBE_MX_SPEC;
+    l.N    = mkv(p[0], p[1], p[2]);
+    const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
+    const V3 X = mkv(p[3], p[4], p[5]);
+    if (bsdl_max_abs_xyz(X) < 1e-4f || fabsf(dot3(Z, vnormalized(X))) > 0.999f) {
+        TangentFrame f = frame_from_normal(Z);
+        l.fu           = f.u;
+        l.fv           = f.v;
+    } else {
+        l.fv = vnormalized(cross3(Z, X));
+        l.fu = cross3(l.fv, Z);
+    }
+    l.N               = Z;
+    const float cosNO = dot3(Z, wo);
+    if (id == MX_CONDUCTOR_ID)
+        l.mx = mx_conductor_setup(luts, cosNO, p[6], p[7], mkv(p[8], p[9], p[10]), mkv(p[11], p[12], p[13]),
+                                  path_roughness);
+    else if (id == MX_DIELECTRIC_ID)
+        l.mx = mx_dielectric_setup(luts, cosNO, mkv(p[6], p[7], p[8]), mkv(p[9], p[10], p[11]), p[12], p[13], p[14],
+                                   mkv(p[18], p[19], p[20]), backfacing, path_roughness);
+    else
+        l.mx = mx_schlick_setup(luts, cosNO, mkv(p[6], p[7], p[8]), mkv(p[9], p[10], p[11]), p[12], p[13],
+                                mkv(p[14], p[15], p[16]), mkv(p[17], p[18], p[19]), p[20], backfacing, path_roughness);
+}
+#endif
 // tools.h:200-278
 OSLD V3 bsdl_sample_cos_hemisphere(float randu, float randv)
 {

@@ -68,6 +68,8 @@ struct RenderScene {
     // The leaf loop reads them with three contiguous 16-byte loads instead of the reference's
     // index -> triangle -> vertex gather (same values, one dependent load level instead of three).
     const float4* leaf_tris;
+    // energy-compensation tables of the MaterialX microfacet closures (osl_b200_mxlobes.cuh), or null
+    const float* bsdl_luts;
 };
 
 // Path state: one 128-byte record (8 x float4) per path slot.  After the live
@@ -334,7 +336,13 @@ OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
 }
 #define OSLD_INF __int_as_float(0x7f800000)
 enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
-       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY, LOBE_BSDL_SHEEN };
+       LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY, LOBE_BSDL_SHEEN,
+       LOBE_MX_SPEC /* conductor / dielectric / generalized schlick */, LOBE_MX_TRANSLUCENT };
+}  // namespace osld
+#ifdef OSLD_MX_LOBES
+#include "osl_b200_mxlobes.cuh"
+#endif
+namespace osld {
 struct Lobe {
     int type;
     V3 N;
@@ -347,6 +355,9 @@ struct Lobe {
     float ax, ay;
     int refract, ggx;
     V3 albedo;
+#endif
+#ifdef OSLD_MX_LOBES
+    MxSpec mx;   // LOBE_MX_SPEC: frame in (fu, fv, N)
 #endif
 };
 }  // namespace osld
@@ -363,6 +374,12 @@ OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
         return l.albedo;  // BSDL_WRAP::get_albedo = albedo_impl().toRGB(0)
     if (l.type == LOBE_BSDL_SHEEN)
         return l.albedo * (1 - l.eta);  // tint * (1 - Emiss)
+#endif
+#ifdef OSLD_MX_LOBES
+    if (l.type == LOBE_MX_SPEC)
+        return mx_albedo(l.mx);
+    if (l.type == LOBE_MX_TRANSLUCENT)
+        return l.albedo;
 #endif
     if (l.type == LOBE_REFLECTION) {
         float cosNO = dot3(l.N, wo);
@@ -389,6 +406,19 @@ OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
         return bsdl_diffuse_eval(l, wo, wi);
     if (l.type == LOBE_BSDL_SHEEN)
         return sheen_eval(l, wo, wi);
+#endif
+#ifdef OSLD_MX_LOBES
+    if (l.type == LOBE_MX_SPEC) {   // BSDL_WRAP::eval (shading.cpp:88-93)
+        BSample s = mx_eval_local(l.mx, frame_tolocal(l, wo), frame_tolocal(l, wi));
+        s.wi      = wi;
+        return s;
+    }
+    if (l.type == LOBE_MX_TRANSLUCENT) {   // mtx::TranslucentLobe (bsdf_translucent_impl.h)
+        const float z = dot3(wi, l.N);
+        if (z >= 0.0f)
+            return bs_make(wi, mkv(0.0f), 0.0f, 0.0f);
+        return bs_make(wi, l.albedo, fabsf(z) * (1 / (float)OSLD_PI), 1.0f);
+    }
 #endif
     return bs_null();
 }
@@ -422,6 +452,20 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
     case LOBE_BSDL_OREN_NAYAR:
     case LOBE_BSDL_BURLEY: return bsdl_diffuse_sample(l, wo, rx, ry);
     case LOBE_BSDL_SHEEN: return sheen_sample(l, wo, rx, ry);
+#endif
+#ifdef OSLD_MX_LOBES
+    case LOBE_MX_SPEC: {   // BSDL_WRAP::sample (shading.cpp:94-101)
+        BSample s = mx_sample_local(l.mx, frame_tolocal(l, wo), rx, ry, rz);
+        s.wi      = frame_toworld(l, s.wi);
+        return s;
+    }
+    case LOBE_MX_TRANSLUCENT: {
+        V3 wi_l = bsdl_sample_cos_hemisphere(rx, ry);
+        wi_l.z  = -wi_l.z;
+        if (wi_l.z >= 0.0f)
+            return bs_make(frame_toworld(l, mkv(0.0f)), mkv(0.0f), 0.0f, 0.0f);
+        return bs_make(frame_toworld(l, wi_l), l.albedo, fabsf(wi_l.z) * (1 / (float)OSLD_PI), 1.0f);
+    }
 #endif
     default: return bs_make(-wo, mkv(1.0f), OSLD_INF, 0.0f);
     }
@@ -495,7 +539,8 @@ OSLD BSample bsdf_sample(const CompositeBSDF& B, V3 wo, float rx, float ry, floa
 #ifdef OSLD_GLOSSY_LOBES
 // evaluate_layer_opacity (shading.cpp:1198-1282): what the top stack of a layer() takes;
 // returns the weight held when the walk ends, as the reference does
-OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool backfacing, float path_roughness)
+OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool backfacing, float path_roughness,
+                               const float* luts)
 {
     if (!closure)
         return mkv(0.0f);
@@ -532,6 +577,19 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
                 l.albedo = mkv(q[3], q[4], q[5]);
                 sheen_setup(l, wo, q[6], backfacing, path_roughness);
                 weight = weight * (w * (mkv(1.0f) - mkv(l.eta)));
+#ifdef OSLD_MX_LOBES
+            } else if (id == MX_DIELECTRIC_ID) {
+                Lobe l;
+                mx_from_component(luts, l, id, q, wo, backfacing, path_roughness);
+                weight = weight * (w * (mkv(1.0f) - mx_filter_o(l.mx, false)));
+            } else if (id == MX_GENERALIZED_SCHLICK_ID) {
+                // transmissive dielectrics are opaque to the layer below
+                if (q[9] == 0 && q[10] == 0 && q[11] == 0) {
+                    Lobe l;
+                    mx_from_component(luts, l, id, q, wo, backfacing, path_roughness);
+                    weight = weight * (w * (mkv(1.0f) - mx_filter_o(l.mx, true)));
+                }
+#endif
             }  // anything else: opaque
         }
         if (closure == 0 && sp > 0) {
@@ -545,7 +603,8 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
 
 // closure tree -> emission + lobes (16-deep explicit stack, weights root->leaf)
 OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only,
-                          V3 wo = mkv(0.0f, 0.0f, 1.0f), bool backfacing = false, float path_roughness = 0.0f)
+                          V3 wo = mkv(0.0f, 0.0f, 1.0f), bool backfacing = false, float path_roughness = 0.0f,
+                          const float* luts = nullptr)
 {
     int ptr_stack[OSLD_CLOSURE_STACK];
     V3 weight_stack[OSLD_CLOSURE_STACK];
@@ -597,11 +656,27 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                     sheen_setup(l, wo, q[6], backfacing, path_roughness);
                     known = __float_as_int(q[7]) == 0;
                     break;
+#ifdef OSLD_MX_LOBES
+                case MX_CONDUCTOR_ID:
+                case MX_DIELECTRIC_ID:
+                case MX_GENERALIZED_SCHLICK_ID: mx_from_component(luts, l, id, q, wo, backfacing, path_roughness); break;
+                case MX_TRANSLUCENT_ID:
+                    // params: N, albedo: a cosine lobe on the far side of the visible normal
+                    l.type   = LOBE_MX_TRANSLUCENT;
+                    l.albedo = mkv(q[3], q[4], q[5]);
+                    lobe_set_bsdl_frame(l, wo);
+                    break;
+                case MX_SUBSURFACE_ID:
+                    // no BSSRDF in testrender: a diffuse lobe weighted by the albedo (shading.cpp:1626-1635)
+                    l.type = LOBE_DIFFUSE;
+                    cw     = cw * mkv(q[3], q[4], q[5]);
+                    break;
+#endif
                 case MX_LAYER_ID: {
                     // layer(top, base): the base is attenuated by what the top stack takes
                     // (shading.cpp:1645-1661)
                     const int top = __float_as_int(q[0]), base = __float_as_int(q[1]);
-                    V3 op     = evaluate_layer_opacity(pool, top, wo, backfacing, path_roughness);
+                    V3 op     = evaluate_layer_opacity(pool, top, wo, backfacing, path_roughness, luts);
                     op        = mkv(fminf(fmaxf(op.x, 0.f), 1.f), fminf(fmaxf(op.y, 0.f), 1.f), fminf(fmaxf(op.z, 0.f), 1.f));
                     V3 base_w = weight * (mkv(1.0f) - op);
                     closure   = top;
@@ -1148,7 +1223,7 @@ OSLD void queue_push(int* queue, int* counter, int value, bool pred)
     pool.bind(reinterpret_cast<float*>(smem_words) + threadIdx.x, blockDim.x)
 #else
 #define OSLD_POOL_DECL(pool, smem_words)     \
-    float pool##_store_[OSLD_POOL_WORDS];    \
+    float pool##_store_[OSLD_POOL_STORE];    \
     ClosurePool pool;                        \
     pool.bind(pool##_store_, 1)
 #endif
@@ -1538,7 +1613,7 @@ OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
         CompositeBSDF bsdf;
         bsdf.num               = 0;
         const bool last_bounce = b == S.max_bounces;
-        process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness);
+        process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness, S.bsdl_luts);
         const int nlights = S.nlightprims;
         float k           = 1;
         if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {
@@ -1733,7 +1808,7 @@ extern "C" __global__ void __launch_bounds__(32) rt_tail(const __grid_constant__
         return;
     const RenderScene& S = L.S;
     unsigned* const stk  = smem_;
-    OSLD_POOL_DECL(pool, smem_ + OSLD_STK_WORDS * OSLD_BVH_STACK * 32);
+    OSLD_POOL_DECL(pool, smem_ + OSLD_STK_WORDS * OSLD_BVH_STACK * 32);   // OSLD_POOL_STORE words per thread
     const int n = L.counters[C_LIVE];
     for (int q = blockIdx.x; q < n; q += gridDim.x) {
         const int slot = L.queue_in[q];

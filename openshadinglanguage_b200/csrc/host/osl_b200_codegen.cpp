@@ -334,6 +334,7 @@ private:
     void emit_matrix_op(const Opcode& op);
     void emit_printf(const Opcode& op);
     bool journal_ok = false;  // grid kernels write printf records to the launch's journal
+    bool material_mode = false;  // group compiled as a renderer material: no launch block, no userdata
     bool uses_closures = false;  // a grid kernel then carries a per-point closure pool
     void gen_layer(int layer);
     void emit_block(int b, int e, const Ctx* ctx);
@@ -1222,6 +1223,12 @@ Gen::emit_op(const Opcode& op)
             { "sheen_bsdf", 3, "MX_SHEEN_ID", "mode:i" },
             { "layer", 2, "MX_LAYER_ID", nullptr },  // closure-typed params: pool word offsets
             { "uniform_edf", 1, "MX_UNIFORM_EDF_ID", nullptr },
+            // libbsdl Data structs: bsdf_conductor_decl.h:43-46, bsdf_dielectric_decl.h:112-120 (c = color: 3 words)
+            { "conductor_bsdf", 7, "MX_CONDUCTOR_ID", "thinfilm_thickness:f,thinfilm_ior:f" },
+            { "dielectric_bsdf", 8, "MX_DIELECTRIC_ID", "thinfilm_thickness:f,thinfilm_ior:f,absorption:c,dispersion:f" },
+            { "generalized_schlick_bsdf", 10, "MX_GENERALIZED_SCHLICK_ID", nullptr },
+            { "translucent_bsdf", 2, "MX_TRANSLUCENT_ID", nullptr },
+            { "subsurface_bssrdf", 4, "MX_SUBSURFACE_ID", nullptr },
             { "emission", 0, "EMISSION_ID" },       { "background", 0, "BACKGROUND_ID" },
             { "diffuse", 1, "DIFFUSE_ID" },         { "oren_nayar", 2, "OREN_NAYAR_ID" },
             { "translucent", 1, "TRANSLUCENT_ID" }, { "phong", 2, "PHONG_ID" },
@@ -1269,7 +1276,8 @@ Gen::emit_op(const Opcode& op)
             }
         }
         const int key_base = nwords;
-        nwords += (int)keys.size();
+        for (auto& kt : keys)
+            nwords += kt.second == 'c' ? 3 : 1;
         const std::string cn = cname;
         g.closure_in_loop |= loop_depth > 0;
         g.pool_words_bound += 4 + nwords;
@@ -1281,6 +1289,9 @@ Gen::emit_op(const Opcode& op)
         if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
             || cn == "burley_diffuse_bsdf" || cn == "sheen_bsdf" || cn == "layer")
             g.uses_glossy_lobes = true;
+        if (cn == "conductor_bsdf" || cn == "dielectric_bsdf" || cn == "generalized_schlick_bsdf"
+            || cn == "translucent_bsdf" || cn == "subsurface_bssrdf")
+            g.uses_glossy_lobes = g.uses_mx_lobes = true;
         std::string wexpr = "mkv(1.0f)";
         if (weight >= 0) {
             w("V3 w_; assign(w_, " + R(weight) + ");");
@@ -1304,12 +1315,15 @@ Gen::emit_op(const Opcode& op)
             w("    putp(sg.pool->w + c_ + " + std::to_string(4 + off) + ", " + e + ");");
             off += S(a).type.ncomp();
         }
+        int koff = key_base;
         for (size_t k = 0; k < keys.size(); ++k) {
-            std::string e = keys[k].second == 'i' ? "0" : "0.0f";
+            const char kt = keys[k].second;
+            std::string e = kt == 'i' ? "0" : (kt == 'c' ? "mkv(0.0f)" : "0.0f");
             for (size_t j = 0; j + 1 < kw.size(); j += 2) {
                 const Symbol& ks = S(kw[j]);
                 const Symbol& kv = S(kw[j + 1]);
-                bool type_ok = keys[k].second == 'i' ? kv.type.base == Base::Int : kv.type.base == Base::Float;
+                bool type_ok = kt == 'i' ? kv.type.base == Base::Int
+                                         : (kt == 'c' ? kv.type.ncomp() == 3 : kv.type.base == Base::Float);
                 if (ks.type.base == Base::String && ks.const_value() && !ks.svals.empty() && ks.svals[0] == keys[k].first
                     && type_ok && kv.type.arraylen == 0) {
                     e = R(kw[j + 1]);
@@ -1317,7 +1331,8 @@ Gen::emit_op(const Opcode& op)
                         e = "nd(" + e + ")";
                 }
             }
-            w("    putp(sg.pool->w + c_ + " + std::to_string(4 + key_base + (int)k) + ", " + e + ");");
+            w("    putp(sg.pool->w + c_ + " + std::to_string(4 + koff) + ", " + e + ");");
+            koff += kt == 'c' ? 3 : 1;
         }
         w("}");
         w(R(op.args[0]) + " = c_;");
@@ -1374,6 +1389,45 @@ Gen::gen_layer(int layer)
             continue;
         std::vector<std::string> vals = initvals(s);
         std::string r                 = ref(layer, s);
+        // interpolated parameter: the renderer's userdata wins (osl_bind_interpolated_param,
+        // llvm_instance.cpp:805-970), points without it run the default / init ops
+        const UserData* ud = nullptr;
+        if (s.interpolated && !material_mode && !s.type.arraylen)
+            for (const UserData& u : g.userdata)
+                if (u.name == s.name && u.ncomp == s.type.ncomp() && u.is_int == (s.type.base == Base::Int)
+                    && s.type.base != Base::String && s.type.base != Base::Matrix && s.type.base != Base::Closure)
+                    ud = &u;
+        if (ud) {
+            w("bool got_" + std::to_string(si) + " = L.userdata_base != nullptr;");
+            if (ud->valid_offset >= 0)
+                w("if (got_" + std::to_string(si) + ") got_" + std::to_string(si)
+                  + " = __ldg((const int*)((const char*)L.userdata_base + " + std::to_string(ud->valid_offset) + "ll + "
+                  + std::to_string(ud->valid_stride) + "ll * (long long)sg.shadeindex)) != 0;");
+            w("if (got_" + std::to_string(si) + ") {");
+            ++ind;
+            w("const float* p_ = (const float*)((const char*)L.userdata_base + " + std::to_string(ud->offset) + "ll + "
+              + std::to_string(ud->stride) + "ll * (long long)sg.shadeindex);");
+            auto ld = [&](int i) { return "__ldg(p_ + " + std::to_string(i) + ")"; };
+            if (ud->is_int)
+                w(r + " = __float_as_int(" + ld(0) + ");");
+            else if (ud->ncomp == 1) {
+                if (s.has_derivs)
+                    w(r + " = mkd(" + ld(0) + ", " + (ud->derivs ? ld(1) : std::string("0.0f")) + ", "
+                      + (ud->derivs ? ld(2) : std::string("0.0f")) + ");");
+                else
+                    w(r + " = " + ld(0) + ";");
+            } else {
+                auto v3 = [&](int b) { return "mkv(" + ld(b) + ", " + ld(b + 1) + ", " + ld(b + 2) + ")"; };
+                if (s.has_derivs)
+                    w(r + " = mkdv(" + v3(0) + ", " + (ud->derivs ? v3(3) : std::string("mkv(0.0f)")) + ", "
+                      + (ud->derivs ? v3(6) : std::string("mkv(0.0f)")) + ");");
+                else
+                    w(r + " = " + v3(0) + ";");
+            }
+            --ind;
+            w("} else {");
+            ++ind;
+        }
         if (s.type.arraylen)
             for (size_t i = 0; i < vals.size(); ++i)
                 w(r + "[" + std::to_string(i) + "] = " + vals[i] + ";");
@@ -1383,6 +1437,10 @@ Gen::gen_layer(int layer)
         if (s.initexpr && mi != m.methods.end()) {
             ensured.clear();
             emit_block(mi->second.first, mi->second.second, nullptr);
+        }
+        if (ud) {
+            --ind;
+            w("}");
         }
     }
     ensured.clear();
@@ -1692,7 +1750,7 @@ Gen::run()
     emit_fetch("tile_ + gridDim.x");
     out << "        GD gd;\n        gd.ran = 0u;\n";
     if (uses_closures)
-        out << "        float pool_store_[OSLD_POOL_WORDS];\n        ClosurePool pool_;\n        pool_.bind(pool_store_, 1);\n"
+        out << "        float pool_store_[OSLD_POOL_STORE];\n        ClosurePool pool_;\n        pool_.bind(pool_store_, 1);\n"
                "        pool_.reset();\n        sg.pool = &pool_;\n        sg.Ci = 0;\n";
     out << "        if (active_) {\n";
     out << "            layer_" << (nlayers - 1) << "(sg, gd, L);\n";
@@ -1757,6 +1815,7 @@ Gen::run()
 std::string
 Gen::run_material(const std::string& ns)
 {
+    material_mode = true;
     int nlayers = (int)g.layers.size();
     if (nlayers > 32)
         throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
@@ -1799,7 +1858,7 @@ std::string
 generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderModuleInfo* info)
 {
     std::string mats;
-    bool color = false, glossy = false, in_loop = false;
+    bool color = false, glossy = false, mx = false, in_loop = false;
     int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
     int pool_words = 2, lobes = 1, adds = 0;
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -1813,6 +1872,7 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         mats += Gen(g).run_material("mat" + std::to_string(k));
         color |= g.uses_colorsystem;
         glossy |= g.uses_glossy_lobes;
+        mx |= g.uses_mx_lobes;
         in_loop |= g.closure_in_loop;
         pool_words = std::max(pool_words, g.pool_words_bound);
         lobes      = std::max(lobes, g.lobe_bound);
@@ -1848,6 +1908,11 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
     // the integrator is specialised to the lobes the scene's materials can create
     if (glossy)
         out << "#define OSLD_GLOSSY_LOBES 1\n";
+    if (mx)
+        out << "#define OSLD_MX_LOBES 1\n";
+    mi.uses_mx_lobes = mx;
+    if (info)
+        info->uses_mx_lobes = mx;
     if (has_background)
         out << "#define OSLD_HAS_BACKGROUND 1\n";
     out << "#include \"osl_b200_render.cuh\"\n";

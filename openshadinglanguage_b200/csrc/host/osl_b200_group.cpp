@@ -186,6 +186,8 @@ parse_oso(const std::string& text)
                 if (v[0] == '%') {
                     if (v == "%initexpr")
                         s.initexpr = true;
+                    else if (v == "%meta{int,lockgeom,0}")
+                        s.interpolated = true;   // [[ int lockgeom = 0 ]]: bound to userdata per point
                     continue;
                 }
                 if (v[0] == '"')

@@ -45,6 +45,7 @@ struct Symbol {
     std::vector<int> ivals;
     std::vector<std::string> svals;
     bool initexpr       = false;
+    bool interpolated   = false;  // lockgeom=0: the renderer may supply the value per point (userdata)
     bool has_derivs     = false;
     bool written        = false;
     bool connected_down = false;
@@ -56,7 +57,7 @@ struct Symbol {
     // would the runtime optimizer have folded this to a constant?
     bool const_value() const
     {
-        return is_const() || (symtype == SymType::Param && conn_layer < 0 && !initexpr && !written);
+        return is_const() || (symtype == SymType::Param && conn_layer < 0 && !initexpr && !written && !interpolated);
     }
 };
 
@@ -127,8 +128,17 @@ struct JournalFormat {
     std::vector<JournalArg> args;
 };
 
+// one b200_userdata entry (include/osl_b200.h)
+struct UserData {
+    std::string name;
+    int ncomp = 1;
+    bool is_int = false, derivs = false;
+    long long offset = 0, stride = 0, valid_offset = -1, valid_stride = 0;
+};
+
 struct Group {
     std::string name;
+    std::vector<UserData> userdata;            // what the renderer supplies for interpolated params
     std::vector<OutCluster> clusters;
     bool stage_ok = false;  // every cluster dense and small enough to stage
     int block     = 256;    // CTA size the kernel is generated for
@@ -140,6 +150,7 @@ struct Group {
     std::set<int> globals_read;                // b200_sg_field ids the kernel loads
     bool fma = true;                           // allow FMA contraction in generated code
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
+    bool uses_mx_lobes     = false;            // set by codegen: conductor / dielectric / generalized schlick ...
     bool uses_colorsystem  = false;            // set by codegen: luminance / blackbody / transformc ...
     std::string colorspace = "Rec709";         // ShadingSystem attribute "colorspace"
     std::vector<JournalFormat> jformats;       // printf sites (id = index), grid kernels only
@@ -185,6 +196,7 @@ struct RenderModuleInfo {
     int max_lobes     = 8;      // OSLD_MAX_LOBES
     int closure_stack = 16;     // OSLD_CLOSURE_STACK
     bool pool_in_smem = false;  // OSLD_POOL_SMEM: arena staged in shared memory
+    bool uses_mx_lobes = false; // OSLD_MX_LOBES: the module reads the libbsdl energy tables
 };
 std::string generate_cuda_render(std::vector<Group*>& groups, bool has_background = false,
                                  RenderModuleInfo* info = nullptr);

@@ -157,14 +157,19 @@ struct b200_group {
     unsigned journal_words = 4u << 20;   // option journal=WORDS
     std::map<int, unsigned*> journal_dev;
     std::string journal_text;
-    // staging buffers for execute_host (per group, grown on demand)
+    // staging buffers for execute_host: one set per device (its streams belong to that device's
+    // context), grown on demand.  host_mu serialises execute_host callers of this group: the
+    // reference lets many threads execute one group, each with its own context; here they
+    // share the group's staging area, so they take turns (the device path has no such state).
     struct Stage {
-        int device       = -1;
         char* d_in       = nullptr;
         char* d_out      = nullptr;
-        size_t in_bytes  = 0, out_bytes = 0;
+        char* d_ud       = nullptr;
+        size_t in_bytes  = 0, out_bytes = 0, ud_bytes = 0;
         cudaStream_t streams[3] = { nullptr, nullptr, nullptr };
-    } stage;
+    };
+    std::map<int, Stage> stages;
+    std::mutex host_mu;
 };
 
 static std::map<std::string, std::string>
@@ -301,6 +306,15 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             const b200_symloc& s = desc->outputs[i];
             G->g.add_output(s.name, s.offset, s.stride, s.derivs != 0);
         }
+        for (int i = 0; i < desc->nuserdata && desc->userdata; ++i) {
+            const b200_userdata& u = desc->userdata[i];
+            if (!u.name || (u.ncomp != 1 && u.ncomp != 3) || u.stride < 0 || (u.is_int && u.ncomp != 1))
+                return fail(B200_ERR_INVALID, "bad userdata description");
+            UserData d;
+            d.name = u.name; d.ncomp = u.ncomp; d.is_int = u.is_int != 0; d.derivs = u.derivs != 0;
+            d.offset = u.offset; d.stride = u.stride; d.valid_offset = u.valid_offset; d.valid_stride = u.valid_stride;
+            G->g.userdata.push_back(d);
+        }
         G->g.block = G->block;
         G->g.finalize();
         G->source = generate_cuda(G->g);
@@ -325,13 +339,15 @@ b200_group_destroy(b200_group* g)
             driver().cuModuleUnload(kv.second.first);
     for (void* p : g->texture_allocs)
         cudaFree(p);
-    if (g->stage.d_in)
-        cudaFree(g->stage.d_in);
-    if (g->stage.d_out)
-        cudaFree(g->stage.d_out);
-    for (auto s : g->stage.streams)
-        if (s)
-            cudaStreamDestroy(s);
+    for (auto& kv : g->stages) {
+        b200_group::Stage& st = kv.second;
+        cudaSetDevice(kv.first);
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+        if (st.d_ud) cudaFree(st.d_ud);
+        for (cudaStream_t q : st.streams)
+            if (q) cudaStreamDestroy(q);
+    }
     for (auto& kv : g->journal_dev)
         if (kv.second)
             cudaFree(kv.second);
@@ -532,6 +548,25 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
     int rc = ensure_loaded(g, device, &fn);
     if (rc != B200_OK)
         return rc;
+    // the kernel belongs to the primary context of `device`: make it current for the launch
+    // (the caller's own current device is put back afterwards)
+    struct DeviceScope {
+        int prev = -1;
+        explicit DeviceScope(int d)
+        {
+            if (cudaGetDevice(&prev) != cudaSuccess)
+                prev = -1;
+            if (prev != d)
+                cudaSetDevice(d);
+            else
+                prev = -1;
+        }
+        ~DeviceScope()
+        {
+            if (prev >= 0)
+                cudaSetDevice(prev);
+        }
+    } scope(device);
     LaunchBlock L;
     memcpy(L.varying, sg->varying, sizeof L.varying);
     memcpy(L.uniform, sg->uniform, sizeof L.uniform);
@@ -604,8 +639,9 @@ b200_group_execute(b200_group* g, int device, void* stream, long long npoints, c
 
 // Host-pointer path: stage only the planes the kernel reads, pipelined in
 // chunks over three streams so H2D, kernel and D2H overlap.
-int
-b200_group_execute_host(b200_group* g, int device, long long npoints, const b200_globals* sg, void* output_base)
+static int
+execute_host_impl(b200_group* g, int device, long long npoints, const b200_globals* sg, const void* userdata_host,
+                  long long userdata_bytes, void* output_base)
 {
     if (!g || !sg || npoints < 0)
         return fail(B200_ERR_INVALID, "b200_group_execute_host: bad arguments");
@@ -615,7 +651,18 @@ b200_group_execute_host(b200_group* g, int device, long long npoints, const b200
     int rc = ensure_loaded(g, device, &fn);
     if (rc != B200_OK)
         return rc;
+    std::lock_guard<std::mutex> host_lock(g->host_mu);
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
     cudaSetDevice(device);
+    struct Restore {
+        int d;
+        ~Restore()
+        {
+            if (d >= 0)
+                cudaSetDevice(d);
+        }
+    } restore { prev_device == device ? -1 : prev_device };
     struct Plane {
         int field, comps;
     };
@@ -638,25 +685,46 @@ b200_group_execute_host(b200_group* g, int device, long long npoints, const b200
     const long long CH    = 1 << 20;  // points per chunk
     const int NS          = 3;
     long long chunk       = npoints < CH ? npoints : CH;
-    b200_group::Stage& st = g->stage;
+    b200_group::Stage& st = g->stages[device];
     size_t need_in = (size_t)chunk * in_bpp * NS, need_out = (size_t)chunk * out_bpp * NS;
-    if (st.device != device || st.in_bytes < need_in || st.out_bytes < need_out) {
+    if (st.in_bytes < need_in) {
         if (st.d_in) cudaFree(st.d_in);
-        if (st.d_out) cudaFree(st.d_out);
-        st.d_in = st.d_out = nullptr;
-        if (need_in && cudaMalloc(&st.d_in, need_in) != cudaSuccess)
+        st.d_in = nullptr; st.in_bytes = 0;
+        if (cudaMalloc(&st.d_in, need_in) != cudaSuccess)
             return fail(B200_ERR_CUDA, "cudaMalloc(staging in) failed");
-        if (need_out && cudaMalloc(&st.d_out, need_out) != cudaSuccess)
-            return fail(B200_ERR_CUDA, "cudaMalloc(staging out) failed");
-        st.in_bytes  = need_in;
-        st.out_bytes = need_out;
-        st.device    = device;
-        for (int s = 0; s < NS; ++s)
-            if (!st.streams[s])
-                cudaStreamCreateWithFlags(&st.streams[s], cudaStreamNonBlocking);
+        st.in_bytes = need_in;
     }
+    if (st.out_bytes < need_out) {
+        if (st.d_out) cudaFree(st.d_out);
+        st.d_out = nullptr; st.out_bytes = 0;
+        if (cudaMalloc(&st.d_out, need_out) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "cudaMalloc(staging out) failed");
+        st.out_bytes = need_out;
+    }
+    for (int s = 0; s < NS; ++s)
+        if (!st.streams[s] && cudaStreamCreateWithFlags(&st.streams[s], cudaStreamNonBlocking) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "cudaStreamCreate failed");
+    // userdata arena: uploaded whole, once (the kernel indexes it by shade index)
+    const void* d_userdata = nullptr;
+    if (userdata_host && userdata_bytes > 0 && !g->g.userdata.empty()) {
+        if (st.ud_bytes < (size_t)userdata_bytes) {
+            if (st.d_ud) cudaFree(st.d_ud);
+            st.d_ud = nullptr; st.ud_bytes = 0;
+            if (cudaMalloc(&st.d_ud, (size_t)userdata_bytes) != cudaSuccess)
+                return fail(B200_ERR_CUDA, "cudaMalloc(userdata) failed");
+            st.ud_bytes = (size_t)userdata_bytes;
+        }
+        if (cudaMemcpy(st.d_ud, userdata_host, (size_t)userdata_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(B200_ERR_CUDA, "userdata upload failed");
+        d_userdata = st.d_ud;
+    }
+    auto out_bytes_of = [&](int k) -> size_t {
+        const Symbol& sy = g->g.layers[g->g.outputs[k].first].m.syms[g->g.outputs[k].second];
+        return (size_t)4 * sy.type.ncomp() * (sy.type.arraylen ? sy.type.arraylen : 1) * (sy.out.derivs ? 3 : 1);
+    };
+    cudaError_t ce = cudaSuccess;
     int slot = 0;
-    for (long long b = 0; b < npoints; b += chunk, slot = (slot + 1) % NS) {
+    for (long long b = 0; b < npoints && ce == cudaSuccess; b += chunk, slot = (slot + 1) % NS) {
         long long n     = (npoints - b) < chunk ? (npoints - b) : chunk;
         cudaStream_t s  = st.streams[slot];
         char* din       = st.d_in + (size_t)slot * chunk * in_bpp;
@@ -668,7 +736,8 @@ b200_group_execute_host(b200_group* g, int device, long long npoints, const b200
             dg.varying[p.field] = (const float*)(din + off);
             for (int c = 0; c < p.comps; ++c) {
                 const float* src = sg->varying[p.field] + (size_t)c * sg->plane_stride + b;
-                cudaMemcpyAsync(din + off, src, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+                cudaError_t e = cudaMemcpyAsync(din + off, src, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) ce = e;
                 off += (size_t)n * 4;
             }
         }
@@ -684,22 +753,54 @@ b200_group_execute_host(b200_group* g, int device, long long npoints, const b200
                 adjust[k] = (long long)region - c.lo - c.stride * b;
             region += (size_t)n * c.stride;
         }
-        rc = launch_group(g, device, s, n, &dg, nullptr, nullptr, dout, b, adjust);
+        rc = launch_group(g, device, s, n, &dg, nullptr, d_userdata, dout, b, adjust);
         if (rc != B200_OK)
             return rc;
         region = 0;
         for (const Cluster& c : clusters) {
-            size_t bytes = (size_t)(n - 1) * c.stride + (size_t)(c.hi - c.lo);
-            cudaMemcpyAsync((char*)output_base + c.lo + c.stride * b, dout + region, bytes, cudaMemcpyDeviceToHost, s);
+            char* hdst = (char*)output_base + c.lo + c.stride * b;
+            if (c.dense) {
+                // the fields tile the record: one contiguous copy of n whole records
+                size_t bytes  = (size_t)(n - 1) * c.stride + (size_t)(c.hi - c.lo);
+                cudaError_t e = cudaMemcpyAsync(hdst, dout + region, bytes, cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) ce = e;
+            } else {
+                // sparse record (the renderer owns the bytes between the fields): copy each
+                // symbol's bytes only, the SymLocationDesc contract of the device path
+                for (int k : c.outs) {
+                    const Symbol& sy = g->g.layers[g->g.outputs[k].first].m.syms[g->g.outputs[k].second];
+                    size_t foff      = (size_t)(sy.out.offset - c.lo);
+                    cudaError_t e    = cudaMemcpy2DAsync(hdst + foff, (size_t)c.stride, dout + region + foff,
+                                                         (size_t)c.stride, out_bytes_of(k), (size_t)n,
+                                                         cudaMemcpyDeviceToHost, s);
+                    if (e != cudaSuccess) ce = e;
+                }
+            }
             region += (size_t)n * c.stride;
         }
     }
-    for (int s = 0; s < NS; ++s)
-        cudaStreamSynchronize(st.streams[s]);
-    cudaError_t ce = cudaGetLastError();
+    for (int s = 0; s < NS; ++s) {
+        cudaError_t e = cudaStreamSynchronize(st.streams[s]);
+        if (e != cudaSuccess) ce = e;
+    }
+    if (ce == cudaSuccess)
+        ce = cudaGetLastError();
     if (ce != cudaSuccess)
         return fail(B200_ERR_CUDA, std::string("execute_host: ") + cudaGetErrorString(ce));
     return B200_OK;
+}
+
+int
+b200_group_execute_host(b200_group* g, int device, long long npoints, const b200_globals* sg, void* output_base)
+{
+    return execute_host_impl(g, device, npoints, sg, nullptr, 0, output_base);
+}
+
+int
+b200_group_execute_host_userdata(b200_group* g, int device, long long npoints, const b200_globals* sg,
+                                 const void* userdata_base, long long userdata_bytes, void* output_base)
+{
+    return execute_host_impl(g, device, npoints, sg, userdata_base, userdata_bytes, output_base);
 }
 
 }  // extern "C"

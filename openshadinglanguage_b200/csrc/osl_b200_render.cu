@@ -11,6 +11,7 @@
 #include "osl_b200_jit.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -59,6 +60,7 @@ struct DevScene {
     int bg_res;
     float bg_invres, bg_invjacobian;
     const void* leaf_tris;
+    const float* bsdl_luts;
 };
 enum { PATH_QUADS = 8, SHADOW_QUADS = 4 };  // 128 B of path state + 64 B of pending shadow rays per slot
 // device loop state (osld::C_*)
@@ -332,12 +334,33 @@ upload(b200_render::Dev& d, const T* host, size_t n, bool& ok)
     return (const T*)p;
 }
 
+// openshadinglanguage_b200/data/bsdl_luts.bin, found relative to this shared library
+static std::string
+load_bsdl_luts(std::vector<float>& out)
+{
+    Dl_info info;
+    if (!dladdr((const void*)&load_bsdl_luts, &info) || !info.dli_fname)
+        return "cannot locate libosl_b200.so to find data/bsdl_luts.bin";
+    std::string path = info.dli_fname;
+    size_t slash     = path.rfind('/');
+    path             = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/data/bsdl_luts.bin";
+    FILE* f          = fopen(path.c_str(), "rb");
+    if (!f)
+        return "cannot open " + path + " (energy tables of the MaterialX microfacet closures; tools/bake_bsdl_luts.cpp)";
+    out.resize(256 + 3 * 8192);
+    size_t n = fread(out.data(), sizeof(float), out.size(), f);
+    fclose(f);
+    if (n != out.size())
+        return path + " is truncated";
+    return "";
+}
+
 // dynamic shared memory (bytes) and CTA size of kernel k; *block = 0 for kernels without any
 static size_t
 kernel_smem(const b200_render* r, int k, unsigned* block)
 {
     const size_t stack = (size_t)r->stk_words * r->bvh_stack * 4;              // per thread
-    const size_t pool  = r->info.pool_in_smem ? (size_t)r->info.pool_words * 4 : 0;  // per thread
+    const size_t pool  = r->info.pool_in_smem ? (size_t)(r->info.pool_words + 4) * 4 : 0;  // per thread (OSLD_POOL_STORE)
     switch (k) {
     case K_TRACE: *block = TRACE_BLOCK; return stack * TRACE_BLOCK;
     case K_SHADE:
@@ -437,6 +460,16 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
             memcpy(&lt[(size_t)12 * p + 3], &id, 4);
         }
         S.leaf_tris = upload(d, lt.data(), lt.size(), ok);
+    }
+    if (r->info.uses_mx_lobes) {
+        // energy-compensation tables of the MaterialX microfacet closures: product data next to the library
+        std::vector<float> luts;
+        std::string lerr = load_bsdl_luts(luts);
+        if (!lerr.empty()) {
+            free_dev(d);
+            return set_error(B200_ERR_INVALID, lerr);
+        }
+        S.bsdl_luts = upload(d, luts.data(), luts.size(), ok);
     }
     if (!ok) {
         free_dev(d);

@@ -30,7 +30,41 @@ class Launch(ctypes.Structure):
                 ("output_base", ctypes.c_void_p),
                 ("userdata_base", ctypes.c_void_p),
                 ("ntransforms", ctypes.c_int),
-                ("transforms", ctypes.c_void_p)]
+                ("transforms", ctypes.c_void_p),
+                ("nuserdata", ctypes.c_int),
+                ("userdata", ctypes.c_void_p)]
+
+
+class UserDataDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("ncomp", ctypes.c_int), ("is_int", ctypes.c_int),
+                ("offset", ctypes.c_longlong), ("stride", ctypes.c_longlong), ("derivs", ctypes.c_int),
+                ("valid_offset", ctypes.c_longlong), ("valid_stride", ctypes.c_longlong)]
+
+
+def pack_userdata(entries):
+    """entries: list of dict(name, data [n, ncomp] or [n, 3*ncomp] with derivs (val,dx,dy), or int32 [n];
+    derivs=bool, valid=int32[n] or None) -> (arena uint8 array, list of descriptor dicts).  One dense
+    array per entry (offset = its start, stride = its row size): the layout testshade uses for
+    its outputs, here for the UserData arena."""
+    blobs, descs, off = [], [], 0
+    for e in entries:
+        a = np.ascontiguousarray(e["data"])
+        is_int = a.dtype.kind in "iu"
+        a = a.astype(np.int32 if is_int else np.float32).reshape(len(a), -1)
+        derivs = bool(e.get("derivs"))
+        ncomp = a.shape[1] // (3 if derivs else 1)
+        d = dict(name=e["name"], ncomp=ncomp, is_int=int(is_int), offset=off, stride=a.shape[1] * 4,
+                 derivs=int(derivs), valid_offset=-1, valid_stride=0)
+        blobs.append(a.tobytes())
+        off += (len(blobs[-1]) + 15) // 16 * 16
+        blobs[-1] = blobs[-1].ljust((len(blobs[-1]) + 15) // 16 * 16, b"\0")
+        if e.get("valid") is not None:
+            v = np.ascontiguousarray(e["valid"], np.int32)
+            d["valid_offset"], d["valid_stride"] = off, 4
+            blobs.append(v.tobytes().ljust((v.nbytes + 15) // 16 * 16, b"\0"))
+            off += len(blobs[-1])
+        descs.append(d)
+    return np.frombuffer(b"".join(blobs) or b"\0" * 16, np.uint8).copy(), descs
 
 
 class NamedTransform(ctypes.Structure):
@@ -141,6 +175,19 @@ def make_launch(n, varying, uniform, output, shadeindex=None, keep=None):
         L.shadeindex = None
     L.output_base = output.ctypes.data if output is not None else None
     L.userdata_base = None
+    L.nuserdata, L.userdata = 0, None
+    ud = uniform.get("userdata")
+    if ud:
+        arena, descs = ud if isinstance(ud, tuple) else pack_userdata(ud)
+        arr = (UserDataDesc * len(descs))()
+        for k, d in enumerate(descs):
+            nm = d["name"].encode()
+            keep.append(nm)
+            arr[k].name, arr[k].ncomp, arr[k].is_int = nm, d["ncomp"], d["is_int"]
+            arr[k].offset, arr[k].stride, arr[k].derivs = d["offset"], d["stride"], d["derivs"]
+            arr[k].valid_offset, arr[k].valid_stride = d["valid_offset"], d["valid_stride"]
+        keep += [arena, arr]
+        L.userdata_base, L.nuserdata, L.userdata = arena.ctypes.data, len(descs), ctypes.cast(arr, ctypes.c_void_p)
     keep.append(output)
     xf = uniform.get("transforms") or {}
     arr = (NamedTransform * max(1, len(xf)))()

@@ -57,6 +57,20 @@ struct Launch {
     // (ShaderGlobals::shader2common / object2common + RendererServices::get_matrix)
     int ntransforms;
     const struct NamedTransform* transforms;
+    // userdata the renderer supplies per point (RendererServices::get_userdata /
+    // SymLocationDesc arena UserData, llvm_instance.cpp:805-970): value of point i at
+    // userdata_base + offset + stride * shadeindex, val[,dx,dy] when derivs; an optional
+    // int32 plane says whether the point has the value at all
+    int nuserdata;
+    const struct UserDataDesc* userdata;
+};
+struct UserDataDesc {
+    const char* name;
+    int ncomp;    // 1 or 3
+    int is_int;
+    long long offset, stride;
+    int derivs;
+    long long valid_offset, valid_stride;   // valid_offset < 0: every point has it
 };
 inline TransformSet xf_set(const Launch* L)
 {
@@ -134,6 +148,65 @@ inline void load_sg(SG& sg, const Launch* L, long long i, Ctx* ctx)
     sg.shadeindex     = L->shadeindex ? L->shadeindex[i] : (int)i;
     sg.ctx            = ctx;
 }
+
+// osl_bind_interpolated_param (llvm_instance.cpp:805-970): fetch the value of an interpolated
+// ([[ int lockgeom = 0 ]]) parameter from the renderer's userdata; false = not supplied for this
+// point (wrong name, wrong type, or masked out): the caller then runs the default / init ops.
+inline const float* userdata_ptr(const Launch* L, const SG& sg, const char* name, int ncomp, int is_int, bool* derivs)
+{
+    for (int k = 0; L && k < L->nuserdata; ++k) {   // (renderer materials run without a Launch: no userdata)
+        const UserDataDesc& d = L->userdata[k];
+        if (d.ncomp != ncomp || d.is_int != is_int || std::strcmp(d.name, name) != 0)
+            continue;
+        const char* base = (const char*)L->userdata_base;
+        if (d.valid_offset >= 0) {
+            int v;
+            std::memcpy(&v, base + d.valid_offset + d.valid_stride * (long long)sg.shadeindex, 4);
+            if (!v)
+                return nullptr;
+        }
+        *derivs = d.derivs != 0;
+        return (const float*)(base + d.offset + d.stride * (long long)sg.shadeindex);
+    }
+    return nullptr;
+}
+inline bool bind_userdata(const Launch* L, const SG& sg, const char* name, float& dst)
+{
+    bool dv;
+    const float* p = userdata_ptr(L, sg, name, 1, 0, &dv);
+    if (p) dst = p[0];
+    return p != nullptr;
+}
+inline bool bind_userdata(const Launch* L, const SG& sg, const char* name, Df& dst)
+{
+    bool dv;
+    const float* p = userdata_ptr(L, sg, name, 1, 0, &dv);
+    if (p) dst = dv ? Df(p[0], p[1], p[2]) : Df(p[0]);
+    return p != nullptr;
+}
+inline bool bind_userdata(const Launch* L, const SG& sg, const char* name, V3& dst)
+{
+    bool dv;
+    const float* p = userdata_ptr(L, sg, name, 3, 0, &dv);
+    if (p) dst = V3(p[0], p[1], p[2]);
+    return p != nullptr;
+}
+inline bool bind_userdata(const Launch* L, const SG& sg, const char* name, Dv& dst)
+{
+    bool dv;
+    const float* p = userdata_ptr(L, sg, name, 3, 0, &dv);
+    if (p)
+        dst = dv ? Dv(V3(p[0], p[1], p[2]), V3(p[3], p[4], p[5]), V3(p[6], p[7], p[8])) : Dv(V3(p[0], p[1], p[2]));
+    return p != nullptr;
+}
+inline bool bind_userdata(const Launch* L, const SG& sg, const char* name, int& dst)
+{
+    bool dv;
+    const float* p = userdata_ptr(L, sg, name, 1, 1, &dv);
+    if (p) std::memcpy(&dst, p, 4);
+    return p != nullptr;
+}
+template<class T> inline bool bind_userdata(const Launch*, const SG&, const char*, T&) { return false; }
 
 // ---------------------------------------------------------------------------
 // printf capture.  The generator splits the format at gen time and calls one

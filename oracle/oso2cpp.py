@@ -71,7 +71,7 @@ class OSym:
         if self.symtype == "const":
             return True
         return (self.symtype == "param" and self.connected_from is None
-                and not self.initexpr and not self.written)
+                and not self.initexpr and not self.written and not getattr(self, "interpolated", False))
 
 
 class OOp:
@@ -154,6 +154,7 @@ def parse_oso(text):
                     vals.append(struct.unpack("f", struct.pack("f", float(t)))[0])
             s = OSym(name, symtype, OType(base, arr), vals)
             s.initexpr = "%initexpr" in hints
+            s.interpolated = "%meta{int,lockgeom,0}" in hints   # [[ int lockgeom = 0 ]]
             m.byname[name] = s
             m.syms.append(s)
             continue
@@ -575,6 +576,11 @@ class Gen:
                 continue   # value arrives from upstream (possibly lazily)
             vals = self.initval(s)
             r = self.ref(l, s)
+            bound = getattr(s, "interpolated", False) and not s.t.arr
+            if bound:
+                # interpolated parameter: the renderer's userdata wins, else default / init ops
+                self.w('if (!bind_userdata(L, sg, "%s", %s)) {' % (s.name, r))
+                self.ind += 1
             if s.t.arr:
                 for i, v in enumerate(vals):
                     self.w("%s[%d] = %s;" % (r, i, v))
@@ -584,6 +590,9 @@ class Gen:
                 b, e = m.methods[s.name]
                 self.ensured = set()
                 self.emit_block(b, e, None)
+            if bound:
+                self.ind -= 1
+                self.w("}")
         self.ensured = set()
         b, e = m.methods.get("___main___", (0, 0))
         self.emit_block(b, e, None)

@@ -33,7 +33,12 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          "render-mx-furnace-burley-diffuse": ("mx_furnace_burley.xml", 384, 64, 16),
          # BASELINE config 4: layer() of sheen_bsdf / reflection / oren_nayar_diffuse_bsdf / diffuse,
          # lit by a procedural sky + sun through the 1024^2 background importance table
-         "render-mx-layer": ("mx_layer.xml", 160, 120, 6)}
+         "render-mx-layer": ("mx_layer.xml", 160, 120, 6),
+         # libbsdl microfacet lobes with tabulated energy compensation (a16): conductor_bsdf with
+         # artistic_ior, layer(dielectric_bsdf, diffuse), generalized_schlick_bsdf; anisotropic GGX
+         "render-mx-conductor": ("mx_conductor.xml", 160, 120, 16),
+         "render-mx-dielectric": ("mx_dielectric.xml", 160, 120, 16),
+         "render-mx-generalized-schlick": ("mx_generalized_schlick.xml", 160, 120, 16)}
 # BASELINE config 4's other half: glossy glass spheres under the kitchen light probe, read by
 # texture() in the background shader (1024^2 importance table + directly seen + bounce misses).
 # Texture filtering is OIIO's in the reference (not buildable here), so this golden pins the
@@ -97,6 +102,8 @@ def test_oracle_matches_reference_golden_render(case):
         # loosens them "to allow a little more LSB noise between platforms"): ~4 % of
         # pixels differ by one or two paths out of 256.  The difference must be unbiased.
         assert exact > 0.95 and abs(float((img - ref).mean())) < 1e-4, (exact, float((img - ref).mean()))
+    elif case in ("render-mx-conductor", "render-mx-dielectric", "render-mx-generalized-schlick"):
+        assert exact > 0.985, exact      # measured 0.993 / 0.991 / 0.990
     else:
         assert exact > 0.99, exact
 

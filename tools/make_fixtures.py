@@ -72,6 +72,11 @@ SHADERS = {
     "mxlayer_layer": "render-mx-layer/layer.osl",
     "mxlayer_envmap": "render-mx-layer/envmap.osl",
     "mf_envmap": "render-microfacet/envmap.osl",      # texture() of the HDR probe
+    # MaterialX microfacet closures (libbsdl conductor / dielectric / generalized Schlick lobes)
+    "mxspec_envmap": "render-mx-conductor/envmap.osl",
+    "mxcond_glossy": "render-mx-conductor/glossy.osl",
+    "mxdiel_glossy": "render-mx-dielectric/glossy.osl",
+    "mxgs_glossy": "render-mx-generalized-schlick/glossy.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -96,6 +101,10 @@ SCENES = {
     # (microfacet.xml is this repo's own emitter-lit variant; this is the reference's scene, whose
     #  environment shader reads ../common/textures/kitchen_probe.hdr -> ../textures/ here)
     "render_microfacet.xml": ("render-microfacet/scene.xml", {"envmap": "mf_envmap"}),
+    "mx_conductor.xml": ("render-mx-conductor/scene.xml", {"glossy": "mxcond_glossy", "envmap": "mxspec_envmap"}),
+    "mx_dielectric.xml": ("render-mx-dielectric/scene.xml", {"glossy": "mxdiel_glossy", "envmap": "mxspec_envmap"}),
+    "mx_generalized_schlick.xml": ("render-mx-generalized-schlick/scene.xml",
+                                   {"glossy": "mxgs_glossy", "envmap": "mxspec_envmap"}),
 }
 # input images read by texture() (test input data, copied byte for byte)
 TEXTURES = {"kitchen_probe.hdr": "common/textures/kitchen_probe.hdr"}
@@ -111,6 +120,9 @@ RENDERS = {
     "render-mx-furnace-burley-diffuse": "render-mx-furnace-burley-diffuse/ref/out.exr",
     "render-mx-layer": "render-mx-layer/ref/out.exr",
     "render-microfacet": "render-microfacet/ref/out.exr",
+    "render-mx-conductor": "render-mx-conductor/ref/out.exr",
+    "render-mx-dielectric": "render-mx-dielectric/ref/out.exr",
+    "render-mx-generalized-schlick": "render-mx-generalized-schlick/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image

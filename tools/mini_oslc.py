@@ -1883,6 +1883,11 @@ class Compiler:
             line += "\t%%read{%d,%d} %%write{%d,%d}" % (r[0], r[1], w[0], w[1])
             if s.initexpr:
                 line += " %initexpr"
+            # parameter metadata the runtime acts on: [[ int lockgeom = 0 ]] marks an
+            # interpolated (userdata-bound) parameter (oslc writes %meta{type,name,value})
+            for mt, mname, mval in (getattr(s, "meta", None) or []):
+                if mname == "lockgeom" and getattr(mval, "kind", None) == "lit":
+                    line += " %%meta{int,lockgeom,%d}" % int(mval.value)
             return line
 
         for s in self.syms:
