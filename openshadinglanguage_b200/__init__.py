@@ -8,8 +8,8 @@ the host-side mirror of testshade's grid setup.  It FAILS LOUDLY if the CUDA
 library is missing: there is no CPU fallback in the product path.
 """
 from .api import (B200Error, ShaderGroup, lib, library_path, shadeop_hash,  # noqa: F401
-                  shadeop_noise, SG_FIELDS, launch_count, add_texture)
+                  shadeop_noise, SG_FIELDS, launch_count, add_texture, pack_userdata)
 from .testshade import grid_globals  # noqa: F401
 
 __all__ = ["B200Error", "ShaderGroup", "lib", "library_path", "shadeop_noise", "shadeop_hash",
-           "grid_globals", "SG_FIELDS", "launch_count", "add_texture"]
+           "grid_globals", "SG_FIELDS", "launch_count", "add_texture", "pack_userdata"]

@@ -343,6 +343,7 @@ private:
     void op_percomp(const Opcode& op);
     void op_cmp(const Opcode& op);
     void op_noise(const Opcode& op, bool periodic);
+    void op_noise_named(const Opcode& op, bool periodic, const std::string& runtime_name);
     void emit_copy(int dl, const Symbol& d, int sl, const Symbol& s);
 };
 
@@ -558,6 +559,39 @@ Gen::op_cmp(const Opcode& op)
 void
 Gen::op_noise(const Opcode& op, bool periodic)
 {
+    // A name that is not known at compile time: the reference calls osl_genericnoise /
+    // osl_genericpnoise, which compare the name at run time (GenericNoise / GenericPNoise,
+    // opnoise.cpp:704-900).  Here every name the reference accepts gets the code the
+    // compile-time path would emit for it, selected by the interned name id: a warp whose
+    // lanes agree on the name (the usual case: a string parameter) runs exactly one branch.
+    if (op.args.size() > 1 && S(op.args[1]).type.base == Base::String && !S(op.args[1]).const_value()) {
+        static const char* const names[][2]  = { { "perlin", "snoise" },   { "uperlin", "noise" }, { "simplex", "simplexnoise" },
+                                                 { "usimplex", "usimplexnoise" }, { "cell", nullptr }, { "hash", nullptr },
+                                                 { "gabor", nullptr } };
+        w("const int nm_ = " + R(op.args[1]) + ";");
+        bool first = true;
+        for (auto& pr : names) {
+            if (periodic && (std::string(pr[0]) == "simplex" || std::string(pr[0]) == "usimplex"))
+                continue;   // GenericPNoise has no simplex branch
+            std::string cond = "nm_ == " + std::to_string(g.intern(pr[0]));
+            if (pr[1])
+                cond += " || nm_ == " + std::to_string(g.intern(pr[1]));
+            w(std::string(first ? "if (" : "} else if (") + cond + ") {");
+            first = false;
+            ++ind;
+            op_noise_named(op, periodic, pr[0]);
+            --ind;
+        }
+        // unknown name: the reference reports "Unknown noise type" and leaves the result alone
+        w("}");
+        return;
+    }
+    op_noise_named(op, periodic, "");
+}
+
+void
+Gen::op_noise_named(const Opcode& op, bool periodic, const std::string& runtime_name)
+{
     // llvm_gen_noise (llvm_gen.cpp:3117-3299): the noise name is resolved at
     // code-generation time; the float vs Dual2 entry is chosen from has_derivs
     std::vector<int> rest(op.args.begin() + 1, op.args.end());
@@ -565,9 +599,10 @@ Gen::op_noise(const Opcode& op, bool periodic)
     std::string name = op.name;
     if (!rest.empty() && S(rest[0]).type.base == Base::String) {
         const Symbol& ns = S(rest[0]);
-        if (!ns.const_value())
-            unsupported("noise() with a name that is not known at compile time");
-        name = ns.svals.empty() ? "" : ns.svals[0];
+        if (!runtime_name.empty())
+            name = runtime_name;
+        else
+            name = ns.svals.empty() ? "" : ns.svals[0];
         rest.erase(rest.begin());
     }
     std::vector<int> coords;

@@ -985,20 +985,33 @@ class Gen:
             e = "hash_vf(nd(%s), %s)" % (self.R(ins[0]), self.comp(ins[1], 0, False))
         self.w("%s = %s;" % (self.R(d), e))
 
-    def noise_impl(self, op, periodic):
+    def noise_impl(self, op, periodic, runtime_name=None):
         """llvm_gen_noise (llvm_gen.cpp:3117-3299): resolve the name at gen
-        time, pick float/Dual form from has_derivs of result and inputs."""
+        time, pick float/Dual form from has_derivs of result and inputs.  A name that is
+        not a compile-time constant goes through osl_genericnoise / osl_genericpnoise in the
+        reference (GenericNoise / GenericPNoise, opnoise.cpp:704-900: string compares at run
+        time); here: one branch per accepted name."""
         A = list(op.args)
         d = A[0]
         rest = A[1:]
         name = op.name
         if rest and rest[0].t.base == "string":
-            if not rest[0].constval:
-                raise NotImplementedError("noise with a non-constant name")
-            name = rest[0].vals[0]
+            if not rest[0].constval and runtime_name is None:
+                names = [("perlin", "snoise"), ("uperlin", "noise"), ("simplex", "simplexnoise"),
+                         ("usimplex", "usimplexnoise"), ("cell",), ("hash",), ("gabor",)]
+                if periodic:
+                    names = [n for n in names if "simplex" not in n[0]]
+                self.w("const char* nm_ = %s;" % self.R(rest[0]))
+                for k, alts in enumerate(names):
+                    cond = " || ".join('str_eq(nm_, "%s")' % a for a in alts)
+                    self.w("%sif (%s) {" % ("} else " if k else "", cond))
+                    self.ind += 1
+                    self.noise_impl(op, periodic, runtime_name=alts[0])
+                    self.ind -= 1
+                self.w("}")   # unknown name: "Unknown noise type" error in the reference, result untouched
+                return
+            name = runtime_name if runtime_name is not None else rest[0].vals[0]
             rest = rest[1:]
-            if periodic and not name.startswith("p"):
-                pass
         # strip optional token/value pairs
         coords = []
         for a in rest:

@@ -55,6 +55,10 @@ IMAGE_CASES = {
     "pnoise-cell": dict(shader="testpnoise", res=512,
                         params=dict(noisename="cell", offset=0.0, scale=1.0)),
     "pnoise-perlin": dict(shader="testpnoise", res=512, params=dict(noisename="perlin")),
+    # noise("name", ...) with a name picked per point from a string array: run-time dispatch
+    # (GenericNoise / GenericPNoise, opnoise.cpp:704-900)
+    "noise-generic": dict(shader="noise_generic_test", res=512, params={}),
+    "pnoise-generic": dict(shader="pnoise_generic_test", res=512, params={}),
 }
 
 
@@ -104,6 +108,7 @@ TESTSUITE_TEXT = {
     "printf-whole-array": (1, 1, 0), "select": (2, 2, 0), "shortcircuit": (2, 2, 0),
     "spline-boundarybug": (1, 1, 0), "splineinverse": (3, 1, 1), "ternary": (2, 2, 0),
     "transitive-assign": (1, 1, 0), "trig": (1, 1, 0), "typecast": (2, 2, 0), "userdata-defaults": (1, 1, 0),
+    "userdata": (2, 2, 0),
     "vecctr": (1, 1, 0), "vector": (1, 1, 0),
 }
 
@@ -188,3 +193,30 @@ def layers_group(with_outputs=True, derivs=True):
             outputs = [dict(name="alayer.f_out", offset=0, stride=16, derivs=False),
                        dict(name="alayer.c_out", offset=4, stride=16, derivs=False)]
     return layers, list(LAYERS_LAZY["connections"]), outputs
+
+
+def testshade_userdata(n, var, uni, extra=()):
+    """What testshade's SimpleRenderer::get_userdata supplies (src/testshade/simplerend.cpp:517-590):
+    s = u and t = v with their derivatives, face_idx = int(4u), and three partially available
+    values used by testsuite/userdata-partial: red = u where P.x > 0.5, green = v where
+    P.x < 0.5, blue = 1-u where int(P.y*12) is even.  `extra`: --userdata NAME VALUE entries
+    (name, numpy value), uniform over the grid.  -> entries for pack_userdata()."""
+    def field(name, comps=1):
+        if name in var:
+            return np.asarray(var[name], np.float32).reshape(comps, n).T.copy()
+        vals = list(uni.get(name, [0.0] * comps)) + [0.0] * comps
+        return np.tile(np.asarray(vals[:comps], np.float32), (n, 1))
+    u, dudx, dudy = field("u"), field("dudx"), field("dudy")
+    v, dvdx, dvdy = field("v"), field("dvdx"), field("dvdy")
+    P = field("P", 3)
+    ents = [dict(name="s", data=np.hstack([u, dudx, dudy]), derivs=True),
+            dict(name="t", data=np.hstack([v, dvdx, dvdy]), derivs=True),
+            dict(name="face_idx", data=(np.float32(4) * u[:, 0]).astype(np.int32)),
+            dict(name="red", data=np.hstack([u, dudx, dudy]), derivs=True, valid=(P[:, 0] > np.float32(0.5)).astype(np.int32)),
+            dict(name="green", data=np.hstack([v, dvdx, dvdy]), derivs=True, valid=(P[:, 0] < np.float32(0.5)).astype(np.int32)),
+            dict(name="blue", data=np.hstack([np.float32(1) - u, -dudx, -dudy]), derivs=True,
+                 valid=(((P[:, 1] * np.float32(12)).astype(np.int32) % 2) == 0).astype(np.int32))]
+    for name, val in extra:
+        a = np.asarray(val)
+        ents.append(dict(name=name, data=np.tile(a.reshape(1, -1), (n, 1))))
+    return ents

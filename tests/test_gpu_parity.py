@@ -375,11 +375,14 @@ def test_testsuite_text_goldens_through_the_device(b200lib, cuda_device, d):
     character-for-character equal to the reference's golden text."""
     import torch
     gx, gy, center = helpers.TESTSUITE_TEXT[d]
-    g = b200lib.ShaderGroup([dict(oso=helpers.oso("ts_" + d), name="l0")], (), (), options="fma=0,journal=1")
     var, uni = b200lib.grid_globals(gx, gy, center=bool(center))
+    # what testshade's SimpleRenderer::get_userdata supplies (s, t, face_idx, ...)
+    arena, descs = b200lib.pack_userdata(helpers.testshade_userdata(gx * gy, var, uni))
+    g = b200lib.ShaderGroup([dict(oso=helpers.oso("ts_" + d), name="l0")], (), (), options="fma=0,journal=1",
+                            userdata=descs)
     dvar = {k: torch.from_numpy(v).to(cuda_device) for k, v in var.items()}
     out = torch.zeros(16, dtype=torch.float32, device=cuda_device)
-    g.execute(gx * gy, dvar, uni, out)
+    g.execute(gx * gy, dvar, uni, out, userdata=torch.from_numpy(arena).to(cuda_device))
     assert g.journal().rstrip("\n") == helpers.testsuite_text_want(d).rstrip("\n")
 
 

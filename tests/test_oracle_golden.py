@@ -133,6 +133,7 @@ def test_testsuite_text_goldens(d):
     gx, gy, center = helpers.TESTSUITE_TEXT[d]
     g = oracle.OracleGroup([dict(oso=helpers.oso("ts_" + d), name="l0")])
     var, uni = oracle.testshade_globals(gx, gy, center=bool(center))
+    uni["userdata"] = helpers.testshade_userdata(gx * gy, var, uni)    # SimpleRenderer::get_userdata
     txt = g.run_capture(gx * gy, var, uni)
     assert txt.rstrip("\n") == helpers.testsuite_text_want(d).rstrip("\n")
 

@@ -82,6 +82,10 @@ SHADERS = {
     "color_ops": "repo:tests/shaders/color_ops.osl",
     "matrix_ops": "repo:tests/shaders/matrix_ops.osl",
     "texture_ops": "repo:tests/shaders/texture_ops.osl",
+    "noise_generic_test": "noise-generic/test.osl",
+    "pnoise_generic_test": "pnoise-generic/test.osl",
+    "userdata_partial_test": "userdata-partial/test.osl",
+    "userdata_passthrough_test": "userdata-passthrough/test.osl",
 }
 # scene descriptions + model data of the testrender configs (test input data)
 SCENES = {
@@ -144,6 +148,9 @@ IMAGES = {
     "pnoise": "pnoise/ref/out.tif",
     "pnoise-cell": "pnoise-cell/ref/out.tif",
     "pnoise-perlin": "pnoise-perlin/ref/out.tif",
+    "userdata-partial": "userdata-partial/ref/out.lazy_userdata_ON.tif",
+    "noise-generic": "noise-generic/ref/out.tif",
+    "pnoise-generic": "pnoise-generic/ref/out.tif",
 }
 TEXTS = {
     "hash": "hash/ref/out.txt",
@@ -169,6 +176,7 @@ TESTSUITE_TEXT = {
     "printf-whole-array": (1, 1, 0), "select": (2, 2, 0), "shortcircuit": (2, 2, 0),
     "spline-boundarybug": (1, 1, 0), "splineinverse": (3, 1, 1), "ternary": (2, 2, 0),
     "transitive-assign": (1, 1, 0), "trig": (1, 1, 0), "typecast": (2, 2, 0), "userdata-defaults": (1, 1, 0),
+    "userdata": (2, 2, 0),
     "vecctr": (1, 1, 0), "vector": (1, 1, 0),
 }
 # float / half EXR goldens of testshade image tests (stored as float32 npz, full size)
