@@ -182,6 +182,26 @@ int b200_group_execute_host(b200_group* g, int device, long long npoints,
 int b200_group_execute_host_userdata(b200_group* g, int device, long long npoints, const b200_globals* sg,
                                      const void* userdata_base, long long userdata_bytes, void* output_base);
 
+/* The general host-pointer call: the batch's points carry the shade indices
+ * first_shadeindex .. first_shadeindex + npoints - 1 (what a renderer shading a tile of a larger
+ * arena passes as wide_shadeindex, src/testshade/testshade.cpp:1868): outputs land at
+ * output_base + offset + stride * shadeindex and userdata is read at the same index.
+ * userdata_base may be NULL. */
+int b200_group_execute_host_at(b200_group* g, int device, long long npoints, const b200_globals* sg,
+                               long long first_shadeindex, const void* userdata_base, long long userdata_bytes,
+                               void* output_base);
+
+/* Group option userdata=record: instead of the caller describing its arrays (b200_userdata in
+ * the group description) the library lays out one record per point holding every interpolated
+ * parameter of the group (validity word + value with derivatives).  These calls say how many
+ * fields there are, how long a record is and where each field went; pass the records as
+ * userdata_base (to the host calls: the records of the batch only, record 0 = its first point).  Also: the named coordinate systems the group references, which the caller
+ * must supply in b200_globals.transforms (RendererServices::get_matrix). */
+int b200_group_userdata_fields(const b200_group* g, long long* record_bytes);
+int b200_group_userdata_field(const b200_group* g, int i, b200_userdata* out);
+int b200_group_num_spaces(const b200_group* g);
+const char* b200_group_space_name(const b200_group* g, int i);
+
 /* Text written by the group's printf() ops on `device` since the previous call, ordered by
  * shade index and, within a point, by execution order (what single-threaded testshade
  * prints).  The device only records (format id, argument words); formatting happens here,

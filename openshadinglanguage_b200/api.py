@@ -524,6 +524,61 @@ class Renderer:
         return res
 
 
+def write_scene_blob(path, scene, arrays, oso_lookup, xres, yres, aa, max_bounces=None, rr_depth=None,
+                     no_jitter=False, show_globals=0):
+    """The prepared scene as the flat binary examples/testrender_b200.cpp reads: the arrays of
+    b200_render_scene, the camera and options, then one group description per material."""
+    import struct
+    if max_bounces is None:
+        max_bounces = scene.options.get("max_bounces", 1000000)
+    if rr_depth is None:
+        rr_depth = scene.options.get("rr_depth", 5)
+    out = [struct.pack("<i", 0x42323030)]
+
+    def arr(name, dtype):
+        a = np.ascontiguousarray(arrays[name], dtype).ravel()
+        out.append(struct.pack("<q", a.size))
+        out.append(a.tobytes())
+
+    def s(text):
+        b = text.encode()
+        out.append(struct.pack("<i", len(b)) + b)
+    for name, dt in (("verts", np.float32), ("normals", np.float32), ("uvs", np.float32), ("triangles", np.int32),
+                     ("n_triangles", np.int32), ("uv_triangles", np.int32), ("shaderids", np.int32),
+                     ("meshids", np.int32), ("mesh_surfacearea", np.float32), ("bvh_nodes", np.float32),
+                     ("bvh_indices", np.uint32), ("lightprims", np.uint32), ("shader_is_light", np.int32)):
+        arr(name, dt)
+    out.append(struct.pack("<10f", *[float(x) for x in list(scene.eye) + list(scene.dir) + list(scene.up)], float(scene.fov)))
+    out.append(struct.pack("<9i", xres, yres, aa, max_bounces, rr_depth, int(no_jitter), show_globals,
+                           scene.background_shader, scene.background_resolution))
+    out.append(struct.pack("<i", len(scene.materials)))
+    for layers, conns in scene.materials:
+        out.append(struct.pack("<i", len(layers)))
+        for l in layers:
+            s(oso_lookup(l["shader"]))
+            s(l["name"])
+            params = l["params"] or {}
+            out.append(struct.pack("<i", len(params)))
+            for k, v in params.items():
+                if not isinstance(v, (list, tuple, np.ndarray)):
+                    v = [v]
+                s(k)
+                if isinstance(v[0], str):
+                    out.append(struct.pack("<ii", 2, len(v)))
+                    for x in v:
+                        s(x)
+                elif isinstance(v[0], (int, np.integer)) and not isinstance(v[0], bool):
+                    out.append(struct.pack("<ii", 0, len(v)) + struct.pack("<%di" % len(v), *[int(x) for x in v]))
+                else:
+                    out.append(struct.pack("<ii", 1, len(v)) + struct.pack("<%df" % len(v), *[float(x) for x in v]))
+        out.append(struct.pack("<i", len(conns)))
+        for c in conns:
+            for x in c:
+                s(x)
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
 def tile_list(xres, yres, tile=64):
     """All tiles of an image, row-major, as an int32 [n, 4] array of (x0, y0, w, h)."""
     ts = [(x, y, min(tile, xres - x), min(tile, yres - y)) for y in range(0, yres, tile) for x in range(0, xres, tile)]

@@ -170,6 +170,7 @@ struct b200_group {
     };
     std::map<int, Stage> stages;
     std::mutex host_mu;
+    long long userdata_record = 0;   // option userdata=record: bytes per point
 };
 
 static std::map<std::string, std::string>
@@ -317,6 +318,35 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
         }
         G->g.block = G->block;
         G->g.finalize();
+        if (opt.count("userdata") && opt["userdata"] == "record") {
+            // The library lays the userdata out itself: one record per point holding, for every
+            // interpolated parameter of the group, a validity word and the value with derivatives
+            // (what RendererServices::get_userdata(derivatives=true, ...) fills).  The caller asks
+            // b200_group_userdata_field() where each field went and passes records at execute.
+            long long off = 0;
+            for (Layer& l : G->g.layers)
+                for (Symbol& sy : l.m.syms) {
+                    if (!sy.is_param() || !sy.interpolated || sy.conn_layer >= 0 || sy.type.arraylen)
+                        continue;
+                    const bool is_int = sy.type.base == Base::Int;
+                    if (!is_int && !(sy.type.base == Base::Float || sy.type.is_triple()))
+                        continue;
+                    bool dup = false;
+                    for (const UserData& u : G->g.userdata)
+                        dup |= u.name == sy.name && u.ncomp == sy.type.ncomp() && u.is_int == is_int;
+                    if (dup)
+                        continue;
+                    UserData d;
+                    d.name = sy.name; d.ncomp = sy.type.ncomp(); d.is_int = is_int; d.derivs = !is_int;
+                    d.valid_offset = off;
+                    d.offset       = off + 4;
+                    off += 4 + 4 * d.ncomp * (d.derivs ? 3 : 1);
+                    G->g.userdata.push_back(d);
+                }
+            for (UserData& u : G->g.userdata)
+                u.stride = u.valid_stride = off;
+            G->userdata_record = off;
+        }
         G->source = generate_cuda(G->g);
     } catch (const std::exception& e) {
         return fail(B200_ERR_COMPILE, e.what());
@@ -641,9 +671,9 @@ b200_group_execute(b200_group* g, int device, void* stream, long long npoints, c
 // chunks over three streams so H2D, kernel and D2H overlap.
 static int
 execute_host_impl(b200_group* g, int device, long long npoints, const b200_globals* sg, const void* userdata_host,
-                  long long userdata_bytes, void* output_base)
+                  long long userdata_bytes, void* output_base, long long first)
 {
-    if (!g || !sg || npoints < 0)
+    if (!g || !sg || npoints < 0 || first < 0)
         return fail(B200_ERR_INVALID, "b200_group_execute_host: bad arguments");
     if (npoints == 0)
         return B200_OK;
@@ -716,7 +746,9 @@ execute_host_impl(b200_group* g, int device, long long npoints, const b200_globa
         }
         if (cudaMemcpy(st.d_ud, userdata_host, (size_t)userdata_bytes, cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(B200_ERR_CUDA, "userdata upload failed");
-        d_userdata = st.d_ud;
+        // userdata=record: the caller hands over the records of this batch only (record 0 = the
+        // point with shade index `first`); the kernel indexes by shade index, so rebase
+        d_userdata = g->userdata_record > 0 ? st.d_ud - g->userdata_record * first : st.d_ud;
     }
     auto out_bytes_of = [&](int k) -> size_t {
         const Symbol& sy = g->g.layers[g->g.outputs[k].first].m.syms[g->g.outputs[k].second];
@@ -750,15 +782,15 @@ execute_host_impl(b200_group* g, int device, long long npoints, const b200_globa
         size_t region                      = 0;
         for (const Cluster& c : clusters) {
             for (int k : c.outs)
-                adjust[k] = (long long)region - c.lo - c.stride * b;
+                adjust[k] = (long long)region - c.lo - c.stride * (first + b);
             region += (size_t)n * c.stride;
         }
-        rc = launch_group(g, device, s, n, &dg, nullptr, d_userdata, dout, b, adjust);
+        rc = launch_group(g, device, s, n, &dg, nullptr, d_userdata, dout, first + b, adjust);
         if (rc != B200_OK)
             return rc;
         region = 0;
         for (const Cluster& c : clusters) {
-            char* hdst = (char*)output_base + c.lo + c.stride * b;
+            char* hdst = (char*)output_base + c.lo + c.stride * (first + b);
             if (c.dense) {
                 // the fields tile the record: one contiguous copy of n whole records
                 size_t bytes  = (size_t)(n - 1) * c.stride + (size_t)(c.hi - c.lo);
@@ -793,14 +825,52 @@ execute_host_impl(b200_group* g, int device, long long npoints, const b200_globa
 int
 b200_group_execute_host(b200_group* g, int device, long long npoints, const b200_globals* sg, void* output_base)
 {
-    return execute_host_impl(g, device, npoints, sg, nullptr, 0, output_base);
+    return execute_host_impl(g, device, npoints, sg, nullptr, 0, output_base, 0);
 }
 
 int
 b200_group_execute_host_userdata(b200_group* g, int device, long long npoints, const b200_globals* sg,
                                  const void* userdata_base, long long userdata_bytes, void* output_base)
 {
-    return execute_host_impl(g, device, npoints, sg, userdata_base, userdata_bytes, output_base);
+    return execute_host_impl(g, device, npoints, sg, userdata_base, userdata_bytes, output_base, 0);
+}
+
+/* introspection of the userdata layout and of the named spaces (the C++ API mirror feeds them
+ * from RendererServices::get_userdata / get_matrix) */
+int
+b200_group_userdata_fields(const b200_group* g, long long* record_bytes)
+{
+    if (record_bytes)
+        *record_bytes = g ? g->userdata_record : 0;
+    return g ? (int)g->g.userdata.size() : 0;
+}
+int
+b200_group_userdata_field(const b200_group* g, int i, b200_userdata* out)
+{
+    if (!g || !out || i < 0 || i >= (int)g->g.userdata.size())
+        return fail(B200_ERR_INVALID, "b200_group_userdata_field: bad index");
+    const UserData& u = g->g.userdata[i];
+    out->name = u.name.c_str(); out->ncomp = u.ncomp; out->is_int = u.is_int; out->offset = u.offset;
+    out->stride = u.stride; out->derivs = u.derivs; out->valid_offset = u.valid_offset; out->valid_stride = u.valid_stride;
+    return B200_OK;
+}
+int
+b200_group_num_spaces(const b200_group* g)
+{
+    return g ? (int)g->g.spaces.size() : 0;
+}
+const char*
+b200_group_space_name(const b200_group* g, int i)
+{
+    return (g && i >= 0 && i < (int)g->g.spaces.size()) ? g->g.spaces[i].c_str() : "";
+}
+
+int
+b200_group_execute_host_at(b200_group* g, int device, long long npoints, const b200_globals* sg,
+                           long long first_shadeindex, const void* userdata_base, long long userdata_bytes,
+                           void* output_base)
+{
+    return execute_host_impl(g, device, npoints, sg, userdata_base, userdata_bytes, output_base, first_shadeindex);
 }
 
 }  // extern "C"
