@@ -345,7 +345,85 @@ private:
     void op_noise(const Opcode& op, bool periodic);
     void op_noise_named(const Opcode& op, bool periodic, const std::string& runtime_name);
     void emit_copy(int dl, const Symbol& d, int sl, const Symbol& s);
+    void emit_userdata_load(const UserData& ud, const Symbol& s, const std::string& r, const std::string& flag);
+    // messages (opmessage.cpp): one group-data slot per constant message name, typed by the
+    // first setmessage of that name in layer order
+    struct MsgSlot {
+        int id;
+        Base base;
+        int ncomp;
+    };
+    std::map<std::string, MsgSlot> messages;
+    void scan_messages();
+    std::string message_fields();
 };
+
+// value of userdata entry `ud` for this point -> r; `flag` says whether the point has it
+void
+Gen::emit_userdata_load(const UserData& ud, const Symbol& s, const std::string& r, const std::string& flag)
+{
+    w("bool " + flag + " = L.userdata_base != nullptr;");
+    if (ud.valid_offset >= 0)
+        w("if (" + flag + ") " + flag + " = __ldg((const int*)((const char*)L.userdata_base + "
+          + std::to_string(ud.valid_offset) + "ll + " + std::to_string(ud.valid_stride) + "ll * (long long)sg.shadeindex)) != 0;");
+    w("if (" + flag + ") {");
+    ++ind;
+    w("const float* p_ = (const float*)((const char*)L.userdata_base + " + std::to_string(ud.offset) + "ll + "
+      + std::to_string(ud.stride) + "ll * (long long)sg.shadeindex);");
+    auto ld = [&](int i) { return "__ldg(p_ + " + std::to_string(i) + ")"; };
+    if (ud.is_int)
+        w(r + " = __float_as_int(" + ld(0) + ");");
+    else if (ud.ncomp == 1) {
+        if (s.has_derivs)
+            w(r + " = mkd(" + ld(0) + ", " + (ud.derivs ? ld(1) : std::string("0.0f")) + ", "
+              + (ud.derivs ? ld(2) : std::string("0.0f")) + ");");
+        else
+            w(r + " = " + ld(0) + ";");
+    } else {
+        auto v3 = [&](int b) { return "mkv(" + ld(b) + ", " + ld(b + 1) + ", " + ld(b + 2) + ")"; };
+        if (s.has_derivs)
+            w(r + " = mkdv(" + v3(0) + ", " + (ud.derivs ? v3(3) : std::string("mkv(0.0f)")) + ", "
+              + (ud.derivs ? v3(6) : std::string("mkv(0.0f)")) + ");");
+        else
+            w(r + " = " + v3(0) + ";");
+    }
+    --ind;
+    w("}");
+}
+
+void
+Gen::scan_messages()
+{
+    messages.clear();
+    for (Layer& l : g.layers) {
+        if (l.unused)
+            continue;
+        for (const Opcode& op : l.m.ops) {
+            if (op.name != "setmessage" || op.args.size() != 2)
+                continue;
+            const Symbol& nm = l.m.syms[op.args[0]];
+            const Symbol& v  = l.m.syms[op.args[1]];
+            if (nm.type.base != Base::String || !nm.const_value() || nm.svals.empty() || v.type.arraylen)
+                continue;
+            if (!(v.type.base == Base::Int || v.type.base == Base::Float || v.type.is_triple()))
+                continue;   // closures, strings, matrices and arrays as messages are not built
+            if (!messages.count(nm.svals[0]) && messages.size() < 31)
+                messages[nm.svals[0]] = MsgSlot { (int)messages.size(), v.type.base, v.type.ncomp() };
+        }
+    }
+}
+std::string
+Gen::message_fields()
+{
+    std::string s;
+    if (messages.empty())
+        return s;
+    s += "    unsigned msgset;\n";
+    for (auto& kv : messages)
+        s += std::string("    ") + (kv.second.base == Base::Int ? "int" : (kv.second.ncomp == 3 ? "V3" : "float")) + " M"
+             + std::to_string(kv.second.id) + ";\n";
+    return s;
+}
 
 void
 Gen::emit_copy(int dl, const Symbol& d, int sl, const Symbol& s)
@@ -729,7 +807,43 @@ Gen::emit_printf(const Opcode& op)
     if (f.type.base != Base::String || !f.const_value())
         unsupported("printf with a format that is not known at compile time");
     JournalFormat jf;
-    jf.fmt = f.svals.empty() ? "" : f.svals[0];
+    jf.fmt        = f.svals.empty() ? "" : f.svals[0];
+    jf.kind       = op.name == "error" ? 1 : (op.name == "warning" ? 2 : 0);
+    jf.shadername = L->m.shadername;
+    // The format is applied on the host with the C library: check every conversion against its
+    // argument here, so that a malformed or hand-written .oso cannot make the formatter read a
+    // string pointer out of a float or write through %n (the reference's llvm_gen_printf raises
+    // "Mismatch between format string and arguments" in the same spot).
+    {
+        size_t ai = 1;
+        for (size_t i = 0; i < jf.fmt.size();) {
+            if (jf.fmt[i] != '%') {
+                ++i;
+                continue;
+            }
+            if (i + 1 < jf.fmt.size() && jf.fmt[i + 1] == '%') {
+                i += 2;
+                continue;
+            }
+            size_t j = i + 1;
+            while (j < jf.fmt.size() && strchr("-+ #0123456789.", jf.fmt[j]))
+                ++j;
+            const char conv = j < jf.fmt.size() ? jf.fmt[j] : 0;
+            if (!conv || !strchr("diouxXcfeEgGsm", conv))
+                unsupported("printf format \"" + jf.fmt + "\": unsupported conversion");
+            if (ai >= op.args.size())
+                unsupported("Mismatch between format string and arguments");
+            const Base b = S(op.args[ai++]).type.base;
+            const bool ok = b == Base::String ? conv == 's'
+                                              : (b == Base::Int ? strchr("diouxXcfeEgG", conv) != nullptr
+                                                                : strchr("feEgGdixXm", conv) != nullptr);
+            if (!ok)
+                unsupported("Mismatch between format string and arguments");
+            i = j + 1;
+        }
+        if (ai != op.args.size())
+            unsupported("Mismatch between format string and arguments");
+    }
     std::vector<std::string> words;
     for (size_t a = 1; a < op.args.size(); ++a) {
         const Symbol& s = S(op.args[a]);
@@ -772,7 +886,7 @@ Gen::emit_matrix_op(const Opcode& op)
     auto A               = [&](int i) -> Symbol& { return S(op.args[i]); };
     auto fl              = [&](int i) { return comp(op.args[i], 0, false); };
     auto is_m            = [&](int i) { return A(i).type.base == Base::Matrix; };
-    if (n == "printf" && journal_ok) {
+    if ((n == "printf" || n == "error" || n == "warning") && journal_ok) {
         emit_printf(op);
         return;
     }
@@ -1371,7 +1485,74 @@ Gen::emit_op(const Opcode& op)
         }
         w("}");
         w(R(op.args[0]) + " = c_;");
-    } else if (n == "printf" && journal_ok) {
+    } else if (n == "setmessage") {
+        // osl_setmessage (opmessage.cpp): the first set of a name wins, a second one is an error
+        // in the reference (reported, value ignored)
+        const Symbol& nm = S(op.args[0]);
+        auto it = (nm.type.base == Base::String && nm.const_value() && !nm.svals.empty()) ? messages.find(nm.svals[0])
+                                                                                            : messages.end();
+        const Symbol& v = S(op.args[1]);
+        if (it != messages.end() && v.type.base == it->second.base && v.type.ncomp() == it->second.ncomp && !v.type.arraylen) {
+            std::string bit = std::to_string(1u << it->second.id) + "u";
+            std::string e   = R(op.args[1]);
+            if (v.has_derivs)
+                e = "nd(" + e + ")";
+            w("if (!(gd.msgset & " + bit + ")) { gd.M" + std::to_string(it->second.id) + " = " + e + "; gd.msgset |= " + bit + "; }");
+        } else
+            g.warnings.push_back("setmessage in layer '" + L->layername + "' is not supported on the device (name not constant, "
+                                 "or a closure / string / matrix / array value): ignored");
+    } else if (n == "getmessage") {
+        // osl_getmessage: 1 and the value when a message of that name AND type was set before
+        const bool has_source = op.args.size() == 4;
+        const Symbol& nm      = S(op.args[has_source ? 2 : 1]);
+        const Symbol& dst     = S(op.args.back());
+        auto it = (!has_source && nm.type.base == Base::String && nm.const_value() && !nm.svals.empty())
+                      ? messages.find(nm.svals[0])
+                      : messages.end();
+        if (it != messages.end() && dst.type.base == it->second.base && dst.type.ncomp() == it->second.ncomp
+            && !dst.type.arraylen) {
+            std::string bit = std::to_string(1u << it->second.id) + "u";
+            std::string val = "gd.M" + std::to_string(it->second.id);
+            if (dst.has_derivs)
+                val = dst.type.ncomp() == 3 ? "mkdv(" + val + ")" : "mkd(" + val + ")";
+            w("if (gd.msgset & " + bit + ") { " + R(op.args.back()) + " = " + val + "; " + R(op.args[0]) + " = 1; } else "
+              + R(op.args[0]) + " = 0;");
+        } else
+            w(R(op.args[0]) + " = 0;");
+    } else if (n == "getattribute") {
+        // llvm_gen_getattribute (llvm_gen.cpp:3303-3420) -> RendererServices::get_attribute.  On this
+        // back end a renderer attribute is either one of the few the harness renderers answer for
+        // every object ("osl:version", "shading:index") or per-point userdata (testshade's
+        // SimpleRenderer falls back to get_userdata, simplerend.cpp:480-503): the b200_userdata
+        // entry of that name and type.  Object / array-index lookups and names only known at run
+        // time find nothing.
+        const Symbol& dst = S(op.args.back());
+        const Symbol& nm  = S(op.args[1]);
+        const std::string res = R(op.args[0]);
+        bool done = false;
+        if (op.args.size() == 3 && nm.type.base == Base::String && nm.const_value() && !nm.svals.empty()
+            && !dst.type.arraylen && !material_mode) {
+            const std::string& name = nm.svals[0];
+            if (name == "osl:version" && dst.type.base == Base::Int) {
+                w(R(op.args[2]) + " = 11600;");
+                w(res + " = 1;");
+                done = true;
+            } else if (name == "shading:index" && dst.type.base == Base::Int) {
+                w(R(op.args[2]) + " = sg.shadeindex;");
+                w(res + " = 1;");
+                done = true;
+            } else
+                for (const UserData& u : g.userdata)
+                    if (!done && u.name == name && u.ncomp == dst.type.ncomp() && u.is_int == (dst.type.base == Base::Int)
+                        && (dst.type.base == Base::Int || dst.type.base == Base::Float || dst.type.is_triple())) {
+                        emit_userdata_load(u, dst, R(op.args[2]), "ga_");
+                        w(res + " = ga_ ? 1 : 0;");
+                        done = true;
+                    }
+        }
+        if (!done)
+            w(res + " = 0;");
+    } else if ((n == "printf" || n == "error" || n == "warning") && journal_ok) {
         emit_printf(op);
     } else if (n == "printf" || n == "error" || n == "warning" || n == "fprintf") {
         // error / warning / fprintf, and printf inside renderer materials, have no effect on
@@ -1433,36 +1614,11 @@ Gen::gen_layer(int layer)
                     && s.type.base != Base::String && s.type.base != Base::Matrix && s.type.base != Base::Closure)
                     ud = &u;
         if (ud) {
-            w("bool got_" + std::to_string(si) + " = L.userdata_base != nullptr;");
-            if (ud->valid_offset >= 0)
-                w("if (got_" + std::to_string(si) + ") got_" + std::to_string(si)
-                  + " = __ldg((const int*)((const char*)L.userdata_base + " + std::to_string(ud->valid_offset) + "ll + "
-                  + std::to_string(ud->valid_stride) + "ll * (long long)sg.shadeindex)) != 0;");
-            w("if (got_" + std::to_string(si) + ") {");
-            ++ind;
-            w("const float* p_ = (const float*)((const char*)L.userdata_base + " + std::to_string(ud->offset) + "ll + "
-              + std::to_string(ud->stride) + "ll * (long long)sg.shadeindex);");
-            auto ld = [&](int i) { return "__ldg(p_ + " + std::to_string(i) + ")"; };
-            if (ud->is_int)
-                w(r + " = __float_as_int(" + ld(0) + ");");
-            else if (ud->ncomp == 1) {
-                if (s.has_derivs)
-                    w(r + " = mkd(" + ld(0) + ", " + (ud->derivs ? ld(1) : std::string("0.0f")) + ", "
-                      + (ud->derivs ? ld(2) : std::string("0.0f")) + ");");
-                else
-                    w(r + " = " + ld(0) + ";");
-            } else {
-                auto v3 = [&](int b) { return "mkv(" + ld(b) + ", " + ld(b + 1) + ", " + ld(b + 2) + ")"; };
-                if (s.has_derivs)
-                    w(r + " = mkdv(" + v3(0) + ", " + (ud->derivs ? v3(3) : std::string("mkv(0.0f)")) + ", "
-                      + (ud->derivs ? v3(6) : std::string("mkv(0.0f)")) + ");");
-                else
-                    w(r + " = " + v3(0) + ";");
-            }
-            --ind;
-            w("} else {");
+            emit_userdata_load(*ud, s, r, "got_" + std::to_string(si));
+            w("if (!got_" + std::to_string(si) + ") {");
             ++ind;
         }
+
         if (s.type.arraylen)
             for (size_t i = 0; i < vals.size(); ++i)
                 w(r + "[" + std::to_string(i) + "] = " + vals[i] + ";");
@@ -1630,6 +1786,7 @@ Gen::run()
     g.lobe_bound = g.closure_adds = 0;
     g.closure_in_loop             = false;
     std::ostringstream bodies;
+    scan_messages();
     std::string gd = "struct GD {\n    unsigned ran;\n";
     for (int l = 0; l < nlayers; ++l) {
         if (g.layers[l].unused)
@@ -1642,6 +1799,7 @@ Gen::run()
                 gd += "    " + ctype(s) + " L" + std::to_string(l) + "_" + ident(s.name) + arr + ";\n";
             }
     }
+    gd += message_fields();
     gd += "};\n";
     for (int l = 0; l < nlayers; ++l)
         if (!g.layers[l].unused)
@@ -1784,6 +1942,8 @@ Gen::run()
     out << "        SG sg = sgn_;\n        sg.jseq = 0u;\n";
     emit_fetch("tile_ + gridDim.x");
     out << "        GD gd;\n        gd.ran = 0u;\n";
+    if (!messages.empty())
+        out << "        gd.msgset = 0u;\n";
     if (uses_closures)
         out << "        float pool_store_[OSLD_POOL_STORE];\n        ClosurePool pool_;\n        pool_.bind(pool_store_, 1);\n"
                "        pool_.reset();\n        sg.pool = &pool_;\n        sg.Ci = 0;\n";
@@ -1854,6 +2014,7 @@ Gen::run_material(const std::string& ns)
     int nlayers = (int)g.layers.size();
     if (nlayers > 32)
         throw std::runtime_error("B200 back end: more than 32 layers in a group is not supported yet");
+    scan_messages();
     std::string gd = "struct GD {\n    unsigned ran;\n";
     for (int l = 0; l < nlayers; ++l) {
         if (g.layers[l].unused)
@@ -1866,6 +2027,7 @@ Gen::run_material(const std::string& ns)
                 gd += "    " + ctype(s) + " L" + std::to_string(l) + "_" + ident(s.name) + arr + ";\n";
             }
     }
+    gd += message_fields();
     gd += "};\n";
     for (int l = 0; l < nlayers; ++l)
         if (!g.layers[l].unused)
@@ -1876,6 +2038,8 @@ Gen::run_material(const std::string& ns)
     std::ostringstream out;
     out << "namespace " << ns << " {\n" << gd << o.str();
     out << "static __device__ OSLD_ENTRY_INLINE void entry(SG& sg)\n{\n    GD gd;\n    gd.ran = 0u;\n    B200Launch L;\n";
+    if (!messages.empty())
+        out << "    gd.msgset = 0u;\n";
     out << "    layer_" << (nlayers - 1) << "(sg, gd, L);\n}\n}  // namespace " << ns << "\n";
     return out.str();
 }

@@ -126,6 +126,8 @@ struct JournalArg {
 struct JournalFormat {
     std::string fmt;
     std::vector<JournalArg> args;
+    int kind = 0;            // 0 printf, 1 error(), 2 warning()
+    std::string shadername;  // for the "Shader error [name]: " prefix
 };
 
 // one b200_userdata entry (include/osl_b200.h)

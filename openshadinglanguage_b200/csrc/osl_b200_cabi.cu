@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -171,6 +172,8 @@ struct b200_group {
     std::map<int, Stage> stages;
     std::mutex host_mu;
     long long userdata_record = 0;   // option userdata=record: bytes per point
+    bool error_repeats = false;      // option error_repeats=1: report identical error()/warning() texts again
+    std::set<std::string> messages_seen;
 };
 
 static std::map<std::string, std::string>
@@ -268,6 +271,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             if (jw > 1)
                 G->journal_words = (unsigned)jw;
         }
+        if (opt.count("error_repeats"))
+            G->error_repeats = atoi(opt["error_repeats"].c_str()) != 0;
         if (opt.count("block"))
             G->block = atoi(opt["block"].c_str());
         if (opt.count("stage"))
@@ -405,7 +410,7 @@ journal_format(const Group& g, const JournalFormat& jf, const unsigned* w, size_
             continue;
         }
         size_t j = i + 1;
-        while (j < f.size() && !strchr("cdefgimnopsuvxXEG", f[j]))
+        while (j < f.size() && !strchr("cdefgimopsuxXEG", f[j]))
             ++j;
         std::string spec = f.substr(i, j + 1 - i);
         char conv        = j < f.size() ? f[j] : 'g';
@@ -495,8 +500,25 @@ b200_group_journal(b200_group* g, int device)
                      [](const Ref& a, const Ref& b) { return a.si != b.si ? (int)a.si < (int)b.si : a.seq < b.seq; });
     for (const Ref& r : refs) {
         unsigned fmt = rec[r.at + 3];
-        if (fmt < g->g.jformats.size())
-            journal_format(g->g, g->g.jformats[fmt], rec.data() + r.at + 4, rec[r.at] - 4, g->journal_text);
+        if (fmt >= g->g.jformats.size())
+            continue;
+        const JournalFormat& jf = g->g.jformats[fmt];
+        if (jf.kind == 0) {
+            journal_format(g->g, jf, rec.data() + r.at + 4, rec[r.at] - 4, g->journal_text);
+            continue;
+        }
+        // error() / warning(): what the reference's error handler prints for testshade, a
+        // message reported before is dropped (attribute error_repeats = 0; option error_repeats=1)
+        std::string msg = jf.kind == 1 ? "ERROR: Shader error [" : "WARNING: Shader warning [";
+        msg += jf.shadername + "]: ";
+        journal_format(g->g, jf, rec.data() + r.at + 4, rec[r.at] - 4, msg);
+        msg += "\n";
+        if (!g->error_repeats) {
+            if (g->messages_seen.count(msg))
+                continue;
+            g->messages_seen.insert(msg);
+        }
+        g->journal_text += msg;
     }
     if (head[1])
         g->journal_text += "[journal overflow: output truncated; raise the group option journal=WORDS]\n";

@@ -241,6 +241,19 @@ inline void pf_fmt(SG& sg, const char* spec, const char* v)
     snprintf(buf, sizeof buf, spec, v ? v : "");
     sg.ctx->out->append(buf);
 }
+// error() / warning(): prefix, message, newline; repeated messages are reported once
+// (error_repeats = 0; shadingsys.cpp ShadingSystemImpl::error)
+inline void report_message(SG& sg, const char* prefix, const std::string& msg)
+{
+    if (!(sg.ctx && sg.ctx->out))
+        return;
+    std::string full = std::string(prefix) + msg + "\n";
+    for (const std::string& s : sg.ctx->errseen)
+        if (s == full)
+            return;
+    sg.ctx->errseen.push_back(full);
+    sg.ctx->out->append(full);
+}
 inline void pf_f(SG& sg, const char* spec, float v) { pf_fmt(sg, spec, (double)v); }
 inline void pf_f(SG& sg, const char* spec, const Df& v) { pf_fmt(sg, spec, (double)v.val); }
 inline void pf_f(SG& sg, const char* spec, int v) { pf_fmt(sg, spec, (double)v); }

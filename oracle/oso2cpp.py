@@ -389,6 +389,7 @@ class Gen:
         self.out = []
         self.ind = 1
         self.label = 0
+        self.messages = {}
 
     def w(self, s):
         self.out.append("    " * self.ind + s)
@@ -477,9 +478,11 @@ class Gen:
         one point at a time: simpleraytracer.cpp:1034)."""
         g = self.g
         o = self.out
+        self.scan_messages()
         o.append("namespace %s {" % ns)
         o.append("struct GD {")
         o.append("    bool ran[%d];" % max(1, len(g.layers)))
+        o.extend(self.message_fields())
         for l in g.layers:
             if l.unused:
                 continue
@@ -510,8 +513,10 @@ class Gen:
         o.append('#include "osl_oracle_runtime.h"')
         o.append("using namespace oslo;")
         o.append("namespace {")
+        self.scan_messages()
         o.append("struct GD {")
         o.append("    bool ran[%d];" % max(1, len(g.layers)))
+        o.extend(self.message_fields())
         for l in g.layers:
             if l.unused:
                 continue
@@ -1309,6 +1314,100 @@ class Gen:
         if not fmt.constval:
             raise NotImplementedError("printf with non-constant format")
         self.emit_format(fmt.vals[0], A[1:])
+
+    def scan_messages(self):
+        """one group-data slot per constant message name, typed by the first setmessage of that
+        name in layer order (opmessage.cpp keeps a per-execution list; same observable behaviour
+        for int / float / triple values)"""
+        self.messages = {}
+        for l in self.g.layers:
+            if l.unused:
+                continue
+            for op in l.m.ops:
+                if op.name != "setmessage" or len(op.args) != 2:
+                    continue
+                nm, v = op.args
+                if nm.t.base != "string" or not nm.constval or v.t.arr:
+                    continue
+                if not (v.t.base in ("int", "float") or v.t.triple):
+                    continue
+                if nm.vals[0] not in self.messages and len(self.messages) < 31:
+                    ctype = "int" if v.t.base == "int" else ("V3" if v.t.triple else "float")
+                    self.messages[nm.vals[0]] = (len(self.messages), ctype)
+
+    def message_fields(self):
+        out = []
+        if self.messages:
+            out.append("    unsigned msgset = 0u;")
+            for name, (k, ctype) in self.messages.items():
+                out.append("    %s M%d;" % (ctype, k))
+        return out
+
+    def _msg_ctype(self, s):
+        return "int" if s.t.base == "int" else ("V3" if s.t.triple else ("float" if s.t.base == "float" else None))
+
+    def op_setmessage(self, op):
+        nm, v = op.args
+        slot = self.messages.get(nm.vals[0]) if (nm.t.base == "string" and nm.constval) else None
+        if slot and not v.t.arr and self._msg_ctype(v) == slot[1]:
+            e = self.R(v)
+            if v.has_derivs:
+                e = "nd(%s)" % e
+            self.w("if (!(gd.msgset & %du)) { gd.M%d = %s; gd.msgset |= %du; }" % (1 << slot[0], slot[0], e, 1 << slot[0]))
+
+    def op_getmessage(self, op):
+        A = op.args
+        res, dst = self.R(A[0]), A[-1]
+        nm = A[1]
+        slot = self.messages.get(nm.vals[0]) if (len(A) == 3 and nm.t.base == "string" and nm.constval) else None
+        if slot and not dst.t.arr and self._msg_ctype(dst) == slot[1]:
+            val = "gd.M%d" % slot[0]
+            if dst.has_derivs:
+                val = ("Dv(%s)" if dst.t.triple else "Df(%s)") % val
+            self.w("if (gd.msgset & %du) { %s = %s; %s = 1; } else %s = 0;" % (1 << slot[0], self.R(dst), val, res, res))
+        else:
+            self.w("%s = 0;" % res)
+
+    def op_getattribute(self, op):
+        """llvm_gen_getattribute (llvm_gen.cpp:3303-3420) -> RendererServices::get_attribute.  The
+        harness renderer answers "osl:version" / "shading:index" and otherwise falls back to
+        per-point userdata of that name and type (simplerend.cpp:480-503); object and array
+        index lookups find nothing here."""
+        A = op.args
+        res, dst = self.R(A[0]), A[-1]
+        nm = A[1]
+        if len(A) == 3 and nm.t.base == "string" and nm.constval and not dst.t.arr:
+            name = nm.vals[0]
+            if name == "osl:version" and dst.t.base == "int":
+                self.w("%s = 11600; %s = 1;" % (self.R(dst), res))
+                return
+            if name == "shading:index" and dst.t.base == "int":
+                self.w("%s = sg.shadeindex; %s = 1;" % (self.R(dst), res))
+                return
+            if dst.t.base in ("int", "float") or dst.t.triple:
+                self.w("%s = bind_userdata(L, sg, %s, %s) ? 1 : 0;" % (res, cstr(name), self.R(dst)))
+                return
+        self.w("%s = 0;" % res)
+
+    def op_error(self, op, kind="error"):
+        """osl_error / osl_warning (llvm_gen_printf with the error / warning flavours): the
+        formatted message goes to the error handler, which testshade prints as
+        "ERROR: Shader error [<shader>]: <message>" followed by a newline; a message already
+        reported is dropped (ShadingSystem attribute error_repeats = 0, the default)."""
+        A = op.args
+        if not A[0].constval:
+            raise NotImplementedError("%s with non-constant format" % kind)
+        self.w("if (sg.ctx && sg.ctx->out) {")
+        self.ind += 1
+        self.w("std::string msg_; std::string* save_ = sg.ctx->out; sg.ctx->out = &msg_;")
+        self.emit_format(A[0].vals[0], A[1:])
+        self.w("sg.ctx->out = save_;")
+        self.w("report_message(sg, %s, msg_);" % cstr("%s: Shader %s [%s]: " % (kind.upper(), kind, self.l.m.name)))
+        self.ind -= 1
+        self.w("}")
+
+    def op_warning(self, op):
+        return self.op_error(op, "warning")
 
     def emit_format(self, f, args):
         """Split an OSL format string at gen time (reference: llvm_gen_printf,

@@ -82,6 +82,11 @@ SHADERS = {
     "color_ops": "repo:tests/shaders/color_ops.osl",
     "matrix_ops": "repo:tests/shaders/matrix_ops.osl",
     "texture_ops": "repo:tests/shaders/texture_ops.osl",
+    "constfold_ops": "repo:tests/shaders/constfold_ops.osl",
+    "message_a": "repo:tests/shaders/message_a.osl",
+    "message_b": "repo:tests/shaders/message_b.osl",
+    "error_dupes_test": "error-dupes/test.osl",
+    "userdata_custom_test": "userdata-custom/test.osl",
     "noise_generic_test": "noise-generic/test.osl",
     "pnoise_generic_test": "pnoise-generic/test.osl",
     "userdata_partial_test": "userdata-partial/test.osl",
@@ -160,6 +165,8 @@ TEXTS = {
     "matrix": "matrix/ref/out.txt",
     "transform": "transform/ref/out.txt",
     "transformc": "transformc/ref/out.txt",
+    "error-dupes": "error-dupes/ref/out.txt",
+    "userdata-custom": "userdata-custom/ref/out.txt",
 }
 # testsuite directories whose run.py is a single `testshade [-g X Y] [-center] test` with a text
 # golden: (grid x, grid y, center).  Fixtures: oso/ts_<dir>.oso, text/ts_<dir>.txt.
