@@ -1908,7 +1908,7 @@ Gen::run()
     long long stage_words = 0;
     for (const OutCluster& c : g.clusters)
         stage_words += c.stride / 4;
-    out << "extern \"C\" __global__ void __launch_bounds__(" << B
+    out << "extern \"C\" __global__ void __launch_bounds__(" << B << "%MINBLOCKS%"
         << ") osl_b200_group_kernel(const __grid_constant__ B200Launch L)\n{\n";
     // Staging is per WARP and double buffered: a warp's 32 records are contiguous in the
     // output arena, so lane 0 issues the warp's own TMA bulk store and only __syncwarp is

@@ -149,6 +149,7 @@ struct b200_group {
     std::string source;
     std::vector<char> cubin;
     int block = 256;
+    int minblocks = 0;      // option minblocks=N: resident CTAs per SM the register allocator must allow (0: its own choice)
     int stage_outputs = 1;  // option stage=0 forces direct stores
     std::mutex mu;
     std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
@@ -200,6 +201,8 @@ nvrtc_compile(b200_group* G, std::string& log)
     std::string src = G->source;
     for (size_t p; (p = src.find("%BLOCK%")) != std::string::npos;)
         src.replace(p, 7, std::to_string(G->block));
+    for (size_t p; (p = src.find("%MINBLOCKS%")) != std::string::npos;)
+        src.replace(p, 11, G->minblocks > 0 ? ", " + std::to_string(G->minblocks) : std::string());
     G->source = src;
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, src.c_str(), "osl_b200_group.cu", osl_b200_num_device_headers,
@@ -271,6 +274,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             if (jw > 1)
                 G->journal_words = (unsigned)jw;
         }
+        if (opt.count("minblocks"))
+            G->minblocks = std::max(0, atoi(opt["minblocks"].c_str()));
         if (opt.count("error_repeats"))
             G->error_repeats = atoi(opt["error_repeats"].c_str()) != 0;
         if (opt.count("block"))

@@ -479,9 +479,225 @@ struct CompositeBSDF {
         return BSample();
     }
 };
+// ---- participating media (shading.h:438-725, shading.cpp:1152-1196) ---------------------------
+// OIIO::fast_sinpi / fast_cospi (fmath.h; not in the reference tree): parabola-based sine of pi*x
+inline float fast_sinpi(float x)
+{
+    const float z = x - ((x + 25165824.0f) - 25165824.0f);   // strip the integral part: [-1, 1]
+    const float y = z - z * std::fabs(z);
+    const float Q = 3.10396624f;
+    const float P = 3.584135056f;
+    return y * (Q + P * std::fabs(y));
+}
+inline float fast_cospi(float x) { return fast_sinpi(x + 0.5f); }
+
+struct MediumParams {
+    V3 sigma_t = V3(0.0f);   // extinction coefficient; vacuum by default
+    V3 sigma_s = V3(0.0f);   // scattering
+    float medium_g       = 0.0f;
+    float refraction_ior = 1.0f;
+    int priority         = 0;
+    bool is_vaccum() const { return sigma_t.x <= 0.0f && sigma_t.y <= 0.0f && sigma_t.z <= 0.0f; }
+    bool is_special_priority() const { return priority == 0; }
+    // HenyeyGreenstein = bsdl::spi::VolumeLobe{g, g, blend 0} in the frame Frame(-wo)
+    // (shading.cpp:1152-1196, BSDL/SPI/bsdf_volume_impl.h)
+    static float phase_func(float costheta, float g)
+    {
+        if (g == 0)
+            return 0.25f * (1 / float(M_PI));
+        const float num = 0.25f * (1 / float(M_PI)) * (1 - g * g);
+        const float den = 1 + g * g + 2.0f * g * costheta;
+        return num / std::sqrt(den * den * den);
+    }
+    BSample sample_phase_func(const V3& wo, float rx, float ry, float /*rz*/) const
+    {
+        if (is_vaccum())
+            return BSample(V3(1.0f), V3(1.0f), 0.0f, 0.0f);
+        const float g1 = mx_clamp(medium_g, -0.99f, 0.99f), g2 = g1, blend = 0.0f;
+        // sample_phase
+        float g, x;
+        if (rx < blend) {
+            g = g2;
+            x = rx / blend;
+        } else {
+            g = g1;
+            x = (rx - blend) / (1 - blend);
+        }
+        float cosTheta;
+        if (std::fabs(g) < 1e-3f)
+            cosTheta = 1 - 2 * x;
+        else {
+            float k  = (1 - g * g) / (1 - g + 2 * g * x);
+            cosTheta = (1 + g * g - k * k) / (2 * g);
+        }
+        float sinTheta = std::sqrt(std::max(0.0f, 1.0f - cosTheta * cosTheta));
+        float phi      = 2 * ry;
+        V3 wi_l(sinTheta * fast_cospi(phi), sinTheta * fast_sinpi(phi), cosTheta);
+        // eval_impl: pdf = lerp(blend, phase(g1), phase(g2)) of cos = clamp(-wi.z)
+        float OdotI = mx_clamp(-wi_l.z, -1.0f, 1.0f);
+        float pdf   = mx_lerp(blend, phase_func(OdotI, g1), phase_func(OdotI, g2));
+        TangentFrame f = TangentFrame::from_normal(-wo);   // bsdl::Frame(Z) = the same orthonormal basis
+        return BSample(f.get(wi_l.x, wi_l.y, wi_l.z), V3(1.0f), pdf, 1.0f);
+    }
+};
+
+struct MediumStack {
+    enum { MaxEntries = 8 };
+    MediumParams pool[MaxEntries];
+    int mediums[MaxEntries];       // pool indices, sorted by descending priority
+    int entry_order[MaxEntries];   // pool indices in LIFO order
+    float cdf[MaxEntries];
+    int overlapping_medium_indices[MaxEntries];
+    MediumParams current_params;
+    int depth = 0, pool_size = 0, num_overlapping = 0;
+
+    const MediumParams* get_current_params() const { return depth > 0 ? &pool[mediums[0]] : nullptr; }
+    void compute_current_params()
+    {
+        MediumParams np;
+        num_overlapping = 0;
+        for (int i = 0; i < depth; i++) {
+            const MediumParams& pi = pool[mediums[i]];
+            if (i == 0)
+                np.priority = pi.priority;
+            if (pi.priority != np.priority)
+                continue;
+            overlapping_medium_indices[num_overlapping] = i;
+            np.sigma_t = np.sigma_t + pi.sigma_t;
+            np.sigma_s = np.sigma_s + pi.sigma_s;
+            float avg  = (pi.sigma_s.x + pi.sigma_s.y + pi.sigma_s.z) / 3.0f;
+            cdf[num_overlapping] = (num_overlapping > 0 ? cdf[num_overlapping - 1] : 0.0f) + avg;
+            num_overlapping++;
+        }
+        if (num_overlapping > 1 && !np.is_vaccum()) {
+            float total_cdf = cdf[num_overlapping - 1];
+            if (total_cdf > 0.0f)
+                for (int i = 0; i < num_overlapping; i++)
+                    cdf[i] /= total_cdf;
+        }
+        np.sigma_s = V3(std::min(np.sigma_s.x, np.sigma_t.x), std::min(np.sigma_s.y, np.sigma_t.y),
+                        std::min(np.sigma_s.z, np.sigma_t.z));
+        current_params = np;
+    }
+    static V3 vdiv(const V3& a, float d) { return V3(a.x / d, a.y / d, a.z / d); }   // Imath Vec3 / T
+    static V3 transmittance(const V3& sigma_t, float distance)
+    {
+        return V3(expf(-sigma_t.x * distance), expf(-sigma_t.y * distance), expf(-sigma_t.z * distance));
+    }
+    // returns true when the path scattered inside the medium (new origin / direction in r)
+    template<class SamplerT>
+    bool integrate(Ray& r, SamplerT& sampler, float hit_t, V3& path_weight, float& bsdf_pdf)
+    {
+        if (depth <= 0 || current_params.is_vaccum())
+            return false;
+        const V3 ws = V3(path_weight.x * current_params.sigma_s.x / current_params.sigma_t.x,
+                         path_weight.y * current_params.sigma_s.y / current_params.sigma_t.y,
+                         path_weight.z * current_params.sigma_s.z / current_params.sigma_t.z);
+        float cw[3] = { ws.x, ws.y, ws.z };
+        float total = cw[0] + cw[1] + cw[2];
+        if (total <= 0.0f) {
+            path_weight = path_weight * transmittance(current_params.sigma_t, hit_t);
+            return false;
+        }
+        float inv_total = 1.0f / total;
+        cw[0] *= inv_total; cw[1] *= inv_total; cw[2] *= inv_total;
+        V3 rnd = sampler.get();
+        int channel;
+        if (rnd.y < cw[0])
+            channel = 0;
+        else if (rnd.y < cw[0] + cw[1])
+            channel = 1;
+        else
+            channel = 2;
+        float sigma_t_channel = current_params.sigma_t[channel];
+        float t_volume        = -logf(1.0f - rnd.x) / sigma_t_channel;
+        bool scatter = t_volume < hit_t;
+        float t      = scatter ? t_volume : hit_t;
+        V3 tr        = transmittance(current_params.sigma_t, t);
+        V3 density   = scatter ? (current_params.sigma_t * tr) : tr;
+        float pdf    = density.x * cw[0] + density.y * cw[1] + density.z * cw[2];
+        if (pdf <= 0.0f)
+            return false;
+        if (scatter)
+            path_weight = path_weight * vdiv(tr * current_params.sigma_s, pdf);
+        else {
+            path_weight = path_weight * vdiv(tr, pdf);
+            return false;
+        }
+        r.origin  = r.origin + r.direction * t_volume;
+        int index = 0;
+        if (num_overlapping > 1)
+            for (index = 0; index < num_overlapping - 1; ++index)
+                if (rnd.z < cdf[index])
+                    break;
+        int medium_index = overlapping_medium_indices[index];
+        V3 rp            = sampler.get();
+        BSample ps       = pool[mediums[medium_index]].sample_phase_func(-r.direction, rp.x, rp.y, rp.z);
+        if (ps.pdf > 0.0f) {
+            path_weight = path_weight * ps.weight;
+            r.direction = ps.wi;
+            bsdf_pdf    = ps.pdf;
+            return true;
+        }
+        return false;
+    }
+    bool add_medium(const MediumParams& np)
+    {
+        if (depth >= MaxEntries || pool_size >= MaxEntries)
+            return false;
+        const int p = pool_size++;
+        pool[p]     = np;
+        int insert_pos = depth;
+        for (int i = 0; i < depth; ++i)
+            if (np.priority > pool[mediums[i]].priority) {
+                insert_pos = i;
+                break;
+            }
+        for (int j = depth; j > insert_pos; --j)
+            mediums[j] = mediums[j - 1];
+        mediums[insert_pos] = p;
+        entry_order[depth]  = p;
+        depth++;
+        compute_current_params();
+        return true;
+    }
+    void pop_medium()
+    {
+        if (depth <= 0)
+            return;
+        depth--;
+        const int p      = entry_order[depth];
+        int sorted_index = -1;
+        for (int i = 0; i <= depth; ++i)
+            if (mediums[i] == p) {
+                sorted_index = i;
+                break;
+            }
+        if (sorted_index < 0)
+            return;
+        for (int j = sorted_index; j < depth; ++j)
+            mediums[j] = mediums[j + 1];
+        if (p == pool_size - 1)
+            pool_size--;
+        compute_current_params();
+    }
+    bool false_intersection_with(const MediumParams& entrant) const
+    {
+        const MediumParams* current = get_current_params();
+        if (!current)
+            return false;
+        if (entrant.is_special_priority() && current->is_special_priority())
+            return false;
+        if (entrant.priority == current->priority)
+            return true;
+        return entrant.priority > current->priority;
+    }
+};
+
 struct ShadingResult {
     V3 Le = V3(0.0f);
     CompositeBSDF bsdf;
+    MediumParams medium_data;   // what the surface encloses (medium_vdf / anisotropic_vdf closures)
 };
 
 inline const Clos* clos_ptr_param(const ClosComp* c, int word)
@@ -602,12 +818,119 @@ inline V3 evaluate_layer_opacity(const SG& sg, float path_roughness, const Clos*
     return weight;
 }
 
-// process_bsdf_closure: explicit 16-deep stack, weights multiplied root->leaf
-inline void process_closure(const SG& sg, ShadingResult& result, const Clos* closure, bool light_only,
-                            float path_roughness = 0.0f)
+// process_medium_closure (shading.cpp:1283-1447): what the surface encloses, found before the
+// BSDF pass so that nested dielectrics can be resolved against the medium stack
+inline bool is_black3(const V3& c) { return c.x == 0 && c.y == 0 && c.z == 0; }
+inline void process_medium_closure(const SG& sg, float path_roughness, ShadingResult& result,
+                                   const MediumStack& medium_stack, const Clos* closure)
 {
     if (!closure)
         return;
+    const int STACK_SIZE = 16;
+    int stack_idx        = 0;
+    const Clos* ptr_stack[STACK_SIZE];
+    V3 weight_stack[STACK_SIZE];
+    V3 weight(1.0f);
+    auto clamp_s = [&]() {
+        MediumParams& m = result.medium_data;
+        m.sigma_s = V3(std::min(m.sigma_s.x, m.sigma_t.x), std::min(m.sigma_s.y, m.sigma_t.y),
+                       std::min(m.sigma_s.z, m.sigma_t.z));
+    };
+    while (closure) {
+        switch (closure->id) {
+        case CL_MUL:
+            weight  = weight * ((const ClosMul*)closure)->weight;
+            closure = ((const ClosMul*)closure)->closure;
+            break;
+        case CL_ADD:
+            weight_stack[stack_idx] = weight;
+            ptr_stack[stack_idx++]  = ((const ClosAdd*)closure)->b;
+            closure                 = ((const ClosAdd*)closure)->a;
+            break;
+        default: {
+            const ClosComp* comp = (const ClosComp*)closure;
+            const float* p       = comp->params;
+            closure              = nullptr;
+            switch (comp->id) {
+            case MX_LAYER_ID: {
+                const Clos* top  = clos_ptr_param(comp, 0);
+                const Clos* base = clos_ptr_param(comp, 2);
+                V3 base_w = weight * (V3(1.0f) - clamp01(evaluate_layer_opacity(sg, path_roughness, top)));
+                closure                   = top;
+                ptr_stack[stack_idx]      = base;
+                weight_stack[stack_idx++] = weight * base_w;   // (sic) the weight enters twice
+                break;
+            }
+            case MX_ANISOTROPIC_VDF_ID: {
+                // params: albedo, extinction, anisotropy
+                V3 cw                       = weight * comp->w;
+                result.medium_data.sigma_t  = cw * V3(p[3], p[4], p[5]);
+                result.medium_data.sigma_s  = V3(p[0], p[1], p[2]) * result.medium_data.sigma_t;
+                result.medium_data.medium_g = p[6];
+                result.medium_data.priority = 0;
+                clamp_s();
+                break;
+            }
+            case MX_MEDIUM_VDF_ID: {
+                // params: albedo, transmission_depth, transmission_color, anisotropy, ior, priority
+                V3 cw = weight * comp->w;
+                const V3 albedo(p[0], p[1], p[2]), t_color(p[4], p[5], p[6]);
+                if (is_black3(albedo) && is_black3(t_color)) {
+                    result.medium_data.sigma_t = V3(0.0f);
+                    result.medium_data.sigma_s = V3(0.0f);
+                } else {
+                    const float epsilon = 1e-10f;
+                    V3 st(-fast_log(fmaxf(t_color.x, epsilon)), -fast_log(fmaxf(t_color.y, epsilon)),
+                          -fast_log(fmaxf(t_color.z, epsilon)));
+                    result.medium_data.sigma_t = st * MediumStack::vdiv(cw, p[3]);
+                    result.medium_data.sigma_s = albedo * result.medium_data.sigma_t;
+                    clamp_s();
+                }
+                result.medium_data.medium_g       = p[7];
+                result.medium_data.refraction_ior = sg.backfacing ? 1.0f / p[8] : p[8];
+                result.medium_data.priority       = (int)f2u(p[9]);
+                break;
+            }
+            case MX_DIELECTRIC_ID:
+            case MX_GENERALIZED_SCHLICK_ID: {
+                // refr_tint: dielectric params[9..11], schlick params[9..11] as well (after N, U, refl_tint)
+                if (!is_black3(weight * comp->w * V3(p[9], p[10], p[11]))) {
+                    float ior;
+                    if (comp->id == MX_DIELECTRIC_ID)
+                        ior = p[14];
+                    else {
+                        // F0 = params[14..16]
+                        float avg_F0  = mx_clamp((p[14] + p[15] + p[16]) / 3.0f, 0.0f, 0.99f);
+                        float sqrt_F0 = sqrtf(avg_F0);
+                        ior           = (1 + sqrt_F0) / (1 - sqrt_F0);
+                    }
+                    result.medium_data.refraction_ior = sg.backfacing ? 1.0f / ior : ior;
+                    const MediumParams* current       = medium_stack.get_current_params();
+                    if (current && result.medium_data.priority <= current->priority)
+                        result.medium_data.refraction_ior = current->refraction_ior;
+                }
+                break;
+            }
+            default: break;
+            }
+            break;
+        }
+        }
+        if (closure == nullptr && stack_idx > 0) {
+            closure = ptr_stack[--stack_idx];
+            weight  = weight_stack[stack_idx];
+        }
+    }
+}
+
+// process_bsdf_closure: explicit 16-deep stack, weights multiplied root->leaf
+inline void process_closure(const SG& sg, ShadingResult& result, const Clos* closure, bool light_only,
+                            float path_roughness = 0.0f, const MediumStack* medium_stack = nullptr)
+{
+    if (!closure)
+        return;
+    if (!light_only && medium_stack)
+        process_medium_closure(sg, path_roughness, result, *medium_stack, closure);
     const int STACK_SIZE = 16;
     int stack_idx        = 0;
     const Clos* ptr_stack[STACK_SIZE];
@@ -667,7 +990,14 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                 case MX_SHEEN_ID: known = sheen_from_component(l, comp, sg, path_roughness); break;
                 case MX_CONDUCTOR_ID:
                 case MX_DIELECTRIC_ID:
-                case MX_GENERALIZED_SCHLICK_ID: mx_from_component(l, comp, sg, path_roughness); break;
+                case MX_GENERALIZED_SCHLICK_ID:
+                    // a boundary the medium stack says is not there (nested dielectrics) is passed through
+                    if (comp->id != MX_CONDUCTOR_ID && medium_stack
+                        && medium_stack->false_intersection_with(result.medium_data))
+                        l.type = LOBE_TRANSPARENT;
+                    else
+                        mx_from_component(l, comp, sg, path_roughness);
+                    break;
                 case MX_TRANSLUCENT_ID: {
                     // params: N, albedo (bsdf_translucent_impl.h): cosine lobe on the far side
                     l.type   = LOBE_MX_TRANSLUCENT;
@@ -1142,6 +1472,7 @@ struct Renderer {
         int prev_id    = -1;
         float bsdf_pdf = inf;
         ClosurePool pool, light_pool;
+        MediumStack medium_stack;
         for (int b = 0; b <= S.max_bounces; b++) {
             SG sg;
             Intersection hit = scene_intersect(S, r, inf, (unsigned)prev_id);
@@ -1158,6 +1489,8 @@ struct Renderer {
                 }
                 break;
             }
+            if (medium_stack.integrate(r, sampler, hit.t, path_weight, bsdf_pdf))
+                continue;   // scattered inside the medium: a bounce without a surface
             globals_from_hit(S, sg, r, hit.t, hit.id, hit.u, hit.v);
             if (S.show_globals) {
                 V3 v = sg.Ng;
@@ -1178,7 +1511,7 @@ struct Renderer {
             execute(shaderID, sg, pool);
             ShadingResult result;
             bool last_bounce = b == S.max_bounces;
-            process_closure(sg, result, sg.Ci, last_bounce, r.roughness);
+            process_closure(sg, result, sg.Ci, last_bounce, r.roughness, &medium_stack);
             const int nlights = S.nlightprims;
             float k           = 1;
             if (S.shader_is_light[shaderID] && nlights > 0) {
@@ -1240,6 +1573,12 @@ struct Renderer {
             r.radius    = radius;
             r.spread    = std::max(r.spread, p.roughness);
             r.roughness = p.roughness;
+            if (dot(sg.Ng, p.wi) < 0) {   // the sampled direction crosses the surface
+                if (!sg.backfacing)
+                    medium_stack.add_medium(result.medium_data);
+                else
+                    medium_stack.pop_medium();
+            }
             if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
                 break;
             prev_id  = hit.id;

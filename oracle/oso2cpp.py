@@ -369,7 +369,9 @@ CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
             ("conductor_bsdf", 7): "MX_CONDUCTOR_ID", ("dielectric_bsdf", 8): "MX_DIELECTRIC_ID",
             ("generalized_schlick_bsdf", 10): "MX_GENERALIZED_SCHLICK_ID",
             ("translucent_bsdf", 2): "MX_TRANSLUCENT_ID",
-            ("subsurface_bssrdf", 4): "MX_SUBSURFACE_ID"}
+            ("subsurface_bssrdf", 4): "MX_SUBSURFACE_ID",
+            # participating media (shading.cpp:265-284)
+            ("anisotropic_vdf", 3): "MX_ANISOTROPIC_VDF_ID", ("medium_vdf", 6): "MX_MEDIUM_VDF_ID"}
 # keyword parameters per closure id, in slot order after the positional words; value
 # type "int" / "float".  Unspecified keywords are zero (llvm_gen_closure memsets the
 # parameter block when there is no prepare callback).  String keywords ("label") have
