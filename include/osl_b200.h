@@ -4,7 +4,7 @@
  * Plain C: pointers and sizes only, status codes, no exceptions cross this
  * boundary.  Every entry point names the reference interface it stands in for
  * (paths relative to the OSL source tree).  The C++ mirror of the reference
- * API (OSL::ShadingSystem / BatchedExecutor) in include/OSL/oslexec_b200.h is
+ * API (OSL::ShadingSystem / BatchedExecutor) in include/OSL/oslexec.h is
  * a thin layer over these calls; INTEGRATION.md shows the binding a reference
  * maintainer would add.
  */
@@ -281,8 +281,17 @@ typedef struct b200_render_stats {
 
 typedef struct b200_render b200_render;
 
+/* Scene BVH of the testrender path: binned SAH over the triangles, the tree of the reference's
+ * build_bvh (src/testrender/bvh.cpp:42-237: 16 bins, depth <= 64, in-place partition, children
+ * numbered depth first), float32 operation for operation, so that traversal order - and with it
+ * every render - matches.  nodes: room for max_nodes x 8 words (2 * ntriangles - 1 always
+ * suffices), layout as b200_render_scene::bvh_nodes; indices: ntriangles words. */
+int b200_build_bvh(const float* verts, int nverts, const int* triangles, int ntriangles, float* nodes, int max_nodes,
+                   unsigned* indices, int* nnodes);
+
 /* options: fma=0|1, sort=0|1 (order live paths by closure signature / material),
- * slots=N (path slots in the regenerating pool), tail=N (run the last N paths in one launch) */
+ * slots=N (path slots in the regenerating pool), tail=N (run the last N paths in one launch),
+ * compile=0 (generate the CUDA source only; NVRTC runs at the first render or cubin request) */
 int b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_group_desc* materials,
                        const char* options, b200_render** out);
 void b200_render_destroy(b200_render* r);

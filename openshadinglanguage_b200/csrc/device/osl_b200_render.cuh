@@ -125,6 +125,7 @@ struct RenderLaunch {
     int total;            // samples in the round = nsamples * npix
     float* result;        // total x 3: radiance of every sample of the round
     float* accum;         // running per-pixel result, 3 floats per work-set pixel
+    float* medium;        // nslots x OSLD_MEDIUM_WORDS: the medium stack of every path (null: no media)
 };
 
 OSLD V3 ld3(const float* p, int i) { return mkv(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2)); }
@@ -604,7 +605,7 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
 // closure tree -> emission + lobes (16-deep explicit stack, weights root->leaf)
 OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, CompositeBSDF& B, bool light_only,
                           V3 wo = mkv(0.0f, 0.0f, 1.0f), bool backfacing = false, float path_roughness = 0.0f,
-                          const float* luts = nullptr)
+                          const float* luts = nullptr, bool false_intersection = false)
 {
     int ptr_stack[OSLD_CLOSURE_STACK];
     V3 weight_stack[OSLD_CLOSURE_STACK];
@@ -659,7 +660,14 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
 #ifdef OSLD_MX_LOBES
                 case MX_CONDUCTOR_ID:
                 case MX_DIELECTRIC_ID:
-                case MX_GENERALIZED_SCHLICK_ID: mx_from_component(luts, l, id, q, wo, backfacing, path_roughness); break;
+                case MX_GENERALIZED_SCHLICK_ID:
+                    // a boundary the medium stack rules out (nested dielectrics) is passed straight
+                    // through (shading.cpp:1580-1609)
+                    if (id != MX_CONDUCTOR_ID && false_intersection)
+                        l.type = LOBE_TRANSPARENT;
+                    else
+                        mx_from_component(luts, l, id, q, wo, backfacing, path_roughness);
+                    break;
                 case MX_TRANSLUCENT_ID:
                     // params: N, albedo: a cosine lobe on the far side of the visible normal
                     l.type   = LOBE_MX_TRANSLUCENT;
@@ -1315,6 +1323,336 @@ extern "C" __global__ void __launch_bounds__(256) rt_bg_scale(const __grid_const
 }
 #endif  // OSLD_HAS_BACKGROUND
 
+#ifdef OSLD_HAS_MEDIA
+// ---- participating media -------------------------------------------------------------------------
+// MediumParams / MediumStack (shading.h:438-725) per path slot, OSLD_MEDIUM_WORDS words:
+//   w0 = depth | pool_size << 8      w1,w2 = mediums[8] (pool indices by descending priority, one byte each)
+//   w3,w4 = entry_order[8] (LIFO)    w8 + 8 p .. = pool[p] = sigma_t.rgb, sigma_s.rgb, g, priority
+// current_params / cdf / overlapping_medium_indices are functions of the stack and are recomputed
+// where integrate() needs them (same additions in the same order, hence the same floats).
+// refraction_ior is carried by the reference but never read by a lobe, so it has no slot here.
+#define OSLD_MEDIUM_WORDS 72
+struct MediumData {
+    V3 sigma_t, sigma_s;
+    float g;
+    int priority;
+};
+OSLD MediumData medium_vacuum()
+{
+    MediumData m;
+    m.sigma_t = m.sigma_s = mkv(0.0f);
+    m.g        = 0.0f;
+    m.priority = 0;
+    return m;
+}
+OSLD bool medium_is_vacuum(const MediumData& m) { return m.sigma_t.x <= 0.0f && m.sigma_t.y <= 0.0f && m.sigma_t.z <= 0.0f; }
+struct MediumHead {
+    int depth, pool_size;
+    unsigned long long mediums, order;
+};
+OSLD int mbyte(unsigned long long v, int i) { return (int)((v >> (8 * i)) & 0xffull); }
+OSLD MediumHead medium_head(const float* med)
+{
+    const float4 h = *reinterpret_cast<const float4*>(med);
+    MediumHead H;
+    const int w0 = __float_as_int(h.x);
+    H.depth      = w0 & 0xff;
+    H.pool_size  = (w0 >> 8) & 0xff;
+    H.mediums    = (unsigned long long)(unsigned)__float_as_int(h.y)
+                | ((unsigned long long)(unsigned)__float_as_int(h.z) << 32);
+    H.order = (unsigned long long)(unsigned)__float_as_int(h.w)
+              | ((unsigned long long)(unsigned)__float_as_int(med[4]) << 32);
+    return H;
+}
+OSLD void medium_store_head(float* med, const MediumHead& H)
+{
+    *reinterpret_cast<float4*>(med) = mki4(H.depth | (H.pool_size << 8), (int)(unsigned)H.mediums,
+                                           (int)(unsigned)(H.mediums >> 32), (int)(unsigned)H.order);
+    med[4] = __int_as_float((int)(unsigned)(H.order >> 32));
+}
+OSLD MediumData medium_entry(const float* med, int p)
+{
+    const float4* e = reinterpret_cast<const float4*>(med + 8 + 8 * p);
+    const float4 a = e[0], b = e[1];
+    MediumData m;
+    m.sigma_t  = mkv(a.x, a.y, a.z);
+    m.sigma_s  = mkv(a.w, b.x, b.y);
+    m.g        = b.z;
+    m.priority = __float_as_int(b.w);
+    return m;
+}
+OSLD int medium_entry_priority(const float* med, int p) { return __float_as_int(med[8 + 8 * p + 7]); }
+// MediumStack::add_medium / pop_medium (shading.h:615-676)
+OSLD void medium_add(float* med, const MediumData& np)
+{
+    MediumHead H = medium_head(med);
+    if (H.depth >= 8 || H.pool_size >= 8)
+        return;
+    const int p = H.pool_size++;
+    float4* e   = reinterpret_cast<float4*>(med + 8 + 8 * p);
+    e[0]        = make_float4(np.sigma_t.x, np.sigma_t.y, np.sigma_t.z, np.sigma_s.x);
+    e[1]        = make_float4(np.sigma_s.y, np.sigma_s.z, np.g, __int_as_float(np.priority));
+    int insert_pos = H.depth;
+    for (int i = 0; i < H.depth; ++i)
+        if (np.priority > medium_entry_priority(med, mbyte(H.mediums, i))) {
+            insert_pos = i;
+            break;
+        }
+    const unsigned long long lowmask = insert_pos ? (~0ull >> (64 - 8 * insert_pos)) : 0ull;
+    const unsigned long long high    = insert_pos < 7 ? ((H.mediums & ~lowmask) << 8) : 0ull;
+    H.mediums = (H.mediums & lowmask) | ((unsigned long long)p << (8 * insert_pos)) | high;
+    H.order   = (H.order & ~(0xffull << (8 * H.depth))) | ((unsigned long long)p << (8 * H.depth));
+    H.depth++;
+    medium_store_head(med, H);
+}
+OSLD void medium_pop(float* med)
+{
+    MediumHead H = medium_head(med);
+    if (H.depth <= 0)
+        return;
+    H.depth--;
+    const int p      = mbyte(H.order, H.depth);
+    int sorted_index = -1;
+    for (int i = 0; i <= H.depth; ++i)
+        if (mbyte(H.mediums, i) == p) {
+            sorted_index = i;
+            break;
+        }
+    if (sorted_index >= 0) {
+        const unsigned long long lowmask = sorted_index ? (~0ull >> (64 - 8 * sorted_index)) : 0ull;
+        H.mediums = (H.mediums & lowmask) | ((H.mediums >> 8) & ~lowmask);
+        if (p == H.pool_size - 1)
+            H.pool_size--;
+    }
+    medium_store_head(med, H);
+}
+// MediumStack::false_intersection_with (shading.h:678-695)
+OSLD bool medium_false_intersection(int entrant_priority, bool has_current, int current_priority)
+{
+    if (!has_current)
+        return false;
+    if (entrant_priority == 0 && current_priority == 0)
+        return false;
+    if (entrant_priority == current_priority)
+        return true;
+    return entrant_priority > current_priority;
+}
+// OIIO::fast_sinpi / fast_cospi (fmath.h): BSDLConfig::Fast::sinpif / cospif of the phase sampler
+OSLD float fast_sinpi(float x)
+{
+    const float z = x - ((x + 25165824.0f) - 25165824.0f);
+    const float y = z - z * fabsf(z);
+    const float Q = 3.10396624f;
+    const float P = 3.584135056f;
+    return y * (Q + P * fabsf(y));
+}
+OSLD float fast_cospi(float x) { return fast_sinpi(x + 0.5f); }
+// expf / logf of the host's libm: evaluated in double and rounded once, which is what a
+// correctly rounded libm returns (glibc's are within 0.502 / 0.818 ulp: a rare last-bit difference)
+OSLD float libm_expf(float x) { return (float)exp((double)x); }
+OSLD float libm_logf(float x) { return (float)log((double)x); }
+OSLD V3 medium_transmittance(V3 sigma_t, float distance)
+{
+    return mkv(libm_expf(-sigma_t.x * distance), libm_expf(-sigma_t.y * distance), libm_expf(-sigma_t.z * distance));
+}
+// spi::VolumeLobe{g, g, blend 0} (BSDL/SPI/bsdf_volume_impl.h) in the frame around -wo:
+// MediumParams::sample_phase_func (shading.cpp:1185-1196)
+OSLD float hg_phase(float costheta, float g)
+{
+    if (g == 0)
+        return 0.25f * (float)(1.0 / OSLD_PI);
+    const float num = 0.25f * (float)(1.0 / OSLD_PI) * (1 - g * g);
+    const float den = 1 + g * g + 2.0f * g * costheta;
+    return num / sqrtf(den * den * den);
+}
+OSLD BSample medium_sample_phase(const MediumData& m, V3 wo, float rx, float ry)
+{
+    BSample s;
+    if (medium_is_vacuum(m)) {
+        s.wi = mkv(1.0f); s.weight = mkv(1.0f); s.pdf = 0.0f; s.roughness = 0.0f;
+        return s;
+    }
+    const float g1 = fminf(fmaxf(m.g, -0.99f), 0.99f), blend = 0.0f;
+    float g, x;
+    if (rx < blend) {
+        g = g1;
+        x = rx / blend;
+    } else {
+        g = g1;
+        x = (rx - blend) / (1 - blend);
+    }
+    float cosTheta;
+    if (fabsf(g) < 1e-3f)
+        cosTheta = 1 - 2 * x;
+    else {
+        float k  = (1 - g * g) / (1 - g + 2 * g * x);
+        cosTheta = (1 + g * g - k * k) / (2 * g);
+    }
+    const float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - cosTheta * cosTheta));
+    const float phi      = 2 * ry;
+    const V3 wl          = mkv(sinTheta * fast_cospi(phi), sinTheta * fast_sinpi(phi), cosTheta);
+    const float OdotI    = fminf(fmaxf(-wl.z, -1.0f), 1.0f);
+    const float p1       = hg_phase(OdotI, g1);
+    const float pdf      = (1 - blend) * p1 + blend * p1;   // LERP(blend, p1, p2) with g2 = g1
+    TangentFrame f       = frame_from_normal(-wo);
+    s.wi        = frame_get(f, wl.x, wl.y, wl.z);
+    s.weight    = mkv(1.0f);
+    s.pdf       = pdf;
+    s.roughness = 1.0f;
+    return s;
+}
+// MediumStack::integrate (shading.h:521-613) on the stack stored at `med`.  Returns true when
+// the path scattered inside the medium: origin / direction / bsdf_pdf then describe the new ray.
+OSLD bool medium_integrate(const float* med, const MediumHead& H, Ray& r, Sampler& sampler, float hit_t, V3& path_weight,
+                           float& bsdf_pdf)
+{
+    if (H.depth <= 0)
+        return false;
+    // compute_current_params (shading.h:473-519)
+    MediumData cur = medium_vacuum();
+    int novl       = 0;
+    float total_cdf = 0.0f;
+    for (int i = 0; i < H.depth; i++) {
+        const MediumData pi = medium_entry(med, mbyte(H.mediums, i));
+        if (i == 0)
+            cur.priority = pi.priority;
+        if (pi.priority != cur.priority)
+            continue;
+        cur.sigma_t = cur.sigma_t + pi.sigma_t;
+        cur.sigma_s = cur.sigma_s + pi.sigma_s;
+        const float avg = (pi.sigma_s.x + pi.sigma_s.y + pi.sigma_s.z) / 3.0f;
+        total_cdf       = (novl > 0 ? total_cdf : 0.0f) + avg;
+        novl++;
+    }
+    const bool normalise = novl > 1 && !medium_is_vacuum(cur) && total_cdf > 0.0f;
+    cur.sigma_s = mkv(fminf(cur.sigma_s.x, cur.sigma_t.x), fminf(cur.sigma_s.y, cur.sigma_t.y),
+                      fminf(cur.sigma_s.z, cur.sigma_t.z));
+    if (medium_is_vacuum(cur))
+        return false;
+    float cw0 = path_weight.x * cur.sigma_s.x / cur.sigma_t.x;
+    float cw1 = path_weight.y * cur.sigma_s.y / cur.sigma_t.y;
+    float cw2 = path_weight.z * cur.sigma_s.z / cur.sigma_t.z;
+    const float total = cw0 + cw1 + cw2;
+    if (total <= 0.0f) {
+        path_weight = path_weight * medium_transmittance(cur.sigma_t, hit_t);
+        return false;
+    }
+    const float inv_total = 1.0f / total;
+    cw0 *= inv_total; cw1 *= inv_total; cw2 *= inv_total;
+    const V3 rnd = sampler.get();
+    int channel;
+    if (rnd.y < cw0)
+        channel = 0;
+    else if (rnd.y < cw0 + cw1)
+        channel = 1;
+    else
+        channel = 2;
+    const float sigma_t_channel = vcomp(cur.sigma_t, channel);
+    const float t_volume        = -libm_logf(1.0f - rnd.x) / sigma_t_channel;
+    const bool scatter = t_volume < hit_t;
+    const float t      = scatter ? t_volume : hit_t;
+    const V3 tr        = medium_transmittance(cur.sigma_t, t);
+    const V3 density   = scatter ? (cur.sigma_t * tr) : tr;
+    const float pdf    = density.x * cw0 + density.y * cw1 + density.z * cw2;
+    if (pdf <= 0.0f)
+        return false;
+    if (!scatter) {
+        path_weight = path_weight * vdiv(tr, pdf);
+        return false;
+    }
+    path_weight = path_weight * vdiv(tr * cur.sigma_s, pdf);
+    r.origin    = ray_point(r, t_volume);
+    // which of the overlapping media scatters: walk the cdf again
+    int medium_index = 0, k = 0;
+    float cum        = 0.0f;
+    for (int i = 0; i < H.depth; i++) {
+        const MediumData pi = medium_entry(med, mbyte(H.mediums, i));
+        if (pi.priority != cur.priority)
+            continue;
+        medium_index    = i;   // ends on the last overlapping entry when no cdf entry stops the walk
+        const float avg = (pi.sigma_s.x + pi.sigma_s.y + pi.sigma_s.z) / 3.0f;
+        cum             = (k > 0 ? cum : 0.0f) + avg;
+        if (novl > 1 && k < novl - 1 && rnd.z < (normalise ? cum / total_cdf : cum))
+            break;
+        k++;
+    }
+    const V3 rp      = sampler.get();
+    const BSample ps = medium_sample_phase(medium_entry(med, mbyte(H.mediums, medium_index)), -r.direction, rp.x, rp.y);
+    if (ps.pdf > 0.0f) {
+        path_weight = path_weight * ps.weight;
+        r.direction = ps.wi;
+        bsdf_pdf    = ps.pdf;
+        return true;
+    }
+    return false;
+}
+// process_medium_closure (shading.cpp:1283-1447): the medium a surface encloses, gathered before
+// the BSDF pass.  (refraction_ior is write-only in the reference: not kept.)
+OSLD void process_medium_closure(const ClosurePool& pool, int closure, MediumData& md, V3 wo, bool backfacing,
+                                 float path_roughness, const float* luts)
+{
+    int ptr_stack[OSLD_CLOSURE_STACK];
+    V3 weight_stack[OSLD_CLOSURE_STACK];
+    int sp    = 0;
+    V3 weight = mkv(1.0f);
+    while (closure) {
+        int id = pool.id(closure);
+        if (id == CL_MUL) {
+            weight  = weight * pool.weight(closure);
+            closure = __float_as_int(pool.w[closure + 4]);
+        } else if (id == CL_ADD) {
+            weight_stack[sp] = weight;
+            ptr_stack[sp++]  = __float_as_int(pool.w[closure + 2]);
+            closure          = __float_as_int(pool.w[closure + 1]);
+        } else {
+            const V3 cw     = weight * pool.weight(closure);
+            const PoolPtr q = pool.w + (closure + 4);
+            closure         = 0;
+            if (id == MX_ANISOTROPIC_VDF_ID) {
+                // params: albedo, extinction, anisotropy
+                md.sigma_t  = cw * mkv(q[3], q[4], q[5]);
+                md.sigma_s  = mkv(q[0], q[1], q[2]) * md.sigma_t;
+                md.g        = q[6];
+                md.priority = 0;
+                md.sigma_s  = mkv(fminf(md.sigma_s.x, md.sigma_t.x), fminf(md.sigma_s.y, md.sigma_t.y),
+                                  fminf(md.sigma_s.z, md.sigma_t.z));
+            } else if (id == MX_MEDIUM_VDF_ID) {
+                // params: albedo, transmission_depth, transmission_color, anisotropy, ior, priority
+                const V3 albedo = mkv(q[0], q[1], q[2]), tc = mkv(q[4], q[5], q[6]);
+                if (albedo.x == 0 && albedo.y == 0 && albedo.z == 0 && tc.x == 0 && tc.y == 0 && tc.z == 0) {
+                    md.sigma_t = md.sigma_s = mkv(0.0f);
+                } else {
+                    const float epsilon = 1e-10f;
+                    const V3 st = mkv(-fast_log(fmaxf(tc.x, epsilon)), -fast_log(fmaxf(tc.y, epsilon)),
+                                      -fast_log(fmaxf(tc.z, epsilon)));
+                    md.sigma_t  = st * vdiv(cw, q[3]);
+                    md.sigma_s  = albedo * md.sigma_t;
+                    md.sigma_s  = mkv(fminf(md.sigma_s.x, md.sigma_t.x), fminf(md.sigma_s.y, md.sigma_t.y),
+                                      fminf(md.sigma_s.z, md.sigma_t.z));
+                }
+                md.g        = q[7];
+                md.priority = __float_as_int(q[9]);
+            }
+#ifdef OSLD_GLOSSY_LOBES
+            else if (id == MX_LAYER_ID) {
+                const int top = __float_as_int(q[0]), base = __float_as_int(q[1]);
+                V3 op     = evaluate_layer_opacity(pool, top, wo, backfacing, path_roughness, luts);
+                op        = mkv(fminf(fmaxf(op.x, 0.f), 1.f), fminf(fmaxf(op.y, 0.f), 1.f), fminf(fmaxf(op.z, 0.f), 1.f));
+                V3 base_w = weight * (mkv(1.0f) - op);
+                closure   = top;
+                ptr_stack[sp]      = base;
+                weight_stack[sp++] = weight * base_w;   // (sic)
+            }
+#endif
+        }
+        if (closure == 0 && sp > 0) {
+            closure = ptr_stack[--sp];
+            weight  = weight_stack[sp];
+        }
+    }
+}
+#endif  // OSLD_HAS_MEDIA
+
 // ---- path life cycle ---------------------------------------------------------------------------
 // Sample `sid` of the round = sample plane sid / npix of work-set pixel sid % npix
 // (antialias_pixel, simpleraytracer.cpp:1197-1213): camera sample -> initial path state.
@@ -1340,6 +1678,9 @@ OSLD void path_start(const RenderLaunch& L, int slot, int sid)
     rec[3] = make_float4(0.0f, 0.0f, 0.0f, r.roughness);
     rec[5] = mki4(r.raytype, -1, 0, (int)sampler.seed);
     rec[6] = mki4((int)sampler.index, sid, 0, 0);
+#ifdef OSLD_HAS_MEDIA
+    L.medium[(size_t)slot * OSLD_MEDIUM_WORDS] = 0.0f;   // depth 0, empty pool
+#endif
 }
 // a finished sample: its radiance goes to the sample's own slot (rt_resolve folds in order)
 OSLD void path_finish(const RenderLaunch& L, int slot)
@@ -1587,6 +1928,24 @@ OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
 #endif
             break;
         }
+#ifdef OSLD_HAS_MEDIA
+        // the medium the ray crossed on its way to the hit (simpleraytracer.cpp:999-1002)
+        float* const med    = L.medium + (size_t)slot * OSLD_MEDIUM_WORDS;
+        const MediumHead mh = medium_head(med);
+        Sampler sampler;
+        sampler.seed  = seed_now;
+        sampler.index = (u32)__float_as_int(q6.x);
+        if (medium_integrate(med, mh, r, sampler, ht, path_weight, bsdf_pdf)) {
+            // scattered inside: a bounce without a surface; prev_id stays
+            rec[0] = mkf4(r.origin, r.radius);
+            rec[1] = mkf4(r.direction, r.spread);
+            rec[2] = mkf4(path_weight, bsdf_pdf);
+            rec[5] = mki4(r.raytype, __float_as_int(q5.y), b + 1, (int)sampler.seed);
+            alive  = b + 1 <= S.max_bounces;
+            break;
+        }
+        seed_now = sampler.seed;
+#endif
         SG sg;
         globals_from_hit(S, sg, r, ht, hid, hu, hv);
         if (S.show_globals) {
@@ -1613,7 +1972,17 @@ OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
         CompositeBSDF bsdf;
         bsdf.num               = 0;
         const bool last_bounce = b == S.max_bounces;
+#ifdef OSLD_HAS_MEDIA
+        MediumData md = medium_vacuum();
+        if (!last_bounce)
+            process_medium_closure(pool, sg.Ci, md, -sg.I, sg.backfacing != 0, r.roughness, S.bsdl_luts);
+        const bool false_isect = medium_false_intersection(
+            md.priority, mh.depth > 0, mh.depth > 0 ? medium_entry_priority(med, mbyte(mh.mediums, 0)) : 0);
+        process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness, S.bsdl_luts,
+                        false_isect);
+#else
         process_closure(pool, sg.Ci, Le, bsdf, last_bounce, -sg.I, sg.backfacing != 0, r.roughness, S.bsdl_luts);
+#endif
         const int nlights = S.nlightprims;
         float k           = 1;
         if (__ldg(S.shader_is_light + shaderID) && nlights > 0) {
@@ -1626,9 +1995,11 @@ OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
             break;
         const V3 wo = -sg.I;
         bsdf_prepare(bsdf, wo, path_weight, b >= S.rr_depth);
+#ifndef OSLD_HAS_MEDIA
         Sampler sampler;
         sampler.seed  = seed_now;
         sampler.index = (u32)__float_as_int(q6.x);
+#endif
         V3 s          = sampler.get();
         seed_now      = sampler.seed;
         const float xi = s.x, yi = s.y, zi = s.z;
@@ -1669,6 +2040,14 @@ OSLD int shade_path(const RenderLaunch& L, int slot, ClosurePool& pool)
         // the shadow rays start at P and skip this primitive, whether or not the path goes on
         rec[0] = mkf4(sg.P, radius);
         rec[5] = mki4(RAY_DIFFUSE, hid, b + 1, (int)seed_now);
+#ifdef OSLD_HAS_MEDIA
+        if (dot3(sg.Ng, p.wi) < 0) {   // the sampled direction crosses the surface (simpleraytracer.cpp:1174-1182)
+            if (!sg.backfacing)
+                medium_add(med, md);
+            else
+                medium_pop(med);
+        }
+#endif
         if (!(path_weight.x > 0) && !(path_weight.y > 0) && !(path_weight.z > 0))
             break;
         // continue the path

@@ -1378,6 +1378,9 @@ Gen::emit_op(const Opcode& op)
             { "generalized_schlick_bsdf", 10, "MX_GENERALIZED_SCHLICK_ID", nullptr },
             { "translucent_bsdf", 2, "MX_TRANSLUCENT_ID", nullptr },
             { "subsurface_bssrdf", 4, "MX_SUBSURFACE_ID", nullptr },
+            // participating media (shading.cpp:265-284)
+            { "anisotropic_vdf", 3, "MX_ANISOTROPIC_VDF_ID", nullptr },
+            { "medium_vdf", 6, "MX_MEDIUM_VDF_ID", nullptr },
             { "emission", 0, "EMISSION_ID" },       { "background", 0, "BACKGROUND_ID" },
             { "diffuse", 1, "DIFFUSE_ID" },         { "oren_nayar", 2, "OREN_NAYAR_ID" },
             { "translucent", 1, "TRANSLUCENT_ID" }, { "phong", 2, "PHONG_ID" },
@@ -1433,6 +1436,8 @@ Gen::emit_op(const Opcode& op)
         g.closure_names.insert(cname);
         if (cn == "layer")
             g.closure_adds += 1;
+        else if (cn == "anisotropic_vdf" || cn == "medium_vdf")
+            g.uses_media = true;
         else if (cn != "emission" && cn != "background" && cn != "uniform_edf")
             g.lobe_bound += 1;
         if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
@@ -2057,7 +2062,7 @@ std::string
 generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderModuleInfo* info)
 {
     std::string mats;
-    bool color = false, glossy = false, mx = false, in_loop = false;
+    bool color = false, glossy = false, mx = false, in_loop = false, media = false;
     int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
     int pool_words = 2, lobes = 1, adds = 0;
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -2072,6 +2077,7 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         color |= g.uses_colorsystem;
         glossy |= g.uses_glossy_lobes;
         mx |= g.uses_mx_lobes;
+        media |= g.uses_media;
         in_loop |= g.closure_in_loop;
         pool_words = std::max(pool_words, g.pool_words_bound);
         lobes      = std::max(lobes, g.lobe_bound);
@@ -2109,9 +2115,14 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         out << "#define OSLD_GLOSSY_LOBES 1\n";
     if (mx)
         out << "#define OSLD_MX_LOBES 1\n";
+    if (media)
+        out << "#define OSLD_HAS_MEDIA 1\n";
     mi.uses_mx_lobes = mx;
-    if (info)
+    mi.uses_media    = media;
+    if (info) {
         info->uses_mx_lobes = mx;
+        info->uses_media    = media;
+    }
     if (has_background)
         out << "#define OSLD_HAS_BACKGROUND 1\n";
     out << "#include \"osl_b200_render.cuh\"\n";

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <sstream>
 
 namespace oslb200 {
@@ -80,7 +81,9 @@ struct DevLaunch {
     int nslots, npix, s0, nsamples, total;
     float* result;
     float* accum;
+    float* medium;
 };
+enum { MEDIUM_WORDS = 72 };  // OSLD_MEDIUM_WORDS: per-slot medium stack of modules with volume closures
 
 const char* KERNELS[] = { "rt_camera", "rt_generate", "rt_trace", "rt_light", "rt_sort_scatter", "rt_shade",
                           "rt_swap", "rt_resolve", "rt_tail",
@@ -96,7 +99,8 @@ enum { TRACE_BLOCK = 128, SHADE_BLOCK = 128 };  // OSLD_TRACE_BLOCK / OSLD_SHADE
 struct b200_render {
     std::vector<std::unique_ptr<Group>> groups;
     std::string source;
-    std::vector<char> cubin;
+    std::vector<char> cubin;           // empty until the module is compiled (option compile=0 defers it)
+    std::mutex jit_mu;
     b200_render_scene host;  // host-pointer copy of the description
     bool fma = true, sort = true;
     long long slots_target = 0;         // option slots=N: path slots in the pool (0 = default)
@@ -121,6 +125,7 @@ struct b200_render {
         void* shrec          = nullptr;  // nslots x 64 B shadow records
         int* queues          = nullptr;  // 4 x nslots
         int* sort_keys       = nullptr;
+        float* medium        = nullptr;  // nslots x 288 B medium stacks (scenes with volume closures)
         int* counters        = nullptr;
         volatile int* host_state = nullptr;  // mapped pinned: {iter, live, shadow, next}
         // work set
@@ -149,6 +154,20 @@ parse_opts(const char* s)
             m[kv.substr(0, e)] = kv.substr(e + 1);
     }
     return m;
+}
+
+static int
+ensure_compiled(b200_render* r)
+{
+    std::lock_guard<std::mutex> lock(r->jit_mu);
+    if (!r->cubin.empty())
+        return B200_OK;
+    std::string err = jit_compile(r->source, "osl_b200_render.cu", r->fma, r->cubin);
+    if (!err.empty()) {
+        r->cubin.clear();
+        return set_error(B200_ERR_COMPILE, err);
+    }
+    return B200_OK;
 }
 
 extern "C" int
@@ -271,9 +290,12 @@ b200_render_create(const b200_render_scene* scene, int nmaterials, const b200_gr
     } catch (const std::exception& e) {
         return set_error(B200_ERR_COMPILE, e.what());
     }
-    std::string err = jit_compile(R->source, "osl_b200_render.cu", R->fma, R->cubin);
-    if (!err.empty())
-        return set_error(B200_ERR_COMPILE, err);
+    // compile=0: generate the module's source only; NVRTC runs at the first render / cubin request
+    if (!(opt.count("compile") && atoi(opt["compile"].c_str()) == 0)) {
+        int rc = ensure_compiled(R.get());
+        if (rc != B200_OK)
+            return rc;
+    }
     *out = R.release();
     return B200_OK;
 }
@@ -287,6 +309,8 @@ b200_render_cuda_source(const b200_render* r)
 extern "C" const void*
 b200_render_cubin(const b200_render* r, long long* size)
 {
+    if (r && ensure_compiled(const_cast<b200_render*>(r)) != B200_OK)
+        r = nullptr;
     if (size)
         *size = r ? (long long)r->cubin.size() : 0;
     return r ? r->cubin.data() : nullptr;
@@ -384,6 +408,11 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
         return set_error(B200_ERR_CUDA, "CUDA driver unavailable: " + drv.why);
     if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
         return set_error(B200_ERR_CUDA, "cudaSetDevice failed");
+    {
+        int rc = ensure_compiled(r);
+        if (rc != B200_OK)
+            return rc;
+    }
     b200_render::Dev d;
     CUresult_ cr = drv.cuModuleLoadData(&d.mod, r->cubin.data());
     if (cr != 0)
@@ -620,6 +649,10 @@ b200_render_tiles(b200_render* r, int device, int ntiles, const int* tiles, void
         long long c1 = d.nslots_cap, c2 = d.nslots_cap, c3 = d.nslots_cap, c4 = d.nslots_cap;
         bool ok = grow(d, d.rec, c1, nslots, (size_t)16 * PATH_QUADS) && grow(d, d.shrec, c2, nslots, (size_t)16 * SHADOW_QUADS)
                   && grow(d, d.queues, c3, nslots, sizeof(int) * 4) && grow(d, d.sort_keys, c4, nslots, sizeof(int));
+        if (ok && r->info.uses_media) {
+            long long c5 = d.nslots_cap;
+            ok           = grow(d, d.medium, c5, nslots, sizeof(float) * MEDIUM_WORDS);
+        }
         if (!ok) {
             d.nslots_cap = 0;
             return set_error(B200_ERR_CUDA, "cudaMalloc(path pool) failed");
@@ -670,6 +703,7 @@ b200_render_tiles(b200_render* r, int device, int ntiles, const int* tiles, void
     L.npix        = (int)npix;
     L.result      = d.result;
     L.accum       = out_on_device ? (float*)out_rgb : d.accum;
+    L.medium      = d.medium;
     long long launches = 0, iters = 0;
     cudaEvent_t e0, e1, t0, t1;
     cudaEventCreate(&e0);

@@ -181,6 +181,27 @@ class Scene:
 
     # -- BVH (bvh.cpp) --------------------------------------------------------
     def build_bvh(self):
+        """The scene BVH, built by the library's native builder (b200_build_bvh)."""
+        import ctypes
+        from .. import api
+        L = api.lib()
+        verts = np.ascontiguousarray(np.array(self.verts, f32).reshape(-1, 3))
+        tris = np.ascontiguousarray(np.array(self.triangles, np.int32).reshape(-1, 3))
+        n = len(tris)
+        nodes = np.zeros((max(2 * n - 1, 1), 8), f32)
+        indices = np.zeros(n, np.uint32)
+        count = ctypes.c_int(0)
+        L.b200_build_bvh.restype = ctypes.c_int
+        rc = L.b200_build_bvh(ctypes.c_void_p(verts.ctypes.data), ctypes.c_int(len(verts)),
+                              ctypes.c_void_p(tris.ctypes.data), ctypes.c_int(n),
+                              ctypes.c_void_p(nodes.ctypes.data), ctypes.c_int(len(nodes)),
+                              ctypes.c_void_p(indices.ctypes.data), ctypes.byref(count))
+        if rc != 0:
+            raise ValueError("b200_build_bvh failed (%d): bad triangle indices?" % rc)
+        return nodes[:count.value].copy(), indices
+
+    def build_bvh_py(self):
+        """The same builder in numpy (slow; kept as the cross-check of the native one in tests)."""
         verts = np.array(self.verts, f32).reshape(-1, 3)
         tris = np.array(self.triangles, np.int32).reshape(-1, 3)
         n = len(tris)

@@ -472,8 +472,12 @@ class OracleRender:
             self.lib.oracle_set_bsdl_luts.argtypes = [ctypes.c_void_p]
             self.lib.oracle_set_bsdl_luts(self._luts.ctypes.data)
 
-    def render(self, xres, yres, aa, nthreads=None, **kw):
+    def render(self, xres, yres, aa, nthreads=None, rows=None, **kw):
+        """The whole image, or with rows=(y0, y1) only that band of it (the other rows stay 0;
+        pixels are independent, so a band equals the same rows of a full render)."""
         rs, keep = fill_render_scene(RenderScene, self.scene, self.arrays, xres, yres, aa, **kw)
         out = np.zeros((yres, xres, 3), np.float32)
-        self.lib.oracle_render(ctypes.byref(rs), out.ctypes.data, nthreads or (os.cpu_count() or 1))
+        y0, y1 = rows if rows else (0, yres)
+        self.lib.oracle_render_band(ctypes.c_void_p(ctypes.addressof(rs)), ctypes.c_void_p(out.ctypes.data),
+                                    int(nthreads or (os.cpu_count() or 1)), int(y0), int(y1))
         return out

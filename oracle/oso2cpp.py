@@ -1606,7 +1606,8 @@ static void oracle_render_rows(const RenderScene* S, int y0, int y1, float* out,
             p[0] = c.x; p[1] = c.y; p[2] = c.z;
         }
 }
-extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
+// rows [y0, y1) of the image (pixels are independent: a band equals the same rows of a full render)
+extern "C" void oracle_render_band(const RenderScene* S0, float* out, int nthreads, int y0, int y1)
 {
     RenderScene S1 = *S0;
     camera_finalize(S1);
@@ -1622,18 +1623,24 @@ extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
         g_background = &bg;
     }
     // scanline-parallel like the reference (parallel_for_chunked, simpleraytracer.cpp:1428)
-    if (nthreads <= 1) { oracle_render_rows(S, 0, S->yres, out, nullptr); return; }
+    y0 = std::max(y0, 0);
+    y1 = std::min(y1, S->yres);
+    if (nthreads <= 1) { oracle_render_rows(S, y0, y1, out, nullptr); return; }
     std::vector<std::thread> th;
-    std::atomic<int> next{0};
+    std::atomic<int> next{y0};
     for (int t = 0; t < nthreads; ++t)
         th.emplace_back([&] {
             for (;;) {
-                int y = next.fetch_add(4);
-                if (y >= S->yres) break;
-                oracle_render_rows(S, y, std::min(S->yres, y + 4), out, nullptr);
+                int y = next.fetch_add(2);
+                if (y >= y1) break;
+                oracle_render_rows(S, y, std::min(y1, y + 2), out, nullptr);
             }
         });
     for (auto& t : th) t.join();
+}
+extern "C" void oracle_render(const RenderScene* S0, float* out, int nthreads)
+{
+    oracle_render_band(S0, out, nthreads, 0, S0->yres);
 }
 """
 

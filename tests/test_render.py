@@ -38,7 +38,28 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          # artistic_ior, layer(dielectric_bsdf, diffuse), generalized_schlick_bsdf; anisotropic GGX
          "render-mx-conductor": ("mx_conductor.xml", 160, 120, 16),
          "render-mx-dielectric": ("mx_dielectric.xml", 160, 120, 16),
-         "render-mx-generalized-schlick": ("mx_generalized_schlick.xml", 160, 120, 16)}
+         "render-mx-generalized-schlick": ("mx_generalized_schlick.xml", 160, 120, 16),
+         # refracting dielectric / generalized-Schlick spheres that also declare the (vacuum) medium they
+         # enclose: medium_vdf closures, the per-path MediumStack, and - in -medium-vdf-glass - nested
+         # and overlapping spheres whose priorities turn boundaries into pass-through (a15)
+         "render-mx-dielectric-glass": ("mx_dielectric_glass.xml", 160, 120, 16),
+         "render-mx-generalized-schlick-glass": ("mx_generalized_schlick_glass.xml", 160, 120, 16),
+         "render-mx-medium-vdf-glass": ("mx_medium_vdf_glass.xml", 98, 98, 16)}
+# Scattering / absorbing media: free-flight sampling, Henyey-Greenstein phase function.  The
+# reference calls libm's expf / logf here; the device evaluates them in double and rounds once,
+# which differs from glibc in the last bit of a small share of calls, so these two compare within
+# a tolerance instead of bit for bit (GPU test below).
+MEDIA_CASES = {"render-mx-medium-vdf": ("mx_medium_vdf.xml", 98, 98, 32),
+               "render-mx-anisotropic-vdf": ("mx_anisotropic_vdf.xml", 98, 98, 32)}
+# The CPU suite pins the oracle on a band of rows of the slower scenes (pixels are independent, so
+# a band equals the same rows of the full render); the GPU tests compare whole frames against the
+# oracle and the golden images.
+BANDS = {"render-mx-furnace-oren-nayar": (24, 40), "render-mx-furnace-burley-diffuse": (24, 40),
+         "render-mx-medium-vdf-glass": (20, 44), "render-mx-generalized-schlick-glass": (36, 60),
+         "render-mx-anisotropic-vdf": (40, 56), "render-mx-medium-vdf": (40, 56),
+         "render-mx-dielectric-glass": (48, 72), "render-mx-generalized-schlick": (48, 72),
+         "render-mx-conductor": (48, 72), "render-mx-dielectric": (48, 72), "render-ward": (50, 80),
+         "render-oren-nayar": (50, 80)}
 # BASELINE config 4's other half: glossy glass spheres under the kitchen light probe, read by
 # texture() in the background shader (1024^2 importance table + directly seen + bounce misses).
 # Texture filtering is OIIO's in the reference (not buildable here), so this golden pins the
@@ -52,7 +73,8 @@ _cache = {}
 
 def _scene(case):
     if case not in _cache:
-        S = sc.load_scene(os.path.join(SCENES, (CASES.get(case) or TEXTURED_CASES.get(case) or OWN_CASES[case])[0]))
+        S = sc.load_scene(os.path.join(SCENES, (CASES.get(case) or TEXTURED_CASES.get(case) or MEDIA_CASES.get(case)
+                                                or OWN_CASES[case])[0]))
         _cache[case] = (S, S.prepare())
     return _cache[case]
 
@@ -85,27 +107,49 @@ def test_scene_preparation_invariants():
             assert np.all(nodes[c, [0, 2, 4]] >= nodes[i, [0, 2, 4]]) and np.all(nodes[c, [1, 3, 5]] <= nodes[i, [1, 3, 5]])
 
 
-@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("case", ["render-veachmis", "render-bunny"])
+def test_native_bvh_equals_numpy_builder(b200lib, case):
+    """b200_build_bvh (C++) against the numpy restatement of bvh.cpp it replaced: the same nodes,
+    bit for bit, and the same primitive order (the traversal order decides ties between hits)."""
+    S, _ = _scene(case)
+    n1, i1 = S.build_bvh()
+    n2, i2 = S.build_bvh_py()
+    assert np.array_equal(n1.view(np.uint32), n2.view(np.uint32)) and np.array_equal(i1, i2)
+
+
+@pytest.mark.parametrize("case", sorted(CASES) + sorted(MEDIA_CASES))
 def test_oracle_matches_reference_golden_render(case):
     S, A = _scene(case)
-    xml, xres, yres, aa = CASES[case]
+    xml, xres, yres, aa = CASES.get(case) or MEDIA_CASES[case]
     R = oracle.OracleRender(S, A, helpers.oso)
-    img = R.render(xres, yres, aa, nthreads=8)
+    y0, y1 = BANDS.get(case, (0, yres))
+    img = R.render(xres, yres, aa, nthreads=8, rows=(y0, y1))
     ref = _golden(case)
     assert img.shape == ref.shape
+    img, ref = img[y0:y1], ref[y0:y1]
+    if case in BANDS and "furnace" not in case:
+        assert ref.std() > 0.01       # the band crosses the objects, not just the backdrop
     _check_thresholds(img, ref)
     # far stronger in practice: identical after rounding to the golden's half precision
     h = img.astype(np.float16).astype(np.float32)
     exact = (np.abs(h - ref).max(axis=2) == 0).mean()
-    if case.startswith("render-mx-furnace"):
-        # These goldens carry per-path noise against this host (the reference's run.py
-        # loosens them "to allow a little more LSB noise between platforms"): ~4 % of
-        # pixels differ by one or two paths out of 256.  The difference must be unbiased.
-        assert exact > 0.95 and abs(float((img - ref).mean())) < 1e-4, (exact, float((img - ref).mean()))
-    elif case in ("render-mx-conductor", "render-mx-dielectric", "render-mx-generalized-schlick"):
-        assert exact > 0.985, exact      # measured 0.993 / 0.991 / 0.990
-    else:
-        assert exact > 0.99, exact
+    # Share of the compared pixels that equal the golden at its half precision (measured value in
+    # the comment; the default 0.99 holds for the whole-frame cases).  The rest differ by a path or
+    # two out of aa^2: platform LSB noise that the reference's run.py thresholds allow for, which
+    # long refractive chains amplify (the reference keeps out-linux-alt.exr for the same reason).
+    # It must be unbiased.
+    exact_min = {"render-mx-furnace-oren-nayar": 0.86,          # 0.887 (band through the spheres)
+                 "render-mx-furnace-burley-diffuse": 0.87,      # 0.894
+                 "render-mx-conductor": 0.96,                   # 0.979
+                 "render-mx-dielectric": 0.955,                 # 0.975
+                 "render-mx-generalized-schlick": 0.95,         # 0.968
+                 "render-mx-dielectric-glass": 0.74,            # 0.770 (whole frame 0.930)
+                 "render-mx-generalized-schlick-glass": 0.95,   # 0.969
+                 "render-mx-medium-vdf-glass": 0.87,            # 0.897
+                 "render-mx-medium-vdf": 0.98,                  # 0.990
+                 "render-mx-anisotropic-vdf": 0.985}            # 0.997
+    assert exact > exact_min.get(case, 0.99), exact
+    assert abs(float((img - ref).mean())) < 1e-4, float((img - ref).mean())
 
 
 def test_oracle_render_microfacet_within_reference_thresholds():
@@ -161,6 +205,39 @@ def test_gpu_render_bit_exact_vs_oracle(b200lib, cuda_device, case, sort):
         _check_thresholds(got, _golden(case))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(MEDIA_CASES))
+def test_gpu_render_media_vs_oracle(b200lib, cuda_device, case):
+    """Volume scattering: the same paths as the oracle up to the last bit of expf / logf.
+    Tolerance: every pixel within 2e-3 of the oracle (the noise of one path in 1024 that took a
+    different branch after a last-bit difference), 99 % of them within 1e-5, no bias; and the
+    reference's own thresholds against its golden image."""
+    from openshadinglanguage_b200 import api
+    S, A = _scene(case)
+    xml, xres, yres, aa = MEDIA_CASES[case]
+    want = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
+    for opts in ("fma=0", "fma=0,sort=0,tail=0"):
+        R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options=opts)
+        got = R.render()
+        assert R.stats["paths"] == xres * yres * aa * aa
+        d = np.abs(got - want).max(axis=2)
+        assert d.max() < 2e-3, d.max()
+        assert (d < 1e-5).mean() > 0.99, (d < 1e-5).mean()
+        assert abs(float((got - want).mean())) < 1e-6
+        _check_thresholds(got, _golden(case))
+
+
+def test_media_module_is_specialised(b200lib):
+    """Only scenes whose materials create medium_vdf / anisotropic_vdf closures carry the per-slot
+    medium stack and the free-flight code."""
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-mx-dielectric")
+    assert "OSLD_HAS_MEDIA" not in api.Renderer(S, A, helpers.oso, 32, 32, 1, options="compile=0").cuda_source
+    for case in ("render-mx-medium-vdf", "render-mx-medium-vdf-glass"):
+        S, A = _scene(case)
+        assert "#define OSLD_HAS_MEDIA 1" in api.Renderer(S, A, helpers.oso, 32, 32, 1, options="compile=0").cuda_source
+
+
 def test_oracle_microfacet_scene_is_sane():
     """Energy / finiteness checks on the own microfacet scene (no golden image):
     every distribution and refract mode is hit, nothing is NaN, the unknown
@@ -178,10 +255,10 @@ def test_glossy_module_is_specialised(b200lib):
     creates them (phong / ward / microfacet closures)."""
     from openshadinglanguage_b200 import api
     S, A = _scene("render-cornell")
-    assert "OSLD_GLOSSY_LOBES" not in api.Renderer(S, A, helpers.oso, 32, 32, 1).cuda_source
+    assert "OSLD_GLOSSY_LOBES" not in api.Renderer(S, A, helpers.oso, 32, 32, 1, options="compile=0").cuda_source
     for case in ("render-veachmis", "render-ward", "microfacet"):
         S, A = _scene(case)
-        src = api.Renderer(S, A, helpers.oso, 32, 32, 1).cuda_source
+        src = api.Renderer(S, A, helpers.oso, 32, 32, 1, options="compile=0").cuda_source
         assert "#define OSLD_GLOSSY_LOBES 1" in src
     assert "MICROFACET_ID" in src
 

@@ -77,6 +77,13 @@ SHADERS = {
     "mxcond_glossy": "render-mx-conductor/glossy.osl",
     "mxdiel_glossy": "render-mx-dielectric/glossy.osl",
     "mxgs_glossy": "render-mx-generalized-schlick/glossy.osl",
+    # refractive MaterialX lobes and participating media (MediumStack)
+    "mxdielglass_glossy": "render-mx-dielectric-glass/glossy.osl",
+    "mxgsglass_glossy": "render-mx-generalized-schlick-glass/glossy.osl",
+    "mxmed_envmap": "render-mx-medium-vdf/envmap.osl",
+    "mxmed_medium": "render-mx-medium-vdf/medium.osl",
+    "mxmedglass_glossy": "render-mx-medium-vdf-glass/glossy.osl",
+    "mxaniso_anisotropic": "render-mx-anisotropic-vdf/anisotropic.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -114,6 +121,14 @@ SCENES = {
     "mx_dielectric.xml": ("render-mx-dielectric/scene.xml", {"glossy": "mxdiel_glossy", "envmap": "mxspec_envmap"}),
     "mx_generalized_schlick.xml": ("render-mx-generalized-schlick/scene.xml",
                                    {"glossy": "mxgs_glossy", "envmap": "mxspec_envmap"}),
+    "mx_dielectric_glass.xml": ("render-mx-dielectric-glass/scene.xml",
+                                {"glossy": "mxdielglass_glossy", "envmap": "mxspec_envmap"}),
+    "mx_generalized_schlick_glass.xml": ("render-mx-generalized-schlick-glass/scene.xml",
+                                         {"glossy": "mxgsglass_glossy", "envmap": "mxspec_envmap"}),
+    "mx_medium_vdf.xml": ("render-mx-medium-vdf/scene.xml", {"medium": "mxmed_medium", "envmap": "mxmed_envmap"}),
+    "mx_medium_vdf_glass.xml": ("render-mx-medium-vdf-glass/scene.xml", {"glossy": "mxmedglass_glossy"}),
+    "mx_anisotropic_vdf.xml": ("render-mx-anisotropic-vdf/scene.xml",
+                               {"anisotropic": "mxaniso_anisotropic", "envmap": "mxmed_envmap"}),
 }
 # input images read by texture() (test input data, copied byte for byte)
 TEXTURES = {"kitchen_probe.hdr": "common/textures/kitchen_probe.hdr"}
@@ -132,6 +147,11 @@ RENDERS = {
     "render-mx-conductor": "render-mx-conductor/ref/out.exr",
     "render-mx-dielectric": "render-mx-dielectric/ref/out.exr",
     "render-mx-generalized-schlick": "render-mx-generalized-schlick/ref/out.exr",
+    "render-mx-dielectric-glass": "render-mx-dielectric-glass/ref/out.exr",
+    "render-mx-generalized-schlick-glass": "render-mx-generalized-schlick-glass/ref/out.exr",
+    "render-mx-medium-vdf": "render-mx-medium-vdf/ref/out.exr",
+    "render-mx-medium-vdf-glass": "render-mx-medium-vdf-glass/ref/out.exr",
+    "render-mx-anisotropic-vdf": "render-mx-anisotropic-vdf/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
