@@ -441,8 +441,42 @@ OSLD float sheen_conty_albedo(float cosNO, float rough)
     rx = rx + 1086.96473f * rough * rough;      ry = ry + 3045.55075f * rough * rough;
     return bsdl_clamp(rx / ry, 0.0f, 1.0f);
 }
-// everything SheenLobe's constructor derives; l.N (shading normal) and l.albedo set by the caller
-OSLD void sheen_setup(Lobe& l, V3 wo, float roughness_param, bool backfacing, float path_roughness)
+// ---- mtx::ZeltnerBurleySheen (MTX/bsdf_sheen_impl.h:205-355): sheen as a linearly transformed
+// cosine.  The (A, B, R) coefficients are bilinear look-ups in a 32 x 32 table over (roughness,
+// cos theta_o) that follows the energy tables in the LUT block (data/zeltner_ltc.bin); they depend
+// on the view direction only, so the lobe fetches them once at set-up (l.ltc).  Compiled into
+// modules whose materials pass a "mode" keyword to sheen_bsdf (OSLD_SHEEN_LTC).
+#ifdef OSLD_SHEEN_LTC
+#define OSLD_LUT_ZELTNER (256 + 3 * 8192)
+OSLD V3 zeltner_fetch_coeffs(const float* luts, float roughness, float cosNO)
+{
+    const float ALMOSTONE = 0.999999940395355224609375f;
+    const float row = bsdl_clamp(roughness, 0.0f, ALMOSTONE) * 31;
+    const float col = bsdl_clamp(cosNO, 0.0f, ALMOSTONE) * 31;
+    const float r = floorf(row), c = floorf(col);
+    const float rf = row - r, cf = col - c;
+    const float* T = luts + OSLD_LUT_ZELTNER + 3 * ((int)r * 32 + (int)c);
+    const V3 v1 = mkv(__ldg(T), __ldg(T + 1), __ldg(T + 2)), v2 = mkv(__ldg(T + 3), __ldg(T + 4), __ldg(T + 5));
+    const V3 v3 = mkv(__ldg(T + 96), __ldg(T + 97), __ldg(T + 98)), v4 = mkv(__ldg(T + 99), __ldg(T + 100), __ldg(T + 101));
+    const V3 a = (1 - cf) * v1 + cf * v2, b = (1 - cf) * v3 + cf * v4;
+    return (1 - rf) * a + rf * b;
+}
+OSLD BSample zeltner_eval_ltc(V3 wi, V3 ltc)
+{
+    const float a_inv = ltc.x, b_inv = ltc.y, r_coeff = ltc.z;
+    const V3 wi_orig  = mkv(a_inv * wi.x + b_inv * wi.z, a_inv * wi.y, wi.z);
+    const float q        = a_inv / dot3(wi_orig, wi_orig);
+    const float jacobian = q * q;
+    const float pdf      = jacobian * fmaxf(wi_orig.z, 0.0f) * (1 / (float)OSLD_PI);
+    if (pdf > 1.17549435e-38f)
+        return bs_make(wi, mkv(r_coeff), pdf, 0.0f);
+    return bs_null();
+}
+#endif
+// everything SheenLobe's constructor derives; l.N (shading normal) and l.albedo set by the caller.
+// l.refract: bit 0 = backfacing, bit 1 = Zeltner mode ("mode" keyword == 1)
+OSLD void sheen_setup(Lobe& l, V3 wo, float roughness_param, bool backfacing, float path_roughness, int mode = 0,
+                      const float* luts = nullptr)
 {
     const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
     // Frame(Z, X = wo) (tools.h:483-495)
@@ -461,10 +495,20 @@ OSLD void sheen_setup(Lobe& l, V3 wo, float roughness_param, bool backfacing, fl
     l.refract     = backfacing ? 1 : 0;
     const float cosNO = bsdl_clamp(dot3(Z, wo), 0.0f, 1.0f);
     const float tmax  = fmaxf(l.albedo.x, fmaxf(l.albedo.y, l.albedo.z));
+#ifdef OSLD_SHEEN_LTC
+    if (mode == 1) {
+        l.refract |= 2;
+        l.ax = bsdl_clamp(fmaxf(0.02f, sqrtf(l.ay)), 0.02f, 1.0f);   // sheen_alpha, then ZeltnerBurleySheen's clamp
+        // eval / sample look the coefficients up at wo.z in the lobe's frame
+        l.ltc = zeltner_fetch_coeffs(luts, l.ax, dot3(Z, wo));
+        l.eta = backfacing ? 1.0f : 1 - fminf(zeltner_fetch_coeffs(luts, l.ax, cosNO).z * tmax, 1.0f);
+        return;
+    }
+#endif
     l.eta = backfacing ? 1.0f : 1 - fminf(sheen_conty_albedo(cosNO, bsdl_clamp(l.ax, 0.06f, 1.0f)) * tmax, 1.0f);
 }
-// SheenMicrofacet<ContyKullaDist<false>>::eval, then SheenLobe's tint and roughness tag
-OSLD BSample sheen_micro_eval(const Lobe& l, V3 wo, V3 wi)
+// SheenMicrofacet<ContyKullaDist<false>>::eval
+OSLD BSample sheen_conty_eval(const Lobe& l, V3 wo, V3 wi)
 {
     const float PI_F = (float)OSLD_PI, ONEOVERPI = 1 / (float)OSLD_PI;
     const float cosNO = wo.z, cosNI = wi.z;
@@ -481,24 +525,43 @@ OSLD BSample sheen_micro_eval(const Lobe& l, V3 wo, V3 wi)
             s = bs_make(wi, mkv(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0.0f);
         }
     }
-    s.weight    = s.weight * l.albedo;
-    s.roughness = l.ay;
     return s;
 }
+// SheenLobe::eval_impl / sample_impl: the mode's lobe, then the tint and the roughness tag
 OSLD BSample sheen_eval(const Lobe& l, V3 wo, V3 wi)
 {
     const V3 wo_l = frame_tolocal(l, wo), wi_l = frame_tolocal(l, wi);
     BSample s     = bs_null();
-    if (wi_l.z > 0 && wo_l.z >= 0 && !l.refract)
-        s = sheen_micro_eval(l, wo_l, wi_l);
+    if (wi_l.z > 0 && wo_l.z >= 0 && !(l.refract & 1)) {
+#ifdef OSLD_SHEEN_LTC
+        if (l.refract & 2)
+            s = zeltner_eval_ltc(wi_l, l.ltc);
+        else
+#endif
+            s = sheen_conty_eval(l, wo_l, wi_l);
+        s.weight    = s.weight * l.albedo;
+        s.roughness = l.ay;
+    }
     s.wi = wi;
     return s;
 }
 OSLD BSample sheen_sample(const Lobe& l, V3 wo, float rx, float ry)
 {
     BSample s = bs_null();
-    if (!l.refract)
-        s = sheen_micro_eval(l, frame_tolocal(l, wo), bsdl_sample_uniform_hemisphere(rx, ry));
+    if (!(l.refract & 1)) {
+        const V3 wo_l = frame_tolocal(l, wo);
+#ifdef OSLD_SHEEN_LTC
+        if (l.refract & 2) {
+            if (!(wo_l.z < 0)) {   // cosine base distribution transformed by M
+                const V3 o = bsdl_sample_cos_hemisphere(rx, ry);
+                s = zeltner_eval_ltc(vnormalized(mkv(o.x - o.z * l.ltc.y, o.y, l.ltc.x * o.z)), l.ltc);
+            }
+        } else
+#endif
+            s = sheen_conty_eval(l, wo_l, bsdl_sample_uniform_hemisphere(rx, ry));
+        s.weight    = s.weight * l.albedo;
+        s.roughness = l.ay;
+    }
     s.wi = frame_toworld(l, s.wi);
     return s;
 }

@@ -356,6 +356,9 @@ struct Lobe {
     float ax, ay;
     int refract, ggx;
     V3 albedo;
+#ifdef OSLD_SHEEN_LTC
+    V3 ltc;      // Zeltner-Burley sheen: the view's (A, B, R) coefficients
+#endif
 #endif
 #ifdef OSLD_MX_LOBES
     MxSpec mx;   // LOBE_MX_SPEC: frame in (fu, fv, N)
@@ -576,7 +579,7 @@ OSLD V3 evaluate_layer_opacity(const ClosurePool& pool, int closure, V3 wo, bool
                 Lobe l;
                 l.N      = mkv(q[0], q[1], q[2]);
                 l.albedo = mkv(q[3], q[4], q[5]);
-                sheen_setup(l, wo, q[6], backfacing, path_roughness);
+                sheen_setup(l, wo, q[6], backfacing, path_roughness, __float_as_int(q[7]), luts);
                 weight = weight * (w * (mkv(1.0f) - mkv(l.eta)));
 #ifdef OSLD_MX_LOBES
             } else if (id == MX_DIELECTRIC_ID) {
@@ -654,7 +657,7 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                     // params: N, albedo, roughness, mode; mode 1 (Zeltner LTC sheen) is not built
                     l.albedo = mkv(q[3], q[4], q[5]);
                     l.type   = LOBE_BSDL_SHEEN;
-                    sheen_setup(l, wo, q[6], backfacing, path_roughness);
+                    sheen_setup(l, wo, q[6], backfacing, path_roughness, __float_as_int(q[7]), luts);
                     known = __float_as_int(q[7]) == 0;
                     break;
 #ifdef OSLD_MX_LOBES

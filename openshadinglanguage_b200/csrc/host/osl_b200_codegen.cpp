@@ -1438,6 +1438,8 @@ Gen::emit_op(const Opcode& op)
             g.closure_adds += 1;
         else if (cn == "anisotropic_vdf" || cn == "medium_vdf")
             g.uses_media = true;
+        if (cn == "sheen_bsdf" && !kw.empty())   // a "mode" keyword may select the Zeltner-Burley LTC sheen
+            g.uses_sheen_ltc = true;
         else if (cn != "emission" && cn != "background" && cn != "uniform_edf")
             g.lobe_bound += 1;
         if (cn == "phong" || cn == "ward" || cn == "microfacet" || cn == "oren_nayar" || cn == "oren_nayar_diffuse_bsdf"
@@ -2062,7 +2064,7 @@ std::string
 generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderModuleInfo* info)
 {
     std::string mats;
-    bool color = false, glossy = false, mx = false, in_loop = false, media = false;
+    bool color = false, glossy = false, mx = false, in_loop = false, media = false, sheen_ltc = false;
     int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
     int pool_words = 2, lobes = 1, adds = 0;
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -2078,6 +2080,7 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         glossy |= g.uses_glossy_lobes;
         mx |= g.uses_mx_lobes;
         media |= g.uses_media;
+        sheen_ltc |= g.uses_sheen_ltc;
         in_loop |= g.closure_in_loop;
         pool_words = std::max(pool_words, g.pool_words_bound);
         lobes      = std::max(lobes, g.lobe_bound);
@@ -2117,9 +2120,13 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         out << "#define OSLD_MX_LOBES 1\n";
     if (media)
         out << "#define OSLD_HAS_MEDIA 1\n";
+    if (sheen_ltc)
+        out << "#define OSLD_SHEEN_LTC 1\n";
     mi.uses_mx_lobes = mx;
     mi.uses_media    = media;
+    mi.uses_luts     = mx || sheen_ltc;
     if (info) {
+        info->uses_luts     = mx || sheen_ltc;
         info->uses_mx_lobes = mx;
         info->uses_media    = media;
     }

@@ -152,6 +152,7 @@ struct Group {
     std::set<int> globals_read;                // b200_sg_field ids the kernel loads
     bool fma = true;                           // allow FMA contraction in generated code
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
+    bool uses_sheen_ltc    = false;            // set by codegen: sheen_bsdf with a "mode" keyword
     bool uses_media        = false;            // set by codegen: medium_vdf / anisotropic_vdf closures
     bool uses_mx_lobes     = false;            // set by codegen: conductor / dielectric / generalized schlick ...
     bool uses_colorsystem  = false;            // set by codegen: luminance / blackbody / transformc ...
@@ -200,6 +201,7 @@ struct RenderModuleInfo {
     int closure_stack = 16;     // OSLD_CLOSURE_STACK
     bool pool_in_smem = false;  // OSLD_POOL_SMEM: arena staged in shared memory
     bool uses_mx_lobes = false; // OSLD_MX_LOBES: the module reads the libbsdl energy tables
+    bool uses_luts     = false; // the module reads the LUT block (energy tables and / or sheen LTC coefficients)
     bool uses_media    = false; // OSLD_HAS_MEDIA: every path slot carries a medium stack
 };
 std::string generate_cuda_render(std::vector<Group*>& groups, bool has_background = false,

@@ -367,15 +367,24 @@ load_bsdl_luts(std::vector<float>& out)
         return "cannot locate libosl_b200.so to find data/bsdl_luts.bin";
     std::string path = info.dli_fname;
     size_t slash     = path.rfind('/');
-    path             = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/data/bsdl_luts.bin";
-    FILE* f          = fopen(path.c_str(), "rb");
-    if (!f)
-        return "cannot open " + path + " (energy tables of the MaterialX microfacet closures; tools/bake_bsdl_luts.cpp)";
-    out.resize(256 + 3 * 8192);
-    size_t n = fread(out.data(), sizeof(float), out.size(), f);
-    fclose(f);
-    if (n != out.size())
-        return path + " is truncated";
+    const std::string dir = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/data/";
+    // energy tables of the MaterialX microfacet closures (tools/bake_bsdl_luts.cpp), then the
+    // Zeltner-Burley sheen LTC coefficients (tools/bake_zeltner_ltc.py): one block, in this order
+    const struct { const char* file; size_t words; } parts[] = { { "bsdl_luts.bin", 256 + 3 * 8192 },
+                                                                  { "zeltner_ltc.bin", 32 * 32 * 3 } };
+    out.clear();
+    for (const auto& part : parts) {
+        const std::string file = dir + part.file;
+        FILE* f                = fopen(file.c_str(), "rb");
+        if (!f)
+            return "cannot open " + file + " (tables of the MaterialX closures)";
+        const size_t at = out.size();
+        out.resize(at + part.words);
+        size_t n = fread(out.data() + at, sizeof(float), part.words, f);
+        fclose(f);
+        if (n != part.words)
+            return file + " is truncated";
+    }
     return "";
 }
 
@@ -490,7 +499,7 @@ ensure_device(b200_render* r, int device, b200_render::Dev** out)
         }
         S.leaf_tris = upload(d, lt.data(), lt.size(), ok);
     }
-    if (r->info.uses_mx_lobes) {
+    if (r->info.uses_luts) {
         // energy-compensation tables of the MaterialX microfacet closures: product data next to the library
         std::vector<float> luts;
         std::string lerr = load_bsdl_luts(luts);

@@ -246,7 +246,9 @@ BSDL_LUTS = os.path.join(os.path.dirname(oso2cpp.HERE), "openshadinglanguage_b20
 def bsdl_luts():
     """The energy tables of the libbsdl microfacet lobes (float32, layout in osl_oracle_mxlobes.h):
     data baked by tools/bake_bsdl_luts.cpp and shipped with the product."""
-    return np.fromfile(BSDL_LUTS, np.float32)
+    luts = np.fromfile(BSDL_LUTS, np.float32)
+    ltc = os.path.join(os.path.dirname(BSDL_LUTS), "zeltner_ltc.bin")   # tools/bake_zeltner_ltc.py
+    return np.concatenate([luts, np.fromfile(ltc, np.float32)])
 
 
 def shadeops():

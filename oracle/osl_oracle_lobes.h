@@ -480,40 +480,89 @@ inline float sheen_conty_albedo(float cosNO, float rough)
     rx = rx + 1086.96473f * rough * rough;      ry = ry + 3045.55075f * rough * rough;
     return bsdl_clamp(rx / ry, 0.0f, 1.0f);
 }
+// ---- mtx::ZeltnerBurleySheen (MTX/bsdf_sheen_impl.h:205-355): sheen as a linearly transformed
+// cosine; the (A, B, R) coefficients come from a 32 x 32 table over (roughness, cos theta_o)
+// that follows the energy tables in the LUT block (data/zeltner_ltc.bin)
+enum { LUT_ZELTNER = LUT_WORDS, LUT_WORDS_ALL = LUT_WORDS + 32 * 32 * 3 };
+inline V3 zeltner_fetch_coeffs(float roughness, float cosNO)
+{
+    const float ALMOSTONE = 0.999999940395355224609375f;
+    const int ltc_res     = 32;
+    float row = bsdl_clamp(roughness, 0.0f, ALMOSTONE) * (ltc_res - 1);
+    float col = bsdl_clamp(cosNO, 0.0f, ALMOSTONE) * (ltc_res - 1);
+    float r   = std::floor(row);
+    float c   = std::floor(col);
+    float rf  = row - r;
+    float cf  = col - c;
+    int ri    = (int)r;
+    int ci    = (int)c;
+    const float* T = bsdl_luts() + LUT_ZELTNER;
+    auto at = [&](int rr, int cc) { const float* q = T + 3 * (rr * 32 + cc); return V3(q[0], q[1], q[2]); };
+    auto lerp3 = [](float f, const V3& a, const V3& b) { return (1 - f) * a + f * b; };
+    return lerp3(rf, lerp3(cf, at(ri, ci), at(ri, ci + 1)), lerp3(cf, at(ri + 1, ci), at(ri + 1, ci + 1)));
+}
+inline BSample zeltner_eval_ltc(float roughness, const V3& wi, const V3& ltc)
+{
+    const float a_inv = ltc.x, b_inv = ltc.y, r_coeff = ltc.z;
+    const V3 wi_orig(a_inv * wi.x + b_inv * wi.z, a_inv * wi.y, wi.z);
+    const float q        = a_inv / dot(wi_orig, wi_orig);
+    const float jacobian = q * q;
+    const float pdf      = jacobian * std::max(wi_orig.z, 0.0f) * (1 / float(M_PI));
+    if (pdf > std::numeric_limits<float>::min())
+        return BSample(wi, V3(r_coeff), pdf, roughness);
+    return BSample();
+}
 // set up everything SheenLobe's constructor derives (sheen_alpha in ax, regularized
-// roughness in ay, Emiss in emiss)
-inline void sheen_setup(Lobe& l, const V3& wo, float roughness_param, bool backfacing, float path_roughness)
+// roughness in ay, Emiss in emiss, mode in refract)
+inline void sheen_setup(Lobe& l, const V3& wo, float roughness_param, bool backfacing, float path_roughness, int mode = 0)
 {
     const V3 Z   = bsdl_visible_normal(wo, l.N, l.N);
     l.tf         = bsdl_frame_zx(Z, wo);
     const float r = bsdl_clamp(roughness_param, 0.0f, 1.0f);
     l.ay         = 1.0f - (1.0f - r) * (1.0f - path_roughness);   // regularize_roughness
-    l.ax         = std::max(0.06f, l.ay);                          // ContyKullaDist::MIN_ROUGHNESS
+    l.refract    = mode == 1;                                      // SheenLobe::ZELTNER
+    // MIN_ROUGHNESS of ZeltnerBurleySheen / ContyKullaDist
+    l.ax         = l.refract ? std::max(0.02f, std::sqrt(l.ay)) : std::max(0.06f, l.ay);
     l.backfacing = backfacing;
     const float cosNO = bsdl_clamp(dot(Z, wo), 0.0f, 1.0f);
     const float tmax  = std::max(l.albedo.x, std::max(l.albedo.y, l.albedo.z));
-    l.emiss = backfacing ? 1.0f : 1 - std::min(sheen_conty_albedo(cosNO, bsdl_clamp(l.ax, 0.06f, 1.0f)) * tmax, 1.0f);
+    if (backfacing)
+        l.emiss = 1.0f;
+    else if (l.refract)
+        l.emiss = 1 - std::min(zeltner_fetch_coeffs(bsdl_clamp(l.ax, 0.02f, 1.0f), cosNO).z * tmax, 1.0f);
+    else
+        l.emiss = 1 - std::min(sheen_conty_albedo(cosNO, bsdl_clamp(l.ax, 0.06f, 1.0f)) * tmax, 1.0f);
+}
+// SheenMicrofacet<ContyKullaDist<false>>::eval
+inline BSample sheen_conty_eval(const Lobe& l, const V3& wo, const V3& wi)
+{
+    const float PI_F = float(M_PI), ONEOVERPI = 1 / float(M_PI);
+    const float cosNO = wo.z, cosNI = wi.z;
+    if (cosNI <= 1e-5f || cosNO <= 1e-5f)
+        return BSample();
+    const float a   = bsdl_clamp(l.ax, 0.06f, 1.0f);
+    const V3 Hr     = normalized(wo + wi);
+    float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
+    float sin_theta = std::sqrt(1.0f - SQR(cos_theta));
+    const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
+    if (D < 1e-6)
+        return BSample();
+    float cI = std::min(1.0f, wi.z), cO = std::min(1.0f, wo.z);
+    const float G2 = (cI * cO) / (cI + cO - cI * cO);
+    return BSample(wi, V3(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0);
 }
 inline BSample sheen_eval_local(const Lobe& l, const V3& wo, const V3& wi)
 {
-    const float PI_F = float(M_PI), ONEOVERPI = 1 / float(M_PI);
     const float cosNO = wo.z, cosNI = wi.z;
     const bool is_reflection = cosNI > 0 && cosNO >= 0;
     BSample s;
     if (is_reflection && !l.backfacing) {
-        // SheenMicrofacet<ContyKullaDist<false>>::eval
-        if (!(cosNI <= 1e-5f || cosNO <= 1e-5f)) {
-            const float a  = bsdl_clamp(l.ax, 0.06f, 1.0f);
-            const V3 Hr    = normalized(wo + wi);
-            float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
-            float sin_theta = std::sqrt(1.0f - SQR(cos_theta));
-            const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
-            if (!(D < 1e-6)) {
-                float cI = std::min(1.0f, wi.z), cO = std::min(1.0f, wo.z);
-                const float G2 = (cI * cO) / (cI + cO - cI * cO);
-                s = BSample(wi, V3(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0);
-            }
-        }
+        if (l.refract) {
+            const float rough = bsdl_clamp(l.ax, 0.02f, 1.0f);
+            if (!(wo.z < 0 || wi.z <= 0))
+                s = zeltner_eval_ltc(rough, wi, zeltner_fetch_coeffs(rough, wo.z));
+        } else
+            s = sheen_conty_eval(l, wo, wi);
         s.weight    = s.weight * l.albedo;
         s.roughness = l.ay;
     }
@@ -529,22 +578,19 @@ inline BSample sheen_sample(const Lobe& l, const V3& wo, float rx, float ry)
     BSample s;
     if (!l.backfacing) {
         const V3 wo_l = l.tf.tolocal(wo);
-        const V3 wi   = bsdl_sample_uniform_hemisphere(rx, ry);
-        // SheenMicrofacet::sample -> eval, then SheenLobe::sample_impl scales and tags it
-        const float PI_F = float(M_PI), ONEOVERPI = 1 / float(M_PI);
-        const float cosNO = wo_l.z, cosNI = wi.z;
-        if (!(cosNI <= 1e-5f || cosNO <= 1e-5f)) {
-            const float a  = bsdl_clamp(l.ax, 0.06f, 1.0f);
-            const V3 Hr    = normalized(wo_l + wi);
-            float cos_theta = bsdl_clamp(Hr.z, 0.0f, 1.0f);
-            float sin_theta = std::sqrt(1.0f - SQR(cos_theta));
-            const float D   = fast_safe_pow(sin_theta, 1 / a) * (2 + 1 / a) * 0.5f * ONEOVERPI;
-            if (!(D < 1e-6)) {
-                float cI = std::min(1.0f, wi.z), cO = std::min(1.0f, wo_l.z);
-                const float G2 = (cI * cO) / (cI + cO - cI * cO);
-                s = BSample(wi, V3(D * G2 * 0.5f * PI_F / cosNO), 0.5f * ONEOVERPI, 0);
+        if (l.refract) {
+            // cosine base distribution transformed by M
+            const float rough = bsdl_clamp(l.ax, 0.02f, 1.0f);
+            if (!(wo_l.z < 0)) {
+                const V3 ltc = zeltner_fetch_coeffs(rough, wo_l.z);
+                const V3 o   = bsdl_sample_cos_hemisphere(rx, ry);
+                const V3 wi(o.x - o.z * ltc.y, o.y, ltc.x * o.z);
+                s = zeltner_eval_ltc(rough, normalized(wi), ltc);
             }
-        }
+        } else
+            // SheenMicrofacet::sample -> eval
+            s = sheen_conty_eval(l, wo_l, bsdl_sample_uniform_hemisphere(rx, ry));
+        // SheenLobe::sample_impl scales and tags it
         s.weight    = s.weight * l.albedo;
         s.roughness = l.ay;
     }

@@ -717,8 +717,9 @@ inline bool sheen_from_component(Lobe& l, const ClosComp* comp, const SG& sg, fl
     l.type   = LOBE_BSDL_SHEEN;
     l.N      = V3(comp->params[0], comp->params[1], comp->params[2]);
     l.albedo = V3(comp->params[3], comp->params[4], comp->params[5]);
-    lobes::sheen_setup(l, -sg.I.val, comp->params[6], sg.backfacing != 0, path_roughness);
-    return f2u(comp->params[7]) == 0;   // mode 1 (Zeltner LTC sheen) is not restated
+    // "mode" keyword: 1 = Zeltner-Burley LTC sheen, anything else = Conty-Kulla (SheenLobe::use_zeltner)
+    lobes::sheen_setup(l, -sg.I.val, comp->params[6], sg.backfacing != 0, path_roughness, (int)f2u(comp->params[7]));
+    return true;
 }
 // mtx::ConductorLobe / DielectricLobe / SchlickLobe from their closure components (parameter
 // order = the Data structs' registration order; the distribution string takes one word)

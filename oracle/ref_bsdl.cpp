@@ -179,7 +179,7 @@ ref_bsdl(int lobe, const float* p, const float* wo, int backfacing, float path_r
 }
 
 // raw LUT access: table 0 MiniMicrofacetGGX, 1 DielectricReflFront, 2 DielectricBothFront,
-// 3 DielectricBothBack, 4 ZeltnerBurleySheen, 5 ContyKullaSheen, 6 Thinlayer
+// 3 DielectricBothBack, 4 ZeltnerBurleySheen, 5 ContyKullaSheen, 6 Thinlayer, 7 Zeltner LTC coefficients
 extern "C" const float*
 ref_bsdl_lut(int table, int* count)
 {
@@ -195,6 +195,10 @@ ref_bsdl_lut(int table, int* count)
         T(6, spi::Thinlayer)
     }
 #undef T
+    if (table == 7) {   // the 32x32 (A, B, R) coefficients of the Zeltner-Burley sheen LTC
+        *count = 32 * 32 * 3;
+        return &bsdl::mtx::ZeltnerBurleySheen::param_ptr()[0][0].x;
+    }
     *count = 0;
     return nullptr;
 }

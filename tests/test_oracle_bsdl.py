@@ -45,14 +45,17 @@ def libs():
 def test_baked_energy_tables_equal_the_reference_genluts_output(libs):
     ref, _, luts = libs
     tabs = []
-    for t in (0, 1, 2, 3):      # MiniMicrofacetGGX, DielectricReflFront, BothFront, BothBack
+    # MiniMicrofacetGGX, DielectricReflFront, BothFront, BothBack (baked by tools/bake_bsdl_luts.cpp)
+    # + the Zeltner-Burley sheen LTC coefficients (published fit, stored by tools/bake_zeltner_ltc.py)
+    for t in (0, 1, 2, 3, 7):
         n = ctypes.c_int()
         p = ref.ref_bsdl_lut(t, ctypes.byref(n))
         tabs.append(np.ctypeslib.as_array(p, (n.value,)).copy())
     want = np.concatenate(tabs).astype(np.float32)
-    assert luts.size == want.size == 256 + 3 * 8192
+    assert luts.size == want.size == 256 + 3 * 8192 + 32 * 32 * 3
     assert np.array_equal(luts.view(np.uint32), want.view(np.uint32))
-    assert 0.0 <= luts.min() and luts.max() <= 1.0
+    energy = luts[:256 + 3 * 8192]
+    assert 0.0 <= energy.min() and energy.max() <= 1.0
 
 
 def _unit(v):
@@ -74,8 +77,8 @@ def _params(rng, lobe):
         p = np.concatenate([N, U, c(), refr, r2, c() * 0.5, c(), [rng.uniform(1, 8)]])
     elif lobe == 3:     # translucent: N albedo
         p = np.concatenate([N, c()])
-    elif lobe == 4:     # sheen (mode 0): N albedo roughness mode
-        p = np.concatenate([N, c(), [rng.uniform(0, 1), 0]])
+    elif lobe == 4:     # sheen: N albedo roughness mode (0 Conty-Kulla, 1 Zeltner-Burley LTC, other -> Conty-Kulla)
+        p = np.concatenate([N, c(), [rng.uniform(0, 1), float(rng.choice([0, 1, 1, 2]))]])
     elif lobe == 5:     # oren-nayar diffuse: N albedo roughness energy_compensation
         p = np.concatenate([N, c(), [rng.uniform(0, 1), float(rng.integers(0, 2))]])
     else:               # burley diffuse: N albedo roughness

@@ -39,6 +39,11 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          "render-mx-conductor": ("mx_conductor.xml", 160, 120, 16),
          "render-mx-dielectric": ("mx_dielectric.xml", 160, 120, 16),
          "render-mx-generalized-schlick": ("mx_generalized_schlick.xml", 160, 120, 16),
+         # sheen_bsdf in both modes - Conty-Kulla microfacet sheen and the Zeltner-Burley LTC sheen
+         # ("mode", 1: 32 x 32 coefficient table) - alone and layered over diffuse in a furnace
+         "render-mx-sheen": ("mx_sheen.xml", 160, 120, 6),
+         "render-mx-furnace-sheen": ("mx_furnace_sheen.xml", 384, 64, 16),
+         "render-mx-burley-diffuse": ("mx_burley_diffuse.xml", 160, 120, 8),
          # refracting dielectric / generalized-Schlick spheres that also declare the (vacuum) medium they
          # enclose: medium_vdf closures, the per-path MediumStack, and - in -medium-vdf-glass - nested
          # and overlapping spheres whose priorities turn boundaries into pass-through (a15)
@@ -55,6 +60,7 @@ MEDIA_CASES = {"render-mx-medium-vdf": ("mx_medium_vdf.xml", 98, 98, 32),
 # a band equals the same rows of the full render); the GPU tests compare whole frames against the
 # oracle and the golden images.
 BANDS = {"render-mx-furnace-oren-nayar": (24, 40), "render-mx-furnace-burley-diffuse": (24, 40),
+         "render-mx-furnace-sheen": (24, 40), "render-mx-sheen": (48, 72), "render-mx-burley-diffuse": (48, 72),
          "render-mx-medium-vdf-glass": (20, 44), "render-mx-generalized-schlick-glass": (36, 60),
          "render-mx-anisotropic-vdf": (40, 56), "render-mx-medium-vdf": (40, 56),
          "render-mx-dielectric-glass": (48, 72), "render-mx-generalized-schlick": (48, 72),
@@ -140,6 +146,7 @@ def test_oracle_matches_reference_golden_render(case):
     # It must be unbiased.
     exact_min = {"render-mx-furnace-oren-nayar": 0.86,          # 0.887 (band through the spheres)
                  "render-mx-furnace-burley-diffuse": 0.87,      # 0.894
+                 "render-mx-furnace-sheen": 0.85,               # 0.877 (whole frame 0.955)
                  "render-mx-conductor": 0.96,                   # 0.979
                  "render-mx-dielectric": 0.955,                 # 0.975
                  "render-mx-generalized-schlick": 0.95,         # 0.968

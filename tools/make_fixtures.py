@@ -77,6 +77,8 @@ SHADERS = {
     "mxcond_glossy": "render-mx-conductor/glossy.osl",
     "mxdiel_glossy": "render-mx-dielectric/glossy.osl",
     "mxgs_glossy": "render-mx-generalized-schlick/glossy.osl",
+    "mxsheen_sheen": "render-mx-sheen/sheen.osl",     # sheen_bsdf in both modes (Conty-Kulla, Zeltner-Burley LTC)
+    "mxfsheen_sheen": "render-mx-furnace-sheen/sheen.osl",   # ... layered over diffuse in a furnace
     # refractive MaterialX lobes and participating media (MediumStack)
     "mxdielglass_glossy": "render-mx-dielectric-glass/glossy.osl",
     "mxgsglass_glossy": "render-mx-generalized-schlick-glass/glossy.osl",
@@ -121,6 +123,9 @@ SCENES = {
     "mx_dielectric.xml": ("render-mx-dielectric/scene.xml", {"glossy": "mxdiel_glossy", "envmap": "mxspec_envmap"}),
     "mx_generalized_schlick.xml": ("render-mx-generalized-schlick/scene.xml",
                                    {"glossy": "mxgs_glossy", "envmap": "mxspec_envmap"}),
+    "mx_sheen.xml": ("render-mx-sheen/scene.xml", {"sheen": "mxsheen_sheen", "envmap": "mxspec_envmap"}),
+    "mx_furnace_sheen.xml": ("render-mx-furnace-sheen/scene.xml", {"sheen": "mxfsheen_sheen", "envmap": "mx_envmap"}),
+    "mx_burley_diffuse.xml": ("render-mx-burley-diffuse/scene.xml", {"matte": "mxburley_matte", "envmap": "mxspec_envmap"}),
     "mx_dielectric_glass.xml": ("render-mx-dielectric-glass/scene.xml",
                                 {"glossy": "mxdielglass_glossy", "envmap": "mxspec_envmap"}),
     "mx_generalized_schlick_glass.xml": ("render-mx-generalized-schlick-glass/scene.xml",
@@ -147,6 +152,9 @@ RENDERS = {
     "render-mx-conductor": "render-mx-conductor/ref/out.exr",
     "render-mx-dielectric": "render-mx-dielectric/ref/out.exr",
     "render-mx-generalized-schlick": "render-mx-generalized-schlick/ref/out.exr",
+    "render-mx-sheen": "render-mx-sheen/ref/out.exr",
+    "render-mx-furnace-sheen": "render-mx-furnace-sheen/ref/out.exr",
+    "render-mx-burley-diffuse": "render-mx-burley-diffuse/ref/out.exr",
     "render-mx-dielectric-glass": "render-mx-dielectric-glass/ref/out.exr",
     "render-mx-generalized-schlick-glass": "render-mx-generalized-schlick-glass/ref/out.exr",
     "render-mx-medium-vdf": "render-mx-medium-vdf/ref/out.exr",
