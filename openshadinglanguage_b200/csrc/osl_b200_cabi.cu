@@ -149,6 +149,7 @@ struct b200_group {
     std::string source;
     std::vector<char> cubin;
     int block = 256;
+    int gridcap = 8;        // option gridcap=N: at most N CTAs per SM in the grid (CTAs loop over the remaining tiles)
     int minblocks = 0;      // option minblocks=N: resident CTAs per SM the register allocator must allow (0: its own choice)
     int stage_outputs = 1;  // option stage=0 forces direct stores
     std::mutex mu;
@@ -276,6 +277,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
         }
         if (opt.count("minblocks"))
             G->minblocks = std::max(0, atoi(opt["minblocks"].c_str()));
+        if (opt.count("gridcap"))
+            G->gridcap = std::max(1, atoi(opt["gridcap"].c_str()));
         if (opt.count("error_repeats"))
             G->error_repeats = atoi(opt["error_repeats"].c_str()) != 0;
         if (opt.count("block"))
@@ -673,7 +676,7 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
     // grid: one CTA per tile of `block` points, capped at 8 CTAs per SM (a
     // multiple of the SM count); CTAs loop over the remaining tiles
     long long want = (npoints + g->block - 1) / g->block;
-    long long cap  = (long long)sms * 8;
+    long long cap  = (long long)sms * g->gridcap;
     unsigned grid  = (unsigned)(want < cap ? want : cap);
     void* args[]   = { &L };
     CUresult_ r    = driver().cuLaunchKernel(fn, grid, 1, 1, (unsigned)g->block, 1, 1, 0, stream, args, nullptr);
