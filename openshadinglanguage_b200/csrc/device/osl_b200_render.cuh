@@ -654,11 +654,10 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                     lobe_set_bsdl_frame(l, wo);
                     break;
                 case MX_SHEEN_ID:
-                    // params: N, albedo, roughness, mode; mode 1 (Zeltner LTC sheen) is not built
+                    // params: N, albedo, roughness, mode (1: Zeltner-Burley LTC sheen, else Conty-Kulla)
                     l.albedo = mkv(q[3], q[4], q[5]);
                     l.type   = LOBE_BSDL_SHEEN;
                     sheen_setup(l, wo, q[6], backfacing, path_roughness, __float_as_int(q[7]), luts);
-                    known = __float_as_int(q[7]) == 0;
                     break;
 #ifdef OSLD_MX_LOBES
                 case MX_CONDUCTOR_ID:

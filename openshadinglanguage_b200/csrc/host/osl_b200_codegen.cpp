@@ -1180,9 +1180,10 @@ Gen::emit_op(const Opcode& op)
         if (ix.is_const()) {
             w("setc(" + R(op.args[0]) + ", 0, " + comp(op.args[1], ix.ivals.empty() ? 0 : ix.ivals[0], A(0).has_derivs) + ");");
         } else {
-            w("switch (" + R(op.args[2]) + ") {");
+            // out of range: osl_range_check_err clamps (>= 3 -> 2, < 0 -> 0; shadingsys.cpp:4981-4984)
+            w("switch (" + R(op.args[2]) + " < 0 ? 0 : " + R(op.args[2]) + ") {");
             for (int c = 0; c < 3; ++c)
-                w(std::string(c == 0 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
+                w(std::string(c == 2 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
                   + ", 0, " + comp(op.args[1], c, A(0).has_derivs) + "); break;");
             w("}");
         }
@@ -1193,16 +1194,16 @@ Gen::emit_op(const Opcode& op)
         if (ix.is_const()) {
             w("setc(" + R(op.args[0]) + ", " + std::to_string(ix.ivals.empty() ? 0 : ix.ivals[0]) + ", " + v + ");");
         } else {
-            w("switch (" + R(op.args[1]) + ") {");
+            w("switch (" + R(op.args[1]) + " < 0 ? 0 : " + R(op.args[1]) + ") {");
             for (int c = 0; c < 3; ++c)
-                w(std::string(c == 0 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
+                w(std::string(c == 2 ? "default: case " : "case ") + std::to_string(c) + ": setc(" + R(op.args[0])
                   + ", " + std::to_string(c) + ", " + v + "); break;");
             w("}");
         }
     } else if (n == "aref") {
         need(3);
         std::string len = std::to_string(A(1).type.arraylen);
-        w("{ int ix_ = " + R(op.args[2]) + "; if (ix_ < 0 || ix_ >= " + len + ") ix_ = 0; ");
+        w("{ int ix_ = " + R(op.args[2]) + "; ix_ = ix_ < 0 ? 0 : (ix_ >= " + len + " ? " + len + " - 1 : ix_); ");
         if (A(0).type.base == Base::String || A(0).type.base == Base::Int)
             w("  " + R(op.args[0]) + " = " + R(op.args[1]) + "[ix_]; }");
         else
@@ -1210,7 +1211,7 @@ Gen::emit_op(const Opcode& op)
     } else if (n == "aassign") {
         need(3);
         std::string len = std::to_string(A(0).type.arraylen);
-        w("{ int ix_ = " + R(op.args[1]) + "; if (ix_ < 0 || ix_ >= " + len + ") ix_ = 0; ");
+        w("{ int ix_ = " + R(op.args[1]) + "; ix_ = ix_ < 0 ? 0 : (ix_ >= " + len + " ? " + len + " - 1 : ix_); ");
         if (A(0).type.base == Base::String || A(0).type.base == Base::Int)
             w("  " + R(op.args[0]) + "[ix_] = " + R(op.args[2]) + "; }");
         else
@@ -1277,7 +1278,9 @@ Gen::emit_op(const Opcode& op)
           + ") != 0;");
     } else if (n == "isconnected") {
         need(2);
-        w(R(op.args[0]) + " = " + std::to_string(A(1).conn_layer >= 0 ? 1 : (A(1).connected_down ? 2 : 0)) + ";");
+        // (up ? 1 : 0) + ((down || renderer output) ? 2 : 0)  (runtimeoptimize.cpp:2495-2499)
+        w(R(op.args[0]) + " = "
+          + std::to_string((A(1).conn_layer >= 0 ? 1 : 0) + ((A(1).connected_down || A(1).out.placed) ? 2 : 0)) + ";");
     } else if (n == "isconstant") {
         need(2);
         w(R(op.args[0]) + " = " + std::to_string(A(1).const_value() ? 1 : 0) + ";");

@@ -466,6 +466,7 @@ Group::finalize()
     }
     long long stage_bytes = 0;
     stage_ok              = !clusters.empty();
+    stage_record_bytes    = 0;
     for (OutCluster& c : clusters) {
         // dense: the fields cover [lo, lo+stride) with no gap and no overlap
         std::vector<std::pair<long long, long long>> spans;
@@ -483,6 +484,7 @@ Group::finalize()
         c.dense = ok && at == c.lo + c.stride;
         stage_ok &= c.dense;
         stage_bytes += c.stride * block;
+        stage_record_bytes = std::max(stage_record_bytes, c.stride);
     }
     if (2 * stage_bytes > 48 * 1024)  // double-buffered staging must fit static shared memory
         stage_ok = false;

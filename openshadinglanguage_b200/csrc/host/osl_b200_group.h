@@ -143,6 +143,7 @@ struct Group {
     std::vector<UserData> userdata;            // what the renderer supplies for interpolated params
     std::vector<OutCluster> clusters;
     bool stage_ok = false;  // every cluster dense and small enough to stage
+    long long stage_record_bytes = 0;  // largest output record (cluster stride)
     int block     = 256;    // CTA size the kernel is generated for
     std::vector<Layer> layers;
     std::vector<Connection> connections;

@@ -63,6 +63,7 @@ struct Driver {
     CUresult_ (*cuLaunchKernel)(CUfunction_, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                                 unsigned, void*, void**, void**)                           = nullptr;
     CUresult_ (*cuGetErrorString)(CUresult_, const char**)                                 = nullptr;
+    CUresult_ (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction_, int, size_t) = nullptr;
     bool ok = false;
     std::string why;
 };
@@ -91,6 +92,7 @@ driver()
         LOADSYM(cuModuleGetFunction)
         LOADSYM(cuLaunchKernel)
         LOADSYM(cuGetErrorString)
+        LOADSYM(cuOccupancyMaxActiveBlocksPerMultiprocessor)
 #undef LOADSYM
         if (d.cuInit(0) != 0) {
             d.why = "cuInit failed";
@@ -149,12 +151,14 @@ struct b200_group {
     std::string source;
     std::vector<char> cubin;
     int block = 256;
-    int gridcap = 8;        // option gridcap=N: at most N CTAs per SM in the grid (CTAs loop over the remaining tiles)
+    int gridcap = 0;        // option gridcap=N: at most N CTAs per SM in the grid (0: waves x the measured residency)
+    int waves = 12;         // option waves=N: grid = at most N full waves of resident CTAs; CTAs loop over the remaining tiles
     int minblocks = 0;      // option minblocks=N: resident CTAs per SM the register allocator must allow (0: its own choice)
-    int stage_outputs = 1;  // option stage=0 forces direct stores
+    int stage_outputs = -1; // option stage=0|1: direct stores / shared-memory staging + TMA bulk stores (-1: by record size)
     std::mutex mu;
     std::map<int, std::pair<CUmodule_, CUfunction_>> loaded;  // per device
     int sm_count[64] = { 0 };
+    int resident[64] = { 0 };  // CTAs of the kernel one SM holds (cuOccupancyMaxActiveBlocksPerMultiprocessor)
     std::vector<void*> texture_allocs;  // device images of the textures the group reads (all devices)
     // printf journal (only for groups that have printf sites): one device buffer per device
     unsigned journal_words = 4u << 20;   // option journal=WORDS
@@ -279,6 +283,8 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             G->minblocks = std::max(0, atoi(opt["minblocks"].c_str()));
         if (opt.count("gridcap"))
             G->gridcap = std::max(1, atoi(opt["gridcap"].c_str()));
+        if (opt.count("waves"))
+            G->waves = std::max(1, atoi(opt["waves"].c_str()));
         if (opt.count("error_repeats"))
             G->error_repeats = atoi(opt["error_repeats"].c_str()) != 0;
         if (opt.count("block"))
@@ -585,16 +591,25 @@ ensure_loaded(b200_group* g, int device, CUfunction_* fn)
         return fail(B200_ERR_CUDA, "cuModuleLoadData: " + cu_err(r));
     CUfunction_ f;
     r = d.cuModuleGetFunction(&f, mod, "osl_b200_group_kernel");
-    if (r != 0)
+    if (r != 0) {
+        d.cuModuleUnload(mod);
         return fail(B200_ERR_CUDA, "cuModuleGetFunction: " + cu_err(r));
+    }
     std::string terr = bind_module_textures(mod, g->g.textures, g->g.texturepath, g->texture_allocs);
-    if (!terr.empty())
+    if (!terr.empty()) {
+        d.cuModuleUnload(mod);
         return fail(B200_ERR_INVALID, terr);
+    }
     g->loaded[device] = { mod, f };
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (device < 64)
+    if (device < 64) {
         g->sm_count[device] = sms;
+        int nb = 0;
+        if (d.cuOccupancyMaxActiveBlocksPerMultiprocessor
+            && d.cuOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, g->block, 0) == 0 && nb > 0)
+            g->resident[device] = nb;
+    }
     *fn = f;
     return B200_OK;
 }
@@ -638,7 +653,9 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
     L.shadeindex_base = sidx_base;
     for (int k = 0; k < B200_MAX_OUTPUTS; ++k)
         L.out_adjust[k] = out_adjust ? out_adjust[k] : 0;
-    L.stage_outputs = g->stage_outputs;
+    // staging pays for records of two or more 16-byte rows (48 B layers record: 4x); a 12 B colour
+    // record is already written in three nearly-full lines per warp and the staging only adds latency
+    L.stage_outputs = g->stage_outputs >= 0 ? g->stage_outputs : (g->g.stage_record_bytes >= 32 ? 1 : 0);
     L.pad_          = 0;
     // named coordinate systems: resolve the names the generated code references and invert
     // once per launch (the reference inverts per call: rs_get_inverse_matrix_*)
@@ -673,10 +690,13 @@ launch_group(b200_group* g, int device, void* stream, long long npoints, const b
         L.journal_words = g->journal_words;
     }
     int sms = (device >= 0 && device < 64 && g->sm_count[device]) ? g->sm_count[device] : 148;
-    // grid: one CTA per tile of `block` points, capped at 8 CTAs per SM (a
-    // multiple of the SM count); CTAs loop over the remaining tiles
+    // grid: one CTA per tile of `block` points, capped at `waves` full waves of resident CTAs
+    // (SMs x the kernel's measured residency: a cap that is not a multiple of the residency
+    // leaves the last wave partly empty - 8 CTAs/SM against 5 resident cost 20 %); CTAs loop
+    // over the remaining tiles.  Sweep: profiles/group_tune_r02.txt
     long long want = (npoints + g->block - 1) / g->block;
-    long long cap  = (long long)sms * g->gridcap;
+    const int res_ = (device >= 0 && device < 64 && g->resident[device]) ? g->resident[device] : 4;
+    long long cap  = g->gridcap > 0 ? (long long)sms * g->gridcap : (long long)sms * res_ * g->waves;
     unsigned grid  = (unsigned)(want < cap ? want : cap);
     void* args[]   = { &L };
     CUresult_ r    = driver().cuLaunchKernel(fn, grid, 1, 1, (unsigned)g->block, 1, 1, 0, stream, args, nullptr);

@@ -872,10 +872,11 @@ class Gen:
         if i.isconst:
             self.w("setc(%s, 0, %s);" % (self.R(d), self.comp(s, int(i.vals[0]), d.has_derivs)))
         else:
-            self.w("switch (%s) {" % self.R(i))
+            # out of range: osl_range_check_err clamps (>= 3 -> 2, < 0 -> 0)
+            self.w("switch (%s < 0 ? 0 : %s) {" % (self.R(i), self.R(i)))
             for c in range(3):
                 self.w("%s %d: setc(%s, 0, %s); break;" % (
-                    "default: case" if c == 0 else "case", c, self.R(d),
+                    "default: case" if c == 2 else "case", c, self.R(d),
                     self.comp(s, c, d.has_derivs)))
             self.w("}")
 
@@ -885,21 +886,22 @@ class Gen:
         if i.isconst:
             self.w("setc(%s, %d, %s);" % (self.R(d), int(i.vals[0]), v))
         else:
-            self.w("switch (%s) {" % self.R(i))
+            self.w("switch (%s < 0 ? 0 : %s) {" % (self.R(i), self.R(i)))
             for c in range(3):
                 self.w("%s %d: setc(%s, %d, %s); break;" % (
-                    "default: case" if c == 0 else "case", c, self.R(d), c, v))
+                    "default: case" if c == 2 else "case", c, self.R(d), c, v))
             self.w("}")
 
     def op_aref(self, op):
         d, s, i = op.args
-        self.w("{ int ix_ = %s; if (ix_ < 0 || ix_ >= %d) ix_ = 0; assign(%s, %s[ix_]); }" % (
-            self.R(i), s.t.arr, self.R(d), self.R(s)))
+        # osl_range_check_err (shadingsys.cpp:4981-4984): >= length -> length - 1, negative -> 0
+        self.w("{ int ix_ = %s; ix_ = ix_ < 0 ? 0 : (ix_ >= %d ? %d - 1 : ix_); assign(%s, %s[ix_]); }" % (
+            self.R(i), s.t.arr, s.t.arr, self.R(d), self.R(s)))
 
     def op_aassign(self, op):
         d, i, s = op.args
-        self.w("{ int ix_ = %s; if (ix_ < 0 || ix_ >= %d) ix_ = 0; assign(%s[ix_], %s); }" % (
-            self.R(i), d.t.arr, self.R(d), self.R(s)))
+        self.w("{ int ix_ = %s; ix_ = ix_ < 0 ? 0 : (ix_ >= %d ? %d - 1 : ix_); assign(%s[ix_], %s); }" % (
+            self.R(i), d.t.arr, d.t.arr, self.R(d), self.R(s)))
 
     def op_arraylength(self, op):
         self.w("%s = %d;" % (self.R(op.args[0]), op.args[1].t.arr))
@@ -970,7 +972,8 @@ class Gen:
 
     def op_isconnected(self, op):
         d, s = op.args
-        v = 1 if s.connected_from is not None else (2 if s.connected_down else 0)
+        # (up ? 1 : 0) + ((down || renderer output) ? 2 : 0)  (runtimeoptimize.cpp:2495-2499)
+        v = (1 if s.connected_from is not None else 0) + (2 if (s.connected_down or s.renderer_output) else 0)
         self.w("%s = %d;" % (self.R(d), v))
 
     def op_isconstant(self, op):
