@@ -404,6 +404,11 @@ def main():
                 dev_ms.append(max_over_ranks(st["device_ms"]))
                 gather_ms.append(max_over_ranks(gm))
             paths = res * res * aa * aa
+            mine = [round(st["device_ms"], 2), round(st["tail_ms"], 2), int(st["bounce_iterations"])]
+            per_rank = [mine]
+            if world > 1:
+                per_rank = [None] * world
+                dist.all_gather_object(per_rank, mine)
             k = sorted(range(reps), key=lambda i: dev_ms[i])[0]
             med = sorted(dev_ms)[reps // 2]
             extra[rname] = {
@@ -414,6 +419,7 @@ def main():
                 "e2e_includes": "render + NCCL gather of the strips + scatter into the image + D2H to pinned host memory",
                 "partition": "interleaved 64x64 tiles, tile k -> GPU k %% %d (strong scaling)" % world,
                 "bounce_steps": st["bounce_iterations"], "launches": st["launches"], "tail_ms": st["tail_ms"],
+                "per_rank_last_repeat": {"device_ms,tail_ms,bounce_steps": per_rank},
                 "pool_slots": st["slots"], "image_mean": float(himg.mean()) if rank == 0 else None,
                 "ncu": static_profile(rname.split("-")[0] + "-" + rname.split("-")[1])}
             if rank == 0 and not args.no_cpu_baseline:

@@ -1,0 +1,244 @@
+#!/usr/bin/env python3
+"""Replay the reference's BATCHED testsuite through this repo (the `.b200` variant of
+src/cmake/testing.cmake:214-235, which registers every testsuite directory that holds a BATCHED
+marker a second time for the batched back end).
+
+For every such directory under /root/reference/testsuite:
+  1. run.py is executed with stub command builders to obtain its command lines;
+  2. every .osl in the directory is compiled with tools/mini_oslc.py (no oslc exists here);
+  3. each `testshade ...` command is parsed (openshadinglanguage_b200.testshade.parse_command) and
+     the group is built through the PRODUCT's generator + NVRTC (no GPU needed for that);
+  4. the command is replayed on the CPU oracle and its text compared with ref/out.txt, its images
+     with the ref images (8-bit / float TIFFs that PIL reads) at the reference's idiff thresholds.
+
+Results go to tests/golden/testsuite_b200/: manifest.json (status of all directories) and one
+bundle per directory that passed (commands, .oso texts, expected text, reference images), which
+tests/test_testsuite_b200.py replays through the GPU.  Needs /root/reference: run in the build
+container, not on the GPU box.
+"""
+import json
+import os
+import re
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference"
+TS = os.path.join(REF, "testsuite")
+OUT = os.path.join(ROOT, "tests", "golden", "testsuite_b200")
+
+
+def commands_of(d):
+    """run.py with stubbed command builders -> [(tool, argument string)], test settings"""
+    cmds = []
+
+    def stub(name):
+        def f(*a, **k):
+            cmds.append((name, a[0] if a else ""))
+            return ""
+        return f
+    ns = {k: stub(k) for k in ("testshade", "oslc", "testrender", "oiiotool", "oslinfo", "maketx", "idiff",
+                               "testoptix", "diff_command", "oiio_app")}
+    ns.update(dict(command="", outputs=["out.txt"], failthresh=0.004, failpercent=0.02, hardfail=0.012,
+                   allowfailures=0, os=os, OIIO_TESTSUITE_IMAGEDIR="", splitsymbol=";", platform=None))
+    cwd = os.getcwd()
+    os.chdir(os.path.join(TS, d))
+    try:
+        exec(open("run.py").read(), ns)
+    finally:
+        os.chdir(cwd)
+    return cmds, {k: ns[k] for k in ("outputs", "failthresh", "failpercent", "hardfail", "allowfailures")}
+
+
+def read_image(path):
+    if path.endswith(".exr"):
+        os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+        import cv2
+        img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if img is None:
+            raise IOError("cannot read " + path)
+        if img.ndim == 3:
+            img = img[..., ::-1] if img.shape[2] == 3 else img[..., [2, 1, 0, 3]]
+        else:
+            img = img[..., None]
+        return np.ascontiguousarray(img).astype(np.float32), "float"
+    from PIL import Image
+    img = np.array(Image.open(path))
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.dtype == np.uint8:
+        return img.astype(np.float32) / 255.0, "uint8"
+    if img.dtype == np.uint16:
+        return img.astype(np.float32) / 65535.0, "uint16"
+    return img.astype(np.float32), "float"
+
+
+def compare_image(got, ref, kind, st):
+    from openshadinglanguage_b200 import testshade as tsh
+    return tsh.compare_image(got, ref, kind, st["failthresh"], st["failpercent"], st["hardfail"])
+
+
+def main():
+    from tools import mini_oslc
+    from oracle import oracle
+    import helpers
+    import openshadinglanguage_b200 as ob
+    from openshadinglanguage_b200 import testshade as tsh
+    os.makedirs(OUT, exist_ok=True)
+    inc = [os.path.join(REF, "src/shaders")]
+    only = set(sys.argv[1:])
+    dirs = [d for d in sorted(os.listdir(TS)) if os.path.exists(os.path.join(TS, d, "BATCHED"))]
+    manifest = {}
+    for d in dirs:
+        if only and d not in only:
+            continue
+        entry = dict(status="?", reason="")
+        manifest[d] = entry
+        try:
+            cmds, st = commands_of(d)
+        except Exception as e:
+            entry.update(status="harness", reason="run.py: %s" % e)
+            continue
+        tools_used = sorted({t for t, _ in cmds})
+        shade = [a for t, a in cmds if t == "testshade"]
+        if not shade or set(tools_used) - {"testshade", "oslc"}:
+            entry.update(status="harness", reason="uses " + ",".join(tools_used))
+            continue
+        entry["commands"] = shade
+        # 2. compile the directory's shaders
+        oso = {}
+        failed = None
+        for f in sorted(os.listdir(os.path.join(TS, d))):
+            if f.endswith(".osl"):
+                try:
+                    oso[f[:-4]] = mini_oslc.compile_osl(os.path.join(TS, d, f), inc + [os.path.join(TS, d)])
+                except Exception as e:
+                    failed = failed or "%s: %s" % (f, str(e).split("\n")[0][:200])
+        specs = []
+        try:
+            specs = [tsh.parse_command(a) for a in shade]
+        except Exception as e:
+            entry.update(status="harness", reason="command line: %s" % e)
+            continue
+        unsup = sorted({u for s in specs for u in s["unsupported"]})
+        if unsup:
+            entry.update(status="harness", reason="testshade flags not replayed: " + " ".join(unsup))
+            continue
+        need = {l["shader"] for s in specs for l in s["layers"]}
+        # shaders shared between tests live in testsuite/common/shaders (runtest.py compiles them too)
+        common = os.path.join(TS, "common", "shaders")
+        for name in sorted(need - set(oso)):
+            src = os.path.join(common, name + ".osl")
+            if os.path.exists(src):
+                try:
+                    oso[name] = mini_oslc.compile_osl(src, inc + [common])
+                except Exception as e:
+                    failed = failed or "%s: %s" % (name, str(e).split("\n")[0][:200])
+        if failed and (need - set(oso)):
+            entry.update(status="oslc", reason=failed)
+            continue
+        missing = need - set(oso)
+        if missing:
+            entry.update(status="harness", reason="shader(s) not in the directory: " + ",".join(sorted(missing)))
+            continue
+        # 3. product generator + NVRTC
+        def product_group(layers, conns, outs, spec):
+            arena, descs = ob.pack_userdata(helpers.testshade_userdata(
+                spec["xres"] * spec["yres"], *ob.grid_globals(spec["xres"], spec["yres"]), extra=spec["userdata"]))
+            return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1", userdata=descs)
+        try:
+            for s in specs:
+                layers = [dict(oso=oso[l["shader"]], name=l["name"], params=l["params"]) for l in s["layers"]]
+                g = product_group(layers, s["connections"], (), s)
+                assert g.cubin[:4] == b"\x7fELF"
+        except Exception as e:
+            entry.update(status="codegen", reason=str(e).split("\n")[0][:300])
+            continue
+        # 4. oracle replay vs the reference's golden output
+        def oracle_globals(xres, yres, raytype_bit=1, **kw):
+            return oracle.testshade_globals(xres, yres, raytype=raytype_bit, **kw)
+
+        class OracleRunner:
+            def __init__(self, layers, conns, outs, spec):
+                self.g = oracle.OracleGroup(layers, conns, outs)
+                self.spec = spec
+
+            def run(self, n, var, uni, arena):
+                uni = dict(uni)
+                uni["userdata"] = helpers.testshade_userdata(n, var, uni, extra=self.spec["userdata"])
+                return self.g.run_capture(n, var, uni, arena)
+        try:
+            texts, images = [], {}
+            for s in specs:
+                r = tsh.run_command(s, lambda name: oso[name], OracleRunner, oracle_globals)
+                if r["text"]:
+                    texts.append(r["text"])
+                for var, (fn, img) in r["images"].items():
+                    if fn != "null":
+                        images[fn] = img
+            got = "\n".join(texts)
+        except Exception as e:
+            entry.update(status="oracle", reason=(str(e).split("\n")[0] or traceback.format_exc().split("\n")[-2])[:300])
+            continue
+        want_path = os.path.join(TS, d, "ref", "out.txt")
+        want = ""
+        if os.path.exists(want_path):
+            # not the shader's output: oslc's "Compiled ..." lines and a debug print of the reference's
+            # batched code generator ("x is forced llvm bool.")
+            want = "\n".join(l for l in open(want_path).read().split("\n")
+                             if not l.startswith("Compiled") and not l.endswith("is forced llvm bool."))
+        problems = []
+        if "out.txt" in st["outputs"] and os.path.exists(want_path) and got.rstrip("\n") != want.rstrip("\n"):
+            gl, wl = got.rstrip("\n").split("\n"), want.rstrip("\n").split("\n")
+            k = next((i for i in range(min(len(gl), len(wl))) if gl[i] != wl[i]), min(len(gl), len(wl)))
+            problems.append("text differs at line %d: got %r want %r" % (
+                k + 1, gl[k][:80] if k < len(gl) else "<end>", wl[k][:80] if k < len(wl) else "<end>"))
+        ref_images = {}
+        for fn in st["outputs"]:
+            if fn == "out.txt" or fn == "null":
+                continue
+            rp = os.path.join(TS, d, "ref", fn)
+            if not os.path.exists(rp):
+                continue
+            if fn not in images:
+                problems.append("output image %s not produced" % fn)
+                continue
+            try:
+                ref, kind = read_image(rp)
+            except Exception as e:
+                problems.append("reference image %s unreadable here (%s)" % (fn, type(e).__name__))
+                continue
+            p = compare_image(images[fn], ref, kind, st)
+            if p:
+                problems.append("%s: %s" % (fn, p))
+            ref_images[fn] = (ref, kind)
+        if problems:
+            entry.update(status="mismatch", reason="; ".join(problems)[:400])
+            continue
+        entry.update(status="pass", reason="")
+        bundle = dict(commands=shade, oso=oso, want=want, settings=st,
+                      images={fn: dict(kind=kind, shape=list(ref.shape)) for fn, (ref, kind) in ref_images.items()})
+        with open(os.path.join(OUT, d + ".json"), "w") as f:
+            json.dump(bundle, f)
+        if ref_images:
+            np.savez_compressed(os.path.join(OUT, d + ".npz"),
+                                **{re.sub(r"\W", "_", fn): (ref * (255 if kind == "uint8" else 1)).astype(
+                                    np.uint8 if kind == "uint8" else np.float32) for fn, (ref, kind) in ref_images.items()})
+        print("%-32s %s %s" % (d, entry["status"], entry["reason"]), flush=True)
+    for d, e in manifest.items():
+        if e["status"] != "pass":
+            print("%-32s %s %s" % (d, e["status"], e["reason"]), flush=True)
+    if not only:
+        with open(os.path.join(OUT, "manifest.json"), "w") as f:
+            json.dump({d: dict(status=e["status"], reason=e["reason"]) for d, e in manifest.items()}, f, indent=1)
+    import collections
+    c = collections.Counter(e["status"] for e in manifest.values())
+    print("BATCHED testsuite directories: %d; %s" % (len(manifest), dict(c)))
+
+
+if __name__ == "__main__":
+    main()
