@@ -197,6 +197,21 @@ private:
         if (name == "common" || name == g.commonspace_synonym)
             return { "m44_diag(1.0f)", "1" };
         std::string k = std::to_string(space_slot(name));
+        if (journal_ok) {
+            // unknown_coordsys_error = 1 (the default): a look-up of a name the renderer does not
+            // know reports "Unknown transformation" through the error handler, at the op
+            // (opmatrix.cpp:129-134, 160-165, 188-196)
+            JournalFormat jf;
+            jf.fmt        = "Unknown transformation \"" + name + "\"";
+            for (size_t q = 0; q < jf.fmt.size(); ++q)
+                if (jf.fmt[q] == '%')
+                    jf.fmt.insert(q++, "%");
+            jf.kind       = 3;  // an error of the shading system itself: no "Shader error [name]" prefix
+            jf.shadername = L->m.shadername;
+            int id        = (int)g.jformats.size();
+            g.jformats.push_back(jf);
+            w("if (!L.xf_ok[" + k + "]) { (void)jr_reserve(L, sg, " + std::to_string(id) + "u, 0u); }");
+        }
         return { "m44_load(L.xf[" + k + "][" + (inverse ? "1" : "0") + "])", "L.xf_ok[" + k + "]" };
     }
     bool space_is(int si, const char* what)

@@ -126,7 +126,7 @@ struct JournalArg {
 struct JournalFormat {
     std::string fmt;
     std::vector<JournalArg> args;
-    int kind = 0;            // 0 printf, 1 error(), 2 warning()
+    int kind = 0;            // 0 printf, 1 error(), 2 warning(), 3 error of the shading system itself
     std::string shadername;  // for the "Shader error [name]: " prefix
 };
 

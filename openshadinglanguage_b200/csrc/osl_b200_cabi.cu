@@ -523,8 +523,9 @@ b200_group_journal(b200_group* g, int device)
         }
         // error() / warning(): what the reference's error handler prints for testshade, a
         // message reported before is dropped (attribute error_repeats = 0; option error_repeats=1)
-        std::string msg = jf.kind == 1 ? "ERROR: Shader error [" : "WARNING: Shader warning [";
-        msg += jf.shadername + "]: ";
+        std::string msg = jf.kind == 3 ? "ERROR: " : (jf.kind == 1 ? "ERROR: Shader error [" : "WARNING: Shader warning [");
+        if (jf.kind != 3)
+            msg += jf.shadername + "]: ";
         journal_format(g->g, jf, rec.data() + r.at + 4, rec[r.at] - 4, msg);
         msg += "\n";
         if (!g->error_repeats) {

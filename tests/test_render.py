@@ -75,6 +75,15 @@ TEXTURED_CASES = {"render-microfacet": ("render_microfacet.xml", 160, 120, 8)}
 # from shading.cpp and the device must equal the oracle.
 OWN_CASES = {"microfacet": ("microfacet.xml", 160, 120, 4)}   # ggx/beckmann x reflect/refract/both
 _cache = {}
+_oracle_frames = {}
+
+
+def _oracle_frame(case, xres, yres, aa):
+    """whole-frame oracle render, computed once per case and shared by the parametrised GPU tests"""
+    if case not in _oracle_frames:
+        S, A = _scene(case)
+        _oracle_frames[case] = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=os.cpu_count() or 8)
+    return _oracle_frames[case]
 
 
 def _scene(case):
@@ -196,7 +205,7 @@ def test_gpu_render_bit_exact_vs_oracle(b200lib, cuda_device, case, sort):
     from openshadinglanguage_b200 import api
     S, A = _scene(case)
     xml, xres, yres, aa = CASES.get(case) or TEXTURED_CASES[case]
-    want = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
+    want = _oracle_frame(case, xres, yres, aa)
     # sort=0 also keeps every bounce on the staged kernels (tail=0); sort=1 finishes the last
     # <= 2048 paths in rt_tail (the default) - both must give the oracle's pixels
     R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options="fma=0,sort=%d%s" % (sort, "" if sort else ",tail=0"))
@@ -222,7 +231,7 @@ def test_gpu_render_media_vs_oracle(b200lib, cuda_device, case):
     from openshadinglanguage_b200 import api
     S, A = _scene(case)
     xml, xres, yres, aa = MEDIA_CASES[case]
-    want = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
+    want = _oracle_frame(case, xres, yres, aa)
     for opts in ("fma=0", "fma=0,sort=0,tail=0"):
         R = api.Renderer(S, A, helpers.oso, xres, yres, aa, options=opts)
         got = R.render()
