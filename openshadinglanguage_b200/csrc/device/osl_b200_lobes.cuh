@@ -271,12 +271,8 @@ OSLD void lobe_set_bsdl_frame(Lobe& l, V3 wo)
 // mtx::ConductorLobe / DielectricLobe / SchlickLobe from their closure components (parameter
 // order = the libbsdl Data structs' registration order; the distribution string takes one word).
 // Frame(Z = visible normal, X = U) (tools.h:483-495).
-OSLD void mx_from_component(const float* luts, Lobe& l, int id, PoolPtr p, V3 wo, bool backfacing, float path_roughness)
+OSLD void mx_set_frame_zx(Lobe& l, V3 Z, V3 X)
 {
-    l.type = LOBE_MX_SPEC;
-    l.N    = mkv(p[0], p[1], p[2]);
-    const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
-    const V3 X = mkv(p[3], p[4], p[5]);
     if (bsdl_max_abs_xyz(X) < 1e-4f || fabsf(dot3(Z, vnormalized(X))) > 0.999f) {
         TangentFrame f = frame_from_normal(Z);
         l.fu           = f.u;
@@ -285,7 +281,14 @@ OSLD void mx_from_component(const float* luts, Lobe& l, int id, PoolPtr p, V3 wo
         l.fv = vnormalized(cross3(Z, X));
         l.fu = cross3(l.fv, Z);
     }
-    l.N               = Z;
+    l.N = Z;
+}
+OSLD void mx_from_component(const float* luts, Lobe& l, int id, PoolPtr p, V3 wo, bool backfacing, float path_roughness)
+{
+    l.type = LOBE_MX_SPEC;
+    l.N    = mkv(p[0], p[1], p[2]);
+    const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
+    mx_set_frame_zx(l, Z, mkv(p[3], p[4], p[5]));
     const float cosNO = dot3(Z, wo);
     if (id == MX_CONDUCTOR_ID)
         l.mx = mx_conductor_setup(luts, cosNO, p[6], p[7], mkv(p[8], p[9], p[10]), mkv(p[11], p[12], p[13]),

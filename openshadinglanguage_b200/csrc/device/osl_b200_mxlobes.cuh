@@ -38,7 +38,9 @@ OSLD float mx_max_abs(V3 v) { return fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v
 // ---- energy tables ---------------------------------------------------------------------------
 // layout of the table block: [MiniMicrofacetGGX 1x16x16][ReflFront 32x16x16][BothFront][BothBack]
 enum { LUT_GGX = 0, LUT_REFL_FRONT = 256, LUT_BOTH_FRONT = 256 + 8192, LUT_BOTH_BACK = 256 + 2 * 8192,
-       LUT_WORDS = 256 + 3 * 8192 };
+       LUT_WORDS = 256 + 3 * 8192,
+       // then the Zeltner-Burley LTC coefficients (32x32x3) and spi::Thinlayer 32x16x16 (thinlayer closure)
+       LUT_THINLAYER = LUT_WORDS + 32 * 32 * 3 };
 struct EnergyCurve {   // TabulatedEnergyCurve<BSDF> (microfacet_tools_impl.h:110-207)
     const float* storedE;
     int Nf;            // Nr = Nc = 16 for every table used here
@@ -187,6 +189,17 @@ OSLD float v3max(const V3& v) { return fmaxf(v.x, fmaxf(v.y, v.z)); }
 OSLD V3 v3clamped(const V3& v, float a, float b) { return mkv(mx_clamp(v.x, a, b), mx_clamp(v.y, a, b), mx_clamp(v.z, a, b)); }
 OSLD V3 v3sqrt(const V3& v) { return mkv(sqrtf(v.x), sqrtf(v.y), sqrtf(v.z)); }
 OSLD V3 v3div(const V3& a, const V3& b) { return mkv(a.x / b.x, a.y / b.y, a.z / b.z); }
+
+#ifdef OSLD_THINLAYER
+// what spi::ThinLayerLobe boils down to (functions in osl_b200_thinlayer.cuh)
+struct ThinSpec {
+    GGXD d;
+    V3 sigma_t;
+    float eta, thickness, roughness, prob_clamp;
+    V3 refl_tint, refr_tint;
+    float Eo;   // energy the microfacet lobes lose, handed to the diffuse / translucent pair
+};
+#endif
 
 // ---- Fresnel terms ----------------------------------------------------------------------------
 enum { MXF_CONDUCTOR, MXF_DIELECTRIC, MXF_SCHLICK };

@@ -338,7 +338,8 @@ OSLD BSample bs_make(V3 wi, V3 w, float pdf, float r)
 #define OSLD_INF __int_as_float(0x7f800000)
 enum { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION, LOBE_TRANSPARENT,
        LOBE_PHONG, LOBE_WARD, LOBE_MICROFACET, LOBE_BSDL_OREN_NAYAR, LOBE_BSDL_BURLEY, LOBE_BSDL_SHEEN,
-       LOBE_MX_SPEC /* conductor / dielectric / generalized schlick */, LOBE_MX_TRANSLUCENT };
+       LOBE_MX_SPEC /* conductor / dielectric / generalized schlick */, LOBE_MX_TRANSLUCENT,
+       LOBE_SPI_THINLAYER /* spi::ThinLayerLobe */ };
 }  // namespace osld
 #ifdef OSLD_MX_LOBES
 #include "osl_b200_mxlobes.cuh"
@@ -363,10 +364,16 @@ struct Lobe {
 #ifdef OSLD_MX_LOBES
     MxSpec mx;   // LOBE_MX_SPEC: frame in (fu, fv, N)
 #endif
+#ifdef OSLD_THINLAYER
+    ThinSpec thin;   // LOBE_SPI_THINLAYER: frame in (fu, fv, N)
+#endif
 };
 }  // namespace osld
 #ifdef OSLD_GLOSSY_LOBES
 #include "osl_b200_lobes.cuh"
+#endif
+#ifdef OSLD_THINLAYER
+#include "osl_b200_thinlayer.cuh"
 #endif
 namespace osld {
 OSLD V3 lobe_albedo(const Lobe& l, V3 wo)
@@ -417,6 +424,13 @@ OSLD BSample lobe_eval(const Lobe& l, V3 wo, V3 wi)
         s.wi      = wi;
         return s;
     }
+#ifdef OSLD_THINLAYER
+    if (l.type == LOBE_SPI_THINLAYER) {   // SpiThinLayer::eval (shading.cpp:138-143)
+        BSample s = thin_eval_local(l.thin, frame_tolocal(l, wo), frame_tolocal(l, wi));
+        s.wi      = wi;
+        return s;
+    }
+#endif
     if (l.type == LOBE_MX_TRANSLUCENT) {   // mtx::TranslucentLobe (bsdf_translucent_impl.h)
         const float z = dot3(wi, l.N);
         if (z >= 0.0f)
@@ -463,6 +477,13 @@ OSLD BSample lobe_sample(const Lobe& l, V3 wo, float rx, float ry, float rz)
         s.wi      = frame_toworld(l, s.wi);
         return s;
     }
+#ifdef OSLD_THINLAYER
+    case LOBE_SPI_THINLAYER: {   // SpiThinLayer::sample (shading.cpp:144-151)
+        BSample s = thin_sample_local(l.thin, frame_tolocal(l, wo), mkv(rx, ry, rz));
+        s.wi      = frame_toworld(l, s.wi);
+        return s;
+    }
+#endif
     case LOBE_MX_TRANSLUCENT: {
         V3 wi_l = bsdl_sample_cos_hemisphere(rx, ry);
         wi_l.z  = -wi_l.z;
@@ -681,6 +702,18 @@ OSLD void process_closure(const ClosurePool& pool, int closure, V3& Le, Composit
                     l.type = LOBE_DIFFUSE;
                     cw     = cw * mkv(q[3], q[4], q[5]);
                     break;
+#ifdef OSLD_THINLAYER
+                case SPI_THINLAYER: {
+                    // params: N, T, IOR, roughness, anisotropy, thickness, refl_tint, refr_tint, sigma_t
+                    // (ThinLayerLobe::Data registration order; shading.cpp:1668-1674)
+                    l.type     = LOBE_SPI_THINLAYER;
+                    const V3 Z = bsdl_visible_normal(wo, l.N, l.N);
+                    mx_set_frame_zx(l, Z, mkv(q[3], q[4], q[5]));
+                    l.thin = thin_setup(luts, dot3(wo, Z), q[6], q[7], q[8], q[9], mkv(q[10], q[11], q[12]),
+                                        mkv(q[13], q[14], q[15]), mkv(q[16], q[17], q[18]), path_roughness);
+                    break;
+                }
+#endif
 #endif
                 case MX_LAYER_ID: {
                     // layer(top, base): the base is attenuated by what the top stack takes

@@ -1396,6 +1396,8 @@ Gen::emit_op(const Opcode& op)
             { "generalized_schlick_bsdf", 10, "MX_GENERALIZED_SCHLICK_ID", nullptr },
             { "translucent_bsdf", 2, "MX_TRANSLUCENT_ID", nullptr },
             { "subsurface_bssrdf", 4, "MX_SUBSURFACE_ID", nullptr },
+            // spi::ThinLayerLobe (SpiThinLayer, shading.cpp:119-152; Data: SPI/bsdf_thinlayer_decl.h:112-124)
+            { "thinlayer", 9, "SPI_THINLAYER", nullptr },
             // participating media (shading.cpp:265-284)
             { "anisotropic_vdf", 3, "MX_ANISOTROPIC_VDF_ID", nullptr },
             { "medium_vdf", 6, "MX_MEDIUM_VDF_ID", nullptr },
@@ -1466,6 +1468,8 @@ Gen::emit_op(const Opcode& op)
         if (cn == "conductor_bsdf" || cn == "dielectric_bsdf" || cn == "generalized_schlick_bsdf"
             || cn == "translucent_bsdf" || cn == "subsurface_bssrdf")
             g.uses_glossy_lobes = g.uses_mx_lobes = true;
+        if (cn == "thinlayer")   // spi::ThinLayerLobe: GGXDist, energy curve and frame of the MX lobes + its own state
+            g.uses_glossy_lobes = g.uses_mx_lobes = g.uses_thinlayer = true;
         std::string wexpr = "mkv(1.0f)";
         if (weight >= 0) {
             w("V3 w_; assign(w_, " + R(weight) + ");");
@@ -2082,7 +2086,7 @@ std::string
 generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderModuleInfo* info)
 {
     std::string mats;
-    bool color = false, glossy = false, mx = false, in_loop = false, media = false, sheen_ltc = false;
+    bool color = false, glossy = false, mx = false, in_loop = false, media = false, sheen_ltc = false, thin = false;
     int ntex = 0;  // one texture table per module: each group's slots follow the previous group's
     int pool_words = 2, lobes = 1, adds = 0;
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -2099,6 +2103,7 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         mx |= g.uses_mx_lobes;
         media |= g.uses_media;
         sheen_ltc |= g.uses_sheen_ltc;
+        thin |= g.uses_thinlayer;
         in_loop |= g.closure_in_loop;
         pool_words = std::max(pool_words, g.pool_words_bound);
         lobes      = std::max(lobes, g.lobe_bound);
@@ -2140,6 +2145,8 @@ generate_cuda_render(std::vector<Group*>& groups, bool has_background, RenderMod
         out << "#define OSLD_HAS_MEDIA 1\n";
     if (sheen_ltc)
         out << "#define OSLD_SHEEN_LTC 1\n";
+    if (thin)
+        out << "#define OSLD_THINLAYER 1\n";
     mi.uses_mx_lobes = mx;
     mi.uses_media    = media;
     mi.uses_luts     = mx || sheen_ltc;

@@ -153,6 +153,7 @@ struct Group {
     std::set<int> globals_read;                // b200_sg_field ids the kernel loads
     bool fma = true;                           // allow FMA contraction in generated code
     bool uses_glossy_lobes = false;            // set by codegen: phong / ward / microfacet closures
+    bool uses_thinlayer    = false;            // set by codegen: the thinlayer closure (spi::ThinLayerLobe)
     bool uses_sheen_ltc    = false;            // set by codegen: sheen_bsdf with a "mode" keyword
     bool uses_media        = false;            // set by codegen: medium_vdf / anisotropic_vdf closures
     bool uses_mx_lobes     = false;            // set by codegen: conductor / dielectric / generalized schlick ...

@@ -369,9 +369,11 @@ load_bsdl_luts(std::vector<float>& out)
     size_t slash     = path.rfind('/');
     const std::string dir = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/data/";
     // energy tables of the MaterialX microfacet closures (tools/bake_bsdl_luts.cpp), then the
-    // Zeltner-Burley sheen LTC coefficients (tools/bake_zeltner_ltc.py): one block, in this order
+    // Zeltner-Burley sheen LTC coefficients (tools/bake_zeltner_ltc.py), then the spi::Thinlayer
+    // energy table of the thinlayer closure (same baker): one block, in this order
     const struct { const char* file; size_t words; } parts[] = { { "bsdl_luts.bin", 256 + 3 * 8192 },
-                                                                  { "zeltner_ltc.bin", 32 * 32 * 3 } };
+                                                                  { "zeltner_ltc.bin", 32 * 32 * 3 },
+                                                                  { "thinlayer_lut.bin", 32 * 16 * 16 } };
     out.clear();
     for (const auto& part : parts) {
         const std::string file = dir + part.file;

@@ -248,7 +248,8 @@ def bsdl_luts():
     data baked by tools/bake_bsdl_luts.cpp and shipped with the product."""
     luts = np.fromfile(BSDL_LUTS, np.float32)
     ltc = os.path.join(os.path.dirname(BSDL_LUTS), "zeltner_ltc.bin")   # tools/bake_zeltner_ltc.py
-    return np.concatenate([luts, np.fromfile(ltc, np.float32)])
+    thin = os.path.join(os.path.dirname(BSDL_LUTS), "thinlayer_lut.bin")   # spi::Thinlayer, same baker
+    return np.concatenate([luts, np.fromfile(ltc, np.float32), np.fromfile(thin, np.float32)])
 
 
 def shadeops():

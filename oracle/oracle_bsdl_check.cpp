@@ -9,7 +9,7 @@ using namespace oslo;
 extern "C" void oracle_set_bsdl_luts(const float* p) { bsdl_luts() = p; }
 
 // lobe: 0 conductor  1 dielectric  2 generalized schlick  3 translucent  4 sheen  5 oren-nayar diffuse
-//       6 burley diffuse;  p: closure parameters in registration order, strings skipped (see ref_bsdl.cpp)
+//       6 burley diffuse  7 spi thinlayer;  p: closure parameters in registration order, strings skipped (see ref_bsdl.cpp)
 // mode 0: eval(wo, wi = arg)   1: sample(wo, rnd = arg)   2: albedo   3: filter_o
 extern "C" int
 oracle_bsdl(int lobe, const float* p, const float* wo_, int backfacing, float path_roughness, int mode, const float* arg,
@@ -70,6 +70,15 @@ oracle_bsdl(int lobe, const float* p, const float* wo_, int backfacing, float pa
         l.energy_compensation = lobe == 5 ? (int)p[7] : 0;
         l.tf     = TangentFrame::from_normal(lobes::bsdl_visible_normal(wo, l.N, l.N));
         break;
+    case 7: {   // thinlayer: N T IOR roughness anisotropy thickness refl_tint refr_tint sigma_t
+        l.type     = LOBE_SPI_THINLAYER;
+        l.N        = V3(p[0], p[1], p[2]);
+        const V3 Z = lobes::bsdl_visible_normal(wo, l.N, l.N);
+        l.tf       = lobes::bsdl_frame_zx(Z, V3(p[3], p[4], p[5]));
+        l.thin     = lobes::thin_setup(dot(wo, Z), p[6], p[7], p[8], p[9], V3(p[10], p[11], p[12]), V3(p[13], p[14], p[15]),
+                                       V3(p[16], p[17], p[18]), path_roughness);
+        break;
+    }
     default: return 1;
     }
     BSample s;

@@ -483,7 +483,7 @@ inline float sheen_conty_albedo(float cosNO, float rough)
 // ---- mtx::ZeltnerBurleySheen (MTX/bsdf_sheen_impl.h:205-355): sheen as a linearly transformed
 // cosine; the (A, B, R) coefficients come from a 32 x 32 table over (roughness, cos theta_o)
 // that follows the energy tables in the LUT block (data/zeltner_ltc.bin)
-enum { LUT_ZELTNER = LUT_WORDS, LUT_WORDS_ALL = LUT_WORDS + 32 * 32 * 3 };
+enum { LUT_ZELTNER = LUT_WORDS, LUT_WORDS_ALL = LUT_THINLAYER + 32 * 16 * 16 };
 inline V3 zeltner_fetch_coeffs(float roughness, float cosNO)
 {
     const float ALMOSTONE = 0.999999940395355224609375f;
@@ -597,6 +597,8 @@ inline BSample sheen_sample(const Lobe& l, const V3& wo, float rx, float ry)
     return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
 }
 
+#include "osl_oracle_thinlayer.h"
+
 }  // namespace lobes
 
 inline V3 ext_albedo(const Lobe& l, const V3& wo)
@@ -614,6 +616,10 @@ inline BSample ext_eval(const Lobe& l, const V3& wo, const V3& wi)
     case LOBE_BSDL_SHEEN: return lobes::sheen_eval(l, wo, wi);
     case LOBE_MX_SPEC: {   // BSDL_WRAP::eval (shading.cpp:88-93)
         BSample s = mx_eval_local(l.mx, l.tf.tolocal(wo), l.tf.tolocal(wi));
+        return BSample(wi, s.weight, s.pdf, s.roughness);
+    }
+    case LOBE_SPI_THINLAYER: {   // SpiThinLayer::eval (shading.cpp:138-143)
+        BSample s = lobes::thin_eval_local(l.thin, l.tf.tolocal(wo), l.tf.tolocal(wi));
         return BSample(wi, s.weight, s.pdf, s.roughness);
     }
     case LOBE_MX_TRANSLUCENT: {
@@ -636,6 +642,10 @@ inline BSample ext_sample(const Lobe& l, const V3& wo, float rx, float ry, float
     case LOBE_BSDL_SHEEN: return lobes::sheen_sample(l, wo, rx, ry);
     case LOBE_MX_SPEC: {   // BSDL_WRAP::sample (shading.cpp:94-101)
         BSample s = mx_sample_local(l.mx, l.tf.tolocal(wo), rx, ry, rz);
+        return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
+    }
+    case LOBE_SPI_THINLAYER: {   // SpiThinLayer::sample (shading.cpp:144-151)
+        BSample s = lobes::thin_sample_local(l.thin, l.tf.tolocal(wo), V3(rx, ry, rz));
         return BSample(l.tf.toworld(s.wi), s.weight, s.pdf, s.roughness);
     }
     case LOBE_MX_TRANSLUCENT: {

@@ -35,7 +35,9 @@ inline float mx_max_abs(const V3& v) { return std::max(std::fabs(v.x), std::max(
 // ---- energy tables ---------------------------------------------------------------------------
 // layout of the table block: [MiniMicrofacetGGX 1x16x16][ReflFront 32x16x16][BothFront][BothBack]
 enum { LUT_GGX = 0, LUT_REFL_FRONT = 256, LUT_BOTH_FRONT = 256 + 8192, LUT_BOTH_BACK = 256 + 2 * 8192,
-       LUT_WORDS = 256 + 3 * 8192 };
+       LUT_WORDS = 256 + 3 * 8192,
+       // then the Zeltner-Burley LTC coefficients (32x32x3, osl_oracle_lobes.h) and spi::Thinlayer 32x16x16
+       LUT_THINLAYER = LUT_WORDS + 32 * 32 * 3 };
 inline const float*& bsdl_luts()
 {
     static const float* p = nullptr;
@@ -272,6 +274,15 @@ struct MxSpec {
     V3 refl_tint = V3(1.0f), refr_tint = V3(0.0f);
     V3 wo_absorption = V3(1.0f);
     float roughness  = 0;
+};
+
+// ---- what spi::ThinLayerLobe boils down to (functions in osl_oracle_thinlayer.h) ---------------
+struct ThinSpec {
+    GGXD d;
+    V3 sigma_t   = V3(0.0f);
+    float eta    = 1.5f, thickness = 0, roughness = 0, prob_clamp = 0;
+    V3 refl_tint = V3(1.0f), refr_tint = V3(1.0f);
+    float Eo     = 0;   // energy the microfacet lobes lose, handed to the diffuse / translucent pair
 };
 
 // eval_turquin_microms_reflection (microfacet_tools_impl.h:333-362)

@@ -326,7 +326,8 @@ enum LobeType { LOBE_DIFFUSE, LOBE_TRANSLUCENT, LOBE_REFLECTION, LOBE_REFRACTION
                 LOBE_BSDL_BURLEY /* mtx::BurleyDiffuseLobe */,
                 LOBE_BSDL_SHEEN /* mtx::SheenLobe, Conty-Kulla mode */,
                 LOBE_MX_SPEC /* mtx::ConductorLobe / DielectricLobe / SchlickLobe */,
-                LOBE_MX_TRANSLUCENT /* mtx::TranslucentLobe */ };
+                LOBE_MX_TRANSLUCENT /* mtx::TranslucentLobe */,
+                LOBE_SPI_THINLAYER /* spi::ThinLayerLobe (SpiThinLayer, shading.cpp:119-152) */ };
 }  // namespace oslo
 #include "osl_oracle_mxlobes.h"
 namespace oslo {
@@ -351,6 +352,7 @@ struct Lobe {
     bool backfacing = false;
     TangentFrame tf;
     MxSpec mx;   // conductor / dielectric / generalized schlick state (LOBE_MX_SPEC)
+    ThinSpec thin;   // LOBE_SPI_THINLAYER
     V3 get_albedo(const V3& wo) const
     {
         switch (type) {
@@ -1004,6 +1006,18 @@ inline void process_closure(const SG& sg, ShadingResult& result, const Clos* clo
                     l.type   = LOBE_MX_TRANSLUCENT;
                     l.albedo = V3(comp->params[3], comp->params[4], comp->params[5]);
                     l.tf     = TangentFrame::from_normal(lobes::bsdl_visible_normal(-sg.I.val, l.N, l.N));
+                    break;
+                }
+                case SPI_THINLAYER: {
+                    // params: N, T, IOR, roughness, anisotropy, thickness, refl_tint, refr_tint, sigma_t
+                    // (ThinLayerLobe::Data registration order; shading.cpp:1668-1674)
+                    const float* p = comp->params;
+                    const V3 wo    = -sg.I.val;
+                    l.type         = LOBE_SPI_THINLAYER;
+                    const V3 Z     = lobes::bsdl_visible_normal(wo, l.N, l.N);
+                    l.tf           = lobes::bsdl_frame_zx(Z, V3(p[3], p[4], p[5]));
+                    l.thin = lobes::thin_setup(dot(wo, Z), p[6], p[7], p[8], p[9], V3(p[10], p[11], p[12]),
+                                               V3(p[13], p[14], p[15]), V3(p[16], p[17], p[18]), path_roughness);
                     break;
                 }
                 case MX_SUBSURFACE_ID: {

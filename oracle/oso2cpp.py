@@ -370,6 +370,8 @@ CLOSURES = {("emission", 0): "EMISSION_ID", ("background", 0): "BACKGROUND_ID",
             ("generalized_schlick_bsdf", 10): "MX_GENERALIZED_SCHLICK_ID",
             ("translucent_bsdf", 2): "MX_TRANSLUCENT_ID",
             ("subsurface_bssrdf", 4): "MX_SUBSURFACE_ID",
+            # spi::ThinLayerLobe (SpiThinLayer, shading.cpp:119-152; Data: SPI/bsdf_thinlayer_decl.h:112-124)
+            ("thinlayer", 9): "SPI_THINLAYER",
             # participating media (shading.cpp:265-284)
             ("anisotropic_vdf", 3): "MX_ANISOTROPIC_VDF_ID", ("medium_vdf", 6): "MX_MEDIUM_VDF_ID"}
 # keyword parameters per closure id, in slot order after the positional words; value

@@ -120,7 +120,7 @@ int run(const typename W::Data& d, const float* wo_, int backfacing, float path_
 }  // namespace
 
 // lobe: 0 conductor  1 dielectric  2 generalized schlick  3 translucent  4 sheen  5 oren-nayar diffuse
-//       6 burley diffuse
+//       6 burley diffuse  7 spi thinlayer
 // p: the closure's parameters in registration order (strings skipped), see the Data structs
 extern "C" int
 ref_bsdl(int lobe, const float* p, const float* wo, int backfacing, float path_roughness, int mode,
@@ -173,6 +173,32 @@ ref_bsdl(int lobe, const float* p, const float* wo, int backfacing, float path_r
         W::Data d {};
         d.N = v3(p); d.albedo = c3(p + 3); d.roughness = p[6];
         return run<W, false>(d, wo, backfacing, path_roughness, mode, arg, out);
+    }
+    case 7: {   // SpiThinLayer (shading.cpp:119-152): backfacing false, both lobes on, no albedo_impl / filter_o
+        using L = spi::ThinLayerLobe<Root>;
+        struct W : public L {
+            W(const L::Data& d, const V3f& wo, float path_roughness)
+                : L(this, bsdl::BsdfGlobals(wo, d.N, d.N, false, path_roughness, 1.0f, 0), d)
+            {
+            }
+        };
+        L::Data d {};
+        d.N = v3(p); d.T = v3(p + 3); d.IOR = p[6]; d.roughness = p[7]; d.anisotropy = p[8]; d.thickness = p[9];
+        d.prob_clamp = 0;
+        d.refl_tint = c3(p + 10); d.refr_tint = c3(p + 13); d.sigma_t = c3(p + 16);
+        const V3f wov = v3(wo);
+        W lobe(d, wov, path_roughness);
+        if (mode == 0) {
+            const V3f wi = v3(arg);
+            put(out, lobe.eval_impl(lobe.frame.local(wov), lobe.frame.local(wi), true, true), wi);
+        } else if (mode == 1) {
+            bsdl::Sample s = lobe.sample_impl(lobe.frame.local(wov), v3(arg), true, true);
+            put(out, s, lobe.frame.world(s.wi));
+        } else if (mode == 2) {
+            out[0] = out[1] = out[2] = 1.0f;   // BSDF::get_albedo default (shading.h:287)
+        } else
+            return 2;
+        return 0;
     }
     default: return 1;
     }

@@ -47,14 +47,15 @@ def test_baked_energy_tables_equal_the_reference_genluts_output(libs):
     tabs = []
     # MiniMicrofacetGGX, DielectricReflFront, BothFront, BothBack (baked by tools/bake_bsdl_luts.cpp)
     # + the Zeltner-Burley sheen LTC coefficients (published fit, stored by tools/bake_zeltner_ltc.py)
-    for t in (0, 1, 2, 3, 7):
+    # + spi::Thinlayer (same baker, openshadinglanguage_b200/data/thinlayer_lut.bin)
+    for t in (0, 1, 2, 3, 7, 6):
         n = ctypes.c_int()
         p = ref.ref_bsdl_lut(t, ctypes.byref(n))
         tabs.append(np.ctypeslib.as_array(p, (n.value,)).copy())
     want = np.concatenate(tabs).astype(np.float32)
-    assert luts.size == want.size == 256 + 3 * 8192 + 32 * 32 * 3
+    assert luts.size == want.size == 256 + 3 * 8192 + 32 * 32 * 3 + 8192
     assert np.array_equal(luts.view(np.uint32), want.view(np.uint32))
-    energy = luts[:256 + 3 * 8192]
+    energy = np.concatenate([luts[:256 + 3 * 8192], luts[-8192:]])
     assert 0.0 <= energy.min() and energy.max() <= 1.0
 
 
@@ -81,6 +82,10 @@ def _params(rng, lobe):
         p = np.concatenate([N, c(), [rng.uniform(0, 1), float(rng.choice([0, 1, 1, 2]))]])
     elif lobe == 5:     # oren-nayar diffuse: N albedo roughness energy_compensation
         p = np.concatenate([N, c(), [rng.uniform(0, 1), float(rng.integers(0, 2))]])
+    elif lobe == 7:     # spi thinlayer: N T IOR roughness anisotropy thickness refl_tint refr_tint sigma_t
+        sig = c() * rng.choice([0.0, 0.3, 3.0]) if rng.random() < 0.7 else np.zeros(3)
+        p = np.concatenate([N, U, [rng.uniform(1.0, 3.0), rng.uniform(0, 1), rng.uniform(0, 0.95),
+                                   rng.choice([0.0, 1.0, rng.uniform(0, 4)])], c(), c(), sig])
     else:               # burley diffuse: N albedo roughness
         p = np.concatenate([N, c(), [rng.uniform(0, 1)]])
     return N, p.astype(np.float32)
@@ -88,7 +93,7 @@ def _params(rng, lobe):
 
 @pytest.mark.parametrize("lobe,name", [(0, "conductor"), (1, "dielectric"), (2, "generalized_schlick"),
                                        (3, "translucent"), (4, "sheen"), (5, "oren_nayar_diffuse"),
-                                       (6, "burley_diffuse")])
+                                       (6, "burley_diffuse"), (7, "spi_thinlayer")])
 def test_restated_lobe_is_bit_exact_against_the_reference_class(libs, lobe, name):
     ref, orc, _ = libs
     rng = np.random.default_rng(1000 + lobe)

@@ -13,7 +13,9 @@
 // does this tool.  tests/test_oracle_bsdl.py checks the file against the tables the reference's
 // own genluts produces (oracle/_ref), entry by entry.
 //
-//   g++ -std=c++17 -O2 tools/bake_bsdl_luts.cpp -lpthread -o /tmp/bake && /tmp/bake out.bin
+// and, into a second file, spi::Thinlayer 32 x 16 x 16 (SPI/bsdf_thinlayer_decl.h) for the thinlayer closure.
+//
+//   g++ -std=c++17 -O2 tools/bake_bsdl_luts.cpp -lpthread -o /tmp/bake && /tmp/bake bsdl_luts.bin thinlayer_lut.bin
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -327,6 +329,90 @@ template<bool DOREFR, bool BACK> struct Dielectric {   // DielectricBSDF<Dielect
     }
 };
 
+// spi::Thinlayer as genluts builds it: Thinlayer(0, roughness_index, fresnel_index), i.e. thickness 0,
+// no extinction, prob_clamp 0, isotropic (SPI/bsdf_thinlayer_impl.h:114-127, 135-178, 187-310)
+inline float fresnel_dielectric(float cosi, float eta)
+{
+    if (eta == 0.0f)
+        return 1.0f;
+    if (cosi < 0.0f)
+        eta = 1.0f / eta;
+    float c = std::fabs(cosi);
+    float g = eta * eta - 1 + c * c;
+    if (g > 0) {
+        g       = sqrtf(g);
+        float A = (g - c) / (g + c);
+        float B = (c * (g + c) - 1) / (c * (g - c) + 1);
+        return 0.5f * A * A * (1 + B * B);
+    }
+    return 1.0f;
+}
+struct ThinlayerBake {
+    GGX d;
+    float eta, roughness;
+    ThinlayerBake(float, float rough, float fresnel_index, const float*) : d(rough), roughness(rough)
+    {
+        eta = CLAMP(LERP(SQR(fresnel_index), 1.001f, 5.0f), 1.001f, 5.0f);
+    }
+    float F(float c) const
+    {
+        const float g = sqrtf(eta * eta - 1 + c * c);
+        const float A = (g - c) / (g + c);
+        const float B = (c * (g + c) - 1) / (c * (g - c) + 1);
+        return 0.5f * A * A * (1 + B * B);
+    }
+    float avg_invf() const
+    {
+        const float e = 1 / eta;
+        if (e < 1)
+            return 0.997118f + e * (0.1014f + e * (-0.965241f - e * 0.130607f));
+        return (e - 1) / (4.08567f + 1.00071f * e);
+    }
+    float slope_scale(float cosNO) const
+    {
+        cosNO = std::min(cosNO, 1.0f);
+        const float inveta = 1 / eta;
+        const float sinNI  = inveta * sqrtf(1 - SQR(cosNO));
+        if (sinNI > 1.0f)
+            return 1;
+        const float cosNI = -sqrtf(1 - SQR(sinNI));
+        const float je = (1 + inveta * (cosNO / cosNI)), jx = (1 + eta * (cosNI / cosNO));
+        const float refr_variance = SQR(je) + SQR(jx), refl_variance = SQR(2.0f);
+        return std::min(sqrtf((refr_variance / refl_variance) / cosNO), 1 / roughness);
+    }
+    float sample_weight(V3 wo, float ru, float rv, float rw) const
+    {
+        const V3 m = d.sample(wo, ru, rv);
+        if (dot(wo, m) <= 0)
+            return 0.0f;
+        // attenuation(): thickness 0 -> A = 1
+        const V3 wr       = refract(wo, m, eta);
+        const float cosNO = std::min(dot(wo, m), 1.0f);
+        const float cosNR = CLAMP(-wr.z, 0.0f, 1.0f);
+        const float Rout = F(cosNO), Tin = 1.0f - Rout;
+        const float Rin  = LERP(roughness, fresnel_dielectric(cosNR, 1 / eta), avg_invf());
+        const float A = 1, b = SQR(Rin * A);
+        const float R = Rout + (1 - b < 1e-4f ? (A < 1 ? 0 : Tin * 0.5f) : Tin * (1 - Rin) * SQR(A) * Rin / (1 - b));
+        const float T = 1 - b < 1e-4f ? (A < 1 ? 0 : Tin * 0.5f) : Tin * (1 - Rin) * A / (1 - b);
+        const float Fp = R / std::max(R + T, FLT_MIN);
+        auto prob = [](float f) { return LERP(0.0f, f, CLAMP(f, 0.2f, 0.8f)); };
+        const bool isrefl = rw < prob(Fp);
+        const float sc    = slope_scale(wo.z);
+        const V3 mt       = isrefl ? m : normalized({ m.x * sc, m.y * sc, m.z });
+        if (dot(wo, mt) <= 0)
+            return 0.0f;
+        const V3 wif = reflect(wo, mt);
+        const V3 wi  = isrefl ? wif : V3 { wif.x, wif.y, -wif.z };
+        if ((isrefl && wi.z <= 0) || (!isrefl && wi.z >= 0))
+            return 0.0f;
+        const float P = prob(isrefl ? Fp : 1 - Fp);
+        if (P < 1e-6f)
+            return 0.0f;
+        const float out = d.G2_G1({ wi.x, wi.y, std::fabs(wi.z) }, wo) / P;
+        return (isrefl ? R : T) * out;
+    }
+};
+
 // ---- genluts.cpp: the stratified scrambled sample set and the running mean -------------------
 inline uint32_t ri_LP(uint32_t i)
 {
@@ -427,7 +513,7 @@ int
 main(int argc, char** argv)
 {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s out.bin\n", argv[0]);
+        fprintf(stderr, "usage: %s bsdl_luts.bin [thinlayer_lut.bin]\n", argv[0]);
         return 2;
     }
     std::vector<float> luts(256 + 3 * 8192, 0.0f);
@@ -442,5 +528,16 @@ main(int argc, char** argv)
     }
     fclose(f);
     printf("wrote %zu floats to %s\n", luts.size(), argv[1]);
+    if (argc > 2) {   // spi::Thinlayer 32 x 16 x 16 (SPI/bsdf_thinlayer_decl.h:37-41), its own file
+        std::vector<float> thin(8192, 0.0f);
+        bake<ThinlayerBake>(thin.data(), 32, false, nullptr);
+        f = fopen(argv[2], "wb");
+        if (!f || fwrite(thin.data(), sizeof(float), thin.size(), f) != thin.size()) {
+            fprintf(stderr, "cannot write %s\n", argv[2]);
+            return 1;
+        }
+        fclose(f);
+        printf("wrote %zu floats to %s\n", thin.size(), argv[2]);
+    }
     return 0;
 }

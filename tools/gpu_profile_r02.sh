@@ -20,7 +20,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:osl_
     python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline > $O/${TAG}_ncu_full_layers.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:osl_b200_group_kernel -s 4 -c 1 -o $O/${TAG}_full_noise \
     python bench.py --workload noise-1024 --steps 3 --warmup 3 --no-extra --no-cpu-baseline > $O/${TAG}_ncu_full_noise.log 2>&1
-for k in rt_trace rt_shade rt_light; do
+for k in rt_trace rt_shade; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 12 -c 1 -o $O/${TAG}_full_$k \
       python tools/render_bench.py cornell.xml --res 1024 --aa 8 --repeat 1 > $O/${TAG}_ncu_full_$k.log 2>&1
 done

@@ -86,6 +86,7 @@ SHADERS = {
     "mxmed_medium": "render-mx-medium-vdf/medium.osl",
     "mxmedglass_glossy": "render-mx-medium-vdf-glass/glossy.osl",
     "mxaniso_anisotropic": "render-mx-anisotropic-vdf/anisotropic.osl",
+    "spithin_glossy_glass": "render-spi-thinlayer/glossy_glass.osl",   # thinlayer closure (spi::ThinLayerLobe)
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -134,6 +135,7 @@ SCENES = {
     "mx_medium_vdf_glass.xml": ("render-mx-medium-vdf-glass/scene.xml", {"glossy": "mxmedglass_glossy"}),
     "mx_anisotropic_vdf.xml": ("render-mx-anisotropic-vdf/scene.xml",
                                {"anisotropic": "mxaniso_anisotropic", "envmap": "mxmed_envmap"}),
+    "spi_thinlayer.xml": ("render-spi-thinlayer/scene.xml", {"glossy_glass": "spithin_glossy_glass", "envmap": "mf_envmap"}),
 }
 # input images read by texture() (test input data, copied byte for byte)
 TEXTURES = {"kitchen_probe.hdr": "common/textures/kitchen_probe.hdr"}
@@ -160,6 +162,7 @@ RENDERS = {
     "render-mx-medium-vdf": "render-mx-medium-vdf/ref/out.exr",
     "render-mx-medium-vdf-glass": "render-mx-medium-vdf-glass/ref/out.exr",
     "render-mx-anisotropic-vdf": "render-mx-anisotropic-vdf/ref/out.exr",
+    "render-spi-thinlayer": "render-spi-thinlayer/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
