@@ -138,6 +138,12 @@ OSLD V3 vnormalized(V3 v)
     return l != 0.0f ? vdiv(v, l) : v;
 }
 OSLD float vcomp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// (v[kx], v[ky], v[kz]) for the watertight test's axis renaming, kx = (kz + 1) % 3, ky = (kx + 1) % 3:
+// two predicates per ray and selects per component, no branches in the triangle loop
+OSLD V3 vperm_kz(V3 v, bool z0, bool z1)
+{
+    return mkv(z0 ? v.y : (z1 ? v.z : v.x), z0 ? v.z : (z1 ? v.x : v.y), z0 ? v.x : (z1 ? v.y : v.z));
+}
 
 // ---- Ray ---------------------------------------------------------------------------
 enum { RAY_CAMERA = 1, RAY_SHADOW = 2, RAY_DIFFUSE = 16 };
@@ -881,6 +887,64 @@ OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3
     T.shy = vcomp(dir, ky) / vcomp(dir, kz);
     T.shz = vcomp(T.rdir, kz);
 }
+// the triangles of one leaf against the ray (watertight test, bvh.cpp:203-263), in leaf order
+OSLD void trav_leaf(const RenderScene& S, const Trav& T, unsigned child, unsigned nprims, Hit& result)
+{
+    const V3 org = T.org;
+    const bool z0 = T.kz == 0, z1 = T.kz == 1;
+    const float shx = T.shx, shy = T.shy, shz = T.shz;
+    for (unsigned i = 0; i < nprims; i++) {
+        const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
+        const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
+        const unsigned id = fbits(ta.w);
+        const V3 A = vperm_kz(xyz(ta) - org, z0, z1);
+        const V3 B = vperm_kz(xyz(tb) - org, z0, z1);
+        const V3 C = vperm_kz(xyz(tc) - org, z0, z1);
+        const float Ax = A.x - shx * A.z, Ay = A.y - shy * A.z;
+        const float Bx = B.x - shx * B.z, By = B.y - shy * B.z;
+        const float Cx = C.x - shx * C.z, Cy = C.y - shy * C.z;
+        const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+        if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
+            continue;
+        const float det = U + V + W;
+        if (det == 0)
+            continue;
+        const float Tt      = shz * (U * A.z + V * B.z + W * C.z);
+        const unsigned mask = fbits(det) & 0x80000000u;
+        if (xorf(Tt, mask) < 0)
+            continue;
+        if (xorf(Tt, mask) > result.t * xorf(det, mask))
+            continue;
+        if (id == T.skip1 || id == T.skip2)
+            continue;
+        const float rcpDet = 1 / det;
+        result.t  = Tt * rcpDet;
+        result.u  = V * rcpDet;
+        result.v  = W * rcpDet;
+        result.id = id;
+    }
+}
+// one inner node: both children's boxes, far child pushed first (bvh.cpp:300-340)
+OSLD void trav_visit(const RenderScene& S, const Trav& T, unsigned child, float tnear, int& sp)
+{
+    // the two children are adjacent: 64 contiguous bytes
+    const float4* cn = S.bvh_nodes + 2 * (size_t)child;
+    const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
+    float d1 = 0, d2 = 0;
+    bool h1 = box_intersect(T.org, T.rdir, tnear, a0, a1, &d1);
+    bool h2 = box_intersect(T.org, T.rdir, tnear, b0, b1, &d2);
+    unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
+    if (d1 > d2) {
+        bool th = h1; h1 = h2; h2 = th;
+        float td = d1; d1 = d2; d2 = td;
+        unsigned tk = k1; k1 = k2; k2 = tk;
+        unsigned tn = n1; n1 = n2; n2 = tn;
+    }
+    stk_put(T, sp, k2, n2, d2);
+    sp += h2 ? 1 : 0;
+    stk_put(T, sp, k1, n1, d1);
+    sp += h1 ? 1 : 0;
+}
 // Scene::intersect (bvh.cpp:265-356), resumable, one STEP per call: walk at most `max_nodes`
 // inner nodes; if that reaches a leaf, test its triangles.  Returns true when the ray is finished.
 // "while-while" traversal (Aila & Laine) with a bounded walk: every lane first walks inner
@@ -891,7 +955,6 @@ OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3
 // (and any tie between coplanar triangles) is the reference's.
 OSLD bool trav_step(const RenderScene& S, Trav& T, int max_nodes)
 {
-    const V3 org = T.org, rdir = T.rdir;
     int sp = T.sp;
     Hit result = T.hit;
     unsigned child = 0, nprims = 0;
@@ -903,63 +966,61 @@ OSLD bool trav_step(const RenderScene& S, Trav& T, int max_nodes)
         if (nprims)
             break;
         --max_nodes;
-        // the two children are adjacent: 64 contiguous bytes
-        const float4* cn = S.bvh_nodes + 2 * (size_t)child;
-        const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
-        float d1 = 0, d2 = 0;
-        bool h1 = box_intersect(org, rdir, result.t, a0, a1, &d1);
-        bool h2 = box_intersect(org, rdir, result.t, b0, b1, &d2);
-        unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
-        if (d1 > d2) {
-            bool th = h1; h1 = h2; h2 = th;
-            float td = d1; d1 = d2; d2 = td;
-            unsigned tk = k1; k1 = k2; k2 = tk;
-            unsigned tn = n1; n1 = n2; n2 = tn;
-        }
-        stk_put(T, sp, k2, n2, d2);
-        sp += h2 ? 1 : 0;
-        stk_put(T, sp, k1, n1, d1);
-        sp += h1 ? 1 : 0;
+        trav_visit(S, T, child, result.t, sp);
     }
     bool finished = false;
     if (nprims) {
-        const int kx = T.kx, ky = T.ky, kz = T.kz;
-        const float shx = T.shx, shy = T.shy, shz = T.shz;
-        for (unsigned i = 0; i < nprims; i++) {
-            const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
-            const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
-            const unsigned id = fbits(ta.w);
-            const V3 A = xyz(ta) - org;
-            const V3 B = xyz(tb) - org;
-            const V3 C = xyz(tc) - org;
-            const float Ax = vcomp(A, kx) - shx * vcomp(A, kz), Ay = vcomp(A, ky) - shy * vcomp(A, kz);
-            const float Bx = vcomp(B, kx) - shx * vcomp(B, kz), By = vcomp(B, ky) - shy * vcomp(B, kz);
-            const float Cx = vcomp(C, kx) - shx * vcomp(C, kz), Cy = vcomp(C, ky) - shy * vcomp(C, kz);
-            const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
-            if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
-                continue;
-            const float det = U + V + W;
-            if (det == 0)
-                continue;
-            const float Tt      = shz * (U * vcomp(A, kz) + V * vcomp(B, kz) + W * vcomp(C, kz));
-            const unsigned mask = fbits(det) & 0x80000000u;
-            if (xorf(Tt, mask) < 0)
-                continue;
-            if (xorf(Tt, mask) > result.t * xorf(det, mask))
-                continue;
-            if (id == T.skip1 || id == T.skip2)
-                continue;
-            const float rcpDet = 1 / det;
-            result.t  = Tt * rcpDet;
-            result.u  = V * rcpDet;
-            result.v  = W * rcpDet;
-            result.id = id;
-        }
+        trav_leaf(S, T, child, nprims, result);
         // a shadow ray only asks "is anything strictly closer than tmax0": the closest-hit walk
         // can only move t further down from here, so the answer is already known
         finished = T.anyhit && result.t < T.tmax0;
     } else
         finished = sp == 0;
+    T.sp  = sp;
+    T.hit = result;
+    return finished;
+}
+// trav_step for a whole warp (rt_trace): every lane calls it, `active` says whether the lane holds a
+// ray.  Same per-ray visiting order; what changes is how the lanes are grouped.  The walk phase is a
+// warp-uniform loop that ends when the lanes holding a leaf outnumber the lanes still walking (or after
+// max_nodes visits): with the fixed node budget of trav_step the walkers thinned out to 8 of 32 lanes
+// while the others waited with their leaf (ncu source page, profiles/ncu_r02_rt_trace_sass.txt).
+OSLD bool trav_step_warp(const RenderScene& S, Trav& T, bool active, int max_nodes)
+{
+    int sp = T.sp;
+    Hit result = T.hit;
+    unsigned child = 0, nprims = 0;
+    bool walking = active && sp != 0;
+    for (int it = 0; it < max_nodes; ++it) {
+        const unsigned wm = __ballot_sync(0xffffffffu, walking);
+        if (wm == 0u)
+            break;
+        const unsigned lm = __ballot_sync(0xffffffffu, nprims != 0u);
+        if (__popc(wm) < __popc(lm))
+            break;
+        if (walking) {
+            // pop to the next entry the current hit has not culled
+            bool got = false;
+            while (sp != 0) {
+                --sp;
+                if (result.t < stk_dist(T, sp))
+                    continue;
+                stk_get(T, sp, child, nprims);
+                got = true;
+                break;
+            }
+            if (got && nprims == 0u)
+                trav_visit(S, T, child, result.t, sp);
+            walking = nprims == 0u && sp != 0;
+        }
+    }
+    bool finished = false;
+    if (nprims) {
+        trav_leaf(S, T, child, nprims, result);
+        finished = T.anyhit && result.t < T.tmax0;
+        finished = finished || sp == 0;
+    } else
+        finished = active && sp == 0;
     T.sp  = sp;
     T.hit = result;
     return finished;
@@ -1832,7 +1893,7 @@ extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __
         }
         if (hm == 0u)
             break;
-        if (have && trav_step(S, T, OSLD_TRACE_CHUNK)) {
+        if (trav_step_warp(S, T, have, OSLD_TRACE_CHUNK) && have) {
             if (phase == 0) {
                 float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
                 rec[4]      = make_float4(T.hit.t, T.hit.u, T.hit.v, __int_as_float((int)T.hit.id));
