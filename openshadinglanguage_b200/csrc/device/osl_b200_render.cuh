@@ -794,6 +794,22 @@ struct Hit {
 };
 OSLD float minf_(float a, float b) { return b < a ? b : a; }
 OSLD float maxf_(float a, float b) { return b > a ? b : a; }
+// The same slab test with the hardware min / max (one FMNMX each instead of compare + select).
+// minf_ / maxf_ differ from fminf / fmaxf only when their FIRST operand is a NaN, and a NaN can only
+// come from 0 * inf, i.e. from a ray with a zero (or denormal) direction component; trav_init flags those rays
+// (Trav::exact) and they take box_intersect.  The sign of a zero result may differ, which no
+// comparison below can see.
+OSLD bool box_intersect_finite(V3 org, V3 rdir, float tmax, float4 b0, float4 b1, float* dist)
+{
+    const float tx1 = (b0.x - org.x) * rdir.x, tx2 = (b0.y - org.x) * rdir.x;
+    const float ty1 = (b0.z - org.y) * rdir.y, ty2 = (b0.w - org.y) * rdir.y;
+    const float tz1 = (b1.x - org.z) * rdir.z, tz2 = (b1.y - org.z) * rdir.z;
+    float tmin      = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+    tmax            = fminf(fminf(fminf(tmax, fmaxf(tx1, tx2)), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+    *dist           = tmin;
+    tmin            = fmaxf(0.0f, tmin);
+    return tmin <= tmax;
+}
 OSLD bool box_intersect(V3 org, V3 rdir, float tmax, float4 b0, float4 b1, float* dist)
 {
     // bounds = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y } = minx,maxx,miny,maxy,minz,maxz
@@ -834,6 +850,8 @@ struct Trav {
     Hit hit;
     unsigned skip1, skip2;
     int kx, ky, kz, sp, anyhit;
+    bool exact;      // an infinite reciprocal direction: 0 * inf NaNs possible, take the compare-and-select slab test
+    unsigned lchild, lnprims;   // rt_trace: the part of the current leaf not tested yet (lnprims == 0: none)
     unsigned* stk;
     int stride;
 };
@@ -871,10 +889,12 @@ OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3
     T.org = org;
     T.hit.t = tmax; T.hit.u = T.hit.v = 0.0f; T.hit.id = 0;
     T.tmax0 = tmax; T.skip1 = skip1; T.skip2 = skip2; T.anyhit = anyhit;
+    T.lchild = 0u; T.lnprims = 0u;
     const float4 r1 = __ldg(S.bvh_nodes + 1);
     stk_put(T, 0, fbits(r1.z), fbits(r1.w), tmax);
     T.sp   = 1;
     T.rdir = mkv(1 / dir.x, 1 / dir.y, 1 / dir.z);
+    T.exact = fabsf(T.rdir.x) == OSLD_INF || fabsf(T.rdir.y) == OSLD_INF || fabsf(T.rdir.z) == OSLD_INF;
     int kz = 0;
     if (fabsf(dir.y) > fabsf(vcomp(dir, kz)))
         kz = 1;
@@ -887,42 +907,46 @@ OSLD void trav_init(const RenderScene& S, Trav& T, unsigned* stk, int stride, V3
     T.shy = vcomp(dir, ky) / vcomp(dir, kz);
     T.shz = vcomp(T.rdir, kz);
 }
-// the triangles of one leaf against the ray (watertight test, bvh.cpp:203-263), in leaf order
-OSLD void trav_leaf(const RenderScene& S, const Trav& T, unsigned child, unsigned nprims, Hit& result)
+// one triangle of a leaf against the ray (watertight test, bvh.cpp:203-263)
+OSLD void trav_tri(const RenderScene& S, const Trav& T, unsigned at, bool z0, bool z1, Hit& result)
 {
     const V3 org = T.org;
-    const bool z0 = T.kz == 0, z1 = T.kz == 1;
     const float shx = T.shx, shy = T.shy, shz = T.shz;
-    for (unsigned i = 0; i < nprims; i++) {
-        const float4* lt = S.leaf_tris + 3 * (size_t)(child + i);
-        const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
-        const unsigned id = fbits(ta.w);
-        const V3 A = vperm_kz(xyz(ta) - org, z0, z1);
-        const V3 B = vperm_kz(xyz(tb) - org, z0, z1);
-        const V3 C = vperm_kz(xyz(tc) - org, z0, z1);
-        const float Ax = A.x - shx * A.z, Ay = A.y - shy * A.z;
-        const float Bx = B.x - shx * B.z, By = B.y - shy * B.z;
-        const float Cx = C.x - shx * C.z, Cy = C.y - shy * C.z;
-        const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
-        if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
-            continue;
-        const float det = U + V + W;
-        if (det == 0)
-            continue;
-        const float Tt      = shz * (U * A.z + V * B.z + W * C.z);
-        const unsigned mask = fbits(det) & 0x80000000u;
-        if (xorf(Tt, mask) < 0)
-            continue;
-        if (xorf(Tt, mask) > result.t * xorf(det, mask))
-            continue;
-        if (id == T.skip1 || id == T.skip2)
-            continue;
-        const float rcpDet = 1 / det;
-        result.t  = Tt * rcpDet;
-        result.u  = V * rcpDet;
-        result.v  = W * rcpDet;
-        result.id = id;
-    }
+    const float4* lt = S.leaf_tris + 3 * (size_t)at;
+    const float4 ta = __ldg(lt), tb = __ldg(lt + 1), tc = __ldg(lt + 2);
+    const unsigned id = fbits(ta.w);
+    const V3 A = vperm_kz(xyz(ta) - org, z0, z1);
+    const V3 B = vperm_kz(xyz(tb) - org, z0, z1);
+    const V3 C = vperm_kz(xyz(tc) - org, z0, z1);
+    const float Ax = A.x - shx * A.z, Ay = A.y - shy * A.z;
+    const float Bx = B.x - shx * B.z, By = B.y - shy * B.z;
+    const float Cx = C.x - shx * C.z, Cy = C.y - shy * C.z;
+    const float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+    if ((U < 0 || V < 0 || W < 0) && (U > 0 || V > 0 || W > 0))
+        return;
+    const float det = U + V + W;
+    if (det == 0)
+        return;
+    const float Tt      = shz * (U * A.z + V * B.z + W * C.z);
+    const unsigned mask = fbits(det) & 0x80000000u;
+    if (xorf(Tt, mask) < 0)
+        return;
+    if (xorf(Tt, mask) > result.t * xorf(det, mask))
+        return;
+    if (id == T.skip1 || id == T.skip2)
+        return;
+    const float rcpDet = 1 / det;
+    result.t  = Tt * rcpDet;
+    result.u  = V * rcpDet;
+    result.v  = W * rcpDet;
+    result.id = id;
+}
+// the triangles of one leaf, in leaf order
+OSLD void trav_leaf(const RenderScene& S, const Trav& T, unsigned child, unsigned nprims, Hit& result)
+{
+    const bool z0 = T.kz == 0, z1 = T.kz == 1;
+    for (unsigned i = 0; i < nprims; i++)
+        trav_tri(S, T, child + i, z0, z1, result);
 }
 // one inner node: both children's boxes, far child pushed first (bvh.cpp:300-340)
 OSLD void trav_visit(const RenderScene& S, const Trav& T, unsigned child, float tnear, int& sp)
@@ -931,8 +955,14 @@ OSLD void trav_visit(const RenderScene& S, const Trav& T, unsigned child, float 
     const float4* cn = S.bvh_nodes + 2 * (size_t)child;
     const float4 a0 = __ldg(cn), a1 = __ldg(cn + 1), b0 = __ldg(cn + 2), b1 = __ldg(cn + 3);
     float d1 = 0, d2 = 0;
-    bool h1 = box_intersect(T.org, T.rdir, tnear, a0, a1, &d1);
-    bool h2 = box_intersect(T.org, T.rdir, tnear, b0, b1, &d2);
+    bool h1, h2;
+    if (T.exact) {
+        h1 = box_intersect(T.org, T.rdir, tnear, a0, a1, &d1);
+        h2 = box_intersect(T.org, T.rdir, tnear, b0, b1, &d2);
+    } else {
+        h1 = box_intersect_finite(T.org, T.rdir, tnear, a0, a1, &d1);
+        h2 = box_intersect_finite(T.org, T.rdir, tnear, b0, b1, &d2);
+    }
     unsigned k1 = fbits(a1.z), n1 = fbits(a1.w), k2 = fbits(b1.z), n2 = fbits(b1.w);
     if (d1 > d2) {
         bool th = h1; h1 = h2; h2 = th;
@@ -981,49 +1011,68 @@ OSLD bool trav_step(const RenderScene& S, Trav& T, int max_nodes)
     return finished;
 }
 // trav_step for a whole warp (rt_trace): every lane calls it, `active` says whether the lane holds a
-// ray.  Same per-ray visiting order; what changes is how the lanes are grouped.  The walk phase is a
-// warp-uniform loop that ends when the lanes holding a leaf outnumber the lanes still walking (or after
-// max_nodes visits): with the fixed node budget of trav_step the walkers thinned out to 8 of 32 lanes
-// while the others waited with their leaf (ncu source page, profiles/ncu_r02_rt_trace_sass.txt).
-OSLD bool trav_step_warp(const RenderScene& S, Trav& T, bool active, int max_nodes)
+// ray.  Per ray the visiting order is trav_step's (the reference's); what changes is how the lanes are
+// grouped.  Each iteration the warp votes: if at least as many lanes want to visit an inner node as
+// hold an untested leaf triangle, the walkers visit one node, otherwise the leaf holders test one
+// triangle.  A lane moves between the two roles as its ray demands, the phase with more ready lanes
+// always runs, and leaves of different sizes no longer wait for each other.  (With trav_step's fixed
+// walk-then-leaf phases ncu's source page showed 7.7 of 32 lanes in the node visit and 14 in the
+// triangle test: profiles/ncu_r02_rt_trace_sass.txt.)  The call returns when every ray of the warp is
+// finished, after `budget` iterations, or - while the queue can still refill lanes - as soon as
+// `min_busy` or fewer lanes are busy.
+OSLD bool trav_step_warp(const RenderScene& S, Trav& T, bool active, int budget, int min_busy)
 {
     int sp = T.sp;
     Hit result = T.hit;
-    unsigned child = 0, nprims = 0;
-    bool walking = active && sp != 0;
-    for (int it = 0; it < max_nodes; ++it) {
-        const unsigned wm = __ballot_sync(0xffffffffu, walking);
-        if (wm == 0u)
+    unsigned child = T.lchild, nprims = active ? T.lnprims : 0u;
+    bool done = !active || (nprims == 0u && sp == 0);
+    const bool z0 = T.kz == 0, z1 = T.kz == 1;
+    for (int it = 0; it < budget; ++it) {
+        const bool inleaf  = nprims != 0u;
+        const bool walking = !done && !inleaf;
+        const int nw = __popc(__ballot_sync(0xffffffffu, walking)), nl = __popc(__ballot_sync(0xffffffffu, inleaf));
+        if (nw + nl <= min_busy)
             break;
-        const unsigned lm = __ballot_sync(0xffffffffu, nprims != 0u);
-        if (__popc(wm) < __popc(lm))
-            break;
-        if (walking) {
-            // pop to the next entry the current hit has not culled
-            bool got = false;
-            while (sp != 0) {
-                --sp;
-                if (result.t < stk_dist(T, sp))
-                    continue;
-                stk_get(T, sp, child, nprims);
-                got = true;
-                break;
+        if (nw >= nl) {
+            if (walking) {
+                // pop to the next entry the current hit has not culled
+                bool got = false;
+                while (sp != 0) {
+                    --sp;
+                    if (result.t < stk_dist(T, sp))
+                        continue;
+                    stk_get(T, sp, child, nprims);
+                    got = true;
+                    break;
+                }
+                if (!got)
+                    done = true;
+                else if (nprims == 0u) {
+                    trav_visit(S, T, child, result.t, sp);
+                    done = sp == 0;
+                }
             }
-            if (got && nprims == 0u)
-                trav_visit(S, T, child, result.t, sp);
-            walking = nprims == 0u && sp != 0;
+        } else if (inleaf) {
+            // two triangles per vote (the reference's leaves hold 8 on average)
+            trav_tri(S, T, child, z0, z1, result);
+            if (nprims > 1u)
+                trav_tri(S, T, child + 1u, z0, z1, result);
+            const unsigned k = nprims > 1u ? 2u : 1u;
+            child += k;
+            nprims -= k;
+            // a shadow ray only asks "is anything strictly closer than tmax0": answered by the first hit
+            if (T.anyhit && result.t < T.tmax0) {
+                nprims = 0u;
+                done   = true;
+            } else if (nprims == 0u)
+                done = sp == 0;
         }
     }
-    bool finished = false;
-    if (nprims) {
-        trav_leaf(S, T, child, nprims, result);
-        finished = T.anyhit && result.t < T.tmax0;
-        finished = finished || sp == 0;
-    } else
-        finished = active && sp == 0;
-    T.sp  = sp;
-    T.hit = result;
-    return finished;
+    T.sp      = sp;
+    T.hit     = result;
+    T.lchild  = child;
+    T.lnprims = nprims;
+    return active && done;
 }
 OSLD Hit scene_intersect(const RenderScene& S, unsigned* stk, int stride, V3 org, V3 dir, float tmax,
                          unsigned skip1, unsigned skip2, int anyhit = 0)
@@ -1827,7 +1876,7 @@ extern "C" __global__ void __launch_bounds__(256) rt_generate(const __grid_const
 // while the other lanes keep walking (rays of very different length share a warp; without
 // this the warp idles on its longest ray: ncu showed 7 of 32 lanes active in round 1).
 #ifndef OSLD_TRACE_CHUNK
-#define OSLD_TRACE_CHUNK 8    // inner nodes a lane may walk per step before the leaf phase
+#define OSLD_TRACE_CHUNK 64   // iterations (node visits or triangle tests) of one trav_step_warp call
 #endif
 #ifndef OSLD_TRACE_REFILL
 #define OSLD_TRACE_REFILL 16  // idle lanes that trigger a refill from the queues (sweep: profiles/render_tune_r02.txt)
@@ -1893,7 +1942,7 @@ extern "C" __global__ void __launch_bounds__(OSLD_TRACE_BLOCK) rt_trace(const __
         }
         if (hm == 0u)
             break;
-        if (trav_step_warp(S, T, have, OSLD_TRACE_CHUNK) && have) {
+        if (trav_step_warp(S, T, have, OSLD_TRACE_CHUNK, exhausted ? 0 : 32 - OSLD_TRACE_REFILL)) {
             if (phase == 0) {
                 float4* rec = L.rec + (size_t)slot * OSLD_PATH_QUADS;
                 rec[4]      = make_float4(T.hit.t, T.hit.u, T.hit.v, __int_as_float((int)T.hit.id));
