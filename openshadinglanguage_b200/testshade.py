@@ -290,7 +290,8 @@ def run_command(spec, oso, make_group, globals_fn, userdata_fn=None):
         a = arena[off // 4 * n:(off // 4 + nch) * n].reshape(n, nch)
         if is_int:
             a = a.view(np.int32).astype(np.float32)
-        imgs[v] = (fn, a.reshape(spec["yres"], spec["xres"], nch).copy())
+        # keyed by (variable, file): the same variable may be written to several files (testsuite/shaderglobals)
+        imgs[v if fn == "null" else v + "|" + fn] = (fn, a.reshape(spec["yres"], spec["xres"], nch).copy())
     return dict(text=out, images=imgs)
 
 

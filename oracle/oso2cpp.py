@@ -196,6 +196,8 @@ class Layer:
                 v = [v]
             if s.t.base not in ("int", "string"):
                 v = [struct.unpack("f", struct.pack("f", float(x)))[0] for x in v]
+            if s.t.base in ("color", "point", "vector", "normal") and not s.t.arr and len(v) == 1:
+                v = list(v) * 3         # a float value for a triple parameter (shadingsys.cpp:2880-3035)
             s.vals = list(v)
             s.initexpr = False
             s.override = True

@@ -276,6 +276,25 @@ def test_gpu_render_media_vs_oracle(b200lib, cuda_device, case):
         _check_thresholds(got, _golden(case))
 
 
+@pytest.mark.gpu
+def test_gpu_render_config3_full_size_bit_exact(b200lib, cuda_device):
+    """BASELINE config 3 at the size the bench times (render-cornell 1024 x 1024, 64 spp: 67 M paths
+    through the regenerating wavefront, 2 Mi slots reused ~32 times, the tail kernel at the end): every
+    pixel equals the scalar oracle's, bit for bit, in strict mode; fast mode (what bench.py times)
+    stays within the reference test's image thresholds of it."""
+    from openshadinglanguage_b200 import api
+    S, A = _scene("render-cornell")
+    res, aa = 1024, 8
+    want = oracle.OracleRender(S, A, helpers.oso).render(res, res, aa, nthreads=os.cpu_count() or 8)
+    R = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=0,sort=1")
+    got = R.render()
+    assert R.stats["paths"] == res * res * aa * aa and R.stats["slots"] < R.stats["paths"]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+        "max |d| = %g, differing pixels %d" % (np.abs(got - want).max(), (got != want).any(axis=2).sum())
+    fast = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=1,sort=1").render()
+    _check_thresholds(fast, want)
+
+
 def test_media_module_is_specialised(b200lib):
     """Only scenes whose materials create medium_vdf / anisotropic_vdf closures carry the per-slot
     medium stack and the free-flight code."""

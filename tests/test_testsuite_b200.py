@@ -42,7 +42,7 @@ def test_manifest_covers_the_batched_testsuite():
     assert len(MANIFEST) == 171
     c = collections.Counter(e["status"] for e in MANIFEST.values())
     assert set(c) <= {"pass", "harness", "oslc", "codegen", "oracle", "mismatch"}
-    assert c["pass"] >= 80, c
+    assert c["pass"] >= 81, c
     for d, e in MANIFEST.items():
         assert (e["status"] == "pass") == os.path.exists(os.path.join(DIR, d + ".json")), d
         assert e["status"] == "pass" or e["reason"], d
@@ -54,7 +54,7 @@ def test_bundle_commands_parse_and_compile(b200lib, d):
     product's generator and NVRTC to an sm_100a cubin (no GPU needed)."""
     from openshadinglanguage_b200 import testshade as tsh
     b, _ = _bundle(d)
-    for cmd in b["commands"][:2]:
+    for cmd in [c for c in b["commands"] if not c.startswith("\x00echo ")][:2]:
         spec = tsh.parse_command(cmd)
         assert not spec["unsupported"], spec["unsupported"]
         layers = [dict(oso=b["oso"][l["shader"]], name=l["name"], params=l["params"]) for l in spec["layers"]]
@@ -90,6 +90,9 @@ def test_reference_testsuite_directory_through_the_device(b200lib, cuda_device, 
 
     texts, images = [], {}
     for cmd in b["commands"]:
+        if cmd.startswith("\x00echo "):         # an `echo TEXT >> out.txt` line of run.py between the commands
+            texts.append(cmd[6:])
+            continue
         r = tsh.run_command(tsh.parse_command(cmd), lambda name: b["oso"][name], DeviceRunner, b200lib.grid_globals)
         if r["text"]:
             texts.append(r["text"])

@@ -39,7 +39,7 @@ def commands_of(d):
     def stub(name):
         def f(*a, **k):
             cmds.append((name, a[0] if a else ""))
-            return ""
+            return "\x00%d\x00" % (len(cmds) - 1)     # placeholder: keeps the order inside `command`
         return f
     ns = {k: stub(k) for k in ("testshade", "oslc", "testrender", "oiiotool", "oslinfo", "maketx", "idiff",
                                "testoptix", "diff_command", "oiio_app")}
@@ -51,7 +51,21 @@ def commands_of(d):
         exec(open("run.py").read(), ns)
     finally:
         os.chdir(cwd)
-    return cmds, {k: ns[k] for k in ("outputs", "failthresh", "failpercent", "hardfail", "allowfailures")}
+    # run.py may interleave `echo TEXT>> out.txt` lines with the tool commands (error-dupes): they become
+    # ("echo", TEXT) entries at their place in the sequence
+    seq = []
+    for part in re.split(r"(\x00\d+\x00)", ns["command"] if isinstance(ns.get("command"), str) else ""):
+        m = re.fullmatch(r"\x00(\d+)\x00", part)
+        if m:
+            seq.append(cmds[int(m.group(1))])
+            continue
+        for line in part.split("\n"):
+            e = re.match(r"\s*echo\s+(.*?)\s*>>\s*out\.txt", line)
+            if e:
+                seq.append(("echo", e.group(1).strip("\"'")))
+    used = {id(c) for c in seq}
+    seq += [c for c in cmds if id(c) not in used]        # commands run.py did not append to `command`
+    return seq, {k: ns[k] for k in ("outputs", "failthresh", "failpercent", "hardfail", "allowfailures")}
 
 
 def read_image(path):
@@ -104,8 +118,8 @@ def main():
             entry.update(status="harness", reason="run.py: %s" % e)
             continue
         tools_used = sorted({t for t, _ in cmds})
-        shade = [a for t, a in cmds if t == "testshade"]
-        if not shade or set(tools_used) - {"testshade", "oslc"}:
+        shade = [a if t == "testshade" else "\x00echo " + a for t, a in cmds if t in ("testshade", "echo")]
+        if not any(t == "testshade" for t, _ in cmds) or set(tools_used) - {"testshade", "oslc", "echo"}:
             entry.update(status="harness", reason="uses " + ",".join(tools_used))
             continue
         entry["commands"] = shade
@@ -120,7 +134,8 @@ def main():
                     failed = failed or "%s: %s" % (f, str(e).split("\n")[0][:200])
         specs = []
         try:
-            specs = [tsh.parse_command(a) for a in shade]
+            specs = [dict(echo=a[6:], unsupported=[], layers=[]) if a.startswith("\x00echo ") else tsh.parse_command(a)
+                     for a in shade]
         except Exception as e:
             entry.update(status="harness", reason="command line: %s" % e)
             continue
@@ -152,6 +167,8 @@ def main():
             return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1", userdata=descs)
         try:
             for s in specs:
+                if "echo" in s:
+                    continue
                 layers = [dict(oso=oso[l["shader"]], name=l["name"], params=l["params"]) for l in s["layers"]]
                 g = product_group(layers, s["connections"], (), s)
                 assert g.cubin[:4] == b"\x7fELF"
@@ -174,6 +191,9 @@ def main():
         try:
             texts, images = [], {}
             for s in specs:
+                if "echo" in s:
+                    texts.append(s["echo"])
+                    continue
                 r = tsh.run_command(s, lambda name: oso[name], OracleRunner, oracle_globals)
                 if r["text"]:
                     texts.append(r["text"])
