@@ -1570,6 +1570,14 @@ Gen::emit_op(const Opcode& op)
                 w(R(op.args[2]) + " = sg.shadeindex;");
                 w(res + " = 1;");
                 done = true;
+            } else if ((name == "shader:shadername" || name == "shader:layername" || name == "shader:groupname")
+                       && dst.type.base == Base::String) {
+                // folded at optimisation time when the name is a constant (constfold_getattribute, constfold.cpp)
+                const std::string& val = name == "shader:shadername" ? L->m.shadername
+                                         : name == "shader:layername" ? L->layername : g.name;
+                w(R(op.args[2]) + " = " + std::to_string(g.intern(val)) + ";");
+                w(res + " = 1;");
+                done = true;
             } else
                 for (const UserData& u : g.userdata)
                     if (!done && u.name == name && u.ncomp == dst.type.ncomp() && u.is_int == (dst.type.base == Base::Int)

@@ -79,7 +79,7 @@ import shlex
 
 _IGNORED_FLAGS = {"-t": 1, "--threads": 1, "-O0": 0, "-O1": 0, "-O2": 0, "--llvm_opt": 1, "--batched": 0,
                   "--stats": 0, "--runstats": 0, "--debugnan": 0, "--debuguninit": 0, "--no-output-placement": 0,
-                  "--shadeimage": 0, "--noshadeimage": 0, "--groupname": 1, "-groupname": 1, "--jbufferMB": 1,
+                  "--shadeimage": 0, "--noshadeimage": 0, "--jbufferMB": 1,
                   "--warmup": 0, "--locale": 1, "--use_rs_bitcode": 0, "--texoptions": 1, "-texoptions": 1}
 _UNSUPPORTED_FLAGS = {"-v": 0, "--debug": 0, "--debug2": 0, "--group": 1, "-group": 1, "--archivegroup": 1,
                       "--entry": 1, "--entryoutput": 1, "--oslquery": 0, "--print-groupdata": 0,
@@ -145,7 +145,7 @@ def parse_command(argstr):
     spec = dict(xres=1, yres=1, center=False, layers=[], connections=[], outputs=[], dataformat=None,
                 vary_pdxdy=False, vary_udxdy=False, vary_vdxdy=False, raytype="camera", iters=1,
                 uscale=1.0, vscale=1.0, uoffset=0.0, voffset=0.0, userdata=[], options="",
-                userdata_isconnected=False, unsupported=[])
+                userdata_isconnected=False, unsupported=[], groupname="")
     pending, layername = {}, None
     i = 0
 
@@ -194,6 +194,8 @@ def parse_command(argstr):
             spec[base[2:]] = True
         elif base in ("--raytype", "-raytype"):
             spec["raytype"] = take(1)[0]
+        elif base in ("--groupname", "-groupname"):
+            spec["groupname"] = take(1)[0]
         elif base in ("--iters", "-iters"):
             spec["iters"] = int(take(1)[0])
         elif base in ("--scaleuv", "-scaleuv", "--scalest"):
@@ -282,9 +284,14 @@ def run_command(spec, oso, make_group, globals_fn, userdata_fn=None):
     outs = [dict(name=v, offset=off * n, stride=4 * nch, derivs=False) for v, _, off, nch, _ in images]
     g = make_group(layers, spec["connections"], outs, spec)
     text = g.run(n, var, uni, arena)
-    out = "\n".join(lines + ([text.rstrip("\n")] if text.strip("\n") else [])) * 1
+    body = text[:-1] if text.endswith("\n") else text     # keep the empty lines the error handler adds
+    out = "\n".join(lines + ([body] if text.strip("\n") else [])) * 1
     if spec["iters"] > 1 and text.strip("\n"):
-        out = "\n".join(lines + [text.rstrip("\n")] * spec["iters"])
+        out = "\n".join(lines + [body] * spec["iters"])
+    if not spec["outputs"]:
+        # without -o testshade shades the default output "Cout" into a null image and its run ends with an
+        # empty line (visible in goldens of several commands: testsuite/error-dupes, getattribute-shader)
+        out += "\n"
     imgs = {}
     for v, fn, off, nch, is_int in images:
         a = arena[off // 4 * n:(off // 4 + nch) * n].reshape(n, nch)

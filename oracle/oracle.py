@@ -290,9 +290,9 @@ def hash_(inp):
 class OracleGroup:
     """layers: list of dict(oso=<text>, name=<layername>, params={...})"""
 
-    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=(), textures=None):
+    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=(), textures=None, name="group"):
         ls = [oso2cpp.Layer(l["oso"], l["name"], l.get("params")) for l in layers]
-        self.group = oso2cpp.Group(ls, connections, outputs)
+        self.group = oso2cpp.Group(ls, connections, outputs, name=name)
         self.so = oso2cpp.build_group(self.group, opt=opt, extra_flags=flags)
         self.lib = ctypes.CDLL(self.so)
         self.lib.oracle_run_mt.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong, ctypes.c_int]
@@ -306,8 +306,9 @@ class OracleGroup:
         self.lib.oracle_run_mt(ctypes.byref(L), n, nthreads)
         return output
 
-    def run_capture(self, n, varying, uniform, output=None, shadeindex=None):
+    def run_capture(self, n, varying, uniform, output=None, shadeindex=None, error_repeats=False):
         L, keep = make_launch(n, varying, uniform, output, shadeindex)
+        self.lib.oracle_set_error_repeats(1 if error_repeats else 0)
         return self.lib.oracle_run_capture(ctypes.byref(L), 0, n).decode()
 
 

@@ -1393,6 +1393,13 @@ class Gen:
             if name == "shading:index" and dst.t.base == "int":
                 self.w("%s = sg.shadeindex; %s = 1;" % (self.R(dst), res))
                 return
+            # folded at optimisation time when the name is a constant (constfold_getattribute,
+            # constfold.cpp: "shader:shadername" / "shader:layername" / "shader:groupname")
+            shader_attr = {"shader:shadername": self.l.m.name, "shader:layername": self.l.name,
+                           "shader:groupname": self.g.name}
+            if name in shader_attr and dst.t.base == "string":
+                self.w("%s = %s; %s = 1;" % (self.R(dst), cstr(shader_attr[name]), res))
+                return
             if dst.t.base in ("int", "float") or dst.t.triple:
                 self.w("%s = bind_userdata(L, sg, %s, %s) ? 1 : 0;" % (res, cstr(name), self.R(dst)))
                 return
@@ -1581,6 +1588,7 @@ extern "C" void oracle_run_mt(const Launch* L, long long n, int nthreads)
     }
     for (auto& t : th) t.join();
 }
+extern "C" void oracle_set_error_repeats(int v) { oracle_error_repeats() = v; }
 extern "C" const char* oracle_run_capture(const Launch* L, long long begin, long long end)
 {
     static std::string buf;

@@ -164,7 +164,9 @@ def main():
         def product_group(layers, conns, outs, spec):
             arena, descs = ob.pack_userdata(helpers.testshade_userdata(
                 spec["xres"] * spec["yres"], *ob.grid_globals(spec["xres"], spec["yres"]), extra=spec["userdata"]))
-            return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1", userdata=descs)
+            return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1" + (
+                ",error_repeats=1" if "error_repeats=1" in spec["options"] else ""), userdata=descs,
+                                  name=spec.get("groupname") or "group")
         try:
             for s in specs:
                 if "echo" in s:
@@ -181,13 +183,13 @@ def main():
 
         class OracleRunner:
             def __init__(self, layers, conns, outs, spec):
-                self.g = oracle.OracleGroup(layers, conns, outs)
+                self.g = oracle.OracleGroup(layers, conns, outs, name=spec.get("groupname") or "group")
                 self.spec = spec
 
             def run(self, n, var, uni, arena):
                 uni = dict(uni)
                 uni["userdata"] = helpers.testshade_userdata(n, var, uni, extra=self.spec["userdata"])
-                return self.g.run_capture(n, var, uni, arena)
+                return self.g.run_capture(n, var, uni, arena, error_repeats="error_repeats=1" in self.spec["options"])
         try:
             texts, images = [], {}
             for s in specs:
