@@ -168,6 +168,7 @@ parse_oso(const std::string& text)
                 size_t br = tn.find('[');
                 if (br != std::string::npos) {
                     s.type.arraylen = atoi(tn.c_str() + br + 1);
+                    s.unsized       = tn.compare(br, 2, "[]") == 0;   // "type[]": sized below / by the instance
                     tn              = tn.substr(0, br);
                 }
                 if (!parse_base(tn, s.type.base))
@@ -198,6 +199,15 @@ parse_oso(const std::string& text)
                     s.svals.push_back(v);
                 else
                     s.fvals.push_back(strtof(v.c_str(), nullptr));
+            }
+            if (s.unsized) {
+                // an unsized array parameter is as long as its default list until an instance value or a
+                // connection gives it another length (instance.cpp:250-330)
+                size_t nvals    = s.type.base == Base::Int ? s.ivals.size()
+                                  : (s.type.base == Base::String ? s.svals.size() : s.fvals.size());
+                TypeSpec elem   = s.type;
+                elem.arraylen   = 0;
+                s.type.arraylen = std::max(1, (int)(nvals / (size_t)std::max(1, elem.ncomp())));
             }
             m.byname[s.name] = (int)m.syms.size();
             m.syms.push_back(std::move(s));
@@ -299,6 +309,13 @@ Group::add_layer(const std::string& oso_text, const std::string& layername,
             if (s.type.is_triple() && s.fvals.size() == 1)
                 s.fvals.assign(3, s.fvals[0]);
         }
+        if (s.unsized) {
+            size_t nvals    = s.type.base == Base::Int ? s.ivals.size()
+                              : (s.type.base == Base::String ? s.svals.size() : s.fvals.size());
+            TypeSpec elem   = s.type;
+            elem.arraylen   = 0;
+            s.type.arraylen = std::max(1, (int)(nvals / (size_t)std::max(1, elem.ncomp())));
+        }
         s.initexpr = false;
     }
     layers.push_back(std::move(l));
@@ -318,6 +335,8 @@ Group::connect(const std::string& sl, const std::string& sp, const std::string& 
         throw std::runtime_error("ConnectShaders: layer '" + sl + "' has no parameter '" + sp + "'");
     if (ds < 0 || !layers[di].m.syms[ds].is_param())
         throw std::runtime_error("ConnectShaders: layer '" + dl + "' has no parameter '" + dp + "'");
+    if (layers[di].m.syms[ds].unsized && layers[si].m.syms[ss].type.arraylen)
+        layers[di].m.syms[ds].type.arraylen = layers[si].m.syms[ss].type.arraylen;
     layers[si].m.syms[ss].connected_down = true;
     layers[di].m.syms[ds].conn_layer     = si;
     layers[di].m.syms[ds].conn_sym       = ss;

@@ -45,6 +45,7 @@ struct Symbol {
     std::vector<int> ivals;
     std::vector<std::string> svals;
     bool initexpr       = false;
+    bool unsized        = false;  // declared "type[]": length from the default list, the instance value or a connection
     bool interpolated   = false;  // lockgeom=0: the renderer may supply the value per point (userdata)
     bool has_derivs     = false;
     bool written        = false;

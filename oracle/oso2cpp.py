@@ -152,7 +152,11 @@ def parse_oso(text):
                     vals.append(t)
                 else:
                     vals.append(struct.unpack("f", struct.pack("f", float(t)))[0])
+            unsized = arr < 0
+            if unsized:     # "type[]": as long as its default list until an instance value or a connection resizes it
+                arr = max(1, len(vals) // {"matrix": 16, "color": 3, "point": 3, "vector": 3, "normal": 3}.get(base, 1))
             s = OSym(name, symtype, OType(base, arr), vals)
+            s.unsized = unsized
             s.initexpr = "%initexpr" in hints
             s.interpolated = "%meta{int,lockgeom,0}" in hints   # [[ int lockgeom = 0 ]]
             m.byname[name] = s
@@ -198,6 +202,10 @@ class Layer:
                 v = [struct.unpack("f", struct.pack("f", float(x)))[0] for x in v]
             if s.t.base in ("color", "point", "vector", "normal") and not s.t.arr and len(v) == 1:
                 v = list(v) * 3         # a float value for a triple parameter (shadingsys.cpp:2880-3035)
+            if getattr(s, "unsized", False):
+                # an unsized array parameter takes the length of the instance value (instance.cpp:250-330)
+                nc = {"matrix": 16, "color": 3, "point": 3, "vector": 3, "normal": 3}.get(s.t.base, 1)
+                s.t = OType(s.t.base, max(1, len(v) // nc))
             s.vals = list(v)
             s.initexpr = False
             s.override = True
@@ -219,6 +227,8 @@ class Group:
         for (sl, sp, dl, dp) in connections:
             s, d = byname[sl], byname[dl]
             ssym, dsym = s.m.byname[sp], d.m.byname[dp]
+            if getattr(dsym, "unsized", False) and ssym.t.arr:
+                dsym.t = OType(dsym.t.base, ssym.t.arr)     # ... or the length of what is connected to it
             dsym.connected_from = (s.idx, ssym)
             ssym.connected_down = True
             self.connections.append((s.idx, ssym, d.idx, dsym))

@@ -1813,9 +1813,11 @@ class Compiler:
         params = []
         for p in sh.params:
             t = p.type
+            unsized = t.arr < 0
             if t.arr < 0 and p.init is not None and p.init.kind == "initlist":
                 t = T(t.base, len(p.init.items))
             s = self.declare(p.name, t, "oparam" if p.out else "param")
+            s.unsized = unsized      # written as "type[]": the instance value or a connection sets the length
             s.meta = p.meta
             params.append((p, s, t))
         for p, s, t in params:
@@ -1873,6 +1875,8 @@ class Compiler:
 
         def symline(s):
             tname = repr(s.t)
+            if getattr(s, "unsized", False):
+                tname = "%s[]" % s.t.base
             line = "%s\t%s\t%s" % (s.symtype, tname, s.name)
             if s.symtype == "const":
                 line += "\t" + fmtvals(s) + "\t"

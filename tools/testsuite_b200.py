@@ -129,7 +129,11 @@ def main():
         for f in sorted(os.listdir(os.path.join(TS, d))):
             if f.endswith(".osl"):
                 try:
-                    oso[f[:-4]] = mini_oslc.compile_osl(os.path.join(TS, d, f), inc + [os.path.join(TS, d)])
+                    text = mini_oslc.compile_osl(os.path.join(TS, d, f), inc + [os.path.join(TS, d)])
+                    # oslc names the .oso after the SHADER, not the source file (compassign-bool's
+                    # varying_le.osl defines shader varying_lt and the other way round)
+                    m = re.search(r"^(?:shader|surface|displacement|volume)\s+(\S+)", text, re.M)
+                    oso[m.group(1) if m else f[:-4]] = text
                 except Exception as e:
                     failed = failed or "%s: %s" % (f, str(e).split("\n")[0][:200])
         specs = []
