@@ -116,6 +116,29 @@ def static_profile(key):
         return None
 
 
+def render_roofline(key):
+    """Per-kernel figures of a testrender workload from the round's ncu --set full captures (static: one
+    capture per kernel under profiles/, not measured by this run).  The wavefront kernels are bound by SIMT
+    issue and latency, not by HBM or tensor throughput, so what is reported is lane occupancy, issue-slot and
+    FP32 / ALU pipe utilisation, and DRAM bytes per path-step of the launch."""
+    prof = static_profile(key)
+    if not prof:
+        return None
+    out = {"bound": "simt issue / latency (neither HBM nor tensor bound)", "kernels": {},
+           "source": "static: profiles/ncu_metrics_r02.json (%s)" % prof.get("note", "")}
+    for k, v in prof.items():
+        if not isinstance(v, dict) or "duration_us" not in v or k.endswith("_before_vote_scheduler"):
+            continue
+        out["kernels"][k] = {
+            "duration_us": v["duration_us"], "active_lanes_of_32": v.get("active_lanes_per_instruction"),
+            "issue_slots_busy_pct": v.get("issue_slots_busy_pct"), "achieved_occupancy_pct": v.get("achieved_occupancy_pct"),
+            "pipe_fma_pct": v.get("pipe_fma_pct"), "pipe_alu_pct": v.get("pipe_alu_pct"),
+            "dram_throughput_pct": v.get("dram_throughput_pct"),
+            "dram_bytes_per_path_step": round((v.get("dram_read_MB", 0) + v.get("dram_write_MB", 0)) * 1e6 / (2 << 20), 1),
+            "local_memory_instructions": v.get("local_load_instructions", 0) + v.get("local_store_instructions", 0)}
+    return out
+
+
 class CpuGrid:
     """Restated reference algorithm (oracle port) over the FULL grid of a workload."""
 
@@ -421,7 +444,7 @@ def main():
                 "bounce_steps": st["bounce_iterations"], "launches": st["launches"], "tail_ms": st["tail_ms"],
                 "per_rank_last_repeat": {"device_ms,tail_ms,bounce_steps": per_rank},
                 "pool_slots": st["slots"], "image_mean": float(himg.mean()) if rank == 0 else None,
-                "ncu": static_profile(rname.split("-")[0] + "-" + rname.split("-")[1])}
+                "roofline": render_roofline(rname.split("-")[0] + "-" + rname.split("-")[1])}
             if rank == 0 and not args.no_cpu_baseline:
                 from oracle import oracle as _o
                 ncpu = os.cpu_count() or 1
