@@ -87,6 +87,14 @@ SHADERS = {
     "mxmedglass_glossy": "render-mx-medium-vdf-glass/glossy.osl",
     "mxaniso_anisotropic": "render-mx-anisotropic-vdf/anisotropic.osl",
     "spithin_glossy_glass": "render-spi-thinlayer/glossy_glass.osl",   # thinlayer closure (spi::ThinLayerLobe)
+    # bump mapping through Dx / Dy / calculatenormal of displaced P, glass and metal around it
+    "bumptest": "render-bumptest/bumptest.osl",
+    "bump_glass": "render-bumptest/glass.osl",
+    "bump_metal": "render-bumptest/metal.osl",
+    # raytype() queries per bounce kind, <Background /> without a resolution
+    "raytype_envmap": "render-raytypes/raytype-envmap.osl",
+    "raytypes_glossy": "render-raytypes/glossy.osl",
+    "raytypes_magic": "render-raytypes/magic.osl",
     # this repo's own test shaders (path relative to the repo root)
     "glossy_mix": "repo:tests/shaders/glossy_mix.osl",
     "color_ops": "repo:tests/shaders/color_ops.osl",
@@ -135,6 +143,8 @@ SCENES = {
     "mx_medium_vdf_glass.xml": ("render-mx-medium-vdf-glass/scene.xml", {"glossy": "mxmedglass_glossy"}),
     "mx_anisotropic_vdf.xml": ("render-mx-anisotropic-vdf/scene.xml",
                                {"anisotropic": "mxaniso_anisotropic", "envmap": "mxmed_envmap"}),
+    "bumptest.xml": ("render-bumptest/bumptest.xml", {"glass": "bump_glass", "metal": "bump_metal"}),
+    "raytypes.xml": ("render-raytypes/scene.xml", {"glossy": "raytypes_glossy", "magic": "raytypes_magic"}),
     "spi_thinlayer.xml": ("render-spi-thinlayer/scene.xml", {"glossy_glass": "spithin_glossy_glass", "envmap": "mf_envmap"}),
 }
 # input images read by texture() (test input data, copied byte for byte)
@@ -163,6 +173,8 @@ RENDERS = {
     "render-mx-medium-vdf-glass": "render-mx-medium-vdf-glass/ref/out.exr",
     "render-mx-anisotropic-vdf": "render-mx-anisotropic-vdf/ref/out.exr",
     "render-spi-thinlayer": "render-spi-thinlayer/ref/out.exr",
+    "render-bumptest": "render-bumptest/ref/out.exr",
+    "render-raytypes": "render-raytypes/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
