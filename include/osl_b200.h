@@ -97,7 +97,10 @@ typedef struct b200_connection {
 /* SymLocationDesc with arena = Outputs (oslexec.h:69-105): where a renderer
  * output lands: output_base + offset + stride*shadeindex; derivs => val,dx,dy */
 typedef struct b200_symloc {
-    const char* name;  /* "layer.param" or "param" */
+    const char* name;  /* "layer.param" or "param"; also the name of a ShaderGlobals field the entry layer
+                        * uses ("P", "N", "u" ...): execute() hands the globals back as the shaders left them
+                        * (ShaderGlobals is in / out of ShadingSystem::execute, oslexec.h:833) - how a
+                        * displacement shader's P reaches the renderer (simpleraytracer.cpp:1365-1384) */
     long long offset;
     long long stride;
     int derivs;

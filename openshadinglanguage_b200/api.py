@@ -593,3 +593,25 @@ def tile_pixels(tiles):
         ys.append(yy.ravel())
         xs.append(xx.ravel())
     return np.concatenate(ys), np.concatenate(xs)
+
+
+def device_displacer(oso_lookup, device=0, options="fma=1"):
+    """-> callable for render.scene.Scene.prepare(displace=...): runs a displacement group over the vertex
+    batch on the GPU (one b200_group_execute; the ShaderGlobals field P comes back as a renderer output),
+    the counterpart of SimpleRaytracer::prepare_geometry's per-vertex ShadingSystem::execute
+    (src/testrender/simpleraytracer.cpp:1365-1384)."""
+    import torch
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+
+    def run(layers, conns, g, n):
+        ls = [dict(oso=oso_lookup(l["shader"]), name=l["name"], params=l["params"]) for l in layers]
+        grp = ShaderGroup(ls, conns, [dict(name="P", offset=0, stride=12, derivs=False)], options=options)
+        planes = {k: np.ascontiguousarray(v.T).reshape(-1) if v.ndim == 2 else np.ascontiguousarray(v)
+                  for k, v in g.items()}
+        dvar = {k: torch.from_numpy(v).to(dev) for k, v in planes.items()}
+        out = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        grp.execute(n, dvar, {}, out, device=dev.index or 0)
+        torch.cuda.synchronize(dev)
+        return out.cpu().numpy()
+    return run
+

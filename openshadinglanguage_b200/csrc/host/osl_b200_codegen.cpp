@@ -257,6 +257,11 @@ private:
                 if (s.has_derivs) {
                     g.globals_read.insert(gi.dx);
                     g.globals_read.insert(gi.dy);
+                    // a global with derivatives that this layer WRITES ("P += ..." of a displacement
+                    // shader) lives in a layer-local Dv, loaded at entry and stored back at the end
+                    // (gen_layer); the accessor below is an rvalue
+                    if (s.written)
+                        return "gw_" + s.name;
                     return std::string(gi.expr) + "_d()";
                 }
                 return std::string(gi.expr);
@@ -1629,6 +1634,19 @@ Gen::gen_layer(int layer)
             w("const " + ctype(s) + " K_" + ident(s.name) + "[" + std::to_string(s.type.arraylen) + "] = {" + init + "};");
         }
     }
+    // written globals that carry derivatives: layer-local copies (see ref())
+    std::vector<std::string> written_globals;
+    for (Symbol& s : m.syms)
+        if (s.symtype == SymType::Global && s.written && s.has_derivs && s.name != "Ci") {
+            auto it = global_table().find(s.name);
+            if (it != global_table().end() && it->second.dx >= 0) {
+                g.globals_read.insert(it->second.field);
+                g.globals_read.insert(it->second.dx);
+                g.globals_read.insert(it->second.dy);
+                w(std::string(s.type.is_triple() ? "Dv" : "Df") + " gw_" + s.name + " = " + it->second.expr + "_d();");
+                written_globals.push_back(s.name);
+            }
+        }
     // the group entry runs earlier non-lazy layers unconditionally
     // (llvm_instance.cpp:1693-1720)
     if (layer == nlayers - 1)
@@ -1676,6 +1694,10 @@ Gen::gen_layer(int layer)
     if (mi != m.methods.end())
         emit_block(mi->second.first, mi->second.second, nullptr);
     w("layer_end:;");
+    for (const std::string& gn : written_globals) {
+        const std::string e = global_table().find(gn)->second.expr;
+        w(e + " = gw_" + gn + ".val; " + e + "_dx = gw_" + gn + ".dx; " + e + "_dy = gw_" + gn + ".dy;");
+    }
     // hand results to downstream layers (llvm_instance.cpp:1738-1802)
     for (const Connection& c : g.connections)
         if (c.srclayer == layer && !g.layers[c.dstlayer].unused)
@@ -1939,7 +1961,12 @@ Gen::run()
     auto out_expr = [&](int k) {
         L  = &g.layers[g.outputs[k].first];
         li = g.outputs[k].first;
-        return ref(li, out_sym(k));
+        const Symbol& s = out_sym(k);
+        if (s.symtype == SymType::Global) {   // a ShaderGlobals field handed back: read it from sg, not from a layer local
+            const GlobalInfo& gi = global_table().at(s.name);
+            return std::string(gi.expr) + (s.out.derivs && gi.dx >= 0 && s.has_derivs ? "_d()" : "");
+        }
+        return ref(li, s);
     };
     std::string B = "%BLOCK%";
     long long stage_words = 0;

@@ -361,6 +361,18 @@ Group::add_output(const std::string& name, long long offset, long long stride, b
             }
         }
     }
+    if (si < 0 && dot == std::string::npos && !layers.empty()) {
+        // A ShaderGlobals field the entry layer uses: execute() hands the globals back to the renderer
+        // as the shaders left them (ShaderGlobals is in / out, oslexec.h:833; a displacement shader's
+        // "P += ..." is read back this way, simpleraytracer.cpp:1365-1384).  Here the renderer asks for
+        // the field by name like for any other output.
+        int l = (int)layers.size() - 1;
+        int s = layers[l].m.find(name);
+        if (s >= 0 && layers[l].m.syms[s].symtype == SymType::Global) {
+            li = l;
+            si = s;
+        }
+    }
     if (li < 0 || si < 0)
         throw std::runtime_error("renderer output '" + name + "' not found in group");
     Symbol& s    = layers[li].m.syms[si];

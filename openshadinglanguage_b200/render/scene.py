@@ -68,6 +68,7 @@ class Scene:
         self.background_shader = -1
         self.background_resolution = 0
         self.options = {}         # <Option name="int N"/> (max_bounces, rr_depth, ...)
+        self.displacements = {}   # material index -> (layers, connections) of its displacement group
 
     # -- geometry (scene.cpp) -------------------------------------------------
     def add_sphere(self, c, r, shader, resolution=64):
@@ -300,11 +301,79 @@ class Scene:
         return arr, indices
 
     # -- finalize ---------------------------------------------------------------
-    def prepare(self):
+    def displace_geometry(self, verts, normals, tris, displace):
+        """SimpleRaytracer::prepare_geometry (simpleraytracer.cpp:1300-1420): every corner of every triangle
+        whose material has a displacement group is one shading point (P, N, Ng, u, v, I, surfacearea) of
+        that group; the shader's P is handed back, a vertex ends at the average of its corners, and smooth
+        normals are rebuilt from the displaced triangles.  `displace(layers, connections, globals, n)`
+        runs the group over the n points (the hot path itself: a ShaderGroup over an SoA batch) and returns
+        the P the shaders left, float32 [n, 3].  The float32 sums run in the reference's order."""
+        ntri = len(tris)
+        n_tris = np.array(self.n_triangles, np.int32).reshape(-1, 3)
+        uv_tris = np.array(self.uv_triangles, np.int32).reshape(-1, 3)
+        uvs = np.array(self.uvs if self.uvs else [[0, 0]], f32).reshape(-1, 2)
+        shaderids = np.array(self.shaderids, np.int32)
+        p = verts[tris]                                              # [ntri, 3 corners, 3]
+        cr = np.cross((p[:, 0] - p[:, 1]).astype(f32), (p[:, 0] - p[:, 2]).astype(f32)).astype(f32)
+        ln = np.sqrt((cr[:, 0] * cr[:, 0] + cr[:, 1] * cr[:, 1] + cr[:, 2] * cr[:, 2]).astype(f32)).astype(f32)
+        area = (f32(0.5) * ln).astype(f32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            Ng = np.where(ln[:, None] > 0, cr / ln[:, None], cr).astype(f32)          # Imath normalize()
+        smooth = n_tris[:, 0] >= 0
+        N = np.where(smooth[:, None, None], normals[np.maximum(n_tris, 0)], Ng[:, None, :]).astype(f32)
+        has_uv = uv_tris[:, 0] >= 0
+        uv = np.where(has_uv[:, None, None], uvs[np.maximum(uv_tris, 0)], f32(0)).astype(f32)
+        newp = p.copy()
+        has_smooth_normals = False
+        for mat, (layers, conns) in sorted(self.displacements.items()):
+            sel = np.nonzero(shaderids == mat)[0]
+            if not len(sel):
+                continue
+            has_smooth_normals |= bool(smooth[sel].any())
+            P = p[sel].reshape(-1, 3)
+            d = (P - self.eye.astype(f32)).astype(f32)
+            dl = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(f32)).astype(f32)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                I = np.where(dl[:, None] > 0, d / dl[:, None], d).astype(f32)
+            g = dict(P=P, N=N[sel].reshape(-1, 3), Ng=np.repeat(Ng[sel], 3, axis=0), I=I,
+                     u=uv[sel].reshape(-1, 2)[:, 0].copy(), v=uv[sel].reshape(-1, 2)[:, 1].copy(),
+                     surfacearea=np.repeat(area[sel], 3))
+            out = np.asarray(displace(layers, conns, g, len(P)), f32).reshape(-1, 3, 3)
+            newp[sel] = out
+        disp = np.zeros_like(verts)
+        valence = np.zeros(len(verts), np.int32)
+        flat = tris.reshape(-1)
+        np.add.at(valence, flat, 1)
+        for c in range(3):              # float32 sums in corner order a, b, c of ascending triangles
+            np.add.at(disp[:, c], flat, newp.reshape(-1, 3)[:, c])
+        used = valence > 0
+        disp[used] = (disp[used] / valence[used, None].astype(f32)).astype(f32)
+        disp[~used] = verts[~used]
+        if has_smooth_normals:
+            q = disp[tris]
+            cr2 = np.cross((q[:, 0] - q[:, 1]).astype(f32), (q[:, 0] - q[:, 2]).astype(f32)).astype(f32)
+            acc = np.zeros_like(normals)
+            idx = n_tris[smooth].reshape(-1)
+            src = np.repeat(cr2[smooth], 3, axis=0)
+            for c in range(3):
+                np.add.at(acc[:, c], idx, src[:, c])
+            l2 = np.sqrt((acc[:, 0] * acc[:, 0] + acc[:, 1] * acc[:, 1] + acc[:, 2] * acc[:, 2]).astype(f32)).astype(f32)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                normals = np.where(l2[:, None] > 0, acc / l2[:, None], acc).astype(f32)
+        return disp.astype(f32), normals
+
+    def prepare(self, displace=None):
+        """displace: required when the scene has displacement groups, see displace_geometry()."""
         verts = np.array(self.verts, f32).reshape(-1, 3)
         tris = np.array(self.triangles, np.int32).reshape(-1, 3)
+        normals = np.array(self.normals if self.normals else [[0, 0, 0]], f32).reshape(-1, 3)
+        if self.displacements:
+            if displace is None:
+                raise ValueError("the scene has displacement shaders: prepare(displace=...) must run them")
+            verts, normals = self.displace_geometry(verts, normals, tris, displace)
+            self.verts = [v for v in verts]      # the BVH builder below reads self.verts
         out = dict(
-            verts=verts, normals=np.array(self.normals if self.normals else [[0, 0, 0]], f32).reshape(-1, 3),
+            verts=verts, normals=normals,
             uvs=np.array(self.uvs if self.uvs else [[0, 0]], f32).reshape(-1, 2),
             triangles=tris, n_triangles=np.array(self.n_triangles, np.int32).reshape(-1, 3),
             uv_triangles=np.array(self.uv_triangles, np.int32).reshape(-1, 3),
@@ -391,7 +460,12 @@ def load_scene(xmlfile):
             layers, conns = parse_group_spec(text)
             name = a.get("name")
             if name and name in named:
-                sc.materials[named[name]] = (layers, conns)
+                # a second group under a known name updates that material: its displacement or its surface
+                # (simpleraytracer.cpp:472-490)
+                if a.get("type", "surface") == "displacement":
+                    sc.displacements[named[name]] = (layers, conns)
+                else:
+                    sc.materials[named[name]] = (layers, conns)
                 continue
             if name:
                 named[name] = len(sc.materials)

@@ -245,6 +245,11 @@ class Group:
                     if pn in l.m.byname and l.m.byname[pn].symtype in ("param", "oparam"):
                         lay = l
                         break
+                if lay is None and pn in self.layers[-1].m.byname and \
+                        self.layers[-1].m.byname[pn].symtype == "global":
+                    # a ShaderGlobals field as the entry layer left it (globals are in / out of execute():
+                    # a displacement shader's P, simpleraytracer.cpp:1365-1384)
+                    lay = self.layers[-1]
                 if lay is None:
                     raise KeyError("renderer output %s not found" % nm)
             sym = lay.m.byname[pn]

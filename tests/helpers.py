@@ -220,3 +220,25 @@ def testshade_userdata(n, var, uni, extra=()):
         a = np.asarray(val)
         ents.append(dict(name=name, data=np.tile(a.reshape(1, -1), (n, 1))))
     return ents
+
+
+def _displace_planes(g):
+    """displace_geometry()'s per-point globals ([n, 3] rows / [n]) -> SoA planes (x[n] y[n] z[n])."""
+    return {k: np.ascontiguousarray(v.T).reshape(-1) if v.ndim == 2 else np.ascontiguousarray(v) for k, v in g.items()}
+
+
+def oracle_displace(layers, conns, g, n):
+    """Scene.prepare(displace=...): the displacement group over the n vertex points on the CPU oracle."""
+    from oracle import oracle
+    ls = [dict(oso=oso(l["shader"]), name=l["name"], params=l["params"]) for l in layers]
+    og = oracle.OracleGroup(ls, conns, [dict(name="P", offset=0, stride=12, derivs=False)])
+    out = np.zeros((n, 3), np.float32)
+    og.run(n, _displace_planes(g), {}, out, nthreads=os.cpu_count() or 8)
+    return out
+
+
+def device_displace(dev, options="fma=0"):
+    """The same through the product (api.device_displacer): one b200_group_execute over the vertex batch,
+    P read back as a renderer output."""
+    from openshadinglanguage_b200 import api
+    return api.device_displacer(oso, dev, options)

@@ -52,7 +52,10 @@ CASES = {"render-cornell": ("cornell.xml", 128, 128, 4), "render-bunny": ("bunny
          "render-mx-medium-vdf-glass": ("mx_medium_vdf_glass.xml", 98, 98, 16),
          # bump mapping: P displaced by noise, N from calculatenormal() (Dx / Dy of the displaced P), glass
          # spheres of two IORs over a metal floor, max_bounces 10
-         "render-bumptest": ("bumptest.xml", 128, 128, 4)}
+         "render-bumptest": ("bumptest.xml", 128, 128, 4),
+         # a displacement group (P += fBm(P) * N) run over the 786 k vertex corners of a 262 k-triangle sphere
+         # before the BVH is built: the hot path itself as the renderer's geometry pass, P read back as an output
+         "render-displacement": ("displacement.xml", 128, 128, 8)}
 # Scattering / absorbing media: free-flight sampling, Henyey-Greenstein phase function.  The
 # reference calls libm's expf / logf here; the device evaluates them in double and rounds once,
 # which differs from glibc in the last bit of a small share of calls, so these two compare within
@@ -101,7 +104,7 @@ def _scene(case):
     if case not in _cache:
         S = sc.load_scene(os.path.join(SCENES, (CASES.get(case) or TEXTURED_CASES.get(case) or MEDIA_CASES.get(case)
                                                 or OWN_CASES[case])[0]))
-        _cache[case] = (S, S.prepare())
+        _cache[case] = (S, S.prepare(displace=helpers.oracle_displace))
     return _cache[case]
 
 
@@ -173,6 +176,7 @@ def test_oracle_matches_reference_golden_render(case):
                  "render-mx-dielectric-glass": 0.74,            # 0.770 (whole frame 0.930)
                  "render-mx-generalized-schlick-glass": 0.95,   # 0.969
                  "render-mx-medium-vdf-glass": 0.87,            # 0.897
+                 "render-displacement": 0.97,                   # 0.989
                  "render-mx-medium-vdf": 0.98,                  # 0.990
                  "render-mx-anisotropic-vdf": 0.985}            # 0.997
     assert exact > exact_min.get(case, 0.99), exact
@@ -317,6 +321,22 @@ def test_gpu_render_config3_full_size_bit_exact(b200lib, cuda_device):
         "max |d| = %g, differing pixels %d" % (np.abs(got - want).max(), (got != want).any(axis=2).sum())
     fast = api.Renderer(S, A, helpers.oso, res, res, aa, options="fma=1,sort=1").render()
     _check_thresholds(fast, want)
+
+
+@pytest.mark.gpu
+def test_gpu_displacement_pass_bit_exact_vs_oracle(b200lib, cuda_device):
+    """SimpleRaytracer::prepare_geometry's displacement pass through the product: the displacement group
+    over every corner of every triangle (one b200_group_execute of 786 k points, the ShaderGlobals field P
+    handed back as a renderer output) gives the oracle's vertices and normals bit for bit."""
+    S = sc.load_scene(os.path.join(SCENES, "displacement.xml"))
+    verts = np.array(S.verts, np.float32).reshape(-1, 3)
+    normals = np.array(S.normals, np.float32).reshape(-1, 3)
+    tris = np.array(S.triangles, np.int32).reshape(-1, 3)
+    v0, n0 = S.displace_geometry(verts, normals, tris, helpers.oracle_displace)
+    v1, n1 = S.displace_geometry(verts, normals, tris, helpers.device_displace(cuda_device))
+    assert np.abs(v0 - verts).max() > 0.05                      # the sphere did move
+    assert np.array_equal(v0.view(np.uint32), v1.view(np.uint32))
+    assert np.array_equal(n0.view(np.uint32), n1.view(np.uint32))
 
 
 def test_media_module_is_specialised(b200lib):

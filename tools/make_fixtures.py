@@ -91,6 +91,7 @@ SHADERS = {
     "bumptest": "render-bumptest/bumptest.osl",
     "bump_glass": "render-bumptest/glass.osl",
     "bump_metal": "render-bumptest/metal.osl",
+    "disp": "render-displacement/disp.osl",            # displacement group: P += fBm(P) * N, run over the vertices
     # raytype() queries per bounce kind, <Background /> without a resolution
     "raytype_envmap": "render-raytypes/raytype-envmap.osl",
     "raytypes_glossy": "render-raytypes/glossy.osl",
@@ -144,6 +145,7 @@ SCENES = {
     "mx_anisotropic_vdf.xml": ("render-mx-anisotropic-vdf/scene.xml",
                                {"anisotropic": "mxaniso_anisotropic", "envmap": "mxmed_envmap"}),
     "bumptest.xml": ("render-bumptest/bumptest.xml", {"glass": "bump_glass", "metal": "bump_metal"}),
+    "displacement.xml": "render-displacement/scene.xml",
     "raytypes.xml": ("render-raytypes/scene.xml", {"glossy": "raytypes_glossy", "magic": "raytypes_magic"}),
     "spi_thinlayer.xml": ("render-spi-thinlayer/scene.xml", {"glossy_glass": "spithin_glossy_glass", "envmap": "mf_envmap"}),
 }
@@ -175,6 +177,7 @@ RENDERS = {
     "render-spi-thinlayer": "render-spi-thinlayer/ref/out.exr",
     "render-bumptest": "render-bumptest/ref/out.exr",
     "render-raytypes": "render-raytypes/ref/out.exr",
+    "render-displacement": "render-displacement/ref/out.exr",
 }
 IMAGES = {
     # golden name: testsuite-relative image
