@@ -181,12 +181,13 @@ class Scene:
         self.last_index.append(len(self.triangles))
 
     # -- BVH (bvh.cpp) --------------------------------------------------------
-    def build_bvh(self):
-        """The scene BVH, built by the library's native builder (b200_build_bvh)."""
+    def build_bvh(self, verts=None):
+        """The scene BVH, built by the library's native builder (b200_build_bvh); verts: the displaced
+        vertices when the scene has displacement groups."""
         import ctypes
         from .. import api
         L = api.lib()
-        verts = np.ascontiguousarray(np.array(self.verts, f32).reshape(-1, 3))
+        verts = np.ascontiguousarray(np.array(self.verts if verts is None else verts, f32).reshape(-1, 3))
         tris = np.ascontiguousarray(np.array(self.triangles, np.int32).reshape(-1, 3))
         n = len(tris)
         nodes = np.zeros((max(2 * n - 1, 1), 8), f32)
@@ -371,14 +372,13 @@ class Scene:
             if displace is None:
                 raise ValueError("the scene has displacement shaders: prepare(displace=...) must run them")
             verts, normals = self.displace_geometry(verts, normals, tris, displace)
-            self.verts = [v for v in verts]      # the BVH builder below reads self.verts
         out = dict(
             verts=verts, normals=normals,
             uvs=np.array(self.uvs if self.uvs else [[0, 0]], f32).reshape(-1, 2),
             triangles=tris, n_triangles=np.array(self.n_triangles, np.int32).reshape(-1, 3),
             uv_triangles=np.array(self.uv_triangles, np.int32).reshape(-1, 3),
             shaderids=np.array(self.shaderids, np.int32))
-        nodes, indices = self.build_bvh()
+        nodes, indices = self.build_bvh(verts)
         out["bvh_nodes"], out["bvh_indices"] = nodes, indices
         # per-triangle mesh id, per-mesh area (prepare_lights)
         meshids = np.zeros(len(tris), np.int32)
