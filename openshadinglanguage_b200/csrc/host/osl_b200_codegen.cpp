@@ -272,6 +272,46 @@ private:
     }
     std::string R(int si) { return ref(li, S(si)); }
 
+    // Would the reference's constant folder (constfold.cpp, runtimeoptimize.cpp) know this value at
+    // optimisation time?  Constants and instance values do; so does a temporary or local written exactly
+    // once, outside any conditional or loop, by a foldable op whose inputs fold.
+    bool folds_to_constant(int si, int depth)
+    {
+        const Symbol& s = S(si);
+        if (s.const_value())
+            return true;
+        if (depth > 16 || (s.symtype != SymType::Temp && s.symtype != SymType::Local) || s.type.arraylen)
+            return false;
+        static const std::set<std::string> foldable
+            = { "assign", "add",  "sub",  "mul",   "div",   "mod",   "neg",    "abs",    "fabs",  "sqrt", "inversesqrt",
+                "pow",    "min",  "max",  "floor", "ceil",  "round", "trunc",  "sign",   "clamp", "mix",  "color",
+                "point",  "vector", "normal", "float", "int", "compref", "dot", "cross", "length", "normalize",
+                "sin",    "cos",  "tan",  "exp",   "exp2",  "log",   "log2",   "eq",     "neq",   "lt",   "gt",
+                "le",     "ge",   "and",  "or",    "not",   "bitand", "bitor", "xor",    "shl",   "shr",  "compl",
+                "step",   "smoothstep", "select" };
+        const std::vector<Opcode>& ops = L->m.ops;
+        int writer = -1, nwrites = 0;
+        for (size_t i = 0; i < ops.size(); ++i)
+            for (size_t a = 0; a < ops[i].args.size(); ++a)
+                if (ops[i].args[a] == si && ops[i].writes((int)a)) {
+                    ++nwrites;
+                    writer = (int)i;
+                }
+        if (nwrites != 1 || !foldable.count(ops[writer].name) || !ops[writer].jumps.empty())
+            return false;
+        for (size_t j = 0; j < ops.size(); ++j) {   // inside the body of an if / loop: not folded
+            int last = -1;
+            for (int t : ops[j].jumps)
+                last = std::max(last, t);
+            if ((int)j < writer && writer < last)
+                return false;
+        }
+        for (size_t a = 0; a < ops[writer].args.size(); ++a)
+            if (ops[writer].reads((int)a) && !ops[writer].writes((int)a) && !folds_to_constant(ops[writer].args[a], depth + 1))
+                return false;
+        return true;
+    }
+
     // default-value initialiser expressions, one per array element
     std::vector<std::string> initvals(const Symbol& s)
     {
@@ -1302,8 +1342,11 @@ Gen::emit_op(const Opcode& op)
         w(R(op.args[0]) + " = "
           + std::to_string((A(1).conn_layer >= 0 ? 1 : 0) + ((A(1).connected_down || A(1).out.placed) ? 2 : 0)) + ";");
     } else if (n == "isconstant") {
+        // 1 when the runtime optimizer would have reduced the argument to a constant (constfold.cpp):
+        // constants, instance parameter values, and top-level temporaries computed from those by
+        // foldable arithmetic
         need(2);
-        w(R(op.args[0]) + " = " + std::to_string(A(1).const_value() ? 1 : 0) + ";");
+        w(R(op.args[0]) + " = " + std::to_string(folds_to_constant(op.args[1], 0) ? 1 : 0) + ";");
     } else if (n == "hash") {
         size_t nin = op.args.size() - 1;
         std::string e;

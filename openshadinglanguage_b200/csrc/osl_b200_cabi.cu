@@ -491,13 +491,18 @@ b200_group_journal(b200_group* g, int device)
         return g->journal_text.c_str();
     }
     unsigned head[2] = { 0, 0 };
-    cudaMemcpy(head, it->second, sizeof head, cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(head, it->second, sizeof head, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(B200_ERR_CUDA, std::string("journal read-back: ") + cudaGetErrorString(cudaGetLastError()));
+        return g->journal_text.c_str();
+    }
     size_t used = head[0];
     if (used > (size_t)g->journal_words - 2)
         used = (size_t)g->journal_words - 2;
     std::vector<unsigned> rec(used);
-    if (used)
-        cudaMemcpy(rec.data(), it->second + 2, used * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (used && cudaMemcpy(rec.data(), it->second + 2, used * sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(B200_ERR_CUDA, std::string("journal read-back: ") + cudaGetErrorString(cudaGetLastError()));
+        return g->journal_text.c_str();
+    }
     struct Ref {
         unsigned si, seq;
         size_t at;
@@ -537,7 +542,8 @@ b200_group_journal(b200_group* g, int device)
     }
     if (head[1])
         g->journal_text += "[journal overflow: output truncated; raise the group option journal=WORDS]\n";
-    cudaMemset(it->second, 0, sizeof(unsigned) * (2 + used));
+    if (cudaMemset(it->second, 0, sizeof(unsigned) * (2 + used)) != cudaSuccess)
+        fail(B200_ERR_CUDA, std::string("journal reset: ") + cudaGetErrorString(cudaGetLastError()));
     return g->journal_text.c_str();
 }
 

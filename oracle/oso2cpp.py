@@ -995,8 +995,32 @@ class Gen:
         v = (1 if s.connected_from is not None else 0) + (2 if (s.connected_down or s.renderer_output) else 0)
         self.w("%s = %d;" % (self.R(d), v))
 
+    FOLDABLE = {"assign", "add", "sub", "mul", "div", "mod", "neg", "abs", "fabs", "sqrt", "inversesqrt", "pow",
+                "min", "max", "floor", "ceil", "round", "trunc", "sign", "clamp", "mix", "color", "point", "vector",
+                "normal", "float", "int", "compref", "dot", "cross", "length", "normalize", "sin", "cos", "tan",
+                "exp", "exp2", "log", "log2", "eq", "neq", "lt", "gt", "le", "ge", "and", "or", "not", "bitand",
+                "bitor", "xor", "shl", "shr", "compl", "step", "smoothstep", "select"}
+
+    def folds_to_constant(self, s, depth=0):
+        """What the reference's constant folder (constfold.cpp) knows at optimisation time: constants,
+        instance values, and top-level temporaries computed from those by foldable ops."""
+        if s.constval:
+            return True
+        if depth > 16 or s.symtype not in ("temp", "local") or s.t.arr:
+            return False
+        ops = self.l.m.ops
+        writers = [i for i, op in enumerate(ops) for a, c in zip(op.args, op.rw) if a is s and c in "wW"]
+        if len(writers) != 1:
+            return False
+        w = writers[0]
+        if ops[w].name not in self.FOLDABLE or ops[w].jumps:
+            return False
+        if any(j < w < max(op.jumps) for j, op in enumerate(ops) if op.jumps):
+            return False
+        return all(self.folds_to_constant(a, depth + 1) for a, c in zip(ops[w].args, ops[w].rw) if c == "r")
+
     def op_isconstant(self, op):
-        self.w("%s = %d;" % (self.R(op.args[0]), 1 if op.args[1].constval else 0))
+        self.w("%s = %d;" % (self.R(op.args[0]), 1 if self.folds_to_constant(op.args[1]) else 0))
 
     def op_hash(self, op):
         A = op.args
