@@ -80,12 +80,11 @@ import shlex
 _IGNORED_FLAGS = {"-t": 1, "--threads": 1, "-O0": 0, "-O1": 0, "-O2": 0, "--llvm_opt": 1, "--batched": 0,
                   "--stats": 0, "--runstats": 0, "--debugnan": 0, "--debuguninit": 0, "--no-output-placement": 0,
                   "--shadeimage": 0, "--noshadeimage": 0, "--jbufferMB": 1,
-                  "--warmup": 0, "--locale": 1, "--use_rs_bitcode": 0, "--texoptions": 1, "-texoptions": 1}
+                  "--warmup": 0, "--locale": 1, "--raytype_opt": 0, "--groupoutputs": 0, "--use_rs_bitcode": 0, "--texoptions": 1, "-texoptions": 1}
 _UNSUPPORTED_FLAGS = {"-v": 0, "--debug": 0, "--debug2": 0, "--group": 1, "-group": 1, "--archivegroup": 1,
                       "--entry": 1, "--entryoutput": 1, "--oslquery": 0, "--print-groupdata": 0,
                       "--print-group-stats": 0, "--inbuffer": 0, "--expr": 1, "-expr": 1, "--reparam": 3,
-                      "-reparam": 3, "--groupoutputs": 0, "--print": 0, "--colorspace": 1, "-colorspace": 1,
-                      "--profile": 0, "--raytype_opt": 0}
+                      "-reparam": 3, "--profile": 0}
 
 
 def _float_list(s, n):
@@ -145,7 +144,7 @@ def parse_command(argstr):
     spec = dict(xres=1, yres=1, center=False, layers=[], connections=[], outputs=[], dataformat=None,
                 vary_pdxdy=False, vary_udxdy=False, vary_vdxdy=False, raytype="camera", iters=1,
                 uscale=1.0, vscale=1.0, uoffset=0.0, voffset=0.0, userdata=[], options="",
-                userdata_isconnected=False, unsupported=[], groupname="")
+                userdata_isconnected=False, unsupported=[], groupname="", colorspace="", print=False)
     pending, layername = {}, None
     i = 0
 
@@ -194,6 +193,10 @@ def parse_command(argstr):
             spec[base[2:]] = True
         elif base in ("--raytype", "-raytype"):
             spec["raytype"] = take(1)[0]
+        elif base == "--print":
+            spec["print"] = True                  # print every output value per pixel (save_outputs, testshade.cpp:1246-1290)
+        elif base in ("--colorspace", "-colorspace"):
+            spec["colorspace"] = take(1)[0]       # ShadingSystem attribute "colorspace"
         elif base in ("--groupname", "-groupname"):
             spec["groupname"] = take(1)[0]
         elif base in ("--iters", "-iters"):
@@ -288,6 +291,18 @@ def run_command(spec, oso, make_group, globals_fn, userdata_fn=None):
     out = "\n".join(lines + ([body] if text.strip("\n") else [])) * 1
     if spec["iters"] > 1 and text.strip("\n"):
         out = "\n".join(lines + [body] * spec["iters"])
+    if spec["print"]:
+        if text.strip("\n"):
+            raise NotImplementedError("--print together with shader printf output (interleaved per point)")
+        plines = []
+        for y in range(spec["yres"]):
+            for x in range(spec["xres"]):
+                plines.append("Pixel (%d, %d):" % (x, y))
+                for v, fn, off, nch, is_int in images:
+                    a = arena[off // 4 * n:(off // 4 + nch) * n].reshape(n, nch)[y * spec["xres"] + x]
+                    vals = a.view(np.int32) if is_int else a
+                    plines.append("  %s :%s" % (v, "".join((" %d" % t) if is_int else (" %g" % t) for t in vals)))
+        out = "\n".join([out] + plines) if out else "\n".join(plines)
     if not spec["outputs"]:
         # without -o testshade shades the default output "Cout" into a null image and its run ends with an
         # empty line (visible in goldens of several commands: testsuite/error-dupes, getattribute-shader)

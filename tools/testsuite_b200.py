@@ -68,13 +68,66 @@ def commands_of(d):
     return seq, {k: ns[k] for k in ("outputs", "failthresh", "failpercent", "hardfail", "allowfailures")}
 
 
+def read_exr_scanlines(path):
+    """Minimal OpenEXR reader for what OpenCV refuses (single-channel / oddly named channels): scan-line files,
+    NONE / ZIPS / ZIP compression, half or float channels.  -> float32 [h, w, nchannels], channels in file
+    (alphabetical) order."""
+    import struct
+    import zlib
+    d = open(path, "rb").read()
+    if d[:4] != b"\x76\x2f\x31\x01" or d[5] & 0x02:
+        raise IOError("not a scan-line OpenEXR file: " + path)
+    i, attrs = 8, {}
+    while d[i] != 0:
+        j = d.index(b"\0", i)
+        k = d.index(b"\0", j + 1)
+        size = struct.unpack_from("<i", d, k + 1)[0]
+        attrs[d[i:j].decode()] = d[k + 5:k + 5 + size]
+        i = k + 5 + size
+    i += 1
+    chans, c = [], attrs["channels"]
+    p = 0
+    while c[p] != 0:
+        q = c.index(b"\0", p)
+        chans.append((c[p:q].decode(), struct.unpack_from("<i", c, q + 1)[0]))     # name, 1 = half, 2 = float
+        p = q + 17
+    comp = attrs["compression"][0]
+    if comp not in (0, 2, 3) or any(t not in (1, 2) for _, t in chans):
+        raise IOError("unsupported OpenEXR flavour: " + path)
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    per = {0: 1, 2: 1, 3: 16}[comp]
+    nblocks = (h + per - 1) // per
+    offs = struct.unpack_from("<%dQ" % nblocks, d, i)
+    img = np.zeros((h, w, len(chans)), np.float32)
+    line_bytes = sum(w * (2 if t == 1 else 4) for _, t in chans)
+    for o in offs:
+        y, size = struct.unpack_from("<ii", d, o)
+        raw = d[o + 8:o + 8 + size]
+        nl = min(per, y1 - y + 1)
+        if comp and size < nl * line_bytes:
+            b = np.frombuffer(zlib.decompress(raw), np.uint8).astype(np.int32)
+            b = np.cumsum(np.concatenate([b[:1], b[1:] - 128]), dtype=np.int64).astype(np.uint8)   # predictor
+            half = (len(b) + 1) // 2
+            out = np.empty(len(b), np.uint8)
+            out[0::2], out[1::2] = b[:half], b[half:]                                              # de-interleave
+            raw = out.tobytes()
+        p = 0
+        for ln in range(nl):
+            for ci, (_, t) in enumerate(chans):
+                n = w * (2 if t == 1 else 4)
+                img[y - y0 + ln, :, ci] = np.frombuffer(raw[p:p + n], np.float16 if t == 1 else np.float32)
+                p += n
+    return img
+
+
 def read_image(path):
     if path.endswith(".exr"):
         os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
         import cv2
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         if img is None:
-            raise IOError("cannot read " + path)
+            return read_exr_scanlines(path), "float"
         if img.ndim == 3:
             img = img[..., ::-1] if img.shape[2] == 3 else img[..., [2, 1, 0, 3]]
         else:
@@ -169,7 +222,8 @@ def main():
             arena, descs = ob.pack_userdata(helpers.testshade_userdata(
                 spec["xres"] * spec["yres"], *ob.grid_globals(spec["xres"], spec["yres"]), extra=spec["userdata"]))
             return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1" + (
-                ",error_repeats=1" if "error_repeats=1" in spec["options"] else ""), userdata=descs,
+                ",error_repeats=1" if "error_repeats=1" in spec["options"] else "") + (
+                ",colorspace=" + spec["colorspace"] if spec.get("colorspace") else ""), userdata=descs,
                                   name=spec.get("groupname") or "group")
         try:
             for s in specs:
@@ -187,7 +241,8 @@ def main():
 
         class OracleRunner:
             def __init__(self, layers, conns, outs, spec):
-                self.g = oracle.OracleGroup(layers, conns, outs, name=spec.get("groupname") or "group")
+                self.g = oracle.OracleGroup(layers, conns, outs, name=spec.get("groupname") or "group", flags=(
+                    ('-DOSLO_COLORSPACE="%s"' % spec["colorspace"],) if spec.get("colorspace") else ()))
                 self.spec = spec
 
             def run(self, n, var, uni, arena):
