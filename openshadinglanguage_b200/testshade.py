@@ -83,8 +83,7 @@ _IGNORED_FLAGS = {"-t": 1, "--threads": 1, "-O0": 0, "-O1": 0, "-O2": 0, "--llvm
                   "--warmup": 0, "--locale": 1, "--raytype_opt": 0, "--groupoutputs": 0, "--use_rs_bitcode": 0, "--texoptions": 1, "-texoptions": 1}
 _UNSUPPORTED_FLAGS = {"-v": 0, "--debug": 0, "--debug2": 0, "--group": 1, "-group": 1, "--archivegroup": 1,
                       "--entry": 1, "--entryoutput": 1, "--oslquery": 0, "--print-groupdata": 0,
-                      "--print-group-stats": 0, "--inbuffer": 0, "--expr": 1, "-expr": 1, "--reparam": 3,
-                      "-reparam": 3, "--profile": 0}
+                      "--print-group-stats": 0, "--inbuffer": 0, "--expr": 1, "-expr": 1, "--profile": 0}
 
 
 def _float_list(s, n):
@@ -144,7 +143,7 @@ def parse_command(argstr):
     spec = dict(xres=1, yres=1, center=False, layers=[], connections=[], outputs=[], dataformat=None,
                 vary_pdxdy=False, vary_udxdy=False, vary_vdxdy=False, raytype="camera", iters=1,
                 uscale=1.0, vscale=1.0, uoffset=0.0, voffset=0.0, userdata=[], options="",
-                userdata_isconnected=False, unsupported=[], groupname="", colorspace="", print=False)
+                userdata_isconnected=False, unsupported=[], groupname="", colorspace="", print=False, reparams=[])
     pending, layername = {}, None
     i = 0
 
@@ -193,6 +192,10 @@ def parse_command(argstr):
             spec[base[2:]] = True
         elif base in ("--raytype", "-raytype"):
             spec["raytype"] = take(1)[0]
+        elif base in ("--reparam", "-reparam"):
+            # ShadingSystem::ReParameter after the first iteration (testshade.cpp:2245-2255)
+            layer, name, value = take(3)
+            spec["reparams"].append((layer, name, parse_param_value(a, value)[0]))
         elif base == "--print":
             spec["print"] = True                  # print every output value per pixel (save_outputs, testshade.cpp:1246-1290)
         elif base in ("--colorspace", "-colorspace"):
@@ -289,7 +292,20 @@ def run_command(spec, oso, make_group, globals_fn, userdata_fn=None):
     text = g.run(n, var, uni, arena)
     body = text[:-1] if text.endswith("\n") else text     # keep the empty lines the error handler adds
     out = "\n".join(lines + ([body] if text.strip("\n") else [])) * 1
-    if spec["iters"] > 1 and text.strip("\n"):
+    if spec["iters"] > 1 and spec["reparams"]:
+        # ReParameter between the first and the second iteration: the later iterations (whose outputs
+        # are the ones saved) see the new instance values.  The group is rebuilt with them here; a
+        # renderer with "interactive" parameters does the same through ShadingSystem::ReParameter.
+        layers2 = [dict(l, params=dict(l["params"])) for l in layers]
+        for lname, pname, value in spec["reparams"]:
+            for l in layers2:
+                if l["name"] == lname:
+                    l["params"][pname] = value
+        text2 = make_group(layers2, spec["connections"], outs, spec).run(n, var, uni, arena)
+        body2 = text2[:-1] if text2.endswith("\n") else text2
+        out = "\n".join(lines + ([body] if text.strip("\n") else [])
+                         + ([body2] * (spec["iters"] - 1) if text2.strip("\n") else []))
+    elif spec["iters"] > 1 and text.strip("\n"):
         out = "\n".join(lines + [body] * spec["iters"])
     if spec["print"]:
         if text.strip("\n"):
