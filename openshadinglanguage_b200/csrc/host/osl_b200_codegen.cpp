@@ -1101,7 +1101,9 @@ Gen::emit_op(const Opcode& op)
         need(2);
         const Symbol &d = A(0), &s = A(1);
         if (d.type.arraylen) {
-            for (int i = 0; i < d.type.arraylen; ++i)
+            // array = array copies as many elements as both have (llvm_assign_impl; testsuite/array-copy)
+            const int ncopy = s.type.arraylen ? std::min(d.type.arraylen, s.type.arraylen) : d.type.arraylen;
+            for (int i = 0; i < ncopy; ++i)
                 w("assign(" + R(op.args[0]) + "[" + std::to_string(i) + "], " + R(op.args[1]) + "["
                   + std::to_string(i) + "]);");
         } else if (d.type.base == Base::String) {

@@ -844,7 +844,9 @@ class Gen:
     def op_assign(self, op):
         d, s = op.args
         if d.t.arr:
-            for i in range(d.t.arr):
+            # array = array copies as many elements as both have (llvm_assign_impl, llvm_gen.cpp:770-800;
+            # testsuite/array-copy assigns an int[2] to an int[3])
+            for i in range(min(d.t.arr, s.t.arr or d.t.arr)):
                 self.w("assign(%s[%d], %s[%d]);" % (self.R(d), i, self.R(s), i))
         elif d.t.base == "matrix":
             if s.t.base == "matrix":

@@ -138,7 +138,9 @@ def assignable(a, b):
     if b.is_closure:
         return False
     if a.arr or b.arr:
-        return False
+        # arrays of one element type assign whatever their lengths: the shorter length is copied
+        # (testsuite/array-copy: int[3] = int[2])
+        return a.arr > 0 and b.arr > 0 and (a.base == b.base or (a.base in TRIPLES and b.base in TRIPLES))
     if a.is_float:
         return b.is_int
     if a.is_triple:
@@ -187,6 +189,10 @@ class Preprocessor:
     def __init__(self, include_dirs, defines=None):
         self.include_dirs = include_dirs
         self.macros = dict(defines or {})  # name -> (params|None, body)
+        # what oslc predefines (liboslcomp/oslcomp.cpp preprocess_buffer): the reference tree is 1.16.0
+        for name, body in (("OSL_VERSION_MAJOR", "1"), ("OSL_VERSION_MINOR", "16"), ("OSL_VERSION_PATCH", "0"),
+                           ("OSL_VERSION", "11600")):
+            self.macros.setdefault(name, (None, body))
         self.included = set()
 
     def find(self, name, curdir):
