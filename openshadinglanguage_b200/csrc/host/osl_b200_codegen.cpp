@@ -333,6 +333,8 @@ private:
                     out.push_back(s.has_derivs ? "mkdv(" + v + ")" : v);
                 } else if (s.type.base == Base::Matrix)
                     out.push_back(m44_literal(s.fvals, (size_t)e * 16));
+                else if (s.type.base == Base::Closure)
+                    out.push_back("0");   // closure-typed parameters default to the null closure (pool offset 0)
                 else
                     unsupported("default value of '" + s.name + "'");
             }

@@ -87,7 +87,10 @@ TEXTURED_CASES = {"render-microfacet": ("render_microfacet.xml", 160, 120, 8),
 TEXTURED_THRESH = {"render-microfacet": (0.04, 0.03), "render-spi-thinlayer": (0.02, 0.01), "render-raytypes": (0.01, 0.0)}
 # scenes of this repo (no reference golden image): the oracle restates the lobes
 # from shading.cpp and the device must equal the oracle.
-OWN_CASES = {"microfacet": ("microfacet.xml", 160, 120, 4)}   # ggx/beckmann x reflect/refract/both
+OWN_CASES = {"microfacet": ("microfacet.xml", 160, 120, 4),   # ggx/beckmann x reflect/refract/both
+             # material NETWORKS: closures travel through closure-typed output / input parameters of connected
+             # layers (one input left unconnected: the null closure), lazily run upstream layers
+             "closure-network": ("closure_network.xml", 160, 120, 4)}
 _cache = {}
 _oracle_frames = {}
 
@@ -360,6 +363,18 @@ def test_oracle_microfacet_scene_is_sane():
     img = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
     assert np.isfinite(img).all() and img.min() >= 0.0
     assert 0.01 < img.mean() < 1.0
+
+
+def test_oracle_closure_network_scene_is_sane():
+    """Closures handed from layer to layer through connected closure parameters: the mixes show up as the
+    expected colours (red/blue mix, green at 0.8 with the other input null, checker + glossy)."""
+    S, A = _scene("closure-network")
+    xml, xres, yres, aa = OWN_CASES["closure-network"]
+    img = oracle.OracleRender(S, A, helpers.oso).render(xres, yres, aa, nthreads=8)
+    assert np.isfinite(img).all() and img.min() >= 0.0
+    left, mid = img[55:65, 35:45].mean(axis=(0, 1)), img[55:65, 75:85].mean(axis=(0, 1))
+    assert left[0] > left[1] and left[2] > left[1]        # red and blue over green
+    assert mid[1] > 2 * mid[0] and mid[1] > 2 * mid[2]    # the green branch alone
 
 
 def test_glossy_module_is_specialised(b200lib):

@@ -104,6 +104,8 @@ SHADERS = {
     "constfold_ops": "repo:tests/shaders/constfold_ops.osl",
     "message_a": "repo:tests/shaders/message_a.osl",
     "message_b": "repo:tests/shaders/message_b.osl",
+    "closure_base": "repo:tests/shaders/closure_base.osl",    # closure-typed output parameter
+    "closure_mix": "repo:tests/shaders/closure_mix.osl",      # closure-typed input parameters
     "error_dupes_test": "error-dupes/test.osl",
     "userdata_custom_test": "userdata-custom/test.osl",
     "noise_generic_test": "noise-generic/test.osl",
