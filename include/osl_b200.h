@@ -15,7 +15,7 @@
 extern "C" {
 #endif
 
-#define OSL_B200_ABI_VERSION 2
+#define OSL_B200_ABI_VERSION 3
 #define B200_MAX_OUTPUTS 16  /* renderer outputs per group */
 
 /* status codes */
@@ -126,6 +126,18 @@ typedef struct b200_userdata {
     long long valid_stride;
 } b200_userdata;
 
+/* RendererServices::get_attribute (rendererservices.h:232-262) for values that do not vary over the
+ * batch - "camera:fov", "camera:resolution", object-independent renderer attributes: typed constants
+ * that getattribute() returns when the requested type matches (scalars, triples and arrays of them;
+ * strings).  A name known when the group is compiled folds to the value, a name computed by the
+ * shader is compared against the table at run time. */
+typedef struct b200_attribute {
+    const char* name;
+    int type;              /* 0 = int, 1 = float-based, 2 = string */
+    int nvalues;           /* ints / floats: number of scalars (a float[4] or a color = 4 / 3) */
+    const void* values;    /* int* / float* / const char** */
+} b200_attribute;
+
 /* ShaderGroupBegin ... ShaderGroupEnd (oslexec.h:634-650) */
 typedef struct b200_group_desc {
     const char* name;
@@ -141,6 +153,8 @@ typedef struct b200_group_desc {
     const char* options;
     int nuserdata;                 /* may be 0 */
     const b200_userdata* userdata;
+    int nattributes;               /* may be 0 (ABI 3) */
+    const b200_attribute* attributes;
 } b200_group_desc;
 
 typedef struct b200_group b200_group;

@@ -70,7 +70,8 @@ class _GroupDesc(ctypes.Structure):
                 ("layers", ctypes.POINTER(_Layer)), ("nconnections", ctypes.c_int),
                 ("connections", ctypes.POINTER(_Connection)), ("noutputs", ctypes.c_int),
                 ("outputs", ctypes.POINTER(_SymLoc)), ("options", ctypes.c_char_p),
-                ("nuserdata", ctypes.c_int), ("userdata", ctypes.POINTER(_UserData))]
+                ("nuserdata", ctypes.c_int), ("userdata", ctypes.POINTER(_UserData)),
+                ("nattributes", ctypes.c_int), ("attributes", ctypes.POINTER(_Param))]   # b200_attribute = b200_param layout
 
 
 def pack_userdata(entries):
@@ -208,9 +209,11 @@ class ShaderGroup:
     options:      'fma=0' selects strict IEEE evaluation (bit-parity mode)
     """
 
-    def __init__(self, layers, connections=(), outputs=(), options="", name="group", userdata=()):
+    def __init__(self, layers, connections=(), outputs=(), options="", name="group", userdata=(), attributes=None):
         """userdata: descriptor dicts (pack_userdata) of the per-point values the renderer supplies
-        for interpolated ([[ int lockgeom = 0 ]]) parameters."""
+        for interpolated ([[ int lockgeom = 0 ]]) parameters.
+        attributes: {name: value(s)} uniform renderer attributes getattribute() can return
+        (RendererServices::get_attribute for values that do not vary over the batch; b200_attribute)."""
         L = lib()
         keep = []
 
@@ -252,8 +255,22 @@ class ShaderGroup:
             cud[i].name, cud[i].ncomp, cud[i].is_int = cs(u["name"]), int(u["ncomp"]), int(u["is_int"])
             cud[i].offset, cud[i].stride, cud[i].derivs = int(u["offset"]), int(u["stride"]), int(u["derivs"])
             cud[i].valid_offset, cud[i].valid_stride = int(u["valid_offset"]), int(u["valid_stride"])
+        attributes = attributes or {}
+        cat = (_Param * max(1, len(attributes)))()
+        for j, (k, v) in enumerate(attributes.items()):
+            if not isinstance(v, (list, tuple, np.ndarray)):
+                v = [v]
+            if isinstance(v[0], str):
+                arr, t = (ctypes.c_char_p * len(v))(*[cs(x) for x in v]), 2
+            elif isinstance(v[0], (int, np.integer)) and not isinstance(v[0], bool):
+                arr, t = (ctypes.c_int * len(v))(*[int(x) for x in v]), 0
+            else:
+                arr, t = (ctypes.c_float * len(v))(*[float(x) for x in v]), 1
+            keep.append(arr)
+            cat[j].name, cat[j].type, cat[j].nvalues = cs(k), t, len(v)
+            cat[j].values = ctypes.cast(arr, ctypes.c_void_p)
         desc = _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, len(outputs), cout,
-                          cs(options), len(userdata), cud)
+                          cs(options), len(userdata), cud, len(attributes), cat)
         h = ctypes.c_void_p()
         _check(L.b200_group_compile(ctypes.byref(desc), ctypes.byref(h)))
         self._h = h
@@ -412,7 +429,7 @@ def _group_desc(layers, connections, name, options, keep):
     for i, (a, b, c, d) in enumerate(connections):
         cconn[i].srclayer, cconn[i].srcparam, cconn[i].dstlayer, cconn[i].dstparam = cs(a), cs(b), cs(c), cs(d)
     keep += [clayers, cconn]
-    return _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, 0, None, cs(options), 0, None)
+    return _GroupDesc(cs(name), len(layers), clayers, len(connections), cconn, 0, None, cs(options), 0, None, 0, None)
 
 
 class Renderer:

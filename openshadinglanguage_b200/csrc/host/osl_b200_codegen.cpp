@@ -1611,7 +1611,63 @@ Gen::emit_op(const Opcode& op)
         const Symbol& nm  = S(op.args[1]);
         const std::string res = R(op.args[0]);
         bool done = false;
-        if (op.args.size() == 3 && nm.type.base == Base::String && nm.const_value() && !nm.svals.empty()
+        // uniform renderer attributes (b200_attribute): the statements that hand attribute `at` to dst,
+        // or "" when the requested type does not match (get_attribute is asked for an exact TypeDesc)
+        auto attr_stores = [&](const Attribute& at) -> std::string {
+            const int n = (dst.type.arraylen ? dst.type.arraylen : 1) * dst.type.ncomp();
+            const std::string d = R((int)op.args.back());
+            std::string out;
+            if (dst.type.base == Base::Int) {
+                if (at.type != 0 || (int)at.ivals.size() != n)
+                    return "";
+                for (int k = 0; k < n; ++k)
+                    out += d + (dst.type.arraylen ? "[" + std::to_string(k) + "]" : "") + " = " + std::to_string(at.ivals[k]) + "; ";
+            } else if (dst.type.base == Base::String) {
+                if (at.type != 2 || (int)at.svals.size() != n)
+                    return "";
+                for (int k = 0; k < n; ++k)
+                    out += d + (dst.type.arraylen ? "[" + std::to_string(k) + "]" : "") + " = "
+                           + std::to_string(g.intern(at.svals[k])) + "; ";
+            } else if (dst.type.base == Base::Float || dst.type.is_triple()) {
+                if (at.type != 1 || (int)at.fvals.size() != n)
+                    return "";
+                const int per = dst.type.ncomp(), cnt = dst.type.arraylen ? dst.type.arraylen : 1;
+                for (int e = 0; e < cnt; ++e) {
+                    const std::string el = d + (dst.type.arraylen ? "[" + std::to_string(e) + "]" : "");
+                    if (per == 1)
+                        out += "assign(" + el + ", " + cfloat(at.fvals[e]) + "); ";
+                    else
+                        out += "assign(" + el + ", mkv(" + cfloat(at.fvals[3 * e]) + ", " + cfloat(at.fvals[3 * e + 1]) + ", "
+                               + cfloat(at.fvals[3 * e + 2]) + ")); ";
+                }
+            } else
+                return "";
+            return out;
+        };
+        if (op.args.size() == 3 && nm.type.base == Base::String && !g.attributes.empty() && !material_mode) {
+            if (nm.const_value() && !nm.svals.empty()) {
+                for (const Attribute& at : g.attributes)
+                    if (!done && at.name == nm.svals[0]) {
+                        const std::string st = attr_stores(at);
+                        if (!st.empty()) {
+                            w(st);
+                            w(res + " = 1;");
+                            done = true;
+                        }
+                    }
+            } else if (!nm.type.arraylen) {
+                // a name the shader computes: compared with the table at run time
+                w("{ const int nm_ = " + R(op.args[1]) + "; " + res + " = 0;");
+                for (const Attribute& at : g.attributes) {
+                    const std::string st = attr_stores(at);
+                    if (!st.empty())
+                        w("  if (nm_ == " + std::to_string(g.intern(at.name)) + ") { " + st + res + " = 1; }");
+                }
+                w("}");
+                done = true;
+            }
+        }
+        if (!done && op.args.size() == 3 && nm.type.base == Base::String && nm.const_value() && !nm.svals.empty()
             && !dst.type.arraylen && !material_mode) {
             const std::string& name = nm.svals[0];
             if (name == "osl:version" && dst.type.base == Base::Int) {

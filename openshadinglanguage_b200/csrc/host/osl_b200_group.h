@@ -139,8 +139,18 @@ struct UserData {
     long long offset = 0, stride = 0, valid_offset = -1, valid_stride = 0;
 };
 
+// a uniform renderer attribute (b200_attribute): what RendererServices::get_attribute answers for every point
+struct Attribute {
+    std::string name;
+    int type = 1;   // 0 int, 1 float, 2 string
+    std::vector<int> ivals;
+    std::vector<float> fvals;
+    std::vector<std::string> svals;
+};
+
 struct Group {
     std::string name;
+    std::vector<Attribute> attributes;         // uniform renderer attributes getattribute() can return
     std::vector<UserData> userdata;            // what the renderer supplies for interpolated params
     std::vector<OutCluster> clusters;
     bool stage_ok = false;  // every cluster dense and small enough to stage

@@ -326,6 +326,23 @@ b200_group_compile(const b200_group_desc* desc, b200_group** out)
             const b200_symloc& s = desc->outputs[i];
             G->g.add_output(s.name, s.offset, s.stride, s.derivs != 0);
         }
+        for (int i = 0; i < desc->nattributes && desc->attributes; ++i) {
+            const b200_attribute& a = desc->attributes[i];
+            if (!a.name || a.nvalues < 0 || a.type < 0 || a.type > 2 || (a.nvalues && !a.values))
+                return fail(B200_ERR_INVALID, "bad attribute description");
+            Attribute at;
+            at.name = a.name;
+            at.type = a.type;
+            for (int k = 0; k < a.nvalues; ++k) {
+                if (a.type == 0)
+                    at.ivals.push_back(((const int*)a.values)[k]);
+                else if (a.type == 1)
+                    at.fvals.push_back(((const float*)a.values)[k]);
+                else
+                    at.svals.push_back(((const char* const*)a.values)[k] ? ((const char* const*)a.values)[k] : "");
+            }
+            G->g.attributes.push_back(at);
+        }
         for (int i = 0; i < desc->nuserdata && desc->userdata; ++i) {
             const b200_userdata& u = desc->userdata[i];
             if (!u.name || (u.ncomp != 1 && u.ncomp != 3) || u.stride < 0 || (u.is_int && u.ncomp != 1))

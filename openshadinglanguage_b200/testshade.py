@@ -67,6 +67,17 @@ def grid_globals(xres, yres, center=False, vary_udxdy=False, vary_vdxdy=False, v
     return varying, uniform
 
 
+def harness_attributes(xres, yres):
+    """What testshade's SimpleRenderer answers to get_attribute for every point (simplerend.cpp:246-266,
+    330-346: camera set up as perspective, fov 90, hither 0.1, yon 1000 by testshade.cpp): the uniform
+    renderer attributes handed to the group as b200_attribute entries."""
+    aspect = float(np.float32(xres) / np.float32(yres))
+    return {"camera:resolution": [int(xres), int(yres)], "camera:projection": "perspective", "camera:fov": 90.0,
+            "camera:pixelaspect": 1.0, "camera:clip_near": 0.1, "camera:clip_far": 1000.0, "camera:clip": [0.1, 1000.0],
+            "camera:shutter_open": 0.0, "camera:shutter_close": 1.0, "camera:shutter": [0.0, 1.0],
+            "camera:screen_window": [-aspect, -1.0, aspect, 1.0]}
+
+
 # ---------------------------------------------------------------------------------------------
 # The testshade command line (src/testshade/testshade.cpp:705-905, 495-700) -> a group run
 # description, so that the reference's testsuite commands can be replayed through this library

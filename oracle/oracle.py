@@ -290,9 +290,10 @@ def hash_(inp):
 class OracleGroup:
     """layers: list of dict(oso=<text>, name=<layername>, params={...})"""
 
-    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=(), textures=None, name="group"):
+    def __init__(self, layers, connections=(), outputs=(), opt="-O2", flags=(), textures=None, name="group",
+                 attributes=None):
         ls = [oso2cpp.Layer(l["oso"], l["name"], l.get("params")) for l in layers]
-        self.group = oso2cpp.Group(ls, connections, outputs, name=name)
+        self.group = oso2cpp.Group(ls, connections, outputs, name=name, attributes=attributes)
         self.so = oso2cpp.build_group(self.group, opt=opt, extra_flags=flags)
         self.lib = ctypes.CDLL(self.so)
         self.lib.oracle_run_mt.argtypes = [ctypes.POINTER(Launch), ctypes.c_longlong, ctypes.c_int]

@@ -217,9 +217,11 @@ class Group:
     """layers: list[Layer]; connections: (srclayer, srcparam, dstlayer, dstparam);
     outputs: list of dict(name='layer.param' or 'param', offset, stride, derivs)."""
 
-    def __init__(self, layers, connections=(), outputs=(), name="group"):
+    def __init__(self, layers, connections=(), outputs=(), name="group", attributes=None):
         self.layers = list(layers)
         self.name = name
+        # uniform renderer attributes getattribute() can return: {name: int | float | str | list of those}
+        self.attributes = dict(attributes or {})
         for i, l in enumerate(self.layers):
             l.idx = i
         byname = {l.name: l for l in self.layers}
@@ -1426,6 +1428,46 @@ class Gen:
         A = op.args
         res, dst = self.R(A[0]), A[-1]
         nm = A[1]
+
+        def attr_stores(val):
+            """statements handing a uniform renderer attribute to dst, or None when the type asked for differs"""
+            v = list(val) if isinstance(val, (list, tuple)) else [val]
+            per = 3 if dst.t.triple else 1
+            cnt = dst.t.arr or 1
+            d = self.R(dst)
+            el = (lambda e: "%s[%d]" % (d, e)) if dst.t.arr else (lambda e: d)
+            if dst.t.base == "int":
+                if len(v) != cnt or not all(isinstance(x, int) and not isinstance(x, bool) for x in v):
+                    return None
+                return " ".join("%s = %d;" % (el(e), v[e]) for e in range(cnt))
+            if dst.t.base == "string":
+                if len(v) != cnt or not all(isinstance(x, str) for x in v):
+                    return None
+                return " ".join("%s = %s;" % (el(e), cstr(v[e])) for e in range(cnt))
+            if dst.t.base == "float" or dst.t.triple:
+                if len(v) != cnt * per or not all(isinstance(x, float) for x in v):
+                    return None
+                if per == 1:
+                    return " ".join("assign(%s, %s);" % (el(e), cfloat(v[e])) for e in range(cnt))
+                return " ".join("assign(%s, V3(%s, %s, %s));" % (el(e), cfloat(v[3 * e]), cfloat(v[3 * e + 1]),
+                                                                 cfloat(v[3 * e + 2])) for e in range(cnt))
+            return None
+
+        if len(A) == 3 and nm.t.base == "string" and self.g.attributes:
+            if nm.constval:
+                st = attr_stores(self.g.attributes[nm.vals[0]]) if nm.vals[0] in self.g.attributes else None
+                if st:
+                    self.w("%s %s = 1;" % (st, res))
+                    return
+            elif not nm.t.arr:
+                # a name the shader computes: compared with the renderer's table at run time
+                self.w("{ const char* nm_ = %s; %s = 0;" % (self.R(nm), res))
+                for k, val in self.g.attributes.items():
+                    st = attr_stores(val)
+                    if st:
+                        self.w("  if (nm_ && !strcmp(nm_, %s)) { %s %s = 1; }" % (cstr(k), st, res))
+                self.w("}")
+                return
         if len(A) == 3 and nm.t.base == "string" and nm.constval and not dst.t.arr:
             name = nm.vals[0]
             if name == "osl:version" and dst.t.base == "int":

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(b200lib):
     assert len(syms) >= 14
     for s in syms:
         assert hasattr(L, s), "libosl_b200.so does not export %s" % s
-    assert L.b200_abi_version() == 2
+    assert L.b200_abi_version() == 3
 
 
 @pytest.mark.parametrize("case", ["noise", "pnoise", "cellnoise", "noise-perlin"])

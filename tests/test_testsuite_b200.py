@@ -42,7 +42,7 @@ def test_manifest_covers_the_batched_testsuite():
     assert len(MANIFEST) == 171
     c = collections.Counter(e["status"] for e in MANIFEST.values())
     assert set(c) <= {"pass", "harness", "oslc", "codegen", "oracle", "mismatch"}
-    assert c["pass"] >= 95, c
+    assert c["pass"] >= 96, c
     for d, e in MANIFEST.items():
         assert (e["status"] == "pass") == os.path.exists(os.path.join(DIR, d + ".json")), d
         assert e["status"] == "pass" or e["reason"], d
@@ -81,7 +81,8 @@ def test_reference_testsuite_directory_through_the_device(b200lib, cuda_device, 
             self.g = b200lib.ShaderGroup(layers, conns, outs, options="fma=0,journal=1" + (
                 ",error_repeats=1" if "error_repeats=1" in spec["options"] else "") + (
                 ",colorspace=" + spec["colorspace"] if spec.get("colorspace") else ""), userdata=descs,
-                                  name=spec.get("groupname") or "group")
+                                  name=spec.get("groupname") or "group",
+                                  attributes=tsh.harness_attributes(spec["xres"], spec["yres"]))
 
         def run(self, n, var, uni, arena):
             ud, _ = b200lib.pack_userdata(helpers.testshade_userdata(n, var, uni, extra=self.spec["userdata"]))

@@ -224,7 +224,8 @@ def main():
             return ob.ShaderGroup(layers, conns, outs, options="fma=0,journal=1" + (
                 ",error_repeats=1" if "error_repeats=1" in spec["options"] else "") + (
                 ",colorspace=" + spec["colorspace"] if spec.get("colorspace") else ""), userdata=descs,
-                                  name=spec.get("groupname") or "group")
+                                  name=spec.get("groupname") or "group",
+                                  attributes=tsh.harness_attributes(spec["xres"], spec["yres"]))
         try:
             for s in specs:
                 if "echo" in s:
@@ -242,7 +243,8 @@ def main():
         class OracleRunner:
             def __init__(self, layers, conns, outs, spec):
                 self.g = oracle.OracleGroup(layers, conns, outs, name=spec.get("groupname") or "group", flags=(
-                    ('-DOSLO_COLORSPACE="%s"' % spec["colorspace"],) if spec.get("colorspace") else ()))
+                    ('-DOSLO_COLORSPACE="%s"' % spec["colorspace"],) if spec.get("colorspace") else ()),
+                    attributes=tsh.harness_attributes(spec["xres"], spec["yres"]))
                 self.spec = spec
 
             def run(self, n, var, uni, arena):
