@@ -358,6 +358,10 @@ def compare_image(got, ref, kind, failthresh=0.004, failpercent=0.02, hardfail=0
         g = np.round(np.clip(g, 0, 1) * 255.0) / 255.0
     elif kind == "uint16":
         g = np.round(np.clip(g, 0, 1) * 65535.0) / 65535.0
+    elif kind == "float":
+        with np.errstate(over="ignore"):
+            if np.array_equal(ref, ref.astype(np.float16).astype(np.float32)):
+                g = g.astype(np.float16).astype(np.float32)      # a half-float file (-od half): written through half
     d = np.abs(g - ref[..., :nch]).max(axis=2)
     bad = (d > failthresh).mean() * 100.0
     if bad > failpercent or d.max() > max(hardfail, failthresh):
