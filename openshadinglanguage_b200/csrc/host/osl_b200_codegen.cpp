@@ -11,7 +11,9 @@
 // planes); group data lives in registers.
 #include "../../../include/osl_b200.h"
 #include "osl_b200_group.h"
+#include "osl_b200_texture.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1135,8 +1137,10 @@ Gen::emit_op(const Opcode& op)
             unsupported("texture() with a file name that is not constant at compile time");
         size_t slot = 0;
         for (; slot < g.textures.size() && g.textures[slot] != fn.svals[0]; ++slot) {}
+        const bool texture_slot_used_before = slot < g.textures.size();
         if (slot == g.textures.size())
             g.textures.push_back(fn.svals[0]);
+        int missingcolor = -1, missingalpha = -1, alpha_out = -1;
         auto dpart = [&](int ai, const char* which) {
             return A(ai).has_derivs && !A(ai).is_const() ? "(" + R(op.args[ai]) + ")." + which : std::string("0.0f");
         };
@@ -1149,6 +1153,39 @@ Gen::emit_op(const Opcode& op)
             i = 8;
         } else {
             dd[0] = dpart(2, "dx"), dd[1] = dpart(3, "dx"), dd[2] = dpart(2, "dy"), dd[3] = dpart(3, "dy");
+        }
+        for (size_t k = i; k + 1 < op.args.size(); k += 2) {   // options that decide whether there is a lookup at all
+            const Symbol& key = A((int)k);
+            if (!key.const_value() || key.svals.empty())
+                continue;
+            if (key.svals[0] == "missingcolor")
+                missingcolor = (int)k + 1;
+            else if (key.svals[0] == "missingalpha")
+                missingalpha = (int)k + 1;
+            else if (key.svals[0] == "alpha")
+                alpha_out = (int)k + 1;
+        }
+        bool triple = A(0).type.is_triple();
+        if (missingcolor >= 0 || missingalpha >= 0) {
+            // "missingcolor" / "missingalpha": a file that cannot be had is not an error, the result is the
+            // missing colour (zero when only the alpha was given) and alpha the missing alpha
+            // (llvm_gen_texture_options, llvm_gen.cpp:2611-2640; osl_texture, optexture.cpp:283-300).
+            // Whether the image exists is settled here, when the group is compiled: images are
+            // registered or found on texturepath before that (Textures).
+            std::string terr;
+            if (!oslb200::texture_get(fn.svals[0], g.texturepath, terr)) {
+                if (!texture_slot_used_before)
+                    g.textures.pop_back();   // no table entry for an image that is not there
+                for (int c = 0; c < (triple ? 3 : 1); ++c)
+                    w("setc(" + R(op.args[0]) + ", " + std::to_string(c) + ", "
+                      + (missingcolor >= 0 ? comp(op.args[missingcolor], A(missingcolor).type.is_triple() ? c : 0, false)
+                                           : std::string("0.0f"))
+                      + ");");
+                if (alpha_out >= 0)
+                    w("assign(" + R(op.args[alpha_out]) + ", "
+                      + (missingalpha >= 0 ? comp(op.args[missingalpha], 0, false) : std::string("0.0f")) + ");");
+                return;
+            }
         }
         w("{");
         w("    TexOpt o_ = tex_default_options();");
@@ -1180,10 +1217,13 @@ Gen::emit_op(const Opcode& op)
                 w("    o_." + k + " = " + comp(op.args[vi], 0, false) + ";");
             else if (k == "interp")
                 w("    o_.interp = " + code_of(vi, false) + ";");
+            else if (k == "missingcolor" || k == "missingalpha" || k == "alpha")
+                ;   // handled above
             else
                 unsupported("texture option '" + k + "'");
         }
-        bool triple = A(0).type.is_triple();
+        if (alpha_out >= 0)
+            unsupported("texture option 'alpha' of an existing image");
         w("    V3 r_ = texture_lookup(osl_tex_[" + std::to_string(g.texture_base + (int)slot) + "], o_, "
           + comp(op.args[2], 0, false) + ", " + comp(op.args[3], 0, false) + ", " + dd[0] + ", " + dd[1] + ", " + dd[2]
           + ", " + dd[3] + ", " + (triple ? "3" : "1") + ");");

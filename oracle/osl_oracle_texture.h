@@ -21,6 +21,8 @@
 // Derivatives of the RESULT (dresultds/dt) are not produced (returned as zero).
 #pragma once
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -147,6 +149,12 @@ inline void tex_probe(const TexImage& im, const TexOpt& o, int interp, float s, 
         for (int c = 0; c < nc; ++c)
             acc[c] += (weight * wt[j]) * row[c];
     }
+}
+
+inline void unsupported_at_runtime(const char* what)
+{
+    fprintf(stderr, "oracle: %s is not restated\n", what);
+    abort();
 }
 
 // result[0..nchannels): the filtered lookup.  Returns false when the texture is unknown.

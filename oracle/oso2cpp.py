@@ -1272,6 +1272,7 @@ class Gen:
             dd = [dpart(s, "dx"), dpart(t, "dx"), dpart(s, "dy"), dpart(t, "dy")]
         self.w("{")
         self.w("    TexOpt o_;")
+        missing = {}
         while i < len(A):
             key, val = A[i], A[i + 1]
             i += 2
@@ -1288,12 +1289,31 @@ class Gen:
                 self.w("    o_.fill = %s;" % self.fl(val))
             elif k == "interp":
                 self.w("    o_.interp = tex_interp_code(%s);" % self.R(val))
+            elif k in ("missingcolor", "missingalpha", "alpha"):
+                missing[k] = val
             else:
                 raise NotImplementedError("texture option '%s'" % k)
         nch = 3 if d.t.triple else 1
         self.w("    float r_[4];")
-        self.w("    texture_lookup(%s, o_, %s, %s, %s, %s, %s, %s, %d, r_);" % (
+        self.w("    const bool found_ = texture_lookup(%s, o_, %s, %s, %s, %s, %s, %s, %d, r_);" % (
             self.R(fn), self.fl(s), self.fl(t), dd[0], dd[1], dd[2], dd[3], nch))
+        if missing:
+            # a file that cannot be had, with "missingcolor" / "missingalpha" given: no error, the result is
+            # the missing colour (zero when only the alpha was given) and alpha the missing alpha
+            # (llvm_gen_texture_options, llvm_gen.cpp:2611-2640; osl_texture, optexture.cpp:283-300)
+            mc = missing.get("missingcolor")
+            self.w("    if (!found_) {")
+            for c in range(nch):
+                self.w("        r_[%d] = %s;" % (c, self.comp(mc, c if mc.t.triple else 0, False) if mc is not None else "0.0f"))
+            if "alpha" in missing:
+                self.w("        assign(%s, %s);" % (self.R(missing["alpha"]), self.fl(missing["missingalpha"])
+                                                   if "missingalpha" in missing else "0.0f"))
+            self.w("    }")
+            if "alpha" in missing:
+                self.w('    else unsupported_at_runtime("texture option \'alpha\' of an existing image");')
+        elif False:
+            pass
+        self.w("    (void)found_;")
         self.w("    assign(%s, %s);" % (self.R(d), "V3(r_[0], r_[1], r_[2])" if nch == 3 else "r_[0]"))
         self.w("}")
 
