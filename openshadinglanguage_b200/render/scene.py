@@ -43,12 +43,14 @@ def parse_group_spec(text):
         elif tok[0] == "connect":
             (sl, sp), (dl, dp) = tok[1].split(".", 1), tok[2].split(".", 1)
             conns.append((sl, sp, dl, dp))
-        elif tok[0] in ("int",):
+        elif re.fullmatch(r"int(\[\d*\])?", tok[0]):
             pending[tok[1]] = [int(x) for x in tok[2:]]
-        elif tok[0] in ("float", "color", "point", "vector", "normal"):
+        elif re.fullmatch(r"(float|color|point|vector|normal|matrix)(\[\d*\])?", tok[0]):
             pending[tok[1]] = [float(x) for x in tok[2:]]
         elif tok[0] == "string":
             pending[tok[1]] = [" ".join(tok[2:]).strip('"')]
+        elif re.fullmatch(r"string\[\d*\]", tok[0]):
+            pending[tok[1]] = re.findall(r'"([^"]*)"', stmt)
         else:
             raise ValueError("bad group statement: %r" % stmt)
     return layers, conns

@@ -85,6 +85,7 @@ def harness_attributes(xres, yres):
 # grid is interpreted; flags that tune the reference's optimizer / JIT are accepted and ignored,
 # flags this harness does not implement are listed in spec["unsupported"].
 # ---------------------------------------------------------------------------------------------
+import os
 import re
 import shlex
 
@@ -92,7 +93,7 @@ _IGNORED_FLAGS = {"-t": 1, "--threads": 1, "-O0": 0, "-O1": 0, "-O2": 0, "--llvm
                   "--stats": 0, "--runstats": 0, "--debugnan": 0, "--debuguninit": 0, "--no-output-placement": 0,
                   "--shadeimage": 0, "--noshadeimage": 0, "--jbufferMB": 1,
                   "--warmup": 0, "--locale": 1, "--raytype_opt": 0, "--groupoutputs": 0, "--use_rs_bitcode": 0, "--texoptions": 1, "-texoptions": 1}
-_UNSUPPORTED_FLAGS = {"-v": 0, "--debug": 0, "--debug2": 0, "--group": 1, "-group": 1, "--archivegroup": 1,
+_UNSUPPORTED_FLAGS = {"-v": 0, "--debug": 0, "--debug2": 0, "--archivegroup": 1,
                       "--entry": 1, "--entryoutput": 1, "--oslquery": 0, "--print-groupdata": 0,
                       "--print-group-stats": 0, "--inbuffer": 0, "--expr": 1, "-expr": 1, "--profile": 0}
 
@@ -203,6 +204,20 @@ def parse_command(argstr):
             spec[base[2:]] = True
         elif base in ("--raytype", "-raytype"):
             spec["raytype"] = take(1)[0]
+        elif base in ("--group", "-group"):
+            # a serialized group: "param type name values ; shader name layer ; connect a.b c.d ;"
+            # (ShaderGroupBegin(name, usage, groupspec), oslexec.h:634-650); the text itself or a file holding it
+            from .render.scene import parse_group_spec
+            text = take(1)[0]
+            if os.path.exists(text):
+                text = open(text).read()
+            if re.search(r"\[\d+\]\s*(?:[;,]|$)|\.\w+\[\d+\]", text):
+                spec["unsupported"].append("-group with component connections")
+            else:
+                glayers, gconns = parse_group_spec(text)
+                for l in glayers:
+                    spec["layers"].append(dict(shader=l["shader"], name=l["name"], params=l["params"]))
+                spec["connections"] += [tuple(c) for c in gconns]
         elif base in ("--reparam", "-reparam"):
             # ShadingSystem::ReParameter after the first iteration (testshade.cpp:2245-2255)
             layer, name, value = take(3)

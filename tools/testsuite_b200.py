@@ -19,6 +19,7 @@ container, not on the GPU box.
 import json
 import os
 import re
+import shlex
 import sys
 import traceback
 
@@ -175,6 +176,14 @@ def main():
         if not any(t == "testshade" for t, _ in cmds) or set(tools_used) - {"testshade", "oslc", "echo"}:
             entry.update(status="harness", reason="uses " + ",".join(tools_used))
             continue
+        def inline_group_files(a):
+            def sub(m):
+                path = os.path.join(TS, d, m.group(2))
+                if not os.path.exists(path):
+                    path = os.path.join(TS, d, os.path.basename(m.group(2)))     # run.py may name a copy under data/
+                return m.group(1) + " " + shlex.quote(open(path).read()) if os.path.exists(path) else m.group(0)
+            return re.sub(r"(--?group)\s+(\S+\.oslgroup)", sub, a)
+        shade = [inline_group_files(a) for a in shade]
         entry["commands"] = shade
         # 2. compile the directory's shaders
         oso = {}
