@@ -82,7 +82,7 @@ class OOp:
         self.derivs, self.method = derivs, method
 
 
-TOK = re.compile(r'"(?:\\.|[^"\\])*"|%\w+\{[^}]*\}|%\w+|\S+')
+TOK = re.compile(r'"(?:\\.|[^"\\])*"|%\w+\{(?:"(?:\\.|[^"\\])*"|[^}"])*\}|%\w+|\S+')   # a %hint{...} may quote braces
 
 
 def _unescape(s):

@@ -1866,8 +1866,22 @@ class Compiler:
                     wr[a] = (min(lo, i), max(hi, i))
         out = ["OpenShadingLanguage 1.00", "# Compiled by mini_oslc (osl-b200 fixture compiler)",
                "# options: "]
+        def metahint(mt, mname, mval):
+            if getattr(mval, "kind", None) != "lit":
+                return ""
+            v = mval.value
+            if isinstance(v, str):
+                v = '"%s"' % v.replace("\\", "\\\\").replace('"', '\\"')
+            elif mt.base == "int":
+                v = str(int(v))
+            else:
+                v = fmt_float(v)
+            return " %%meta{%s,%s,%s}" % (mt.base, mname, v)
+
         hdr = "%s %s" % (sh.stype, sh.name)
-        out.append(hdr)
+        if getattr(self, "emit_metadata", False):
+            hdr += "\t" + "".join(metahint(*m) for m in (sh.meta or [])).strip()
+        out.append(hdr.rstrip())
 
         def fmtvals(s):
             if s.value is None:
@@ -1898,6 +1912,8 @@ class Compiler:
             for mt, mname, mval in (getattr(s, "meta", None) or []):
                 if mname == "lockgeom" and getattr(mval, "kind", None) == "lit":
                     line += " %%meta{int,lockgeom,%d}" % int(mval.value)
+                elif getattr(self, "emit_metadata", False):
+                    line += metahint(mt, mname, mval)
             return line
 
         for s in self.syms:
@@ -1931,8 +1947,10 @@ class Compiler:
         return "\n".join(out) + "\n"
 
 
-def compile_osl(path, include_dirs=(), defines=None, stdosl=None, source=None):
-    """Compile an .osl file (or `source` text) and return .oso text."""
+def compile_osl(path, include_dirs=(), defines=None, stdosl=None, source=None, metadata=False):
+    """Compile an .osl file (or `source` text) and return .oso text.  metadata: write every literal
+    [[ ... ]] entry of the shader and its parameters as %meta{type,name,value} hints (oslc does; the
+    fixtures only carry the one the runtime acts on, lockgeom)."""
     inc = list(include_dirs)
     pp = Preprocessor(inc, defines)
     text = ""
@@ -1953,6 +1971,7 @@ def compile_osl(path, include_dirs=(), defines=None, stdosl=None, source=None):
     if shader is None:
         raise CompileError("no shader found in %s" % path)
     c = Compiler()
+    c.emit_metadata = metadata
     for fn in funcs:
         c.declare_function(fn)
     return c.compile_shader(shader)

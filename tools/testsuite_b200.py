@@ -69,6 +69,48 @@ def commands_of(d):
     return seq, {k: ns[k] for k in ("outputs", "failthresh", "failpercent", "hardfail", "allowfailures")}
 
 
+def oslinfo_verbose(oso):
+    """What `oslinfo -v shader` prints (src/oslinfo/oslinfo.cpp:150-260) for the parameters and
+    metadata found in an .oso text (OSLQuery's view: name, type, default values, %meta hints)."""
+    lines = []
+    hint = re.compile(r'%meta\{(\w+),(\w+),("(?:\\.|[^"\\])*"|[^}]*)\}')
+
+    def metas(text):
+        out = []
+        for t, n, v in hint.findall(text):
+            out.append("\t\tmetadata: %s %s = %s" % (t, n, v))
+        return out
+    for ln in oso.split("\n"):
+        m = re.match(r"(shader|surface|displacement|volume)\s+(\S+)(.*)", ln)
+        if m and not lines:
+            lines.append('%s "%s"' % (m.group(1), m.group(2)))
+            lines += metas(m.group(3))
+            continue
+        m = re.match(r"(param|oparam)\t(\S+(?: color)?)\t(\S+)\t([^\t]*)\t(.*)", ln)
+        if not m:
+            continue
+        kind, typ, name, vals, rest = m.groups()
+        if "lockgeom" in rest and not [h for h in hint.findall(rest) if h[1] != "lockgeom"]:
+            rest = ""
+        lines.append('    "%s" "%s%s"' % (name, "output " if kind == "oparam" else "", typ))
+        base = typ.split("[")[0]
+        agg = {"color": 3, "point": 3, "vector": 3, "normal": 3, "matrix": 16}.get(base, 1)
+        if base == "string":
+            sv = re.findall(r'"((?:\\.|[^"\\])*)"', vals)
+            if "[" in typ:
+                lines.append("\t\tDefault value: [ " + " ".join('"%s"' % v for v in sv) + " ]")
+            else:
+                lines.append('\t\tDefault value: "%s"' % (sv[0] if sv else ""))
+        else:
+            toks = vals.split()
+            if base != "int":
+                toks = ["%g" % float(t) for t in toks]
+            body = " " + " ".join(toks)
+            lines.append("\t\tDefault value:" + (" [" + body + " ]" if ("[" in typ or agg > 1) else body))
+        lines += [l for l in metas(rest) if " lockgeom " not in l]
+    return "\n".join(lines)
+
+
 def read_exr_scanlines(path):
     """Minimal OpenEXR reader for what OpenCV refuses (single-channel / oddly named channels): scan-line files,
     NONE / ZIPS / ZIP compression, half or float channels.  -> float32 [h, w, nchannels], channels in file
@@ -172,8 +214,12 @@ def main():
             entry.update(status="harness", reason="run.py: %s" % e)
             continue
         tools_used = sorted({t for t, _ in cmds})
-        shade = [a if t == "testshade" else "\x00echo " + a for t, a in cmds if t in ("testshade", "echo")]
-        if not any(t == "testshade" for t, _ in cmds) or set(tools_used) - {"testshade", "oslc", "echo"}:
+        # `oslinfo -v shader` between the commands: emulated from the compiled .oso further down
+        info_ok = all(re.fullmatch(r"-v\s+\S+", a.strip()) for t, a in cmds if t == "oslinfo")
+        shade = [a if t == "testshade" else ("\x00oslinfo " + a.split()[-1] if t == "oslinfo" else "\x00echo " + a)
+                 for t, a in cmds if t in ("testshade", "echo", "oslinfo")]
+        if not any(t == "testshade" for t, _ in cmds) or not info_ok \
+                or set(tools_used) - {"testshade", "oslc", "echo", "oslinfo"}:
             entry.update(status="harness", reason="uses " + ",".join(tools_used))
             continue
         def inline_group_files(a):
@@ -191,7 +237,8 @@ def main():
         for f in sorted(os.listdir(os.path.join(TS, d))):
             if f.endswith(".osl"):
                 try:
-                    text = mini_oslc.compile_osl(os.path.join(TS, d, f), inc + [os.path.join(TS, d)])
+                    text = mini_oslc.compile_osl(os.path.join(TS, d, f), inc + [os.path.join(TS, d)],
+                                                 metadata="oslinfo" in tools_used)
                     # oslc names the .oso after the SHADER, not the source file (compassign-bool's
                     # varying_le.osl defines shader varying_lt and the other way round)
                     m = re.search(r"^(?:shader|surface|displacement|volume)\s+(\S+)", text, re.M)
@@ -200,6 +247,12 @@ def main():
                     failed = failed or "%s: %s" % (f, str(e).split("\n")[0][:200])
         specs = []
         try:
+            # oslinfo output is fixed once the shaders are compiled: from here on it is an echo line
+            shade = ["\x00echo " + oslinfo_verbose(oso[a[9:]]) if a.startswith("\x00oslinfo ") and a[9:] in oso else a
+                     for a in shade]
+            if any(a.startswith("\x00oslinfo ") for a in shade):
+                raise ValueError("oslinfo of a shader that did not compile")
+            entry["commands"] = shade
             specs = [dict(echo=a[6:], unsupported=[], layers=[]) if a.startswith("\x00echo ") else tsh.parse_command(a)
                      for a in shade]
         except Exception as e:
